@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — DQN transitions trained/sec (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+A "step" is one Agent.Learn over one sampled batch.  Default workload = the wide
+DQN config the metric's target is quoted on (BASELINE.json configs[2]: MLP
+128->512->512->18, batch 8192 per GPU, bf16 tcgen05 GEMMs, fp32 master weights);
+N > 1 = batch-sharded data parallelism (configs[3]), weak scaling: 8192 rows per
+GPU, one gradient all-reduce per step.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from gold_b200 import synth  # noqa: E402
+
+WORKLOADS = {
+    # name: (dims, per-GPU batch, replay rows per GPU, replicas per GPU (0 = single agent), default precision)
+    "wide": (synth.WIDE, 8192, 1 << 20, 0, "bf16"),
+    "cartpole4096": (synth.CARTPOLE, 4096, 1 << 20, 0, "fp32"),
+    "replicas": (synth.CARTPOLE, 20, 4096, 128, "fp32"),
+}
+TARGET_SYNC_EVERY = 100  # Hyperparameters.UpdateTargetSteps (agent.go:63)
+
+
+def algorithmic_work(dims, B, replicas=1):
+    """bytes/transition = 8D+13, parameter bytes/step = 28P,
+    FLOPs/transition = 6*P_w + 2*(P_w - D*H1)."""
+    D, H1, H2, A = dims
+    P = synth.nparams(dims)
+    Pw = D * H1 + H1 * H2 + H2 * A
+    bytes_step = B * (8 * D + 13) + 28 * P
+    flops_step = B * (6 * Pw + 2 * (Pw - D * H1))
+    return bytes_step * replicas, flops_step * replicas
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            j = json.load(open(path))
+            p.update({k: j[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in j})
+            p["source"] = "measured"
+        except Exception:
+            pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def pinned_array(G, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = G.lib().goldq_host_alloc(n)
+    if not p:
+        raise RuntimeError("goldq_host_alloc failed")
+    buf = (C.c_uint8 * n).from_address(p)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+
+# --------------------------------------------------------------------------- reference arm
+def cpu_learn_rate(dims, rows, steps, warmup, threads):
+    """Times the oracle port of Agent.Learn (reference structure: 2*rows single-row
+    Predicts + one FitBatch + multi-pass Adam) on `rows` sampled transitions."""
+    from oracle import binding as O
+    O.set_threads(threads)
+    P = synth.nparams(dims)
+    N = max(4 * rows, 4096)
+    data = synth.replay(dims, N)
+    th = synth.glorot_params(dims, synth.SEED_ONLINE)
+    tt = synth.glorot_params(dims, synth.SEED_TARGET)
+    m = np.zeros(P, np.float32); v = np.zeros(P, np.float32)
+    it = 0
+    times = []
+    for step in range(warmup + steps):
+        idx = synth.sample_indices(N, rows, step)
+        t0 = time.perf_counter()
+        s, a, r, s2, d = O.gather(dims[0], *data, idx)
+        out = O.learn(dims, rows, th, tt, m, v, it, s, a, r, s2, d, want_debug=False)
+        it = out["iter"]
+        if (step + 1) % TARGET_SYNC_EVERY == 0:
+            tt = th.copy()
+        dt = time.perf_counter() - t0
+        if step >= warmup:
+            times.append(dt)
+    O.set_threads(1)
+    return rows * len(times) / sum(times), float(np.mean(times))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import binding as O
+    dims, B, _, replicas, prec = WORKLOADS[args.workload]
+    threads = O.max_threads()
+    rows = args.cpu_rows or (512 if dims == synth.WIDE else 4096)
+    if replicas:
+        rows = 20
+    rate, sec = cpu_learn_rate(dims, rows, args.steps, min(args.warmup, 2), threads)
+    line = {
+        "impl": "reference", "metric": "dqn_transitions_trained_per_sec", "value": rate, "unit": "transitions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, dims, B, replicas, prec),
+        "cpu_baseline": {"value": rate, "unit": "transitions/s", "cores": threads, "kind": "port",
+                         "sample": f"{rows}-row learn steps of the same workload (oracle port of the Gorgonia "
+                                   f"learn step: per-event Predicts + FitBatch + multi-pass Adam), OpenMP over rows; "
+                                   f"the Go reference cannot run here (no Go toolchain)"},
+        "e2e": {"value": rate, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, dims, B, replicas, prec):
+    n = args.gpus
+    cfg = {"workload": {"wide": "wide DQN MLP 128->512->512->18, learn step (BASELINE configs[2]; N>1: configs[3] data-parallel)",
+                        "cartpole4096": "CartPole DQN 4->24->24->2 learn step, batch 4096 (BASELINE configs[1])",
+                        "replicas": "independent CartPole DQN replicas, batch 20 each (BASELINE configs[4])"}[args.workload],
+           "dims": list(dims), "batch_per_gpu": B, "global_batch": B * n * max(replicas, 1),
+           "replay_rows_per_gpu": WORKLOADS[args.workload][2], "precision": prec,
+           "parallelism": (f"dp{n}" if not replicas else f"replicas{replicas}x{n}"),
+           "target_sync_every": TARGET_SYNC_EVERY,
+           "l2": "inputs larger than L2: rows are drawn at random from a replay ring far above 126 MB"
+                 if not replicas and dims == synth.WIDE else "replay rows drawn at random each step; weights stay L2-resident by design"}
+    return cfg
+
+
+# --------------------------------------------------------------------------- own arm
+def build_handle(G, args, dims, B, N, replicas, prec, rank, world, local_rank):
+    kw = dict(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3], batch_size=B,
+              replay_capacity=N, device=local_rank,
+              precision=G.PREC_BF16 if prec == "bf16" else G.PREC_FP32)
+    if replicas:
+        kw["n_replicas"] = replicas
+    else:
+        kw["global_batch"] = B * world
+    h = G.Handle(**kw)
+    R = max(replicas, 1)
+    th = np.concatenate([synth.glorot_params(dims, synth.SEED_ONLINE + 1000 * r) for r in range(R)])
+    tt = np.concatenate([synth.glorot_params(dims, synth.SEED_TARGET + 1000 * r) for r in range(R)])
+    h.set_params(G.NET_ONLINE, th)
+    h.set_params(G.NET_TARGET, tt)
+    # synthetic replay, pushed in chunks (host RAM stays bounded)
+    chunk = min(N, 1 << 16)
+    for c in range(0, N, chunk):
+        n = min(chunk, N - c)
+        parts = [synth.replay(dims, n, seed=synth.SEED_DATA + 7919 * (c // chunk) + 104729 * r + 15485863 * rank)
+                 for r in range(R)]
+        h.replay_push(*[np.concatenate([p[k] for p in parts]) for k in range(5)])
+    h.sync()
+    return h
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+
+    from gold_b200 import _capi as G
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dims, B, N, replicas, prec = WORKLOADS[args.workload]
+    if args.precision:
+        prec = args.precision
+    if args.replay_rows:
+        N = args.replay_rows
+    h = build_handle(G, args, dims, B, N, replicas, prec, rank, world, local_rank)
+    if world > 1 and not replicas:
+        uid = [G.Handle.dp_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.dp_init(uid[0], rank, world)
+    R = max(replicas, 1)
+    rows_per_step_gpu = B * R
+    K, W = args.steps, max(args.warmup, 3)
+
+    def step_resident(i):
+        h.learn(None, seed=1_000_003 * (rank + 1) + i)     # device sampler: nothing crosses PCIe
+        if (i + 1) % TARGET_SYNC_EVERY == 0:
+            h.sync_target()
+
+    # ---------------- value: inputs resident in HBM --------------------------------
+    for i in range(W):
+        step_resident(i)
+    h.sync()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    l0 = h.launch_count()
+    h.timer_start()
+    for i in range(K):
+        step_resident(W + i)
+    ms = h.timer_stop()
+    barrier()
+    launches = h.launch_count() - l0
+    ms = max_over_ranks(ms)
+    clocks = sampler.stop() if sampler else None
+    value = rows_per_step_gpu * world * K / (ms * 1e-3)
+
+    # ---------------- e2e: host buffers through the public C ABI ---------------------
+    # every step: B fresh transitions pushed from pinned host memory (H2D), the sampled
+    # index list from host memory (H2D), loss read back (D2H + sync).
+    D = dims[0]
+    bufs = []
+    for k in range(2):
+        arrs = [pinned_array(G, (R * B, D), np.float32), pinned_array(G, (R * B,), np.int32),
+                pinned_array(G, (R * B,), np.float32), pinned_array(G, (R * B, D), np.float32),
+                pinned_array(G, (R * B,), np.uint8)]
+        parts = [synth.replay(dims, B, seed=4242 + k + 31 * r) for r in range(R)]
+        fresh = [np.concatenate([p[j] for p in parts]) for j in range(5)]
+        for (a, _), src in zip(arrs, (fresh[0], fresh[1], fresh[2], fresh[3], fresh[4])):
+            a[...] = src.reshape(a.shape)
+        bufs.append(arrs)
+    idx_host = [np.stack([synth.sample_indices(N, B, 7 * i + r) for r in range(R)]).astype(np.int32)
+                for i in range(8)]
+    h2d = R * B * (8 * D + 9) + R * B * 4
+    d2h = 4 * R
+
+    def step_e2e(i):
+        arrs = bufs[i & 1]
+        h.replay_push_raw(B, *[p for _, p in arrs])
+        ix = idx_host[i % len(idx_host)]
+        h.learn_raw(ix.ctypes.data)
+        loss = h.last_loss()                                  # D2H + stream sync
+        if (i + 1) % TARGET_SYNC_EVERY == 0:
+            h.sync_target()
+        return loss
+
+    Ke = max(3, min(K, args.e2e_steps))
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        last = step_e2e(i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = rows_per_step_gpu * world * Ke / e2e_s
+
+    # ---------------- roofline of the step ------------------------------------------
+    pk = peaks()
+    bytes_step, flops_step = algorithmic_work(dims, B, R)
+    step_s = ms * 1e-3 / K
+    if dims == synth.WIDE:
+        peak = pk["bf16_tflops_sustained"] if prec == "bf16" else pk["bf16_tflops_sustained"]
+        ach = flops_step / step_s / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "peak_source": pk["source"] + " (sustained: timed inside a long step)",
+                "kernel": "whole learn step", "flops_per_step": flops_step}
+    else:
+        ach = bytes_step / step_s / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "traffic": None, "peak_source": pk["source"], "kernel": "narrow_learn_kernel (whole step, one launch)",
+                "bytes_per_step": bytes_step}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rows = args.cpu_rows or (256 if dims == synth.WIDE else (20 if replicas else 4096))
+        reps = 3 if dims == synth.WIDE else 20
+        rate, sec = cpu_learn_rate(dims, rows, reps, 1, 1)
+        cpu = {"value": rate, "unit": "transitions/s", "cores": 1, "kind": "port",
+               "sample": f"{reps} learn steps of {rows} rows of the same workload, single thread (the Gorgonia VM is "
+                         f"single-threaded); oracle port, the Go reference cannot run here"}
+
+    if rank == 0:
+        line = {
+            "metric": "dqn_transitions_trained_per_sec", "value": value, "unit": "transitions/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32",
+            "data": "synthetic", "config": workload_config(args, dims, B, replicas, prec),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "what": "per step: goldq_replay_push of a fresh batch from pinned host memory + goldq_learn with "
+                            "host indices + goldq_last_loss readback; host wall clock, max over ranks"},
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "path": {1: "generic", 2: "narrow", 3: "wide"}[h.path], "last_loss": [float(x) for x in last[:4]],
+        }
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="wide", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--replay-rows", type=int, default=0)
+    ap.add_argument("--cpu-rows", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,301 @@
+"""ctypes binding of include/goldq.h (libgoldq.so).
+
+There is deliberately no fallback: if the CUDA library is missing or a call
+fails, an exception is raised.  Nothing here imports oracle/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgoldq.so")
+
+OK, EINVAL, ECUDA, ENOTREADY, EUNSUPPORTED, ENCCL = 0, -1, -2, -3, -4, -5
+NET_ONLINE, NET_TARGET = 0, 1
+LOSS_MSE = 0
+PREC_FP32, PREC_BF16 = 0, 1
+PATH_AUTO, PATH_GENERIC, PATH_NARROW, PATH_WIDE = 0, 1, 2, 3
+DBG_Q_ONLINE, DBG_Q_TARGET, DBG_TD, DBG_GRADS, DBG_INDICES, DBG_BATCH_S, DBG_BATCH_A = range(7)
+ABI_VERSION = 1
+
+# every symbol include/goldq.h declares (tests/test_abi.py checks header <-> list <-> .so)
+SYMBOLS = [
+    "goldq_default_config", "goldq_create", "goldq_destroy", "goldq_last_error",
+    "goldq_abi_version", "goldq_param_count", "goldq_selected_path", "goldq_set_params",
+    "goldq_get_params", "goldq_set_adam_state", "goldq_get_adam_state", "goldq_replay_push",
+    "goldq_replay_len", "goldq_replay_push_wait", "goldq_host_alloc", "goldq_host_free",
+    "goldq_learn", "goldq_learn_device_indices", "goldq_sampler_indices", "goldq_sync_target",
+    "goldq_last_loss", "goldq_predict", "goldq_greedy_action", "goldq_fit_batch",
+    "goldq_dp_unique_id", "goldq_dp_init", "goldq_sync", "goldq_stream", "goldq_launch_count",
+    "goldq_debug_enable", "goldq_debug_fetch", "goldq_timer_start", "goldq_timer_stop",
+]
+
+
+class GoldqConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("obs_dim", C.c_int32), ("hidden1", C.c_int32),
+        ("hidden2", C.c_int32), ("n_actions", C.c_int32), ("batch_size", C.c_int32),
+        ("global_batch", C.c_int32), ("replay_capacity", C.c_int64), ("gamma", C.c_float),
+        ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+        ("loss", C.c_int32), ("precision", C.c_int32), ("path", C.c_int32), ("device", C.c_int32),
+        ("n_replicas", C.c_int32), ("reserved0", C.c_int32), ("stream", C.c_void_p),
+    ]
+
+
+class GoldqError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"goldq error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libgoldq.so (raises if it has not been built: no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C gold_b200/csrc).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    fp, ip, up = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+    sig = {
+        "goldq_default_config": (C.c_int, [C.POINTER(GoldqConfig)]),
+        "goldq_create": (vp, [C.POINTER(GoldqConfig)]),
+        "goldq_destroy": (None, [vp]),
+        "goldq_last_error": (C.c_char_p, [vp]),
+        "goldq_abi_version": (C.c_int, []),
+        "goldq_param_count": (i64, [vp]),
+        "goldq_selected_path": (C.c_int, [vp]),
+        "goldq_set_params": (C.c_int, [vp, C.c_int, fp]),
+        "goldq_get_params": (C.c_int, [vp, C.c_int, fp]),
+        "goldq_set_adam_state": (C.c_int, [vp, fp, fp, i64]),
+        "goldq_get_adam_state": (C.c_int, [vp, fp, fp, C.POINTER(i64)]),
+        "goldq_replay_push": (C.c_int, [vp, i64, vp, vp, vp, vp, vp]),
+        "goldq_replay_len": (i64, [vp]),
+        "goldq_replay_push_wait": (C.c_int, [vp]),
+        "goldq_host_alloc": (vp, [i64]),
+        "goldq_host_free": (None, [vp]),
+        "goldq_learn": (C.c_int, [vp, vp, u64]),
+        "goldq_learn_device_indices": (C.c_int, [vp, vp]),
+        "goldq_sampler_indices": (C.c_int, [i64, i32, u64, i32, ip]),
+        "goldq_sync_target": (C.c_int, [vp]),
+        "goldq_last_loss": (C.c_int, [vp, fp]),
+        "goldq_predict": (C.c_int, [vp, C.c_int, C.c_int, i64, fp, fp]),
+        "goldq_greedy_action": (C.c_int, [vp, C.c_int, i64, fp, ip]),
+        "goldq_fit_batch": (C.c_int, [vp, i64, fp, fp]),
+        "goldq_dp_unique_id": (C.c_int, [up]),
+        "goldq_dp_init": (C.c_int, [vp, up, C.c_int, C.c_int]),
+        "goldq_sync": (C.c_int, [vp]),
+        "goldq_stream": (vp, [vp]),
+        "goldq_launch_count": (i64, [vp]),
+        "goldq_debug_enable": (C.c_int, [vp, C.c_int]),
+        "goldq_debug_fetch": (C.c_int, [vp, C.c_int, vp, i64]),
+        "goldq_timer_start": (C.c_int, [vp]),
+        "goldq_timer_stop": (C.c_int, [vp, fp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if L.goldq_abi_version() != ABI_VERSION:
+        raise ImportError("libgoldq.so ABI version mismatch: rebuild")
+    _lib = L
+    return L
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def default_config(**kw):
+    cfg = GoldqConfig()
+    lib().goldq_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise TypeError(f"unknown config field {k}")
+        setattr(cfg, k, v)
+    return cfg
+
+
+def sampler_indices(length, batch, seed, replica=0):
+    out = np.empty(batch, np.int32)
+    rc = lib().goldq_sampler_indices(length, batch, seed, replica, out.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc:
+        raise GoldqError(rc, "sampler_indices: bad argument")
+    return out
+
+
+class Handle:
+    """Thin owner of a goldq_t*; one per agent (or replica group) per GPU."""
+
+    def __init__(self, cfg=None, **kw):
+        self._L = lib()
+        self.cfg = cfg if cfg is not None else default_config(**kw)
+        self._h = self._L.goldq_create(C.byref(self.cfg))
+        if not self._h:
+            msg = self._L.goldq_last_error(None).decode()
+            raise GoldqError(EINVAL, msg)
+        self.P = int(self._L.goldq_param_count(self._h))
+        self.R = int(self.cfg.n_replicas)
+        self.B = int(self.cfg.batch_size)
+        self.D = int(self.cfg.obs_dim)
+        self.A = int(self.cfg.n_actions)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.goldq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GoldqError(rc, self._L.goldq_last_error(self._h).decode())
+
+    @property
+    def path(self):
+        return int(self._L.goldq_selected_path(self._h))
+
+    # parameters / solver state -------------------------------------------
+    def set_params(self, net, theta):
+        theta = np.ascontiguousarray(theta, np.float32)
+        assert theta.size == self.R * self.P, (theta.size, self.R, self.P)
+        self._ck(self._L.goldq_set_params(self._h, net, _f(theta)))
+
+    def get_params(self, net):
+        out = np.empty(self.R * self.P, np.float32)
+        self._ck(self._L.goldq_get_params(self._h, net, _f(out)))
+        return out
+
+    def set_adam_state(self, m, v, it):
+        m = np.ascontiguousarray(m, np.float32)
+        v = np.ascontiguousarray(v, np.float32)
+        assert m.size == self.R * self.P and v.size == self.R * self.P
+        self._ck(self._L.goldq_set_adam_state(self._h, _f(m), _f(v), it))
+
+    def get_adam_state(self):
+        m = np.empty(self.R * self.P, np.float32)
+        v = np.empty(self.R * self.P, np.float32)
+        it = C.c_int64(0)
+        self._ck(self._L.goldq_get_adam_state(self._h, _f(m), _f(v), C.byref(it)))
+        return m, v, it.value
+
+    # replay ---------------------------------------------------------------
+    def replay_push(self, s, a, r, s2, done):
+        s = np.ascontiguousarray(s, np.float32)
+        s2 = np.ascontiguousarray(s2, np.float32)
+        a = np.ascontiguousarray(a, np.int32)
+        r = np.ascontiguousarray(r, np.float32)
+        done = np.ascontiguousarray(done, np.uint8)
+        n = a.size // self.R
+        assert s.size == self.R * n * self.D and s2.size == s.size and r.size == a.size == done.size
+        self._ck(self._L.goldq_replay_push(self._h, n, s.ctypes.data, a.ctypes.data, r.ctypes.data,
+                                           s2.ctypes.data, done.ctypes.data))
+
+    def replay_push_raw(self, n, s_ptr, a_ptr, r_ptr, s2_ptr, done_ptr):
+        self._ck(self._L.goldq_replay_push(self._h, n, s_ptr, a_ptr, r_ptr, s2_ptr, done_ptr))
+
+    def replay_push_wait(self):
+        self._ck(self._L.goldq_replay_push_wait(self._h))
+
+    def replay_len(self):
+        return int(self._L.goldq_replay_len(self._h))
+
+    # learn ------------------------------------------------------------------
+    def learn(self, idx=None, seed=0):
+        if idx is None:
+            self._ck(self._L.goldq_learn(self._h, None, seed))
+        else:
+            idx = np.ascontiguousarray(idx, np.int32)
+            assert idx.size == self.R * self.B
+            self._ck(self._L.goldq_learn(self._h, idx.ctypes.data, seed))
+
+    def learn_raw(self, idx_host_ptr, seed=0):
+        self._ck(self._L.goldq_learn(self._h, idx_host_ptr, seed))
+
+    def learn_device_indices(self, dev_ptr):
+        self._ck(self._L.goldq_learn_device_indices(self._h, dev_ptr))
+
+    def sync_target(self):
+        self._ck(self._L.goldq_sync_target(self._h))
+
+    def last_loss(self):
+        out = np.empty(self.R, np.float32)
+        self._ck(self._L.goldq_last_loss(self._h, _f(out)))
+        return out
+
+    # model surface ----------------------------------------------------------
+    def predict(self, net, x, replica=0):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, self.D)
+        q = np.empty((x.shape[0], self.A), np.float32)
+        self._ck(self._L.goldq_predict(self._h, net, replica, x.shape[0], _f(x), _f(q)))
+        return q
+
+    def greedy_action(self, x, replica=0):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, self.D)
+        a = np.empty(x.shape[0], np.int32)
+        self._ck(self._L.goldq_greedy_action(self._h, replica, x.shape[0], _f(x),
+                                             a.ctypes.data_as(C.POINTER(C.c_int32))))
+        return a
+
+    def fit_batch(self, x, y):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, self.D)
+        y = np.ascontiguousarray(y, np.float32).reshape(-1, self.A)
+        if x.shape[0] != y.shape[0]:
+            raise GoldqError(EINVAL, "fit_batch: x and y row counts differ")
+        self._ck(self._L.goldq_fit_batch(self._h, x.shape[0], _f(x), _f(y)))
+
+    # data parallel ----------------------------------------------------------
+    @staticmethod
+    def dp_unique_id():
+        buf = (C.c_uint8 * 128)()
+        rc = lib().goldq_dp_unique_id(buf)
+        if rc:
+            raise GoldqError(rc, lib().goldq_last_error(None).decode())
+        return bytes(buf)
+
+    def dp_init(self, uid, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(self._L.goldq_dp_init(self._h, buf, rank, world))
+
+    # plumbing ---------------------------------------------------------------
+    def sync(self):
+        self._ck(self._L.goldq_sync(self._h))
+
+    def stream(self):
+        return self._L.goldq_stream(self._h)
+
+    def launch_count(self):
+        return int(self._L.goldq_launch_count(self._h))
+
+    def debug_enable(self, on=True):
+        self._ck(self._L.goldq_debug_enable(self._h, 1 if on else 0))
+
+    def debug_fetch(self, what):
+        RB = self.R * self.B
+        shape, dt = {
+            DBG_Q_ONLINE: ((RB, self.A), np.float32), DBG_Q_TARGET: ((RB, self.A), np.float32),
+            DBG_TD: ((RB,), np.float32), DBG_GRADS: ((self.R * self.P,), np.float32),
+            DBG_INDICES: ((RB,), np.int32), DBG_BATCH_S: ((RB, self.D), np.float32),
+            DBG_BATCH_A: ((RB,), np.int32),
+        }[what]
+        out = np.empty(shape, dt)
+        self._ck(self._L.goldq_debug_fetch(self._h, what, out.ctypes.data, out.nbytes))
+        return out
+
+    def timer_start(self):
+        self._ck(self._L.goldq_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._ck(self._L.goldq_timer_stop(self._h, C.byref(ms)))
+        return ms.value

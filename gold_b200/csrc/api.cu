@@ -1,0 +1,952 @@
+// api.cu — C ABI (include/goldq.h) and host runtime of libgoldq.
+//
+// Owns the device state of one deepq agent (or n_replicas of them): online and
+// target parameters, Adam moments, the SoA replay ring, per-step scratch; one
+// CUDA stream per handle.  No CPU compute path exists here by design: every
+// entry point that computes launches CUDA kernels or fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "sampler.cuh"
+#include "wide.cuh"
+
+using namespace gq;
+
+// ---------------------------------------------------------------------------
+// NCCL, resolved at run time so that libgoldq.so loads without it (and shares
+// the copy torch already loaded when it runs inside a torch process).
+// ---------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string &err)
+    {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { err = std::string("dlopen libnccl failed: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
+            err = "libnccl is missing required symbols";
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+std::string g_create_error;
+}  // namespace
+
+struct goldq {
+    goldq_config_t cfg;
+    Dims dims;
+    Offsets off;
+    int P = 0, R = 1, B = 0, Bglobal = 0;
+    int dev = 0, sm_count = 148;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    int path = GOLDQ_PATH_GENERIC;
+
+    float *theta = nullptr, *theta_t = nullptr, *m = nullptr, *v = nullptr;  // [R][P]
+    int64_t iter = 0;
+    Replay rp{};
+    int32_t *d_idx = nullptr;  // [R][B]
+
+    // push staging (device) + scatter
+    float *stg_s = nullptr, *stg_s2 = nullptr, *stg_r = nullptr;
+    int32_t *stg_a = nullptr;
+    uint8_t *stg_done = nullptr;
+    int64_t stg_cap = 0;
+    cudaEvent_t ev_push = nullptr;
+
+    // reduced gradient + loss: [R][P+1]; loss per replica
+    float *flat = nullptr, *loss = nullptr;
+    // narrow path
+    float *partial = nullptr;
+    unsigned int *ticket = nullptr;
+    int n_ctas = 1, n_warps = 1;
+    // generic path scratch (rows = gen_rows)
+    int gen_rows = 0;
+    float *bs = nullptr, *bs2 = nullptr, *br = nullptr;
+    int32_t *ba = nullptr;
+    uint8_t *bdone = nullptr;
+    float *h1 = nullptr, *h2 = nullptr, *q = nullptr, *t1 = nullptr, *t2 = nullptr, *qt = nullptr;
+    float *td = nullptr, *dq = nullptr, *dh2 = nullptr, *dh1 = nullptr, *ylab = nullptr;
+    uint8_t *mk1 = nullptr, *mk2 = nullptr;
+    float *gslice = nullptr, *loss_part = nullptr;
+    int nsplit = 1;
+    // predict scratch
+    int64_t pred_rows = 0;
+    float *px = nullptr, *ph1 = nullptr, *ph2 = nullptr, *pq = nullptr;
+    int32_t *pact = nullptr;
+    // wide (tcgen05) path
+    WideState *wide = nullptr;
+
+    bool debug = false;
+    float *dbg_q = nullptr, *dbg_qt = nullptr, *dbg_td = nullptr;
+    int32_t *dbg_idx = nullptr;
+
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(goldq_t *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CK(h, expr)                                                                      \
+    do {                                                                                 \
+        cudaError_t e_ = (expr);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(h, GOLDQ_ECUDA,                                                  \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));             \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t n)
+{
+    if (n == 0) n = 1;
+    return cudaMalloc((void **)p, n * sizeof(T));
+}
+
+int check_launch(goldq_t *h, const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, GOLDQ_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return GOLDQ_OK;
+}
+
+AdamConsts adam_consts(const goldq_config_t &c, int64_t iter)
+{
+    // vendor/gorgonia.org/gorgonia/solvers.go:446-447 (float64), :490-503 (casts)
+    double correction1 = 1.0 - pow(c.beta1, (double)iter);
+    double correction2 = 1.0 - pow(c.beta2, (double)iter);
+    AdamConsts a;
+    a.beta1 = (float)c.beta1;
+    a.beta2 = (float)c.beta2;
+    a.omb1 = 1.0f - (float)c.beta1;
+    a.omb2 = 1.0f - (float)c.beta2;
+    a.eps = (float)c.eps;
+    a.neg_eta = (float)(-c.lr);
+    a.c1 = 1.0f / (float)correction1;
+    a.c2 = 1.0f / (float)correction2;
+    return a;
+}
+
+StepScalars step_scalars(const goldq_t *h, int rows_global)
+{
+    StepScalars s;
+    s.gamma = h->cfg.gamma;
+    s.count = (float)((int64_t)rows_global * h->dims.A);
+    s.inv_count = 1.0f / s.count;
+    return s;
+}
+
+int ensure_generic(goldq_t *h, int rows)
+{
+    if (h->gen_rows >= rows) return GOLDQ_OK;
+    const Dims &d = h->dims;
+    float **fp[] = {&h->bs, &h->bs2, &h->br, &h->h1, &h->h2, &h->q, &h->t1, &h->t2, &h->qt,
+                    &h->td, &h->dq, &h->dh2, &h->dh1, &h->ylab, &h->gslice, &h->loss_part};
+    for (auto p : fp) { if (*p) cudaFree(*p); *p = nullptr; }
+    if (h->ba) cudaFree(h->ba);
+    if (h->bdone) cudaFree(h->bdone);
+    if (h->mk1) cudaFree(h->mk1);
+    if (h->mk2) cudaFree(h->mk2);
+    size_t n = rows;
+    CK(h, dalloc(&h->bs, n * d.D));
+    CK(h, dalloc(&h->bs2, n * d.D));
+    CK(h, dalloc(&h->br, n));
+    CK(h, dalloc(&h->ba, n));
+    CK(h, dalloc(&h->bdone, n));
+    CK(h, dalloc(&h->h1, n * d.H1));
+    CK(h, dalloc(&h->h2, n * d.H2));
+    CK(h, dalloc(&h->q, n * d.A));
+    CK(h, dalloc(&h->t1, n * d.H1));
+    CK(h, dalloc(&h->t2, n * d.H2));
+    CK(h, dalloc(&h->qt, n * d.A));
+    CK(h, dalloc(&h->td, n));
+    CK(h, dalloc(&h->dq, n * d.A));
+    CK(h, dalloc(&h->dh2, n * d.H2));
+    CK(h, dalloc(&h->dh1, n * d.H1));
+    CK(h, dalloc(&h->ylab, n * d.A));
+    CK(h, dalloc(&h->mk1, n * d.H1));
+    CK(h, dalloc(&h->mk2, n * d.H2));
+    h->nsplit = rows / 512;
+    if (h->nsplit < 1) h->nsplit = 1;
+    if (h->nsplit > 32) h->nsplit = 32;
+    CK(h, dalloc(&h->gslice, (size_t)h->nsplit * h->P));
+    CK(h, dalloc(&h->loss_part, (size_t)(rows * d.A + 255) / 256 + 1));
+    h->gen_rows = rows;
+    return GOLDQ_OK;
+}
+
+// forward of one net over n rows with the generic kernels
+void generic_forward(goldq_t *h, const float *theta, const float *x, int n, float *h1, uint8_t *mk1,
+                     float *h2, uint8_t *mk2, float *q)
+{
+    const Dims &d = h->dims;
+    const Offsets &o = h->off;
+    launch_fc_forward(x, theta + o.w1, theta + o.b1, h1, mk1, n, d.D, d.H1, true, h->st);
+    launch_fc_forward(h1, theta + o.w2, theta + o.b2, h2, mk2, n, d.H1, d.H2, true, h->st);
+    launch_fc_forward(h2, theta + o.w3, theta + o.b3, q, nullptr, n, d.H2, d.A, false, h->st);
+    h->launches += 3;
+}
+
+// backward from dq through the online net (activations in h->h1/h2/mk1/mk2, input x)
+void generic_backward(goldq_t *h, const float *x, int n)
+{
+    const Dims &d = h->dims;
+    const Offsets &o = h->off;
+    const float *th = h->theta;
+    launch_grad_w(h->h2, h->dq, n, d.H2, d.A, h->gslice, h->P, h->nsplit, o.w3, o.b3, h->st);
+    launch_grad_x(h->dq, th + o.w3, h->mk2, h->dh2, n, d.H2, d.A, h->st);
+    launch_grad_w(h->h1, h->dh2, n, d.H1, d.H2, h->gslice, h->P, h->nsplit, o.w2, o.b2, h->st);
+    launch_grad_x(h->dh2, th + o.w2, h->mk1, h->dh1, n, d.H1, d.H2, h->st);
+    launch_grad_w(x, h->dh1, n, d.D, d.H1, h->gslice, h->P, h->nsplit, o.w1, o.b1, h->st);
+    h->launches += 5;
+}
+
+int allreduce_flat(goldq_t *h)
+{
+    if (h->world <= 1) return GOLDQ_OK;
+    ncclResult_t r = g_nccl.AllReduce(h->flat, h->flat, (size_t)h->P + 1, ncclFloat, ncclSum,
+                                      h->comm, h->st);
+    if (r != ncclSuccess)
+        return fail(h, GOLDQ_ENCCL, std::string("ncclAllReduce: ") +
+                                        (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    h->launches += 1;
+    return GOLDQ_OK;
+}
+
+int learn_generic(goldq_t *h, const int32_t *idx_dev)
+{
+    int rc = ensure_generic(h, h->B);
+    if (rc) return rc;
+    const Dims &d = h->dims;
+    launch_gather(h->rp, d.D, idx_dev, h->B, h->bs, h->bs2, h->ba, h->br, h->bdone, h->st);
+    h->launches += 1;
+    generic_forward(h, h->theta, h->bs, h->B, h->h1, h->mk1, h->h2, h->mk2, h->q);
+    generic_forward(h, h->theta_t, h->bs2, h->B, h->t1, nullptr, h->t2, nullptr, h->qt);
+    int nlp = 0;
+    StepScalars sc = step_scalars(h, h->Bglobal);
+    launch_td(h->q, h->qt, h->ba, h->br, h->bdone, h->B, d.A, sc, h->td, h->dq, h->loss_part, &nlp,
+              h->st);
+    h->launches += 1;
+    generic_backward(h, h->bs, h->B);
+    launch_reduce_slices(h->gslice, h->P, h->nsplit, h->P, h->loss_part, nlp, sc.count, h->flat,
+                         h->st);
+    h->launches += 1;
+    rc = allreduce_flat(h);
+    if (rc) return rc;
+    h->iter += 1;
+    launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), h->st);
+    h->launches += 1;
+    CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+    return check_launch(h, "learn_generic");
+}
+
+int learn_narrow(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
+{
+    NarrowArgs a{};
+    a.dims = h->dims;
+    a.rp = h->rp;
+    a.idx = idx_dev;
+    a.seed = seed;
+    a.B = h->B;
+    a.replicas = h->R;
+    a.theta = h->theta;
+    a.theta_t = h->theta_t;
+    a.m = h->m;
+    a.v = h->v;
+    a.partial = h->partial;
+    a.ticket = h->ticket;
+    a.flat = h->flat;
+    a.loss = h->loss;
+    a.fuse_adam = h->world <= 1 ? 1 : 0;
+    a.sc = step_scalars(h, h->Bglobal);
+    h->iter += 1;
+    a.adam = adam_consts(h->cfg, h->iter);
+    if (h->debug) {
+        a.dbg_q = h->dbg_q;
+        a.dbg_qt = h->dbg_qt;
+        a.dbg_td = h->dbg_td;
+        a.dbg_idx = h->dbg_idx;
+    }
+    a.ctas_per_replica = h->n_ctas;
+    a.warps_per_cta = h->n_warps;
+    launch_narrow_learn(a, h->st);
+    h->launches += 1;
+    int rc = check_launch(h, "narrow_learn_kernel");
+    if (rc) return rc;
+    if (h->world > 1) {
+        rc = allreduce_flat(h);
+        if (rc) return rc;
+        launch_adam(h->theta, h->flat, h->m, h->v, h->P, a.adam, h->st);
+        h->launches += 1;
+        CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice,
+                              h->st));
+    }
+    return check_launch(h, "learn_narrow");
+}
+
+int learn_wide(goldq_t *h, const int32_t *idx_dev)
+{
+    WideStep ws{};
+    ws.rp = h->rp;
+    ws.idx = idx_dev;
+    ws.B = h->B;
+    ws.theta = h->theta;
+    ws.theta_t = h->theta_t;
+    ws.flat = h->flat;
+    ws.sc = step_scalars(h, h->Bglobal);
+    std::string err;
+    int n = wide_forward_backward(h->wide, ws, h->st, err);
+    if (n < 0) return fail(h, GOLDQ_ECUDA, err);
+    h->launches += n;
+    int rc = allreduce_flat(h);
+    if (rc) return rc;
+    h->iter += 1;
+    launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), h->st);
+    h->launches += 1;
+    n = wide_after_update(h->wide, h->theta, h->st, err);   // refresh the bf16 shadow of the online net
+    if (n < 0) return fail(h, GOLDQ_ECUDA, err);
+    h->launches += n;
+    CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+    return check_launch(h, "learn_wide");
+}
+
+int run_learn(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
+{
+    if (h->rp.len < h->B) return fail(h, GOLDQ_ENOTREADY, "replay shorter than batch");
+    if (h->path == GOLDQ_PATH_NARROW) return learn_narrow(h, idx_dev, seed);
+    if (!idx_dev) {
+        launch_sample_indices(h->d_idx, h->B, h->rp.len, seed, h->R, h->st);
+        h->launches += 1;
+        idx_dev = h->d_idx;
+    }
+    if (h->path == GOLDQ_PATH_WIDE) return learn_wide(h, idx_dev);
+    return learn_generic(h, idx_dev);
+}
+
+__global__ void replay_scatter_kernel(Replay rp, int D, int R, int64_t n, int64_t skip,
+                                      const float *__restrict__ s, const int32_t *__restrict__ a,
+                                      const float *__restrict__ r, const float *__restrict__ s2,
+                                      const uint8_t *__restrict__ done)
+{
+    // item (rep, k), k in [skip, n): physical slot (head + k - skip) mod cap
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t m = n - skip;
+    int64_t per = m * D;
+    if (t >= per * R) return;
+    int rep = (int)(t / per);
+    int64_t e = t - (int64_t)rep * per;
+    int64_t k = e / D;
+    int c = (int)(e - k * D);
+    int64_t slot = (rp.head + k) % rp.cap;
+    int64_t src = ((int64_t)rep * n + skip + k);
+    int64_t dst = (int64_t)rep * rp.cap + slot;
+    rp.s[dst * D + c] = s[src * D + c];
+    rp.s2[dst * D + c] = s2[src * D + c];
+    if (c == 0) {
+        rp.a[dst] = a[src];
+        rp.r[dst] = r[src];
+        rp.done[dst] = done[src];
+    }
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int goldq_abi_version(void) { return GOLDQ_ABI_VERSION; }
+
+int goldq_default_config(goldq_config_t *c)
+{
+    if (!c) return GOLDQ_EINVAL;
+    memset(c, 0, sizeof(*c));
+    c->abi_version = GOLDQ_ABI_VERSION;
+    c->obs_dim = 4;       // CartPole-v0
+    c->hidden1 = 24;      // policy.go:55-56
+    c->hidden2 = 24;
+    c->n_actions = 2;
+    c->batch_size = 20;   // policy.go:36
+    c->global_batch = 0;
+    c->replay_capacity = 10000000;  // agent.go:64 (10e6)
+    c->gamma = 0.95f;     // agent.go:62
+    c->lr = 0.0005;       // policy.go:34
+    c->beta1 = 0.9;       // solvers.go:425-426
+    c->beta2 = 0.999;
+    c->eps = 1e-8;
+    c->loss = GOLDQ_LOSS_MSE;
+    c->precision = GOLDQ_PREC_FP32;
+    c->path = GOLDQ_PATH_AUTO;
+    c->device = 0;
+    c->n_replicas = 1;
+    c->stream = nullptr;
+    return GOLDQ_OK;
+}
+
+const char *goldq_last_error(const goldq_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+goldq_t *goldq_create(const goldq_config_t *cfg)
+{
+    if (!cfg) { fail(nullptr, GOLDQ_EINVAL, "config is NULL"); return nullptr; }
+    if (cfg->abi_version != GOLDQ_ABI_VERSION) { fail(nullptr, GOLDQ_EINVAL, "abi_version mismatch"); return nullptr; }
+    if (cfg->obs_dim < 1 || cfg->hidden1 < 1 || cfg->hidden2 < 1 || cfg->n_actions < 1 ||
+        cfg->batch_size < 1 || cfg->replay_capacity < 1 || cfg->n_replicas < 1) {
+        fail(nullptr, GOLDQ_EINVAL, "dimensions, batch_size, replay_capacity and n_replicas must be >= 1");
+        return nullptr;
+    }
+    if (cfg->loss != GOLDQ_LOSS_MSE) { fail(nullptr, GOLDQ_EUNSUPPORTED, "only model.MSE is implemented"); return nullptr; }
+    if (cfg->replay_capacity > 0x7fffffffLL) { fail(nullptr, GOLDQ_EINVAL, "replay_capacity must fit int32 indices"); return nullptr; }
+
+    goldq_t *h = new goldq();
+    h->cfg = *cfg;
+    h->dims = Dims{cfg->obs_dim, cfg->hidden1, cfg->hidden2, cfg->n_actions};
+    h->off = make_offsets(h->dims);
+    h->P = h->off.P;
+    h->R = cfg->n_replicas;
+    h->B = cfg->batch_size;
+    h->Bglobal = cfg->global_batch > 0 ? cfg->global_batch : cfg->batch_size;
+    h->dev = cfg->device;
+
+    auto bail = [&](const std::string &msg) -> goldq_t * {
+        g_create_error = msg.empty() ? h->err : msg;
+        goldq_destroy(h);
+        return nullptr;
+    };
+
+    cudaError_t e = cudaSetDevice(h->dev);
+    if (e != cudaSuccess) return bail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, h->dev);
+    if (e != cudaSuccess) return bail(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    h->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10)
+        return bail("libgoldq is built for sm_100a (B200) only; device is sm_" +
+                    std::to_string(prop.major) + std::to_string(prop.minor));
+
+    // path selection
+    int path = cfg->path;
+    if (path == GOLDQ_PATH_AUTO) {
+        if (cfg->precision == GOLDQ_PREC_BF16) path = GOLDQ_PATH_WIDE;
+        else if (narrow_supported(h->dims)) path = GOLDQ_PATH_NARROW;
+        else path = GOLDQ_PATH_GENERIC;
+    }
+    if (path == GOLDQ_PATH_NARROW && !narrow_supported(h->dims))
+        return bail("narrow path: shape not instantiated (24-24 hidden, (D,A) in {(4,2),(2,3),(6,3),(8,4)})");
+    if (path == GOLDQ_PATH_NARROW && cfg->precision != GOLDQ_PREC_FP32)
+        return bail("narrow path computes in fp32");
+    if (path == GOLDQ_PATH_WIDE && cfg->precision != GOLDQ_PREC_BF16)
+        return bail("wide (tcgen05) path requires GOLDQ_PREC_BF16");
+    if (path == GOLDQ_PATH_GENERIC && cfg->precision != GOLDQ_PREC_FP32)
+        return bail("generic path computes in fp32");
+    if (h->R > 1 && path != GOLDQ_PATH_NARROW)
+        return bail("n_replicas > 1 is implemented on the narrow path only");
+    h->path = path;
+
+    if (cfg->stream) h->st = (cudaStream_t)cfg->stream;
+    else {
+        e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+        h->own_stream = true;
+    }
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    cudaEventCreateWithFlags(&h->ev_push, cudaEventDisableTiming);
+
+    size_t RP = (size_t)h->R * h->P;
+    bool ok = true;
+    ok &= dalloc(&h->theta, RP) == cudaSuccess;
+    ok &= dalloc(&h->theta_t, RP) == cudaSuccess;
+    ok &= dalloc(&h->m, RP) == cudaSuccess;
+    ok &= dalloc(&h->v, RP) == cudaSuccess;
+    ok &= dalloc(&h->flat, (size_t)h->R * (h->P + 1)) == cudaSuccess;
+    ok &= dalloc(&h->loss, (size_t)h->R) == cudaSuccess;
+    ok &= dalloc(&h->d_idx, (size_t)h->R * h->B) == cudaSuccess;
+    size_t cap = (size_t)cfg->replay_capacity, RC = (size_t)h->R * cap;
+    ok &= dalloc(&h->rp.s, RC * h->dims.D) == cudaSuccess;
+    ok &= dalloc(&h->rp.s2, RC * h->dims.D) == cudaSuccess;
+    ok &= dalloc(&h->rp.a, RC) == cudaSuccess;
+    ok &= dalloc(&h->rp.r, RC) == cudaSuccess;
+    ok &= dalloc(&h->rp.done, RC) == cudaSuccess;
+    if (!ok) return bail(std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError()));
+    h->rp.cap = (int64_t)cap;
+    h->rp.len = 0;
+    h->rp.head = 0;
+    cudaMemsetAsync(h->theta, 0, RP * 4, h->st);
+    cudaMemsetAsync(h->theta_t, 0, RP * 4, h->st);
+    cudaMemsetAsync(h->m, 0, RP * 4, h->st);
+    cudaMemsetAsync(h->v, 0, RP * 4, h->st);
+    cudaMemsetAsync(h->loss, 0, (size_t)h->R * 4, h->st);
+
+    if (path == GOLDQ_PATH_NARROW) {
+        NarrowArgs a{};
+        a.B = h->B;
+        a.replicas = h->R;
+        narrow_plan(a, h->sm_count);
+        h->n_ctas = a.ctas_per_replica;
+        h->n_warps = a.warps_per_cta;
+        ok &= dalloc(&h->partial, (size_t)h->R * h->n_ctas * (h->P + 1)) == cudaSuccess;
+        ok &= dalloc(&h->ticket, (size_t)h->R) == cudaSuccess;
+        if (!ok) return bail("cudaMalloc failed (narrow scratch)");
+        cudaMemsetAsync(h->ticket, 0, (size_t)h->R * sizeof(unsigned), h->st);
+    } else if (path == GOLDQ_PATH_WIDE) {
+        std::string err;
+        h->wide = wide_create(h->dims, h->B, h->sm_count, err);
+        if (!h->wide) return bail("wide path: " + err);
+    }
+    e = cudaStreamSynchronize(h->st);
+    if (e != cudaSuccess) return bail(std::string("init sync: ") + cudaGetErrorString(e));
+    return h;
+}
+
+void goldq_destroy(goldq_t *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    if (h->st) cudaStreamSynchronize(h->st);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->wide) wide_destroy(h->wide);
+    void *ptrs[] = {h->theta, h->theta_t, h->m, h->v, h->flat, h->loss, h->d_idx, h->rp.s, h->rp.s2,
+                    h->rp.a, h->rp.r, h->rp.done, h->stg_s, h->stg_s2, h->stg_r, h->stg_a,
+                    h->stg_done, h->partial, h->ticket, h->bs, h->bs2, h->br, h->ba, h->bdone, h->h1,
+                    h->h2, h->q, h->t1, h->t2, h->qt, h->td, h->dq, h->dh2, h->dh1, h->ylab, h->mk1,
+                    h->mk2, h->gslice, h->loss_part, h->px, h->ph1, h->ph2, h->pq, h->pact,
+                    h->dbg_q, h->dbg_qt, h->dbg_td, h->dbg_idx};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_push) cudaEventDestroy(h->ev_push);
+    if (h->own_stream && h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+int64_t goldq_param_count(const goldq_t *h) { return h ? h->P : 0; }
+int goldq_selected_path(const goldq_t *h) { return h ? h->path : GOLDQ_EINVAL; }
+int64_t goldq_replay_len(const goldq_t *h) { return h ? h->rp.len : 0; }
+int64_t goldq_launch_count(const goldq_t *h) { return h ? h->launches : 0; }
+void *goldq_stream(goldq_t *h) { return h ? (void *)h->st : nullptr; }
+
+int goldq_sync(goldq_t *h)
+{
+    if (!h) return GOLDQ_EINVAL;
+    CK(h, cudaSetDevice(h->dev));
+    CK(h, cudaStreamSynchronize(h->st));
+    return GOLDQ_OK;
+}
+
+int goldq_set_params(goldq_t *h, int net, const float *theta)
+{
+    if (!h || !theta || (net != GOLDQ_NET_ONLINE && net != GOLDQ_NET_TARGET))
+        return fail(h, GOLDQ_EINVAL, "set_params: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    float *dst = net == GOLDQ_NET_ONLINE ? h->theta : h->theta_t;
+    CK(h, cudaMemcpyAsync(dst, theta, (size_t)h->R * h->P * 4, cudaMemcpyHostToDevice, h->st));
+    if (h->wide) {
+        std::string err;
+        int n = wide_set_params(h->wide, net, dst, h->st, err);
+        if (n < 0) return fail(h, GOLDQ_ECUDA, err);
+        h->launches += n;
+    }
+    CK(h, cudaStreamSynchronize(h->st));
+    return GOLDQ_OK;
+}
+
+int goldq_get_params(goldq_t *h, int net, float *theta)
+{
+    if (!h || !theta || (net != GOLDQ_NET_ONLINE && net != GOLDQ_NET_TARGET))
+        return fail(h, GOLDQ_EINVAL, "get_params: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    const float *src = net == GOLDQ_NET_ONLINE ? h->theta : h->theta_t;
+    CK(h, cudaMemcpyAsync(theta, src, (size_t)h->R * h->P * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    return GOLDQ_OK;
+}
+
+int goldq_set_adam_state(goldq_t *h, const float *m, const float *v, int64_t iter)
+{
+    if (!h || !m || !v || iter < 0) return fail(h, GOLDQ_EINVAL, "set_adam_state: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    CK(h, cudaMemcpyAsync(h->m, m, (size_t)h->R * h->P * 4, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->v, v, (size_t)h->R * h->P * 4, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    h->iter = iter;
+    return GOLDQ_OK;
+}
+
+int goldq_get_adam_state(goldq_t *h, float *m, float *v, int64_t *iter)
+{
+    if (!h) return GOLDQ_EINVAL;
+    CK(h, cudaSetDevice(h->dev));
+    if (m) CK(h, cudaMemcpyAsync(m, h->m, (size_t)h->R * h->P * 4, cudaMemcpyDeviceToHost, h->st));
+    if (v) CK(h, cudaMemcpyAsync(v, h->v, (size_t)h->R * h->P * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    if (iter) *iter = h->iter;
+    return GOLDQ_OK;
+}
+
+int goldq_replay_push(goldq_t *h, int64_t n, const float *s, const int32_t *a, const float *r,
+                      const float *s2, const uint8_t *done)
+{
+    if (!h || n < 0 || (n > 0 && (!s || !a || !r || !s2 || !done)))
+        return fail(h, GOLDQ_EINVAL, "replay_push: bad argument");
+    if (n == 0) return GOLDQ_OK;
+    CK(h, cudaSetDevice(h->dev));
+    const int D = h->dims.D, R = h->R;
+    if (h->stg_cap < n) {
+        void *old[] = {h->stg_s, h->stg_s2, h->stg_r, h->stg_a, h->stg_done};
+        CK(h, cudaStreamSynchronize(h->st));
+        for (void *p : old)
+            if (p) cudaFree(p);
+        int64_t cap = n < 1024 ? 1024 : n;
+        CK(h, dalloc(&h->stg_s, (size_t)R * cap * D));
+        CK(h, dalloc(&h->stg_s2, (size_t)R * cap * D));
+        CK(h, dalloc(&h->stg_r, (size_t)R * cap));
+        CK(h, dalloc(&h->stg_a, (size_t)R * cap));
+        CK(h, dalloc(&h->stg_done, (size_t)R * cap));
+        h->stg_cap = cap;
+    }
+    size_t rows = (size_t)R * n;
+    CK(h, cudaMemcpyAsync(h->stg_s, s, rows * D * 4, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->stg_s2, s2, rows * D * 4, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->stg_a, a, rows * 4, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->stg_r, r, rows * 4, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->stg_done, done, rows, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaEventRecord(h->ev_push, h->st));
+    // only the newest `cap` of the n items survive (PushFront + PopBack, agent.go:224-229)
+    int64_t skip = n > h->rp.cap ? n - h->rp.cap : 0;
+    int64_t mcount = n - skip;
+    int64_t total = mcount * D * R;
+    replay_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->st>>>(
+        h->rp, D, R, n, skip, h->stg_s, h->stg_a, h->stg_r, h->stg_s2, h->stg_done);
+    h->launches += 1;
+    h->rp.head = (h->rp.head + mcount) % h->rp.cap;
+    h->rp.len = h->rp.len + mcount > h->rp.cap ? h->rp.cap : h->rp.len + mcount;
+    return check_launch(h, "replay_scatter_kernel");
+}
+
+int goldq_replay_push_wait(goldq_t *h)
+{
+    if (!h) return GOLDQ_EINVAL;
+    CK(h, cudaSetDevice(h->dev));
+    CK(h, cudaEventSynchronize(h->ev_push));
+    return GOLDQ_OK;
+}
+
+void *goldq_host_alloc(int64_t bytes)
+{
+    void *p = nullptr;
+    if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void goldq_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int goldq_learn(goldq_t *h, const int32_t *idx, uint64_t seed)
+{
+    if (!h) return GOLDQ_EINVAL;
+    CK(h, cudaSetDevice(h->dev));
+    if (h->rp.len < h->B) return fail(h, GOLDQ_ENOTREADY, "replay shorter than batch");
+    const int32_t *idx_dev = nullptr;
+    if (idx) {
+        size_t n = (size_t)h->R * h->B;
+        for (size_t i = 0; i < n; i++)
+            if (idx[i] < 0 || idx[i] >= h->rp.len)
+                return fail(h, GOLDQ_EINVAL, "learn: sampled index out of range");
+        CK(h, cudaMemcpyAsync(h->d_idx, idx, n * 4, cudaMemcpyHostToDevice, h->st));
+        idx_dev = h->d_idx;
+    }
+    return run_learn(h, idx_dev, seed);
+}
+
+int goldq_learn_device_indices(goldq_t *h, const int32_t *idx_dev)
+{
+    if (!h || !idx_dev) return fail(h, GOLDQ_EINVAL, "learn_device_indices: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    return run_learn(h, idx_dev, 0);
+}
+
+int goldq_sync_target(goldq_t *h)
+{
+    if (!h) return GOLDQ_EINVAL;
+    CK(h, cudaSetDevice(h->dev));
+    CK(h, cudaMemcpyAsync(h->theta_t, h->theta, (size_t)h->R * h->P * 4, cudaMemcpyDeviceToDevice,
+                          h->st));
+    h->launches += 1;
+    if (h->wide) {
+        std::string err;
+        int n = wide_sync_target(h->wide, h->st, err);
+        if (n < 0) return fail(h, GOLDQ_ECUDA, err);
+        h->launches += n;
+    }
+    return GOLDQ_OK;
+}
+
+int goldq_last_loss(goldq_t *h, float *out)
+{
+    if (!h || !out) return fail(h, GOLDQ_EINVAL, "last_loss: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    CK(h, cudaMemcpyAsync(out, h->loss, (size_t)h->R * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    return GOLDQ_OK;
+}
+
+static int ensure_predict(goldq_t *h, int64_t n)
+{
+    if (h->pred_rows >= n) return GOLDQ_OK;
+    void *old[] = {h->px, h->ph1, h->ph2, h->pq, h->pact};
+    for (void *p : old)
+        if (p) cudaFree(p);
+    int64_t cap = n < 256 ? 256 : n;
+    const Dims &d = h->dims;
+    CK(h, dalloc(&h->px, (size_t)cap * d.D));
+    CK(h, dalloc(&h->ph1, (size_t)cap * d.H1));
+    CK(h, dalloc(&h->ph2, (size_t)cap * d.H2));
+    CK(h, dalloc(&h->pq, (size_t)cap * d.A));
+    CK(h, dalloc(&h->pact, (size_t)cap));
+    h->pred_rows = cap;
+    return GOLDQ_OK;
+}
+
+static int predict_dev(goldq_t *h, int net, int replica, int64_t n, const float *x)
+{
+    if (replica < 0 || replica >= h->R) return fail(h, GOLDQ_EINVAL, "predict: replica out of range");
+    if (n < 1 || n > 0x7fffffff / (h->dims.D > h->dims.H1 ? h->dims.D : h->dims.H1))
+        return fail(h, GOLDQ_EINVAL, "predict: bad row count");
+    int rc = ensure_predict(h, n);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(h->px, x, (size_t)n * h->dims.D * 4, cudaMemcpyHostToDevice, h->st));
+    const float *theta = (net == GOLDQ_NET_ONLINE ? h->theta : h->theta_t) + (size_t)replica * h->P;
+    generic_forward(h, theta, h->px, (int)n, h->ph1, nullptr, h->ph2, nullptr, h->pq);
+    return check_launch(h, "predict");
+}
+
+int goldq_predict(goldq_t *h, int net, int replica, int64_t n, const float *x, float *q)
+{
+    if (!h || !x || !q || (net != GOLDQ_NET_ONLINE && net != GOLDQ_NET_TARGET))
+        return fail(h, GOLDQ_EINVAL, "predict: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    int rc = predict_dev(h, net, replica, n, x);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(q, h->pq, (size_t)n * h->dims.A * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    return GOLDQ_OK;
+}
+
+int goldq_greedy_action(goldq_t *h, int replica, int64_t n, const float *x, int32_t *action)
+{
+    if (!h || !x || !action) return fail(h, GOLDQ_EINVAL, "greedy_action: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    int rc = predict_dev(h, GOLDQ_NET_ONLINE, replica, n, x);
+    if (rc) return rc;
+    launch_argmax_rows(h->pq, (int)n, h->dims.A, h->pact, h->st);
+    h->launches += 1;
+    CK(h, cudaMemcpyAsync(action, h->pact, (size_t)n * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    return check_launch(h, "greedy_action");
+}
+
+int goldq_fit_batch(goldq_t *h, int64_t n, const float *x, const float *y)
+{
+    if (!h || !x || !y) return fail(h, GOLDQ_EINVAL, "fit_batch: bad argument");
+    // goro compiles one graph for batch_size rows and one for a single row
+    // (model.go:260-312); any other leading dimension is a shape error (io.go:138-153)
+    if (n != h->B && n != 1)
+        return fail(h, GOLDQ_EINVAL, "fit_batch: rows must equal batch_size (FitBatch) or 1 (Fit)");
+    if (h->world > 1) return fail(h, GOLDQ_EUNSUPPORTED, "fit_batch is single-GPU");
+    CK(h, cudaSetDevice(h->dev));
+    int rc = ensure_generic(h, h->B > 1 ? h->B : 1);
+    if (rc) return rc;
+    const Dims &d = h->dims;
+    CK(h, cudaMemcpyAsync(h->bs, x, (size_t)n * d.D * 4, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->ylab, y, (size_t)n * d.A * 4, cudaMemcpyHostToDevice, h->st));
+    generic_forward(h, h->theta, h->bs, (int)n, h->h1, h->mk1, h->h2, h->mk2, h->q);
+    StepScalars sc;
+    sc.gamma = h->cfg.gamma;
+    sc.count = (float)(n * d.A);
+    sc.inv_count = 1.0f / sc.count;
+    int nlp = 0;
+    launch_label_loss(h->q, h->ylab, (int)n, d.A, sc, h->dq, h->loss_part, &nlp, h->st);
+    h->launches += 1;
+    generic_backward(h, h->bs, (int)n);
+    launch_reduce_slices(h->gslice, h->P, h->nsplit, h->P, h->loss_part, nlp, sc.count, h->flat,
+                         h->st);
+    h->iter += 1;
+    launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), h->st);
+    h->launches += 2;
+    CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+    if (h->wide) {
+        std::string err;
+        int k = wide_after_update(h->wide, h->theta, h->st, err);
+        if (k < 0) return fail(h, GOLDQ_ECUDA, err);
+        h->launches += k;
+    }
+    return check_launch(h, "fit_batch");
+}
+
+int goldq_dp_unique_id(uint8_t id[128])
+{
+    std::string err;
+    if (!g_nccl.load(err)) return fail(nullptr, GOLDQ_ENCCL, err);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId uid;
+    ncclResult_t r = g_nccl.GetUniqueId(&uid);
+    if (r != ncclSuccess) return fail(nullptr, GOLDQ_ENCCL, "ncclGetUniqueId failed");
+    memcpy(id, &uid, 128);
+    return GOLDQ_OK;
+}
+
+int goldq_dp_init(goldq_t *h, const uint8_t id[128], int rank, int world)
+{
+    if (!h || !id || world < 1 || rank < 0 || rank >= world)
+        return fail(h, GOLDQ_EINVAL, "dp_init: bad argument");
+    if (h->R > 1) return fail(h, GOLDQ_EUNSUPPORTED, "dp_init: replicas are independent; no group needed");
+    if (h->Bglobal != h->B * world)
+        return fail(h, GOLDQ_EINVAL, "dp_init: global_batch must equal batch_size * world");
+    if (world == 1) { h->world = 1; h->rank = 0; return GOLDQ_OK; }
+    std::string err;
+    if (!g_nccl.load(err)) return fail(h, GOLDQ_ENCCL, err);
+    CK(h, cudaSetDevice(h->dev));
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, uid, rank);
+    if (r != ncclSuccess)
+        return fail(h, GOLDQ_ENCCL, std::string("ncclCommInitRank: ") +
+                                        (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    h->rank = rank;
+    h->world = world;
+    return GOLDQ_OK;
+}
+
+int goldq_debug_enable(goldq_t *h, int on)
+{
+    if (!h) return GOLDQ_EINVAL;
+    CK(h, cudaSetDevice(h->dev));
+    if (on && !h->dbg_q) {
+        size_t RB = (size_t)h->R * h->B;
+        CK(h, dalloc(&h->dbg_q, RB * h->dims.A));
+        CK(h, dalloc(&h->dbg_qt, RB * h->dims.A));
+        CK(h, dalloc(&h->dbg_td, RB));
+        CK(h, dalloc(&h->dbg_idx, RB));
+    }
+    h->debug = on != 0;
+    if (h->wide) wide_set_debug(h->wide, h->debug);
+    return GOLDQ_OK;
+}
+
+int goldq_debug_fetch(goldq_t *h, int what, void *out, int64_t out_bytes)
+{
+    if (!h || !out) return fail(h, GOLDQ_EINVAL, "debug_fetch: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    const Dims &d = h->dims;
+    size_t RB = (size_t)h->R * h->B;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    bool narrow = h->path == GOLDQ_PATH_NARROW;
+    if (narrow && !h->debug && what != GOLDQ_DBG_GRADS)
+        return fail(h, GOLDQ_EINVAL, "debug_fetch: call goldq_debug_enable(h,1) before the step");
+    const float *wq = nullptr, *wqt = nullptr, *wtd = nullptr;
+    if (h->wide) wide_debug_ptrs(h->wide, &wq, &wqt, &wtd);
+    switch (what) {
+    case GOLDQ_DBG_Q_ONLINE: src = narrow ? h->dbg_q : (h->wide ? wq : h->q); bytes = RB * d.A * 4; break;
+    case GOLDQ_DBG_Q_TARGET: src = narrow ? h->dbg_qt : (h->wide ? wqt : h->qt); bytes = RB * d.A * 4; break;
+    case GOLDQ_DBG_TD: src = narrow ? h->dbg_td : (h->wide ? wtd : h->td); bytes = RB * 4; break;
+    case GOLDQ_DBG_GRADS: {
+        // flat is [R][P+1]; return the P gradient entries of each replica
+        if ((size_t)out_bytes < (size_t)h->R * h->P * 4) return fail(h, GOLDQ_EINVAL, "debug_fetch: buffer too small");
+        CK(h, cudaMemcpy2DAsync(out, (size_t)h->P * 4, h->flat, (size_t)(h->P + 1) * 4, (size_t)h->P * 4,
+                                h->R, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+        return GOLDQ_OK;
+    }
+    case GOLDQ_DBG_INDICES: src = narrow ? h->dbg_idx : h->d_idx; bytes = RB * 4; break;
+    case GOLDQ_DBG_BATCH_S: src = h->bs; bytes = RB * d.D * 4; break;
+    case GOLDQ_DBG_BATCH_A: src = h->ba; bytes = RB * 4; break;
+    default: return fail(h, GOLDQ_EINVAL, "debug_fetch: unknown selector");
+    }
+    if (!src) return fail(h, GOLDQ_EINVAL, "debug_fetch: not available on this path / before any step");
+    if ((size_t)out_bytes < bytes) return fail(h, GOLDQ_EINVAL, "debug_fetch: buffer too small");
+    CK(h, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    if (what == GOLDQ_DBG_Q_TARGET && !narrow) {
+        // rows of terminal events are never evaluated by the reference (agent.go:138); report 0
+        std::vector<uint8_t> dn(RB);
+        const uint8_t *dsrc = h->wide ? wide_done_ptr(h->wide) : h->bdone;
+        CK(h, cudaMemcpy(dn.data(), dsrc, RB, cudaMemcpyDeviceToHost));
+        float *o = (float *)out;
+        for (size_t b = 0; b < RB; b++)
+            if (dn[b])
+                for (int j = 0; j < d.A; j++) o[b * d.A + j] = 0.f;
+    }
+    return GOLDQ_OK;
+}
+
+int goldq_timer_start(goldq_t *h)
+{
+    if (!h) return GOLDQ_EINVAL;
+    CK(h, cudaSetDevice(h->dev));
+    CK(h, cudaEventRecord(h->ev0, h->st));
+    return GOLDQ_OK;
+}
+
+int goldq_timer_stop(goldq_t *h, float *ms)
+{
+    if (!h || !ms) return GOLDQ_EINVAL;
+    CK(h, cudaSetDevice(h->dev));
+    CK(h, cudaEventRecord(h->ev1, h->st));
+    CK(h, cudaEventSynchronize(h->ev1));
+    CK(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return GOLDQ_OK;
+}
+
+/* Host-side mirror of the device sampler: the indices goldq_learn(h, NULL, seed)
+ * draws for replica `replica` when the replay holds `len` events. */
+int goldq_sampler_indices(int64_t len, int32_t batch, uint64_t seed, int32_t replica, int32_t *out)
+{
+    if (len < 1 || len > 0x7fffffffLL || batch < 0 || !out) return GOLDQ_EINVAL;
+    for (int b = 0; b < batch; b++)
+        out[b] = (int32_t)perm_index((uint32_t)b, (uint32_t)len,
+                                     seed + 0x9E3779B97F4A7C15ull * (uint64_t)replica);
+    return GOLDQ_OK;
+}
+
+}  // extern "C"

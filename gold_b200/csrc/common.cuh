@@ -1,0 +1,119 @@
+// common.cuh — internal declarations shared by the libgoldq translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/goldq.h"
+
+namespace gq {
+
+struct Dims {
+    int D, H1, H2, A;
+};
+
+// Flat learnable layout [W1,b1,W2,b2,W3,b3]; W is (in x out) row-major.
+// Reference: vendor/github.com/aunum/goro/pkg/v1/layer/fc.go:98-101,164-169.
+struct Offsets {
+    int w1, b1, w2, b2, w3, b3, P;
+};
+
+__host__ __device__ inline Offsets make_offsets(const Dims &d)
+{
+    Offsets o;
+    o.w1 = 0;
+    o.b1 = o.w1 + d.D * d.H1;
+    o.w2 = o.b1 + d.H1;
+    o.b2 = o.w2 + d.H1 * d.H2;
+    o.w3 = o.b2 + d.H2;
+    o.b3 = o.w3 + d.H2 * d.A;
+    o.P = o.b3 + d.A;
+    return o;
+}
+
+// Replay ring, structure of arrays.  Per replica r the arrays start at r*cap.
+// head = next physical slot to write; logical index i (i-th newest, the
+// reference's deque.At(i) after PushFront) lives at (head - 1 - i) mod cap.
+struct Replay {
+    float *s;       // [R][cap][D]
+    float *s2;      // [R][cap][D]
+    int32_t *a;     // [R][cap]
+    float *r;       // [R][cap]
+    uint8_t *done;  // [R][cap]
+    int64_t cap;
+    int64_t len;
+    int64_t head;
+};
+
+// Adam constants, computed on the host exactly as the reference does
+// (vendor/gorgonia.org/gorgonia/solvers.go:446-447,490-503): the bias corrections
+// in float64, then cast.
+struct AdamConsts {
+    float beta1, beta2, omb1, omb2, eps, neg_eta, c1, c2;
+};
+
+// Scalars of one learn step.
+struct StepScalars {
+    float gamma;
+    float count;      // float32(B_global * A)   (Mean's divisor)
+    float inv_count;  // float32(1) / count
+};
+
+// ---- generic path (kernels_generic.cu) -----------------------------------
+void launch_sample_indices(int32_t *idx, int B, int64_t len, uint64_t seed, int replicas,
+                           cudaStream_t st);
+void launch_gather(const Replay &rp, int D, const int32_t *idx, int B, float *bs, float *bs2,
+                   int32_t *ba, float *br, uint8_t *bdone, cudaStream_t st);
+void launch_fc_forward(const float *X, const float *W, const float *bias, float *Y,
+                       uint8_t *mask, int n, int in, int out, bool relu, cudaStream_t st);
+// TD label + dQ: dq is dense [B][A] (zero off-action), loss partials per block.
+void launch_td(const float *q, const float *qt, const int32_t *a, const float *r,
+               const uint8_t *done, int B, int A, StepScalars sc, float *td, float *dq,
+               float *loss_part, int *n_loss_part, cudaStream_t st);
+// Explicit-label variant (FitBatch): dq = 2 (q - y) / count, dense.
+void launch_label_loss(const float *q, const float *y, int n, int A, StepScalars sc, float *dq,
+                       float *loss_part, int *n_loss_part, cudaStream_t st);
+// dW slices: gslice[z][w_off + i*out + j] = sum over the z-th row range of X[r][i]*dZ[r][j];
+// gslice[z][b_off + j] = sum of dZ[r][j].
+void launch_grad_w(const float *X, const float *dZ, int n, int in, int out, float *gslice,
+                   int64_t slice_stride, int nsplit, int w_off, int b_off, cudaStream_t st);
+// dX[n][in] = (dZ[n][out] . W[in][out]^T) * mask
+void launch_grad_x(const float *dZ, const float *W, const uint8_t *mask, float *dX, int n, int in,
+                   int out, cudaStream_t st);
+// flat[i] = sum_z gslice[z][i] (i < P); flat[P] = (sum of loss partials) / count
+void launch_reduce_slices(const float *gslice, int64_t slice_stride, int nsplit, int P,
+                          const float *loss_part, int n_loss_part, float count, float *flat,
+                          cudaStream_t st);
+// Fused Adam incl. the reference's double update; replicas laid out [R][P].
+void launch_adam(float *w, const float *g, float *m, float *v, int64_t n, AdamConsts c,
+                 cudaStream_t st);
+void launch_argmax_rows(const float *q, int n, int A, int32_t *out, cudaStream_t st);
+
+// ---- narrow fused path (kernels_narrow.cu) --------------------------------
+bool narrow_supported(const Dims &d);
+struct NarrowArgs {
+    Dims dims;
+    Replay rp;
+    const int32_t *idx;   // [R][B] or nullptr -> sample on device
+    uint64_t seed;
+    int B;
+    int replicas;
+    float *theta;         // [R][P]
+    const float *theta_t; // [R][P]
+    float *m, *v;         // [R][P]
+    float *partial;       // [R][ctas][P+1] scratch
+    unsigned int *ticket; // [R] zero-initialised, self-resetting
+    float *flat;          // [R][P+1]: reduced gradient + loss (always written)
+    float *loss;          // [R]
+    int fuse_adam;        // 1: apply Adam in the same kernel; 0: stop at `flat` (data-parallel)
+    StepScalars sc;
+    AdamConsts adam;
+    // debug snapshots (nullptr to skip)
+    float *dbg_q, *dbg_qt, *dbg_td;
+    int32_t *dbg_idx;
+    int ctas_per_replica; // filled by narrow_plan
+    int warps_per_cta;
+};
+void narrow_plan(NarrowArgs &a, int sm_count);
+void launch_narrow_learn(const NarrowArgs &a, cudaStream_t st);
+
+}  // namespace gq

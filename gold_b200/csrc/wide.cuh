@@ -1,0 +1,32 @@
+// wide.cuh — interface of the bf16 tcgen05 path (kernels_wide.cu).
+#pragma once
+#include <string>
+
+#include "common.cuh"
+
+namespace gq {
+
+struct WideState;
+
+struct WideStep {
+    Replay rp;
+    const int32_t *idx;    // [B] device
+    int B;
+    const float *theta;    // fp32 master parameters (biases are read from here)
+    const float *theta_t;
+    float *flat;           // [P+1] out: reduced gradient + loss
+    StepScalars sc;
+};
+
+WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err);
+void wide_destroy(WideState *w);
+// each returns the number of kernels launched, or -1 with err set
+int wide_set_params(WideState *w, int net, const float *theta_dev, cudaStream_t st, std::string &err);
+int wide_after_update(WideState *w, const float *theta_dev, cudaStream_t st, std::string &err);
+int wide_sync_target(WideState *w, cudaStream_t st, std::string &err);
+int wide_forward_backward(WideState *w, const WideStep &s, cudaStream_t st, std::string &err);
+void wide_set_debug(WideState *w, bool on);
+void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const float **td);
+const uint8_t *wide_done_ptr(WideState *w);
+
+}  // namespace gq

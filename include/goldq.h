@@ -1,0 +1,189 @@
+/* goldq.h — C ABI of the B200-native DQN learn step (libgoldq.so).
+ *
+ * This is the drop-in boundary for gold's `pkg/v1/agent/deepq` hot path: a Go
+ * package (go/deepq, cgo) or any other FFI binds exactly these entry points.
+ * Plain pointers and sizes only; no C++/torch types.  Every function that returns
+ * `int` returns 0 on success and a negative GOLDQ_E* code on failure; the message
+ * is available from goldq_last_error().  The library never retains a caller
+ * pointer: host buffers are copied (or the copy is enqueued from a staging area)
+ * before the call returns, which is the rule cgo needs.
+ *
+ * Calls on one handle are not re-entrant (the reference is single-goroutine:
+ * global solver / math/rand singletons, pkg/v1/agent/deepq/policy.go:32-38,
+ * memory.go:59).  Every entry point selects the handle's device first, because a
+ * cgo call may arrive on any OS thread.
+ *
+ * Reference paths below are relative to the aunum/gold tree; V/ = vendor/.
+ */
+#ifndef GOLDQ_H
+#define GOLDQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOLDQ_ABI_VERSION 1
+
+/* error codes */
+#define GOLDQ_OK 0
+#define GOLDQ_EINVAL (-1)   /* bad argument / shape mismatch (goro io.go:138-153 returns an error) */
+#define GOLDQ_ECUDA (-2)    /* CUDA runtime error */
+#define GOLDQ_ENOTREADY (-3)/* replay shorter than the batch (agent.go:127 returns nil: caller maps to no-op) */
+#define GOLDQ_EUNSUPPORTED (-4) /* configuration the CUDA path does not implement (no CPU fallback by design) */
+#define GOLDQ_ENCCL (-5)
+
+/* which network */
+#define GOLDQ_NET_ONLINE 0  /* Agent.Policy        (agent.go:27) */
+#define GOLDQ_NET_TARGET 1  /* Agent.TargetPolicy  (agent.go:30) */
+
+/* loss (V/github.com/aunum/goro/pkg/v1/model/loss.go) */
+#define GOLDQ_LOSS_MSE 0    /* model.MSE, loss.go:22-42 */
+
+/* arithmetic of the forward/backward pass */
+#define GOLDQ_PREC_FP32 0   /* reference arithmetic: fp32, multiply then add, k-sequential */
+#define GOLDQ_PREC_BF16 1   /* bf16 operands, fp32 accumulate on tcgen05 tensor cores; fp32 master weights + Adam */
+
+/* kernel path selection (GOLDQ_PATH_AUTO picks by shape and precision) */
+#define GOLDQ_PATH_AUTO 0
+#define GOLDQ_PATH_GENERIC 1 /* tiled CUDA-core kernels, any shape */
+#define GOLDQ_PATH_NARROW 2  /* one fused warp-per-row kernel, classic-control shapes (H<=32) */
+#define GOLDQ_PATH_WIDE 3    /* tcgen05 GEMM tiles (requires GOLDQ_PREC_BF16) */
+
+/* goldq_debug_fetch selectors: state of the LAST learn step (parity tests) */
+#define GOLDQ_DBG_Q_ONLINE 0  /* float[B*A]  online Q(s)            */
+#define GOLDQ_DBG_Q_TARGET 1  /* float[B*A]  target Q(s')           */
+#define GOLDQ_DBG_TD 2        /* float[B]    TD targets             */
+#define GOLDQ_DBG_GRADS 3     /* float[P]    dL/dtheta before Adam  */
+#define GOLDQ_DBG_INDICES 4   /* int32[B]    sampled logical indices */
+#define GOLDQ_DBG_BATCH_S 5   /* float[B*D]  gathered states        */
+#define GOLDQ_DBG_BATCH_A 6   /* int32[B]    gathered actions       */
+
+typedef struct goldq goldq_t;
+
+/* Flat POD mirror of deepq.AgentConfig / PolicyConfig / AdamSolver
+ * (agent.go:44-85, policy.go:14-38, V/gorgonia.org/gorgonia/solvers.go:399-438). */
+typedef struct goldq_config {
+    int32_t abi_version;      /* must be GOLDQ_ABI_VERSION */
+    int32_t obs_dim;          /* D: env.ObservationSpaceShape()[0]            (policy.go:75) */
+    int32_t hidden1;          /* layer.FC{Output: 24}                         (policy.go:55) */
+    int32_t hidden2;          /* layer.FC{Input: 24, Output: 24}              (policy.go:56) */
+    int32_t n_actions;        /* A: PotentialsShape(env.ActionSpace)[0]       (policy.go:78) */
+    int32_t batch_size;       /* PolicyConfig.BatchSize (rows THIS handle trains per step) */
+    int32_t global_batch;     /* rows of the whole data-parallel job; 0 = batch_size */
+    int64_t replay_capacity;  /* Hyperparameters.BufferSize                   (agent.go:57,64) */
+    float gamma;              /* Hyperparameters.Gamma, a float32             (agent.go:48) */
+    double lr;                /* AdamSolver.eta                               (solvers.go:400) */
+    double beta1, beta2, eps; /* AdamSolver.beta1/beta2/eps                   (solvers.go:401-403) */
+    int32_t loss;             /* GOLDQ_LOSS_* */
+    int32_t precision;        /* GOLDQ_PREC_* */
+    int32_t path;             /* GOLDQ_PATH_* */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t n_replicas;       /* >= 1: independent agents (own weights, solver state, replay) in one grid */
+    int32_t reserved0;
+    void *stream;             /* cudaStream_t to run on, or NULL to create one */
+} goldq_config_t;
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* Replaces deepq.NewAgent → MakePolicy ×2 → Sequential.Compile (agent.go:88-123,
+ * policy.go:74-110, goro model.go:260-312): allocates both networks, the Adam
+ * state and the replay ring on the device.  Parameters start at zero; the host
+ * layer initialises them (GlorotN) through goldq_set_params. */
+int goldq_default_config(goldq_config_t *cfg);               /* gold's defaults: CartPole shape, B=20, γ=.95, Adam 5e-4 */
+goldq_t *goldq_create(const goldq_config_t *cfg);            /* NULL on failure: see goldq_last_error(NULL) */
+void goldq_destroy(goldq_t *h);
+const char *goldq_last_error(const goldq_t *h);              /* h may be NULL (creation errors) */
+int goldq_abi_version(void);
+int64_t goldq_param_count(const goldq_t *h);                 /* P per replica */
+int goldq_selected_path(const goldq_t *h);                   /* GOLDQ_PATH_* actually in use */
+
+/* ---- parameters and solver state --------------------------------------- */
+/* Learnable order [W1,b1,W2,b2,W3,b3], W (in×out) row-major, bias (out)
+ * (goro layer/chain.go:38-44, fc.go:98-101,164-169).  Arrays hold
+ * n_replicas × P floats.  Replaces reading/writing Sequential.Learnables()
+ * (model.go:17-50). */
+int goldq_set_params(goldq_t *h, int net, const float *theta);
+int goldq_get_params(goldq_t *h, int net, float *theta);
+/* AdamSolver's cache (means in .Value, variances in .d) and iter
+ * (solvers.go:412-414, 441-445). */
+int goldq_set_adam_state(goldq_t *h, const float *m, const float *v, int64_t iter);
+int goldq_get_adam_state(goldq_t *h, float *m, float *v, int64_t *iter);
+
+/* ---- replay memory ------------------------------------------------------ */
+/* deepq.Memory + Agent.Remember (memory.go:41-51, agent.go:224-229): append n
+ * transitions, given oldest first; each becomes the new front (logical index 0 =
+ * newest), the oldest are evicted past replay_capacity.  Layout: s, s2 are
+ * [n_replicas][n][D] floats; a, r, done are [n_replicas][n]. */
+int goldq_replay_push(goldq_t *h, int64_t n, const float *s, const int32_t *a,
+                      const float *r, const float *s2, const uint8_t *done);
+int64_t goldq_replay_len(const goldq_t *h);                  /* Memory.Len() */
+/* Pageable host buffers are consumed before goldq_replay_push returns.  Buffers
+ * from goldq_host_alloc (pinned) are copied asynchronously: do not overwrite them
+ * until goldq_replay_push_wait (or goldq_sync) returns. */
+int goldq_replay_push_wait(goldq_t *h);
+void *goldq_host_alloc(int64_t bytes);                       /* pinned host memory (cudaHostAlloc) */
+void goldq_host_free(void *p);
+
+/* ---- the learn step ----------------------------------------------------- */
+/* Agent.Learn (agent.go:126-178) minus the ε decay and the steps%N test, which
+ * stay in the host layer: sample → two forwards per event → label → FitBatch
+ * (goro model.go:552-573) → AdamSolver.Step.  Asynchronous on the handle's stream.
+ *   idx != NULL: the sampled logical indices, [n_replicas][batch_size], host
+ *                memory (Memory.Sample's output, memory.go:54-69; injected so that
+ *                runs are reproducible — the reference reseeds from the clock).
+ *   idx == NULL: indices are drawn on the device: the first batch_size entries of
+ *                a keyed pseudo-random permutation of [0, Len) — distinct and
+ *                uniform like rand.Perm(Len)[:B] — from `seed`.
+ * Returns GOLDQ_ENOTREADY if Len < batch_size (agent.go:127). */
+int goldq_learn(goldq_t *h, const int32_t *idx, uint64_t seed);
+/* Same, with the index list already in device memory (no host traffic). */
+int goldq_learn_device_indices(goldq_t *h, const int32_t *idx_dev);
+/* Host mirror of the device sampler: the indices goldq_learn(h, NULL, seed) draws
+ * for `replica` when the replay holds `len` events (lets the host layer fill
+ * Event.i as Memory.Sample does, memory.go:63).  Pure CPU integer code. */
+int goldq_sampler_indices(int64_t len, int32_t batch, uint64_t seed, int32_t replica, int32_t *out);
+/* Agent.updateTarget's copy (agent.go:181-190) = Sequential.CloneLearnablesTo
+ * (goro model.go:606-636): target ← online.  Solver state untouched. */
+int goldq_sync_target(goldq_t *h);
+/* Loss of the last learn step (the value gold's tracker reads from the
+ * `<name>_train_batch_loss` node, goro model.go:404-408).  Synchronises.
+ * out: float[n_replicas]. */
+int goldq_last_loss(goldq_t *h, float *out);
+
+/* ---- goro model.Model surface ------------------------------------------ */
+/* Sequential.Predict / PredictBatch (model.go:500-512, 514-526): q = net(x) for n
+ * rows of replica `replica`; x is [n][D], q is [n][A] (host).  Synchronous: the
+ * returned q is a fresh copy owned by the caller, as the reference returns a
+ * clone (V/gorgonia.org/gorgonia/vm_tape.go:691-697). */
+int goldq_predict(goldq_t *h, int net, int replica, int64_t n, const float *x, float *q);
+/* Agent.action (agent.go:207-221): first-argmax of the online prediction. */
+int goldq_greedy_action(goldq_t *h, int replica, int64_t n, const float *x, int32_t *action);
+/* Sequential.FitBatch / Fit (model.go:528-573) on explicit labels: x [n][D],
+ * y [n][A]; one MSE + Adam step on the ONLINE net of replica 0.  n must equal
+ * batch_size (FitBatch) or 1 (Fit) — goro rejects other shapes (io.go:138-153). */
+int goldq_fit_batch(goldq_t *h, int64_t n, const float *x, const float *y);
+
+/* ---- data-parallel group (new capability) ------------------- */
+/* One handle per GPU/process.  Each rank trains batch_size rows of a
+ * global_batch-row step; gradients are summed with one all-reduce per step so
+ * every rank applies the identical Adam update (loss = mean over the GLOBAL batch,
+ * loss.go:28-42).  The 128-byte id comes from goldq_dp_unique_id on rank 0 and is
+ * distributed by the caller (torch.distributed / any side channel). */
+int goldq_dp_unique_id(uint8_t id[128]);
+int goldq_dp_init(goldq_t *h, const uint8_t id[128], int rank, int world);
+
+/* ---- plumbing ----------------------------------------------------------- */
+int goldq_sync(goldq_t *h);                                  /* wait for the handle's stream */
+void *goldq_stream(goldq_t *h);                              /* the cudaStream_t in use */
+int64_t goldq_launch_count(const goldq_t *h);                /* kernels launched so far by this handle */
+int goldq_debug_enable(goldq_t *h, int on);                  /* keep Q/TD/grad snapshots of each step */
+int goldq_debug_fetch(goldq_t *h, int what, void *out, int64_t out_bytes);
+/* CUDA-event timer on the handle's stream (bench.py): start; ...; stop → ms. */
+int goldq_timer_start(goldq_t *h);
+int goldq_timer_stop(goldq_t *h, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOLDQ_H */

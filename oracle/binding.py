@@ -147,6 +147,29 @@ def learn(dims, B, theta, theta_t, m, v, it, s, a, r, s2, done, gamma=0.95, lr=5
     return out
 
 
+def fit(dims, theta, m, v, it, x, y, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-8, dtype=np.float32):
+    """Sequential.FitBatch on explicit labels; theta/m/v updated IN PLACE."""
+    D, H1, H2, A = dims
+    f32 = dtype == np.float32
+    ct = C.c_float if f32 else C.c_double
+    P = nparams(*dims)
+    x = np.ascontiguousarray(x, dtype).reshape(-1, D)
+    y = np.ascontiguousarray(y, dtype).reshape(-1, A)
+    n = x.shape[0]
+    assert y.shape[0] == n
+    for arr in (theta, m, v):
+        assert arr.dtype == dtype and arr.flags.c_contiguous and arr.size == P
+    cfg = OqCfg(OqDims(D, H1, H2, A), n, 0.0, lr, beta1, beta2, eps)
+    loss = np.zeros(1, dtype)
+    grads = np.zeros(P, dtype)
+    itc = C.c_int64(it)
+    fn = lib().oq_fit_f32 if f32 else lib().oq_fit_f64
+    rc = fn(C.byref(cfg), n, _p(theta, ct), _p(m, ct), _p(v, ct), C.byref(itc), _p(x, ct),
+            _p(y, ct), _p(loss, ct), _p(grads, ct))
+    assert rc == 0
+    return {"iter": itc.value, "loss": loss[0], "grads": grads}
+
+
 def gather(D, order_s, order_a, order_r, order_s2, order_done, idx):
     """Rows idx (i = i-th newest) out of arrival-ordered arrays."""
     n = order_a.shape[0]

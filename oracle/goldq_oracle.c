@@ -207,6 +207,21 @@ int oq_learn_f64(const oq_cfg_t *cfg, double *theta, const double *theta_t, doub
                      q_target, td, loss, grads);
 }
 
+/* Sequential.FitBatch (n = batch) / Fit (n = 1) on explicit labels. */
+int oq_fit_f32(const oq_cfg_t *cfg, int n, float *theta, float *m, float *v, int64_t *iter,
+               const float *x, const float *y, float *loss, float *grads)
+{
+    *iter += 1;
+    return fit_f32(cfg, n, theta, m, v, *iter, x, y, loss, grads);
+}
+
+int oq_fit_f64(const oq_cfg_t *cfg, int n, double *theta, double *m, double *v, int64_t *iter,
+               const double *x, const double *y, double *loss, double *grads)
+{
+    *iter += 1;
+    return fit_f64(cfg, n, theta, m, v, *iter, x, y, loss, grads);
+}
+
 /* Replay indexing convention of deepq.Memory: Remember = PushFront
  * (agent.go:224-229), Sample reads At(i) (memory.go:62) and At(0) is the front
  * (V/github.com/gammazero/deque/deque.go:112-118), so logical index i is the

@@ -32,3 +32,57 @@ def rel_err(x, ref):
     x = np.asarray(x, np.float64)
     ref = np.asarray(ref, np.float64)
     return float(np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-300))
+
+
+class OracleAgent:
+    """Oracle-side twin of one goldq handle (test infrastructure).
+
+    Holds the reference-arithmetic state (fp32) and an fp64 shadow used only to
+    budget the error of order-dependent sums (loss, gradients)."""
+
+    def __init__(self, dims, B, theta, theta_t, gamma=0.95, lr=5e-4, capacity=None):
+        from oracle import binding as O
+        self.O = O
+        self.dims, self.B, self.gamma, self.lr = dims, B, gamma, lr
+        P = O.nparams(*dims)
+        self.theta = np.array(theta, np.float32).copy()
+        self.theta_t = np.array(theta_t, np.float32).copy()
+        self.m = np.zeros(P, np.float32)
+        self.v = np.zeros(P, np.float32)
+        self.iter = 0
+        self.capacity = capacity
+        D = dims[0]
+        self.s = np.zeros((0, D), np.float32)
+        self.s2 = np.zeros((0, D), np.float32)
+        self.a = np.zeros(0, np.int32)
+        self.r = np.zeros(0, np.float32)
+        self.done = np.zeros(0, np.uint8)
+
+    def push(self, s, a, r, s2, done):
+        self.s = np.concatenate([self.s, s]); self.s2 = np.concatenate([self.s2, s2])
+        self.a = np.concatenate([self.a, a]); self.r = np.concatenate([self.r, r])
+        self.done = np.concatenate([self.done, done])
+        if self.capacity is not None and len(self.a) > self.capacity:   # PopBack: drop the oldest
+            k = len(self.a) - self.capacity
+            self.s, self.s2, self.a, self.r, self.done = (x[k:] for x in (self.s, self.s2, self.a, self.r, self.done))
+
+    def batch(self, idx):
+        return self.O.gather(self.dims[0], self.s, self.a, self.r, self.s2, self.done, idx)
+
+    def learn(self, idx, with64=True):
+        s, a, r, s2, done = self.batch(idx)
+        out64 = None
+        if with64:
+            th64 = self.theta.astype(np.float64); m64 = self.m.astype(np.float64); v64 = self.v.astype(np.float64)
+            out64 = self.O.learn(self.dims, self.B, th64, self.theta_t.astype(np.float64), m64, v64, self.iter,
+                                 s.astype(np.float64), a, r.astype(np.float64), s2.astype(np.float64), done,
+                                 gamma=self.gamma, lr=self.lr, dtype=np.float64)
+            out64["theta"] = th64
+        out = self.O.learn(self.dims, self.B, self.theta, self.theta_t, self.m, self.v, self.iter,
+                           s, a, r, s2, done, gamma=self.gamma, lr=self.lr)
+        self.iter = out["iter"]
+        out["done"] = done
+        return out, out64
+
+    def sync_target(self):
+        self.theta_t = self.theta.copy()
