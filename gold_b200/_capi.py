@@ -29,6 +29,7 @@ SYMBOLS = [
     "goldq_last_loss", "goldq_predict", "goldq_greedy_action", "goldq_fit_batch",
     "goldq_dp_unique_id", "goldq_dp_init", "goldq_sync", "goldq_stream", "goldq_launch_count",
     "goldq_debug_enable", "goldq_debug_fetch", "goldq_timer_start", "goldq_timer_stop",
+    "goldq_selftest_umma",
 ]
 
 
@@ -97,6 +98,7 @@ def lib():
         "goldq_debug_fetch": (C.c_int, [vp, C.c_int, vp, i64]),
         "goldq_timer_start": (C.c_int, [vp]),
         "goldq_timer_stop": (C.c_int, [vp, fp]),
+        "goldq_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, fp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -127,6 +129,17 @@ def sampler_indices(length, batch, seed, replica=0):
     rc = lib().goldq_sampler_indices(length, batch, seed, replica, out.ctypes.data_as(C.POINTER(C.c_int32)))
     if rc:
         raise GoldqError(rc, "sampler_indices: bad argument")
+    return out
+
+
+def selftest_umma(mode, A_bits, B_bits, M, N, K, nsplit=1):
+    """A_bits/B_bits: uint16 bf16 bit patterns in the layout `mode` expects."""
+    A_bits = np.ascontiguousarray(A_bits, np.uint16)
+    B_bits = np.ascontiguousarray(B_bits, np.uint16)
+    out = np.empty((M, N), np.float32)
+    rc = lib().goldq_selftest_umma(mode, M, N, K, nsplit, A_bits.ctypes.data, B_bits.ctypes.data, _f(out))
+    if rc:
+        raise GoldqError(rc, lib().goldq_last_error(None).decode())
     return out
 
 

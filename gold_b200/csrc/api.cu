@@ -938,6 +938,14 @@ int goldq_timer_stop(goldq_t *h, float *ms)
     return GOLDQ_OK;
 }
 
+int goldq_selftest_umma(int mode, int M, int N, int K, int nsplit, const uint16_t *A, const uint16_t *B, float *C)
+{
+    std::string err;
+    int rc = wide_selftest_gemm(mode, M, N, K, nsplit, A, B, C, err);
+    if (rc) return fail(nullptr, GOLDQ_ECUDA, err);
+    return GOLDQ_OK;
+}
+
 /* Host-side mirror of the device sampler: the indices goldq_learn(h, NULL, seed)
  * draws for replica `replica` when the replay holds `len` events. */
 int goldq_sampler_indices(int64_t len, int32_t batch, uint64_t seed, int32_t replica, int32_t *out)

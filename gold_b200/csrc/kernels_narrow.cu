@@ -239,14 +239,21 @@ narrow_learn_kernel(NarrowArgs p)
     }
 
     // ---- last CTA of this replica: reduce, loss, K5 Adam ----------------------------
-    const float *allpart = p.partial + (int64_t)rep * ctas * P1;
+    // Cross-CTA sum in a fixed order, with the loads spread over the whole CTA:
+    // warp w sums the partials of CTAs w, w+nwarps, ... (independent coalesced loads),
+    // then the per-warp sums are added in warp order.
+    if (ctas > 1) {
+        const float *allpart = p.partial + (int64_t)rep * ctas * P1;
+        for (int i = lane; i < P1; i += 32) {
+            float g = 0.f;
+            for (int c = warp; c < ctas; c += nwarps) g += __ldcg(allpart + (int64_t)c * P1 + i);
+            sPart[warp * P1 + i] = g;
+        }
+        __syncthreads();
+    }
     for (int i = tid; i < P1; i += blockDim.x) {
         float g = 0.f;
-        if (ctas > 1) {
-            for (int c = 0; c < ctas; c++) g += __ldcg(allpart + (int64_t)c * P1 + i);
-        } else {
-            for (int w = 0; w < nwarps; w++) g += sPart[w * P1 + i];
-        }
+        for (int w = 0; w < nwarps; w++) g += sPart[w * P1 + i];
         if (i == P) {
             g = __fdiv_rn(g, p.sc.count);
             p.loss[rep] = g;

@@ -28,5 +28,7 @@ int wide_forward_backward(WideState *w, const WideStep &s, cudaStream_t st, std:
 void wide_set_debug(WideState *w, bool on);
 void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const float **td);
 const uint8_t *wide_done_ptr(WideState *w);
+int wide_selftest_gemm(int mode, int M, int N, int K, int nsplit, const uint16_t *A, const uint16_t *B, float *C,
+                       std::string &err);
 
 }  // namespace gq

@@ -182,6 +182,11 @@ int goldq_debug_fetch(goldq_t *h, int what, void *out, int64_t out_bytes);
 /* CUDA-event timer on the handle's stream (bench.py): start; ...; stop → ms. */
 int goldq_timer_start(goldq_t *h);
 int goldq_timer_stop(goldq_t *h, float *ms);
+/* Diagnostic: run one stand-alone tcgen05 GEMM on device 0 and return fp32 C[M][N].
+ * A, B are bf16 bit patterns.  mode 0: C = A[M][K] . B[N][K]^T (both K-major);
+ * mode 1: C = A[K][M]^T . B[K][N] (both MN-major); mode 2: mode 0 with the 32-wide
+ * N tile.  nsplit > 1 exercises the split-K slices.  Used by tests/test_gpu_umma.py. */
+int goldq_selftest_umma(int mode, int M, int N, int K, int nsplit, const uint16_t *A, const uint16_t *B, float *C);
 
 #ifdef __cplusplus
 }
