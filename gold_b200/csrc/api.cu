@@ -521,10 +521,11 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
         narrow_plan(a, h->sm_count);
         h->n_ctas = a.ctas_per_replica;
         h->n_warps = a.warps_per_cta;
-        ok &= dalloc(&h->partial, (size_t)h->R * h->n_ctas * (h->P + 1)) == cudaSuccess;
-        ok &= dalloc(&h->ticket, (size_t)h->R) == cudaSuccess;
+        size_t nt = (size_t)h->R * (NARROW_MAX_GROUPS + 1);
+        ok &= dalloc(&h->partial, (size_t)h->R * narrow_partial_floats(h->n_ctas, h->P)) == cudaSuccess;
+        ok &= dalloc(&h->ticket, nt) == cudaSuccess;
         if (!ok) return bail("cudaMalloc failed (narrow scratch)");
-        cudaMemsetAsync(h->ticket, 0, (size_t)h->R * sizeof(unsigned), h->st);
+        cudaMemsetAsync(h->ticket, 0, nt * sizeof(unsigned), h->st);
     } else if (path == GOLDQ_PATH_WIDE) {
         std::string err;
         h->wide = wide_create(h->dims, h->B, h->sm_count, err);

@@ -89,7 +89,10 @@ void launch_adam(float *w, const float *g, float *m, float *v, int64_t n, AdamCo
 void launch_argmax_rows(const float *q, int n, int A, int32_t *out, cudaStream_t st);
 
 // ---- narrow fused path (kernels_narrow.cu) --------------------------------
+#define NARROW_GROUP 8        // CTAs summed by one level-1 leader
+#define NARROW_MAX_GROUPS 64  // => at most 512 CTAs per replica
 bool narrow_supported(const Dims &d);
+size_t narrow_partial_floats(int ctas, int P);
 struct NarrowArgs {
     Dims dims;
     Replay rp;
@@ -100,8 +103,8 @@ struct NarrowArgs {
     float *theta;         // [R][P]
     const float *theta_t; // [R][P]
     float *m, *v;         // [R][P]
-    float *partial;       // [R][ctas][P+1] scratch
-    unsigned int *ticket; // [R] zero-initialised, self-resetting
+    float *partial;       // [R][ctas + groups][P+1] scratch
+    unsigned int *ticket; // [R][NARROW_MAX_GROUPS+1] zero-initialised, self-resetting
     float *flat;          // [R][P+1]: reduced gradient + loss (always written)
     float *loss;          // [R]
     int fuse_adam;        // 1: apply Adam in the same kernel; 0: stop at `flat` (data-parallel)

@@ -4,17 +4,18 @@
 // are launch-latency bound, not HBM or FLOP bound: the step moves 205 KB at
 // B = 4096.  So the design goal is one launch and no intermediate HBM traffic:
 //
-//   * one warp per sampled row, lane j = neuron j of the current layer; the
-//     activations of the previous layer are broadcast with warp shuffles, both
-//     networks' weights live in shared memory (6 KB), nothing but the replay row
-//     is read from HBM;
+//   * one warp per sampled row (two rows in flight per warp for latency hiding),
+//     lane j = neuron j of the current layer; the activations of the previous layer
+//     are broadcast with warp shuffles, both networks' weights live in shared
+//     memory (6 KB), nothing but the replay row is read from HBM;
 //   * the forward pass keeps gonum's arithmetic (k-sequential, multiply then add,
 //     reference: vendor/gonum.org/v1/gonum/blas/gonum/sgemm.go:258-270), so Q(s),
 //     Q'(s'), the first-max and the TD target are bit-identical to the CPU path;
 //   * each lane accumulates "its" column of every weight gradient in registers
 //     over the rows its warp handles: no atomics, no cross-lane reduction;
-//   * warps are reduced through shared memory, CTAs through a [ctas][P+1] scratch
-//     in a fixed order (deterministic); the last CTA to arrive sums the scratch,
+//   * warps are reduced through shared memory; CTAs through global scratch in two
+//     levels of "last arriver sums a fixed group in a fixed order" (deterministic):
+//     groups of NARROW_GROUP CTAs, then the groups.  The CTA that finishes last also
 //     finishes the loss and applies the fused Adam update in the same launch.
 //
 // Replicas (independent agents) are blockIdx.y: same kernel, own
@@ -44,6 +45,8 @@ __device__ __forceinline__ void adam_update_n(float &w, float g, float &m, float
 }
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int NR = 2;          // rows in flight per warp
+constexpr int MIN_WARPS = 4;   // the tail keeps ELEMS sums per thread in registers
 
 template <int D, int H1, int H2, int A>
 __global__ void __launch_bounds__(512)
@@ -53,16 +56,21 @@ narrow_learn_kernel(NarrowArgs p)
     constexpr int oW1 = 0, oB1 = oW1 + D * H1, oW2 = oB1 + H1, oB2 = oW2 + H1 * H2,
                   oW3 = oB2 + H2, oB3 = oW3 + H2 * A, P = oB3 + A;
     constexpr int P1 = P + 1;
+    constexpr int GROUP = NARROW_GROUP;
+    constexpr int ELEMS = (P1 + MIN_WARPS * 32 - 1) / (MIN_WARPS * 32);
 
     extern __shared__ float smem[];
     float *sOn = smem;             // online parameters, flat
     float *sTg = sOn + P;          // target parameters, flat
     float *sW2T = sTg + P;         // online W2 transposed [H2][H1] (for dh1)
     float *sPart = sW2T + H1 * H2; // [warps][P1] per-warp gradient partials
-    __shared__ int sIsLast;
+    __shared__ int sFlag;
 
     const int rep = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // shuffled from lane 0 so that the compiler knows it is warp-uniform (no
+    // convergence barriers around the shuffles in the row loop)
+    const int warp = __shfl_sync(FULL, tid >> 5, 0);
     const int nwarps = blockDim.x >> 5;
     const int64_t pofs = (int64_t)rep * P;
 
@@ -96,108 +104,146 @@ narrow_learn_kernel(NarrowArgs p)
     for (int k = 0; k < A; k++) gW3[k] = 0.f;
 
     const int total_warps = gridDim.x * nwarps;
-    for (int b = blockIdx.x * nwarps + warp; b < p.B; b += total_warps) {
+    const int gw = blockIdx.x * nwarps + warp;
+    // warp `gw` owns rows gw, gw + total_warps, ...; NR of them are processed together
+    for (int b0 = gw; b0 < p.B; b0 += NR * total_warps) {
         // ---- K1: sample / gather -------------------------------------------------
-        int32_t li;
-        if (p.idx) li = p.idx[(int64_t)rep * p.B + b];
-        else li = (int32_t)perm_index((uint32_t)b, (uint32_t)p.rp.len,
-                                      p.seed + 0x9E3779B97F4A7C15ull * (uint64_t)rep);
-        int64_t phys = p.rp.head - 1 - (int64_t)li;
-        if (phys < 0) phys += p.rp.cap;
-        float x = 0.f, x2 = 0.f;
-        if (lane < D) {
-            x = __ldg(rs + phys * D + lane);
-            x2 = __ldg(rs2 + phys * D + lane);
+        float x[NR], x2[NR], rew[NR];
+        int act[NR], dn[NR], li[NR];
+        bool live[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            const int b = b0 + r * total_warps;
+            live[r] = b < p.B;
+            const int bb = live[r] ? b : b0;
+            if (p.idx) li[r] = p.idx[(int64_t)rep * p.B + bb];
+            else li[r] = (int32_t)perm_index((uint32_t)bb, (uint32_t)p.rp.len,
+                                             p.seed + 0x9E3779B97F4A7C15ull * (uint64_t)rep);
         }
-        const int act = __ldg(ra + phys);
-        const float rew = __ldg(rr + phys);
-        const int dn = __ldg(rd + phys);
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            int64_t phys = p.rp.head - 1 - (int64_t)li[r];
+            if (phys < 0) phys += p.rp.cap;
+            x[r] = 0.f; x2[r] = 0.f;
+            if (lane < D) {
+                x[r] = __ldg(rs + phys * D + lane);
+                x2[r] = __ldg(rs2 + phys * D + lane);
+            }
+            act[r] = __ldg(ra + phys);
+            rew[r] = __ldg(rr + phys);
+            dn[r] = __ldg(rd + phys);
+        }
 
-        // ---- K2: forward, online on s and target on s' interleaved ---------------
-        float z = 0.f, zt = 0.f;
+        // ---- K2: forward, online on s and target on s' (2*NR independent chains) ----
+        float z[NR], zt[NR], h1[NR], h1t[NR], mk1[NR], h2[NR], h2t[NR], mk2[NR], q[NR], qt[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) { z[r] = 0.f; zt[r] = 0.f; }
 #pragma unroll
         for (int k = 0; k < D; k++) {
-            float xk = __shfl_sync(FULL, x, k), xk2 = __shfl_sync(FULL, x2, k);
-            z = __fadd_rn(z, __fmul_rn(xk, sOn[oW1 + k * H1 + j1]));
-            zt = __fadd_rn(zt, __fmul_rn(xk2, sTg[oW1 + k * H1 + j1]));
+            const float w = sOn[oW1 + k * H1 + j1], wt = sTg[oW1 + k * H1 + j1];
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                z[r] = __fadd_rn(z[r], __fmul_rn(__shfl_sync(FULL, x[r], k), w));
+                zt[r] = __fadd_rn(zt[r], __fmul_rn(__shfl_sync(FULL, x2[r], k), wt));
+            }
         }
-        float a1 = __fadd_rn(z, sOn[oB1 + j1]);
-        float a1t = __fadd_rn(zt, sTg[oB1 + j1]);
-        // Rectify: h = a * (a >= 0 ? 1 : 0)   (vendor/gorgonia.org/gorgonia/nn.go:162-189)
-        const float mk1 = (in1 && a1 >= 0.f) ? 1.f : 0.f;
-        float h1 = in1 ? __fmul_rn(a1, mk1) : 0.f;
-        float h1t = in1 ? __fmul_rn(a1t, (a1t >= 0.f) ? 1.f : 0.f) : 0.f;
-
-        z = 0.f; zt = 0.f;
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            const float a1 = __fadd_rn(z[r], sOn[oB1 + j1]);
+            const float a1t = __fadd_rn(zt[r], sTg[oB1 + j1]);
+            // Rectify: h = a * (a >= 0 ? 1 : 0)   (vendor/gorgonia.org/gorgonia/nn.go:162-189)
+            mk1[r] = (in1 && a1 >= 0.f) ? 1.f : 0.f;
+            h1[r] = in1 ? __fmul_rn(a1, mk1[r]) : 0.f;
+            h1t[r] = in1 ? __fmul_rn(a1t, (a1t >= 0.f) ? 1.f : 0.f) : 0.f;
+            z[r] = 0.f; zt[r] = 0.f;
+        }
 #pragma unroll
         for (int k = 0; k < H1; k++) {
-            float hk = __shfl_sync(FULL, h1, k), hkt = __shfl_sync(FULL, h1t, k);
-            z = __fadd_rn(z, __fmul_rn(hk, sOn[oW2 + k * H2 + j2]));
-            zt = __fadd_rn(zt, __fmul_rn(hkt, sTg[oW2 + k * H2 + j2]));
+            const float w = sOn[oW2 + k * H2 + j2], wt = sTg[oW2 + k * H2 + j2];
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                z[r] = __fadd_rn(z[r], __fmul_rn(__shfl_sync(FULL, h1[r], k), w));
+                zt[r] = __fadd_rn(zt[r], __fmul_rn(__shfl_sync(FULL, h1t[r], k), wt));
+            }
         }
-        float a2 = __fadd_rn(z, sOn[oB2 + j2]);
-        float a2t = __fadd_rn(zt, sTg[oB2 + j2]);
-        const float mk2 = (in2 && a2 >= 0.f) ? 1.f : 0.f;
-        float h2 = in2 ? __fmul_rn(a2, mk2) : 0.f;
-        float h2t = in2 ? __fmul_rn(a2t, (a2t >= 0.f) ? 1.f : 0.f) : 0.f;
-
-        z = 0.f; zt = 0.f;
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            const float a2 = __fadd_rn(z[r], sOn[oB2 + j2]);
+            const float a2t = __fadd_rn(zt[r], sTg[oB2 + j2]);
+            mk2[r] = (in2 && a2 >= 0.f) ? 1.f : 0.f;
+            h2[r] = in2 ? __fmul_rn(a2, mk2[r]) : 0.f;
+            h2t[r] = in2 ? __fmul_rn(a2t, (a2t >= 0.f) ? 1.f : 0.f) : 0.f;
+            z[r] = 0.f; zt[r] = 0.f;
+        }
 #pragma unroll
         for (int k = 0; k < H2; k++) {
-            float hk = __shfl_sync(FULL, h2, k), hkt = __shfl_sync(FULL, h2t, k);
-            z = __fadd_rn(z, __fmul_rn(hk, sOn[oW3 + k * A + jA]));
-            zt = __fadd_rn(zt, __fmul_rn(hkt, sTg[oW3 + k * A + jA]));
+            const float w = sOn[oW3 + k * A + jA], wt = sTg[oW3 + k * A + jA];
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                z[r] = __fadd_rn(z[r], __fmul_rn(__shfl_sync(FULL, h2[r], k), w));
+                zt[r] = __fadd_rn(zt[r], __fmul_rn(__shfl_sync(FULL, h2t[r], k), wt));
+            }
         }
-        const float q = __fadd_rn(z, sOn[oB3 + jA]);     // lane a < A holds Q(s)[a]
-        const float qt = __fadd_rn(zt, sTg[oB3 + jA]);   // lane a < A holds Q'(s')[a]
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            q[r] = __fadd_rn(z[r], sOn[oB3 + jA]);    // lane a < A holds Q(s)[a]
+            qt[r] = __fadd_rn(zt[r], sTg[oB3 + jA]);  // lane a < A holds Q'(s')[a]
+        }
 
         // ---- K3: first-max (ArgmaxF32 rules), TD target, dQ ----------------------
-        float f = __shfl_sync(FULL, qt, 0);
-        bool decided = false;
+        float dqv[NR];
 #pragma unroll
-        for (int i = 1; i < A; i++) {
-            float v = __shfl_sync(FULL, qt, i);
-            if (!decided) {
-                if (isnan(v) || (isinf(v) && v > 0.f)) { f = v; decided = true; }
-                else if (v > f) f = v;
+        for (int r = 0; r < NR; r++) {
+            float f = __shfl_sync(FULL, qt[r], 0);
+            bool decided = false;
+#pragma unroll
+            for (int i = 1; i < A; i++) {
+                float v = __shfl_sync(FULL, qt[r], i);
+                if (!decided) {
+                    if (isnan(v) || (isinf(v) && v > 0.f)) { f = v; decided = true; }
+                    else if (v > f) f = v;
+                }
+            }
+            float t = rew[r];
+            if (!dn[r]) t = __fadd_rn(rew[r], __fmul_rn(p.sc.gamma, f));   // agent.go:149
+            const float qa = __shfl_sync(FULL, q[r], act[r]);
+            const float d = __fsub_rn(qa, t);
+            dqv[r] = live[r] ? __fmul_rn(__fmul_rn(d, 2.f), p.sc.inv_count) : 0.f;
+            if (live[r]) lossacc = __fadd_rn(lossacc, __fmul_rn(d, d));
+            if (p.dbg_q && live[r]) {
+                const int b = b0 + r * total_warps;
+                if (inA) {
+                    p.dbg_q[((int64_t)rep * p.B + b) * A + lane] = q[r];
+                    p.dbg_qt[((int64_t)rep * p.B + b) * A + lane] = dn[r] ? 0.f : qt[r];
+                }
+                if (lane == 0) {
+                    p.dbg_td[(int64_t)rep * p.B + b] = t;
+                    p.dbg_idx[(int64_t)rep * p.B + b] = li[r];
+                }
             }
         }
-        float t = rew;
-        if (!dn) t = __fadd_rn(rew, __fmul_rn(p.sc.gamma, f));   // agent.go:149
-        const float qa = __shfl_sync(FULL, q, act);
-        const float d = __fsub_rn(qa, t);
-        lossacc = __fadd_rn(lossacc, __fmul_rn(d, d));
-        const float dqv = __fmul_rn(__fmul_rn(d, 2.f), p.sc.inv_count);
 
-        if (p.dbg_q) {
-            if (inA) {
-                p.dbg_q[((int64_t)rep * p.B + b) * A + lane] = q;
-                p.dbg_qt[((int64_t)rep * p.B + b) * A + lane] = dn ? 0.f : qt;
-            }
-            if (lane == 0) {
-                p.dbg_td[(int64_t)rep * p.B + b] = t;
-                p.dbg_idx[(int64_t)rep * p.B + b] = li;
-            }
+        // ---- K4: backward (a dead row has dqv = 0 and contributes exact zeros) -----
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            // layer 3: dW3[j][a] = h2[j]*dq[a]; db3 = dq; dh2[j] = dq[act]*W3[j][act]
+            if (lane == act[r]) gb3 += dqv[r];
+#pragma unroll
+            for (int a = 0; a < A; a++) gW3[a] += (a == act[r]) ? h2[r] * dqv[r] : 0.f;
+            const float dz2 = __fmul_rn(__fmul_rn(dqv[r], sOn[oW3 + j2 * A + act[r]]), mk2[r]);
+            // layer 2: dW2[i][j] += h1[i]*dz2[j]; dh1[i] = sum_j dz2[j]*W2[i][j]
+            gb2 += dz2;
+            float dh1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < H1; k++) gW2[k] = fmaf(__shfl_sync(FULL, h1[r], k), dz2, gW2[k]);
+#pragma unroll
+            for (int k = 0; k < H2; k++) dh1 = fmaf(__shfl_sync(FULL, dz2, k), sW2T[k * H1 + j1], dh1);
+            const float dz1 = __fmul_rn(dh1, mk1[r]);
+            // layer 1: dW1[k][j] += x[k]*dz1[j]
+            gb1 += dz1;
+#pragma unroll
+            for (int k = 0; k < D; k++) gW1[k] = fmaf(__shfl_sync(FULL, x[r], k), dz1, gW1[k]);
         }
-
-        // ---- K4: backward --------------------------------------------------------
-        // layer 3: dW3[j][a] = h2[j]*dq[a]; db3 = dq; dh2[j] = dq[act]*W3[j][act]
-        if (lane == act) gb3 += dqv;
-#pragma unroll
-        for (int a = 0; a < A; a++) gW3[a] += (a == act) ? h2 * dqv : 0.f;
-        const float dz2 = __fmul_rn(__fmul_rn(dqv, sOn[oW3 + j2 * A + act]), mk2);
-        // layer 2: dW2[i][j] += h1[i]*dz2[j]; dh1[i] = sum_j dz2[j]*W2[i][j]
-        gb2 += dz2;
-        float dh1 = 0.f;
-#pragma unroll
-        for (int k = 0; k < H1; k++) gW2[k] = fmaf(__shfl_sync(FULL, h1, k), dz2, gW2[k]);
-#pragma unroll
-        for (int k = 0; k < H2; k++) dh1 = fmaf(__shfl_sync(FULL, dz2, k), sW2T[k * H1 + j1], dh1);
-        const float dz1 = __fmul_rn(dh1, mk1);
-        // layer 1: dW1[k][j] += x[k]*dz1[j]
-        gb1 += dz1;
-#pragma unroll
-        for (int k = 0; k < D; k++) gW1[k] = fmaf(__shfl_sync(FULL, x, k), dz1, gW1[k]);
     }
 
     // ---- warp partials -> shared ---------------------------------------------------
@@ -218,42 +264,86 @@ narrow_learn_kernel(NarrowArgs p)
     if (lane == 0) mine[P] = lossacc;
     __syncthreads();
 
-    const int ctas = gridDim.x;
-    float *gpart = p.partial + ((int64_t)rep * ctas + blockIdx.x) * P1;
-    float *flat = p.flat + (int64_t)rep * P1;
-    if (ctas > 1) {
-        for (int i = tid; i < P1; i += blockDim.x) {
-            float s = 0.f;
+    // CTA sum in warp order, kept in registers (thread t owns elements t, t+blockDim, ...)
+    float mysum[ELEMS];
+#pragma unroll
+    for (int e = 0; e < ELEMS; e++) {
+        const int i = tid + e * blockDim.x;
+        float s = 0.f;
+        if (i < P1)
             for (int w = 0; w < nwarps; w++) s += sPart[w * P1 + i];
-            gpart[i] = s;
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            unsigned tk = atomicAdd(p.ticket + rep, 1u);
-            sIsLast = (tk == (unsigned)(ctas - 1));
-        }
-        __syncthreads();
-        if (!sIsLast) return;
-        __threadfence();
+        mysum[e] = s;
     }
 
-    // ---- last CTA of this replica: reduce, loss, K5 Adam ----------------------------
-    // Cross-CTA sum in a fixed order, with the loads spread over the whole CTA:
-    // warp w sums the partials of CTAs w, w+nwarps, ... (independent coalesced loads),
-    // then the per-warp sums are added in warp order.
+    const int ctas = gridDim.x;
+    float *flat = p.flat + (int64_t)rep * P1;
     if (ctas > 1) {
-        const float *allpart = p.partial + (int64_t)rep * ctas * P1;
-        for (int i = lane; i < P1; i += 32) {
-            float g = 0.f;
-            for (int c = warp; c < ctas; c += nwarps) g += __ldcg(allpart + (int64_t)c * P1 + i);
-            sPart[warp * P1 + i] = g;
+        // ---- level 1: the last CTA of each group of GROUP sums the group in order -----
+        const int ngroups = (ctas + GROUP - 1) / GROUP;
+        const int grp = blockIdx.x / GROUP;
+        const int gfirst = grp * GROUP;
+        const int gsize = min(GROUP, ctas - gfirst);
+        float *part1 = p.partial + (int64_t)rep * (ctas + ngroups) * P1;   // [ctas][P1]
+        float *part2 = part1 + (int64_t)ctas * P1;                         // [ngroups][P1]
+        unsigned int *tick1 = p.ticket + (int64_t)rep * (NARROW_MAX_GROUPS + 1);
+        unsigned int *tick2 = tick1 + NARROW_MAX_GROUPS;
+#pragma unroll
+        for (int e = 0; e < ELEMS; e++) {
+            const int i = tid + e * blockDim.x;
+            if (i < P1) part1[(int64_t)blockIdx.x * P1 + i] = mysum[e];
         }
+        __threadfence();
         __syncthreads();
+        if (tid == 0) sFlag = (atomicAdd(tick1 + grp, 1u) == (unsigned)(gsize - 1));
+        __syncthreads();
+        if (!sFlag) return;
+        __threadfence();
+#pragma unroll
+        for (int e = 0; e < ELEMS; e++) {
+            const int i = tid + e * blockDim.x;
+            float v[GROUP];
+#pragma unroll
+            for (int c = 0; c < GROUP; c++)
+                v[c] = (i < P1 && c < gsize) ? __ldcg(part1 + (int64_t)(gfirst + c) * P1 + i) : 0.f;
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < GROUP; c++) s += v[c];
+            mysum[e] = s;
+            if (i < P1) part2[(int64_t)grp * P1 + i] = s;
+        }
+        if (tid == 0) tick1[grp] = 0u;
+        // ---- level 2: the last group leader sums the groups in order --------------------
+        if (ngroups > 1) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) sFlag = (atomicAdd(tick2, 1u) == (unsigned)(ngroups - 1));
+            __syncthreads();
+            if (!sFlag) return;
+            __threadfence();
+#pragma unroll
+            for (int e = 0; e < ELEMS; e++) {
+                const int i = tid + e * blockDim.x;
+                float s = 0.f;
+                for (int g0 = 0; g0 < ngroups; g0 += GROUP) {
+                    float v[GROUP];
+#pragma unroll
+                    for (int c = 0; c < GROUP; c++)
+                        v[c] = (i < P1 && g0 + c < ngroups) ? __ldcg(part2 + (int64_t)(g0 + c) * P1 + i) : 0.f;
+#pragma unroll
+                    for (int c = 0; c < GROUP; c++) s += v[c];
+                }
+                mysum[e] = s;
+            }
+            if (tid == 0) *tick2 = 0u;
+        }
     }
-    for (int i = tid; i < P1; i += blockDim.x) {
-        float g = 0.f;
-        for (int w = 0; w < nwarps; w++) g += sPart[w * P1 + i];
+
+    // ---- the last CTA of this replica: loss, K5 Adam --------------------------------
+#pragma unroll
+    for (int e = 0; e < ELEMS; e++) {
+        const int i = tid + e * blockDim.x;
+        if (i >= P1) continue;
+        float g = mysum[e];
         if (i == P) {
             g = __fdiv_rn(g, p.sc.count);
             p.loss[rep] = g;
@@ -269,7 +359,6 @@ narrow_learn_kernel(NarrowArgs p)
             }
         }
     }
-    if (tid == 0 && ctas > 1) p.ticket[rep] = 0u;
 }
 
 template <int D, int H1, int H2, int A>
@@ -298,17 +387,24 @@ bool narrow_supported(const Dims &d)
 
 void narrow_plan(NarrowArgs &a, int sm_count)
 {
-    int need = (a.B + 1) / 2;  // two rows per warp
+    int need = (a.B + NR - 1) / NR;  // NR rows per warp
     int max_ctas = (2 * sm_count) / (a.replicas > 0 ? a.replicas : 1);
     if (max_ctas < 1) max_ctas = 1;
+    if (max_ctas > NARROW_GROUP * NARROW_MAX_GROUPS) max_ctas = NARROW_GROUP * NARROW_MAX_GROUPS;
     int ctas = (need + 15) / 16;
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
     int warps = (need + ctas - 1) / ctas;
     if (warps > 16) warps = 16;
-    if (warps < 1) warps = 1;
+    if (warps < MIN_WARPS) warps = MIN_WARPS;
     a.ctas_per_replica = ctas;
     a.warps_per_cta = warps;
+}
+
+size_t narrow_partial_floats(int ctas, int P)
+{
+    int ngroups = (ctas + NARROW_GROUP - 1) / NARROW_GROUP;
+    return (size_t)(ctas + ngroups) * (P + 1);
 }
 
 void launch_narrow_learn(const NarrowArgs &a, cudaStream_t st)

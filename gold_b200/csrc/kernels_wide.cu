@@ -401,6 +401,7 @@ wide_td_kernel(const float *__restrict__ q, const float *__restrict__ qt, const 
     __syncthreads();
     for (int j = tid; j < H2; j += blockDim.x) {
         float db2 = 0.f;
+#pragma unroll 8
         for (int rr = 0; rr < nrows; rr++) {
             const int b = r0 + rr;
             const float dqv = sRow[rr];
@@ -432,46 +433,85 @@ wide_td_kernel(const float *__restrict__ q, const float *__restrict__ qt, const 
     }
 }
 
-// db1 partials: column sums of dZ1 (bf16 [B][H1]) over CS_ROWS-row ranges
+// db1 partials: column sums of dZ1 (bf16 [B][H1]) over CS_ROWS-row ranges.  A warp covers
+// 64 columns (one bfloat162 per lane), the 8 warps of a block take interleaved rows with
+// 8 independent loads in flight each; warps are then summed in order through smem.
 constexpr int CS_ROWS = 256;
 __global__ void __launch_bounds__(256)
 wide_colsum_kernel(const __nv_bfloat16 *__restrict__ dz, int B, int H, float *__restrict__ part /* [blocks.y][H] */)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= H) return;
+    __shared__ float2 sh[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 64 + lane * 2;
     const int r0 = blockIdx.y * CS_ROWS, r1 = min(B, r0 + CS_ROWS);
-    float s = 0.f;
-    for (int b = r0; b < r1; b++) s += __bfloat162float(dz[(int64_t)b * H + j]);
-    part[(int64_t)blockIdx.y * H + j] = s;
+    float2 s = make_float2(0.f, 0.f);
+    if (j < H) {
+        for (int b = r0 + warp; b < r1; b += 64) {
+            __nv_bfloat162 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int bb = b + 8 * u;
+                v[u] = (bb < r1) ? *reinterpret_cast<const __nv_bfloat162 *>(dz + (int64_t)bb * H + j)
+                                 : __floats2bfloat162_rn(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                float2 f = __bfloat1622float2(v[u]);
+                s.x += f.x;
+                s.y += f.y;
+            }
+        }
+    }
+    sh[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && j < H) {
+        float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < 8; w++) { t.x += sh[w][lane].x; t.y += sh[w][lane].y; }
+        part[(int64_t)blockIdx.y * H + j] = t.x;
+        if (j + 1 < H) part[(int64_t)blockIdx.y * H + j + 1] = t.y;
+    }
 }
 
-// flat[P+1] = fixed-order sums of all partial buffers; flat[P] = loss
+// flat[P+1] = fixed-order sums of all partial buffers; flat[P] = loss.
+// Block = 32 elements x 8 partial-chunks: thread (x, y) sums partials y, y+8, ... with the
+// loads issued in batches of 4, then the 8 chunk sums are added in order.
 __global__ void __launch_bounds__(256)
 wide_reduce_kernel(Dims d, Offsets o, const float *__restrict__ w1_slices, int n1, const float *__restrict__ w2_slices,
                    int n2, const float *__restrict__ b1_part, int nb1, const float *__restrict__ td_part, int ntd,
                    float count, float *__restrict__ flat)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float sh[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + x;
     const int tdw = d.H2 * d.A + d.H2 + d.A + 1;
-    if (i > o.P) return;
+    const float *base = nullptr;
+    int n = 0;
+    int64_t stride = 0;
+    if (i < o.b1) { base = w1_slices + i; n = n1; stride = (int64_t)d.D * d.H1; }
+    else if (i < o.w2) { base = b1_part + (i - o.b1); n = nb1; stride = d.H1; }
+    else if (i < o.b2) { base = w2_slices + (i - o.w2); n = n2; stride = (int64_t)d.H1 * d.H2; }
+    else if (i < o.w3) { base = td_part + d.H2 * d.A + (i - o.b2); n = ntd; stride = tdw; }
+    else if (i < o.b3) { base = td_part + (i - o.w3); n = ntd; stride = tdw; }
+    else if (i < o.P) { base = td_part + d.H2 * d.A + d.H2 + (i - o.b3); n = ntd; stride = tdw; }
+    else if (i == o.P) { base = td_part + d.H2 * d.A + d.H2 + d.A; n = ntd; stride = tdw; }
     float s = 0.f;
-    if (i < o.b1) {
-        for (int z = 0; z < n1; z++) s += w1_slices[(int64_t)z * (d.D * d.H1) + i];
-    } else if (i < o.w2) {
-        for (int z = 0; z < nb1; z++) s += b1_part[(int64_t)z * d.H1 + (i - o.b1)];
-    } else if (i < o.b2) {
-        for (int z = 0; z < n2; z++) s += w2_slices[(int64_t)z * (d.H1 * d.H2) + (i - o.w2)];
-    } else if (i < o.w3) {
-        for (int z = 0; z < ntd; z++) s += td_part[(int64_t)z * tdw + d.H2 * d.A + (i - o.b2)];
-    } else if (i < o.b3) {
-        for (int z = 0; z < ntd; z++) s += td_part[(int64_t)z * tdw + (i - o.w3)];
-    } else if (i < o.P) {
-        for (int z = 0; z < ntd; z++) s += td_part[(int64_t)z * tdw + d.H2 * d.A + d.H2 + (i - o.b3)];
-    } else {
-        for (int z = 0; z < ntd; z++) s += td_part[(int64_t)z * tdw + d.H2 * d.A + d.H2 + d.A];
-        s = __fdiv_rn(s, count);
+    for (int z = y; z < n; z += 32) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = (z + 8 * u < n) ? __ldg(base + (int64_t)(z + 8 * u) * stride) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; u++) s += v[u];
     }
-    flat[i] = s;
+    sh[y][x] = s;
+    __syncthreads();
+    if (y == 0 && i <= o.P) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += sh[w][x];
+        if (i == o.P) t = __fdiv_rn(t, count);
+        flat[i] = t;
+    }
 }
 
 template <typename T>
@@ -696,11 +736,11 @@ int wide_forward_backward(WideState *w, const WideStep &s, cudaStream_t st, std:
     g.out_f32 = w->w1_slices; g.ldo = d.H1; g.n_store = d.H1; g.slice_stride = (long long)d.D * d.H1;
     WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_x_mm, w->tm_dz1_mm, g, w->ns1, st)));
     {
-        dim3 grid((d.H1 + 255) / 256, w->nb1);
+        dim3 grid((d.H1 + 63) / 64, w->nb1);
         wide_colsum_kernel<<<grid, 256, 0, st>>>(w->dz1, B, d.H1, w->b1_part);
         WCK(cudaGetLastError());
     }
-    wide_reduce_kernel<<<(o.P + 1 + 255) / 256, 256, 0, st>>>(d, o, w->w1_slices, w->ns1, w->w2_slices, w->ns2, w->b1_part,
+    wide_reduce_kernel<<<(o.P + 1 + 31) / 32, 256, 0, st>>>(d, o, w->w1_slices, w->ns1, w->w2_slices, w->ns2, w->b1_part,
                                                            w->nb1, w->td_part, w->ntd, s.sc.count, s.flat);
     WCK(cudaGetLastError());
     launches += 5;

@@ -4,8 +4,9 @@ Stated tolerance (north_star: "bf16 wide configs within a stated 1e-2"):
   Q(s), Q'(s'), TD targets : |x - ref| <= 1e-2 * max|ref|      (bf16 operands, fp32 accumulate)
   loss                      : 2e-2 relative
   gradients                 : ||g - ref||_2 <= 2e-2 ||ref||_2 and elementwise 2e-2 * max|ref|
-  post-Adam parameters      : 1e-5 relative on well-conditioned elements (|g| >= 1e-2 max|g|),
-                              hard bound 2*lr*(1+|g|) on the rest (tests/util.py)
+  post-Adam parameters      : |w - ref| <= 1e-2 * max|ref| and inside Adam's hard bound 2*lr*(1+|g|)
+                              everywhere, > 80 % of elements within 1e-5 relative; the Adam kernel
+                              applied to the GPU's own gradient reproduces the reference solver to 1e-6
   greedy actions            : equal wherever the oracle's top-2 Q gap exceeds the Q tolerance
 """
 import numpy as np
@@ -13,7 +14,7 @@ import pytest
 
 from gold_b200 import _capi as G
 from gold_b200 import synth
-from util import OracleAgent, assert_params_close
+from util import OracleAgent
 
 pytestmark = pytest.mark.gpu
 
@@ -32,6 +33,7 @@ def make(dims, B, N):
 
 
 def check(h, o, idx):
+    w0, m0, v0, it0 = o.theta.copy(), o.m.copy(), o.v.copy(), o.iter
     out, out64 = o.learn(idx)
     h.learn(idx)
     q = h.debug_fetch(G.DBG_Q_ONLINE); qt = h.debug_fetch(G.DBG_Q_TARGET); td = h.debug_fetch(G.DBG_TD)
@@ -47,14 +49,25 @@ def check(h, o, idx):
     ref = out64["grads"]
     assert np.linalg.norm(g - ref) <= 2e-2 * np.linalg.norm(ref), np.linalg.norm(g - ref) / np.linalg.norm(ref)
     assert np.abs(g - ref).max() <= 2e-2 * np.abs(ref).max()
-    # per-block checks so that a broken small block (biases, W3) cannot hide in the norm
+    # per-block sanity so that a broken small block (biases, W3) cannot hide in the norm; the
+    # exact per-block check is test_wide_matches_bf16_emulation
     off = synth.offsets(o.dims)
     for name, (a, b) in off.items():
         nr = np.linalg.norm(ref[a:b])
-        assert np.linalg.norm(g[a:b] - ref[a:b]) <= 3e-2 * nr + 1e-12, (name, np.linalg.norm(g[a:b] - ref[a:b]) / nr)
+        assert np.linalg.norm(g[a:b] - ref[a:b]) <= 1e-1 * nr + 1e-12, (name, np.linalg.norm(g[a:b] - ref[a:b]) / nr)
     w = h.get_params(G.NET_ONLINE)
-    frac = assert_params_close(w, out64["theta"], ref, lr=o.lr, cond=1e-2, what="bf16 params")
-    assert frac < 0.25
+    # (i) the Adam kernel itself: applied to the GPU's own gradient it must reproduce the
+    #     reference solver (double update included) to fp32 rounding
+    from oracle import binding as O
+    w_chk = w0.copy(); m_chk = m0.copy(); v_chk = v0.copy()
+    O.adam(w_chk, h.debug_fetch(G.DBG_GRADS).copy(), m_chk, v_chk, it0 + 1, lr=o.lr)
+    np.testing.assert_allclose(w, w_chk, rtol=1e-6, atol=1e-8)
+    # (ii) against the fp64 oracle: every element inside Adam's hard bound, and within the
+    #      stated 1e-2 (relative to the weight scale); the bulk agrees to 1e-5
+    dw = np.abs(w - out64["theta"])
+    assert (dw <= 2 * o.lr * (1 + np.abs(ref)) + 1e-7).all()
+    assert dw.max() <= 1e-2 * np.abs(out64["theta"]).max()
+    assert np.mean(dw <= 1e-5 * np.abs(out64["theta"]) + 1e-7) > 0.80
     h.set_params(G.NET_ONLINE, o.theta)
     h.set_adam_state(o.m, o.v, o.iter)
 
@@ -67,6 +80,78 @@ def test_wide_bf16_learn_step(dims, B):
         check(h, o, synth.sample_indices(N, B, step))
         if step == 0:
             h.sync_target(); o.sync_target()
+    h.close()
+
+
+def _bf(x):
+    """round-to-nearest-even to bf16, returned as float64 values"""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint32) << 16
+    return r.astype(np.uint32).view(np.float32).astype(np.float64)
+
+
+def _emulate_bf16_step(dims, th, tt, s, a, r, s2, done, gamma, count):
+    """The wide path's arithmetic restated in numpy: bf16 roundings at exactly the points
+    where the kernels round (inputs, weights, activations, dZ), exact accumulation."""
+    D, H1, H2, A = dims
+    off = synth.offsets(dims)
+    def unpack(t):
+        g = lambda k, shape: t[off[k][0]:off[k][1]].astype(np.float64).reshape(shape)
+        return g("w1", (D, H1)), g("b1", (H1,)), g("w2", (H1, H2)), g("b2", (H2,)), g("w3", (H2, A)), g("b3", (A,))
+    def fwd(t, x):
+        w1, b1, w2, b2, w3, b3 = unpack(t)
+        a1 = _bf(x) @ _bf(w1) + b1
+        h1 = _bf(np.where(a1 >= 0, a1, 0.0)); m1 = a1 >= 0
+        a2 = h1 @ _bf(w2) + b2
+        h2 = _bf(np.where(a2 >= 0, a2, 0.0)); m2 = a2 >= 0
+        q = h2 @ _bf(w3) + b3
+        return _bf(x), h1, m1, h2, m2, q
+    x, h1, m1, h2, m2, q = fwd(th, s)
+    qt = fwd(tt, s2)[5].astype(np.float32)
+    g32 = np.float32(gamma)
+    td = np.where(done.astype(bool), r, (r + g32 * qt.max(axis=1)).astype(np.float32)).astype(np.float32)
+    B = len(a)
+    q32 = q.astype(np.float32)
+    d = (q32[np.arange(B), a] - td).astype(np.float32)
+    dqv = ((d * np.float32(2)) * (np.float32(1) / np.float32(count))).astype(np.float64)
+    w1, b1, w2, b2, w3, b3 = unpack(th)
+    dz2 = _bf(np.where(m2, dqv[:, None] * w3[:, a].T, 0.0))
+    gw3 = np.zeros((H2, A)); gb3 = np.zeros(A)
+    for act in range(A):
+        sel = a == act
+        gw3[:, act] = (h2[sel] * dqv[sel, None]).sum(axis=0)
+        gb3[act] = dqv[sel].sum()
+    gb2 = dz2.sum(axis=0)
+    gw2 = h1.T @ dz2
+    dz1 = _bf(np.where(m1, dz2 @ _bf(w2).T, 0.0))
+    gw1 = x.T @ dz1
+    gb1 = dz1.sum(axis=0)
+    grads = np.concatenate([gw1.ravel(), gb1, gw2.ravel(), gb2, gw3.ravel(), gb3])
+    loss = float((d.astype(np.float64) ** 2).sum() / count)
+    return q, qt, td, loss, grads
+
+
+@pytest.mark.parametrize("dims,B", [(synth.WIDE, 512), ((64, 256, 128, 6), 200)])
+def test_wide_matches_bf16_emulation(dims, B):
+    """Correctness independent of precision: against a numpy restatement that rounds to bf16
+    at the same points, every gradient block must agree to accumulation-order noise."""
+    N = 2 * B
+    h, o = make(dims, B, N)
+    idx = synth.sample_indices(N, B, 3)
+    s, a, r, s2, done = o.batch(idx)
+    q, qt, td, loss, grads = _emulate_bf16_step(dims, o.theta, o.theta_t, s, a, r, s2, done, o.gamma, B * dims[3])
+    h.learn(idx)
+    qg = h.debug_fetch(G.DBG_Q_ONLINE)
+    np.testing.assert_allclose(qg, q, rtol=1e-4, atol=1e-4 * np.abs(q).max())
+    # a rounding-boundary flip of one bf16 activation moves q by ~1e-3 relative at most
+    np.testing.assert_allclose(h.debug_fetch(G.DBG_TD), td, rtol=2e-3, atol=2e-3)
+    assert abs(float(h.last_loss()[0]) - loss) <= 5e-3 * loss
+    g = h.debug_fetch(G.DBG_GRADS).astype(np.float64)
+    off = synth.offsets(dims)
+    for name, (lo, hi) in off.items():
+        nr = np.linalg.norm(grads[lo:hi])
+        err = np.linalg.norm(g[lo:hi] - grads[lo:hi])
+        assert err <= 1e-2 * nr + 1e-12, (name, err / nr)
     h.close()
 
 
