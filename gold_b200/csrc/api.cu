@@ -320,28 +320,37 @@ int learn_narrow(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
     return check_launch(h, "learn_narrow");
 }
 
-int learn_wide(goldq_t *h, const int32_t *idx_dev)
+int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
 {
     WideStep ws{};
     ws.rp = h->rp;
     ws.idx = idx_dev;
+    ws.seed = seed;
+    ws.idx_out = h->d_idx;
     ws.B = h->B;
     ws.theta = h->theta;
     ws.theta_t = h->theta_t;
     ws.flat = h->flat;
     ws.sc = step_scalars(h, h->Bglobal);
-    std::string err;
-    int n = wide_forward_backward(h->wide, ws, h->st, err);
-    if (n < 0) return fail(h, GOLDQ_ECUDA, err);
-    h->launches += n;
-    int rc = allreduce_flat(h);
-    if (rc) return rc;
+    ws.fuse_update = h->world <= 1 ? 1 : 0;
+    ws.theta_rw = h->theta;
+    ws.m = h->m;
+    ws.v = h->v;
     h->iter += 1;
-    launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), h->st);
-    h->launches += 1;
-    n = wide_after_update(h->wide, h->theta, h->st, err);   // refresh the bf16 shadow of the online net
+    ws.adam = adam_consts(h->cfg, h->iter);
+    std::string err;
+    int n = wide_step(h->wide, ws, h->st, err);
     if (n < 0) return fail(h, GOLDQ_ECUDA, err);
     h->launches += n;
+    if (h->world > 1) {
+        int rc = allreduce_flat(h);
+        if (rc) return rc;
+        launch_adam(h->theta, h->flat, h->m, h->v, h->P, ws.adam, h->st);
+        h->launches += 1;
+        n = wide_after_update(h->wide, h->theta, h->st, err);   // refresh the bf16 shadow of the online net
+        if (n < 0) return fail(h, GOLDQ_ECUDA, err);
+        h->launches += n;
+    }
     CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
     return check_launch(h, "learn_wide");
 }
@@ -350,12 +359,12 @@ int run_learn(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
 {
     if (h->rp.len < h->B) return fail(h, GOLDQ_ENOTREADY, "replay shorter than batch");
     if (h->path == GOLDQ_PATH_NARROW) return learn_narrow(h, idx_dev, seed);
+    if (h->path == GOLDQ_PATH_WIDE) return learn_wide(h, idx_dev, seed);
     if (!idx_dev) {
         launch_sample_indices(h->d_idx, h->B, h->rp.len, seed, h->R, h->st);
         h->launches += 1;
         idx_dev = h->d_idx;
     }
-    if (h->path == GOLDQ_PATH_WIDE) return learn_wide(h, idx_dev);
     return learn_generic(h, idx_dev);
 }
 

@@ -10,16 +10,18 @@
 // of the weights is refreshed after every update.
 //
 // GEMM shapes per step (B rows):
-//   forward (both nets)  H1 = relu(X  W1 + b1)      KK mode  M=B   N=H1  K=D
-//                        H2 = relu(H1 W2 + b2)      KK       M=B   N=H2  K=H1
-//                        Q  =      H2 W3 + b3       KK, BN=32 M=B  N=A   K=H2
+//   forward (both nets)  H1 = relu(X  W1 + b1)      KM mode  M=B   N=H1  K=D
+//                        H2 = relu(H1 W2 + b2)      KM       M=B   N=H2  K=H1
+//                        Q  =      H2 W3 + b3       KM, BN=64 M=B  N=A   K=H2 (W3 padded to 64 columns)
 //   backward             dW2 = H1^T dZ2             MM mode  M=H1  N=H2  K=B (split-K)
 //                        dZ1 = (dZ2 W2^T) * mask1   KK       M=B   N=H1  K=H2
 //                        dW1 = X^T dZ1              MM       M=D   N=H1  K=B (split-K)
-//   layer 3's backward is rank-1 per row (dq has one non-zero per row: the taken
-//   action), so dW3/db3/dZ2 are computed on CUDA cores in wide_td_kernel.
+//                        dW3 = H2^T dQ              MK mode  M=H2  N=32  K=B (split-K), dQ^T [32][B]
+//   dQ has one non-zero per row (the taken action), so dZ2 = dq * W3[:,a] * mask2 is an
+//   elementwise kernel (wide_dz2_kernel), not a GEMM.
 // KK: both operands K-major (A [M][K], B [N][K] row-major).  MM: both MN-major
 // (A [K][M], B [K][N] row-major) — the activations are used as stored, no transposes.
+// MK: A MN-major, B K-major.  KM: A K-major, B MN-major (forward: W [in][out] as stored).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -42,19 +44,20 @@ constexpr int UK = 16;    // K of one tcgen05.mma for 16-bit inputs
 constexpr int STAGES = 3;
 constexpr int GEMM_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 
-enum { MODE_KK = 0, MODE_MM = 1 };
+enum { MODE_KK = 0, MODE_MM = 1, MODE_MK = 2, MODE_KM = 3 };
 enum { EPI_BIAS_RELU_BF16 = 0, EPI_BIAS_F32 = 1, EPI_MASK_BF16 = 2, EPI_F32_SLICE = 3 };
 
 struct GemmArgs {
     int M, N, K;          // logical problem (K = full reduction length)
-    int k_per_split;      // multiple of BK; blockIdx.z selects the range
-    // epilogue operands
-    __nv_bfloat16 *out_bf16;      // [M][ldo]
-    float *out_f32;               // [M][ldo] (+ blockIdx.z * slice_stride for EPI_F32_SLICE)
-    const float *bias;            // [N]
-    const __nv_bfloat16 *mask_src;// [M][ldo]: sign bit set <=> ReLU mask 0
-    int ldo;                      // row pitch of the output in elements
-    int n_store;                  // columns actually stored (<= N tile coverage)
+    int k_per_split;      // multiple of BK
+    int nsplit;           // blockIdx.z = problem * nsplit + split
+    // epilogue operands (problem 0 / problem 1: the online and the target network share one launch)
+    __nv_bfloat16 *out_bf16, *out_bf16_1;   // [M][ldo]
+    float *out_f32, *out_f32_1;             // [M][ldo] (+ split * slice_stride for EPI_F32_SLICE)
+    const float *bias, *bias_1;             // [N]
+    const __nv_bfloat16 *mask_src;          // [M][ldo]: sign bit set <=> ReLU mask 0
+    int ldo;                                // row pitch of the output in elements
+    int n_store;                            // columns actually stored (<= N tile coverage)
     long long slice_stride;
 };
 
@@ -62,32 +65,37 @@ __device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_
 
 template <int MODE, int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const GemmArgs g)
 {
+    constexpr bool A_MN = (MODE == MODE_MM || MODE == MODE_MK), B_MN = (MODE == MODE_MM || MODE == MODE_KM);
     static_assert(BN == 128 || BN == 64 || BN == 32, "BN");
-    static_assert(MODE == MODE_KK || BN % 64 == 0, "MN-major B tiles are 64-wide swizzle atoms");
+    static_assert(!B_MN || BN % 64 == 0, "MN-major B tiles are 64-wide swizzle atoms");
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = BN * BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-    constexpr uint32_t IDESC = make_idesc_bf16(BM, BN, MODE == MODE_MM, MODE == MODE_MM);
+    constexpr uint32_t IDESC = make_idesc_bf16(BM, BN, A_MN, B_MN);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float s_bias[BN];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-    const int k_begin = blockIdx.z * g.k_per_split;
+    const int prob = blockIdx.z / g.nsplit, split = blockIdx.z - prob * g.nsplit;
+    const CUtensorMap *tmA = prob ? &tmA1 : &tmA0, *tmB = prob ? &tmB1 : &tmB0;
+    const int k_begin = split * g.k_per_split;
     int k_end = k_begin + g.k_per_split;
     if (k_end > g.K) k_end = g.K;
     const int nkb = (k_end - k_begin + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmA);
-        prefetch_tmap(&tmB);
+        prefetch_tmap(tmA);
+        prefetch_tmap(tmB);
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -111,16 +119,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint8_t *sA = smem + s * STAGE_BYTES, *sB = sA + A_BYTES;
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 const int k = k_begin + kb * BK;
-                if (MODE == MODE_KK) {
-                    tma_load_2d(sA, &tmA, k, m0, &full_bar[s]);       // box {64 k, 128 rows}
-                    tma_load_2d(sB, &tmB, k, n0, &full_bar[s]);       // box {64 k, BN rows}
-                } else {
-                    // MN-major: box {64 mn, 64 k-rows}; one 8 KB atom column per 64 mn
-                    for (int h = 0; h < BM / 64; h++)
-                        tma_load_2d(sA + h * 8192, &tmA, m0 + 64 * h, k, &full_bar[s]);
-                    for (int h = 0; h < BN / 64; h++)
-                        tma_load_2d(sB + h * 8192, &tmB, n0 + 64 * h, k, &full_bar[s]);
-                }
+                // K-major: box {64 k, rows}.  MN-major: box {64 mn, 64 k-rows}, one 8 KB atom
+                // column per 64 mn.
+                if (!A_MN) tma_load_2d(sA, tmA, k, m0, &full_bar[s]);
+                else
+                    for (int h = 0; h < BM / 64; h++) tma_load_2d(sA + h * 8192, tmA, m0 + 64 * h, k, &full_bar[s]);
+                if (!B_MN) tma_load_2d(sB, tmB, k, n0, &full_bar[s]);
+                else
+                    for (int h = 0; h < BN / 64; h++) tma_load_2d(sB + h * 8192, tmB, n0 + 64 * h, k, &full_bar[s]);
             }
         }
     } else if (warp == 1) {
@@ -134,18 +140,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t aaddr = smem_u32(smem + s * STAGE_BYTES), baddr = aaddr + A_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < BK / UK; kk++) {
-                    uint64_t ad, bd;
-                    if (MODE == MODE_KK) {
-                        // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); the 16
-                        // k-elements of this MMA start 32 B further inside the swizzle row.
-                        ad = make_smem_desc(aaddr + kk * 32, 16, 1024);
-                        bd = make_smem_desc(baddr + kk * 32, 16, 1024);
-                    } else {
-                        // MN-major SW128: k-rows of 128 B (64 mn), 8-k-row groups 1024 B apart
-                        // (SBO), 64-mn groups 8192 B apart (LBO); 16 k-rows = 2048 B per MMA.
-                        ad = make_smem_desc(aaddr + kk * 2048, 8192, 1024);
-                        bd = make_smem_desc(baddr + kk * 2048, 8192, 1024);
-                    }
+                    // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); the 16
+                    // k-elements of this MMA start 32 B further inside the swizzle row.
+                    // MN-major SW128: k-rows of 128 B (64 mn), 8-k-row groups 1024 B apart
+                    // (SBO), 64-mn groups 8192 B apart (LBO); 16 k-rows = 2048 B per MMA.
+                    const uint64_t ad = A_MN ? make_smem_desc(aaddr + kk * 2048, 8192, 1024)
+                                             : make_smem_desc(aaddr + kk * 32, 16, 1024);
+                    const uint64_t bd = B_MN ? make_smem_desc(baddr + kk * 2048, 8192, 1024)
+                                             : make_smem_desc(baddr + kk * 32, 16, 1024);
                     mma_bf16(tmem_acc, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
                 }
                 mma_commit(&empty_bar[s]);                 // smem slot free once these MMAs retire
@@ -157,6 +159,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===== epilogue: TMEM -> registers -> global =====
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         const int row = m0 + q * 32 + lane;
+        __nv_bfloat16 *const out_bf16 = prob ? g.out_bf16_1 : g.out_bf16;
+        float *const out_f32 = prob ? g.out_f32_1 : g.out_f32;
+        if (EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_BIAS_F32) {
+            // stage this tile's bias once (one coalesced load), while the mainloop runs
+            const float *const bias = prob ? g.bias_1 : g.bias;
+            const int t = threadIdx.x - 64;
+            if (t < BN) s_bias[t] = (n0 + t < g.N && n0 + t < g.n_store) ? __ldg(bias + n0 + t) : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         if (nkb > 0) {
             mbar_wait(&tmem_full_bar, 0);
             tc_fence_after();
@@ -188,9 +199,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j = 0; j < 32; j += 2) {
                         float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
                         if (EPI == EPI_BIAS_RELU_BF16) {
-                            const int c = col0 + j;
-                            v0 += (c < g.N) ? __ldg(g.bias + c) : 0.f;
-                            v1 += (c + 1 < g.N) ? __ldg(g.bias + c + 1) : 0.f;
+                            v0 += s_bias[c0 + j];
+                            v1 += s_bias[c0 + j + 1];
                             // Rectify keeps the sign of a*0: -0.0 marks a masked unit (nn.go:162-189)
                             v0 = (v0 >= 0.f) ? v0 : -0.0f;
                             v1 = (v1 >= 0.f) ? v1 : -0.0f;
@@ -202,7 +212,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
                         packed[j >> 1] = *reinterpret_cast<uint32_t *>(&p);
                     }
-                    uint4 *op = reinterpret_cast<uint4 *>(g.out_bf16 + (size_t)row * g.ldo + col0);
+                    uint4 *op = reinterpret_cast<uint4 *>(out_bf16 + (size_t)row * g.ldo + col0);
 #pragma unroll
                     for (int v = 0; v < 4; v++)
                         if (col0 + 8 * v < g.n_store)
@@ -211,10 +221,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const int c = col0 + j;
-                        if (c < g.n_store) g.out_f32[(size_t)row * g.ldo + c] = __uint_as_float(r[j]) + __ldg(g.bias + c);
+                        if (c < g.n_store) out_f32[(size_t)row * g.ldo + c] = __uint_as_float(r[j]) + s_bias[c0 + j];
                     }
                 } else {  // EPI_F32_SLICE
-                    float *o = g.out_f32 + (size_t)blockIdx.z * g.slice_stride + (size_t)row * g.ldo + col0;
+                    float *o = out_f32 + (size_t)split * g.slice_stride + (size_t)row * g.ldo + col0;
                     if (col0 + 32 <= g.n_store && (g.ldo & 3) == 0) {
 #pragma unroll
                         for (int v = 0; v < 8; v++)
@@ -285,8 +295,10 @@ bool make_tmap(CUtensorMap *m, const void *base, int rows, int cols, int ld, int
     return true;
 }
 
+// one problem (ta1/tb1 = nullptr) or two problems sharing the launch
 template <int MODE, int BN, int EPI>
-cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmArgs &g, int nsplit, cudaStream_t st)
+cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, GemmArgs g, int nsplit, cudaStream_t st,
+                        const CUtensorMap *ta1 = nullptr, const CUtensorMap *tb1 = nullptr)
 {
     constexpr size_t smem = gemm_smem_bytes<MODE, BN>();
     static bool configured = false;
@@ -296,25 +308,29 @@ cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const Gemm
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit);
-    umma_gemm_kernel<MODE, BN, EPI><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, g);
+    g.nsplit = nsplit;
+    const int nprob = ta1 ? 2 : 1;
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit * nprob);
+    umma_gemm_kernel<MODE, BN, EPI><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, ta1 ? *ta1 : ta, tb1 ? *tb1 : tb, g);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------
 // CUDA-core helpers of the wide path
 // ---------------------------------------------------------------------------
-// K1: gather + fp32 -> bf16 (replay stays fp32 in HBM; the cast is fused into the gather)
+// K1: sample (optional) + gather + fp32 -> bf16.  The replay stays fp32 in HBM; index
+// generation and the cast are fused into the gather.  One thread per 16-byte granule.
 __global__ void __launch_bounds__(256)
-wide_gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx, int B, __nv_bfloat16 *__restrict__ x,
-                   __nv_bfloat16 *__restrict__ x2, int32_t *__restrict__ ba, float *__restrict__ br,
-                   uint8_t *__restrict__ bdone)
+wide_gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx, uint64_t seed, int32_t *__restrict__ idx_out,
+                   int B, __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ x2, int32_t *__restrict__ ba,
+                   float *__restrict__ br, uint8_t *__restrict__ bdone)
 {
     const int chunks = D >> 2;  // float4 granules per row (D % 8 == 0 is required by the path)
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * chunks) return;
     int b = t / chunks, c = t - b * chunks;
-    int64_t phys = rp.head - 1 - (int64_t)idx[b];
+    const int32_t li = idx ? idx[b] : (int32_t)perm_index((uint32_t)b, (uint32_t)rp.len, seed);
+    int64_t phys = rp.head - 1 - (int64_t)li;
     if (phys < 0) phys += rp.cap;
     float4 v = __ldg(reinterpret_cast<const float4 *>(rp.s + phys * D) + c);
     float4 w = __ldg(reinterpret_cast<const float4 *>(rp.s2 + phys * D) + c);
@@ -328,109 +344,160 @@ wide_gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx, int B, __n
         ba[b] = rp.a[phys];
         br[b] = rp.r[phys];
         bdone[b] = rp.done[phys];
+        if (idx_out && !idx) idx_out[b] = li;
     }
 }
 
-// bf16 shadow of one network's weights: W1^T [H1][D], W2^T [H2][H1], W2 [H1][H2] (online
-// only, for dX), W3^T padded [32][H2].  K-major B operands of the KK GEMMs.
+// bf16 shadow element writes for parameter i of value w (shared by the shadow kernel and
+// the fused update kernel).  The weights keep the reference's (in x out) layout: W1 [D][H1]
+// and W2 [H1][H2] are MN-major B operands of the forward GEMMs as stored (W2 is also the
+// K-major B operand of dX); W3 is padded to 64 columns for the forward tile, and kept
+// transposed [32][H2] for the dZ2 kernel's contiguous column reads.
+constexpr int W3_PAD = 64;
+struct ShadowPtrs {
+    __nv_bfloat16 *w1, *w2, *w3p, *w3t;
+};
+__device__ __forceinline__ void shadow_store(const Dims &d, const Offsets &o, const ShadowPtrs &sp, int i, float w)
+{
+    const __nv_bfloat16 v = __float2bfloat16_rn(w);
+    if (i < o.b1) {
+        sp.w1[i] = v;
+    } else if (i >= o.w2 && i < o.b2) {
+        sp.w2[i - o.w2] = v;
+    } else if (i >= o.w3 && i < o.b3) {
+        const int u = i - o.w3;
+        const int k = u / d.A, a = u - k * d.A;            // W3[k][a]
+        sp.w3p[(size_t)k * W3_PAD + a] = v;
+        if (sp.w3t) sp.w3t[(size_t)a * d.H2 + k] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256)
-wide_shadow_kernel(const float *__restrict__ theta, Dims d, Offsets o, __nv_bfloat16 *__restrict__ w1t,
-                   __nv_bfloat16 *__restrict__ w2t, __nv_bfloat16 *__restrict__ w2, __nv_bfloat16 *__restrict__ w3t)
+wide_shadow_kernel(const float *__restrict__ theta, Dims d, Offsets o, ShadowPtrs sp)
 {
-    const int n1 = d.D * d.H1, n2 = d.H1 * d.H2, n3 = 32 * d.H2;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n1 + n2 + n3; t += gridDim.x * blockDim.x) {
-        if (t < n1) {
-            int j = t / d.D, k = t - j * d.D;                 // w1t[j][k] = W1[k][j]
-            w1t[t] = __float2bfloat16_rn(theta[o.w1 + k * d.H1 + j]);
-        } else if (t < n1 + n2) {
-            int u = t - n1;
-            int j = u / d.H1, k = u - j * d.H1;               // w2t[j][k] = W2[k][j]
-            w2t[u] = __float2bfloat16_rn(theta[o.w2 + k * d.H2 + j]);
-            if (w2) w2[u] = __float2bfloat16_rn(theta[o.w2 + u]);
-        } else {
-            int u = t - n1 - n2;
-            int a = u / d.H2, k = u - a * d.H2;               // w3t[a][k] = W3[k][a], rows >= A are zero
-            w3t[u] = (a < d.A) ? __float2bfloat16_rn(theta[o.w3 + k * d.A + a]) : __float2bfloat16_rn(0.f);
-        }
-    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < o.P) shadow_store(d, o, sp, i, theta[i]);
+    // the padding of W3 stays zero from allocation time (cudaMemset in wide_create)
 }
 
-// K3 + layer-3 backward.  One block per TD_ROWS rows, one thread per hidden unit j.
-//   nextMax (first-max rules), td, d = q[a]-td, loss partial, dqv = 2 d / count
-//   dZ2[b][j] = dqv * W3[j][a] * mask2[b][j]              (bf16 out, operand of dW2 / dX)
-//   partials: dW3[j][a] += h2[b][j]*dqv ; db3[a] += dqv ; db2[j] += dZ2[b][j]
-constexpr int TD_ROWS = 64;
-__global__ void __launch_bounds__(512)
-wide_td_kernel(const float *__restrict__ q, const float *__restrict__ qt, const int32_t *__restrict__ act,
-               const float *__restrict__ rew, const uint8_t *__restrict__ done, int B, int H2, int A,
-               const float *__restrict__ w3 /* fp32 master [H2][A] */, const __nv_bfloat16 *__restrict__ h2,
-               StepScalars sc, float *__restrict__ td_out, __nv_bfloat16 *__restrict__ dz2,
-               float *__restrict__ part /* [blocks][H2*A + H2 + A + 1] */)
+// K3 (per row): first-max over Q'(s') (ArgmaxF32 rules), TD target, d = q[a] - t,
+// dqv = (2 d) / count; dQ^T [32][B] bf16 (one non-zero per column b) is the K-major B
+// operand of the dW3 GEMM.  Per block: loss partial and db3 partial (fixed order).
+constexpr int ROWS_TB = 64;   // small blocks: the kernel is latency-bound, spread it over the SMs
+__global__ void __launch_bounds__(ROWS_TB)
+wide_td_rows_kernel(const float *__restrict__ q, const float *__restrict__ qt, const int32_t *__restrict__ act,
+                    const float *__restrict__ rew, const uint8_t *__restrict__ done, int B, int A, StepScalars sc,
+                    float *__restrict__ td_out, float *__restrict__ dqv_out, __nv_bfloat16 *__restrict__ dqT,
+                    float *__restrict__ part /* [blocks][A + 1]: db3, loss */)
 {
-    extern __shared__ float sm[];
-    float *sW3 = sm;                 // [H2*A]
-    float *sG3 = sW3 + H2 * A;       // [A][H2] dW3 accumulators (thread j owns column j)
-    float *sRow = sG3 + H2 * A;      // [TD_ROWS] dqv
-    int *sAct = reinterpret_cast<int *>(sRow + TD_ROWS);  // [TD_ROWS]
-    __shared__ float sSq[TD_ROWS];
-    const int tid = threadIdx.x;
-    const int r0 = blockIdx.x * TD_ROWS;
-    const int nrows = min(TD_ROWS, B - r0);
-    for (int i = tid; i < H2 * A; i += blockDim.x) { sW3[i] = w3[i]; sG3[i] = 0.f; }
-    __syncthreads();
-    if (tid < nrows) {
-        const int b = r0 + tid;
-        float t = rew[b];
-        if (!done[b]) {
-            const float *row = qt + (int64_t)b * A;
-            float f = row[0];
-            for (int i = 1; i < A; i++) {
-                float v = row[i];
-                if (isnan(v) || (isinf(v) && v > 0.f)) { f = v; break; }
-                if (v > f) f = v;
+    __shared__ float sh[ROWS_TB / 32][33];
+    const int b = blockIdx.x * ROWS_TB + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float dqv = 0.f, sq = 0.f;
+    int a = -1;
+    if (b < B) {
+        // all loads of the row first (A <= 32), then the scan
+        const float *row = qt + (int64_t)b * A;
+        float rv[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) rv[i] = (i < A) ? __ldg(row + i) : 0.f;
+        a = act[b];
+        const float rwd = rew[b];
+        const int dn = done[b];
+        const float qa = __ldg(q + (int64_t)b * A + a);
+        float t = rwd;
+        if (!dn) {
+            float f = rv[0];
+            bool decided = false;
+#pragma unroll
+            for (int i = 1; i < 32; i++) {
+                if (i < A && !decided) {
+                    const float v = rv[i];
+                    if (isnan(v) || (isinf(v) && v > 0.f)) { f = v; decided = true; }
+                    else if (v > f) f = v;
+                }
             }
-            t = __fadd_rn(rew[b], __fmul_rn(sc.gamma, f));
+            t = __fadd_rn(rwd, __fmul_rn(sc.gamma, f));         // agent.go:149
         }
         td_out[b] = t;
-        const int a = act[b];
-        const float dd = __fsub_rn(q[(int64_t)b * A + a], t);
-        sRow[tid] = __fmul_rn(__fmul_rn(dd, 2.f), sc.inv_count);
-        sAct[tid] = a;
-        sSq[tid] = __fmul_rn(dd, dd);
+        const float dd = __fsub_rn(qa, t);
+        dqv = __fmul_rn(__fmul_rn(dd, 2.f), sc.inv_count);
+        sq = __fmul_rn(dd, dd);
+        dqv_out[b] = dqv;
+        const __nv_bfloat16 v = __float2bfloat16_rn(dqv), z = __float2bfloat16_rn(0.f);
+        for (int i = 0; i < 32; i++) dqT[(int64_t)i * B + b] = (i == a) ? v : z;
+    }
+    // db3[i] = sum of dqv over rows with act == i; slot A = loss partial
+    for (int i = 0; i <= A; i++) {
+        float v = (i == A) ? sq : ((a == i) ? dqv : 0.f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[warp][i] = v;
     }
     __syncthreads();
-    for (int j = tid; j < H2; j += blockDim.x) {
-        float db2 = 0.f;
-#pragma unroll 8
-        for (int rr = 0; rr < nrows; rr++) {
-            const int b = r0 + rr;
-            const float dqv = sRow[rr];
-            const int a = sAct[rr];
-            const __nv_bfloat16 hb = h2[(int64_t)b * H2 + j];
-            const bool masked = (__bfloat16_as_ushort(hb) & 0x8000u) != 0;
-            const float hv = __bfloat162float(hb);
-            float dz = masked ? 0.f : dqv * sW3[j * A + a];
-            dz2[(int64_t)b * H2 + j] = __float2bfloat16_rn(dz);
-            // accumulate the ROUNDED dz so that db2 matches the bf16 operand of dW2 / dX
-            db2 += __bfloat162float(__float2bfloat16_rn(dz));
-            sG3[a * H2 + j] += hv * dqv;
+    if (threadIdx.x <= A) {
+        float t = 0.f;
+        for (int w = 0; w < ROWS_TB / 32; w++) t += sh[w][threadIdx.x];
+        part[(int64_t)blockIdx.x * (A + 1) + threadIdx.x] = t;
+    }
+}
+
+// dZ2[b][j] = dqv[b] * W3[j][a_b] * mask2[b][j] (bf16 out, operand of dW2 / dX) and the
+// db2 partial of the block.  Thread (x, y): 8 columns (16-byte vectors), rows y, y+4, ...
+constexpr int DZ_ROWS = 32;
+__global__ void __launch_bounds__(256)
+wide_dz2_kernel(const __nv_bfloat16 *__restrict__ h2, const __nv_bfloat16 *__restrict__ w3t /* [32][H2] */,
+                const float *__restrict__ dqv, const int32_t *__restrict__ act, int B, int H2,
+                __nv_bfloat16 *__restrict__ dz2, float *__restrict__ part /* [blocks][H2] */)
+{
+    extern __shared__ float sm[];            // [4][H2] column-sum staging
+    __shared__ float sDq[DZ_ROWS];
+    __shared__ int sAct[DZ_ROWS];
+    const int x = threadIdx.x & 63, y = threadIdx.x >> 6;
+    const int r0 = blockIdx.x * DZ_ROWS;
+    if (threadIdx.x < DZ_ROWS) {
+        const int b = r0 + threadIdx.x;
+        sDq[threadIdx.x] = b < B ? dqv[b] : 0.f;
+        sAct[threadIdx.x] = b < B ? act[b] : 0;
+    }
+    __syncthreads();
+    for (int c = x; c < (H2 >> 3); c += 64) {
+        float cs[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) cs[e] = 0.f;
+        uint4 hv[DZ_ROWS / 4], wv[DZ_ROWS / 4];
+#pragma unroll
+        for (int u = 0; u < DZ_ROWS / 4; u++) {
+            const int rr = y + 4 * u, b = r0 + rr;
+            hv[u] = b < B ? __ldg(reinterpret_cast<const uint4 *>(h2 + (int64_t)b * H2) + c) : make_uint4(0, 0, 0, 0);
+            wv[u] = __ldg(reinterpret_cast<const uint4 *>(w3t + (int64_t)sAct[rr] * H2) + c);
         }
-        float *p = part + (int64_t)blockIdx.x * (H2 * A + H2 + A + 1);
-        for (int a = 0; a < A; a++) p[j * A + a] = sG3[a * H2 + j];
-        p[H2 * A + j] = db2;
+#pragma unroll
+        for (int u = 0; u < DZ_ROWS / 4; u++) {
+            const int rr = y + 4 * u, b = r0 + rr;
+            const float dq = sDq[rr];
+            const uint32_t hw[4] = {hv[u].x, hv[u].y, hv[u].z, hv[u].w};
+            const uint32_t ww[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float w0 = __uint_as_float(ww[e] << 16), w1 = __uint_as_float(ww[e] & 0xffff0000u);
+                const float z0 = (hw[e] & 0x8000u) ? 0.f : dq * w0;
+                const float z1 = (hw[e] & 0x80000000u) ? 0.f : dq * w1;
+                __nv_bfloat162 pk = __floats2bfloat162_rn(z0, z1);
+                ow[e] = *reinterpret_cast<uint32_t *>(&pk);
+                // sum the ROUNDED values so that db2 matches the bf16 operand of dW2 / dX
+                cs[2 * e] += __uint_as_float(ow[e] << 16);
+                cs[2 * e + 1] += __uint_as_float(ow[e] & 0xffff0000u);
+            }
+            if (b < B) reinterpret_cast<uint4 *>(dz2 + (int64_t)b * H2)[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) sm[y * H2 + c * 8 + e] = cs[e];
     }
-    // db3 and the loss partial, rows in order (deterministic)
-    float *p = part + (int64_t)blockIdx.x * (H2 * A + H2 + A + 1);
-    if (tid < A) {
-        float sb = 0.f;
-        for (int rr = 0; rr < nrows; rr++) sb += (sAct[rr] == tid) ? sRow[rr] : 0.f;
-        p[H2 * A + H2 + tid] = sb;
-    }
-    if (tid == A) {
-        float sl = 0.f;
-        for (int rr = 0; rr < nrows; rr++) sl += sSq[rr];
-        p[H2 * A + H2 + A] = sl;
-    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < H2; j += blockDim.x)
+        part[(int64_t)blockIdx.x * H2 + j] = ((sm[j] + sm[H2 + j]) + sm[2 * H2 + j]) + sm[3 * H2 + j];
 }
 
 // db1 partials: column sums of dZ1 (bf16 [B][H1]) over CS_ROWS-row ranges.  A warp covers
@@ -473,44 +540,167 @@ wide_colsum_kernel(const __nv_bfloat16 *__restrict__ dz, int B, int H, float *__
     }
 }
 
-// flat[P+1] = fixed-order sums of all partial buffers; flat[P] = loss.
-// Block = 32 elements x 8 partial-chunks: thread (x, y) sums partials y, y+8, ... with the
-// loads issued in batches of 4, then the 8 chunk sums are added in order.
-__global__ void __launch_bounds__(256)
-wide_reduce_kernel(Dims d, Offsets o, const float *__restrict__ w1_slices, int n1, const float *__restrict__ w2_slices,
-                   int n2, const float *__restrict__ b1_part, int nb1, const float *__restrict__ td_part, int ntd,
-                   float count, float *__restrict__ flat)
+// Fixed-order sums of all partial buffers -> flat[P+1] (flat[P] = loss) and, when FUSE,
+// the Adam update (kernels_generic.cu K5 semantics) plus the bf16 shadow refresh in the
+// same pass.
+struct PartialSrc {
+    const float *w1_slices; int n1;     // [n1][D*H1]
+    const float *b1_part;   int nb1;    // [nb1][H1]
+    const float *w2_slices; int n2;     // [n2][H1*H2]
+    const float *b2_part;   int nb2;    // [nb2][H2]
+    const float *w3_slices; int n3;     // [n3][H2*A]
+    const float *row_part;  int nrow;   // [nrow][A+1]: db3, loss
+};
+
+__device__ __forceinline__ void adam_update_w(float &w, float g, float &m, float &v, const AdamConsts &c)
 {
-    __shared__ float sh[8][33];
-    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + x;
-    const int tdw = d.H2 * d.A + d.H2 + d.A + 1;
-    const float *base = nullptr;
-    int n = 0;
-    int64_t stride = 0;
-    if (i < o.b1) { base = w1_slices + i; n = n1; stride = (int64_t)d.D * d.H1; }
-    else if (i < o.w2) { base = b1_part + (i - o.b1); n = nb1; stride = d.H1; }
-    else if (i < o.b2) { base = w2_slices + (i - o.w2); n = n2; stride = (int64_t)d.H1 * d.H2; }
-    else if (i < o.w3) { base = td_part + d.H2 * d.A + (i - o.b2); n = ntd; stride = tdw; }
-    else if (i < o.b3) { base = td_part + (i - o.w3); n = ntd; stride = tdw; }
-    else if (i < o.P) { base = td_part + d.H2 * d.A + d.H2 + (i - o.b3); n = ntd; stride = tdw; }
-    else if (i == o.P) { base = td_part + d.H2 * d.A + d.H2 + d.A; n = ntd; stride = tdw; }
-    float s = 0.f;
-    for (int z = y; z < n; z += 32) {
-        float v[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) v[u] = (z + 8 * u < n) ? __ldg(base + (int64_t)(z + 8 * u) * stride) : 0.f;
-#pragma unroll
-        for (int u = 0; u < 4; u++) s += v[u];
+    // vendor/gorgonia.org/gorgonia/solvers.go:551-615, incl. the double weight update
+    float t1 = __fmul_rn(g, c.omb1);
+    float g2 = __fmul_rn(__fmul_rn(g, g), c.omb2);
+    m = __fadd_rn(t1, __fmul_rn(c.beta1, m));
+    v = __fadd_rn(g2, __fmul_rn(c.beta2, v));
+    float mh = __fmul_rn(m, c.c1);
+    float vh = __fmul_rn(v, c.c2);
+    float den = __fadd_rn(__fsqrt_rn(vh), c.eps);
+    float u = __fmul_rn(mh, c.neg_eta);
+    if (den == 0.f) w = __int_as_float(0x7f800000);
+    else w = __fadd_rn(w, __fdiv_rn(u, den));
+    w = __fadd_rn(w, u);
+}
+
+// Work decomposition of the update kernel (one launch, three block ranges):
+//   A  thread per float4 group of W1 / W2 / W3: few partials (split-K slices), batches of 8
+//      independent 16-byte loads;
+//   B  warp per float4 group of b1 / b2: many partials (one per row block): lanes stride
+//      over the partials, fixed-order butterfly;
+//   C  warp per scalar of b3 and the loss.
+struct UpdatePlan {
+    int nA;        // float4 groups in W1, W2, W3 (in parameter order)
+    int nB;        // float4 groups in b1, b2
+    int nC;        // A + 1 scalars
+    int blocksA, blocksB, blocksC;
+};
+
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+template <bool FUSE>
+__device__ __forceinline__ void finish4(const Dims &d, const Offsets &o, int i, float4 g, float *flat, float *theta,
+                                        float *m, float *v, float4 w4, float4 m4, float4 v4, const AdamConsts &ac,
+                                        const ShadowPtrs &sp)
+{
+    *reinterpret_cast<float4 *>(flat + i) = g;
+    if (!FUSE) return;
+    adam_update_w(w4.x, g.x, m4.x, v4.x, ac);
+    adam_update_w(w4.y, g.y, m4.y, v4.y, ac);
+    adam_update_w(w4.z, g.z, m4.z, v4.z, ac);
+    adam_update_w(w4.w, g.w, m4.w, v4.w, ac);
+    *reinterpret_cast<float4 *>(theta + i) = w4;
+    *reinterpret_cast<float4 *>(m + i) = m4;
+    *reinterpret_cast<float4 *>(v + i) = v4;
+    if (i < o.b1 || (i >= o.w2 && i < o.b2)) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(w4.x, w4.y), p1 = __floats2bfloat162_rn(w4.z, w4.w);
+        uint2 pk = make_uint2(*reinterpret_cast<uint32_t *>(&p0), *reinterpret_cast<uint32_t *>(&p1));
+        __nv_bfloat16 *dst = (i < o.b1) ? sp.w1 + i : sp.w2 + (i - o.w2);
+        *reinterpret_cast<uint2 *>(dst) = pk;
+    } else if (i >= o.w3 && i < o.b3) {
+        shadow_store(d, o, sp, i, w4.x);
+        shadow_store(d, o, sp, i + 1, w4.y);
+        shadow_store(d, o, sp, i + 2, w4.z);
+        shadow_store(d, o, sp, i + 3, w4.w);
     }
-    sh[y][x] = s;
-    __syncthreads();
-    if (y == 0 && i <= o.P) {
-        float t = 0.f;
+}
+
+template <bool FUSE>
+__global__ void __launch_bounds__(128)
+wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count, float *__restrict__ flat,
+                   float *__restrict__ theta, float *__restrict__ m, float *__restrict__ v, AdamConsts ac, ShadowPtrs sp)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if ((int)blockIdx.x < pl.blocksA) {
+        // ---- A: weights ------------------------------------------------------------
+        const int gidx = blockIdx.x * 128 + threadIdx.x;
+        if (gidx >= pl.nA) return;
+        const int n1g = (d.D * d.H1) >> 2, n2g = (d.H1 * d.H2) >> 2;
+        int i, n;
+        const float *base;
+        int64_t stride;
+        if (gidx < n1g) { i = o.w1 + gidx * 4; base = ps.w1_slices + gidx * 4; n = ps.n1; stride = (int64_t)d.D * d.H1; }
+        else if (gidx < n1g + n2g) { const int u = (gidx - n1g) * 4; i = o.w2 + u; base = ps.w2_slices + u; n = ps.n2; stride = (int64_t)d.H1 * d.H2; }
+        else { const int u = (gidx - n1g - n2g) * 4; i = o.w3 + u; base = ps.w3_slices + u; n = ps.n3; stride = (int64_t)d.H2 * d.A; }
+        float4 w4 = make_float4(0, 0, 0, 0), m4 = w4, v4 = w4;
+        if (FUSE) {
+            w4 = *reinterpret_cast<const float4 *>(theta + i);
+            m4 = *reinterpret_cast<const float4 *>(m + i);
+            v4 = *reinterpret_cast<const float4 *>(v + i);
+        }
+        float4 g = make_float4(0, 0, 0, 0);
+        for (int z = 0; z < n; z += 8) {
+            float4 t[8];
 #pragma unroll
-        for (int w = 0; w < 8; w++) t += sh[w][x];
-        if (i == o.P) t = __fdiv_rn(t, count);
-        flat[i] = t;
+            for (int u = 0; u < 8; u++)
+                t[u] = (z + u < n) ? __ldg(reinterpret_cast<const float4 *>(base + (int64_t)(z + u) * stride))
+                                   : make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 8; u++) g = f4add(g, t[u]);
+        }
+        finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
+    } else if ((int)blockIdx.x < pl.blocksA + pl.blocksB) {
+        // ---- B: biases of the hidden layers, warp per float4 group -------------------
+        const int gidx = (blockIdx.x - pl.blocksA) * 4 + warp;
+        if (gidx >= pl.nB) return;
+        const int nb1g = d.H1 >> 2;
+        int i, n;
+        const float *base;
+        int64_t stride;
+        if (gidx < nb1g) { i = o.b1 + gidx * 4; base = ps.b1_part + gidx * 4; n = ps.nb1; stride = d.H1; }
+        else { const int u = (gidx - nb1g) * 4; i = o.b2 + u; base = ps.b2_part + u; n = ps.nb2; stride = d.H2; }
+        float4 g = make_float4(0, 0, 0, 0);
+        for (int z = lane; z < n; z += 32 * 4) {
+            float4 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                t[u] = (z + 32 * u < n) ? __ldg(reinterpret_cast<const float4 *>(base + (int64_t)(z + 32 * u) * stride))
+                                        : make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; u++) g = f4add(g, t[u]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            g.x += __shfl_xor_sync(0xffffffffu, g.x, off);
+            g.y += __shfl_xor_sync(0xffffffffu, g.y, off);
+            g.z += __shfl_xor_sync(0xffffffffu, g.z, off);
+            g.w += __shfl_xor_sync(0xffffffffu, g.w, off);
+        }
+        if (lane == 0) {
+            float4 w4 = make_float4(0, 0, 0, 0), m4 = w4, v4 = w4;
+            if (FUSE) {
+                w4 = *reinterpret_cast<const float4 *>(theta + i);
+                m4 = *reinterpret_cast<const float4 *>(m + i);
+                v4 = *reinterpret_cast<const float4 *>(v + i);
+            }
+            finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
+        }
+    } else {
+        // ---- C: b3 and the loss, warp per scalar ---------------------------------------
+        const int e = (blockIdx.x - pl.blocksA - pl.blocksB) * 4 + warp;
+        if (e >= pl.nC) return;
+        const int i = o.b3 + e;
+        const float *base = ps.row_part + e;
+        float g = 0.f;
+        for (int z = lane; z < ps.nrow; z += 32) g += __ldg(base + (int64_t)z * (d.A + 1));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) g += __shfl_xor_sync(0xffffffffu, g, off);
+        if (lane == 0) {
+            if (i == o.P) g = __fdiv_rn(g, count);
+            flat[i] = g;
+            if (FUSE && i < o.P) {
+                float wi = theta[i], mi = m[i], vi = v[i];
+                adam_update_w(wi, g, mi, vi, ac);
+                theta[i] = wi;
+                m[i] = mi;
+                v[i] = vi;
+            }
+        }
     }
 }
 
@@ -528,8 +718,8 @@ bool dmalloc(T **p, size_t n, std::string &err)
 // WideState
 // ---------------------------------------------------------------------------
 struct WideNet {
-    __nv_bfloat16 *w1t = nullptr, *w2t = nullptr, *w2 = nullptr, *w3t = nullptr;
-    CUtensorMap tm_w1t, tm_w2t, tm_w2, tm_w3t;
+    __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3p = nullptr, *w3t = nullptr;
+    CUtensorMap tm_w1_mn, tm_w2_mn, tm_w3p_mn, tm_w2_k;
 };
 
 struct WideState {
@@ -538,15 +728,16 @@ struct WideState {
     int B = 0, sm_count = 148;
     WideNet net[2];
     __nv_bfloat16 *x = nullptr, *x2 = nullptr, *h1 = nullptr, *h2 = nullptr, *t1 = nullptr, *t2 = nullptr;
-    __nv_bfloat16 *dz2 = nullptr, *dz1 = nullptr;
-    float *q = nullptr, *qt = nullptr, *td = nullptr, *br = nullptr;
+    __nv_bfloat16 *dz2 = nullptr, *dz1 = nullptr, *dqT = nullptr;
+    float *q = nullptr, *qt = nullptr, *td = nullptr, *br = nullptr, *dqv = nullptr;
     int32_t *ba = nullptr;
     uint8_t *bdone = nullptr;
-    float *w1_slices = nullptr, *w2_slices = nullptr, *b1_part = nullptr, *td_part = nullptr;
-    int ns1 = 1, ns2 = 1, kps1 = 0, kps2 = 0, nb1 = 1, ntd = 1;
-    // activation tensor maps: KK A-operands (box 128 rows) and MM operands (box 64 k-rows)
+    float *w1_slices = nullptr, *w2_slices = nullptr, *w3_slices = nullptr, *b1_part = nullptr, *b2_part = nullptr,
+          *row_part = nullptr;
+    int ns1 = 1, ns2 = 1, ns3 = 1, kps1 = 0, kps2 = 0, kps3 = 0, nb1 = 1, nb2 = 1, nrow = 1;
+    // activation tensor maps: KK A-operands (box 128 rows) and MN-major operands (box 64 k-rows)
     CUtensorMap tm_x_a, tm_x2_a, tm_h1_a, tm_t1_a, tm_h2_a, tm_t2_a, tm_dz2_a;
-    CUtensorMap tm_x_mm, tm_h1_mm, tm_dz2_mm, tm_dz1_mm;
+    CUtensorMap tm_x_mm, tm_h1_mm, tm_h2_mm, tm_dz2_mm, tm_dz1_mm, tm_dqT_b;
     bool debug = false;
 };
 
@@ -565,8 +756,8 @@ static int split_for(int tiles, int K, int sm_count, int *kps)
 WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
 {
     if ((d.D % 8) || (d.H1 % 8) || (d.H2 % 8)) { err = "bf16 path needs D, H1, H2 to be multiples of 8 (16-byte TMA pitch)"; return nullptr; }
+    if (B % 8) { err = "bf16 path needs batch_size to be a multiple of 8 (16-byte pitch of dQ^T)"; return nullptr; }
     if (d.A > 32) { err = "bf16 path supports up to 32 actions"; return nullptr; }
-    if ((size_t)2 * d.H2 * d.A * 4 > 200 * 1024) { err = "bf16 path: hidden2 * n_actions too large for the layer-3 backward kernel"; return nullptr; }
     if (!load_encode(err)) return nullptr;
     WideState *w = new WideState();
     w->d = d;
@@ -575,43 +766,53 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     w->sm_count = sm_count;
     bool ok = true;
     for (int n = 0; n < 2; n++) {
-        ok = ok && dmalloc(&w->net[n].w1t, (size_t)d.H1 * d.D, err) && dmalloc(&w->net[n].w2t, (size_t)d.H2 * d.H1, err) &&
-             dmalloc(&w->net[n].w3t, (size_t)32 * d.H2, err);
+        ok = ok && dmalloc(&w->net[n].w1, (size_t)d.D * d.H1, err) && dmalloc(&w->net[n].w2, (size_t)d.H1 * d.H2, err) &&
+             dmalloc(&w->net[n].w3p, (size_t)d.H2 * W3_PAD, err);
+        if (ok) cudaMemset(w->net[n].w3p, 0, (size_t)d.H2 * W3_PAD * 2);
     }
-    ok = ok && dmalloc(&w->net[0].w2, (size_t)d.H1 * d.H2, err);
+    ok = ok && dmalloc(&w->net[0].w3t, (size_t)32 * d.H2, err);
+    if (ok) cudaMemset(w->net[0].w3t, 0, (size_t)32 * d.H2 * 2);
     size_t n = B;
     ok = ok && dmalloc(&w->x, n * d.D, err) && dmalloc(&w->x2, n * d.D, err) && dmalloc(&w->h1, n * d.H1, err) &&
          dmalloc(&w->h2, n * d.H2, err) && dmalloc(&w->t1, n * d.H1, err) && dmalloc(&w->t2, n * d.H2, err) &&
-         dmalloc(&w->dz2, n * d.H2, err) && dmalloc(&w->dz1, n * d.H1, err) && dmalloc(&w->q, n * d.A, err) &&
-         dmalloc(&w->qt, n * d.A, err) && dmalloc(&w->td, n, err) && dmalloc(&w->br, n, err) &&
-         dmalloc(&w->ba, n, err) && dmalloc(&w->bdone, n, err);
+         dmalloc(&w->dz2, n * d.H2, err) && dmalloc(&w->dz1, n * d.H1, err) && dmalloc(&w->dqT, n * 32, err) &&
+         dmalloc(&w->q, n * d.A, err) && dmalloc(&w->qt, n * d.A, err) && dmalloc(&w->td, n, err) &&
+         dmalloc(&w->dqv, n, err) && dmalloc(&w->br, n, err) && dmalloc(&w->ba, n, err) && dmalloc(&w->bdone, n, err);
     if (!ok) { wide_destroy(w); return nullptr; }
     int tiles1 = ((d.D + BM - 1) / BM) * ((d.H1 + 127) / 128);
     int tiles2 = ((d.H1 + BM - 1) / BM) * ((d.H2 + 127) / 128);
+    int tiles3 = (d.H2 + BM - 1) / BM;
     w->ns1 = split_for(tiles1, B, sm_count, &w->kps1);
     w->ns2 = split_for(tiles2, B, sm_count, &w->kps2);
+    w->ns3 = split_for(tiles3, B, sm_count, &w->kps3);
     w->nb1 = (B + CS_ROWS - 1) / CS_ROWS;
-    w->ntd = (B + TD_ROWS - 1) / TD_ROWS;
+    w->nb2 = (B + DZ_ROWS - 1) / DZ_ROWS;
+    w->nrow = (B + ROWS_TB - 1) / ROWS_TB;
     ok = ok && dmalloc(&w->w1_slices, (size_t)w->ns1 * d.D * d.H1, err) &&
-         dmalloc(&w->w2_slices, (size_t)w->ns2 * d.H1 * d.H2, err) && dmalloc(&w->b1_part, (size_t)w->nb1 * d.H1, err) &&
-         dmalloc(&w->td_part, (size_t)w->ntd * (d.H2 * d.A + d.H2 + d.A + 1), err);
+         dmalloc(&w->w2_slices, (size_t)w->ns2 * d.H1 * d.H2, err) &&
+         dmalloc(&w->w3_slices, (size_t)w->ns3 * d.H2 * d.A, err) && dmalloc(&w->b1_part, (size_t)w->nb1 * d.H1, err) &&
+         dmalloc(&w->b2_part, (size_t)w->nb2 * d.H2, err) && dmalloc(&w->row_part, (size_t)w->nrow * (d.A + 1), err);
     if (!ok) { wide_destroy(w); return nullptr; }
-    // weight maps: [N rows][K cols]
+    // weight maps.  MN-major B operands: [K rows][N cols], box 64 k-rows x 64 n
     for (int k = 0; k < 2; k++) {
         WideNet &nn = w->net[k];
-        ok = ok && make_tmap(&nn.tm_w1t, nn.w1t, d.H1, d.D, d.D, 128, err) &&
-             make_tmap(&nn.tm_w2t, nn.w2t, d.H2, d.H1, d.H1, 128, err) &&
-             make_tmap(&nn.tm_w3t, nn.w3t, 32, d.H2, d.H2, 32, err);
+        ok = ok && make_tmap(&nn.tm_w1_mn, nn.w1, d.D, d.H1, d.H1, 64, err) &&
+             make_tmap(&nn.tm_w2_mn, nn.w2, d.H1, d.H2, d.H2, 64, err) &&
+             make_tmap(&nn.tm_w3p_mn, nn.w3p, d.H2, W3_PAD, W3_PAD, 64, err);
     }
-    ok = ok && make_tmap(&w->net[0].tm_w2, w->net[0].w2, d.H1, d.H2, d.H2, 128, err);
+    // W2 as the K-major B operand of dX: [N = H1 rows][K = H2 cols], box 128 rows
+    ok = ok && make_tmap(&w->net[0].tm_w2_k, w->net[0].w2, d.H1, d.H2, d.H2, 128, err);
     // activations as KK A operands: [B rows][K cols], box 128 rows
     ok = ok && make_tmap(&w->tm_x_a, w->x, B, d.D, d.D, BM, err) && make_tmap(&w->tm_x2_a, w->x2, B, d.D, d.D, BM, err) &&
          make_tmap(&w->tm_h1_a, w->h1, B, d.H1, d.H1, BM, err) && make_tmap(&w->tm_t1_a, w->t1, B, d.H1, d.H1, BM, err) &&
          make_tmap(&w->tm_h2_a, w->h2, B, d.H2, d.H2, BM, err) && make_tmap(&w->tm_t2_a, w->t2, B, d.H2, d.H2, BM, err) &&
          make_tmap(&w->tm_dz2_a, w->dz2, B, d.H2, d.H2, BM, err);
-    // activations as MM operands: [K = B rows][MN cols], box 64 k-rows x 64 mn
+    // activations as MN-major operands: [K = B rows][MN cols], box 64 k-rows x 64 mn
     ok = ok && make_tmap(&w->tm_x_mm, w->x, B, d.D, d.D, 64, err) && make_tmap(&w->tm_h1_mm, w->h1, B, d.H1, d.H1, 64, err) &&
-         make_tmap(&w->tm_dz2_mm, w->dz2, B, d.H2, d.H2, 64, err) && make_tmap(&w->tm_dz1_mm, w->dz1, B, d.H1, d.H1, 64, err);
+         make_tmap(&w->tm_h2_mm, w->h2, B, d.H2, d.H2, 64, err) && make_tmap(&w->tm_dz2_mm, w->dz2, B, d.H2, d.H2, 64, err) &&
+         make_tmap(&w->tm_dz1_mm, w->dz1, B, d.H1, d.H1, 64, err);
+    // dQ^T [32 rows][B cols]: K-major B operand of the dW3 GEMM, box 32 rows
+    ok = ok && make_tmap(&w->tm_dqT_b, w->dqT, 32, B, B, 32, err);
     if (!ok) { wide_destroy(w); return nullptr; }
     return w;
 }
@@ -620,22 +821,26 @@ void wide_destroy(WideState *w)
 {
     if (!w) return;
     for (int n = 0; n < 2; n++) {
-        void *p[] = {w->net[n].w1t, w->net[n].w2t, w->net[n].w2, w->net[n].w3t};
+        void *p[] = {w->net[n].w1, w->net[n].w2, w->net[n].w3p, w->net[n].w3t};
         for (void *q : p)
             if (q) cudaFree(q);
     }
-    void *p[] = {w->x, w->x2, w->h1, w->h2, w->t1, w->t2, w->dz2, w->dz1, w->q, w->qt, w->td, w->br, w->ba, w->bdone,
-                 w->w1_slices, w->w2_slices, w->b1_part, w->td_part};
+    void *p[] = {w->x, w->x2, w->h1, w->h2, w->t1, w->t2, w->dz2, w->dz1, w->dqT, w->q, w->qt, w->td, w->dqv, w->br,
+                 w->ba, w->bdone, w->w1_slices, w->w2_slices, w->w3_slices, w->b1_part, w->b2_part, w->row_part};
     for (void *q : p)
         if (q) cudaFree(q);
     delete w;
 }
 
-static int shadow(WideState *w, int net, const float *theta, cudaStream_t st, std::string &err)
+static ShadowPtrs shadow_ptrs(WideState *w, int net)
 {
     WideNet &n = w->net[net];
-    int total = w->d.D * w->d.H1 + w->d.H1 * w->d.H2 + 32 * w->d.H2;
-    wide_shadow_kernel<<<(total + 255) / 256, 256, 0, st>>>(theta, w->d, w->o, n.w1t, n.w2t, n.w2, n.w3t);
+    return ShadowPtrs{n.w1, n.w2, n.w3p, n.w3t};
+}
+
+static int shadow(WideState *w, int net, const float *theta, cudaStream_t st, std::string &err)
+{
+    wide_shadow_kernel<<<(w->o.P + 255) / 256, 256, 0, st>>>(theta, w->d, w->o, shadow_ptrs(w, net));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("wide_shadow_kernel: ") + cudaGetErrorString(e); return -1; }
     return 1;
@@ -653,11 +858,11 @@ int wide_after_update(WideState *w, const float *theta_dev, cudaStream_t st, std
 
 int wide_sync_target(WideState *w, cudaStream_t st, std::string &err)
 {
-    // target <- online: copy the bf16 shadows (W2 plain is online-only)
+    // target <- online: copy the bf16 shadows (W3^T is online-only)
     const Dims &d = w->d;
-    cudaError_t e = cudaMemcpyAsync(w->net[1].w1t, w->net[0].w1t, (size_t)d.H1 * d.D * 2, cudaMemcpyDeviceToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(w->net[1].w2t, w->net[0].w2t, (size_t)d.H2 * d.H1 * 2, cudaMemcpyDeviceToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(w->net[1].w3t, w->net[0].w3t, (size_t)32 * d.H2 * 2, cudaMemcpyDeviceToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(w->net[1].w1, w->net[0].w1, (size_t)d.D * d.H1 * 2, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(w->net[1].w2, w->net[0].w2, (size_t)d.H1 * d.H2 * 2, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(w->net[1].w3p, w->net[0].w3p, (size_t)d.H2 * W3_PAD * 2, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) { err = std::string("wide_sync_target: ") + cudaGetErrorString(e); return -1; }
     return 3;
 }
@@ -668,27 +873,7 @@ int wide_sync_target(WideState *w, cudaStream_t st, std::string &err)
         if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return -1; } \
     } while (0)
 
-static int forward_net(WideState *w, int net, const CUtensorMap &tx, const CUtensorMap &th1, const CUtensorMap &th2,
-                       __nv_bfloat16 *h1, __nv_bfloat16 *h2, float *q, const float *theta, cudaStream_t st,
-                       std::string &err)
-{
-    const Dims &d = w->d;
-    const Offsets &o = w->o;
-    WideNet &n = w->net[net];
-    GemmArgs g{};
-    g.M = w->B; g.N = d.H1; g.K = d.D; g.k_per_split = ((d.D + BK - 1) / BK) * BK;
-    g.out_bf16 = h1; g.bias = theta + o.b1; g.ldo = d.H1; g.n_store = d.H1;
-    WCK((launch_gemm<MODE_KK, 128, EPI_BIAS_RELU_BF16>(tx, n.tm_w1t, g, 1, st)));
-    g.N = d.H2; g.K = d.H1; g.k_per_split = ((d.H1 + BK - 1) / BK) * BK;
-    g.out_bf16 = h2; g.bias = theta + o.b2; g.ldo = d.H2; g.n_store = d.H2;
-    WCK((launch_gemm<MODE_KK, 128, EPI_BIAS_RELU_BF16>(th1, n.tm_w2t, g, 1, st)));
-    g.N = 32; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
-    g.out_bf16 = nullptr; g.out_f32 = q; g.bias = theta + o.b3; g.ldo = d.A; g.n_store = d.A;
-    WCK((launch_gemm<MODE_KK, 32, EPI_BIAS_F32>(th2, n.tm_w3t, g, 1, st)));
-    return 3;
-}
-
-int wide_forward_backward(WideState *w, const WideStep &s, cudaStream_t st, std::string &err)
+int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err)
 {
     const Dims &d = w->d;
     const Offsets &o = w->o;
@@ -696,32 +881,43 @@ int wide_forward_backward(WideState *w, const WideStep &s, cudaStream_t st, std:
     int launches = 0;
     {
         int n = B * (d.D >> 2);
-        wide_gather_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.rp, d.D, s.idx, B, w->x, w->x2, w->ba, w->br, w->bdone);
+        wide_gather_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.rp, d.D, s.idx, s.seed, s.idx_out, B, w->x, w->x2, w->ba,
+                                                           w->br, w->bdone);
         WCK(cudaGetLastError());
         launches++;
     }
-    int k = forward_net(w, 0, w->tm_x_a, w->tm_h1_a, w->tm_h2_a, w->h1, w->h2, w->q, s.theta, st, err);
-    if (k < 0) return -1;
-    launches += k;
-    k = forward_net(w, 1, w->tm_x2_a, w->tm_t1_a, w->tm_t2_a, w->t1, w->t2, w->qt, s.theta_t, st, err);
-    if (k < 0) return -1;
-    launches += k;
-    {
-        size_t smem = sizeof(float) * ((size_t)2 * d.H2 * d.A + TD_ROWS) + sizeof(int) * TD_ROWS;
-        static bool conf = false;
-        if (!conf && smem > 48 * 1024) {
-            WCK(cudaFuncSetAttribute(wide_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            conf = true;
-        }
-        int threads = d.H2 < 512 ? ((d.H2 + 31) / 32) * 32 : 512;
-        if (threads < TD_ROWS) threads = TD_ROWS;
-        wide_td_kernel<<<w->ntd, threads, smem, st>>>(w->q, w->qt, w->ba, w->br, w->bdone, B, d.H2, d.A, s.theta + o.w3,
-                                                       w->h2, s.sc, w->td, w->dz2, w->td_part);
-        WCK(cudaGetLastError());
-        launches++;
-    }
+    // forward, online (problem 0) and target (problem 1) in one launch per layer
+    WideNet &on = w->net[0], &tg = w->net[1];
     GemmArgs g{};
+    g.M = B; g.N = d.H1; g.K = d.D; g.k_per_split = ((d.D + BK - 1) / BK) * BK;
+    g.out_bf16 = w->h1; g.out_bf16_1 = w->t1; g.bias = s.theta + o.b1; g.bias_1 = s.theta_t + o.b1;
+    g.ldo = d.H1; g.n_store = d.H1;
+    WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_x_a, on.tm_w1_mn, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn)));
+    g.N = d.H2; g.K = d.H1; g.k_per_split = ((d.H1 + BK - 1) / BK) * BK;
+    g.out_bf16 = w->h2; g.out_bf16_1 = w->t2; g.bias = s.theta + o.b2; g.bias_1 = s.theta_t + o.b2;
+    g.ldo = d.H2; g.n_store = d.H2;
+    WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_h1_a, on.tm_w2_mn, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn)));
+    g.N = W3_PAD; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
+    g.out_bf16 = g.out_bf16_1 = nullptr; g.out_f32 = w->q; g.out_f32_1 = w->qt;
+    g.bias = s.theta + o.b3; g.bias_1 = s.theta_t + o.b3; g.ldo = d.A; g.n_store = d.A;
+    WCK((launch_gemm<MODE_KM, 64, EPI_BIAS_F32>(w->tm_h2_a, on.tm_w3p_mn, g, 1, st, &w->tm_t2_a, &tg.tm_w3p_mn)));
+    launches += 3;
+
+    wide_td_rows_kernel<<<w->nrow, ROWS_TB, 0, st>>>(w->q, w->qt, w->ba, w->br, w->bdone, B, d.A, s.sc, w->td, w->dqv,
+                                                      w->dqT, w->row_part);
+    WCK(cudaGetLastError());
+    wide_dz2_kernel<<<w->nb2, 256, sizeof(float) * 4 * d.H2, st>>>(w->h2, on.w3t, w->dqv, w->ba, B, d.H2, w->dz2,
+                                                                    w->b2_part);
+    WCK(cudaGetLastError());
+    launches += 2;
+
+    // dW3 = H2^T dQ : M = H2, N = 32 (A stored), K = B ; A MN-major (h2 as stored), B = dQ^T K-major
+    g = GemmArgs{};
+    g.M = d.H2; g.N = 32; g.K = B; g.k_per_split = w->kps3;
+    g.out_f32 = w->w3_slices; g.ldo = d.A; g.n_store = d.A; g.slice_stride = (long long)d.H2 * d.A;
+    WCK((launch_gemm<MODE_MK, 32, EPI_F32_SLICE>(w->tm_h2_mm, w->tm_dqT_b, g, w->ns3, st)));
     // dW2 = H1^T dZ2 : M = H1, N = H2, K = B
+    g = GemmArgs{};
     g.M = d.H1; g.N = d.H2; g.K = B; g.k_per_split = w->kps2;
     g.out_f32 = w->w2_slices; g.ldo = d.H2; g.n_store = d.H2; g.slice_stride = (long long)d.H1 * d.H2;
     WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, st)));
@@ -729,7 +925,7 @@ int wide_forward_backward(WideState *w, const WideStep &s, cudaStream_t st, std:
     g = GemmArgs{};
     g.M = B; g.N = d.H1; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = w->dz1; g.mask_src = w->h1; g.ldo = d.H1; g.n_store = d.H1;
-    WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16>(w->tm_dz2_a, w->net[0].tm_w2, g, 1, st)));
+    WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16>(w->tm_dz2_a, on.tm_w2_k, g, 1, st)));
     // dW1 = X^T dZ1 : M = D, N = H1, K = B
     g = GemmArgs{};
     g.M = d.D; g.N = d.H1; g.K = B; g.k_per_split = w->kps1;
@@ -740,10 +936,26 @@ int wide_forward_backward(WideState *w, const WideStep &s, cudaStream_t st, std:
         wide_colsum_kernel<<<grid, 256, 0, st>>>(w->dz1, B, d.H1, w->b1_part);
         WCK(cudaGetLastError());
     }
-    wide_reduce_kernel<<<(o.P + 1 + 31) / 32, 256, 0, st>>>(d, o, w->w1_slices, w->ns1, w->w2_slices, w->ns2, w->b1_part,
-                                                           w->nb1, w->td_part, w->ntd, s.sc.count, s.flat);
-    WCK(cudaGetLastError());
     launches += 5;
+
+    PartialSrc ps{w->w1_slices, w->ns1, w->b1_part, w->nb1, w->w2_slices, w->ns2,
+                  w->b2_part,   w->nb2, w->w3_slices, w->ns3, w->row_part, w->nrow};
+    UpdatePlan pl;
+    pl.nA = (d.D * d.H1 + d.H1 * d.H2 + d.H2 * d.A) >> 2;
+    pl.nB = (d.H1 + d.H2) >> 2;
+    pl.nC = d.A + 1;
+    pl.blocksA = (pl.nA + 127) / 128;
+    pl.blocksB = (pl.nB + 3) / 4;
+    pl.blocksC = (pl.nC + 3) / 4;
+    const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
+    if (s.fuse_update)
+        wide_update_kernel<true><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
+                                                         shadow_ptrs(w, 0));
+    else
+        wide_update_kernel<false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
+                                                          s.adam, shadow_ptrs(w, 0));
+    WCK(cudaGetLastError());
+    launches++;
     return launches;
 }
 
@@ -786,6 +998,15 @@ int wide_selftest_gemm(int mode, int M, int N, int K, int nsplit, const uint16_t
     } else if (mode == 2) {   // KK with the 32-wide N tile
         if (!make_tmap(&ta, dA, M, K, K, BM, err) || !make_tmap(&tb, dB, N, K, K, 32, err)) return -1;
         WCK((launch_gemm<MODE_KK, 32, EPI_F32_SLICE>(ta, tb, g, nsplit, 0)));
+    } else if (mode == 3) {   // MK: A MN-major [K][M], B K-major [N=32][K]
+        if (!make_tmap(&ta, dA, K, M, M, 64, err) || !make_tmap(&tb, dB, N, K, K, 32, err)) return -1;
+        WCK((launch_gemm<MODE_MK, 32, EPI_F32_SLICE>(ta, tb, g, nsplit, 0)));
+    } else if (mode == 4) {   // KM: A K-major [M][K], B MN-major [K][N]
+        if (!make_tmap(&ta, dA, M, K, K, BM, err) || !make_tmap(&tb, dB, K, N, N, 64, err)) return -1;
+        WCK((launch_gemm<MODE_KM, 128, EPI_F32_SLICE>(ta, tb, g, nsplit, 0)));
+    } else if (mode == 5) {   // KM with the 64-wide N tile
+        if (!make_tmap(&ta, dA, M, K, K, BM, err) || !make_tmap(&tb, dB, K, N, N, 64, err)) return -1;
+        WCK((launch_gemm<MODE_KM, 64, EPI_F32_SLICE>(ta, tb, g, nsplit, 0)));
     } else {
         err = "selftest: unknown mode";
         return -1;

@@ -10,12 +10,17 @@ struct WideState;
 
 struct WideStep {
     Replay rp;
-    const int32_t *idx;    // [B] device
+    const int32_t *idx;    // [B] device, or nullptr: draw on the device from `seed`
+    uint64_t seed;
+    int32_t *idx_out;      // where device-drawn indices are recorded (nullable)
     int B;
     const float *theta;    // fp32 master parameters (biases are read from here)
     const float *theta_t;
     float *flat;           // [P+1] out: reduced gradient + loss
     StepScalars sc;
+    int fuse_update;       // 1: Adam + bf16 shadow refresh in the reduction kernel
+    float *theta_rw, *m, *v;
+    AdamConsts adam;
 };
 
 WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err);
@@ -24,7 +29,7 @@ void wide_destroy(WideState *w);
 int wide_set_params(WideState *w, int net, const float *theta_dev, cudaStream_t st, std::string &err);
 int wide_after_update(WideState *w, const float *theta_dev, cudaStream_t st, std::string &err);
 int wide_sync_target(WideState *w, cudaStream_t st, std::string &err);
-int wide_forward_backward(WideState *w, const WideStep &s, cudaStream_t st, std::string &err);
+int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err);
 void wide_set_debug(WideState *w, bool on);
 void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const float **td);
 const uint8_t *wide_done_ptr(WideState *w);

@@ -1,5 +1,5 @@
 """Stand-alone checks of the hand-written tcgen05 GEMM tiles (umma_gemm_kernel)
-against numpy on the same bf16 operands: both operand layouts, the 32-wide N tile,
+against numpy on the same bf16 operands: all operand layouts (KK, MM, MK), the 32-wide N tile,
 ragged shapes (TMA zero-fill + store guards) and split-K slices."""
 import numpy as np
 import pytest
@@ -23,6 +23,8 @@ def bf16_bits(x):
     (2, 128, 32, 64, 1), (2, 384, 32, 512, 1), (2, 100, 18, 512, 1),
     (1, 128, 128, 64, 1), (1, 128, 128, 256, 1), (1, 512, 512, 1024, 4), (1, 128, 512, 8192, 32),
     (1, 136, 200, 100, 2),
+    (3, 128, 32, 64, 1), (3, 512, 32, 8192, 32), (3, 256, 32, 1000, 3),
+    (4, 128, 128, 128, 1), (4, 8192, 512, 512, 1), (4, 200, 136, 72, 1), (5, 256, 64, 512, 1), (5, 100, 64, 128, 1),
 ])
 def test_umma_gemm_matches_numpy(mode, M, N, K, nsplit):
     rng = np.random.Generator(np.random.PCG64(M * 7 + N * 3 + K + mode))
@@ -36,6 +38,12 @@ def test_umma_gemm_matches_numpy(mode, M, N, K, nsplit):
             pytest.skip("MN-major operands need a 16-byte row pitch")
         abits = np.ascontiguousarray(abits.T)      # [K][M]
         bbits = np.ascontiguousarray(bbits.T)      # [K][N]
+    elif mode == 3:
+        abits = np.ascontiguousarray(abits.T)      # A MN-major [K][M], B stays K-major [N][K]
+    elif mode in (4, 5):
+        if (K % 8) or (N % 8):
+            pytest.skip("16-byte row pitch")
+        bbits = np.ascontiguousarray(bbits.T)      # A K-major [M][K], B MN-major [K][N]
     elif K % 8:
         pytest.skip("K-major operands need a 16-byte row pitch")
     if mode == 2 and N < 32:
