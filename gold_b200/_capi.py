@@ -25,7 +25,7 @@ SYMBOLS = [
     "goldq_abi_version", "goldq_param_count", "goldq_selected_path", "goldq_set_params",
     "goldq_get_params", "goldq_set_adam_state", "goldq_get_adam_state", "goldq_replay_push",
     "goldq_replay_len", "goldq_replay_push_wait", "goldq_host_alloc", "goldq_host_free",
-    "goldq_learn", "goldq_learn_device_indices", "goldq_sampler_indices", "goldq_sync_target",
+    "goldq_learn", "goldq_learn_device_indices", "goldq_learn_many", "goldq_sampler_indices", "goldq_sync_target",
     "goldq_last_loss", "goldq_predict", "goldq_greedy_action", "goldq_fit_batch",
     "goldq_dp_unique_id", "goldq_dp_init", "goldq_sync", "goldq_stream", "goldq_launch_count",
     "goldq_debug_enable", "goldq_debug_fetch", "goldq_timer_start", "goldq_timer_stop",
@@ -83,6 +83,7 @@ def lib():
         "goldq_host_free": (None, [vp]),
         "goldq_learn": (C.c_int, [vp, vp, u64]),
         "goldq_learn_device_indices": (C.c_int, [vp, vp]),
+        "goldq_learn_many": (C.c_int, [vp, i32, u64]),
         "goldq_sampler_indices": (C.c_int, [i64, i32, u64, i32, ip]),
         "goldq_sync_target": (C.c_int, [vp]),
         "goldq_last_loss": (C.c_int, [vp, fp]),
@@ -234,6 +235,9 @@ class Handle:
 
     def learn_raw(self, idx_host_ptr, seed=0):
         self._ck(self._L.goldq_learn(self._h, idx_host_ptr, seed))
+
+    def learn_many(self, n, seed=0):
+        self._ck(self._L.goldq_learn_many(self._h, n, seed))
 
     def learn_device_indices(self, dev_ptr):
         self._ck(self._L.goldq_learn_device_indices(self._h, dev_ptr))

@@ -113,6 +113,17 @@ struct goldq {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     std::string err;
+
+    // CUDA-graph replay of learn steps (goldq_learn_many)
+    static constexpr int GRAPH_MAX = 32;
+    StepDev *d_steps = nullptr;                  // [GRAPH_MAX] per-step scalars read by captured kernels
+    StepDev *h_steps[2] = {nullptr, nullptr};    // pinned staging, double buffered
+    cudaEvent_t ev_steps[2] = {nullptr, nullptr};
+    int steps_buf = 0;
+    cudaGraphExec_t graph_exec[GRAPH_MAX + 1] = {};
+    int64_t graph_launches[GRAPH_MAX + 1] = {};
+    int64_t graph_head = -1, graph_len = -1;     // replay state the cached graphs were captured with
+    bool graph_debug = false;
 };
 
 namespace {
@@ -249,7 +260,7 @@ int allreduce_flat(goldq_t *h)
     return GOLDQ_OK;
 }
 
-int learn_generic(goldq_t *h, const int32_t *idx_dev)
+int learn_generic(goldq_t *h, const int32_t *idx_dev, const StepDev *step)
 {
     int rc = ensure_generic(h, h->B);
     if (rc) return rc;
@@ -270,19 +281,20 @@ int learn_generic(goldq_t *h, const int32_t *idx_dev)
     rc = allreduce_flat(h);
     if (rc) return rc;
     h->iter += 1;
-    launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), h->st);
+    launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), step, h->st);
     h->launches += 1;
     CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
     return check_launch(h, "learn_generic");
 }
 
-int learn_narrow(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
+int learn_narrow(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev *step)
 {
     NarrowArgs a{};
     a.dims = h->dims;
     a.rp = h->rp;
     a.idx = idx_dev;
     a.seed = seed;
+    a.step = step;
     a.B = h->B;
     a.replicas = h->R;
     a.theta = h->theta;
@@ -312,7 +324,7 @@ int learn_narrow(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
     if (h->world > 1) {
         rc = allreduce_flat(h);
         if (rc) return rc;
-        launch_adam(h->theta, h->flat, h->m, h->v, h->P, a.adam, h->st);
+        launch_adam(h->theta, h->flat, h->m, h->v, h->P, a.adam, step, h->st);
         h->launches += 1;
         CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice,
                               h->st));
@@ -320,12 +332,13 @@ int learn_narrow(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
     return check_launch(h, "learn_narrow");
 }
 
-int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
+int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev *step)
 {
     WideStep ws{};
     ws.rp = h->rp;
     ws.idx = idx_dev;
     ws.seed = seed;
+    ws.step = step;
     ws.idx_out = h->d_idx;
     ws.B = h->B;
     ws.theta = h->theta;
@@ -345,7 +358,7 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
     if (h->world > 1) {
         int rc = allreduce_flat(h);
         if (rc) return rc;
-        launch_adam(h->theta, h->flat, h->m, h->v, h->P, ws.adam, h->st);
+        launch_adam(h->theta, h->flat, h->m, h->v, h->P, ws.adam, step, h->st);
         h->launches += 1;
         n = wide_after_update(h->wide, h->theta, h->st, err);   // refresh the bf16 shadow of the online net
         if (n < 0) return fail(h, GOLDQ_ECUDA, err);
@@ -355,17 +368,45 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
     return check_launch(h, "learn_wide");
 }
 
-int run_learn(goldq_t *h, const int32_t *idx_dev, uint64_t seed)
+int run_learn(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev *step = nullptr)
 {
     if (h->rp.len < h->B) return fail(h, GOLDQ_ENOTREADY, "replay shorter than batch");
-    if (h->path == GOLDQ_PATH_NARROW) return learn_narrow(h, idx_dev, seed);
-    if (h->path == GOLDQ_PATH_WIDE) return learn_wide(h, idx_dev, seed);
+    if (h->path == GOLDQ_PATH_NARROW) return learn_narrow(h, idx_dev, seed, step);
+    if (h->path == GOLDQ_PATH_WIDE) return learn_wide(h, idx_dev, seed, step);
     if (!idx_dev) {
-        launch_sample_indices(h->d_idx, h->B, h->rp.len, seed, h->R, h->st);
+        launch_sample_indices(h->d_idx, h->B, h->rp.len, seed, step, h->R, h->st);
         h->launches += 1;
         idx_dev = h->d_idx;
     }
-    return learn_generic(h, idx_dev);
+    return learn_generic(h, idx_dev, step);
+}
+
+void drop_graphs(goldq_t *h)
+{
+    for (int i = 0; i <= goldq::GRAPH_MAX; i++)
+        if (h->graph_exec[i]) { cudaGraphExecDestroy(h->graph_exec[i]); h->graph_exec[i] = nullptr; }
+}
+
+// Capture c consecutive learn steps (device sampler, per-step scalars from d_steps[i]) into
+// one executable graph.  Kernel arguments are frozen at capture time, so the cache is keyed
+// on everything they contain that can change: the replay ring position and the debug flag.
+int build_graph(goldq_t *h, int c)
+{
+    const int64_t iter0 = h->iter, launches0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    CK(h, cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+    int rc = GOLDQ_OK;
+    for (int i = 0; i < c && rc == GOLDQ_OK; i++) rc = run_learn(h, nullptr, 0, h->d_steps + i);
+    cudaError_t e = cudaStreamEndCapture(h->st, &graph);
+    h->graph_launches[c] = h->launches - launches0;
+    h->iter = iter0;            // capturing executes nothing
+    h->launches = launches0;
+    if (rc != GOLDQ_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(h, GOLDQ_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->graph_exec[c], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(h, GOLDQ_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    return GOLDQ_OK;
 }
 
 __global__ void replay_scatter_kernel(Replay rp, int D, int R, int64_t n, int64_t skip,
@@ -497,6 +538,12 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
     cudaEventCreateWithFlags(&h->ev_push, cudaEventDisableTiming);
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&h->ev_steps[i], cudaEventDisableTiming);
+        if (cudaHostAlloc((void **)&h->h_steps[i], sizeof(StepDev) * goldq::GRAPH_MAX, cudaHostAllocDefault) != cudaSuccess)
+            return bail("cudaHostAlloc failed (step slots)");
+    }
+    if (dalloc(&h->d_steps, (size_t)goldq::GRAPH_MAX) != cudaSuccess) return bail("cudaMalloc failed (step slots)");
 
     size_t RP = (size_t)h->R * h->P;
     bool ok = true;
@@ -530,6 +577,7 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
         narrow_plan(a, h->sm_count);
         h->n_ctas = a.ctas_per_replica;
         h->n_warps = a.warps_per_cta;
+        narrow_configure(h->dims, h->n_warps);
         size_t nt = (size_t)h->R * (NARROW_MAX_GROUPS + 1);
         ok &= dalloc(&h->partial, (size_t)h->R * narrow_partial_floats(h->n_ctas, h->P)) == cudaSuccess;
         ok &= dalloc(&h->ticket, nt) == cudaSuccess;
@@ -550,6 +598,12 @@ void goldq_destroy(goldq_t *h)
     if (!h) return;
     cudaSetDevice(h->dev);
     if (h->st) cudaStreamSynchronize(h->st);
+    drop_graphs(h);
+    for (int i = 0; i < 2; i++) {
+        if (h->h_steps[i]) cudaFreeHost(h->h_steps[i]);
+        if (h->ev_steps[i]) cudaEventDestroy(h->ev_steps[i]);
+    }
+    if (h->d_steps) cudaFree(h->d_steps);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->wide) wide_destroy(h->wide);
     void *ptrs[] = {h->theta, h->theta_t, h->m, h->v, h->flat, h->loss, h->d_idx, h->rp.s, h->rp.s2,
@@ -715,6 +769,47 @@ int goldq_learn_device_indices(goldq_t *h, const int32_t *idx_dev)
     return run_learn(h, idx_dev, 0);
 }
 
+int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
+{
+    if (!h || n < 0) return fail(h, GOLDQ_EINVAL, "learn_many: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    if (h->rp.len < h->B) return fail(h, GOLDQ_ENOTREADY, "replay shorter than batch");
+    if (h->path == GOLDQ_PATH_GENERIC) {          // no allocation may happen under capture
+        int rc = ensure_generic(h, h->B);
+        if (rc) return rc;
+    }
+    if (h->graph_head != h->rp.head || h->graph_len != h->rp.len || h->graph_debug != h->debug) {
+        drop_graphs(h);
+        h->graph_head = h->rp.head;
+        h->graph_len = h->rp.len;
+        h->graph_debug = h->debug;
+    }
+    while (n > 0) {
+        const int c = n < goldq::GRAPH_MAX ? n : goldq::GRAPH_MAX;
+        if (!h->graph_exec[c]) {
+            int rc = build_graph(h, c);
+            if (rc) return rc;
+        }
+        const int b = h->steps_buf;
+        h->steps_buf ^= 1;
+        CK(h, cudaEventSynchronize(h->ev_steps[b]));     // the staging buffer's previous copy has run
+        for (int i = 0; i < c; i++) {
+            AdamConsts ac = adam_consts(h->cfg, h->iter + 1 + i);
+            h->h_steps[b][i].seed = seed + (uint64_t)i;
+            h->h_steps[b][i].c1 = ac.c1;
+            h->h_steps[b][i].c2 = ac.c2;
+        }
+        CK(h, cudaMemcpyAsync(h->d_steps, h->h_steps[b], sizeof(StepDev) * c, cudaMemcpyHostToDevice, h->st));
+        CK(h, cudaEventRecord(h->ev_steps[b], h->st));
+        CK(h, cudaGraphLaunch(h->graph_exec[c], h->st));
+        h->iter += c;
+        h->launches += h->graph_launches[c];
+        seed += (uint64_t)c;
+        n -= c;
+    }
+    return GOLDQ_OK;
+}
+
 int goldq_sync_target(goldq_t *h)
 {
     if (!h) return GOLDQ_EINVAL;
@@ -821,7 +916,7 @@ int goldq_fit_batch(goldq_t *h, int64_t n, const float *x, const float *y)
     launch_reduce_slices(h->gslice, h->P, h->nsplit, h->P, h->loss_part, nlp, sc.count, h->flat,
                          h->st);
     h->iter += 1;
-    launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), h->st);
+    launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), nullptr, h->st);
     h->launches += 2;
     CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
     if (h->wide) {

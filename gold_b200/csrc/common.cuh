@@ -51,6 +51,14 @@ struct AdamConsts {
     float beta1, beta2, omb1, omb2, eps, neg_eta, c1, c2;
 };
 
+// Per-step scalars that live in DEVICE memory when a step is replayed from a CUDA graph
+// (goldq_learn_many): the kernel arguments of a captured step are frozen, so the sampler
+// seed and Adam's bias corrections of step i are read from slot i instead.
+struct StepDev {
+    unsigned long long seed;
+    float c1, c2;
+};
+
 // Scalars of one learn step.
 struct StepScalars {
     float gamma;
@@ -59,8 +67,8 @@ struct StepScalars {
 };
 
 // ---- generic path (kernels_generic.cu) -----------------------------------
-void launch_sample_indices(int32_t *idx, int B, int64_t len, uint64_t seed, int replicas,
-                           cudaStream_t st);
+void launch_sample_indices(int32_t *idx, int B, int64_t len, uint64_t seed, const StepDev *step,
+                           int replicas, cudaStream_t st);
 void launch_gather(const Replay &rp, int D, const int32_t *idx, int B, float *bs, float *bs2,
                    int32_t *ba, float *br, uint8_t *bdone, cudaStream_t st);
 void launch_fc_forward(const float *X, const float *W, const float *bias, float *Y,
@@ -85,7 +93,7 @@ void launch_reduce_slices(const float *gslice, int64_t slice_stride, int nsplit,
                           cudaStream_t st);
 // Fused Adam incl. the reference's double update; replicas laid out [R][P].
 void launch_adam(float *w, const float *g, float *m, float *v, int64_t n, AdamConsts c,
-                 cudaStream_t st);
+                 const StepDev *step, cudaStream_t st);
 void launch_argmax_rows(const float *q, int n, int A, int32_t *out, cudaStream_t st);
 
 // ---- narrow fused path (kernels_narrow.cu) --------------------------------
@@ -98,6 +106,7 @@ struct NarrowArgs {
     Replay rp;
     const int32_t *idx;   // [R][B] or nullptr -> sample on device
     uint64_t seed;
+    const StepDev *step;  // non-null: seed / c1 / c2 come from device memory (graph replay)
     int B;
     int replicas;
     float *theta;         // [R][P]
@@ -117,6 +126,7 @@ struct NarrowArgs {
     int warps_per_cta;
 };
 void narrow_plan(NarrowArgs &a, int sm_count);
+void narrow_configure(const Dims &d, int warps_per_cta);
 void launch_narrow_learn(const NarrowArgs &a, cudaStream_t st);
 
 }  // namespace gq

@@ -17,19 +17,20 @@ namespace gq {
 // (replaces rand.Perm(Len)[:B], pkg/v1/agent/deepq/memory.go:54-69)
 // ---------------------------------------------------------------------------
 __global__ void sample_indices_kernel(int32_t *__restrict__ idx, int B, uint32_t len, uint64_t seed,
-                                      int replicas)
+                                      const StepDev *__restrict__ step, int replicas)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * replicas) return;
+    if (step) seed = step->seed;
     int rep = t / B, b = t - rep * B;
     idx[t] = (int32_t)perm_index((uint32_t)b, len, seed + 0x9E3779B97F4A7C15ull * (uint64_t)rep);
 }
 
-void launch_sample_indices(int32_t *idx, int B, int64_t len, uint64_t seed, int replicas,
-                           cudaStream_t st)
+void launch_sample_indices(int32_t *idx, int B, int64_t len, uint64_t seed, const StepDev *step,
+                           int replicas, cudaStream_t st)
 {
     int n = B * replicas;
-    sample_indices_kernel<<<(n + 255) / 256, 256, 0, st>>>(idx, B, (uint32_t)len, seed, replicas);
+    sample_indices_kernel<<<(n + 255) / 256, 256, 0, st>>>(idx, B, (uint32_t)len, seed, step, replicas);
 }
 
 // ---------------------------------------------------------------------------
@@ -457,10 +458,11 @@ __device__ __forceinline__ void adam_update(float &w, float g, float &m, float &
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restrict__ m,
-            float *__restrict__ v, int64_t n, AdamConsts c)
+            float *__restrict__ v, int64_t n, AdamConsts c, const StepDev *__restrict__ step)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (step) { c.c1 = step->c1; c.c2 = step->c2; }
     float wi = w[i], mi = m[i], vi = v[i];
     adam_update(wi, g[i], mi, vi, c);
     w[i] = wi;
@@ -469,9 +471,9 @@ adam_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restric
 }
 
 void launch_adam(float *w, const float *g, float *m, float *v, int64_t n, AdamConsts c,
-                 cudaStream_t st)
+                 const StepDev *step, cudaStream_t st)
 {
-    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, m, v, n, c);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, m, v, n, c, step);
 }
 
 __global__ void argmax_rows_kernel(const float *__restrict__ q, int n, int A,

@@ -66,6 +66,11 @@ narrow_learn_kernel(NarrowArgs p)
     float *sPart = sW2T + H1 * H2; // [warps][P1] per-warp gradient partials
     __shared__ int sFlag;
 
+    if (p.step) {   // graph replay: per-step scalars live in device memory
+        p.seed = p.step->seed;
+        p.adam.c1 = p.step->c1;
+        p.adam.c2 = p.step->c2;
+    }
     const int rep = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31;
     // shuffled from lane 0 so that the compiler knows it is warp-uniform (no
@@ -366,14 +371,31 @@ void launch_t(const NarrowArgs &a, cudaStream_t st)
 {
     constexpr int P = D * H1 + H1 + H1 * H2 + H2 + H2 * A + A;
     size_t smem = sizeof(float) * (2 * P + H1 * H2 + (size_t)a.warps_per_cta * (P + 1));
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(narrow_learn_kernel<D, H1, H2, A>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(a.ctas_per_replica, a.replicas);
     narrow_learn_kernel<D, H1, H2, A><<<grid, a.warps_per_cta * 32, smem, st>>>(a);
 }
 
+template <int D, int H1, int H2, int A>
+void configure_t(int warps)
+{
+    constexpr int P = D * H1 + H1 + H1 * H2 + H2 + H2 * A + A;
+    size_t smem = sizeof(float) * (2 * P + H1 * H2 + (size_t)warps * (P + 1));
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(narrow_learn_kernel<D, H1, H2, A>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
 }  // namespace
+
+// opt in to > 48 KB of dynamic shared memory once, at handle creation (not at launch:
+// launches may be under stream capture)
+void narrow_configure(const Dims &d, int warps)
+{
+    if (d.D == 4 && d.A == 2) configure_t<4, 24, 24, 2>(warps);
+    else if (d.D == 2 && d.A == 3) configure_t<2, 24, 24, 3>(warps);
+    else if (d.D == 6 && d.A == 3) configure_t<6, 24, 24, 3>(warps);
+    else if (d.D == 8 && d.A == 4) configure_t<8, 24, 24, 4>(warps);
+}
 
 // Instantiated for gym's classic-control observation/action shapes behind
 // deepq.DefaultFCLayerBuilder's 24-24 hidden layers (pkg/v1/agent/deepq/policy.go:53-59):

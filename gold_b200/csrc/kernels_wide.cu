@@ -296,18 +296,34 @@ bool make_tmap(CUtensorMap *m, const void *base, int rows, int cols, int ld, int
 }
 
 // one problem (ta1/tb1 = nullptr) or two problems sharing the launch
+// opt in to the dynamic shared memory of one instantiation (called at create time, never
+// under stream capture)
+template <int MODE, int BN, int EPI>
+cudaError_t configure_gemm()
+{
+    return cudaFuncSetAttribute(umma_gemm_kernel<MODE, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)gemm_smem_bytes<MODE, BN>());
+}
+
+cudaError_t configure_all_gemms()
+{
+    cudaError_t e = configure_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KM, 64, EPI_BIAS_F32>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_MK, 32, EPI_F32_SLICE>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_MM, 128, EPI_F32_SLICE>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KK, 128, EPI_MASK_BF16>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KK, 128, EPI_F32_SLICE>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KK, 32, EPI_F32_SLICE>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KM, 128, EPI_F32_SLICE>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KM, 64, EPI_F32_SLICE>();
+    return e;
+}
+
 template <int MODE, int BN, int EPI>
 cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, GemmArgs g, int nsplit, cudaStream_t st,
                         const CUtensorMap *ta1 = nullptr, const CUtensorMap *tb1 = nullptr)
 {
     constexpr size_t smem = gemm_smem_bytes<MODE, BN>();
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<MODE, BN, EPI>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
     g.nsplit = nsplit;
     const int nprob = ta1 ? 2 : 1;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit * nprob);
@@ -321,14 +337,15 @@ cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, GemmArgs g
 // K1: sample (optional) + gather + fp32 -> bf16.  The replay stays fp32 in HBM; index
 // generation and the cast are fused into the gather.  One thread per 16-byte granule.
 __global__ void __launch_bounds__(256)
-wide_gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx, uint64_t seed, int32_t *__restrict__ idx_out,
-                   int B, __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ x2, int32_t *__restrict__ ba,
+wide_gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx, uint64_t seed,
+                   const StepDev *__restrict__ step, int32_t *__restrict__ idx_out, int B, __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ x2, int32_t *__restrict__ ba,
                    float *__restrict__ br, uint8_t *__restrict__ bdone)
 {
     const int chunks = D >> 2;  // float4 granules per row (D % 8 == 0 is required by the path)
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * chunks) return;
     int b = t / chunks, c = t - b * chunks;
+    if (step) seed = step->seed;
     const int32_t li = idx ? idx[b] : (int32_t)perm_index((uint32_t)b, (uint32_t)rp.len, seed);
     int64_t phys = rp.head - 1 - (int64_t)li;
     if (phys < 0) phys += rp.cap;
@@ -613,9 +630,11 @@ __device__ __forceinline__ void finish4(const Dims &d, const Offsets &o, int i, 
 template <bool FUSE>
 __global__ void __launch_bounds__(128)
 wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count, float *__restrict__ flat,
-                   float *__restrict__ theta, float *__restrict__ m, float *__restrict__ v, AdamConsts ac, ShadowPtrs sp)
+                   float *__restrict__ theta, float *__restrict__ m, float *__restrict__ v, AdamConsts ac,
+                   const StepDev *__restrict__ step, ShadowPtrs sp)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (FUSE && step) { ac.c1 = step->c1; ac.c2 = step->c2; }
     if ((int)blockIdx.x < pl.blocksA) {
         // ---- A: weights ------------------------------------------------------------
         const int gidx = blockIdx.x * 128 + threadIdx.x;
@@ -738,6 +757,10 @@ struct WideState {
     // activation tensor maps: KK A-operands (box 128 rows) and MN-major operands (box 64 k-rows)
     CUtensorMap tm_x_a, tm_x2_a, tm_h1_a, tm_t1_a, tm_h2_a, tm_t2_a, tm_dz2_a;
     CUtensorMap tm_x_mm, tm_h1_mm, tm_h2_mm, tm_dz2_mm, tm_dz1_mm, tm_dqT_b;
+    // side streams: independent backward GEMMs run concurrently (fork/join by events; under
+    // stream capture these become parallel branches of the step graph)
+    cudaStream_t s1 = nullptr, s2 = nullptr;
+    cudaEvent_t ev_dz2 = nullptr, ev_dx = nullptr, ev_s1 = nullptr, ev_s2 = nullptr;
     bool debug = false;
 };
 
@@ -759,6 +782,10 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     if (B % 8) { err = "bf16 path needs batch_size to be a multiple of 8 (16-byte pitch of dQ^T)"; return nullptr; }
     if (d.A > 32) { err = "bf16 path supports up to 32 actions"; return nullptr; }
     if (!load_encode(err)) return nullptr;
+    {
+        cudaError_t e = configure_all_gemms();
+        if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return nullptr; }
+    }
     WideState *w = new WideState();
     w->d = d;
     w->o = make_offsets(d);
@@ -814,6 +841,10 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     // dQ^T [32 rows][B cols]: K-major B operand of the dW3 GEMM, box 32 rows
     ok = ok && make_tmap(&w->tm_dqT_b, w->dqT, 32, B, B, 32, err);
     if (!ok) { wide_destroy(w); return nullptr; }
+    cudaStreamCreateWithFlags(&w->s1, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&w->s2, cudaStreamNonBlocking);
+    cudaEvent_t *evs[] = {&w->ev_dz2, &w->ev_dx, &w->ev_s1, &w->ev_s2};
+    for (cudaEvent_t *e : evs) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
     return w;
 }
 
@@ -829,6 +860,11 @@ void wide_destroy(WideState *w)
                  w->ba, w->bdone, w->w1_slices, w->w2_slices, w->w3_slices, w->b1_part, w->b2_part, w->row_part};
     for (void *q : p)
         if (q) cudaFree(q);
+    if (w->s1) cudaStreamDestroy(w->s1);
+    if (w->s2) cudaStreamDestroy(w->s2);
+    cudaEvent_t evs[] = {w->ev_dz2, w->ev_dx, w->ev_s1, w->ev_s2};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
     delete w;
 }
 
@@ -881,7 +917,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     int launches = 0;
     {
         int n = B * (d.D >> 2);
-        wide_gather_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.rp, d.D, s.idx, s.seed, s.idx_out, B, w->x, w->x2, w->ba,
+        wide_gather_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.rp, d.D, s.idx, s.seed, s.step, s.idx_out, B, w->x, w->x2, w->ba,
                                                            w->br, w->bdone);
         WCK(cudaGetLastError());
         launches++;
@@ -911,31 +947,41 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     WCK(cudaGetLastError());
     launches += 2;
 
+    // backward: three independent chains after dZ2 —  s1: dW2 | s2: dW3, db1 | st: dX -> dW1
+    WCK(cudaEventRecord(w->ev_dz2, st));
+    WCK(cudaStreamWaitEvent(w->s1, w->ev_dz2, 0));
+    WCK(cudaStreamWaitEvent(w->s2, w->ev_dz2, 0));
     // dW3 = H2^T dQ : M = H2, N = 32 (A stored), K = B ; A MN-major (h2 as stored), B = dQ^T K-major
     g = GemmArgs{};
     g.M = d.H2; g.N = 32; g.K = B; g.k_per_split = w->kps3;
     g.out_f32 = w->w3_slices; g.ldo = d.A; g.n_store = d.A; g.slice_stride = (long long)d.H2 * d.A;
-    WCK((launch_gemm<MODE_MK, 32, EPI_F32_SLICE>(w->tm_h2_mm, w->tm_dqT_b, g, w->ns3, st)));
+    WCK((launch_gemm<MODE_MK, 32, EPI_F32_SLICE>(w->tm_h2_mm, w->tm_dqT_b, g, w->ns3, w->s2)));
     // dW2 = H1^T dZ2 : M = H1, N = H2, K = B
     g = GemmArgs{};
     g.M = d.H1; g.N = d.H2; g.K = B; g.k_per_split = w->kps2;
     g.out_f32 = w->w2_slices; g.ldo = d.H2; g.n_store = d.H2; g.slice_stride = (long long)d.H1 * d.H2;
-    WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, st)));
+    WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, w->s1)));
+    WCK(cudaEventRecord(w->ev_s1, w->s1));
     // dZ1 = (dZ2 W2^T) * mask1 : M = B, N = H1, K = H2 ; B operand = W2 [H1 rows][H2 cols]
     g = GemmArgs{};
     g.M = B; g.N = d.H1; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = w->dz1; g.mask_src = w->h1; g.ldo = d.H1; g.n_store = d.H1;
     WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16>(w->tm_dz2_a, on.tm_w2_k, g, 1, st)));
+    WCK(cudaEventRecord(w->ev_dx, st));
+    WCK(cudaStreamWaitEvent(w->s2, w->ev_dx, 0));
+    {
+        dim3 grid((d.H1 + 63) / 64, w->nb1);
+        wide_colsum_kernel<<<grid, 256, 0, w->s2>>>(w->dz1, B, d.H1, w->b1_part);
+        WCK(cudaGetLastError());
+    }
+    WCK(cudaEventRecord(w->ev_s2, w->s2));
     // dW1 = X^T dZ1 : M = D, N = H1, K = B
     g = GemmArgs{};
     g.M = d.D; g.N = d.H1; g.K = B; g.k_per_split = w->kps1;
     g.out_f32 = w->w1_slices; g.ldo = d.H1; g.n_store = d.H1; g.slice_stride = (long long)d.D * d.H1;
     WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_x_mm, w->tm_dz1_mm, g, w->ns1, st)));
-    {
-        dim3 grid((d.H1 + 63) / 64, w->nb1);
-        wide_colsum_kernel<<<grid, 256, 0, st>>>(w->dz1, B, d.H1, w->b1_part);
-        WCK(cudaGetLastError());
-    }
+    WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
+    WCK(cudaStreamWaitEvent(st, w->ev_s2, 0));
     launches += 5;
 
     PartialSrc ps{w->w1_slices, w->ns1, w->b1_part, w->nb1, w->w2_slices, w->ns2,
@@ -950,10 +996,10 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
     if (s.fuse_update)
         wide_update_kernel<true><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
-                                                         shadow_ptrs(w, 0));
+                                                         s.step, shadow_ptrs(w, 0));
     else
         wide_update_kernel<false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
-                                                          s.adam, shadow_ptrs(w, 0));
+                                                          s.adam, s.step, shadow_ptrs(w, 0));
     WCK(cudaGetLastError());
     launches++;
     return launches;
@@ -975,6 +1021,7 @@ int wide_selftest_gemm(int mode, int M, int N, int K, int nsplit, const uint16_t
                        std::string &err)
 {
     if (!load_encode(err)) return -1;
+    WCK(configure_all_gemms());
     if (nsplit < 1) nsplit = 1;
     __nv_bfloat16 *dA = nullptr, *dB = nullptr;
     float *dC = nullptr;

@@ -12,6 +12,7 @@ struct WideStep {
     Replay rp;
     const int32_t *idx;    // [B] device, or nullptr: draw on the device from `seed`
     uint64_t seed;
+    const StepDev *step;   // non-null: seed / c1 / c2 from device memory (graph replay)
     int32_t *idx_out;      // where device-drawn indices are recorded (nullable)
     int B;
     const float *theta;    // fp32 master parameters (biases are read from here)

@@ -303,3 +303,54 @@ def test_large_batch_linearity_property():
         return g
     g_all = grads(np.arange(B)); g_a = grads(np.arange(B // 2)); g_b = grads(np.arange(B // 2, B))
     np.testing.assert_allclose(g_all, 0.5 * (g_a + g_b), rtol=1e-4, atol=1e-6 * np.abs(g_all).max())
+
+
+@pytest.mark.parametrize("kind", ["narrow", "generic", "wide", "replicas"])
+def test_learn_many_graph_replay_equals_single_steps(kind):
+    """goldq_learn_many (CUDA-graph replay, per-step scalars in device memory) must be
+    bit-identical to the same steps issued one by one, across graph rebuilds."""
+    if kind == "wide":
+        dims, B, N, kw = (64, 256, 128, 6), 256, 2048, dict(precision=G.PREC_BF16)
+    elif kind == "generic":
+        dims, B, N, kw = (5, 17, 33, 3), 64, 512, dict(path=G.PATH_GENERIC)
+    elif kind == "replicas":
+        dims, B, N, kw = synth.CARTPOLE, 20, 256, dict(n_replicas=3)
+    else:
+        dims, B, N, kw = synth.CARTPOLE, 512, 4096, {}
+    R = kw.get("n_replicas", 1)
+    th = np.concatenate([synth.glorot_params(dims, 1 + r) for r in range(R)])
+    tt = np.concatenate([synth.glorot_params(dims, 40 + r) for r in range(R)])
+    parts = [synth.replay(dims, N, seed=5 + r) for r in range(R)]
+    data = [np.concatenate([p[k] for p in parts]) for k in range(5)]
+    more = [synth.replay(dims, 100, seed=70 + r) for r in range(R)]
+    more = [np.concatenate([p[k] for p in more]) for k in range(5)]
+
+    def run(many):
+        h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3], batch_size=B,
+                     replay_capacity=N, **kw)
+        h.set_params(G.NET_ONLINE, th); h.set_params(G.NET_TARGET, tt)
+        h.replay_push(*data)
+        seed = 1000
+        for n in (5, 37, 2):                       # 37 > 32: two graph chunks
+            if many:
+                h.learn_many(n, seed)
+            else:
+                for i in range(n):
+                    h.learn(None, seed + i)
+            seed += n
+            h.sync_target()
+        h.replay_push(*more)                       # moves the ring: cached graphs must be rebuilt
+        if many:
+            h.learn_many(4, seed)
+        else:
+            for i in range(4):
+                h.learn(None, seed + i)
+        w = h.get_params(G.NET_ONLINE); m, v, it = h.get_adam_state(); loss = h.last_loss()
+        h.close()
+        return w, m, v, it, loss
+
+    a, b = run(False), run(True)
+    assert a[3] == b[3] == 48
+    for x, y in zip(a[:3], b[:3]):
+        np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(a[4], b[4])

@@ -26,6 +26,16 @@ def probe(name, **kw):
         h.learn(None, seed=200 + i)
     t_issue = time.perf_counter() - t0
     ms = h.timer_stop()
+    h.sync()
+    for i in range(3):
+        h.learn_many(20, 5000 + 20 * i)
+    h.sync()
+    t0 = time.perf_counter(); h.timer_start()
+    for i in range(K // 20):
+        h.learn_many(20, 9000 + 20 * i)
+    t_issue_g = time.perf_counter() - t0
+    ms_g = h.timer_stop()
+    print(f"{name}: graph replay (20 steps/launch) {ms_g/K*1e3:.1f} us/step; host issue {t_issue_g/K*1e6:.2f} us/step")
     print(f"{name}: single-step GPU latency median {np.median(single)*1e3:.1f} us (min {min(single)*1e3:.1f}); "
           f"back-to-back {ms/K*1e3:.1f} us/step; host issue {t_issue/K*1e6:.1f} us/step; launches/step "
           f"{h.launch_count()/(K+40):.1f}", flush=True)
