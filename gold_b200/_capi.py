@@ -29,7 +29,7 @@ SYMBOLS = [
     "goldq_last_loss", "goldq_predict", "goldq_greedy_action", "goldq_fit_batch",
     "goldq_dp_unique_id", "goldq_dp_init", "goldq_sync", "goldq_stream", "goldq_launch_count",
     "goldq_debug_enable", "goldq_debug_fetch", "goldq_timer_start", "goldq_timer_stop",
-    "goldq_selftest_umma",
+    "goldq_selftest_umma", "goldq_step_breakdown",
 ]
 
 
@@ -100,6 +100,7 @@ def lib():
         "goldq_timer_start": (C.c_int, [vp]),
         "goldq_timer_stop": (C.c_int, [vp, fp]),
         "goldq_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, fp]),
+        "goldq_step_breakdown": (C.c_int, [vp, u64, i32, fp, ip, C.c_char_p, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -308,6 +309,15 @@ class Handle:
         out = np.empty(shape, dt)
         self._ck(self._L.goldq_debug_fetch(self._h, what, out.ctypes.data, out.nbytes))
         return out
+
+    def step_breakdown(self, seed=0):
+        """[(kernel label, ms)] of one eager, serialised learn step."""
+        ms = np.zeros(64, np.float32)
+        n = C.c_int32(0)
+        names = C.create_string_buffer(2048)
+        self._ck(self._L.goldq_step_breakdown(self._h, seed, 64, _f(ms), C.byref(n), names, 2048))
+        labels = names.value.decode().split("\n")
+        return [(labels[i] if i < len(labels) else f"kernel{i}", float(ms[i])) for i in range(n.value)]
 
     def timer_start(self):
         self._ck(self._L.goldq_timer_start(self._h))

@@ -124,6 +124,10 @@ struct goldq {
     int64_t graph_launches[GRAPH_MAX + 1] = {};
     int64_t graph_head = -1, graph_len = -1;     // replay state the cached graphs were captured with
     bool graph_debug = false;
+
+    // goldq_step_breakdown
+    cudaEvent_t *prof_evs = nullptr;
+    int prof_n = 0;
 };
 
 namespace {
@@ -351,6 +355,8 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     ws.v = h->v;
     h->iter += 1;
     ws.adam = adam_consts(h->cfg, h->iter);
+    ws.prof_evs = h->prof_evs;
+    ws.prof_n = &h->prof_n;
     std::string err;
     int n = wide_step(h->wide, ws, h->st, err);
     if (n < 0) return fail(h, GOLDQ_ECUDA, err);
@@ -808,6 +814,47 @@ int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
         n -= c;
     }
     return GOLDQ_OK;
+}
+
+/* Diagnostic: run ONE eager learn step (device sampler) with a CUDA event after every
+ * kernel launch, everything serialised on the handle's stream, and return the time of each
+ * launch.  Used by bench.py to time the dominant kernel live (roofline.achieved). */
+int goldq_step_breakdown(goldq_t *h, uint64_t seed, int32_t max_kernels, float *ms, int32_t *n_kernels,
+                         char *names, int32_t names_bytes)
+{
+    if (!h || !ms || !n_kernels || max_kernels < 1) return fail(h, GOLDQ_EINVAL, "step_breakdown: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    const int cap = 64;
+    std::vector<cudaEvent_t> evs(cap + 1);
+    for (auto &e : evs) CK(h, cudaEventCreate(&e));
+    CK(h, cudaStreamSynchronize(h->st));
+    int rc;
+    if (h->path == GOLDQ_PATH_WIDE) {
+        h->prof_evs = evs.data() + 1;
+        h->prof_n = 0;
+        CK(h, cudaEventRecord(evs[0], h->st));
+        rc = run_learn(h, nullptr, seed);
+        h->prof_evs = nullptr;
+        if (names && names_bytes > 0) snprintf(names, names_bytes, "%s", wide_step_kernel_names());
+    } else {
+        // single fused launch (narrow) or an unfused chain (generic): one interval for the step
+        CK(h, cudaEventRecord(evs[0], h->st));
+        rc = run_learn(h, nullptr, seed);
+        CK(h, cudaEventRecord(evs[1], h->st));
+        h->prof_n = 1;
+        if (names && names_bytes > 0)
+            snprintf(names, names_bytes, "%s", h->path == GOLDQ_PATH_NARROW ? "narrow_learn_kernel (whole step)" : "generic path (whole step)");
+    }
+    if (rc == GOLDQ_OK) {
+        cudaError_t e = cudaStreamSynchronize(h->st);
+        if (e != cudaSuccess) rc = fail(h, GOLDQ_ECUDA, cudaGetErrorString(e));
+    }
+    int n = h->prof_n < max_kernels ? h->prof_n : max_kernels;
+    if (rc == GOLDQ_OK)
+        for (int i = 0; i < n; i++) cudaEventElapsedTime(&ms[i], evs[i], evs[i + 1]);
+    *n_kernels = n;
+    for (auto &e : evs) cudaEventDestroy(e);
+    return rc;
 }
 
 int goldq_sync_target(goldq_t *h)

@@ -915,12 +915,16 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     const Offsets &o = w->o;
     const int B = w->B;
     int launches = 0;
+    const bool prof = s.prof_evs != nullptr;
+    cudaStream_t s1 = prof ? st : w->s1, s2 = prof ? st : w->s2;
+    auto mark = [&]() { if (prof) cudaEventRecord(s.prof_evs[(*s.prof_n)++], st); };
     {
         int n = B * (d.D >> 2);
         wide_gather_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.rp, d.D, s.idx, s.seed, s.step, s.idx_out, B, w->x, w->x2, w->ba,
                                                            w->br, w->bdone);
         WCK(cudaGetLastError());
         launches++;
+        mark();
     }
     // forward, online (problem 0) and target (problem 1) in one launch per layer
     WideNet &on = w->net[0], &tg = w->net[1];
@@ -929,59 +933,75 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g.out_bf16 = w->h1; g.out_bf16_1 = w->t1; g.bias = s.theta + o.b1; g.bias_1 = s.theta_t + o.b1;
     g.ldo = d.H1; g.n_store = d.H1;
     WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_x_a, on.tm_w1_mn, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn)));
+    mark();
     g.N = d.H2; g.K = d.H1; g.k_per_split = ((d.H1 + BK - 1) / BK) * BK;
     g.out_bf16 = w->h2; g.out_bf16_1 = w->t2; g.bias = s.theta + o.b2; g.bias_1 = s.theta_t + o.b2;
     g.ldo = d.H2; g.n_store = d.H2;
     WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_h1_a, on.tm_w2_mn, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn)));
+    mark();
     g.N = W3_PAD; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = g.out_bf16_1 = nullptr; g.out_f32 = w->q; g.out_f32_1 = w->qt;
     g.bias = s.theta + o.b3; g.bias_1 = s.theta_t + o.b3; g.ldo = d.A; g.n_store = d.A;
     WCK((launch_gemm<MODE_KM, 64, EPI_BIAS_F32>(w->tm_h2_a, on.tm_w3p_mn, g, 1, st, &w->tm_t2_a, &tg.tm_w3p_mn)));
+    mark();
     launches += 3;
 
     wide_td_rows_kernel<<<w->nrow, ROWS_TB, 0, st>>>(w->q, w->qt, w->ba, w->br, w->bdone, B, d.A, s.sc, w->td, w->dqv,
                                                       w->dqT, w->row_part);
     WCK(cudaGetLastError());
+    mark();
     wide_dz2_kernel<<<w->nb2, 256, sizeof(float) * 4 * d.H2, st>>>(w->h2, on.w3t, w->dqv, w->ba, B, d.H2, w->dz2,
                                                                     w->b2_part);
     WCK(cudaGetLastError());
+    mark();
     launches += 2;
 
     // backward: three independent chains after dZ2 —  s1: dW2 | s2: dW3, db1 | st: dX -> dW1
-    WCK(cudaEventRecord(w->ev_dz2, st));
-    WCK(cudaStreamWaitEvent(w->s1, w->ev_dz2, 0));
-    WCK(cudaStreamWaitEvent(w->s2, w->ev_dz2, 0));
+    if (!prof) {
+        WCK(cudaEventRecord(w->ev_dz2, st));
+        WCK(cudaStreamWaitEvent(s1, w->ev_dz2, 0));
+        WCK(cudaStreamWaitEvent(s2, w->ev_dz2, 0));
+    }
     // dW3 = H2^T dQ : M = H2, N = 32 (A stored), K = B ; A MN-major (h2 as stored), B = dQ^T K-major
     g = GemmArgs{};
     g.M = d.H2; g.N = 32; g.K = B; g.k_per_split = w->kps3;
     g.out_f32 = w->w3_slices; g.ldo = d.A; g.n_store = d.A; g.slice_stride = (long long)d.H2 * d.A;
-    WCK((launch_gemm<MODE_MK, 32, EPI_F32_SLICE>(w->tm_h2_mm, w->tm_dqT_b, g, w->ns3, w->s2)));
+    WCK((launch_gemm<MODE_MK, 32, EPI_F32_SLICE>(w->tm_h2_mm, w->tm_dqT_b, g, w->ns3, s2)));
+    mark();
     // dW2 = H1^T dZ2 : M = H1, N = H2, K = B
     g = GemmArgs{};
     g.M = d.H1; g.N = d.H2; g.K = B; g.k_per_split = w->kps2;
     g.out_f32 = w->w2_slices; g.ldo = d.H2; g.n_store = d.H2; g.slice_stride = (long long)d.H1 * d.H2;
-    WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, w->s1)));
-    WCK(cudaEventRecord(w->ev_s1, w->s1));
+    WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, s1)));
+    mark();
+    if (!prof) WCK(cudaEventRecord(w->ev_s1, s1));
     // dZ1 = (dZ2 W2^T) * mask1 : M = B, N = H1, K = H2 ; B operand = W2 [H1 rows][H2 cols]
     g = GemmArgs{};
     g.M = B; g.N = d.H1; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = w->dz1; g.mask_src = w->h1; g.ldo = d.H1; g.n_store = d.H1;
     WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16>(w->tm_dz2_a, on.tm_w2_k, g, 1, st)));
-    WCK(cudaEventRecord(w->ev_dx, st));
-    WCK(cudaStreamWaitEvent(w->s2, w->ev_dx, 0));
+    mark();
+    if (!prof) {
+        WCK(cudaEventRecord(w->ev_dx, st));
+        WCK(cudaStreamWaitEvent(s2, w->ev_dx, 0));
+    }
     {
         dim3 grid((d.H1 + 63) / 64, w->nb1);
-        wide_colsum_kernel<<<grid, 256, 0, w->s2>>>(w->dz1, B, d.H1, w->b1_part);
+        wide_colsum_kernel<<<grid, 256, 0, s2>>>(w->dz1, B, d.H1, w->b1_part);
         WCK(cudaGetLastError());
+        mark();
     }
-    WCK(cudaEventRecord(w->ev_s2, w->s2));
+    if (!prof) WCK(cudaEventRecord(w->ev_s2, s2));
     // dW1 = X^T dZ1 : M = D, N = H1, K = B
     g = GemmArgs{};
     g.M = d.D; g.N = d.H1; g.K = B; g.k_per_split = w->kps1;
     g.out_f32 = w->w1_slices; g.ldo = d.H1; g.n_store = d.H1; g.slice_stride = (long long)d.D * d.H1;
     WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_x_mm, w->tm_dz1_mm, g, w->ns1, st)));
-    WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
-    WCK(cudaStreamWaitEvent(st, w->ev_s2, 0));
+    mark();
+    if (!prof) {
+        WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
+        WCK(cudaStreamWaitEvent(st, w->ev_s2, 0));
+    }
     launches += 5;
 
     PartialSrc ps{w->w1_slices, w->ns1, w->b1_part, w->nb1, w->w2_slices, w->ns2,
@@ -1001,8 +1021,16 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         wide_update_kernel<false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
                                                           s.adam, s.step, shadow_ptrs(w, 0));
     WCK(cudaGetLastError());
+    mark();
     launches++;
     return launches;
+}
+
+const char *wide_step_kernel_names()
+{
+    return "gather+cast (K1)\nfwd L1 online+target (tcgen05)\nfwd L2 online+target (tcgen05)\nfwd L3 online+target (tcgen05)\n"
+           "TD rows (K3)\ndZ2 + db2\ndW3 (tcgen05)\ndW2 split-K (tcgen05)\ndX -> dZ1 (tcgen05)\ndb1 colsum\n"
+           "dW1 split-K (tcgen05)\nreduce + Adam + bf16 shadow (K5)";
 }
 
 void wide_set_debug(WideState *w, bool on) { w->debug = on; }

@@ -22,6 +22,9 @@ struct WideStep {
     int fuse_update;       // 1: Adam + bf16 shadow refresh in the reduction kernel
     float *theta_rw, *m, *v;
     AdamConsts adam;
+    // profiling (goldq_step_breakdown): record an event after every launch, single stream
+    cudaEvent_t *prof_evs;
+    int *prof_n;
 };
 
 WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err);
@@ -31,6 +34,7 @@ int wide_set_params(WideState *w, int net, const float *theta_dev, cudaStream_t 
 int wide_after_update(WideState *w, const float *theta_dev, cudaStream_t st, std::string &err);
 int wide_sync_target(WideState *w, cudaStream_t st, std::string &err);
 int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err);
+const char *wide_step_kernel_names();
 void wide_set_debug(WideState *w, bool on);
 void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const float **td);
 const uint8_t *wide_done_ptr(WideState *w);

@@ -188,6 +188,11 @@ int goldq_debug_fetch(goldq_t *h, int what, void *out, int64_t out_bytes);
 /* CUDA-event timer on the handle's stream (bench.py): start; ...; stop → ms. */
 int goldq_timer_start(goldq_t *h);
 int goldq_timer_stop(goldq_t *h, float *ms);
+/* Diagnostic: ONE eager learn step (device-drawn indices) with a CUDA event after every
+ * kernel launch, serialised on the handle's stream; ms[i] = duration of launch i,
+ * names = '\n'-joined kernel labels.  It is a real step (parameters are updated). */
+int goldq_step_breakdown(goldq_t *h, uint64_t seed, int32_t max_kernels, float *ms, int32_t *n_kernels,
+                         char *names, int32_t names_bytes);
 /* Diagnostic: run one stand-alone tcgen05 GEMM on device 0 and return fp32 C[M][N].
  * A, B are bf16 bit patterns.  mode 0: C = A[M][K] . B[N][K]^T (both K-major);
  * mode 1: C = A[K][M]^T . B[K][N] (both MN-major); mode 2: mode 0 with the 32-wide

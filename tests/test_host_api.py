@@ -1,0 +1,102 @@
+"""The host layer mirrors gold's deepq package; these tests read like the reference's own
+(pkg/v1/agent/deepq/memory_test.go, policy_test.go) with assertions added where the
+reference only logs."""
+import numpy as np
+import pytest
+
+from gold_b200 import deepq
+from gold_b200 import synth
+
+
+def test_memory():
+    # memory_test.go:12-29: push 10 events, Sample(5) returns 5
+    mem = deepq.Memory()
+    for i in range(10):
+        s = np.array([[i, i + 1, i + 2, i + 3]], np.float32)
+        ev = deepq.new_event(s, 0, deepq.Outcome(observation=s, action=i, reward=1.0, done=False))
+        mem.push_front(ev)
+    sample = mem.sample(5)
+    assert len(sample) == 5
+    assert len({e.i for e in sample}) == 5                       # distinct, like rand.Perm(Len)[:5]
+    for e in sample:
+        assert mem.at(e.i) is e                                   # event.i is its deque index (memory.go:62-63)
+    assert mem.at(0).outcome.action == 9                          # PushFront: newest at index 0
+    with pytest.raises(ValueError, match="queue size 10 is less than batch size 11"):
+        mem.sample(11)                                            # memory.go:55-57
+
+
+def test_decay_schedule():
+    # schedule.go:101-105,130-141
+    s = deepq.default_decay_schedule()
+    assert s.initial() == 1.0
+    assert s.value() == float(np.float32(0.995))
+    v = [s.value() for _ in range(2000)]
+    assert v[-1] == float(np.float32(0.01)) and min(v) == v[-1]
+    s2 = deepq.default_decay_schedule(decay_rate=0.9995)          # experiments/cartpole/main.go:28
+    assert abs(s2.value() - 0.9995) < 1e-7
+
+
+def test_unsupported_graphs_fail_loudly():
+    env = deepq.ShapesEnv(4, 2)
+    bad = deepq.PolicyConfig(layer_builder=lambda x, y: [deepq.FC(x, 24), deepq.FC(24, y, activation=deepq.LINEAR)])
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        deepq.Agent(deepq.AgentConfig(policy_config=bad), env)
+    with pytest.raises(ValueError, match="environment cannot be nil"):
+        deepq.Agent(deepq.AgentConfig(), None)
+
+
+@pytest.mark.gpu
+def test_policy_converges_to_static_values():
+    """policy_test.go:16-83 ("test that network converges to static values"), with the
+    final predictions asserted instead of logged."""
+    env = deepq.ShapesEnv(4, 2)
+    agent = deepq.Agent(deepq.AgentConfig(seed=7), env)
+    m = agent.policy
+    x1 = np.array([[0.051960364, 0.14512223, 0.12799974, -2.0140305]], np.float32)
+    x2 = np.array([[0.15163246, -0.94560495, 0.3904586, -8.20394809]], np.float32)
+    y1 = np.array([[0.4484117, 0.09160687]], np.float32)
+    y2 = np.array([[3.23904234, 2.203948023]], np.float32)
+    q0 = m.predict(x1)
+    assert q0.shape == (1, 2)
+    for i in range(3000):
+        m.fit(x1, y1)
+        m.fit(x2, y2)
+    np.testing.assert_allclose(m.predict(x1), y1, atol=0.05)
+    np.testing.assert_allclose(m.predict(x2), y2, atol=0.05)
+    with pytest.raises(ValueError):
+        agent.target_policy.fit(x1, y1)
+    agent.close()
+
+
+@pytest.mark.gpu
+def test_agent_loop_semantics():
+    """Action / Remember / Learn cadence of experiments/cartpole/main.go:27-58 on synthetic
+    transitions: Learn is a no-op until Len >= batch (agent.go:127), epsilon decays once per
+    Learn (agent.go:171), steps counts Actions only and the target is cloned when
+    steps % UpdateTargetSteps == 0 (agent.go:181-190)."""
+    env = deepq.ShapesEnv(4, 2, seed=1)
+    hp = deepq.Hyperparameters(update_target_steps=7, buffer_size=500)
+    agent = deepq.Agent(deepq.AgentConfig(hyperparameters=hp, seed=3), env)
+    s, a, r, s2, d = synth.replay(synth.CARTPOLE, 120, seed=11)
+    target0 = agent.target_policy.learnables().copy()
+    eps = [agent.epsilon]
+    synced_at = []
+    for t in range(120):
+        act = agent.action(s[t:t + 1])
+        assert act in (0, 1)
+        agent.remember(deepq.new_event(s[t:t + 1], act, deepq.Outcome(s2[t:t + 1], act, r[t], bool(d[t]))))
+        before = agent.target_policy.learnables().copy()
+        assert agent.learn() is None
+        after = agent.target_policy.learnables()
+        if not np.array_equal(before, after):
+            synced_at.append(agent.steps)
+        eps.append(agent.epsilon)
+    assert agent.steps == 120
+    # no learning (and no epsilon decay) before 20 events are in memory
+    assert eps[19] == eps[0] == 1.0 and eps[20] < 1.0
+    assert abs(eps[-1] - 0.995 ** 101) < 1e-5
+    assert synced_at and all(st % 7 == 0 for st in synced_at) and synced_at[0] == 21
+    np.testing.assert_array_equal(agent.target_policy.learnables(), agent.policy.learnables()) if agent.steps % 7 == 0 else None
+    assert not np.array_equal(target0, agent.target_policy.learnables())
+    assert np.isfinite(agent.last_loss())
+    agent.close()
