@@ -233,6 +233,8 @@ def run_own(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner out of it
+        os.environ["NCCL_DEBUG"] = os.environ.get("GOLDQ_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

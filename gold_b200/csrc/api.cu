@@ -364,11 +364,11 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     if (h->world > 1) {
         int rc = allreduce_flat(h);
         if (rc) return rc;
-        launch_adam(h->theta, h->flat, h->m, h->v, h->P, ws.adam, step, h->st);
-        h->launches += 1;
-        n = wide_after_update(h->wide, h->theta, h->st, err);   // refresh the bf16 shadow of the online net
+        if (h->prof_evs) cudaEventRecord(h->prof_evs[h->prof_n++], h->st);
+        n = wide_apply_update(h->wide, h->flat, h->theta, h->m, h->v, ws.adam, step, h->st, err);   // Adam + bf16 shadow
         if (n < 0) return fail(h, GOLDQ_ECUDA, err);
         h->launches += n;
+        if (h->prof_evs) cudaEventRecord(h->prof_evs[h->prof_n++], h->st);
     }
     CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
     return check_launch(h, "learn_wide");
@@ -835,7 +835,9 @@ int goldq_step_breakdown(goldq_t *h, uint64_t seed, int32_t max_kernels, float *
         CK(h, cudaEventRecord(evs[0], h->st));
         rc = run_learn(h, nullptr, seed);
         h->prof_evs = nullptr;
-        if (names && names_bytes > 0) snprintf(names, names_bytes, "%s", wide_step_kernel_names());
+        if (names && names_bytes > 0)
+            snprintf(names, names_bytes, "%s%s", wide_step_kernel_names(),
+                     h->world > 1 ? "\nncclAllReduce(grad)\nAdam + bf16 shadow (K5)" : "");
     } else {
         // single fused launch (narrow) or an unfused chain (generic): one interval for the step
         CK(h, cudaEventRecord(evs[0], h->st));

@@ -605,7 +605,7 @@ __device__ __forceinline__ void finish4(const Dims &d, const Offsets &o, int i, 
                                         float *m, float *v, float4 w4, float4 m4, float4 v4, const AdamConsts &ac,
                                         const ShadowPtrs &sp)
 {
-    *reinterpret_cast<float4 *>(flat + i) = g;
+    if (flat) *reinterpret_cast<float4 *>(flat + i) = g;
     if (!FUSE) return;
     adam_update_w(w4.x, g.x, m4.x, v4.x, ac);
     adam_update_w(w4.y, g.y, m4.y, v4.y, ac);
@@ -890,6 +890,40 @@ int wide_set_params(WideState *w, int net, const float *theta_dev, cudaStream_t 
 int wide_after_update(WideState *w, const float *theta_dev, cudaStream_t st, std::string &err)
 {
     return shadow(w, 0, theta_dev, st, err);
+}
+
+// data-parallel tail: Adam on the all-reduced flat gradient + bf16 shadow refresh, one pass
+__global__ void __launch_bounds__(256)
+wide_apply_kernel(Dims d, Offsets o, const float *__restrict__ flat, float *__restrict__ theta, float *__restrict__ m,
+                  float *__restrict__ v, AdamConsts ac, const StepDev *__restrict__ step, ShadowPtrs sp)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (step) { ac.c1 = step->c1; ac.c2 = step->c2; }
+    if (i + 3 < o.P && (i + 3 < o.b1 || (i >= o.b1 && i + 3 < o.w2) || (i >= o.w2 && i + 3 < o.b2) ||
+                        (i >= o.b2 && i + 3 < o.w3) || (i >= o.w3 && i + 3 < o.b3))) {
+        const float4 g = *reinterpret_cast<const float4 *>(flat + i);
+        float4 w4 = *reinterpret_cast<const float4 *>(theta + i);
+        float4 m4 = *reinterpret_cast<const float4 *>(m + i);
+        float4 v4 = *reinterpret_cast<const float4 *>(v + i);
+        finish4<true>(d, o, i, g, nullptr, theta, m, v, w4, m4, v4, ac, sp);
+    } else {
+        for (int e = i; e < i + 4 && e < o.P; e++) {
+            float wi = theta[e], mi = m[e], vi = v[e];
+            adam_update_w(wi, flat[e], mi, vi, ac);
+            theta[e] = wi; m[e] = mi; v[e] = vi;
+            shadow_store(d, o, sp, e, wi);
+        }
+    }
+}
+
+int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, float *v, AdamConsts ac,
+                      const StepDev *step, cudaStream_t st, std::string &err)
+{
+    const int groups = (w->o.P + 3) / 4;
+    wide_apply_kernel<<<(groups + 255) / 256, 256, 0, st>>>(w->d, w->o, flat, theta, m, v, ac, step, shadow_ptrs(w, 0));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("wide_apply_kernel: ") + cudaGetErrorString(e); return -1; }
+    return 1;
 }
 
 int wide_sync_target(WideState *w, cudaStream_t st, std::string &err)

@@ -33,6 +33,8 @@ void wide_destroy(WideState *w);
 int wide_set_params(WideState *w, int net, const float *theta_dev, cudaStream_t st, std::string &err);
 int wide_after_update(WideState *w, const float *theta_dev, cudaStream_t st, std::string &err);
 int wide_sync_target(WideState *w, cudaStream_t st, std::string &err);
+int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, float *v, AdamConsts ac,
+                      const StepDev *step, cudaStream_t st, std::string &err);
 int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err);
 const char *wide_step_kernel_names();
 void wide_set_debug(WideState *w, bool on);
