@@ -9,6 +9,7 @@
 #include <math.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -789,6 +790,16 @@ int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
         h->graph_head = h->rp.head;
         h->graph_len = h->rp.len;
         h->graph_debug = h->debug;
+    }
+    static const bool no_graph = getenv("GOLDQ_NO_GRAPH") != nullptr;   // diagnostic: eager launches
+    // Data-parallel steps are issued eagerly: an ncclAllReduce captured into a CUDA graph
+    // replays ~80 us slower per step than the eager call (measured at N=2, profiles/README.md).
+    if (no_graph || h->world > 1) {
+        for (int i = 0; i < n; i++) {
+            int rc = run_learn(h, nullptr, seed + (uint64_t)i);
+            if (rc) return rc;
+        }
+        return GOLDQ_OK;
     }
     while (n > 0) {
         const int c = n < goldq::GRAPH_MAX ? n : goldq::GRAPH_MAX;
