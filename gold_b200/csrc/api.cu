@@ -349,6 +349,7 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     ws.theta = h->theta;
     ws.theta_t = h->theta_t;
     ws.flat = h->flat;
+    ws.loss_out = h->loss;
     ws.sc = step_scalars(h, h->Bglobal);
     ws.fuse_update = h->world <= 1 ? 1 : 0;
     ws.theta_rw = h->theta;
@@ -370,8 +371,8 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
         if (n < 0) return fail(h, GOLDQ_ECUDA, err);
         h->launches += n;
         if (h->prof_evs) cudaEventRecord(h->prof_evs[h->prof_n++], h->st);
+        CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
     }
-    CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
     return check_launch(h, "learn_wide");
 }
 

@@ -18,12 +18,14 @@
 //                        dW1 = X^T dZ1              MM       M=D   N=H1  K=B (split-K)
 //                        dW3 = H2^T dQ              MK mode  M=H2  N=32  K=B (split-K), dQ^T [32][B]
 //   dQ has one non-zero per row (the taken action), so dZ2 = dq * W3[:,a] * mask2 is an
-//   elementwise kernel (wide_dz2_kernel), not a GEMM.
+//   elementwise kernel (wide_td_dz2_kernel, fused with the TD label), not a GEMM.
 // KK: both operands K-major (A [M][K], B [N][K] row-major).  MM: both MN-major
 // (A [K][M], B [K][N] row-major) — the activations are used as stored, no transposes.
 // MK: A MN-major, B K-major.  KM: A K-major, B MN-major (forward: W [in][out] as stored).
 #include <cuda.h>
 #include <cuda_bf16.h>
+
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -104,10 +106,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_slot, TMEM_COLS);
+    pdl_launch_dependents();     // the next kernel may begin its own prologue
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_acc = tmem_base_slot;
+    pdl_wait();                  // operands / bias / mask come from the previous kernels
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -296,6 +300,25 @@ bool make_tmap(CUtensorMap *m, const void *base, int rows, int cols, int ld, int
 }
 
 // one problem (ta1/tb1 = nullptr) or two problems sharing the launch
+// Launch with (optionally) programmatic stream serialization: the kernel may start while its
+// same-stream predecessor drains; see pdl_wait() in umma.cuh.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                     Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // opt in to the dynamic shared memory of one instantiation (called at create time, never
 // under stream capture)
 template <int MODE, int BN, int EPI>
@@ -321,14 +344,14 @@ cudaError_t configure_all_gemms()
 
 template <int MODE, int BN, int EPI>
 cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, GemmArgs g, int nsplit, cudaStream_t st,
-                        const CUtensorMap *ta1 = nullptr, const CUtensorMap *tb1 = nullptr)
+                        const CUtensorMap *ta1 = nullptr, const CUtensorMap *tb1 = nullptr, bool pdl = false)
 {
     constexpr size_t smem = gemm_smem_bytes<MODE, BN>();
     g.nsplit = nsplit;
     const int nprob = ta1 ? 2 : 1;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit * nprob);
-    umma_gemm_kernel<MODE, BN, EPI><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, ta1 ? *ta1 : ta, tb1 ? *tb1 : tb, g);
-    return cudaGetLastError();
+    return launch_k(umma_gemm_kernel<MODE, BN, EPI>, grid, dim3(GEMM_THREADS), smem, st, pdl, ta, tb,
+                    ta1 ? *ta1 : ta, tb1 ? *tb1 : tb, g);
 }
 
 // ---------------------------------------------------------------------------
@@ -343,6 +366,8 @@ wide_gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx, uint64_t s
 {
     const int chunks = D >> 2;  // float4 granules per row (D % 8 == 0 is required by the path)
     int t = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();                 // x/x2/ba/... are still being read by the previous step's kernels
     if (t >= B * chunks) return;
     int b = t / chunks, c = t - b * chunks;
     if (step) seed = step->seed;
@@ -397,85 +422,72 @@ wide_shadow_kernel(const float *__restrict__ theta, Dims d, Offsets o, ShadowPtr
     // the padding of W3 stays zero from allocation time (cudaMemset in wide_create)
 }
 
-// K3 (per row): first-max over Q'(s') (ArgmaxF32 rules), TD target, d = q[a] - t,
-// dqv = (2 d) / count; dQ^T [32][B] bf16 (one non-zero per column b) is the K-major B
-// operand of the dW3 GEMM.  Per block: loss partial and db3 partial (fixed order).
-constexpr int ROWS_TB = 64;   // small blocks: the kernel is latency-bound, spread it over the SMs
-__global__ void __launch_bounds__(ROWS_TB)
-wide_td_rows_kernel(const float *__restrict__ q, const float *__restrict__ qt, const int32_t *__restrict__ act,
-                    const float *__restrict__ rew, const uint8_t *__restrict__ done, int B, int A, StepScalars sc,
-                    float *__restrict__ td_out, float *__restrict__ dqv_out, __nv_bfloat16 *__restrict__ dqT,
-                    float *__restrict__ part /* [blocks][A + 1]: db3, loss */)
-{
-    __shared__ float sh[ROWS_TB / 32][33];
-    const int b = blockIdx.x * ROWS_TB + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float dqv = 0.f, sq = 0.f;
-    int a = -1;
-    if (b < B) {
-        // all loads of the row first (A <= 32), then the scan
-        const float *row = qt + (int64_t)b * A;
-        float rv[32];
-#pragma unroll
-        for (int i = 0; i < 32; i++) rv[i] = (i < A) ? __ldg(row + i) : 0.f;
-        a = act[b];
-        const float rwd = rew[b];
-        const int dn = done[b];
-        const float qa = __ldg(q + (int64_t)b * A + a);
-        float t = rwd;
-        if (!dn) {
-            float f = rv[0];
-            bool decided = false;
-#pragma unroll
-            for (int i = 1; i < 32; i++) {
-                if (i < A && !decided) {
-                    const float v = rv[i];
-                    if (isnan(v) || (isinf(v) && v > 0.f)) { f = v; decided = true; }
-                    else if (v > f) f = v;
-                }
-            }
-            t = __fadd_rn(rwd, __fmul_rn(sc.gamma, f));         // agent.go:149
-        }
-        td_out[b] = t;
-        const float dd = __fsub_rn(qa, t);
-        dqv = __fmul_rn(__fmul_rn(dd, 2.f), sc.inv_count);
-        sq = __fmul_rn(dd, dd);
-        dqv_out[b] = dqv;
-        const __nv_bfloat16 v = __float2bfloat16_rn(dqv), z = __float2bfloat16_rn(0.f);
-        for (int i = 0; i < 32; i++) dqT[(int64_t)i * B + b] = (i == a) ? v : z;
-    }
-    // db3[i] = sum of dqv over rows with act == i; slot A = loss partial
-    for (int i = 0; i <= A; i++) {
-        float v = (i == A) ? sq : ((a == i) ? dqv : 0.f);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) sh[warp][i] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x <= A) {
-        float t = 0.f;
-        for (int w = 0; w < ROWS_TB / 32; w++) t += sh[w][threadIdx.x];
-        part[(int64_t)blockIdx.x * (A + 1) + threadIdx.x] = t;
-    }
-}
-
-// dZ2[b][j] = dqv[b] * W3[j][a_b] * mask2[b][j] (bf16 out, operand of dW2 / dX) and the
-// db2 partial of the block.  Thread (x, y): 8 columns (16-byte vectors), rows y, y+4, ...
+// K3 + layer-3 backward, one kernel.  Block = DZ_ROWS rows.
+//   warp 0, lane = row: first-max over Q'(s') (ArgmaxF32 rules), TD target (agent.go:149),
+//     d = q[a] - t, dqv = (2 d) / count; dQ^T [32][B] bf16 (one non-zero per column b) is the
+//     K-major B operand of the dW3 GEMM; db3 / loss partials of the block in a fixed order.
+//   all warps: dZ2[b][j] = dqv[b] * W3[j][a_b] * mask2[b][j] (bf16 out, operand of dW2 / dX)
+//     and the db2 partial.  Thread (x, y): 8 columns (16-byte vectors), rows y, y+4, ...
 constexpr int DZ_ROWS = 32;
 __global__ void __launch_bounds__(256)
-wide_dz2_kernel(const __nv_bfloat16 *__restrict__ h2, const __nv_bfloat16 *__restrict__ w3t /* [32][H2] */,
-                const float *__restrict__ dqv, const int32_t *__restrict__ act, int B, int H2,
-                __nv_bfloat16 *__restrict__ dz2, float *__restrict__ part /* [blocks][H2] */)
+wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, const int32_t *__restrict__ act,
+                   const float *__restrict__ rew, const uint8_t *__restrict__ done, int B, int H2, int A, StepScalars sc,
+                   const __nv_bfloat16 *__restrict__ h2, const __nv_bfloat16 *__restrict__ w3t /* [32][H2] */,
+                   float *__restrict__ td_out, __nv_bfloat16 *__restrict__ dqT, __nv_bfloat16 *__restrict__ dz2,
+                   float *__restrict__ b2_part /* [blocks][H2] */, float *__restrict__ row_part /* [blocks][A+1] */)
 {
     extern __shared__ float sm[];            // [4][H2] column-sum staging
     __shared__ float sDq[DZ_ROWS];
     __shared__ int sAct[DZ_ROWS];
     const int x = threadIdx.x & 63, y = threadIdx.x >> 6;
     const int r0 = blockIdx.x * DZ_ROWS;
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x < DZ_ROWS) {
-        const int b = r0 + threadIdx.x;
-        sDq[threadIdx.x] = b < B ? dqv[b] : 0.f;
-        sAct[threadIdx.x] = b < B ? act[b] : 0;
+        const int lane = threadIdx.x;
+        const int b = r0 + lane;
+        float dqv = 0.f, sq = 0.f;
+        int a = -1;
+        if (b < B) {
+            // all loads of the row first (A <= 32), then the scan
+            const float *row = qt + (int64_t)b * A;
+            float rv[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) rv[i] = (i < A) ? __ldg(row + i) : 0.f;
+            a = act[b];
+            const float rwd = rew[b];
+            const int dn = done[b];
+            const float qa = __ldg(q + (int64_t)b * A + a);
+            float t = rwd;
+            if (!dn) {
+                float f = rv[0];
+                bool decided = false;
+#pragma unroll
+                for (int i = 1; i < 32; i++) {
+                    if (i < A && !decided) {
+                        const float v = rv[i];
+                        if (isnan(v) || (isinf(v) && v > 0.f)) { f = v; decided = true; }
+                        else if (v > f) f = v;
+                    }
+                }
+                t = __fadd_rn(rwd, __fmul_rn(sc.gamma, f));
+            }
+            td_out[b] = t;
+            const float dd = __fsub_rn(qa, t);
+            dqv = __fmul_rn(__fmul_rn(dd, 2.f), sc.inv_count);
+            sq = __fmul_rn(dd, dd);
+            const __nv_bfloat16 v = __float2bfloat16_rn(dqv), z = __float2bfloat16_rn(0.f);
+            for (int i = 0; i < 32; i++) dqT[(int64_t)i * B + b] = (i == a) ? v : z;
+        }
+        sDq[lane] = dqv;
+        sAct[lane] = a < 0 ? 0 : a;
+        // db3[i] = sum of dqv over the block's rows with act == i; slot A = loss partial
+        for (int i = 0; i <= A; i++) {
+            float v = (i == A) ? sq : ((a == i) ? dqv : 0.f);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) row_part[(int64_t)blockIdx.x * (A + 1) + i] = v;
+        }
     }
     __syncthreads();
     for (int c = x; c < (H2 >> 3); c += 64) {
@@ -514,7 +526,7 @@ wide_dz2_kernel(const __nv_bfloat16 *__restrict__ h2, const __nv_bfloat16 *__res
     }
     __syncthreads();
     for (int j = threadIdx.x; j < H2; j += blockDim.x)
-        part[(int64_t)blockIdx.x * H2 + j] = ((sm[j] + sm[H2 + j]) + sm[2 * H2 + j]) + sm[3 * H2 + j];
+        b2_part[(int64_t)blockIdx.x * H2 + j] = ((sm[j] + sm[H2 + j]) + sm[2 * H2 + j]) + sm[3 * H2 + j];
 }
 
 // db1 partials: column sums of dZ1 (bf16 [B][H1]) over CS_ROWS-row ranges.  A warp covers
@@ -526,6 +538,8 @@ wide_colsum_kernel(const __nv_bfloat16 *__restrict__ dz, int B, int H, float *__
 {
     __shared__ float2 sh[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     const int j = blockIdx.x * 64 + lane * 2;
     const int r0 = blockIdx.y * CS_ROWS, r1 = min(B, r0 + CS_ROWS);
     float2 s = make_float2(0.f, 0.f);
@@ -631,9 +645,11 @@ template <bool FUSE>
 __global__ void __launch_bounds__(128)
 wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count, float *__restrict__ flat,
                    float *__restrict__ theta, float *__restrict__ m, float *__restrict__ v, AdamConsts ac,
-                   const StepDev *__restrict__ step, ShadowPtrs sp)
+                   const StepDev *__restrict__ step, ShadowPtrs sp, float *__restrict__ loss_out)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     if (FUSE && step) { ac.c1 = step->c1; ac.c2 = step->c2; }
     if ((int)blockIdx.x < pl.blocksA) {
         // ---- A: weights ------------------------------------------------------------
@@ -710,7 +726,10 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) g += __shfl_xor_sync(0xffffffffu, g, off);
         if (lane == 0) {
-            if (i == o.P) g = __fdiv_rn(g, count);
+            if (i == o.P) {
+                g = __fdiv_rn(g, count);
+                if (loss_out) *loss_out = g;
+            }
             flat[i] = g;
             if (FUSE && i < o.P) {
                 float wi = theta[i], mi = m[i], vi = v[i];
@@ -761,6 +780,7 @@ struct WideState {
     // stream capture these become parallel branches of the step graph)
     cudaStream_t s1 = nullptr, s2 = nullptr;
     cudaEvent_t ev_dz2 = nullptr, ev_dx = nullptr, ev_s1 = nullptr, ev_s2 = nullptr;
+    bool pdl = true;
     bool debug = false;
 };
 
@@ -814,7 +834,7 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     w->ns3 = split_for(tiles3, B, sm_count, &w->kps3);
     w->nb1 = (B + CS_ROWS - 1) / CS_ROWS;
     w->nb2 = (B + DZ_ROWS - 1) / DZ_ROWS;
-    w->nrow = (B + ROWS_TB - 1) / ROWS_TB;
+    w->nrow = w->nb2;   // db3 / loss partials come from the same blocks as db2
     ok = ok && dmalloc(&w->w1_slices, (size_t)w->ns1 * d.D * d.H1, err) &&
          dmalloc(&w->w2_slices, (size_t)w->ns2 * d.H1 * d.H2, err) &&
          dmalloc(&w->w3_slices, (size_t)w->ns3 * d.H2 * d.A, err) && dmalloc(&w->b1_part, (size_t)w->nb1 * d.H1, err) &&
@@ -841,6 +861,7 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     // dQ^T [32 rows][B cols]: K-major B operand of the dW3 GEMM, box 32 rows
     ok = ok && make_tmap(&w->tm_dqT_b, w->dqT, 32, B, B, 32, err);
     if (!ok) { wide_destroy(w); return nullptr; }
+    w->pdl = getenv("GOLDQ_NO_PDL") == nullptr;
     cudaStreamCreateWithFlags(&w->s1, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&w->s2, cudaStreamNonBlocking);
     cudaEvent_t *evs[] = {&w->ev_dz2, &w->ev_dx, &w->ev_s1, &w->ev_s2};
@@ -950,13 +971,13 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     const int B = w->B;
     int launches = 0;
     const bool prof = s.prof_evs != nullptr;
+    const bool pdl = w->pdl && !prof;   // programmatic dependent launch along the st chain
     cudaStream_t s1 = prof ? st : w->s1, s2 = prof ? st : w->s2;
     auto mark = [&]() { if (prof) cudaEventRecord(s.prof_evs[(*s.prof_n)++], st); };
     {
         int n = B * (d.D >> 2);
-        wide_gather_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.rp, d.D, s.idx, s.seed, s.step, s.idx_out, B, w->x, w->x2, w->ba,
-                                                           w->br, w->bdone);
-        WCK(cudaGetLastError());
+        WCK(launch_k(wide_gather_kernel, dim3((n + 255) / 256), dim3(256), 0, st, pdl, s.rp, d.D, s.idx, s.seed, s.step,
+                     s.idx_out, B, w->x, w->x2, w->ba, w->br, w->bdone));
         launches++;
         mark();
     }
@@ -966,29 +987,24 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g.M = B; g.N = d.H1; g.K = d.D; g.k_per_split = ((d.D + BK - 1) / BK) * BK;
     g.out_bf16 = w->h1; g.out_bf16_1 = w->t1; g.bias = s.theta + o.b1; g.bias_1 = s.theta_t + o.b1;
     g.ldo = d.H1; g.n_store = d.H1;
-    WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_x_a, on.tm_w1_mn, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn)));
+    WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_x_a, on.tm_w1_mn, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn, pdl)));
     mark();
     g.N = d.H2; g.K = d.H1; g.k_per_split = ((d.H1 + BK - 1) / BK) * BK;
     g.out_bf16 = w->h2; g.out_bf16_1 = w->t2; g.bias = s.theta + o.b2; g.bias_1 = s.theta_t + o.b2;
     g.ldo = d.H2; g.n_store = d.H2;
-    WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_h1_a, on.tm_w2_mn, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn)));
+    WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_h1_a, on.tm_w2_mn, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn, pdl)));
     mark();
     g.N = W3_PAD; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = g.out_bf16_1 = nullptr; g.out_f32 = w->q; g.out_f32_1 = w->qt;
     g.bias = s.theta + o.b3; g.bias_1 = s.theta_t + o.b3; g.ldo = d.A; g.n_store = d.A;
-    WCK((launch_gemm<MODE_KM, 64, EPI_BIAS_F32>(w->tm_h2_a, on.tm_w3p_mn, g, 1, st, &w->tm_t2_a, &tg.tm_w3p_mn)));
+    WCK((launch_gemm<MODE_KM, 64, EPI_BIAS_F32>(w->tm_h2_a, on.tm_w3p_mn, g, 1, st, &w->tm_t2_a, &tg.tm_w3p_mn, pdl)));
     mark();
     launches += 3;
 
-    wide_td_rows_kernel<<<w->nrow, ROWS_TB, 0, st>>>(w->q, w->qt, w->ba, w->br, w->bdone, B, d.A, s.sc, w->td, w->dqv,
-                                                      w->dqT, w->row_part);
-    WCK(cudaGetLastError());
+    WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), sizeof(float) * 4 * d.H2, st, pdl, w->q, w->qt, w->ba, w->br,
+                 w->bdone, B, d.H2, d.A, s.sc, w->h2, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part));
     mark();
-    wide_dz2_kernel<<<w->nb2, 256, sizeof(float) * 4 * d.H2, st>>>(w->h2, on.w3t, w->dqv, w->ba, B, d.H2, w->dz2,
-                                                                    w->b2_part);
-    WCK(cudaGetLastError());
-    mark();
-    launches += 2;
+    launches += 1;
 
     // backward: three independent chains after dZ2 —  s1: dW2 | s2: dW3, db1 | st: dX -> dW1
     if (!prof) {
@@ -1013,7 +1029,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g = GemmArgs{};
     g.M = B; g.N = d.H1; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = w->dz1; g.mask_src = w->h1; g.ldo = d.H1; g.n_store = d.H1;
-    WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16>(w->tm_dz2_a, on.tm_w2_k, g, 1, st)));
+    WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16>(w->tm_dz2_a, on.tm_w2_k, g, 1, st, nullptr, nullptr, pdl)));
     mark();
     if (!prof) {
         WCK(cudaEventRecord(w->ev_dx, st));
@@ -1030,7 +1046,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g = GemmArgs{};
     g.M = d.D; g.N = d.H1; g.K = B; g.k_per_split = w->kps1;
     g.out_f32 = w->w1_slices; g.ldo = d.H1; g.n_store = d.H1; g.slice_stride = (long long)d.D * d.H1;
-    WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_x_mm, w->tm_dz1_mm, g, w->ns1, st)));
+    WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_x_mm, w->tm_dz1_mm, g, w->ns1, st, nullptr, nullptr, pdl)));
     mark();
     if (!prof) {
         WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
@@ -1048,12 +1064,13 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     pl.blocksB = (pl.nB + 3) / 4;
     pl.blocksC = (pl.nC + 3) / 4;
     const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
+    // (the update kernel follows cross-stream event waits: a full dependency, no PDL)
     if (s.fuse_update)
         wide_update_kernel<true><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
-                                                         s.step, shadow_ptrs(w, 0));
+                                                         s.step, shadow_ptrs(w, 0), s.loss_out);
     else
         wide_update_kernel<false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
-                                                          s.adam, s.step, shadow_ptrs(w, 0));
+                                                          s.adam, s.step, shadow_ptrs(w, 0), nullptr);
     WCK(cudaGetLastError());
     mark();
     launches++;
@@ -1063,7 +1080,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
 const char *wide_step_kernel_names()
 {
     return "gather+cast (K1)\nfwd L1 online+target (tcgen05)\nfwd L2 online+target (tcgen05)\nfwd L3 online+target (tcgen05)\n"
-           "TD rows (K3)\ndZ2 + db2\ndW3 (tcgen05)\ndW2 split-K (tcgen05)\ndX -> dZ1 (tcgen05)\ndb1 colsum\n"
+           "TD + dZ2 + db2/db3 (K3)\ndW3 (tcgen05)\ndW2 split-K (tcgen05)\ndX -> dZ1 (tcgen05)\ndb1 colsum\n"
            "dW1 split-K (tcgen05)\nreduce + Adam + bf16 shadow (K5)";
 }
 

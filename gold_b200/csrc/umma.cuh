@@ -31,6 +31,14 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
+// ---- programmatic dependent launch ---------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// its predecessor in the stream is still draining; pdl_wait() blocks until the predecessor
+// has completed and its writes are visible (no-op without the attribute).  Every kernel of
+// the chain calls it before its first global access, which keeps completion transitive.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier ---------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {

@@ -18,6 +18,7 @@ struct WideStep {
     const float *theta;    // fp32 master parameters (biases are read from here)
     const float *theta_t;
     float *flat;           // [P+1] out: reduced gradient + loss
+    float *loss_out;       // the handle's loss scalar (written by the fused update)
     StepScalars sc;
     int fuse_update;       // 1: Adam + bf16 shadow refresh in the reduction kernel
     float *theta_rw, *m, *v;
