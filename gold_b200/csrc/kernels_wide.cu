@@ -65,15 +65,25 @@ struct GemmArgs {
 
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
 
-template <int MODE, int BN, int EPI>
+// CM > 1: clusters of CM CTAs along M (blockIdx.y) share the B tile — each CTA loads 1/CM of
+// it and multicasts the slice into every CTA of the cluster (tmB* then describe the slice box).
+template <int MODE, int BN, int EPI, int CM>
 __global__ void __launch_bounds__(GEMM_THREADS)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1,
                  const GemmArgs g)
 {
+    // bf16 outputs leave through shared memory + TMA store (full 128-byte lines; rows and
+    // columns outside the tensor are clipped by the hardware); tmC* = box {64 cols, 128 rows}
+    constexpr bool TMA_OUT = (EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_MASK_BF16);
+    static_assert(!TMA_OUT || BN % 64 == 0, "bf16 tiles are stored in 64-column boxes");
     constexpr bool A_MN = (MODE == MODE_MM || MODE == MODE_MK), B_MN = (MODE == MODE_MM || MODE == MODE_KM);
     static_assert(BN == 128 || BN == 64 || BN == 32, "BN");
     static_assert(!B_MN || BN % 64 == 0, "MN-major B tiles are 64-wide swizzle atoms");
+    static_assert(CM == 1 || CM == 2 || CM == 4 || CM == 8, "cluster size");
+    static_assert(CM == 1 || (B_MN ? (64 / CM) % 8 == 0 : (BN / CM) % 8 == 0), "slices are whole swizzle atoms");
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CM) - 1u);
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = BN * BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -100,7 +110,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         prefetch_tmap(tmB);
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CM);     // one tcgen05.commit per CTA of the cluster
         }
         mbar_init(&tmem_full_bar, 1);
         fence_barrier_init();
@@ -108,7 +118,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (warp == 1) tmem_alloc(&tmem_base_slot, TMEM_COLS);
     pdl_launch_dependents();     // the next kernel may begin its own prologue
     tc_fence_before();
-    __syncthreads();
+    if (CM > 1) cluster_sync();  // peers' barriers are initialised before anything is multicast
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_acc = tmem_base_slot;
     pdl_wait();                  // operands / bias / mask come from the previous kernels
@@ -128,9 +139,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 if (!A_MN) tma_load_2d(sA, tmA, k, m0, &full_bar[s]);
                 else
                     for (int h = 0; h < BM / 64; h++) tma_load_2d(sA + h * 8192, tmA, m0 + 64 * h, k, &full_bar[s]);
-                if (!B_MN) tma_load_2d(sB, tmB, k, n0, &full_bar[s]);
-                else
-                    for (int h = 0; h < BN / 64; h++) tma_load_2d(sB + h * 8192, tmB, n0 + 64 * h, k, &full_bar[s]);
+                if (CM == 1) {
+                    if (!B_MN) tma_load_2d(sB, tmB, k, n0, &full_bar[s]);
+                    else
+                        for (int h = 0; h < BN / 64; h++) tma_load_2d(sB + h * 8192, tmB, n0 + 64 * h, k, &full_bar[s]);
+                } else {
+                    const int r = (int)cluster_ctarank();
+                    if (!B_MN) {   // slice = rows [r*BN/CM, ...) of the [BN][64 k] tile
+                        tma_load_2d_mc(sB + r * (BN / CM) * 128, tmB, k, n0 + r * (BN / CM), &full_bar[s], MC_MASK);
+                    } else {       // slice = k-rows [r*64/CM, ...) of every 64-wide n group
+                        for (int h = 0; h < BN / 64; h++)
+                            tma_load_2d_mc(sB + h * 8192 + r * (64 / CM) * 128, tmB, n0 + 64 * h, k + r * (64 / CM),
+                                           &full_bar[s], MC_MASK);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -154,7 +176,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                              : make_smem_desc(baddr + kk * 32, 16, 1024);
                     mma_bf16(tmem_acc, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
                 }
-                mma_commit(&empty_bar[s]);                 // smem slot free once these MMAs retire
+                // smem slot free once these MMAs retire (in every CTA that multicasts into it)
+                if (CM == 1) mma_commit(&empty_bar[s]);
+                else mma_commit_mc(&empty_bar[s], MC_MASK);
                 if (kb == nkb - 1) mma_commit(&tmem_full_bar);
             }
             __syncwarp();
@@ -163,7 +187,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ===== epilogue: TMEM -> registers -> global =====
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         const int row = m0 + q * 32 + lane;
-        __nv_bfloat16 *const out_bf16 = prob ? g.out_bf16_1 : g.out_bf16;
         float *const out_f32 = prob ? g.out_f32_1 : g.out_f32;
         if (EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_BIAS_F32) {
             // stage this tile's bias once (one coalesced load), while the mainloop runs
@@ -216,11 +239,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
                         packed[j >> 1] = *reinterpret_cast<uint32_t *>(&p);
                     }
-                    uint4 *op = reinterpret_cast<uint4 *>(out_bf16 + (size_t)row * g.ldo + col0);
+                    // staging tile = stage 0 of the ring (free: every MMA has retired), laid out as the
+                    // 128B-swizzled boxes the store tensor map describes: [BN/64][128 rows][128 B]
+                    const int rt = q * 32 + lane;
+                    uint8_t *dst = smem + (c0 >> 6) * 16384 + rt * 128;
+                    const int ch0 = (c0 & 63) >> 3;
 #pragma unroll
                     for (int v = 0; v < 4; v++)
-                        if (col0 + 8 * v < g.n_store)
-                            op[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+                        *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
+                            make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
                 } else if (EPI == EPI_BIAS_F32) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
@@ -243,9 +270,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
             }
         }
+        if (TMA_OUT) {
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+                const CUtensorMap *tmC = prob ? &tmC1 : &tmC0;
+                for (int b = 0; b < BN / 64; b++)
+                    if (n0 + 64 * b < g.n_store) tma_store_2d(tmC, smem + b * 16384, n0 + 64 * b, m0);
+                tma_store_commit_and_wait_read();
+            }
+        }
         tc_fence_before();
     }
-    __syncthreads();
+    if (CM > 1) cluster_sync();   // nobody leaves while peers may still signal its barriers
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_acc, TMEM_COLS);
@@ -303,28 +341,46 @@ bool make_tmap(CUtensorMap *m, const void *base, int rows, int cols, int ld, int
 // Launch with (optionally) programmatic stream serialization: the kernel may start while its
 // same-stream predecessor drains; see pdl_wait() in umma.cuh.
 template <typename... KArgs, typename... Args>
-cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
-                     Args &&...args)
+cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                      int cluster_y, Args &&...args)
 {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    if (cluster_y > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = 1;
+        at[n].val.clusterDim.y = (unsigned)cluster_y;
+        at[n].val.clusterDim.z = 1;
+        n++;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                     Args &&...args)
+{
+    return launch_kc(kernel, grid, block, smem, st, pdl, 1, static_cast<Args &&>(args)...);
 }
 
 // opt in to the dynamic shared memory of one instantiation (called at create time, never
 // under stream capture)
-template <int MODE, int BN, int EPI>
+template <int MODE, int BN, int EPI, int CM = 1>
 cudaError_t configure_gemm()
 {
-    return cudaFuncSetAttribute(umma_gemm_kernel<MODE, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(umma_gemm_kernel<MODE, BN, EPI, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)gemm_smem_bytes<MODE, BN>());
 }
 
@@ -339,19 +395,28 @@ cudaError_t configure_all_gemms()
     if (e == cudaSuccess) e = configure_gemm<MODE_KK, 32, EPI_F32_SLICE>();
     if (e == cudaSuccess) e = configure_gemm<MODE_KM, 128, EPI_F32_SLICE>();
     if (e == cudaSuccess) e = configure_gemm<MODE_KM, 64, EPI_F32_SLICE>();
+    // multicast variants
+    if (e == cudaSuccess) e = configure_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16, 4>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KK, 128, EPI_MASK_BF16, 4>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_MM, 128, EPI_F32_SLICE, 4>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KK, 128, EPI_F32_SLICE, 4>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KM, 128, EPI_F32_SLICE, 4>();
     return e;
 }
 
-template <int MODE, int BN, int EPI>
+template <int MODE, int BN, int EPI, int CM = 1>
 cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, GemmArgs g, int nsplit, cudaStream_t st,
-                        const CUtensorMap *ta1 = nullptr, const CUtensorMap *tb1 = nullptr, bool pdl = false)
+                        const CUtensorMap *ta1 = nullptr, const CUtensorMap *tb1 = nullptr, bool pdl = false,
+                        const CUtensorMap *tc0 = nullptr, const CUtensorMap *tc1 = nullptr)
 {
     constexpr size_t smem = gemm_smem_bytes<MODE, BN>();
     g.nsplit = nsplit;
     const int nprob = ta1 ? 2 : 1;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit * nprob);
-    return launch_k(umma_gemm_kernel<MODE, BN, EPI>, grid, dim3(GEMM_THREADS), smem, st, pdl, ta, tb,
-                    ta1 ? *ta1 : ta, tb1 ? *tb1 : tb, g);
+    if (CM > 1 && grid.y % CM != 0) return cudaErrorInvalidConfiguration;
+    if ((EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_MASK_BF16) && !tc0) return cudaErrorInvalidValue;
+    return launch_kc(umma_gemm_kernel<MODE, BN, EPI, CM>, grid, dim3(GEMM_THREADS), smem, st, pdl, CM, ta, tb,
+                     ta1 ? *ta1 : ta, tb1 ? *tb1 : tb, tc0 ? *tc0 : ta, tc1 ? *tc1 : (tc0 ? *tc0 : ta), g);
 }
 
 // ---------------------------------------------------------------------------
@@ -758,6 +823,7 @@ bool dmalloc(T **p, size_t n, std::string &err)
 struct WideNet {
     __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3p = nullptr, *w3t = nullptr;
     CUtensorMap tm_w1_mn, tm_w2_mn, tm_w3p_mn, tm_w2_k;
+    CUtensorMap tm_w1_mn_s4, tm_w2_mn_s4, tm_w2_k_s4;   // multicast slice boxes (clusters of 4)
 };
 
 struct WideState {
@@ -774,13 +840,14 @@ struct WideState {
           *row_part = nullptr;
     int ns1 = 1, ns2 = 1, ns3 = 1, kps1 = 0, kps2 = 0, kps3 = 0, nb1 = 1, nb2 = 1, nrow = 1;
     // activation tensor maps: KK A-operands (box 128 rows) and MN-major operands (box 64 k-rows)
-    CUtensorMap tm_x_a, tm_x2_a, tm_h1_a, tm_t1_a, tm_h2_a, tm_t2_a, tm_dz2_a;
-    CUtensorMap tm_x_mm, tm_h1_mm, tm_h2_mm, tm_dz2_mm, tm_dz1_mm, tm_dqT_b;
+    CUtensorMap tm_x_a, tm_x2_a, tm_h1_a, tm_t1_a, tm_h2_a, tm_t2_a, tm_dz2_a, tm_dz1_a;
+    CUtensorMap tm_x_mm, tm_h1_mm, tm_h2_mm, tm_dz2_mm, tm_dz1_mm, tm_dqT_b, tm_dz2_mm_s4;
     // side streams: independent backward GEMMs run concurrently (fork/join by events; under
     // stream capture these become parallel branches of the step graph)
     cudaStream_t s1 = nullptr, s2 = nullptr;
     cudaEvent_t ev_dz2 = nullptr, ev_dx = nullptr, ev_s1 = nullptr, ev_s2 = nullptr;
     bool pdl = true;
+    bool mc_rows = false, mc_h1 = false;   // B-tile multicast usable: row tiles / H1 tiles divide by 4
     bool debug = false;
 };
 
@@ -849,15 +916,27 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     }
     // W2 as the K-major B operand of dX: [N = H1 rows][K = H2 cols], box 128 rows
     ok = ok && make_tmap(&w->net[0].tm_w2_k, w->net[0].w2, d.H1, d.H2, d.H2, 128, err);
+    // slice boxes for B-tile multicast over clusters of 4 CTAs
+    for (int k = 0; k < 2; k++) {
+        WideNet &nn = w->net[k];
+        ok = ok && make_tmap(&nn.tm_w1_mn_s4, nn.w1, d.D, d.H1, d.H1, 16, err) &&
+             make_tmap(&nn.tm_w2_mn_s4, nn.w2, d.H1, d.H2, d.H2, 16, err);
+    }
+    ok = ok && make_tmap(&w->net[0].tm_w2_k_s4, w->net[0].w2, d.H1, d.H2, d.H2, 32, err);
+    // measured on B200 (round 1): with 128x128 tiles the cluster's lock-step costs more than the
+    // saved L2->SM traffic (95 vs 87 us/step), so B-tile multicast is opt-in
+    w->mc_rows = getenv("GOLDQ_MULTICAST") != nullptr && ((B + BM - 1) / BM) % 4 == 0;
+    w->mc_h1 = getenv("GOLDQ_MULTICAST") != nullptr && ((d.H1 + BM - 1) / BM) % 4 == 0;
     // activations as KK A operands: [B rows][K cols], box 128 rows
     ok = ok && make_tmap(&w->tm_x_a, w->x, B, d.D, d.D, BM, err) && make_tmap(&w->tm_x2_a, w->x2, B, d.D, d.D, BM, err) &&
          make_tmap(&w->tm_h1_a, w->h1, B, d.H1, d.H1, BM, err) && make_tmap(&w->tm_t1_a, w->t1, B, d.H1, d.H1, BM, err) &&
          make_tmap(&w->tm_h2_a, w->h2, B, d.H2, d.H2, BM, err) && make_tmap(&w->tm_t2_a, w->t2, B, d.H2, d.H2, BM, err) &&
-         make_tmap(&w->tm_dz2_a, w->dz2, B, d.H2, d.H2, BM, err);
+         make_tmap(&w->tm_dz2_a, w->dz2, B, d.H2, d.H2, BM, err) && make_tmap(&w->tm_dz1_a, w->dz1, B, d.H1, d.H1, BM, err);
     // activations as MN-major operands: [K = B rows][MN cols], box 64 k-rows x 64 mn
     ok = ok && make_tmap(&w->tm_x_mm, w->x, B, d.D, d.D, 64, err) && make_tmap(&w->tm_h1_mm, w->h1, B, d.H1, d.H1, 64, err) &&
          make_tmap(&w->tm_h2_mm, w->h2, B, d.H2, d.H2, 64, err) && make_tmap(&w->tm_dz2_mm, w->dz2, B, d.H2, d.H2, 64, err) &&
-         make_tmap(&w->tm_dz1_mm, w->dz1, B, d.H1, d.H1, 64, err);
+         make_tmap(&w->tm_dz1_mm, w->dz1, B, d.H1, d.H1, 64, err) &&
+         make_tmap(&w->tm_dz2_mm_s4, w->dz2, B, d.H2, d.H2, 16, err);
     // dQ^T [32 rows][B cols]: K-major B operand of the dW3 GEMM, box 32 rows
     ok = ok && make_tmap(&w->tm_dqT_b, w->dqT, 32, B, B, 32, err);
     if (!ok) { wide_destroy(w); return nullptr; }
@@ -987,12 +1066,18 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g.M = B; g.N = d.H1; g.K = d.D; g.k_per_split = ((d.D + BK - 1) / BK) * BK;
     g.out_bf16 = w->h1; g.out_bf16_1 = w->t1; g.bias = s.theta + o.b1; g.bias_1 = s.theta_t + o.b1;
     g.ldo = d.H1; g.n_store = d.H1;
-    WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_x_a, on.tm_w1_mn, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn, pdl)));
+    if (w->mc_rows)
+        WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16, 4>(w->tm_x_a, on.tm_w1_mn_s4, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn_s4, pdl, &w->tm_h1_a, &w->tm_t1_a)));
+    else
+        WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_x_a, on.tm_w1_mn, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn, pdl, &w->tm_h1_a, &w->tm_t1_a)));
     mark();
     g.N = d.H2; g.K = d.H1; g.k_per_split = ((d.H1 + BK - 1) / BK) * BK;
     g.out_bf16 = w->h2; g.out_bf16_1 = w->t2; g.bias = s.theta + o.b2; g.bias_1 = s.theta_t + o.b2;
     g.ldo = d.H2; g.n_store = d.H2;
-    WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_h1_a, on.tm_w2_mn, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn, pdl)));
+    if (w->mc_rows)
+        WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16, 4>(w->tm_h1_a, on.tm_w2_mn_s4, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn_s4, pdl, &w->tm_h2_a, &w->tm_t2_a)));
+    else
+        WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_h1_a, on.tm_w2_mn, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn, pdl, &w->tm_h2_a, &w->tm_t2_a)));
     mark();
     g.N = W3_PAD; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = g.out_bf16_1 = nullptr; g.out_f32 = w->q; g.out_f32_1 = w->qt;
@@ -1022,14 +1107,20 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g = GemmArgs{};
     g.M = d.H1; g.N = d.H2; g.K = B; g.k_per_split = w->kps2;
     g.out_f32 = w->w2_slices; g.ldo = d.H2; g.n_store = d.H2; g.slice_stride = (long long)d.H1 * d.H2;
-    WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, s1)));
+    if (w->mc_h1)
+        WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE, 4>(w->tm_h1_mm, w->tm_dz2_mm_s4, g, w->ns2, s1)));
+    else
+        WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, s1)));
     mark();
     if (!prof) WCK(cudaEventRecord(w->ev_s1, s1));
     // dZ1 = (dZ2 W2^T) * mask1 : M = B, N = H1, K = H2 ; B operand = W2 [H1 rows][H2 cols]
     g = GemmArgs{};
     g.M = B; g.N = d.H1; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = w->dz1; g.mask_src = w->h1; g.ldo = d.H1; g.n_store = d.H1;
-    WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16>(w->tm_dz2_a, on.tm_w2_k, g, 1, st, nullptr, nullptr, pdl)));
+    if (w->mc_rows)
+        WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16, 4>(w->tm_dz2_a, on.tm_w2_k_s4, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
+    else
+        WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16>(w->tm_dz2_a, on.tm_w2_k, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
     mark();
     if (!prof) {
         WCK(cudaEventRecord(w->ev_dx, st));
@@ -1133,6 +1224,15 @@ int wide_selftest_gemm(int mode, int M, int N, int K, int nsplit, const uint16_t
     } else if (mode == 5) {   // KM with the 64-wide N tile
         if (!make_tmap(&ta, dA, M, K, K, BM, err) || !make_tmap(&tb, dB, K, N, N, 64, err)) return -1;
         WCK((launch_gemm<MODE_KM, 64, EPI_F32_SLICE>(ta, tb, g, nsplit, 0)));
+    } else if (mode == 10) {  // KK, B multicast over clusters of 4 along M
+        if (!make_tmap(&ta, dA, M, K, K, BM, err) || !make_tmap(&tb, dB, N, K, K, 32, err)) return -1;
+        WCK((launch_gemm<MODE_KK, 128, EPI_F32_SLICE, 4>(ta, tb, g, nsplit, 0)));
+    } else if (mode == 11) {  // MM, B multicast
+        if (!make_tmap(&ta, dA, K, M, M, 64, err) || !make_tmap(&tb, dB, K, N, N, 16, err)) return -1;
+        WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE, 4>(ta, tb, g, nsplit, 0)));
+    } else if (mode == 14) {  // KM, B multicast
+        if (!make_tmap(&ta, dA, M, K, K, BM, err) || !make_tmap(&tb, dB, K, N, N, 16, err)) return -1;
+        WCK((launch_gemm<MODE_KM, 128, EPI_F32_SLICE, 4>(ta, tb, g, nsplit, 0)));
     } else {
         err = "selftest: unknown mode";
         return -1;

@@ -25,8 +25,12 @@ def bf16_bits(x):
     (1, 136, 200, 100, 2),
     (3, 128, 32, 64, 1), (3, 512, 32, 8192, 32), (3, 256, 32, 1000, 3),
     (4, 128, 128, 128, 1), (4, 8192, 512, 512, 1), (4, 200, 136, 72, 1), (5, 256, 64, 512, 1), (5, 100, 64, 128, 1),
+    # B tile multicast over clusters of 4 CTAs along M (M tiles must divide by 4)
+    (10, 512, 128, 64, 1), (10, 8192, 512, 512, 1), (10, 1024, 256, 1024, 2), (11, 512, 512, 1024, 4),
+    (11, 512, 128, 192, 1), (14, 512, 128, 128, 1), (14, 8192, 512, 512, 1), (14, 1024, 136, 72, 1),
 ])
 def test_umma_gemm_matches_numpy(mode, M, N, K, nsplit):
+    api_mode, mode = mode, mode % 10
     rng = np.random.Generator(np.random.PCG64(M * 7 + N * 3 + K + mode))
     a = rng.normal(0, 1, (M, K)).astype(np.float32)
     b = rng.normal(0, 1, (N, K)).astype(np.float32)
@@ -50,6 +54,6 @@ def test_umma_gemm_matches_numpy(mode, M, N, K, nsplit):
         # the 32-wide tile reads 32 B rows: pad B with zero rows like W3^T is padded
         bpad = np.zeros((32, K), np.uint16); bpad[:N] = bbits; bbits = bpad
         ref_full = np.zeros((M, 32)); ref_full[:, :N] = ref; ref = ref_full; N = 32
-    out = G.selftest_umma(mode, abits, bbits, M, N, K, nsplit)
+    out = G.selftest_umma(api_mode, abits, bbits, M, N, K, nsplit)
     scale = np.sqrt(K)
     np.testing.assert_allclose(out, ref, rtol=2e-5, atol=2e-5 * scale)
