@@ -56,13 +56,16 @@ narrow_learn_kernel(NarrowArgs p)
     constexpr int oW1 = 0, oB1 = oW1 + D * H1, oW2 = oB1 + H1, oB2 = oW2 + H1 * H2,
                   oW3 = oB2 + H2, oB3 = oW3 + H2 * A, P = oB3 + A;
     constexpr int P1 = P + 1;
+    constexpr int PE = (P + 3) & ~3;   // 16-byte aligned smem slabs
     constexpr int GROUP = NARROW_GROUP;
     constexpr int ELEMS = (P1 + MIN_WARPS * 32 - 1) / (MIN_WARPS * 32);
 
     extern __shared__ float smem[];
-    float *sOn = smem;             // online parameters, flat
-    float *sTg = sOn + P;          // target parameters, flat
-    float *sW2T = sTg + P;         // online W2 transposed [H2][H1] (for dh1)
+    float *sOn = smem;             // online parameters, flat          (P rounded up to even)
+    float *sTg = sOn + PE;         // target parameters, flat
+    float *sM = sTg + PE;          // Adam first moments  (prefetched for the CTA that finishes last)
+    float *sV = sM + PE;           // Adam second moments
+    float *sW2T = sV + PE;         // online W2 transposed [H2][H1] (for dh1)
     float *sPart = sW2T + H1 * H2; // [warps][P1] per-warp gradient partials
     __shared__ int sFlag;
 
@@ -79,15 +82,20 @@ narrow_learn_kernel(NarrowArgs p)
     const int nwarps = blockDim.x >> 5;
     const int64_t pofs = (int64_t)rep * P;
 
-    for (int i = tid; i < P; i += blockDim.x) {
-        sOn[i] = p.theta[pofs + i];
-        sTg[i] = p.theta_t[pofs + i];
+    // Stage both networks and the Adam moments with cp.async (4-byte granules: P is odd for
+    // some shapes, so a replica's slab is only 4-byte aligned); the copies fly while the warps
+    // compute their sample indices and fetch their replay rows.
+    {
+        const float *srcs[4] = {p.theta + pofs, p.theta_t + pofs, p.m + pofs, p.v + pofs};
+        float *dsts[4] = {sOn, sTg, sM, sV};
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+            for (int i = tid; i < P; i += blockDim.x)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dsts[a] + i)),
+                             "l"(srcs[a] + i)
+                             : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    for (int i = tid; i < H1 * H2; i += blockDim.x) {
-        int r = i / H2, c = i - r * H2;  // W2[r][c]
-        sW2T[c * H1 + r] = p.theta[pofs + oW2 + i];
-    }
-    __syncthreads();
 
     // replay views of this replica
     const float *rs = p.rp.s + (int64_t)rep * p.rp.cap * D;
@@ -110,17 +118,17 @@ narrow_learn_kernel(NarrowArgs p)
 
     const int total_warps = gridDim.x * nwarps;
     const int gw = blockIdx.x * nwarps + warp;
-    // warp `gw` owns rows gw, gw + total_warps, ...; NR of them are processed together
-    for (int b0 = gw; b0 < p.B; b0 += NR * total_warps) {
-        // ---- K1: sample / gather -------------------------------------------------
-        float x[NR], x2[NR], rew[NR];
-        int act[NR], dn[NR], li[NR];
-        bool live[NR];
+
+    // ---- K1: sample / gather (one call fetches the NR rows of an iteration) ---------------
+    float x[NR], x2[NR], rew[NR];
+    int act[NR], dn[NR], li[NR];
+    bool live[NR];
+    auto gather = [&](int b0) {
 #pragma unroll
         for (int r = 0; r < NR; r++) {
             const int b = b0 + r * total_warps;
             live[r] = b < p.B;
-            const int bb = live[r] ? b : b0;
+            const int bb = live[r] ? b : (b0 < p.B ? b0 : 0);
             if (p.idx) li[r] = p.idx[(int64_t)rep * p.B + bb];
             else li[r] = (int32_t)perm_index((uint32_t)bb, (uint32_t)p.rp.len,
                                              p.seed + 0x9E3779B97F4A7C15ull * (uint64_t)rep);
@@ -138,7 +146,20 @@ narrow_learn_kernel(NarrowArgs p)
             rew[r] = __ldg(rr + phys);
             dn[r] = __ldg(rd + phys);
         }
+    };
+    if (gw < p.B) gather(gw);     // replay rows are in flight while the parameters land
 
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    for (int i = tid; i < H1 * H2; i += blockDim.x) {
+        int r = i / H2, c = i - r * H2;  // W2[r][c]
+        sW2T[c * H1 + r] = sOn[oW2 + i];
+    }
+    __syncthreads();
+
+    // warp `gw` owns rows gw, gw + total_warps, ...; NR of them are processed together
+    for (int b0 = gw; b0 < p.B; b0 += NR * total_warps) {
+        if (b0 != gw) gather(b0);
         // ---- K2: forward, online on s and target on s' (2*NR independent chains) ----
         float z[NR], zt[NR], h1[NR], h1t[NR], mk1[NR], h2[NR], h2t[NR], mk2[NR], q[NR], qt[NR];
 #pragma unroll
@@ -356,7 +377,7 @@ narrow_learn_kernel(NarrowArgs p)
         } else {
             flat[i] = g;
             if (p.fuse_adam) {
-                float w = sOn[i], m = p.m[pofs + i], v = p.v[pofs + i];
+                float w = sOn[i], m = sM[i], v = sV[i];
                 adam_update_n(w, g, m, v, p.adam);
                 p.theta[pofs + i] = w;
                 p.m[pofs + i] = m;
@@ -370,7 +391,7 @@ template <int D, int H1, int H2, int A>
 void launch_t(const NarrowArgs &a, cudaStream_t st)
 {
     constexpr int P = D * H1 + H1 + H1 * H2 + H2 + H2 * A + A;
-    size_t smem = sizeof(float) * (2 * P + H1 * H2 + (size_t)a.warps_per_cta * (P + 1));
+    size_t smem = sizeof(float) * (4 * ((P + 3) & ~3) + H1 * H2 + (size_t)a.warps_per_cta * (P + 1));
     dim3 grid(a.ctas_per_replica, a.replicas);
     narrow_learn_kernel<D, H1, H2, A><<<grid, a.warps_per_cta * 32, smem, st>>>(a);
 }
@@ -379,7 +400,7 @@ template <int D, int H1, int H2, int A>
 void configure_t(int warps)
 {
     constexpr int P = D * H1 + H1 + H1 * H2 + H2 + H2 * A + A;
-    size_t smem = sizeof(float) * (2 * P + H1 * H2 + (size_t)warps * (P + 1));
+    size_t smem = sizeof(float) * (4 * ((P + 3) & ~3) + H1 * H2 + (size_t)warps * (P + 1));
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(narrow_learn_kernel<D, H1, H2, A>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
