@@ -314,22 +314,27 @@ def run_own(args):
     h2d = R * B * (8 * D + 9) + R * B * 4
     d2h = 4 * R
 
+    def push(i):
+        h.replay_push_raw(B, *[p for _, p in bufs[i & 1]])    # H2D on the library's copy stream
+
     def step_e2e(i):
-        arrs = bufs[i & 1]
-        h.replay_push_raw(B, *[p for _, p in arrs])
+        # the batch of step i was pushed during step i-1 (double-buffered staging): its copy
+        # overlaps that step's kernels; every byte still crosses PCIe inside the timed region
         ix = idx_host[i % len(idx_host)]
-        h.learn_raw(ix.ctypes.data)
+        h.learn_raw(ix.ctypes.data)                           # H2D of the index list + the step
+        push(i + 1)
         loss = h.last_loss()                                  # D2H + stream sync
         if (i + 1) % TARGET_SYNC_EVERY == 0:
             h.sync_target()
         return loss
 
     Ke = max(3, min(K, args.e2e_steps))
+    push(0)
     for i in range(3):
         step_e2e(i)
     barrier()
     t0 = time.perf_counter()
-    for i in range(Ke):
+    for i in range(3, 3 + Ke):
         last = step_e2e(i)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -393,8 +398,9 @@ def run_own(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "what": "per step: goldq_replay_push of a fresh batch from pinned host memory + goldq_learn with "
-                            "host indices + goldq_last_loss readback; host wall clock, max over ranks"},
+                    "what": "per step: goldq_replay_push of a fresh batch from pinned host memory (copy stream, "
+                            "overlapping the previous step) + goldq_learn with host indices + goldq_last_loss "
+                            "readback (sync); host wall clock, max over ranks"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "path": {1: "generic", 2: "narrow", 3: "wide"}[h.path], "last_loss": [float(x) for x in last[:4]],
         }

@@ -75,11 +75,18 @@ struct goldq {
     int32_t *d_idx = nullptr;  // [R][B]
 
     // push staging (device) + scatter
-    float *stg_s = nullptr, *stg_s2 = nullptr, *stg_r = nullptr;
-    int32_t *stg_a = nullptr;
-    uint8_t *stg_done = nullptr;
+    // double-buffered device staging, filled on a dedicated copy stream so that the H2D copy of
+    // push i+1 overlaps the learn step enqueued after push i
+    struct Staging {
+        float *s = nullptr, *s2 = nullptr, *r = nullptr;
+        int32_t *a = nullptr;
+        uint8_t *done = nullptr;
+        cudaEvent_t copied = nullptr, scattered = nullptr;
+    } stg[2];
+    int stg_cur = 0;
     int64_t stg_cap = 0;
-    cudaEvent_t ev_push = nullptr;
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t ev_push = nullptr;      // = copied event of the latest push
 
     // reduced gradient + loss: [R][P+1]; loss per replica
     float *flat = nullptr, *loss = nullptr;
@@ -545,7 +552,11 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
     }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
-    cudaEventCreateWithFlags(&h->ev_push, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking);
+    for (auto &g : h->stg) {
+        cudaEventCreateWithFlags(&g.copied, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g.scattered, cudaEventDisableTiming);
+    }
     for (int i = 0; i < 2; i++) {
         cudaEventCreateWithFlags(&h->ev_steps[i], cudaEventDisableTiming);
         if (cudaHostAlloc((void **)&h->h_steps[i], sizeof(StepDev) * goldq::GRAPH_MAX, cudaHostAllocDefault) != cudaSuccess)
@@ -615,8 +626,8 @@ void goldq_destroy(goldq_t *h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->wide) wide_destroy(h->wide);
     void *ptrs[] = {h->theta, h->theta_t, h->m, h->v, h->flat, h->loss, h->d_idx, h->rp.s, h->rp.s2,
-                    h->rp.a, h->rp.r, h->rp.done, h->stg_s, h->stg_s2, h->stg_r, h->stg_a,
-                    h->stg_done, h->partial, h->ticket, h->bs, h->bs2, h->br, h->ba, h->bdone, h->h1,
+                    h->rp.a, h->rp.r, h->rp.done, h->stg[0].s, h->stg[0].s2, h->stg[0].r, h->stg[0].a,
+                    h->stg[0].done, h->stg[1].s, h->stg[1].s2, h->stg[1].r, h->stg[1].a, h->stg[1].done, h->partial, h->ticket, h->bs, h->bs2, h->br, h->ba, h->bdone, h->h1,
                     h->h2, h->q, h->t1, h->t2, h->qt, h->td, h->dq, h->dh2, h->dh1, h->ylab, h->mk1,
                     h->mk2, h->gslice, h->loss_part, h->px, h->ph1, h->ph2, h->pq, h->pact,
                     h->dbg_q, h->dbg_qt, h->dbg_td, h->dbg_idx};
@@ -624,7 +635,11 @@ void goldq_destroy(goldq_t *h)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->ev_push) cudaEventDestroy(h->ev_push);
+    for (auto &g : h->stg) {
+        if (g.copied) cudaEventDestroy(g.copied);
+        if (g.scattered) cudaEventDestroy(g.scattered);
+    }
+    if (h->copy_st) { cudaStreamSynchronize(h->copy_st); cudaStreamDestroy(h->copy_st); }
     if (h->own_stream && h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -702,31 +717,42 @@ int goldq_replay_push(goldq_t *h, int64_t n, const float *s, const int32_t *a, c
     CK(h, cudaSetDevice(h->dev));
     const int D = h->dims.D, R = h->R;
     if (h->stg_cap < n) {
-        void *old[] = {h->stg_s, h->stg_s2, h->stg_r, h->stg_a, h->stg_done};
+        CK(h, cudaStreamSynchronize(h->copy_st));
         CK(h, cudaStreamSynchronize(h->st));
-        for (void *p : old)
-            if (p) cudaFree(p);
         int64_t cap = n < 1024 ? 1024 : n;
-        CK(h, dalloc(&h->stg_s, (size_t)R * cap * D));
-        CK(h, dalloc(&h->stg_s2, (size_t)R * cap * D));
-        CK(h, dalloc(&h->stg_r, (size_t)R * cap));
-        CK(h, dalloc(&h->stg_a, (size_t)R * cap));
-        CK(h, dalloc(&h->stg_done, (size_t)R * cap));
+        for (auto &g : h->stg) {
+            void *old[] = {g.s, g.s2, g.r, g.a, g.done};
+            for (void *p : old)
+                if (p) cudaFree(p);
+            CK(h, dalloc(&g.s, (size_t)R * cap * D));
+            CK(h, dalloc(&g.s2, (size_t)R * cap * D));
+            CK(h, dalloc(&g.r, (size_t)R * cap));
+            CK(h, dalloc(&g.a, (size_t)R * cap));
+            CK(h, dalloc(&g.done, (size_t)R * cap));
+        }
         h->stg_cap = cap;
     }
+    goldq::Staging &g = h->stg[h->stg_cur];
+    h->stg_cur ^= 1;
     size_t rows = (size_t)R * n;
-    CK(h, cudaMemcpyAsync(h->stg_s, s, rows * D * 4, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaMemcpyAsync(h->stg_s2, s2, rows * D * 4, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaMemcpyAsync(h->stg_a, a, rows * 4, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaMemcpyAsync(h->stg_r, r, rows * 4, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaMemcpyAsync(h->stg_done, done, rows, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaEventRecord(h->ev_push, h->st));
+    // copy stream: wait until the scatter that last read this staging set is done, then copy
+    CK(h, cudaStreamWaitEvent(h->copy_st, g.scattered, 0));
+    CK(h, cudaMemcpyAsync(g.s, s, rows * D * 4, cudaMemcpyHostToDevice, h->copy_st));
+    CK(h, cudaMemcpyAsync(g.s2, s2, rows * D * 4, cudaMemcpyHostToDevice, h->copy_st));
+    CK(h, cudaMemcpyAsync(g.a, a, rows * 4, cudaMemcpyHostToDevice, h->copy_st));
+    CK(h, cudaMemcpyAsync(g.r, r, rows * 4, cudaMemcpyHostToDevice, h->copy_st));
+    CK(h, cudaMemcpyAsync(g.done, done, rows, cudaMemcpyHostToDevice, h->copy_st));
+    CK(h, cudaEventRecord(g.copied, h->copy_st));
+    h->ev_push = g.copied;
+    // main stream: the ring is updated after everything enqueued so far (in stream order)
+    CK(h, cudaStreamWaitEvent(h->st, g.copied, 0));
     // only the newest `cap` of the n items survive (PushFront + PopBack, agent.go:224-229)
     int64_t skip = n > h->rp.cap ? n - h->rp.cap : 0;
     int64_t mcount = n - skip;
     int64_t total = mcount * D * R;
-    replay_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->st>>>(
-        h->rp, D, R, n, skip, h->stg_s, h->stg_a, h->stg_r, h->stg_s2, h->stg_done);
+    replay_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->st>>>(h->rp, D, R, n, skip, g.s, g.a, g.r,
+                                                                             g.s2, g.done);
+    CK(h, cudaEventRecord(g.scattered, h->st));
     h->launches += 1;
     h->rp.head = (h->rp.head + mcount) % h->rp.cap;
     h->rp.len = h->rp.len + mcount > h->rp.cap ? h->rp.cap : h->rp.len + mcount;
@@ -737,7 +763,7 @@ int goldq_replay_push_wait(goldq_t *h)
 {
     if (!h) return GOLDQ_EINVAL;
     CK(h, cudaSetDevice(h->dev));
-    CK(h, cudaEventSynchronize(h->ev_push));
+    if (h->ev_push) CK(h, cudaEventSynchronize(h->ev_push));
     return GOLDQ_OK;
 }
 
