@@ -175,7 +175,7 @@ def run_reference(args):
                                    f"the Go reference cannot run here (no Go toolchain)"},
         "e2e": {"value": rate, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, dims, B, replicas, prec):
@@ -234,7 +234,7 @@ def run_own(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         # stdout carries exactly one JSON line: keep NCCL's version banner out of it
-        os.environ["NCCL_DEBUG"] = os.environ.get("GOLDQ_NCCL_DEBUG", "WARN")
+        os.environ["NCCL_DEBUG"] = os.environ.get("GOLDQ_NCCL_DEBUG", "NONE")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -404,13 +404,30 @@ def run_own(args):
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "path": {1: "generic", 2: "narrow", 3: "wide"}[h.path], "last_loss": [float(x) for x in last[:4]],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     h.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything libraries print meanwhile (NCCL's
+    version banner, torchrun chatter) has been diverted to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

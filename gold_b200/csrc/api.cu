@@ -133,6 +133,9 @@ struct goldq {
     int64_t graph_head = -1, graph_len = -1;     // replay state the cached graphs were captured with
     bool graph_debug = false;
 
+    cudaGraphExec_t dp_graph = nullptr;          // phase 1 of one data-parallel wide step
+    int64_t dp_graph_launches = 0;
+
     // goldq_step_breakdown
     cudaEvent_t *prof_evs = nullptr;
     int prof_n = 0;
@@ -344,7 +347,9 @@ int learn_narrow(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDe
     return check_launch(h, "learn_narrow");
 }
 
-int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev *step)
+// phases: 1 = forward/backward up to the reduced gradient, 2 = all-reduce + update (data-parallel
+// tail), 3 = both.  Single-GPU steps fuse the update into phase 1.
+int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev *step, int phases = 3)
 {
     WideStep ws{};
     ws.rp = h->rp;
@@ -362,15 +367,18 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     ws.theta_rw = h->theta;
     ws.m = h->m;
     ws.v = h->v;
-    h->iter += 1;
+    if (phases & 1) h->iter += 1;
     ws.adam = adam_consts(h->cfg, h->iter);
     ws.prof_evs = h->prof_evs;
     ws.prof_n = &h->prof_n;
     std::string err;
-    int n = wide_step(h->wide, ws, h->st, err);
-    if (n < 0) return fail(h, GOLDQ_ECUDA, err);
-    h->launches += n;
-    if (h->world > 1) {
+    int n = 0;
+    if (phases & 1) {
+        n = wide_step(h->wide, ws, h->st, err);
+        if (n < 0) return fail(h, GOLDQ_ECUDA, err);
+        h->launches += n;
+    }
+    if (h->world > 1 && (phases & 2)) {
         int rc = allreduce_flat(h);
         if (rc) return rc;
         if (h->prof_evs) cudaEventRecord(h->prof_evs[h->prof_n++], h->st);
@@ -398,6 +406,7 @@ int run_learn(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev *
 
 void drop_graphs(goldq_t *h)
 {
+    if (h->dp_graph) { cudaGraphExecDestroy(h->dp_graph); h->dp_graph = nullptr; }
     for (int i = 0; i <= goldq::GRAPH_MAX; i++)
         if (h->graph_exec[i]) { cudaGraphExecDestroy(h->graph_exec[i]); h->graph_exec[i] = nullptr; }
 }
@@ -819,8 +828,51 @@ int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
         h->graph_debug = h->debug;
     }
     static const bool no_graph = getenv("GOLDQ_NO_GRAPH") != nullptr;   // diagnostic: eager launches
-    // Data-parallel steps are issued eagerly: an ncclAllReduce captured into a CUDA graph
-    // replays ~80 us slower per step than the eager call (measured at N=2, profiles/README.md).
+    // Data-parallel steps: an ncclAllReduce captured into a CUDA graph replays ~80 us slower per
+    // step than the eager call (measured at N=2), so only the part of the step before the
+    // all-reduce is replayed from a graph; the collective and the update are launched eagerly.
+    if (!no_graph && h->world > 1 && h->path == GOLDQ_PATH_WIDE) {
+        if (!h->dp_graph) {
+            const int64_t iter0 = h->iter, launches0 = h->launches;
+            cudaGraph_t graph = nullptr;
+            CK(h, cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+            int rc = learn_wide(h, nullptr, 0, h->d_steps, 1);
+            cudaError_t e = cudaStreamEndCapture(h->st, &graph);
+            h->dp_graph_launches = h->launches - launches0;
+            h->iter = iter0;
+            h->launches = launches0;
+            if (rc != GOLDQ_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(h, GOLDQ_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&h->dp_graph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return fail(h, GOLDQ_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        }
+        while (n > 0) {
+            const int c = n < goldq::GRAPH_MAX ? n : goldq::GRAPH_MAX;
+            const int b = h->steps_buf;
+            h->steps_buf ^= 1;
+            CK(h, cudaEventSynchronize(h->ev_steps[b]));
+            for (int i = 0; i < c; i++) {
+                AdamConsts ac = adam_consts(h->cfg, h->iter + 1 + i);
+                h->h_steps[b][i].seed = seed + (uint64_t)i;
+                h->h_steps[b][i].c1 = ac.c1;
+                h->h_steps[b][i].c2 = ac.c2;
+            }
+            for (int i = 0; i < c; i++) {
+                // slot 0 is rewritten in stream order, after the previous step's kernels read it
+                CK(h, cudaMemcpyAsync(h->d_steps, &h->h_steps[b][i], sizeof(StepDev), cudaMemcpyHostToDevice, h->st));
+                CK(h, cudaGraphLaunch(h->dp_graph, h->st));
+                h->iter += 1;
+                h->launches += h->dp_graph_launches;
+                int rc = learn_wide(h, nullptr, 0, h->d_steps, 2);
+                if (rc) return rc;
+            }
+            CK(h, cudaEventRecord(h->ev_steps[b], h->st));
+            seed += (uint64_t)c;
+            n -= c;
+        }
+        return GOLDQ_OK;
+    }
     if (no_graph || h->world > 1) {
         for (int i = 0; i < n; i++) {
             int rc = run_learn(h, nullptr, seed + (uint64_t)i);

@@ -31,7 +31,20 @@ def _worker(rank, world, port, kind, q):
     for step in range(3):
         gidx = synth.sample_indices(N, Bg, step)
         h.learn(dp.shard_indices(gidx, rank, world))
-    q.put((rank, h.get_params(G.NET_ONLINE), float(h.last_loss()[0])))
+    w_after3, loss_after3 = h.get_params(G.NET_ONLINE), float(h.last_loss()[0])
+    # goldq_learn_many (graph replay up to the all-reduce) == the same steps issued one by one
+    h2 = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3], batch_size=Bg // world,
+                  global_batch=Bg, replay_capacity=N, device=rank, **kw)
+    h2.set_params(G.NET_ONLINE, w_after3); h2.set_params(G.NET_TARGET, tt)
+    m, v, it = h.get_adam_state(); h2.set_adam_state(m, v, it)
+    h2.replay_push(*data)
+    dp.init_group(h2, dist)
+    h.learn_many(5, 777 + 1000 * rank)
+    for i in range(5):
+        h2.learn(None, 777 + 1000 * rank + i)
+    same = bool(np.array_equal(h.get_params(G.NET_ONLINE), h2.get_params(G.NET_ONLINE)))
+    h2.close()
+    q.put((rank, w_after3, loss_after3, same))
     h.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -64,6 +77,7 @@ def test_two_rank_dp_equals_single_gpu(kind):
         p.join(timeout=120)
         assert p.exitcode == 0
     np.testing.assert_array_equal(res[0][1], res[1][1])             # ranks stay bit-identical
+    assert res[0][3] and res[1][3], "learn_many differs from single steps under data parallelism"
     assert res[0][2] == res[1][2]
     dims, Bg, N, kw = _cfg(kind)
     th = synth.glorot_params(dims, 1); tt = synth.glorot_params(dims, 2)
