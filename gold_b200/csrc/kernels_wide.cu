@@ -43,7 +43,7 @@ namespace {
 constexpr int BM = 128;   // UMMA M (rows of the output tile; TMEM lanes)
 constexpr int BK = 64;    // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UK = 16;    // K of one tcgen05.mma for 16-bit inputs
-constexpr int STAGES = 3;
+constexpr int DEFAULT_STAGES = 3;
 constexpr int GEMM_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 
 enum { MODE_KK = 0, MODE_MM = 1, MODE_MK = 2, MODE_KM = 3 };
@@ -63,11 +63,9 @@ struct GemmArgs {
     long long slice_stride;
 };
 
-__device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
-
 // CM > 1: clusters of CM CTAs along M (blockIdx.y) share the B tile — each CTA loads 1/CM of
 // it and multicasts the slice into every CTA of the cluster (tmB* then describe the slice box).
-template <int MODE, int BN, int EPI, int CM>
+template <int MODE, int BN, int EPI, int CM, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -79,7 +77,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     constexpr bool TMA_OUT = (EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_MASK_BF16);
     static_assert(!TMA_OUT || BN % 64 == 0, "bf16 tiles are stored in 64-column boxes");
     constexpr bool A_MN = (MODE == MODE_MM || MODE == MODE_MK), B_MN = (MODE == MODE_MM || MODE == MODE_KM);
-    static_assert(BN == 128 || BN == 64 || BN == 32, "BN");
+    static_assert(BN == 256 || BN == 128 || BN == 64 || BN == 32, "BN");
+    static_assert(!(EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_MASK_BF16) || (BN / 64) * 16384 <= STAGES * (BM * BK * 2 + BN * BK * 2),
+                  "the bf16 staging tile must fit in the operand ring");
     static_assert(!B_MN || BN % 64 == 0, "MN-major B tiles are 64-wide swizzle atoms");
     static_assert(CM == 1 || CM == 2 || CM == 4 || CM == 8, "cluster size");
     static_assert(CM == 1 || (B_MN ? (64 / CM) % 8 == 0 : (BN / CM) % 8 == 0), "slices are whole swizzle atoms");
@@ -191,8 +191,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_BIAS_F32) {
             // stage this tile's bias once (one coalesced load), while the mainloop runs
             const float *const bias = prob ? g.bias_1 : g.bias;
-            const int t = threadIdx.x - 64;
-            if (t < BN) s_bias[t] = (n0 + t < g.N && n0 + t < g.n_store) ? __ldg(bias + n0 + t) : 0.f;
+            for (int t = threadIdx.x - 64; t < BN; t += 128)
+                s_bias[t] = (n0 + t < g.N && n0 + t < g.n_store) ? __ldg(bias + n0 + t) : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         if (nkb > 0) {
@@ -290,7 +290,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, int STAGES>
 constexpr size_t gemm_smem_bytes()
 {
     return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
@@ -377,11 +377,11 @@ cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 
 // opt in to the dynamic shared memory of one instantiation (called at create time, never
 // under stream capture)
-template <int MODE, int BN, int EPI, int CM = 1>
+template <int MODE, int BN, int EPI, int CM = 1, int STAGES = DEFAULT_STAGES>
 cudaError_t configure_gemm()
 {
-    return cudaFuncSetAttribute(umma_gemm_kernel<MODE, BN, EPI, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)gemm_smem_bytes<MODE, BN>());
+    return cudaFuncSetAttribute(umma_gemm_kernel<MODE, BN, EPI, CM, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)gemm_smem_bytes<MODE, BN, STAGES>());
 }
 
 cudaError_t configure_all_gemms()
@@ -401,21 +401,26 @@ cudaError_t configure_all_gemms()
     if (e == cudaSuccess) e = configure_gemm<MODE_MM, 128, EPI_F32_SLICE, 4>();
     if (e == cudaSuccess) e = configure_gemm<MODE_KK, 128, EPI_F32_SLICE, 4>();
     if (e == cudaSuccess) e = configure_gemm<MODE_KM, 128, EPI_F32_SLICE, 4>();
+    // 128x256 tiles, two stages (two CTAs per SM: 2 x 97 KB smem, 2 x 256 TMEM columns)
+    if (e == cudaSuccess) e = configure_gemm<MODE_KM, 256, EPI_BIAS_RELU_BF16, 1, 2>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KK, 256, EPI_MASK_BF16, 1, 2>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KM, 256, EPI_F32_SLICE, 1, 2>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KK, 256, EPI_F32_SLICE, 1, 2>();
     return e;
 }
 
-template <int MODE, int BN, int EPI, int CM = 1>
+template <int MODE, int BN, int EPI, int CM = 1, int STAGES = DEFAULT_STAGES>
 cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, GemmArgs g, int nsplit, cudaStream_t st,
                         const CUtensorMap *ta1 = nullptr, const CUtensorMap *tb1 = nullptr, bool pdl = false,
                         const CUtensorMap *tc0 = nullptr, const CUtensorMap *tc1 = nullptr)
 {
-    constexpr size_t smem = gemm_smem_bytes<MODE, BN>();
+    constexpr size_t smem = gemm_smem_bytes<MODE, BN, STAGES>();
     g.nsplit = nsplit;
     const int nprob = ta1 ? 2 : 1;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit * nprob);
     if (CM > 1 && grid.y % CM != 0) return cudaErrorInvalidConfiguration;
     if ((EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_MASK_BF16) && !tc0) return cudaErrorInvalidValue;
-    return launch_kc(umma_gemm_kernel<MODE, BN, EPI, CM>, grid, dim3(GEMM_THREADS), smem, st, pdl, CM, ta, tb,
+    return launch_kc(umma_gemm_kernel<MODE, BN, EPI, CM, STAGES>, grid, dim3(GEMM_THREADS), smem, st, pdl, CM, ta, tb,
                      ta1 ? *ta1 : ta, tb1 ? *tb1 : tb, tc0 ? *tc0 : ta, tc1 ? *tc1 : (tc0 ? *tc0 : ta), g);
 }
 
@@ -824,6 +829,7 @@ struct WideNet {
     __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3p = nullptr, *w3t = nullptr;
     CUtensorMap tm_w1_mn, tm_w2_mn, tm_w3p_mn, tm_w2_k;
     CUtensorMap tm_w1_mn_s4, tm_w2_mn_s4, tm_w2_k_s4;   // multicast slice boxes (clusters of 4)
+    CUtensorMap tm_w2_k256;                              // K-major B operand, 256-row box
 };
 
 struct WideState {
@@ -847,6 +853,7 @@ struct WideState {
     cudaStream_t s1 = nullptr, s2 = nullptr;
     cudaEvent_t ev_dz2 = nullptr, ev_dx = nullptr, ev_s1 = nullptr, ev_s2 = nullptr;
     bool pdl = true;
+    bool bn256 = false;                    // 128x256 output tiles for the N = H GEMMs
     bool mc_rows = false, mc_h1 = false;   // B-tile multicast usable: row tiles / H1 tiles divide by 4
     bool debug = false;
 };
@@ -923,6 +930,8 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
              make_tmap(&nn.tm_w2_mn_s4, nn.w2, d.H1, d.H2, d.H2, 16, err);
     }
     ok = ok && make_tmap(&w->net[0].tm_w2_k_s4, w->net[0].w2, d.H1, d.H2, d.H2, 32, err);
+    ok = ok && make_tmap(&w->net[0].tm_w2_k256, w->net[0].w2, d.H1, d.H2, d.H2, 256, err);
+    w->bn256 = getenv("GOLDQ_NO_BN256") == nullptr && d.H1 % 256 == 0 && d.H2 % 256 == 0;   // 82.3 -> 79.7 us/step
     // measured on B200 (round 1): with 128x128 tiles the cluster's lock-step costs more than the
     // saved L2->SM traffic (95 vs 87 us/step), so B-tile multicast is opt-in
     w->mc_rows = getenv("GOLDQ_MULTICAST") != nullptr && ((B + BM - 1) / BM) % 4 == 0;
@@ -1066,7 +1075,9 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g.M = B; g.N = d.H1; g.K = d.D; g.k_per_split = ((d.D + BK - 1) / BK) * BK;
     g.out_bf16 = w->h1; g.out_bf16_1 = w->t1; g.bias = s.theta + o.b1; g.bias_1 = s.theta_t + o.b1;
     g.ldo = d.H1; g.n_store = d.H1;
-    if (w->mc_rows)
+    if (w->bn256)
+        WCK((launch_gemm<MODE_KM, 256, EPI_BIAS_RELU_BF16, 1, 2>(w->tm_x_a, on.tm_w1_mn, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn, pdl, &w->tm_h1_a, &w->tm_t1_a)));
+    else if (w->mc_rows)
         WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16, 4>(w->tm_x_a, on.tm_w1_mn_s4, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn_s4, pdl, &w->tm_h1_a, &w->tm_t1_a)));
     else
         WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_x_a, on.tm_w1_mn, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn, pdl, &w->tm_h1_a, &w->tm_t1_a)));
@@ -1074,7 +1085,9 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g.N = d.H2; g.K = d.H1; g.k_per_split = ((d.H1 + BK - 1) / BK) * BK;
     g.out_bf16 = w->h2; g.out_bf16_1 = w->t2; g.bias = s.theta + o.b2; g.bias_1 = s.theta_t + o.b2;
     g.ldo = d.H2; g.n_store = d.H2;
-    if (w->mc_rows)
+    if (w->bn256)
+        WCK((launch_gemm<MODE_KM, 256, EPI_BIAS_RELU_BF16, 1, 2>(w->tm_h1_a, on.tm_w2_mn, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn, pdl, &w->tm_h2_a, &w->tm_t2_a)));
+    else if (w->mc_rows)
         WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16, 4>(w->tm_h1_a, on.tm_w2_mn_s4, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn_s4, pdl, &w->tm_h2_a, &w->tm_t2_a)));
     else
         WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_h1_a, on.tm_w2_mn, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn, pdl, &w->tm_h2_a, &w->tm_t2_a)));
@@ -1117,7 +1130,9 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g = GemmArgs{};
     g.M = B; g.N = d.H1; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = w->dz1; g.mask_src = w->h1; g.ldo = d.H1; g.n_store = d.H1;
-    if (w->mc_rows)
+    if (w->bn256)
+        WCK((launch_gemm<MODE_KK, 256, EPI_MASK_BF16, 1, 2>(w->tm_dz2_a, on.tm_w2_k256, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
+    else if (w->mc_rows)
         WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16, 4>(w->tm_dz2_a, on.tm_w2_k_s4, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
     else
         WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16>(w->tm_dz2_a, on.tm_w2_k, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
@@ -1233,6 +1248,12 @@ int wide_selftest_gemm(int mode, int M, int N, int K, int nsplit, const uint16_t
     } else if (mode == 14) {  // KM, B multicast
         if (!make_tmap(&ta, dA, M, K, K, BM, err) || !make_tmap(&tb, dB, K, N, N, 16, err)) return -1;
         WCK((launch_gemm<MODE_KM, 128, EPI_F32_SLICE, 4>(ta, tb, g, nsplit, 0)));
+    } else if (mode == 20) {  // KK, 128x256 tiles, 2 stages
+        if (!make_tmap(&ta, dA, M, K, K, BM, err) || !make_tmap(&tb, dB, N, K, K, 256, err)) return -1;
+        WCK((launch_gemm<MODE_KK, 256, EPI_F32_SLICE, 1, 2>(ta, tb, g, nsplit, 0)));
+    } else if (mode == 24) {  // KM, 128x256 tiles, 2 stages
+        if (!make_tmap(&ta, dA, M, K, K, BM, err) || !make_tmap(&tb, dB, K, N, N, 64, err)) return -1;
+        WCK((launch_gemm<MODE_KM, 256, EPI_F32_SLICE, 1, 2>(ta, tb, g, nsplit, 0)));
     } else {
         err = "selftest: unknown mode";
         return -1;

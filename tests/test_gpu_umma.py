@@ -28,6 +28,8 @@ def bf16_bits(x):
     # B tile multicast over clusters of 4 CTAs along M (M tiles must divide by 4)
     (10, 512, 128, 64, 1), (10, 8192, 512, 512, 1), (10, 1024, 256, 1024, 2), (11, 512, 512, 1024, 4),
     (11, 512, 128, 192, 1), (14, 512, 128, 128, 1), (14, 8192, 512, 512, 1), (14, 1024, 136, 72, 1),
+    # 128x256 tiles, two stages
+    (20, 256, 256, 128, 1), (20, 8192, 512, 512, 1), (20, 200, 264, 72, 1), (24, 256, 256, 128, 1), (24, 8192, 512, 512, 1),
 ])
 def test_umma_gemm_matches_numpy(mode, M, N, K, nsplit):
     api_mode, mode = mode, mode % 10
