@@ -34,7 +34,6 @@ __host__ __device__ inline uint32_t perm_index(uint32_t i, uint32_t n, uint64_t 
     uint32_t x = i;
     do {
         uint32_t L = x >> h, R = x & mask;
-#pragma unroll
         for (int round = 0; round < 4; round++) {
             uint32_t key = mix32(k0 + 0x632BE5ABu * (uint32_t)round, k1 ^ (uint32_t)round);
             uint32_t t = L ^ (mix32(R, key) & mask);

@@ -100,3 +100,40 @@ def test_agent_loop_semantics():
     assert not np.array_equal(target0, agent.target_policy.learnables())
     assert np.isfinite(agent.last_loss())
     agent.close()
+
+
+@pytest.mark.gpu
+def test_her_learn_step_is_deepq_on_state_goal():
+    """her/agent.go:129-189: the learn step equals the DQN step on state‖goal inputs —
+    bit-exact Q/TD against the oracle fed with the concatenated tensors."""
+    from gold_b200 import _capi as G, her
+    from oracle import binding as O
+    sd, gd, A, B = 3, 1, 2, 20          # obs_dim = 4 -> CartPole-shaped policy, fused narrow path
+    agent = her.Agent(her.AgentConfig(seed=5), sd, gd, A)
+    rng = np.random.Generator(np.random.PCG64(1))
+    events = [her.Event(rng.uniform(-1, 1, sd), rng.uniform(-1, 1, gd), int(rng.integers(0, A)),
+                        rng.uniform(-1, 1, sd), -1.0, False) for _ in range(64)]
+    agent.remember(*events)
+    th = agent.policy.learnables().copy(); tt = agent.target_policy.learnables().copy()
+    agent._h.debug_enable(True)
+    idx = np.arange(20, dtype=np.int32) * 3
+    agent.learn(indices=idx)
+    # oracle on the same rows: logical index i = i-th newest
+    rows = [events[len(events) - 1 - i] for i in idx]
+    s = np.stack([np.concatenate([e.state, e.goal]) for e in rows])
+    s2 = np.stack([np.concatenate([e.observation, e.goal]) for e in rows])
+    P = th.size
+    w = th.copy()
+    ref = O.learn((4, 24, 24, 2), B, w, tt, np.zeros(P, np.float32), np.zeros(P, np.float32), 0, s,
+                  [e.action for e in rows], [e.reward for e in rows], s2, [e.done for e in rows], gamma=0.9)
+    np.testing.assert_array_equal(agent._h.debug_fetch(G.DBG_Q_ONLINE), ref["q_online"])
+    np.testing.assert_array_equal(agent._h.debug_fetch(G.DBG_TD), ref["td"])
+    np.testing.assert_allclose(agent.policy.learnables(), w, rtol=1e-5, atol=2e-6)
+    assert agent.episodes == 1
+    # hindsight: one Learn per relabelled event, last one terminal with the successful reward
+    n0 = agent.memory_len()
+    agent.hindsight(events[:5])
+    assert agent.memory_len() == n0 + 5 and agent.episodes == 6
+    a = agent.action(events[0].state, events[0].goal)
+    assert a in (0, 1) and agent.epsilon < 1.0
+    agent.close()
