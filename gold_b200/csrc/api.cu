@@ -926,7 +926,7 @@ int goldq_step_breakdown(goldq_t *h, uint64_t seed, int32_t max_kernels, float *
         rc = run_learn(h, nullptr, seed);
         h->prof_evs = nullptr;
         if (names && names_bytes > 0)
-            snprintf(names, names_bytes, "%s%s", wide_step_kernel_names(),
+            snprintf(names, names_bytes, "%s%s", wide_step_kernel_names(h->wide).c_str(),
                      h->world > 1 ? "\nncclAllReduce(grad)\nAdam + bf16 shadow (K5)" : "");
     } else {
         // single fused launch (narrow) or an unfused chain (generic): one interval for the step

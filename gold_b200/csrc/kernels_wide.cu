@@ -297,6 +297,242 @@ constexpr size_t gemm_smem_bytes()
 }
 
 // ---------------------------------------------------------------------------
+// Fused forward: Q = relu(relu(X W1 + b1) W2 + b2) W3 + b3 for a 128-row slab of ONE network in
+// ONE CTA (blockIdx.y selects online / target).  H1 and H2 never leave the SM between layers:
+// the epilogue writes them (bf16, 128B-swizzled K-major boxes) into shared memory where the
+// next layer's tcgen05.mma reads them as its A operand; the online network's H1/H2 are also
+// TMA-stored to global for the backward pass.  Weights stream through a 3-stage ring of
+// [64 k][256 n] MN-major tiles (96 KB in flight; the X tile aliases the tail of the H tile).  Accumulators: 128 x 512 fp32 = all 512 TMEM columns, as two
+// 256-column halves so that the epilogue of half 0 overlaps the MMAs of half 1.
+//
+// Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..9 = epilogue (warp w reads
+// TMEM lane quarter w % 4 and column group (w - 2) / 4 of every half).
+// Shapes: H1 == H2 == 512, D in {64, 128}, A <= 64 (W3 padded to 64 columns).
+// ---------------------------------------------------------------------------
+constexpr int FF_H = 512;
+constexpr int FF_THREADS = 320;
+constexpr int FF_EPI_THREADS = 256;
+constexpr int FF_WSTAGES = 3;
+constexpr uint32_t FF_BOX = 16384;            // [128 rows][64 bf16] swizzled box
+constexpr uint32_t FF_WSTAGE_BYTES = 32768;   // [4 n-groups][64 k-rows][128 B]
+
+struct FFArgs {
+    int B, D, A;
+    const float *bias[2][3];     // [net][layer]
+    float *q[2];                 // [net]: Q / Q' fp32 [B][A]
+};
+
+template <int KD>   // KD = D / 64 k-blocks of layer 1
+__global__ void __launch_bounds__(FF_THREADS, 1)
+ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+                  const __grid_constant__ CUtensorMap tmW1_0, const __grid_constant__ CUtensorMap tmW1_1,
+                  const __grid_constant__ CUtensorMap tmW2_0, const __grid_constant__ CUtensorMap tmW2_1,
+                  const __grid_constant__ CUtensorMap tmW3_0, const __grid_constant__ CUtensorMap tmW3_1,
+                  const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmH2,
+                  const FFArgs g)
+{
+    constexpr uint32_t X_BYTES = KD * FF_BOX;
+    constexpr uint32_t IDESC_256 = make_idesc_bf16(BM, 256, false, true);
+    constexpr uint32_t IDESC_64 = make_idesc_bf16(BM, 64, false, true);
+    constexpr int KH = FF_H / 64;                       // 8 k-blocks of layers 2 and 3
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sH = smem;                                 // 8 boxes: H1, then H2
+    // X aliases the LAST boxes of the H tile: they belong to accumulator half 1, whose epilogue
+    // starts only after every layer-1 MMA (the readers of X) has retired
+    uint8_t *sX = sH + (KH - KD) * FF_BOX;
+    uint8_t *sW = sH + KH * FF_BOX;                     // weight ring
+    __shared__ uint64_t full_w[FF_WSTAGES], empty_w[FF_WSTAGES], x_full, acc_full[2], acc_free[2], h_ready;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int net = blockIdx.y;
+    const int m0 = blockIdx.x * BM;
+    const CUtensorMap *tmX = net ? &tmX1 : &tmX0;
+    const CUtensorMap *tmW1 = net ? &tmW1_1 : &tmW1_0;
+    const CUtensorMap *tmW2 = net ? &tmW2_1 : &tmW2_0;
+    const CUtensorMap *tmW3 = net ? &tmW3_1 : &tmW3_0;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(tmX); prefetch_tmap(tmW1); prefetch_tmap(tmW2); prefetch_tmap(tmW3);
+        for (int s = 0; s < FF_WSTAGES; s++) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 1); }
+        mbar_init(&x_full, 1);
+        mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+        mbar_init(&acc_free[0], FF_EPI_THREADS / 32); mbar_init(&acc_free[1], FF_EPI_THREADS / 32);
+        mbar_init(&h_ready, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_slot, 512);
+    pdl_launch_dependents();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer: X, then the weight tiles in consumption order =====
+        if (elect_one()) {
+            mbar_expect_tx(&x_full, X_BYTES);
+            for (int kb = 0; kb < KD; kb++) tma_load_2d(sX + kb * FF_BOX, tmX, kb * 64, m0, &x_full);
+            int it = 0;
+            auto load_w = [&](const CUtensorMap *tm, int n_base, int k, int groups) {
+                const int s = it % FF_WSTAGES;
+                const uint32_t ph = (it / FF_WSTAGES) & 1;
+                mbar_wait(&empty_w[s], ph ^ 1);
+                mbar_expect_tx(&full_w[s], groups * 8192);
+                for (int h = 0; h < groups; h++)
+                    tma_load_2d(sW + s * FF_WSTAGE_BYTES + h * 8192, tm, n_base + 64 * h, k, &full_w[s]);
+                it++;
+            };
+            for (int half = 0; half < 2; half++)
+                for (int kb = 0; kb < KD; kb++) load_w(tmW1, half * 256, kb * 64, 4);
+            for (int half = 0; half < 2; half++)
+                for (int kb = 0; kb < KH; kb++) load_w(tmW2, half * 256, kb * 64, 4);
+            for (int kb = 0; kb < KH; kb++) load_w(tmW3, 0, kb * 64, 1);
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        int it = 0;
+        auto mma_block = [&](uint32_t a_box_addr, uint32_t d_tmem, uint32_t idesc, bool first) {
+            const int s = it % FF_WSTAGES;
+            const uint32_t ph = (it / FF_WSTAGES) & 1;
+            mbar_wait(&full_w[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t baddr = smem_u32(sW + s * FF_WSTAGE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < BK / UK; kk++)
+                    mma_bf16(d_tmem, make_smem_desc(a_box_addr + kk * 32, 16, 1024),
+                             make_smem_desc(baddr + kk * 2048, 8192, 1024), idesc, (!first || kk) ? 1u : 0u);
+                mma_commit(&empty_w[s]);
+            }
+            __syncwarp();
+            it++;
+        };
+        // layer 1: A = X
+        mbar_wait(&x_full, 0);
+        for (int half = 0; half < 2; half++) {
+            for (int kb = 0; kb < KD; kb++) mma_block(smem_u32(sX + kb * FF_BOX), tmem + half * 256, IDESC_256, kb == 0);
+            if (elect_one()) mma_commit(&acc_full[half]);
+            __syncwarp();
+        }
+        // layer 2: A = H1 (written by the epilogue); both accumulator halves must be drained
+        mbar_wait(&h_ready, 0);
+        mbar_wait(&acc_free[0], 0);
+        mbar_wait(&acc_free[1], 0);
+        tc_fence_after();
+        for (int half = 0; half < 2; half++) {
+            for (int kb = 0; kb < KH; kb++) mma_block(smem_u32(sH + kb * FF_BOX), tmem + half * 256, IDESC_256, kb == 0);
+            if (elect_one()) mma_commit(&acc_full[half]);
+            __syncwarp();
+        }
+        // layer 3: A = H2, N = 64 (W3 padded)
+        mbar_wait(&h_ready, 1);
+        mbar_wait(&acc_free[0], 1);
+        mbar_wait(&acc_free[1], 1);
+        tc_fence_after();
+        for (int kb = 0; kb < KH; kb++) mma_block(smem_u32(sH + kb * FF_BOX), tmem, IDESC_64, kb == 0);
+        if (elect_one()) mma_commit(&acc_full[0]);
+        __syncwarp();
+    } else {
+        // ===== epilogue warps =====
+        const int q = warp & 3;                 // TMEM lane quarter
+        const int cg = (warp - 2) >> 2;         // column group within a half: chunks cg*4 .. cg*4+3
+        const int rt = q * 32 + lane;           // row within the slab
+        const int et = threadIdx.x - 64;        // 0..255
+        for (int layer = 0; layer < 2; layer++) {
+            const float *bias = g.bias[net][layer];
+            if (layer == 1) {
+                // every L2 MMA has read H1 once acc_full[1] fires; the H1 TMA store must also
+                // have finished reading the tile before H2 overwrites it
+                mbar_wait(&acc_full[1], 1);
+                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            for (int half = 0; half < 2; half++) {
+                mbar_wait(&acc_full[half], (uint32_t)layer);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 4; c++) {
+                    const int c0 = half * 256 + (cg * 4 + c) * 32;       // column within [0, 512)
+                    float bv[32];
+#pragma unroll
+                    for (int v = 0; v < 8; v++) {
+                        const float4 t = __ldg(reinterpret_cast<const float4 *>(bias + c0) + v);
+                        bv[4 * v] = t.x; bv[4 * v + 1] = t.y; bv[4 * v + 2] = t.z; bv[4 * v + 3] = t.w;
+                    }
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                    tmem_ld_wait();
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float v0 = __uint_as_float(r[j]) + bv[j], v1 = __uint_as_float(r[j + 1]) + bv[j + 1];
+                        v0 = (v0 >= 0.f) ? v0 : -0.0f;       // Rectify, sign bit = mask (nn.go:162-189)
+                        v1 = (v1 >= 0.f) ? v1 : -0.0f;
+                        __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+                        packed[j >> 1] = *reinterpret_cast<uint32_t *>(&pk);
+                    }
+                    uint8_t *dst = sH + (c0 >> 6) * FF_BOX + rt * 128;
+                    const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+                    for (int v = 0; v < 4; v++)
+                        *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
+                            make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_free[half])) : "memory");
+            }
+            // H tile complete: visible to the async proxy (next layer's MMA, TMA store)
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) {
+                if (net == 0) {     // the backward pass needs the online network's activations
+                    const CUtensorMap *tmH = layer ? &tmH2 : &tmH1;
+                    for (int b = 0; b < KH; b++) tma_store_2d(tmH, sH + b * FF_BOX, 64 * b, m0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_ready)) : "memory");
+            }
+        }
+        // layer 3: Q = acc + b3 -> global fp32 [B][A]; column group 0 warps only (64 columns)
+        if (cg == 0) {
+            mbar_wait(&acc_full[0], 0);          // third completion of acc_full[0]: parity 0 again
+            tc_fence_after();
+            const float *bias = g.bias[net][2];
+            const int row = m0 + rt;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                tmem_ld_wait();
+                if (row < g.B) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (c0 + j < g.A) g.q[net][(size_t)row * g.A + c0 + j] = __uint_as_float(r[j]) + __ldg(bias + c0 + j);
+                }
+            }
+            tc_fence_before();
+        }
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+template <int KD>
+constexpr size_t ff_smem_bytes()
+{
+    return (size_t)8 * FF_BOX + FF_WSTAGES * FF_WSTAGE_BYTES + 1024;
+}
+
+// ---------------------------------------------------------------------------
 // host: tensor maps
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -406,6 +642,10 @@ cudaError_t configure_all_gemms()
     if (e == cudaSuccess) e = configure_gemm<MODE_KK, 256, EPI_MASK_BF16, 1, 2>();
     if (e == cudaSuccess) e = configure_gemm<MODE_KM, 256, EPI_F32_SLICE, 1, 2>();
     if (e == cudaSuccess) e = configure_gemm<MODE_KK, 256, EPI_F32_SLICE, 1, 2>();
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(ff_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<1>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(ff_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<2>());
     return e;
 }
 
@@ -853,7 +1093,9 @@ struct WideState {
     cudaStream_t s1 = nullptr, s2 = nullptr;
     cudaEvent_t ev_dz2 = nullptr, ev_dx = nullptr, ev_s1 = nullptr, ev_s2 = nullptr;
     bool pdl = true;
+    bool ff = false;                       // fused three-layer forward kernel usable
     bool bn256 = false;                    // 128x256 output tiles for the N = H GEMMs
+    std::vector<const char *> prof_names;  // labels of the launches of the last profiled step
     bool mc_rows = false, mc_h1 = false;   // B-tile multicast usable: row tiles / H1 tiles divide by 4
     bool debug = false;
 };
@@ -931,6 +1173,7 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     }
     ok = ok && make_tmap(&w->net[0].tm_w2_k_s4, w->net[0].w2, d.H1, d.H2, d.H2, 32, err);
     ok = ok && make_tmap(&w->net[0].tm_w2_k256, w->net[0].w2, d.H1, d.H2, d.H2, 256, err);
+    w->ff = getenv("GOLDQ_NO_FF") == nullptr && d.H1 == FF_H && d.H2 == FF_H && (d.D == 64 || d.D == 128) && d.A <= W3_PAD;
     w->bn256 = getenv("GOLDQ_NO_BN256") == nullptr && d.H1 % 256 == 0 && d.H2 % 256 == 0;   // 82.3 -> 79.7 us/step
     // measured on B200 (round 1): with 128x128 tiles the cluster's lock-step costs more than the
     // saved L2->SM traffic (95 vs 87 us/step), so B-tile multicast is opt-in
@@ -1061,17 +1304,39 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     const bool prof = s.prof_evs != nullptr;
     const bool pdl = w->pdl && !prof;   // programmatic dependent launch along the st chain
     cudaStream_t s1 = prof ? st : w->s1, s2 = prof ? st : w->s2;
-    auto mark = [&]() { if (prof) cudaEventRecord(s.prof_evs[(*s.prof_n)++], st); };
+    if (prof) w->prof_names.clear();
+    auto mark = [&](const char *name) {
+        if (prof) { cudaEventRecord(s.prof_evs[(*s.prof_n)++], st); w->prof_names.push_back(name); }
+    };
     {
         int n = B * (d.D >> 2);
         WCK(launch_k(wide_gather_kernel, dim3((n + 255) / 256), dim3(256), 0, st, pdl, s.rp, d.D, s.idx, s.seed, s.step,
                      s.idx_out, B, w->x, w->x2, w->ba, w->br, w->bdone));
         launches++;
-        mark();
+        mark("gather+cast (K1)");
     }
-    // forward, online (problem 0) and target (problem 1) in one launch per layer
     WideNet &on = w->net[0], &tg = w->net[1];
     GemmArgs g{};
+    if (w->ff) {
+        // forward of both networks, all three layers, one launch
+        FFArgs fa{};
+        fa.B = B; fa.D = d.D; fa.A = d.A;
+        fa.bias[0][0] = s.theta + o.b1; fa.bias[0][1] = s.theta + o.b2; fa.bias[0][2] = s.theta + o.b3;
+        fa.bias[1][0] = s.theta_t + o.b1; fa.bias[1][1] = s.theta_t + o.b2; fa.bias[1][2] = s.theta_t + o.b3;
+        fa.q[0] = w->q; fa.q[1] = w->qt;
+        dim3 grid((B + BM - 1) / BM, 2);
+        if (d.D == 128)
+            WCK(launch_k(ff_forward_kernel<2>, grid, dim3(FF_THREADS), ff_smem_bytes<2>(), st, pdl, w->tm_x_a, w->tm_x2_a,
+                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
+                         w->tm_h2_a, fa));
+        else
+            WCK(launch_k(ff_forward_kernel<1>, grid, dim3(FF_THREADS), ff_smem_bytes<1>(), st, pdl, w->tm_x_a, w->tm_x2_a,
+                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
+                         w->tm_h2_a, fa));
+        launches += 1;
+        mark("fused forward L1-L3 online+target (tcgen05)");
+    } else {
+    // forward, online (problem 0) and target (problem 1) in one launch per layer
     g.M = B; g.N = d.H1; g.K = d.D; g.k_per_split = ((d.D + BK - 1) / BK) * BK;
     g.out_bf16 = w->h1; g.out_bf16_1 = w->t1; g.bias = s.theta + o.b1; g.bias_1 = s.theta_t + o.b1;
     g.ldo = d.H1; g.n_store = d.H1;
@@ -1081,7 +1346,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16, 4>(w->tm_x_a, on.tm_w1_mn_s4, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn_s4, pdl, &w->tm_h1_a, &w->tm_t1_a)));
     else
         WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_x_a, on.tm_w1_mn, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn, pdl, &w->tm_h1_a, &w->tm_t1_a)));
-    mark();
+    mark("fwd L1 online+target (tcgen05)");
     g.N = d.H2; g.K = d.H1; g.k_per_split = ((d.H1 + BK - 1) / BK) * BK;
     g.out_bf16 = w->h2; g.out_bf16_1 = w->t2; g.bias = s.theta + o.b2; g.bias_1 = s.theta_t + o.b2;
     g.ldo = d.H2; g.n_store = d.H2;
@@ -1091,17 +1356,18 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16, 4>(w->tm_h1_a, on.tm_w2_mn_s4, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn_s4, pdl, &w->tm_h2_a, &w->tm_t2_a)));
     else
         WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_h1_a, on.tm_w2_mn, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn, pdl, &w->tm_h2_a, &w->tm_t2_a)));
-    mark();
+    mark("fwd L2 online+target (tcgen05)");
     g.N = W3_PAD; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = g.out_bf16_1 = nullptr; g.out_f32 = w->q; g.out_f32_1 = w->qt;
     g.bias = s.theta + o.b3; g.bias_1 = s.theta_t + o.b3; g.ldo = d.A; g.n_store = d.A;
     WCK((launch_gemm<MODE_KM, 64, EPI_BIAS_F32>(w->tm_h2_a, on.tm_w3p_mn, g, 1, st, &w->tm_t2_a, &tg.tm_w3p_mn, pdl)));
-    mark();
+    mark("fwd L3 online+target (tcgen05)");
     launches += 3;
+    }
 
     WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), sizeof(float) * 4 * d.H2, st, pdl, w->q, w->qt, w->ba, w->br,
                  w->bdone, B, d.H2, d.A, s.sc, w->h2, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part));
-    mark();
+    mark("TD + dZ2 + db2/db3 (K3)");
     launches += 1;
 
     // backward: three independent chains after dZ2 —  s1: dW2 | s2: dW3, db1 | st: dX -> dW1
@@ -1115,7 +1381,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g.M = d.H2; g.N = 32; g.K = B; g.k_per_split = w->kps3;
     g.out_f32 = w->w3_slices; g.ldo = d.A; g.n_store = d.A; g.slice_stride = (long long)d.H2 * d.A;
     WCK((launch_gemm<MODE_MK, 32, EPI_F32_SLICE>(w->tm_h2_mm, w->tm_dqT_b, g, w->ns3, s2)));
-    mark();
+    mark("dW3 (tcgen05)");
     // dW2 = H1^T dZ2 : M = H1, N = H2, K = B
     g = GemmArgs{};
     g.M = d.H1; g.N = d.H2; g.K = B; g.k_per_split = w->kps2;
@@ -1124,7 +1390,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE, 4>(w->tm_h1_mm, w->tm_dz2_mm_s4, g, w->ns2, s1)));
     else
         WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, s1)));
-    mark();
+    mark("dW2 split-K (tcgen05)");
     if (!prof) WCK(cudaEventRecord(w->ev_s1, s1));
     // dZ1 = (dZ2 W2^T) * mask1 : M = B, N = H1, K = H2 ; B operand = W2 [H1 rows][H2 cols]
     g = GemmArgs{};
@@ -1136,7 +1402,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16, 4>(w->tm_dz2_a, on.tm_w2_k_s4, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
     else
         WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16>(w->tm_dz2_a, on.tm_w2_k, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
-    mark();
+    mark("dX -> dZ1 (tcgen05)");
     if (!prof) {
         WCK(cudaEventRecord(w->ev_dx, st));
         WCK(cudaStreamWaitEvent(s2, w->ev_dx, 0));
@@ -1145,7 +1411,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         dim3 grid((d.H1 + 63) / 64, w->nb1);
         wide_colsum_kernel<<<grid, 256, 0, s2>>>(w->dz1, B, d.H1, w->b1_part);
         WCK(cudaGetLastError());
-        mark();
+        mark("db1 colsum");
     }
     if (!prof) WCK(cudaEventRecord(w->ev_s2, s2));
     // dW1 = X^T dZ1 : M = D, N = H1, K = B
@@ -1153,7 +1419,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g.M = d.D; g.N = d.H1; g.K = B; g.k_per_split = w->kps1;
     g.out_f32 = w->w1_slices; g.ldo = d.H1; g.n_store = d.H1; g.slice_stride = (long long)d.D * d.H1;
     WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_x_mm, w->tm_dz1_mm, g, w->ns1, st, nullptr, nullptr, pdl)));
-    mark();
+    mark("dW1 split-K (tcgen05)");
     if (!prof) {
         WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
         WCK(cudaStreamWaitEvent(st, w->ev_s2, 0));
@@ -1178,16 +1444,19 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         wide_update_kernel<false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
                                                           s.adam, s.step, shadow_ptrs(w, 0), nullptr);
     WCK(cudaGetLastError());
-    mark();
+    mark("reduce + Adam + bf16 shadow (K5)");
     launches++;
     return launches;
 }
 
-const char *wide_step_kernel_names()
+std::string wide_step_kernel_names(WideState *w)
 {
-    return "gather+cast (K1)\nfwd L1 online+target (tcgen05)\nfwd L2 online+target (tcgen05)\nfwd L3 online+target (tcgen05)\n"
-           "TD + dZ2 + db2/db3 (K3)\ndW3 (tcgen05)\ndW2 split-K (tcgen05)\ndX -> dZ1 (tcgen05)\ndb1 colsum\n"
-           "dW1 split-K (tcgen05)\nreduce + Adam + bf16 shadow (K5)";
+    std::string out;
+    for (size_t i = 0; i < w->prof_names.size(); i++) {
+        if (i) out += "\n";
+        out += w->prof_names[i];
+    }
+    return out;
 }
 
 void wide_set_debug(WideState *w, bool on) { w->debug = on; }

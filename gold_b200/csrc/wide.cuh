@@ -37,7 +37,7 @@ int wide_sync_target(WideState *w, cudaStream_t st, std::string &err);
 int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, float *v, AdamConsts ac,
                       const StepDev *step, cudaStream_t st, std::string &err);
 int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err);
-const char *wide_step_kernel_names();
+std::string wide_step_kernel_names(WideState *w);
 void wide_set_debug(WideState *w, bool on);
 void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const float **td);
 const uint8_t *wide_done_ptr(WideState *w);
