@@ -261,7 +261,8 @@ def run_own(args):
         h.dp_init(uid[0], rank, world)
     R = max(replicas, 1)
     rows_per_step_gpu = B * R
-    K, W = args.steps, max(args.warmup, 3)
+    # warm-up covers at least one 16-step graph launch so that the step graph is built before timing
+    K, W = args.steps, max(args.warmup, 32)
 
     seed0 = 1_000_003 * (rank + 1)
 
@@ -280,7 +281,7 @@ def run_own(args):
     run_resident(0, W)
     h.sync()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
     if sampler:
         sampler.start()
         time.sleep(0.25)
@@ -354,7 +355,8 @@ def run_own(args):
     D_, H1_, H2_, A_ = dims
     if h.path == G.PATH_WIDE:
         # algorithmic FLOPs of each tensor-core launch (2 per MAC; online and target share a launch)
-        kflops = {"fwd L1 online+target (tcgen05)": 2 * 2.0 * B * D_ * H1_,
+        kflops = {"fused forward L1-L3 online+target (tcgen05)": 2 * 2.0 * B * (D_ * H1_ + H1_ * H2_ + H2_ * A_),
+                  "fwd L1 online+target (tcgen05)": 2 * 2.0 * B * D_ * H1_,
                   "fwd L2 online+target (tcgen05)": 2 * 2.0 * B * H1_ * H2_,
                   "fwd L3 online+target (tcgen05)": 2 * 2.0 * B * H2_ * A_,
                   "dW3 (tcgen05)": 2.0 * B * H2_ * A_, "dW2 split-K (tcgen05)": 2.0 * B * H1_ * H2_,
@@ -438,8 +440,9 @@ def main():
     ap.add_argument("--replay-rows", type=int, default=0)
     ap.add_argument("--cpu-rows", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=50)
-    ap.add_argument("--chunk", type=int, default=25, help="learn steps per goldq_learn_many call")
+    ap.add_argument("--chunk", type=int, default=64, help="learn steps per goldq_learn_many call")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample nvidia-smi during the timed region")
     ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for --impl reference")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -124,6 +124,7 @@ struct goldq {
 
     // CUDA-graph replay of learn steps (goldq_learn_many)
     static constexpr int GRAPH_MAX = 32;
+    static constexpr int GRAPH_CHUNK = 16;       // steps per graph launch
     StepDev *d_steps = nullptr;                  // [GRAPH_MAX] per-step scalars read by captured kernels
     StepDev *h_steps[2] = {nullptr, nullptr};    // pinned staging, double buffered
     cudaEvent_t ev_steps[2] = {nullptr, nullptr};
@@ -880,8 +881,17 @@ int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
         }
         return GOLDQ_OK;
     }
+    // One graph size only (GRAPH_CHUNK steps): building a graph costs milliseconds, so a call
+    // never instantiates more than this one; the remainder (< GRAPH_CHUNK steps) is launched eagerly.
     while (n > 0) {
-        const int c = n < goldq::GRAPH_MAX ? n : goldq::GRAPH_MAX;
+        const int c = goldq::GRAPH_CHUNK;
+        if (n < c) {
+            for (int i = 0; i < n; i++) {
+                int rc = run_learn(h, nullptr, seed + (uint64_t)i);
+                if (rc) return rc;
+            }
+            return GOLDQ_OK;
+        }
         if (!h->graph_exec[c]) {
             int rc = build_graph(h, c);
             if (rc) return rc;

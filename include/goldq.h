@@ -140,8 +140,8 @@ int goldq_learn(goldq_t *h, const int32_t *idx, uint64_t seed);
 /* Same, with the index list already in device memory (no host traffic). */
 int goldq_learn_device_indices(goldq_t *h, const int32_t *idx_dev);
 /* n consecutive learn steps with device-drawn indices (step i uses seed + i), enqueued as
- * ONE CUDA graph launch per chunk of up to 32 steps: the same work as n calls of
- * goldq_learn(h, NULL, seed + i), without n times the launch overhead.  No target sync
+ * ONE CUDA graph launch per 16 steps (a remainder below 16 is launched step by step): the
+ * same work as n calls of goldq_learn(h, NULL, seed + i), without n times the launch overhead.  No target sync
  * happens inside; the host layer keeps calling it between its goldq_sync_target calls
  * (agent.go:173,181-190). */
 int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed);

@@ -108,7 +108,7 @@ def test_her_learn_step_is_deepq_on_state_goal():
     bit-exact Q/TD against the oracle fed with the concatenated tensors."""
     from gold_b200 import _capi as G, her
     from oracle import binding as O
-    sd, gd, A, B = 3, 1, 2, 20          # obs_dim = 4 -> CartPole-shaped policy, fused narrow path
+    sd, gd, A, B = 2, 2, 2, 20          # goals live in observation space (her/agent.go:251); obs_dim = 4
     agent = her.Agent(her.AgentConfig(seed=5), sd, gd, A)
     rng = np.random.Generator(np.random.PCG64(1))
     events = [her.Event(rng.uniform(-1, 1, sd), rng.uniform(-1, 1, gd), int(rng.integers(0, A)),
