@@ -125,6 +125,8 @@ struct goldq {
     // CUDA-graph replay of learn steps (goldq_learn_many)
     static constexpr int GRAPH_MAX = 32;
     static constexpr int GRAPH_CHUNK = 16;       // steps per graph launch
+    int pf_set = 0, pf_have = 0;                 // batch double buffering while capturing (build_graph)
+    const StepDev *pf_next = nullptr;
     StepDev *d_steps = nullptr;                  // [GRAPH_MAX] per-step scalars read by captured kernels
     StepDev *h_steps[2] = {nullptr, nullptr};    // pinned staging, double buffered
     cudaEvent_t ev_steps[2] = {nullptr, nullptr};
@@ -372,6 +374,9 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     ws.adam = adam_consts(h->cfg, h->iter);
     ws.prof_evs = h->prof_evs;
     ws.prof_n = &h->prof_n;
+    ws.set = h->pf_set;
+    ws.have = h->pf_have;
+    ws.next_step = h->pf_next;
     std::string err;
     int n = 0;
     if (phases & 1) {
@@ -421,7 +426,18 @@ int build_graph(goldq_t *h, int c)
     cudaGraph_t graph = nullptr;
     CK(h, cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
     int rc = GOLDQ_OK;
-    for (int i = 0; i < c && rc == GOLDQ_OK; i++) rc = run_learn(h, nullptr, 0, h->d_steps + i);
+    static const bool no_prefetch = getenv("GOLDQ_NO_PREFETCH") != nullptr;
+    const bool prefetch = h->path == GOLDQ_PATH_WIDE && h->world <= 1 && !no_prefetch;
+    for (int i = 0; i < c && rc == GOLDQ_OK; i++) {
+        if (prefetch) {   // batch i+1 is gathered on a side branch while step i computes
+            h->pf_set = i & 1;
+            h->pf_have = i > 0;
+            h->pf_next = i + 1 < c ? h->d_steps + i + 1 : nullptr;
+        }
+        rc = run_learn(h, nullptr, 0, h->d_steps + i);
+    }
+    h->pf_set = h->pf_have = 0;
+    h->pf_next = nullptr;
     cudaError_t e = cudaStreamEndCapture(h->st, &graph);
     h->graph_launches[c] = h->launches - launches0;
     h->iter = iter0;            // capturing executes nothing

@@ -1077,21 +1077,29 @@ struct WideState {
     Offsets o;
     int B = 0, sm_count = 148;
     WideNet net[2];
-    __nv_bfloat16 *x = nullptr, *x2 = nullptr, *h1 = nullptr, *h2 = nullptr, *t1 = nullptr, *t2 = nullptr;
+    // gathered batch, double buffered: inside a multi-step graph the gather of step i+1 runs on
+    // a side branch while step i computes (WideStep::set / have / next_step)
+    struct BatchSet {
+        __nv_bfloat16 *x = nullptr, *x2 = nullptr;
+        float *br = nullptr;
+        int32_t *ba = nullptr;
+        uint8_t *bdone = nullptr;
+        CUtensorMap tm_x_a, tm_x2_a, tm_x_mm;
+    } bs[2];
+    int last_set = 0;
+    __nv_bfloat16 *h1 = nullptr, *h2 = nullptr, *t1 = nullptr, *t2 = nullptr;
     __nv_bfloat16 *dz2 = nullptr, *dz1 = nullptr, *dqT = nullptr;
-    float *q = nullptr, *qt = nullptr, *td = nullptr, *br = nullptr, *dqv = nullptr;
-    int32_t *ba = nullptr;
-    uint8_t *bdone = nullptr;
+    float *q = nullptr, *qt = nullptr, *td = nullptr, *dqv = nullptr;
     float *w1_slices = nullptr, *w2_slices = nullptr, *w3_slices = nullptr, *b1_part = nullptr, *b2_part = nullptr,
           *row_part = nullptr;
     int ns1 = 1, ns2 = 1, ns3 = 1, kps1 = 0, kps2 = 0, kps3 = 0, nb1 = 1, nb2 = 1, nrow = 1;
     // activation tensor maps: KK A-operands (box 128 rows) and MN-major operands (box 64 k-rows)
-    CUtensorMap tm_x_a, tm_x2_a, tm_h1_a, tm_t1_a, tm_h2_a, tm_t2_a, tm_dz2_a, tm_dz1_a;
-    CUtensorMap tm_x_mm, tm_h1_mm, tm_h2_mm, tm_dz2_mm, tm_dz1_mm, tm_dqT_b, tm_dz2_mm_s4;
+    CUtensorMap tm_h1_a, tm_t1_a, tm_h2_a, tm_t2_a, tm_dz2_a, tm_dz1_a;
+    CUtensorMap tm_h1_mm, tm_h2_mm, tm_dz2_mm, tm_dz1_mm, tm_dqT_b, tm_dz2_mm_s4;
     // side streams: independent backward GEMMs run concurrently (fork/join by events; under
     // stream capture these become parallel branches of the step graph)
-    cudaStream_t s1 = nullptr, s2 = nullptr;
-    cudaEvent_t ev_dz2 = nullptr, ev_dx = nullptr, ev_s1 = nullptr, ev_s2 = nullptr;
+    cudaStream_t s1 = nullptr, s2 = nullptr, s3 = nullptr;
+    cudaEvent_t ev_dz2 = nullptr, ev_dx = nullptr, ev_s1 = nullptr, ev_s2 = nullptr, ev_fork = nullptr, ev_gather = nullptr;
     bool pdl = true;
     bool ff = false;                       // fused three-layer forward kernel usable
     bool bn256 = false;                    // 128x256 output tiles for the N = H GEMMs
@@ -1136,11 +1144,14 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     ok = ok && dmalloc(&w->net[0].w3t, (size_t)32 * d.H2, err);
     if (ok) cudaMemset(w->net[0].w3t, 0, (size_t)32 * d.H2 * 2);
     size_t n = B;
-    ok = ok && dmalloc(&w->x, n * d.D, err) && dmalloc(&w->x2, n * d.D, err) && dmalloc(&w->h1, n * d.H1, err) &&
+    for (int k = 0; k < 2; k++)
+        ok = ok && dmalloc(&w->bs[k].x, n * d.D, err) && dmalloc(&w->bs[k].x2, n * d.D, err) && dmalloc(&w->bs[k].br, n, err) &&
+             dmalloc(&w->bs[k].ba, n, err) && dmalloc(&w->bs[k].bdone, n, err);
+    ok = ok && dmalloc(&w->h1, n * d.H1, err) &&
          dmalloc(&w->h2, n * d.H2, err) && dmalloc(&w->t1, n * d.H1, err) && dmalloc(&w->t2, n * d.H2, err) &&
          dmalloc(&w->dz2, n * d.H2, err) && dmalloc(&w->dz1, n * d.H1, err) && dmalloc(&w->dqT, n * 32, err) &&
          dmalloc(&w->q, n * d.A, err) && dmalloc(&w->qt, n * d.A, err) && dmalloc(&w->td, n, err) &&
-         dmalloc(&w->dqv, n, err) && dmalloc(&w->br, n, err) && dmalloc(&w->ba, n, err) && dmalloc(&w->bdone, n, err);
+         dmalloc(&w->dqv, n, err);
     if (!ok) { wide_destroy(w); return nullptr; }
     int tiles1 = ((d.D + BM - 1) / BM) * ((d.H1 + 127) / 128);
     int tiles2 = ((d.H1 + BM - 1) / BM) * ((d.H2 + 127) / 128);
@@ -1180,12 +1191,15 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     w->mc_rows = getenv("GOLDQ_MULTICAST") != nullptr && ((B + BM - 1) / BM) % 4 == 0;
     w->mc_h1 = getenv("GOLDQ_MULTICAST") != nullptr && ((d.H1 + BM - 1) / BM) % 4 == 0;
     // activations as KK A operands: [B rows][K cols], box 128 rows
-    ok = ok && make_tmap(&w->tm_x_a, w->x, B, d.D, d.D, BM, err) && make_tmap(&w->tm_x2_a, w->x2, B, d.D, d.D, BM, err) &&
-         make_tmap(&w->tm_h1_a, w->h1, B, d.H1, d.H1, BM, err) && make_tmap(&w->tm_t1_a, w->t1, B, d.H1, d.H1, BM, err) &&
+    for (int k = 0; k < 2; k++)
+        ok = ok && make_tmap(&w->bs[k].tm_x_a, w->bs[k].x, B, d.D, d.D, BM, err) &&
+             make_tmap(&w->bs[k].tm_x2_a, w->bs[k].x2, B, d.D, d.D, BM, err) &&
+             make_tmap(&w->bs[k].tm_x_mm, w->bs[k].x, B, d.D, d.D, 64, err);
+    ok = ok && make_tmap(&w->tm_h1_a, w->h1, B, d.H1, d.H1, BM, err) && make_tmap(&w->tm_t1_a, w->t1, B, d.H1, d.H1, BM, err) &&
          make_tmap(&w->tm_h2_a, w->h2, B, d.H2, d.H2, BM, err) && make_tmap(&w->tm_t2_a, w->t2, B, d.H2, d.H2, BM, err) &&
          make_tmap(&w->tm_dz2_a, w->dz2, B, d.H2, d.H2, BM, err) && make_tmap(&w->tm_dz1_a, w->dz1, B, d.H1, d.H1, BM, err);
     // activations as MN-major operands: [K = B rows][MN cols], box 64 k-rows x 64 mn
-    ok = ok && make_tmap(&w->tm_x_mm, w->x, B, d.D, d.D, 64, err) && make_tmap(&w->tm_h1_mm, w->h1, B, d.H1, d.H1, 64, err) &&
+    ok = ok && make_tmap(&w->tm_h1_mm, w->h1, B, d.H1, d.H1, 64, err) &&
          make_tmap(&w->tm_h2_mm, w->h2, B, d.H2, d.H2, 64, err) && make_tmap(&w->tm_dz2_mm, w->dz2, B, d.H2, d.H2, 64, err) &&
          make_tmap(&w->tm_dz1_mm, w->dz1, B, d.H1, d.H1, 64, err) &&
          make_tmap(&w->tm_dz2_mm_s4, w->dz2, B, d.H2, d.H2, 16, err);
@@ -1195,7 +1209,8 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     w->pdl = getenv("GOLDQ_NO_PDL") == nullptr;
     cudaStreamCreateWithFlags(&w->s1, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&w->s2, cudaStreamNonBlocking);
-    cudaEvent_t *evs[] = {&w->ev_dz2, &w->ev_dx, &w->ev_s1, &w->ev_s2};
+    cudaStreamCreateWithFlags(&w->s3, cudaStreamNonBlocking);
+    cudaEvent_t *evs[] = {&w->ev_dz2, &w->ev_dx, &w->ev_s1, &w->ev_s2, &w->ev_fork, &w->ev_gather};
     for (cudaEvent_t *e : evs) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
     return w;
 }
@@ -1208,13 +1223,18 @@ void wide_destroy(WideState *w)
         for (void *q : p)
             if (q) cudaFree(q);
     }
-    void *p[] = {w->x, w->x2, w->h1, w->h2, w->t1, w->t2, w->dz2, w->dz1, w->dqT, w->q, w->qt, w->td, w->dqv, w->br,
-                 w->ba, w->bdone, w->w1_slices, w->w2_slices, w->w3_slices, w->b1_part, w->b2_part, w->row_part};
+    for (int k = 0; k < 2; k++) {
+        void *p[] = {w->bs[k].x, w->bs[k].x2, w->bs[k].br, w->bs[k].ba, w->bs[k].bdone};
+        for (void *q : p)
+            if (q) cudaFree(q);
+    }
+    void *p[] = {w->h1, w->h2, w->t1, w->t2, w->dz2, w->dz1, w->dqT, w->q, w->qt, w->td, w->dqv, w->w1_slices, w->w2_slices, w->w3_slices, w->b1_part, w->b2_part, w->row_part};
     for (void *q : p)
         if (q) cudaFree(q);
     if (w->s1) cudaStreamDestroy(w->s1);
     if (w->s2) cudaStreamDestroy(w->s2);
-    cudaEvent_t evs[] = {w->ev_dz2, w->ev_dx, w->ev_s1, w->ev_s2};
+    if (w->s3) cudaStreamDestroy(w->s3);
+    cudaEvent_t evs[] = {w->ev_dz2, w->ev_dx, w->ev_s1, w->ev_s2, w->ev_fork, w->ev_gather};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     delete w;
@@ -1308,12 +1328,28 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     auto mark = [&](const char *name) {
         if (prof) { cudaEventRecord(s.prof_evs[(*s.prof_n)++], st); w->prof_names.push_back(name); }
     };
-    {
-        int n = B * (d.D >> 2);
-        WCK(launch_k(wide_gather_kernel, dim3((n + 255) / 256), dim3(256), 0, st, pdl, s.rp, d.D, s.idx, s.seed, s.step,
-                     s.idx_out, B, w->x, w->x2, w->ba, w->br, w->bdone));
+    WideState::BatchSet &bt = w->bs[s.set & 1];
+    w->last_set = s.set & 1;
+    const int gather_threads = B * (d.D >> 2);
+    if (!s.have) {
+        WCK(launch_k(wide_gather_kernel, dim3((gather_threads + 255) / 256), dim3(256), 0, st, pdl, s.rp, d.D, s.idx, s.seed,
+                     s.step, s.idx_out, B, bt.x, bt.x2, bt.ba, bt.br, bt.bdone));
         launches++;
         mark("gather+cast (K1)");
+    } else {
+        WCK(cudaStreamWaitEvent(st, w->ev_gather, 0));   // this step's batch was gathered by the previous step's side branch
+    }
+    if (s.next_step) {
+        // gather the NEXT step's batch into the other buffer set while this step computes.  The fork
+        // follows everything the previous step launched, i.e. every reader of that buffer set.
+        WideState::BatchSet &nx = w->bs[(s.set & 1) ^ 1];
+        WCK(cudaEventRecord(w->ev_fork, st));
+        WCK(cudaStreamWaitEvent(w->s3, w->ev_fork, 0));
+        wide_gather_kernel<<<(gather_threads + 255) / 256, 256, 0, w->s3>>>(s.rp, d.D, nullptr, 0, s.next_step, s.idx_out, B,
+                                                                            nx.x, nx.x2, nx.ba, nx.br, nx.bdone);
+        WCK(cudaGetLastError());
+        WCK(cudaEventRecord(w->ev_gather, w->s3));
+        launches++;
     }
     WideNet &on = w->net[0], &tg = w->net[1];
     GemmArgs g{};
@@ -1326,11 +1362,11 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         fa.q[0] = w->q; fa.q[1] = w->qt;
         dim3 grid((B + BM - 1) / BM, 2);
         if (d.D == 128)
-            WCK(launch_k(ff_forward_kernel<2>, grid, dim3(FF_THREADS), ff_smem_bytes<2>(), st, pdl, w->tm_x_a, w->tm_x2_a,
+            WCK(launch_k(ff_forward_kernel<2>, grid, dim3(FF_THREADS), ff_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
                          on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
                          w->tm_h2_a, fa));
         else
-            WCK(launch_k(ff_forward_kernel<1>, grid, dim3(FF_THREADS), ff_smem_bytes<1>(), st, pdl, w->tm_x_a, w->tm_x2_a,
+            WCK(launch_k(ff_forward_kernel<1>, grid, dim3(FF_THREADS), ff_smem_bytes<1>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
                          on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
                          w->tm_h2_a, fa));
         launches += 1;
@@ -1341,11 +1377,11 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g.out_bf16 = w->h1; g.out_bf16_1 = w->t1; g.bias = s.theta + o.b1; g.bias_1 = s.theta_t + o.b1;
     g.ldo = d.H1; g.n_store = d.H1;
     if (w->bn256)
-        WCK((launch_gemm<MODE_KM, 256, EPI_BIAS_RELU_BF16, 1, 2>(w->tm_x_a, on.tm_w1_mn, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn, pdl, &w->tm_h1_a, &w->tm_t1_a)));
+        WCK((launch_gemm<MODE_KM, 256, EPI_BIAS_RELU_BF16, 1, 2>(bt.tm_x_a, on.tm_w1_mn, g, 1, st, &bt.tm_x2_a, &tg.tm_w1_mn, pdl, &w->tm_h1_a, &w->tm_t1_a)));
     else if (w->mc_rows)
-        WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16, 4>(w->tm_x_a, on.tm_w1_mn_s4, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn_s4, pdl, &w->tm_h1_a, &w->tm_t1_a)));
+        WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16, 4>(bt.tm_x_a, on.tm_w1_mn_s4, g, 1, st, &bt.tm_x2_a, &tg.tm_w1_mn_s4, pdl, &w->tm_h1_a, &w->tm_t1_a)));
     else
-        WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_x_a, on.tm_w1_mn, g, 1, st, &w->tm_x2_a, &tg.tm_w1_mn, pdl, &w->tm_h1_a, &w->tm_t1_a)));
+        WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(bt.tm_x_a, on.tm_w1_mn, g, 1, st, &bt.tm_x2_a, &tg.tm_w1_mn, pdl, &w->tm_h1_a, &w->tm_t1_a)));
     mark("fwd L1 online+target (tcgen05)");
     g.N = d.H2; g.K = d.H1; g.k_per_split = ((d.H1 + BK - 1) / BK) * BK;
     g.out_bf16 = w->h2; g.out_bf16_1 = w->t2; g.bias = s.theta + o.b2; g.bias_1 = s.theta_t + o.b2;
@@ -1365,8 +1401,8 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     launches += 3;
     }
 
-    WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), sizeof(float) * 4 * d.H2, st, pdl, w->q, w->qt, w->ba, w->br,
-                 w->bdone, B, d.H2, d.A, s.sc, w->h2, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part));
+    WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), sizeof(float) * 4 * d.H2, st, pdl, w->q, w->qt, bt.ba, bt.br,
+                 bt.bdone, B, d.H2, d.A, s.sc, w->h2, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part));
     mark("TD + dZ2 + db2/db3 (K3)");
     launches += 1;
 
@@ -1418,7 +1454,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g = GemmArgs{};
     g.M = d.D; g.N = d.H1; g.K = B; g.k_per_split = w->kps1;
     g.out_f32 = w->w1_slices; g.ldo = d.H1; g.n_store = d.H1; g.slice_stride = (long long)d.D * d.H1;
-    WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_x_mm, w->tm_dz1_mm, g, w->ns1, st, nullptr, nullptr, pdl)));
+    WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(bt.tm_x_mm, w->tm_dz1_mm, g, w->ns1, st, nullptr, nullptr, pdl)));
     mark("dW1 split-K (tcgen05)");
     if (!prof) {
         WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
@@ -1464,7 +1500,7 @@ void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const floa
 {
     *q = w->q; *qt = w->qt; *td = w->td;
 }
-const uint8_t *wide_done_ptr(WideState *w) { return w->bdone; }
+const uint8_t *wide_done_ptr(WideState *w) { return w->bs[w->last_set].bdone; }
 
 // ---------------------------------------------------------------------------
 // stand-alone tcgen05 GEMM self-test (diagnostic ABI: goldq_selftest_umma)

@@ -23,6 +23,11 @@ struct WideStep {
     int fuse_update;       // 1: Adam + bf16 shadow refresh in the reduction kernel
     float *theta_rw, *m, *v;
     AdamConsts adam;
+    // batch double buffering inside a captured multi-step graph: `set` = buffer set this step
+    // reads; have = 1: it was already gathered by the previous step's side branch;
+    // next_step != nullptr: gather the next step's batch (seed from *next_step) into the other set
+    int set, have;
+    const StepDev *next_step;
     // profiling (goldq_step_breakdown): record an event after every launch, single stream
     cudaEvent_t *prof_evs;
     int *prof_n;
