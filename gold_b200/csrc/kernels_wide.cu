@@ -307,7 +307,7 @@ constexpr size_t gemm_smem_bytes()
 //
 // Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..9 = epilogue (warp w reads
 // TMEM lane quarter w % 4 and column group (w - 2) / 4 of every half).
-// Shapes: H1 == H2 == 512, D in {64, 128}, A <= 64 (W3 padded to 64 columns).
+// Shapes: H1 == H2 == 512, D in {64, 128}, A <= 32 (W3 padded to 64 columns).
 // ---------------------------------------------------------------------------
 constexpr int FF_H = 512;
 constexpr int FF_THREADS = 320;
@@ -323,7 +323,7 @@ struct FFArgs {
 };
 
 template <int KD>   // KD = D / 64 k-blocks of layer 1
-__global__ void __launch_bounds__(FF_THREADS, 1)
+__global__ void __launch_bounds__(FF_THREADS, 1)   // 168 registers: 3 warps per SM sub-partition
 ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
                   const __grid_constant__ CUtensorMap tmW1_0, const __grid_constant__ CUtensorMap tmW1_1,
                   const __grid_constant__ CUtensorMap tmW2_0, const __grid_constant__ CUtensorMap tmW2_1,
@@ -335,6 +335,7 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     constexpr uint32_t IDESC_256 = make_idesc_bf16(BM, 256, false, true);
     constexpr uint32_t IDESC_64 = make_idesc_bf16(BM, 64, false, true);
     constexpr int KH = FF_H / 64;                       // 8 k-blocks of layers 2 and 3
+    static_assert(KH % 4 == 0, "layer 3 loads four k-blocks per ring stage");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -377,25 +378,29 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             mbar_expect_tx(&x_full, X_BYTES);
             for (int kb = 0; kb < KD; kb++) tma_load_2d(sX + kb * FF_BOX, tmX, kb * 64, m0, &x_full);
             int it = 0;
-            auto load_w = [&](const CUtensorMap *tm, int n_base, int k, int groups) {
+            // one ring stage = 4 boxes of [64 k][64 n]: four n-groups of one k-block (layers 1, 2) or
+            // four consecutive k-blocks of the 64-column W3 tile (layer 3)
+            auto load_w = [&](const CUtensorMap *tm, int n_base, int k, int dn, int dk) {
                 const int s = it % FF_WSTAGES;
                 const uint32_t ph = (it / FF_WSTAGES) & 1;
                 mbar_wait(&empty_w[s], ph ^ 1);
-                mbar_expect_tx(&full_w[s], groups * 8192);
-                for (int h = 0; h < groups; h++)
-                    tma_load_2d(sW + s * FF_WSTAGE_BYTES + h * 8192, tm, n_base + 64 * h, k, &full_w[s]);
+                mbar_expect_tx(&full_w[s], FF_WSTAGE_BYTES);
+                for (int h = 0; h < 4; h++)
+                    tma_load_2d(sW + s * FF_WSTAGE_BYTES + h * 8192, tm, n_base + dn * h, k + dk * h, &full_w[s]);
                 it++;
             };
             for (int half = 0; half < 2; half++)
-                for (int kb = 0; kb < KD; kb++) load_w(tmW1, half * 256, kb * 64, 4);
+                for (int kb = 0; kb < KD; kb++) load_w(tmW1, half * 256, kb * 64, 64, 0);
             for (int half = 0; half < 2; half++)
-                for (int kb = 0; kb < KH; kb++) load_w(tmW2, half * 256, kb * 64, 4);
-            for (int kb = 0; kb < KH; kb++) load_w(tmW3, 0, kb * 64, 1);
+                for (int kb = 0; kb < KH; kb++) load_w(tmW2, half * 256, kb * 64, 64, 0);
+            // all of W3 goes out as soon as two stages free up, i.e. before the H2 store queues
+            // 128 KB on the same TMA unit
+            for (int kq = 0; kq < KH / 4; kq++) load_w(tmW3, 0, kq * 256, 0, 64);
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         int it = 0;
-        auto mma_block = [&](uint32_t a_box_addr, uint32_t d_tmem, uint32_t idesc, bool first) {
+        auto mma_block = [&](uint32_t a_box_addr, uint32_t d_tmem, bool first) {
             const int s = it % FF_WSTAGES;
             const uint32_t ph = (it / FF_WSTAGES) & 1;
             mbar_wait(&full_w[s], ph);
@@ -405,7 +410,7 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
 #pragma unroll
                 for (int kk = 0; kk < BK / UK; kk++)
                     mma_bf16(d_tmem, make_smem_desc(a_box_addr + kk * 32, 16, 1024),
-                             make_smem_desc(baddr + kk * 2048, 8192, 1024), idesc, (!first || kk) ? 1u : 0u);
+                             make_smem_desc(baddr + kk * 2048, 8192, 1024), IDESC_256, (!first || kk) ? 1u : 0u);
                 mma_commit(&empty_w[s]);
             }
             __syncwarp();
@@ -414,7 +419,7 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         // layer 1: A = X
         mbar_wait(&x_full, 0);
         for (int half = 0; half < 2; half++) {
-            for (int kb = 0; kb < KD; kb++) mma_block(smem_u32(sX + kb * FF_BOX), tmem + half * 256, IDESC_256, kb == 0);
+            for (int kb = 0; kb < KD; kb++) mma_block(smem_u32(sX + kb * FF_BOX), tmem + half * 256, kb == 0);
             if (elect_one()) mma_commit(&acc_full[half]);
             __syncwarp();
         }
@@ -424,16 +429,34 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         mbar_wait(&acc_free[1], 0);
         tc_fence_after();
         for (int half = 0; half < 2; half++) {
-            for (int kb = 0; kb < KH; kb++) mma_block(smem_u32(sH + kb * FF_BOX), tmem + half * 256, IDESC_256, kb == 0);
+            for (int kb = 0; kb < KH; kb++) mma_block(smem_u32(sH + kb * FF_BOX), tmem + half * 256, kb == 0);
             if (elect_one()) mma_commit(&acc_full[half]);
             __syncwarp();
         }
-        // layer 3: A = H2, N = 64 (W3 padded)
+        // layer 3: A = H2, N = 64 (W3 padded); a ring stage holds four k-blocks
         mbar_wait(&h_ready, 1);
         mbar_wait(&acc_free[0], 1);
         mbar_wait(&acc_free[1], 1);
         tc_fence_after();
-        for (int kb = 0; kb < KH; kb++) mma_block(smem_u32(sH + kb * FF_BOX), tmem, IDESC_64, kb == 0);
+        for (int kq = 0; kq < KH / 4; kq++) {
+            const int s = it % FF_WSTAGES;
+            const uint32_t ph = (it / FF_WSTAGES) & 1;
+            mbar_wait(&full_w[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t baddr = smem_u32(sW + s * FF_WSTAGE_BYTES);
+#pragma unroll
+                for (int h = 0; h < 4; h++)
+#pragma unroll
+                    for (int kk = 0; kk < BK / UK; kk++)
+                        mma_bf16(tmem, make_smem_desc(smem_u32(sH + (kq * 4 + h) * FF_BOX) + kk * 32, 16, 1024),
+                                 make_smem_desc(baddr + h * 8192 + kk * 2048, 8192, 1024), IDESC_64,
+                                 (kq || h || kk) ? 1u : 0u);
+                mma_commit(&empty_w[s]);
+            }
+            __syncwarp();
+            it++;
+        }
         if (elect_one()) mma_commit(&acc_full[0]);
         __syncwarp();
     } else {
@@ -442,80 +465,138 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         const int cg = (warp - 2) >> 2;         // column group within a half: chunks cg*4 .. cg*4+3
         const int rt = q * 32 + lane;           // row within the slab
         const int et = threadIdx.x - 64;        // 0..255
-        for (int layer = 0; layer < 2; layer++) {
-            const float *bias = g.bias[net][layer];
-            if (layer == 1) {
-                // every L2 MMA has read H1 once acc_full[1] fires; the H1 TMA store must also
-                // have finished reading the tile before H2 overwrites it
-                mbar_wait(&acc_full[1], 1);
-                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
-            for (int half = 0; half < 2; half++) {
-                mbar_wait(&acc_full[half], (uint32_t)layer);
-                tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < 4; c++) {
-                    const int c0 = half * 256 + (cg * 4 + c) * 32;       // column within [0, 512)
-                    float bv[32];
+        const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+        // Bias: lane l keeps element l of each 32-column chunk this warp will process and the values
+        // are broadcast by shuffle.  All loads are issued here, long before they are needed (loads
+        // inside the chunk loop are predicated on nothing the compiler can hoist and cost a full L2
+        // round trip per chunk).
+        float bl[2][8];
 #pragma unroll
-                    for (int v = 0; v < 8; v++) {
-                        const float4 t = __ldg(reinterpret_cast<const float4 *>(bias + c0) + v);
-                        bv[4 * v] = t.x; bv[4 * v + 1] = t.y; bv[4 * v + 2] = t.z; bv[4 * v + 3] = t.w;
-                    }
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                    tmem_ld_wait();
-                    uint32_t packed[16];
+        for (int l = 0; l < 2; l++)
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float v0 = __uint_as_float(r[j]) + bv[j], v1 = __uint_as_float(r[j + 1]) + bv[j + 1];
-                        v0 = (v0 >= 0.f) ? v0 : -0.0f;       // Rectify, sign bit = mask (nn.go:162-189)
-                        v1 = (v1 >= 0.f) ? v1 : -0.0f;
-                        __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
-                        packed[j >> 1] = *reinterpret_cast<uint32_t *>(&pk);
-                    }
-                    uint8_t *dst = sH + (c0 >> 6) * FF_BOX + rt * 128;
-                    const int ch0 = (c0 & 63) >> 3;
+            for (int i = 0; i < 8; i++) bl[l][i] = __ldg(g.bias[net][l] + (i >> 2) * 256 + (cg * 4 + (i & 3)) * 32 + lane);
+        const float b3 = (lane < g.A) ? __ldg(g.bias[net][2] + lane) : 0.f;
+
+        auto pack_chunk = [&](const uint32_t(&r)[32], float bme, uint32_t(&packed)[16]) {
 #pragma unroll
-                    for (int v = 0; v < 4; v++)
-                        *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
-                            make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_free[half])) : "memory");
+            for (int j = 0; j < 32; j += 2) {
+                float v0 = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bme, j);
+                float v1 = __uint_as_float(r[j + 1]) + __shfl_sync(0xffffffffu, bme, j + 1);
+                v0 = (v0 >= 0.f) ? v0 : -0.0f;       // Rectify, sign bit = mask (nn.go:162-189)
+                v1 = (v1 >= 0.f) ? v1 : -0.0f;
+                __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&pk);
             }
-            // H tile complete: visible to the async proxy (next layer's MMA, TMA store)
-            fence_proxy_async_smem();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (et == 0) {
-                if (net == 0) {     // the backward pass needs the online network's activations
-                    const CUtensorMap *tmH = layer ? &tmH2 : &tmH1;
-                    for (int b = 0; b < KH; b++) tma_store_2d(tmH, sH + b * FF_BOX, 64 * b, m0);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_ready)) : "memory");
+        };
+        auto store_chunk = [&](int c0, const uint32_t(&packed)[16]) {
+            uint8_t *dst = sH + (c0 >> 6) * FF_BOX + rt * 128;
+            const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+                *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
+                    make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+        };
+        auto arrive = [&](uint64_t *bar) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+        };
+        auto col0 = [&](int half, int c) { return half * 256 + (cg * 4 + c) * 32; };
+
+        // ---- layer 1 -> H1.  The TMEM load of chunk c+1 is in flight while chunk c is packed.
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            mbar_wait(&acc_full[half], 0);
+            tc_fence_after();
+            uint32_t r[2][32];
+            tmem_ld_32x32(tq + (uint32_t)col0(half, 0), r[0]);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                tmem_ld_wait();
+                if (c < 3) tmem_ld_32x32(tq + (uint32_t)col0(half, c + 1), r[(c + 1) & 1]);
+                uint32_t packed[16];
+                pack_chunk(r[c & 1], bl[0][half * 4 + c], packed);
+                store_chunk(col0(half, c), packed);
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive(&acc_free[half]);
         }
-        // layer 3: Q = acc + b3 -> global fp32 [B][A]; column group 0 warps only (64 columns)
+        fence_proxy_async_smem();      // H1 complete: visible to the async proxy (layer-2 MMA, TMA store)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+            if (net == 0) {            // the backward pass needs the online network's activations
+                for (int b = 0; b < KH; b++) tma_store_2d(&tmH1, sH + b * FF_BOX, 64 * b, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            arrive(&h_ready);
+        }
+
+        // ---- layer 2 -> H2, which overwrites H1 in place.  Accumulator half 0 is drained into
+        // registers while the MMAs of half 1 still read H1; it is written out once they retire.
+        {
+            uint32_t hold[4][16];
+            uint32_t r[32];
+            mbar_wait(&acc_full[0], 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                tmem_ld_32x32(tq + (uint32_t)col0(0, c), r);
+                tmem_ld_wait();
+                pack_chunk(r, bl[1][c], hold[c]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive(&acc_free[0]);
+            // every layer-2 MMA has read H1 once acc_full[1] fires; the H1 TMA store must also have
+            // finished reading the tile
+            mbar_wait(&acc_full[1], 1);
+            tc_fence_after();
+            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            tmem_ld_32x32(tq + (uint32_t)col0(1, 0), r);
+#pragma unroll
+            for (int c = 0; c < 4; c++) store_chunk(col0(0, c), hold[c]);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (c) tmem_ld_32x32(tq + (uint32_t)col0(1, c), r);
+                tmem_ld_wait();
+                uint32_t packed[16];
+                pack_chunk(r, bl[1][4 + c], packed);
+                store_chunk(col0(1, c), packed);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive(&acc_free[1]);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+            if (net == 0) {
+                for (int b = 0; b < KH; b++) tma_store_2d(&tmH2, sH + b * FF_BOX, 64 * b, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            arrive(&h_ready);
+        }
+
+        // ---- layer 3: Q = acc + b3 -> fp32 [B][A] (A <= 32: one chunk).  Column group 0 warps stage
+        // the slab's rows in the (now idle) weight ring and copy them out coalesced: the rows of a
+        // slab are contiguous in Q.
         if (cg == 0) {
             mbar_wait(&acc_full[0], 0);          // third completion of acc_full[0]: parity 0 again
             tc_fence_after();
-            const float *bias = g.bias[net][2];
-            const int row = m0 + rt;
-#pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                tmem_ld_wait();
-                if (row < g.B) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (c0 + j < g.A) g.q[net][(size_t)row * g.A + c0 + j] = __uint_as_float(r[j]) + __ldg(bias + c0 + j);
-                }
-            }
+            uint32_t r[32];
+            tmem_ld_32x32(tq, r);
+            tmem_ld_wait();
             tc_fence_before();
+            float *sQ = reinterpret_cast<float *>(sW);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const float v = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, b3, j);
+                if (j < g.A) sQ[rt * g.A + j] = v;
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            const int rows = (g.B - m0 < BM) ? g.B - m0 : BM;
+            float *dst = g.q[net] + (size_t)m0 * g.A;
+            for (int i = et; i < rows * g.A; i += 128) dst[i] = sQ[i];
         }
         if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
