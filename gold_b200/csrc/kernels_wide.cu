@@ -1583,6 +1583,59 @@ void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const floa
 }
 const uint8_t *wide_done_ptr(WideState *w) { return w->bs[w->last_set].bdone; }
 
+
+// ---------------------------------------------------------------------------
+// Diagnostic: issue / completion rate of back-to-back tcgen05.mma (selftest modes 30, 31).
+// One thread issues 4*iters MMAs (M = 128, K = 16) on resident shared-memory operands.
+// Measured on B200: 139.4 cycles per MMA for N = 64, 128 and 256 alike, K- or MN-major B, one or
+// two accumulators: the instruction streams the 128 rows of A at one row per cycle, so only
+// N = 256 reaches the tensor peak and narrower tiles cost the same time for less work.
+// ---------------------------------------------------------------------------
+template <int N, bool B_MN>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int naccs, float *out)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc(&slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if (threadIdx.x == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, N, false, B_MN);
+        const uint32_t a = smem_u32(smem), b = smem_u32(smem + 16384);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++)
+                mma_bf16(tmem + ((i * 4 + kk) % naccs) * N, make_smem_desc(a + kk * 32, 16, 1024),
+                         B_MN ? make_smem_desc(b + kk * 2048, 8192, 1024) : make_smem_desc(b + kk * 32, 16, 1024), idesc, 1u);
+        }
+        const long long t1 = clock64();
+        mma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        out[blockIdx.x * 2] = float(t1 - t0) / (4.f * iters);
+        out[blockIdx.x * 2 + 1] = float(t2 - t0) / (4.f * iters);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+template <int N, bool B_MN>
+static cudaError_t run_mma_rate(int ctas, int iters, int naccs, float *dout)
+{
+    cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel<N, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 32768 + 1024);
+    if (e != cudaSuccess) return e;
+    mma_rate_kernel<N, B_MN><<<ctas, 128, 16384 + 32768 + 1024>>>(iters, naccs, dout);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------
 // stand-alone tcgen05 GEMM self-test (diagnostic ABI: goldq_selftest_umma)
 //   mode 0 (KK): C[M][N] = sum_k A[m][k] B[n][k]      A [M][K], B [N][K] bf16 (as uint16)
@@ -1594,6 +1647,28 @@ int wide_selftest_gemm(int mode, int M, int N, int K, int nsplit, const uint16_t
     if (!load_encode(err)) return -1;
     WCK(configure_all_gemms());
     if (nsplit < 1) nsplit = 1;
+    if (mode == 30 || mode == 31) {
+        // MMA rate probe: M/128 CTAs, N = MMA width, K = iterations, nsplit = accumulators cycled
+        // through; mode 30: B MN-major, 31: B K-major.  C[0] = issue cycles per MMA, C[1] = issue +
+        // completion cycles per MMA (CTA 0).
+        float *dout = nullptr;
+        const int ctas = M / 128;
+        if (ctas < 1 || K < 1) { err = "selftest: rate probe needs M >= 128, K >= 1"; return -1; }
+        if (!dmalloc(&dout, (size_t)ctas * 2, err)) return -1;
+        const int naccs = nsplit * N <= 512 ? nsplit : 512 / N;
+        cudaError_t e = cudaErrorInvalidValue;
+        if (mode == 30 && N == 256) e = run_mma_rate<256, true>(ctas, K, naccs, dout);
+        else if (mode == 30 && N == 128) e = run_mma_rate<128, true>(ctas, K, naccs, dout);
+        else if (mode == 30 && N == 64) e = run_mma_rate<64, true>(ctas, K, naccs, dout);
+        else if (mode == 31 && N == 256) e = run_mma_rate<256, false>(ctas, K, naccs, dout);
+        else if (mode == 31 && N == 128) e = run_mma_rate<128, false>(ctas, K, naccs, dout);
+        else if (mode == 31 && N == 64) e = run_mma_rate<64, false>(ctas, K, naccs, dout);
+        WCK(e);
+        WCK(cudaDeviceSynchronize());
+        WCK(cudaMemcpy(C, dout, 2 * sizeof(float), cudaMemcpyDeviceToHost));
+        cudaFree(dout);
+        return 0;
+    }
     __nv_bfloat16 *dA = nullptr, *dB = nullptr;
     float *dC = nullptr;
     size_t na = (size_t)M * K, nb = (size_t)N * K;
