@@ -27,7 +27,7 @@ SYMBOLS = [
     "goldq_replay_len", "goldq_replay_push_wait", "goldq_host_alloc", "goldq_host_free",
     "goldq_learn", "goldq_learn_device_indices", "goldq_learn_many", "goldq_sampler_indices", "goldq_sync_target",
     "goldq_last_loss", "goldq_predict", "goldq_greedy_action", "goldq_fit_batch",
-    "goldq_dp_unique_id", "goldq_dp_init", "goldq_sync", "goldq_stream", "goldq_launch_count",
+    "goldq_dp_unique_id", "goldq_dp_init", "goldq_dp_mode", "goldq_sync", "goldq_stream", "goldq_launch_count",
     "goldq_debug_enable", "goldq_debug_fetch", "goldq_timer_start", "goldq_timer_stop",
     "goldq_selftest_umma", "goldq_step_breakdown",
 ]
@@ -92,6 +92,7 @@ def lib():
         "goldq_fit_batch": (C.c_int, [vp, i64, fp, fp]),
         "goldq_dp_unique_id": (C.c_int, [up]),
         "goldq_dp_init": (C.c_int, [vp, up, C.c_int, C.c_int]),
+        "goldq_dp_mode": (C.c_int, [vp]),
         "goldq_sync": (C.c_int, [vp]),
         "goldq_stream": (vp, [vp]),
         "goldq_launch_count": (i64, [vp]),
@@ -284,6 +285,13 @@ class Handle:
     def dp_init(self, uid, rank, world):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._ck(self._L.goldq_dp_init(self._h, buf, rank, world))
+
+    def dp_mode(self):
+        """0: no group, 1: ncclAllReduce + update kernel, 2: fused peer-memory kernel."""
+        return int(self._L.goldq_dp_mode(self._h))
+
+    def last_error(self):
+        return self._L.goldq_last_error(self._h).decode()
 
     # plumbing ---------------------------------------------------------------
     def sync(self):

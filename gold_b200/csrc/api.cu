@@ -32,6 +32,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load(std::string &err)
@@ -46,6 +47,7 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
@@ -139,12 +141,25 @@ struct goldq {
     cudaGraphExec_t dp_graph = nullptr;          // phase 1 of one data-parallel wide step
     int64_t dp_graph_launches = 0;
 
+    // data-parallel tail over NVLink peer memory (wide path): see wide_p2p_apply
+    struct P2P {
+        bool on = false;
+        float *base = nullptr;                   // local exported allocation: [2][ppad] gradients + flags
+        void *peer_base[P2P_MAX_WORLD] = {};     // every rank's allocation as mapped here (own = base)
+        size_t ppad = 0;                         // floats per gradient copy (P + 1 rounded up to 4)
+        uint32_t epoch = 0;                      // data-parallel steps taken (host mirror)
+        int *err_host = nullptr, *err_dev = nullptr;
+        int graph_parity = 0;                    // epoch parity the cached graphs were captured at
+    } p2p;
+
     // goldq_step_breakdown
     cudaEvent_t *prof_evs = nullptr;
     int prof_n = 0;
 };
 
 namespace {
+
+void p2p_teardown(goldq_t *h);
 
 int fail(goldq_t *h, int code, const std::string &msg)
 {
@@ -364,6 +379,8 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     ws.theta = h->theta;
     ws.theta_t = h->theta_t;
     ws.flat = h->flat;
+    if (h->p2p.on && (phases & 1))      // the local gradient goes to this epoch's exported copy
+        ws.flat = h->p2p.base + (size_t)((h->p2p.epoch + 1) & 1) * h->p2p.ppad;
     ws.loss_out = h->loss;
     ws.sc = step_scalars(h, h->Bglobal);
     ws.fuse_update = h->world <= 1 ? 1 : 0;
@@ -384,7 +401,25 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
         if (n < 0) return fail(h, GOLDQ_ECUDA, err);
         h->launches += n;
     }
-    if (h->world > 1 && (phases & 2)) {
+    if (h->p2p.on && (phases & 2)) {
+        // fused all-reduce + Adam + shadow refresh over peer memory (graph-capturable: no NCCL call)
+        h->p2p.epoch += 1;
+        PeerSet ps{};
+        ps.world = h->world;
+        ps.rank = h->rank;
+        const size_t flags_off = 2 * h->p2p.ppad;
+        for (int r = 0; r < h->world; r++) {
+            float *b = (float *)h->p2p.peer_base[r];
+            ps.grad[r] = b + (size_t)(h->p2p.epoch & 1) * h->p2p.ppad;
+            ps.flags[r] = reinterpret_cast<unsigned int *>(b + flags_off);
+        }
+        ps.my_flags = ps.flags[h->rank];
+        ps.err = h->p2p.err_dev;
+        n = wide_p2p_apply(h->wide, ps, h->p2p.epoch, step, h->flat, h->theta, h->m, h->v, ws.adam, h->loss, h->st, err);
+        if (n < 0) return fail(h, GOLDQ_ECUDA, err);
+        h->launches += n;
+        if (h->prof_evs) cudaEventRecord(h->prof_evs[h->prof_n++], h->st);
+    } else if (h->world > 1 && (phases & 2)) {
         int rc = allreduce_flat(h);
         if (rc) return rc;
         if (h->prof_evs) cudaEventRecord(h->prof_evs[h->prof_n++], h->st);
@@ -427,7 +462,8 @@ int build_graph(goldq_t *h, int c)
     CK(h, cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
     int rc = GOLDQ_OK;
     static const bool no_prefetch = getenv("GOLDQ_NO_PREFETCH") != nullptr;
-    const bool prefetch = h->path == GOLDQ_PATH_WIDE && h->world <= 1 && !no_prefetch;
+    const bool prefetch = h->path == GOLDQ_PATH_WIDE && (h->world <= 1 || h->p2p.on) && !no_prefetch;
+    const uint32_t epoch0 = h->p2p.epoch;
     for (int i = 0; i < c && rc == GOLDQ_OK; i++) {
         if (prefetch) {   // batch i+1 is gathered on a side branch while step i computes
             h->pf_set = i & 1;
@@ -442,6 +478,8 @@ int build_graph(goldq_t *h, int c)
     h->graph_launches[c] = h->launches - launches0;
     h->iter = iter0;            // capturing executes nothing
     h->launches = launches0;
+    h->p2p.epoch = epoch0;
+    h->p2p.graph_parity = (int)(epoch0 & 1);
     if (rc != GOLDQ_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return fail(h, GOLDQ_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
     e = cudaGraphInstantiate(&h->graph_exec[c], graph, 0);
@@ -474,6 +512,89 @@ __global__ void replay_scatter_kernel(Replay rp, int D, int R, int64_t n, int64_
         rp.r[dst] = r[src];
         rp.done[dst] = done[src];
     }
+}
+
+}  // namespace
+
+namespace {
+
+void p2p_teardown(goldq_t *h)
+{
+    for (int r = 0; r < P2P_MAX_WORLD; r++)
+        if (h->p2p.peer_base[r] && h->p2p.peer_base[r] != (void *)h->p2p.base) cudaIpcCloseMemHandle(h->p2p.peer_base[r]);
+    if (h->p2p.base) cudaFree(h->p2p.base);
+    if (h->p2p.err_host) cudaFreeHost(h->p2p.err_host);
+    h->p2p = goldq::P2P{};
+}
+
+// Export this rank's gradient/flag allocation through CUDA IPC, map every peer's, and agree with
+// all ranks (NCCL min) that it worked everywhere; otherwise the group keeps the NCCL all-reduce.
+// Returns GOLDQ_OK whether or not peer memory ends up enabled; *why says what prevented it.
+int p2p_setup(goldq_t *h, std::string *why)
+{
+    goldq::P2P &pp = h->p2p;
+    const int W = h->world;
+    auto nccl_ok = [&](ncclResult_t r, const char *what) {
+        if (r == ncclSuccess) return true;
+        *why = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        return false;
+    };
+    int ok = 1;
+    if (W > P2P_MAX_WORLD || !g_nccl.AllGather) { ok = 0; *why = "world size above 8 or ncclAllGather missing"; }
+    pp.ppad = ((size_t)h->P + 1 + 3) & ~(size_t)3;
+    const size_t bytes = (2 * pp.ppad + 64) * sizeof(float);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok && (cudaMalloc((void **)&pp.base, bytes) != cudaSuccess || cudaMemsetAsync(pp.base, 0, bytes, h->st) != cudaSuccess ||
+               cudaIpcGetMemHandle(&mine, pp.base) != cudaSuccess)) {
+        ok = 0; *why = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(cudaGetLastError());
+    }
+    if (ok && (cudaHostAlloc((void **)&pp.err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+               cudaHostGetDevicePointer((void **)&pp.err_dev, pp.err_host, 0) != cudaSuccess)) {
+        ok = 0; *why = "mapped host flag unavailable";
+    }
+    if (pp.err_host) *pp.err_host = 0;
+    // all-gather of the 64-byte handles (a rank that failed above still takes part)
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    unsigned char *xchg = nullptr;
+    std::vector<cudaIpcMemHandle_t> all(P2P_MAX_WORLD);
+    if (cudaMalloc((void **)&xchg, 64 * (size_t)(W > P2P_MAX_WORLD ? W : P2P_MAX_WORLD)) != cudaSuccess)
+        return fail(h, GOLDQ_ECUDA, "cudaMalloc failed (IPC exchange)");
+    cudaMemcpyAsync(xchg + 64 * h->rank, &mine, 64, cudaMemcpyHostToDevice, h->st);
+    if (g_nccl.AllGather && W <= P2P_MAX_WORLD) {
+        if (!nccl_ok(g_nccl.AllGather(xchg + 64 * h->rank, xchg, 64, ncclChar, h->comm, h->st), "ncclAllGather")) ok = 0;
+        cudaMemcpyAsync(all.data(), xchg, 64 * (size_t)W, cudaMemcpyDeviceToHost, h->st);
+    }
+    cudaStreamSynchronize(h->st);
+    if (ok) {
+        for (int r = 0; r < W && ok; r++) {
+            if (r == h->rank) { pp.peer_base[r] = pp.base; continue; }
+            cudaError_t e = cudaIpcOpenMemHandle(&pp.peer_base[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                ok = 0; pp.peer_base[r] = nullptr;
+                *why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+                cudaGetLastError();
+            }
+        }
+    }
+    // unanimous or not at all (this all-reduce also orders every rank's memset before any peer's
+    // first flag store)
+    int *d_ok = reinterpret_cast<int *>(xchg);
+    cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->st);
+    int all_ok = 0;
+    if (nccl_ok(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->st), "ncclAllReduce")) {
+        cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+        cudaStreamSynchronize(h->st);
+    }
+    cudaFree(xchg);
+    if (!all_ok) {
+        if (why->empty()) *why = "a peer rank could not map the group's memory";
+        p2p_teardown(h);
+        return GOLDQ_OK;
+    }
+    pp.on = true;
+    pp.epoch = 0;
+    return GOLDQ_OK;
 }
 
 }  // namespace
@@ -649,6 +770,7 @@ void goldq_destroy(goldq_t *h)
         if (h->ev_steps[i]) cudaEventDestroy(h->ev_steps[i]);
     }
     if (h->d_steps) cudaFree(h->d_steps);
+    p2p_teardown(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->wide) wide_destroy(h->wide);
     void *ptrs[] = {h->theta, h->theta_t, h->m, h->v, h->flat, h->loss, h->d_idx, h->rp.s, h->rp.s2,
@@ -681,6 +803,8 @@ int goldq_sync(goldq_t *h)
     if (!h) return GOLDQ_EINVAL;
     CK(h, cudaSetDevice(h->dev));
     CK(h, cudaStreamSynchronize(h->st));
+    if (h->p2p.on && *(volatile int *)h->p2p.err_host)
+        return fail(h, GOLDQ_ENCCL, "data-parallel peer did not publish its gradient within 5 s");
     return GOLDQ_OK;
 }
 
@@ -838,7 +962,8 @@ int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
         int rc = ensure_generic(h, h->B);
         if (rc) return rc;
     }
-    if (h->graph_head != h->rp.head || h->graph_len != h->rp.len || h->graph_debug != h->debug) {
+    if (h->graph_head != h->rp.head || h->graph_len != h->rp.len || h->graph_debug != h->debug ||
+        (h->p2p.on && h->p2p.graph_parity != (int)(h->p2p.epoch & 1))) {   // gradient copies alternate by epoch parity
         drop_graphs(h);
         h->graph_head = h->rp.head;
         h->graph_len = h->rp.len;
@@ -848,7 +973,7 @@ int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
     // Data-parallel steps: an ncclAllReduce captured into a CUDA graph replays ~80 us slower per
     // step than the eager call (measured at N=2), so only the part of the step before the
     // all-reduce is replayed from a graph; the collective and the update are launched eagerly.
-    if (!no_graph && h->world > 1 && h->path == GOLDQ_PATH_WIDE) {
+    if (!no_graph && h->world > 1 && h->path == GOLDQ_PATH_WIDE && !h->p2p.on) {
         if (!h->dp_graph) {
             const int64_t iter0 = h->iter, launches0 = h->launches;
             cudaGraph_t graph = nullptr;
@@ -890,7 +1015,7 @@ int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
         }
         return GOLDQ_OK;
     }
-    if (no_graph || h->world > 1) {
+    if (no_graph || (h->world > 1 && !h->p2p.on)) {
         for (int i = 0; i < n; i++) {
             int rc = run_learn(h, nullptr, seed + (uint64_t)i);
             if (rc) return rc;
@@ -920,10 +1045,12 @@ int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
             h->h_steps[b][i].seed = seed + (uint64_t)i;
             h->h_steps[b][i].c1 = ac.c1;
             h->h_steps[b][i].c2 = ac.c2;
+            h->h_steps[b][i].epoch = h->p2p.epoch + 1 + (uint32_t)i;
         }
         CK(h, cudaMemcpyAsync(h->d_steps, h->h_steps[b], sizeof(StepDev) * c, cudaMemcpyHostToDevice, h->st));
         CK(h, cudaEventRecord(h->ev_steps[b], h->st));
         CK(h, cudaGraphLaunch(h->graph_exec[c], h->st));
+        if (h->p2p.on) h->p2p.epoch += (uint32_t)c;
         h->iter += c;
         h->launches += h->graph_launches[c];
         seed += (uint64_t)c;
@@ -953,7 +1080,8 @@ int goldq_step_breakdown(goldq_t *h, uint64_t seed, int32_t max_kernels, float *
         h->prof_evs = nullptr;
         if (names && names_bytes > 0)
             snprintf(names, names_bytes, "%s%s", wide_step_kernel_names(h->wide).c_str(),
-                     h->world > 1 ? "\nncclAllReduce(grad)\nAdam + bf16 shadow (K5)" : "");
+                     h->p2p.on ? "\nall-reduce + Adam + bf16 shadow over peer memory (K5p)"
+                                : (h->world > 1 ? "\nncclAllReduce(grad)\nAdam + bf16 shadow (K5)" : ""));
     } else {
         // single fused launch (narrow) or an unfused chain (generic): one interval for the step
         CK(h, cudaEventRecord(evs[0], h->st));
@@ -997,6 +1125,8 @@ int goldq_last_loss(goldq_t *h, float *out)
     CK(h, cudaSetDevice(h->dev));
     CK(h, cudaMemcpyAsync(out, h->loss, (size_t)h->R * 4, cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaStreamSynchronize(h->st));
+    if (h->p2p.on && *(volatile int *)h->p2p.err_host)
+        return fail(h, GOLDQ_ENCCL, "data-parallel peer did not publish its gradient within 5 s");
     return GOLDQ_OK;
 }
 
@@ -1124,7 +1254,22 @@ int goldq_dp_init(goldq_t *h, const uint8_t id[128], int rank, int world)
                                         (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
     h->rank = rank;
     h->world = world;
+    drop_graphs(h);
+    // wide path: the gradient all-reduce and the update run as one kernel over NVLink peer memory
+    // (GOLDQ_NO_P2P=1 keeps ncclAllReduce + a separate update kernel)
+    if (h->path == GOLDQ_PATH_WIDE && getenv("GOLDQ_NO_P2P") == nullptr) {
+        std::string why;
+        int rc = p2p_setup(h, &why);
+        if (rc) return rc;
+        if (!h->p2p.on) h->err = "peer-memory all-reduce unavailable, using NCCL: " + why;
+    }
     return GOLDQ_OK;
+}
+
+int goldq_dp_mode(const goldq_t *h)
+{
+    if (!h) return GOLDQ_EINVAL;
+    return h->world <= 1 ? 0 : (h->p2p.on ? 2 : 1);
 }
 
 int goldq_debug_enable(goldq_t *h, int on)

@@ -57,6 +57,8 @@ struct AdamConsts {
 struct StepDev {
     unsigned long long seed;
     float c1, c2;
+    unsigned int epoch;     // data-parallel step counter (peer-memory all-reduce handshake)
+    unsigned int pad_;
 };
 
 // Scalars of one learn step.

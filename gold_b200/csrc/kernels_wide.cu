@@ -1379,6 +1379,97 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
     return 1;
 }
 
+// ---------------------------------------------------------------------------
+// Fused gradient all-reduce + Adam over NVLink peer memory (data-parallel tail).
+//   1. block 0 stores this step's epoch into slot `rank` of every rank's flag array (the local
+//      gradient was completed by the previous kernel of this stream);
+//   2. every block waits until all `world` slots of the LOCAL flag array have reached the epoch;
+//   3. each thread loads its float4 group from every rank's gradient buffer (one-shot all-reduce:
+//      P2P loads over NVSwitch, all in flight together), adds them in rank order -- so every
+//      rank computes bit-identical sums -- and applies Adam and the bf16 shadow refresh locally.
+// Gradient buffers alternate between two copies by epoch parity: a rank can be at most one step
+// ahead of a peer (step e+1 cannot pass its own wait before the peer has published e+1, which it
+// does only after finishing e), so the copy being read is never the one being rewritten.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_volatile_f4(const float *p)
+{
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_volatile_f1(const float *p)
+{
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+wide_p2p_apply_kernel(Dims d, Offsets o, PeerSet ps, unsigned int epoch, const StepDev *__restrict__ step,
+                      float *__restrict__ flat_out, float *__restrict__ theta, float *__restrict__ m,
+                      float *__restrict__ v, AdamConsts ac, ShadowPtrs sp, float *__restrict__ loss_out)
+{
+    if (step) { ac.c1 = step->c1; ac.c2 = step->c2; epoch = step->epoch; }
+    if (blockIdx.x == 0 && (int)threadIdx.x < ps.world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ps.flags[threadIdx.x] + ps.rank), "r"(epoch) : "memory");
+    }
+    if ((int)threadIdx.x < ps.world) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            unsigned int f;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(ps.my_flags + threadIdx.x) : "memory");
+            if ((int)(f - epoch) >= 0) break;
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 5000000000ull) { *ps.err = 1; break; }     // 5 s: a peer is gone; do not hang the GPU
+        }
+    }
+    __syncthreads();
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i > o.P) return;
+    if (i + 3 < o.P && (i + 3 < o.b1 || (i >= o.b1 && i + 3 < o.w2) || (i >= o.w2 && i + 3 < o.b2) ||
+                        (i >= o.b2 && i + 3 < o.w3) || (i >= o.w3 && i + 3 < o.b3))) {
+        float4 t[P2P_MAX_WORLD];
+#pragma unroll
+        for (int r = 0; r < P2P_MAX_WORLD; r++)
+            t[r] = r < ps.world ? ld_volatile_f4(ps.grad[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 w4 = *reinterpret_cast<const float4 *>(theta + i);
+        float4 m4 = *reinterpret_cast<const float4 *>(m + i);
+        float4 v4 = *reinterpret_cast<const float4 *>(v + i);
+        float4 g = t[0];
+#pragma unroll
+        for (int r = 1; r < P2P_MAX_WORLD; r++)
+            if (r < ps.world) g = f4add(g, t[r]);
+        *reinterpret_cast<float4 *>(flat_out + i) = g;
+        finish4<true>(d, o, i, g, nullptr, theta, m, v, w4, m4, v4, ac, sp);
+    } else {
+        for (int e = i; e < i + 4 && e <= o.P; e++) {
+            float g = ld_volatile_f1(ps.grad[0] + e);
+            for (int r = 1; r < ps.world; r++) g += ld_volatile_f1(ps.grad[r] + e);
+            flat_out[e] = g;
+            if (e == o.P) { *loss_out = g; break; }
+            float wi = theta[e], mi = m[e], vi = v[e];
+            adam_update_w(wi, g, mi, vi, ac);
+            theta[e] = wi; m[e] = mi; v[e] = vi;
+            shadow_store(d, o, sp, e, wi);
+        }
+    }
+}
+
+int wide_p2p_apply(WideState *w, const PeerSet &ps, unsigned int epoch, const StepDev *step, float *flat_out,
+                   float *theta, float *m, float *v, AdamConsts ac, float *loss_out, cudaStream_t st,
+                   std::string &err)
+{
+    const int groups = (w->o.P + 1 + 3) / 4;
+    wide_p2p_apply_kernel<<<(groups + 255) / 256, 256, 0, st>>>(w->d, w->o, ps, epoch, step, flat_out, theta, m, v, ac,
+                                                                shadow_ptrs(w, 0), loss_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("wide_p2p_apply_kernel: ") + cudaGetErrorString(e); return -1; }
+    return 1;
+}
+
 int wide_sync_target(WideState *w, cudaStream_t st, std::string &err)
 {
     // target <- online: copy the bf16 shadows (W3^T is online-only)

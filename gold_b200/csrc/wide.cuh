@@ -42,6 +42,21 @@ int wide_sync_target(WideState *w, cudaStream_t st, std::string &err);
 int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, float *v, AdamConsts ac,
                       const StepDev *step, cudaStream_t st, std::string &err);
 int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err);
+
+// Data-parallel tail over NVLink peer memory (one process per GPU, buffers opened through CUDA
+// IPC): every rank publishes its local gradient, then sums all ranks' gradients straight out of
+// their memory in rank order and applies Adam + the bf16 shadow refresh, in ONE kernel.
+constexpr int P2P_MAX_WORLD = 8;
+struct PeerSet {
+    int world, rank;
+    const float *grad[P2P_MAX_WORLD];      // this step's gradient buffer of every rank ([P+1], loss last)
+    unsigned int *flags[P2P_MAX_WORLD];    // every rank's flag array; slot r is written by rank r
+    unsigned int *my_flags;                // = flags[rank], polled locally
+    int *err;                              // mapped host int: set to 1 when a peer never showed up
+};
+int wide_p2p_apply(WideState *w, const PeerSet &ps, unsigned int epoch, const StepDev *step, float *flat_out,
+                   float *theta, float *m, float *v, AdamConsts ac, float *loss_out, cudaStream_t st,
+                   std::string &err);
 std::string wide_step_kernel_names(WideState *w);
 void wide_set_debug(WideState *w, bool on);
 void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const float **td);
