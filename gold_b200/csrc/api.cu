@@ -143,8 +143,8 @@ struct goldq {
 
     // data-parallel tail over NVLink peer memory (wide path): see wide_p2p_apply
     struct P2P {
-        bool on = false;
-        float *base = nullptr;                   // local exported allocation: [2][ppad] gradients + flags
+        bool on = false, two_shot = false;
+        float *base = nullptr;                   // local exported allocation: [2][ppad] gradients, [ppad] sum, flags
         void *peer_base[P2P_MAX_WORLD] = {};     // every rank's allocation as mapped here (own = base)
         size_t ppad = 0;                         // floats per gradient copy (P + 1 rounded up to 4)
         uint32_t epoch = 0;                      // data-parallel steps taken (host mirror)
@@ -407,13 +407,19 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
         PeerSet ps{};
         ps.world = h->world;
         ps.rank = h->rank;
-        const size_t flags_off = 2 * h->p2p.ppad;
+        // exported allocation: [grad copy 0][grad copy 1][sum][flags 16][flags2 16][ticket ...]
+        const size_t flags_off = 3 * h->p2p.ppad;
         for (int r = 0; r < h->world; r++) {
             float *b = (float *)h->p2p.peer_base[r];
             ps.grad[r] = b + (size_t)(h->p2p.epoch & 1) * h->p2p.ppad;
+            ps.sum[r] = b + 2 * h->p2p.ppad;
             ps.flags[r] = reinterpret_cast<unsigned int *>(b + flags_off);
+            ps.flags2[r] = ps.flags[r] + 16;
         }
         ps.my_flags = ps.flags[h->rank];
+        ps.my_flags2 = ps.flags2[h->rank];
+        ps.ticket = ps.my_flags + 32;
+        ps.two_shot = h->p2p.two_shot ? 1 : 0;
         ps.err = h->p2p.err_dev;
         n = wide_p2p_apply(h->wide, ps, h->p2p.epoch, step, h->flat, h->theta, h->m, h->v, ws.adam, h->loss, h->st, err);
         if (n < 0) return fail(h, GOLDQ_ECUDA, err);
@@ -542,7 +548,10 @@ int p2p_setup(goldq_t *h, std::string *why)
     int ok = 1;
     if (W > P2P_MAX_WORLD || !g_nccl.AllGather) { ok = 0; *why = "world size above 8 or ncclAllGather missing"; }
     pp.ppad = ((size_t)h->P + 1 + 3) & ~(size_t)3;
-    const size_t bytes = (2 * pp.ppad + 64) * sizeof(float);
+    const size_t bytes = (3 * pp.ppad + 64) * sizeof(float);
+    // one-shot pull up to 2 ranks, two-shot (reduce-scatter + all-gather) above; GOLDQ_P2P_SHOTS=1|2 forces
+    pp.two_shot = W > 2;
+    if (const char *e = getenv("GOLDQ_P2P_SHOTS")) pp.two_shot = atoi(e) == 2;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
     if (ok && (cudaMalloc((void **)&pp.base, bytes) != cudaSuccess || cudaMemsetAsync(pp.base, 0, bytes, h->st) != cudaSuccess ||

@@ -1387,6 +1387,10 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
 //   3. each thread loads its float4 group from every rank's gradient buffer (one-shot all-reduce:
 //      P2P loads over NVSwitch, all in flight together), adds them in rank order -- so every
 //      rank computes bit-identical sums -- and applies Adam and the bf16 shadow refresh locally.
+// With more than two ranks the one-shot pull (every rank reads all of every peer's gradient) is
+// replaced by a two-shot: rank r sums the r-th range of blocks only and stores the sums into every
+// rank's `sum` buffer; a second flag round says the range has landed, then Adam runs on the local
+// copy.  Same arithmetic (rank-order sums), 2/world of the NVLink bytes.
 // Gradient buffers alternate between two copies by epoch parity: a rank can be at most one step
 // ahead of a peer (step e+1 cannot pass its own wait before the peer has published e+1, which it
 // does only after finishing e), so the copy being read is never the one being rewritten.
@@ -1404,6 +1408,23 @@ __device__ __forceinline__ float ld_volatile_f1(const float *p)
     return v;
 }
 
+__device__ __forceinline__ void p2p_wait_flags(const unsigned int *flags, int world, unsigned int epoch, int *err)
+{
+    if ((int)threadIdx.x < world) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            unsigned int f;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(flags + threadIdx.x) : "memory");
+            if ((int)(f - epoch) >= 0) break;
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 5000000000ull) { *err = 1; break; }     // 5 s: a peer is gone; do not hang the GPU
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256)
 wide_p2p_apply_kernel(Dims d, Offsets o, PeerSet ps, unsigned int epoch, const StepDev *__restrict__ step,
                       float *__restrict__ flat_out, float *__restrict__ theta, float *__restrict__ m,
@@ -1414,40 +1435,67 @@ wide_p2p_apply_kernel(Dims d, Offsets o, PeerSet ps, unsigned int epoch, const S
         __threadfence_system();
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ps.flags[threadIdx.x] + ps.rank), "r"(epoch) : "memory");
     }
-    if ((int)threadIdx.x < ps.world) {
-        unsigned long long t0;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (;;) {
-            unsigned int f;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(ps.my_flags + threadIdx.x) : "memory");
-            if ((int)(f - epoch) >= 0) break;
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 5000000000ull) { *ps.err = 1; break; }     // 5 s: a peer is gone; do not hang the GPU
-        }
-    }
-    __syncthreads();
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const float *src[P2P_MAX_WORLD];
+    int nsrc = ps.world;
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_WORLD; r++) src[r] = ps.grad[r];
+    if (ps.two_shot) {
+        // ---- reduce-scatter + all-gather of the gradient: this rank owns a contiguous range of blocks
+        const int nb = gridDim.x, lo = (int)((long long)nb * ps.rank / ps.world), hi = (int)((long long)nb * (ps.rank + 1) / ps.world);
+        if ((int)blockIdx.x >= lo && (int)blockIdx.x < hi) {
+            p2p_wait_flags(ps.my_flags, ps.world, epoch, ps.err);
+            if (i <= o.P) {
+                // (the buffers are padded to a multiple of 4 floats, so the float4 holding the loss is whole)
+                float4 t[P2P_MAX_WORLD];
+#pragma unroll
+                for (int r = 0; r < P2P_MAX_WORLD; r++)
+                    t[r] = r < ps.world ? ld_volatile_f4(ps.grad[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 g = t[0];
+#pragma unroll
+                for (int r = 1; r < P2P_MAX_WORLD; r++)
+                    if (r < ps.world) g = f4add(g, t[r]);
+#pragma unroll
+                for (int r = 0; r < P2P_MAX_WORLD; r++)
+                    if (r < ps.world) *reinterpret_cast<float4 *>(ps.sum[r] + i) = g;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned int done = atomicAdd(ps.ticket, 1u) + 1u;
+                if (done % (unsigned int)(hi - lo) == 0u) {       // last block of my range: tell everyone
+                    __threadfence_system();
+                    for (int r = 0; r < ps.world; r++)
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ps.flags2[r] + ps.rank), "r"(epoch) : "memory");
+                }
+            }
+        }
+        p2p_wait_flags(ps.my_flags2, ps.world, epoch, ps.err);
+        src[0] = ps.sum[ps.rank];         // the full sum now sits in local memory
+        nsrc = 1;
+    } else {
+        p2p_wait_flags(ps.my_flags, ps.world, epoch, ps.err);
+    }
     if (i > o.P) return;
     if (i + 3 < o.P && (i + 3 < o.b1 || (i >= o.b1 && i + 3 < o.w2) || (i >= o.w2 && i + 3 < o.b2) ||
                         (i >= o.b2 && i + 3 < o.w3) || (i >= o.w3 && i + 3 < o.b3))) {
         float4 t[P2P_MAX_WORLD];
 #pragma unroll
         for (int r = 0; r < P2P_MAX_WORLD; r++)
-            t[r] = r < ps.world ? ld_volatile_f4(ps.grad[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            t[r] = r < nsrc ? ld_volatile_f4(src[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 w4 = *reinterpret_cast<const float4 *>(theta + i);
         float4 m4 = *reinterpret_cast<const float4 *>(m + i);
         float4 v4 = *reinterpret_cast<const float4 *>(v + i);
         float4 g = t[0];
 #pragma unroll
         for (int r = 1; r < P2P_MAX_WORLD; r++)
-            if (r < ps.world) g = f4add(g, t[r]);
+            if (r < nsrc) g = f4add(g, t[r]);
         *reinterpret_cast<float4 *>(flat_out + i) = g;
         finish4<true>(d, o, i, g, nullptr, theta, m, v, w4, m4, v4, ac, sp);
     } else {
         for (int e = i; e < i + 4 && e <= o.P; e++) {
-            float g = ld_volatile_f1(ps.grad[0] + e);
-            for (int r = 1; r < ps.world; r++) g += ld_volatile_f1(ps.grad[r] + e);
+            float g = ld_volatile_f1(src[0] + e);
+            for (int r = 1; r < nsrc; r++) g += ld_volatile_f1(src[r] + e);
             flat_out[e] = g;
             if (e == o.P) { *loss_out = g; break; }
             float wi = theta[e], mi = m[e], vi = v[e];
@@ -1462,9 +1510,11 @@ int wide_p2p_apply(WideState *w, const PeerSet &ps, unsigned int epoch, const St
                    float *theta, float *m, float *v, AdamConsts ac, float *loss_out, cudaStream_t st,
                    std::string &err)
 {
-    const int groups = (w->o.P + 1 + 3) / 4;
-    wide_p2p_apply_kernel<<<(groups + 255) / 256, 256, 0, st>>>(w->d, w->o, ps, epoch, step, flat_out, theta, m, v, ac,
-                                                                shadow_ptrs(w, 0), loss_out);
+    const int groups = (w->o.P + 1 + 3) / 4, blocks = (groups + 255) / 256;
+    PeerSet p = ps;
+    if (blocks < p.world) p.two_shot = 0;      // every rank must own at least one block of the range split
+    wide_p2p_apply_kernel<<<blocks, 256, 0, st>>>(w->d, w->o, p, epoch, step, flat_out, theta, m, v, ac,
+                                                  shadow_ptrs(w, 0), loss_out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("wide_p2p_apply_kernel: ") + cudaGetErrorString(e); return -1; }
     return 1;

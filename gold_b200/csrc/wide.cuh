@@ -53,6 +53,13 @@ struct PeerSet {
     unsigned int *flags[P2P_MAX_WORLD];    // every rank's flag array; slot r is written by rank r
     unsigned int *my_flags;                // = flags[rank], polled locally
     int *err;                              // mapped host int: set to 1 when a peer never showed up
+    // two-shot variant (world > 2): rank r sums block-range r of the gradient and stores the sums
+    // into every rank's `sum` buffer; flags2 says "rank r's range has landed everywhere"
+    int two_shot;
+    float *sum[P2P_MAX_WORLD];
+    unsigned int *flags2[P2P_MAX_WORLD];
+    unsigned int *my_flags2;
+    unsigned int *ticket;                  // local counter: blocks of my range that have delivered
 };
 int wide_p2p_apply(WideState *w, const PeerSet &ps, unsigned int epoch, const StepDev *step, float *flat_out,
                    float *theta, float *m, float *v, AdamConsts ac, float *loss_out, cudaStream_t st,
