@@ -366,8 +366,12 @@ def run_own(args):
         top = max(cand, key=lambda i: kms[i])
         ach = kflops[labels[top]] / (kms[top] * 1e-3) / 1e12
         peak = pk["bf16_tflops"]      # burst figure: this kernel is timed alone, between events
+        # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
+        # (dram__bytes_read.sum + dram__bytes_write.sum); only valid for the configuration profiled
+        traffic = NCU_TRAFFIC.get((labels[top], tuple(dims), B))
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "kernel": labels[top], "kernel_us": float(kms[top]) * 1e3,
+                "traffic": traffic, "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
+                "kernel": labels[top], "kernel_us": float(kms[top]) * 1e3,
                 "flops_per_launch": kflops[labels[top]],
                 "peak_source": pk["source"] + " bf16_tflops (burst: kernel timed alone between CUDA events)",
                 "step": {"flops_per_step": flops_step, "achieved_tflops": flops_step / step_s / 1e12,
@@ -414,6 +418,10 @@ def run_own(args):
 
 
 _REAL_STDOUT = None
+
+# ff_forward_kernel, wide config, B=8192: 5.739 MB read + 0.024 MB written per launch
+NCU_TRAFFIC = {("fused forward L1-L3 online+target (tcgen05)", (128, 512, 512, 18), 8192): 5739264 + 24320}
+NCU_TRAFFIC_SOURCE = "profiles/r01_wide_v3_ncu_full_raw.csv"
 
 
 def emit(line):
