@@ -143,13 +143,12 @@ struct goldq {
 
     // data-parallel tail over NVLink peer memory (wide path): see wide_p2p_apply
     struct P2P {
-        bool on = false, two_shot = false;
-        float *base = nullptr;                   // local exported allocation: [2][ppad] gradients, [ppad] sum, flags
+        bool on = false;
+        int chunk_f = 0;                         // floats owned per rank
+        float *base = nullptr;                   // local exported allocation: {value, epoch} windows
         void *peer_base[P2P_MAX_WORLD] = {};     // every rank's allocation as mapped here (own = base)
-        size_t ppad = 0;                         // floats per gradient copy (P + 1 rounded up to 4)
         uint32_t epoch = 0;                      // data-parallel steps taken (host mirror)
         int *err_host = nullptr, *err_dev = nullptr;
-        int graph_parity = 0;                    // epoch parity the cached graphs were captured at
     } p2p;
 
     // goldq_step_breakdown
@@ -379,8 +378,6 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     ws.theta = h->theta;
     ws.theta_t = h->theta_t;
     ws.flat = h->flat;
-    if (h->p2p.on && (phases & 1))      // the local gradient goes to this epoch's exported copy
-        ws.flat = h->p2p.base + (size_t)((h->p2p.epoch + 1) & 1) * h->p2p.ppad;
     ws.loss_out = h->loss;
     ws.sc = step_scalars(h, h->Bglobal);
     ws.fuse_update = h->world <= 1 ? 1 : 0;
@@ -396,6 +393,22 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     ws.next_step = h->pf_next;
     std::string err;
     int n = 0;
+    PeerSet ps{};
+    if (h->p2p.on) {
+        // every float of the gradient travels as a {value, epoch} word: pushed to its owner by the
+        // slice-reduction kernel (phase 1), summed and redistributed by wide_p2p_apply (phase 2)
+        if (phases & 1) h->p2p.epoch += 1;
+        ps.world = h->world;
+        ps.rank = h->rank;
+        ps.chunk_f = h->p2p.chunk_f;
+        for (int r = 0; r < h->world; r++) {
+            ps.rs[r] = (unsigned long long *)h->p2p.peer_base[r];
+            ps.ag[r] = ps.rs[r] + (size_t)2 * h->world * h->p2p.chunk_f;
+        }
+        ps.err = h->p2p.err_dev;
+        ws.push = &ps;
+        ws.epoch = h->p2p.epoch;
+    }
     if (phases & 1) {
         n = wide_step(h->wide, ws, h->st, err);
         if (n < 0) return fail(h, GOLDQ_ECUDA, err);
@@ -403,24 +416,6 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     }
     if (h->p2p.on && (phases & 2)) {
         // fused all-reduce + Adam + shadow refresh over peer memory (graph-capturable: no NCCL call)
-        h->p2p.epoch += 1;
-        PeerSet ps{};
-        ps.world = h->world;
-        ps.rank = h->rank;
-        // exported allocation: [grad copy 0][grad copy 1][sum][flags 16][flags2 16][ticket ...]
-        const size_t flags_off = 3 * h->p2p.ppad;
-        for (int r = 0; r < h->world; r++) {
-            float *b = (float *)h->p2p.peer_base[r];
-            ps.grad[r] = b + (size_t)(h->p2p.epoch & 1) * h->p2p.ppad;
-            ps.sum[r] = b + 2 * h->p2p.ppad;
-            ps.flags[r] = reinterpret_cast<unsigned int *>(b + flags_off);
-            ps.flags2[r] = ps.flags[r] + 16;
-        }
-        ps.my_flags = ps.flags[h->rank];
-        ps.my_flags2 = ps.flags2[h->rank];
-        ps.ticket = ps.my_flags + 32;
-        ps.two_shot = h->p2p.two_shot ? 1 : 0;
-        ps.err = h->p2p.err_dev;
         n = wide_p2p_apply(h->wide, ps, h->p2p.epoch, step, h->flat, h->theta, h->m, h->v, ws.adam, h->loss, h->st, err);
         if (n < 0) return fail(h, GOLDQ_ECUDA, err);
         h->launches += n;
@@ -485,7 +480,6 @@ int build_graph(goldq_t *h, int c)
     h->iter = iter0;            // capturing executes nothing
     h->launches = launches0;
     h->p2p.epoch = epoch0;
-    h->p2p.graph_parity = (int)(epoch0 & 1);
     if (rc != GOLDQ_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return fail(h, GOLDQ_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
     e = cudaGraphInstantiate(&h->graph_exec[c], graph, 0);
@@ -547,11 +541,10 @@ int p2p_setup(goldq_t *h, std::string *why)
     };
     int ok = 1;
     if (W > P2P_MAX_WORLD || !g_nccl.AllGather) { ok = 0; *why = "world size above 8 or ncclAllGather missing"; }
-    pp.ppad = ((size_t)h->P + 1 + 3) & ~(size_t)3;
-    const size_t bytes = (3 * pp.ppad + 64) * sizeof(float);
-    // one-shot pull up to 2 ranks, two-shot (reduce-scatter + all-gather) above; GOLDQ_P2P_SHOTS=1|2 forces
-    pp.two_shot = W > 2;
-    if (const char *e = getenv("GOLDQ_P2P_SHOTS")) pp.two_shot = atoi(e) == 2;
+    // exported allocation: reduce-scatter windows [2][W][chunk_f] + all-gather windows [2][W * chunk_f],
+    // 8-byte {value, epoch} words, zeroed (epochs start at 1)
+    pp.chunk_f = wide_p2p_chunk_floats(h->wide, W > 0 ? W : 1);
+    const size_t bytes = (size_t)4 * W * pp.chunk_f * sizeof(unsigned long long);
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
     if (ok && (cudaMalloc((void **)&pp.base, bytes) != cudaSuccess || cudaMemsetAsync(pp.base, 0, bytes, h->st) != cudaSuccess ||
@@ -971,8 +964,7 @@ int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
         int rc = ensure_generic(h, h->B);
         if (rc) return rc;
     }
-    if (h->graph_head != h->rp.head || h->graph_len != h->rp.len || h->graph_debug != h->debug ||
-        (h->p2p.on && h->p2p.graph_parity != (int)(h->p2p.epoch & 1))) {   // gradient copies alternate by epoch parity
+    if (h->graph_head != h->rp.head || h->graph_len != h->rp.len || h->graph_debug != h->debug) {
         drop_graphs(h);
         h->graph_head = h->rp.head;
         h->graph_len = h->rp.len;

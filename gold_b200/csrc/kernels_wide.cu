@@ -1005,6 +1005,40 @@ struct UpdatePlan {
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
+// ---- {value, epoch} words (data-parallel exchange, see PeerSet in wide.cuh) ---------------------
+__device__ __forceinline__ void ll_store(unsigned long long *p, float val, unsigned int epoch)
+{
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(val)), "r"(epoch) : "memory");
+}
+// two adjacent words in one 16-byte access (each 8-byte half stays atomic; halves carry their own tag)
+__device__ __forceinline__ void ll_store2(unsigned long long *p, float v0, float v1, unsigned int epoch)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(v0)), "r"(epoch),
+                 "r"(__float_as_uint(v1)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load2(const unsigned long long *p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// local gradient element e of this rank -> the receive window of the rank that owns e
+__device__ __forceinline__ void ll_push(const PeerSet &L, unsigned int epoch, int e, float val)
+{
+    const int owner = e / L.chunk_f;
+    unsigned long long *dst = L.rs[owner] + ((size_t)(epoch & 1u) * L.world + L.rank) * L.chunk_f + (e - owner * L.chunk_f);
+    ll_store(dst, val, epoch);
+}
+
+// a whole float4 group (i multiple of 4: one owner, 32-byte aligned destination)
+__device__ __forceinline__ void ll_push4(const PeerSet &L, unsigned int epoch, int i, float4 g)
+{
+    const int owner = i / L.chunk_f;
+    unsigned long long *dst = L.rs[owner] + ((size_t)(epoch & 1u) * L.world + L.rank) * L.chunk_f + (i - owner * L.chunk_f);
+    ll_store2(dst, g.x, g.y, epoch);
+    ll_store2(dst + 2, g.z, g.w, epoch);
+}
+
 template <bool FUSE>
 __device__ __forceinline__ void finish4(const Dims &d, const Offsets &o, int i, float4 g, float *flat, float *theta,
                                         float *m, float *v, float4 w4, float4 m4, float4 v4, const AdamConsts &ac,
@@ -1036,12 +1070,16 @@ template <bool FUSE>
 __global__ void __launch_bounds__(128)
 wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count, float *__restrict__ flat,
                    float *__restrict__ theta, float *__restrict__ m, float *__restrict__ v, AdamConsts ac,
-                   const StepDev *__restrict__ step, ShadowPtrs sp, float *__restrict__ loss_out)
+                   const StepDev *__restrict__ step, ShadowPtrs sp, float *__restrict__ loss_out, PeerSet push,
+                   unsigned int epoch)
 {
+    // push.world > 0 (only with FUSE == false): the reduced local gradient goes to its owners' windows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_launch_dependents();
     pdl_wait();
     if (FUSE && step) { ac.c1 = step->c1; ac.c2 = step->c2; }
+    if (step) epoch = step->epoch;
+    const bool do_push = !FUSE && push.world > 0;
     if ((int)blockIdx.x < pl.blocksA) {
         // ---- A: weights ------------------------------------------------------------
         const int gidx = blockIdx.x * 128 + threadIdx.x;
@@ -1069,7 +1107,11 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
 #pragma unroll
             for (int u = 0; u < 8; u++) g = f4add(g, t[u]);
         }
-        finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
+        if (do_push) {
+            ll_push4(push, epoch, i, g);
+        } else {
+            finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
+        }
     } else if ((int)blockIdx.x < pl.blocksA + pl.blocksB) {
         // ---- B: biases of the hidden layers, warp per float4 group -------------------
         const int gidx = (blockIdx.x - pl.blocksA) * 4 + warp;
@@ -1104,7 +1146,11 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
                 m4 = *reinterpret_cast<const float4 *>(m + i);
                 v4 = *reinterpret_cast<const float4 *>(v + i);
             }
-            finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
+            if (do_push) {
+                ll_push4(push, epoch, i, g);
+            } else {
+                finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
+            }
         }
     } else {
         // ---- C: b3 and the loss, warp per scalar ---------------------------------------
@@ -1121,7 +1167,8 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
                 g = __fdiv_rn(g, count);
                 if (loss_out) *loss_out = g;
             }
-            flat[i] = g;
+            if (do_push) ll_push(push, epoch, i, g);
+            else flat[i] = g;
             if (FUSE && i < o.P) {
                 float wi = theta[i], mi = m[i], vi = v[i];
                 adam_update_w(wi, g, mi, vi, ac);
@@ -1380,122 +1427,100 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
 }
 
 // ---------------------------------------------------------------------------
-// Fused gradient all-reduce + Adam over NVLink peer memory (data-parallel tail).
-//   1. block 0 stores this step's epoch into slot `rank` of every rank's flag array (the local
-//      gradient was completed by the previous kernel of this stream);
-//   2. every block waits until all `world` slots of the LOCAL flag array have reached the epoch;
-//   3. each thread loads its float4 group from every rank's gradient buffer (one-shot all-reduce:
-//      P2P loads over NVSwitch, all in flight together), adds them in rank order -- so every
-//      rank computes bit-identical sums -- and applies Adam and the bf16 shadow refresh locally.
-// With more than two ranks the one-shot pull (every rank reads all of every peer's gradient) is
-// replaced by a two-shot: rank r sums the r-th range of blocks only and stores the sums into every
-// rank's `sum` buffer; a second flag round says the range has landed, then Adam runs on the local
-// copy.  Same arithmetic (rank-order sums), 2/world of the NVLink bytes.
-// Gradient buffers alternate between two copies by epoch parity: a rank can be at most one step
-// ahead of a peer (step e+1 cannot pass its own wait before the peer has published e+1, which it
-// does only after finishing e), so the copy being read is never the one being rewritten.
+// Fused gradient all-reduce + Adam over NVLink peer memory (data-parallel tail; protocol in
+// wide.cuh at PeerSet).  One thread per float4 group of the flat vector [P + 1]:
+//   reduce  (threads whose group this rank owns) wait for the `world` pushed copies of each element,
+//           add them in rank order, write {sum, epoch} into every rank's all-gather window;
+//   apply   (all threads) wait for their group's sums in the local window, then Adam + shadow.
+// Blocks never wait on blocks of the same grid that might not be resident: the words an apply
+// thread waits for are produced by owner threads that wait only on pushes of the previous kernel.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float4 ld_volatile_f4(const float *p)
-{
-    float4 v;
-    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ld_volatile_f1(const float *p)
-{
-    float v;
-    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-
-__device__ __forceinline__ void p2p_wait_flags(const unsigned int *flags, int world, unsigned int epoch, int *err)
-{
-    if ((int)threadIdx.x < world) {
-        unsigned long long t0;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (;;) {
-            unsigned int f;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(flags + threadIdx.x) : "memory");
-            if ((int)(f - epoch) >= 0) break;
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 5000000000ull) { *err = 1; break; }     // 5 s: a peer is gone; do not hang the GPU
-        }
-    }
-    __syncthreads();
-}
-
 __global__ void __launch_bounds__(256)
 wide_p2p_apply_kernel(Dims d, Offsets o, PeerSet ps, unsigned int epoch, const StepDev *__restrict__ step,
                       float *__restrict__ flat_out, float *__restrict__ theta, float *__restrict__ m,
                       float *__restrict__ v, AdamConsts ac, ShadowPtrs sp, float *__restrict__ loss_out)
 {
     if (step) { ac.c1 = step->c1; ac.c2 = step->c2; epoch = step->epoch; }
-    if (blockIdx.x == 0 && (int)threadIdx.x < ps.world) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ps.flags[threadIdx.x] + ps.rank), "r"(epoch) : "memory");
-    }
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const float *src[P2P_MAX_WORLD];
-    int nsrc = ps.world;
+    if (i > o.P) return;
+    const size_t par = epoch & 1u;
+    const int nvalid = (o.P + 1 - i) < 4 ? (o.P + 1 - i) : 4;      // elements past the loss do not exist
+    const int lo = ps.rank * ps.chunk_f;
+    unsigned long long *my_ag = ps.ag[ps.rank] + par * (size_t)ps.world * ps.chunk_f;
+    // elements that do not exist (past the loss, last group only) count as arrived
+    const unsigned int need0 = nvalid > 0, need1 = nvalid > 1, need2 = nvalid > 2, need3 = nvalid > 3;
+    unsigned long long t0 = 0;
+    if (i >= lo && i < lo + ps.chunk_f) {
+        // ---- reduce: this rank owns the group.  All copies are polled together (independent loads).
+        const unsigned long long *my_rs = ps.rs[ps.rank] + par * (size_t)ps.world * ps.chunk_f + (i - lo);
+        uint4 a[P2P_MAX_WORLD], b[P2P_MAX_WORLD];
+        for (;;) {
+            bool all = true;
 #pragma unroll
-    for (int r = 0; r < P2P_MAX_WORLD; r++) src[r] = ps.grad[r];
-    if (ps.two_shot) {
-        // ---- reduce-scatter + all-gather of the gradient: this rank owns a contiguous range of blocks
-        const int nb = gridDim.x, lo = (int)((long long)nb * ps.rank / ps.world), hi = (int)((long long)nb * (ps.rank + 1) / ps.world);
-        if ((int)blockIdx.x >= lo && (int)blockIdx.x < hi) {
-            p2p_wait_flags(ps.my_flags, ps.world, epoch, ps.err);
-            if (i <= o.P) {
-                // (the buffers are padded to a multiple of 4 floats, so the float4 holding the loss is whole)
-                float4 t[P2P_MAX_WORLD];
-#pragma unroll
-                for (int r = 0; r < P2P_MAX_WORLD; r++)
-                    t[r] = r < ps.world ? ld_volatile_f4(ps.grad[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 g = t[0];
-#pragma unroll
-                for (int r = 1; r < P2P_MAX_WORLD; r++)
-                    if (r < ps.world) g = f4add(g, t[r]);
-#pragma unroll
-                for (int r = 0; r < P2P_MAX_WORLD; r++)
-                    if (r < ps.world) *reinterpret_cast<float4 *>(ps.sum[r] + i) = g;
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const unsigned int done = atomicAdd(ps.ticket, 1u) + 1u;
-                if (done % (unsigned int)(hi - lo) == 0u) {       // last block of my range: tell everyone
-                    __threadfence_system();
-                    for (int r = 0; r < ps.world; r++)
-                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ps.flags2[r] + ps.rank), "r"(epoch) : "memory");
+            for (int r = 0; r < P2P_MAX_WORLD; r++) {
+                if (r < ps.world) {
+                    a[r] = ll_load2(my_rs + (size_t)r * ps.chunk_f);
+                    b[r] = ll_load2(my_rs + (size_t)r * ps.chunk_f + 2);
                 }
             }
+#pragma unroll
+            for (int r = 0; r < P2P_MAX_WORLD; r++) {
+                if (r < ps.world)
+                    all = all && (!need0 || a[r].y == epoch) && (!need1 || a[r].w == epoch) && (!need2 || b[r].y == epoch) &&
+                          (!need3 || b[r].w == epoch);
+            }
+            if (all) break;
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (!t0) t0 = t1;
+            if (t1 - t0 > 5000000000ull) { *ps.err = 1; break; }     // 5 s: a peer is gone; do not hang the GPU
         }
-        p2p_wait_flags(ps.my_flags2, ps.world, epoch, ps.err);
-        src[0] = ps.sum[ps.rank];         // the full sum now sits in local memory
-        nsrc = 1;
-    } else {
-        p2p_wait_flags(ps.my_flags, ps.world, epoch, ps.err);
+        float acc0 = __uint_as_float(a[0].x), acc1 = __uint_as_float(a[0].z), acc2 = __uint_as_float(b[0].x),
+              acc3 = __uint_as_float(b[0].z);
+#pragma unroll
+        for (int r = 1; r < P2P_MAX_WORLD; r++) {
+            if (r < ps.world) {
+                acc0 += __uint_as_float(a[r].x); acc1 += __uint_as_float(a[r].z);
+                acc2 += __uint_as_float(b[r].x); acc3 += __uint_as_float(b[r].z);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < P2P_MAX_WORLD; r++) {
+            if (r < ps.world) {
+                unsigned long long *dst = ps.ag[r] + par * (size_t)ps.world * ps.chunk_f + i;
+                ll_store2(dst, acc0, acc1, epoch);
+                ll_store2(dst + 2, acc2, acc3, epoch);
+            }
+        }
     }
-    if (i > o.P) return;
+    // ---- apply
+    float gs[4];
+    {
+        uint4 a, b;
+        t0 = 0;
+        for (;;) {
+            a = ll_load2(my_ag + i);
+            b = ll_load2(my_ag + i + 2);
+            if ((!need0 || a.y == epoch) && (!need1 || a.w == epoch) && (!need2 || b.y == epoch) && (!need3 || b.w == epoch)) break;
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (!t0) t0 = t1;
+            if (t1 - t0 > 5000000000ull) { *ps.err = 1; break; }
+        }
+        gs[0] = __uint_as_float(a.x); gs[1] = __uint_as_float(a.z); gs[2] = __uint_as_float(b.x); gs[3] = __uint_as_float(b.z);
+    }
     if (i + 3 < o.P && (i + 3 < o.b1 || (i >= o.b1 && i + 3 < o.w2) || (i >= o.w2 && i + 3 < o.b2) ||
                         (i >= o.b2 && i + 3 < o.w3) || (i >= o.w3 && i + 3 < o.b3))) {
-        float4 t[P2P_MAX_WORLD];
-#pragma unroll
-        for (int r = 0; r < P2P_MAX_WORLD; r++)
-            t[r] = r < nsrc ? ld_volatile_f4(src[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 w4 = *reinterpret_cast<const float4 *>(theta + i);
         float4 m4 = *reinterpret_cast<const float4 *>(m + i);
         float4 v4 = *reinterpret_cast<const float4 *>(v + i);
-        float4 g = t[0];
-#pragma unroll
-        for (int r = 1; r < P2P_MAX_WORLD; r++)
-            if (r < nsrc) g = f4add(g, t[r]);
+        const float4 g = make_float4(gs[0], gs[1], gs[2], gs[3]);
         *reinterpret_cast<float4 *>(flat_out + i) = g;
         finish4<true>(d, o, i, g, nullptr, theta, m, v, w4, m4, v4, ac, sp);
     } else {
-        for (int e = i; e < i + 4 && e <= o.P; e++) {
-            float g = ld_volatile_f1(src[0] + e);
-            for (int r = 1; r < nsrc; r++) g += ld_volatile_f1(src[r] + e);
+        for (int k = 0; k < nvalid; k++) {
+            const int e = i + k;
+            const float g = gs[k];
             flat_out[e] = g;
             if (e == o.P) { *loss_out = g; break; }
             float wi = theta[e], mi = m[e], vi = v[e];
@@ -1510,14 +1535,19 @@ int wide_p2p_apply(WideState *w, const PeerSet &ps, unsigned int epoch, const St
                    float *theta, float *m, float *v, AdamConsts ac, float *loss_out, cudaStream_t st,
                    std::string &err)
 {
-    const int groups = (w->o.P + 1 + 3) / 4, blocks = (groups + 255) / 256;
-    PeerSet p = ps;
-    if (blocks < p.world) p.two_shot = 0;      // every rank must own at least one block of the range split
-    wide_p2p_apply_kernel<<<blocks, 256, 0, st>>>(w->d, w->o, p, epoch, step, flat_out, theta, m, v, ac,
-                                                  shadow_ptrs(w, 0), loss_out);
+    const int groups = (w->o.P + 1 + 3) / 4;
+    wide_p2p_apply_kernel<<<(groups + 255) / 256, 256, 0, st>>>(w->d, w->o, ps, epoch, step, flat_out, theta, m, v, ac,
+                                                                shadow_ptrs(w, 0), loss_out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("wide_p2p_apply_kernel: ") + cudaGetErrorString(e); return -1; }
     return 1;
+}
+
+// floats owned per rank: an equal split of [P + 1] rounded up to whole 256-group blocks
+int wide_p2p_chunk_floats(const WideState *w, int world)
+{
+    const int per = (w->o.P + 1 + world - 1) / world;
+    return (per + 1023) / 1024 * 1024;
 }
 
 int wide_sync_target(WideState *w, cudaStream_t st, std::string &err)
@@ -1697,10 +1727,11 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     // (the update kernel follows cross-stream event waits: a full dependency, no PDL)
     if (s.fuse_update)
         wide_update_kernel<true><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
-                                                         s.step, shadow_ptrs(w, 0), s.loss_out);
+                                                         s.step, shadow_ptrs(w, 0), s.loss_out, PeerSet{}, 0u);
     else
         wide_update_kernel<false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
-                                                          s.adam, s.step, shadow_ptrs(w, 0), nullptr);
+                                                          s.adam, s.step, shadow_ptrs(w, 0), nullptr,
+                                                          s.push ? *s.push : PeerSet{}, s.epoch);
     WCK(cudaGetLastError());
     mark("reduce + Adam + bf16 shadow (K5)");
     launches++;

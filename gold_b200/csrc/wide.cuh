@@ -8,6 +8,26 @@ namespace gq {
 
 struct WideState;
 
+// Data-parallel exchange over NVLink peer memory (one process per GPU, buffers opened through
+// CUDA IPC).  Every float travels as one 8-byte word {value, epoch}: an 8-byte store is atomic, so
+// the epoch tag IS the arrival flag -- no separate flag words, no fences, no pull round trips.
+//   push   the slice-reduction kernel of rank s writes its local gradient element e straight into
+//          the receive window of the rank that owns e:        rs[owner(e)][parity][s][e - lo(owner)]
+//   reduce the owner polls the `world` words of each of its elements, adds them in rank order (so
+//          the sum is bit-identical everywhere) and writes {sum, epoch} into EVERY rank's  ag[parity][e]
+//   apply  every rank polls its own ag words and runs Adam + the bf16 shadow refresh
+// Windows alternate by epoch parity; a rank cannot be more than one step ahead of a peer (it needs
+// every owner's sums of step e+1, which an owner produces only after finishing step e), so a word
+// of epoch e is never overwritten before it has been consumed.
+constexpr int P2P_MAX_WORLD = 8;
+struct PeerSet {
+    int world, rank;
+    int chunk_f;                           // floats owned per rank (multiple of 1024: block-aligned groups)
+    unsigned long long *rs[P2P_MAX_WORLD]; // every rank's reduce-scatter window [2][world][chunk_f] words
+    unsigned long long *ag[P2P_MAX_WORLD]; // every rank's all-gather window     [2][world * chunk_f] words
+    int *err;                              // mapped host int: set to 1 when a word never arrives (5 s)
+};
+
 struct WideStep {
     Replay rp;
     const int32_t *idx;    // [B] device, or nullptr: draw on the device from `seed`
@@ -28,6 +48,8 @@ struct WideStep {
     // next_step != nullptr: gather the next step's batch (seed from *next_step) into the other set
     int set, have;
     const StepDev *next_step;
+    const PeerSet *push;   // non-null (data-parallel, peer memory): the slice reduction pushes the local
+    unsigned int epoch;    // gradient to its owners instead of writing `flat`
     // profiling (goldq_step_breakdown): record an event after every launch, single stream
     cudaEvent_t *prof_evs;
     int *prof_n;
@@ -43,27 +65,10 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
                       const StepDev *step, cudaStream_t st, std::string &err);
 int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err);
 
-// Data-parallel tail over NVLink peer memory (one process per GPU, buffers opened through CUDA
-// IPC): every rank publishes its local gradient, then sums all ranks' gradients straight out of
-// their memory in rank order and applies Adam + the bf16 shadow refresh, in ONE kernel.
-constexpr int P2P_MAX_WORLD = 8;
-struct PeerSet {
-    int world, rank;
-    const float *grad[P2P_MAX_WORLD];      // this step's gradient buffer of every rank ([P+1], loss last)
-    unsigned int *flags[P2P_MAX_WORLD];    // every rank's flag array; slot r is written by rank r
-    unsigned int *my_flags;                // = flags[rank], polled locally
-    int *err;                              // mapped host int: set to 1 when a peer never showed up
-    // two-shot variant (world > 2): rank r sums block-range r of the gradient and stores the sums
-    // into every rank's `sum` buffer; flags2 says "rank r's range has landed everywhere"
-    int two_shot;
-    float *sum[P2P_MAX_WORLD];
-    unsigned int *flags2[P2P_MAX_WORLD];
-    unsigned int *my_flags2;
-    unsigned int *ticket;                  // local counter: blocks of my range that have delivered
-};
 int wide_p2p_apply(WideState *w, const PeerSet &ps, unsigned int epoch, const StepDev *step, float *flat_out,
                    float *theta, float *m, float *v, AdamConsts ac, float *loss_out, cudaStream_t st,
                    std::string &err);
+int wide_p2p_chunk_floats(const WideState *w, int world);
 std::string wide_step_kernel_names(WideState *w);
 void wide_set_debug(WideState *w, bool on);
 void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const float **td);
