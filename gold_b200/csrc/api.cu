@@ -380,7 +380,7 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     ws.flat = h->flat;
     ws.loss_out = h->loss;
     ws.sc = step_scalars(h, h->Bglobal);
-    ws.fuse_update = h->world <= 1 ? 1 : 0;
+    ws.fuse_update = (h->world <= 1 || h->p2p.on) ? 1 : 0;
     ws.theta_rw = h->theta;
     ws.m = h->m;
     ws.v = h->v;
@@ -395,8 +395,7 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     int n = 0;
     PeerSet ps{};
     if (h->p2p.on) {
-        // every float of the gradient travels as a {value, epoch} word: pushed to its owner by the
-        // slice-reduction kernel (phase 1), summed and redistributed by wide_p2p_apply (phase 2)
+        // every float of the gradient travels as a {value, epoch} word, exchanged inside the update kernel
         if (phases & 1) h->p2p.epoch += 1;
         ps.world = h->world;
         ps.rank = h->rank;
@@ -414,12 +413,8 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
         if (n < 0) return fail(h, GOLDQ_ECUDA, err);
         h->launches += n;
     }
-    if (h->p2p.on && (phases & 2)) {
-        // fused all-reduce + Adam + shadow refresh over peer memory (graph-capturable: no NCCL call)
-        n = wide_p2p_apply(h->wide, ps, h->p2p.epoch, step, h->flat, h->theta, h->m, h->v, ws.adam, h->loss, h->st, err);
-        if (n < 0) return fail(h, GOLDQ_ECUDA, err);
-        h->launches += n;
-        if (h->prof_evs) cudaEventRecord(h->prof_evs[h->prof_n++], h->st);
+    if (h->p2p.on) {
+        // (the exchange happened inside the update kernel of wide_step)
     } else if (h->world > 1 && (phases & 2)) {
         int rc = allreduce_flat(h);
         if (rc) return rc;
@@ -1081,8 +1076,7 @@ int goldq_step_breakdown(goldq_t *h, uint64_t seed, int32_t max_kernels, float *
         h->prof_evs = nullptr;
         if (names && names_bytes > 0)
             snprintf(names, names_bytes, "%s%s", wide_step_kernel_names(h->wide).c_str(),
-                     h->p2p.on ? "\nall-reduce + Adam + bf16 shadow over peer memory (K5p)"
-                                : (h->world > 1 ? "\nncclAllReduce(grad)\nAdam + bf16 shadow (K5)" : ""));
+                     (h->world > 1 && !h->p2p.on) ? "\nncclAllReduce(grad)\nAdam + bf16 shadow (K5)" : "");
     } else {
         // single fused launch (narrow) or an unfused chain (generic): one interval for the step
         CK(h, cudaEventRecord(evs[0], h->st));

@@ -1039,6 +1039,104 @@ __device__ __forceinline__ void ll_push4(const PeerSet &L, unsigned int epoch, i
     ll_store2(dst + 2, g.z, g.w, epoch);
 }
 
+// The whole exchange for one float4 group, called by the SAME thread (same launch geometry) on
+// every rank: push the local value to the owner; on the owner wait for the `world` copies, add
+// them in rank order and write the sums into every rank's all-gather window; wait for the sums.
+// A thread only ever waits on words produced by threads that wait on nothing but pushes, and the
+// whole grid is resident (<= 2368 CTAs of 128 threads), so no wait can starve its producer.
+__device__ __forceinline__ bool ll_timed_out(unsigned long long &t0, int *err)
+{
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (!t0) t0 = t1;
+    if (t1 - t0 > 5000000000ull) { *err = 1; return true; }      // 5 s: a peer is gone; do not hang the GPU
+    return false;
+}
+__device__ __forceinline__ float4 dp_exchange4(const PeerSet &L, unsigned int epoch, int i, float4 g)
+{
+    ll_push4(L, epoch, i, g);
+    const size_t par = epoch & 1u;
+    const int owner = i / L.chunk_f;
+    if (owner == L.rank) {
+        const unsigned long long *my_rs = L.rs[L.rank] + par * (size_t)L.world * L.chunk_f + (i - owner * L.chunk_f);
+        uint4 a[P2P_MAX_WORLD], b[P2P_MAX_WORLD];
+        unsigned long long t0 = 0;
+        for (;;) {
+            bool all = true;
+#pragma unroll
+            for (int r = 0; r < P2P_MAX_WORLD; r++) {
+                if (r < L.world) {
+                    a[r] = ll_load2(my_rs + (size_t)r * L.chunk_f);
+                    b[r] = ll_load2(my_rs + (size_t)r * L.chunk_f + 2);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < P2P_MAX_WORLD; r++)
+                if (r < L.world) all = all && a[r].y == epoch && a[r].w == epoch && b[r].y == epoch && b[r].w == epoch;
+            if (all || ll_timed_out(t0, L.err)) break;
+        }
+        float4 acc = make_float4(__uint_as_float(a[0].x), __uint_as_float(a[0].z), __uint_as_float(b[0].x), __uint_as_float(b[0].z));
+#pragma unroll
+        for (int r = 1; r < P2P_MAX_WORLD; r++)
+            if (r < L.world)
+                acc = f4add(acc, make_float4(__uint_as_float(a[r].x), __uint_as_float(a[r].z), __uint_as_float(b[r].x),
+                                             __uint_as_float(b[r].z)));
+#pragma unroll
+        for (int r = 0; r < P2P_MAX_WORLD; r++) {
+            if (r < L.world) {
+                unsigned long long *dst = L.ag[r] + par * (size_t)L.world * L.chunk_f + i;
+                ll_store2(dst, acc.x, acc.y, epoch);
+                ll_store2(dst + 2, acc.z, acc.w, epoch);
+            }
+        }
+    }
+    const unsigned long long *my_ag = L.ag[L.rank] + par * (size_t)L.world * L.chunk_f + i;
+    uint4 a, b;
+    unsigned long long t0 = 0;
+    for (;;) {
+        a = ll_load2(my_ag);
+        b = ll_load2(my_ag + 2);
+        if ((a.y == epoch && a.w == epoch && b.y == epoch && b.w == epoch) || ll_timed_out(t0, L.err)) break;
+    }
+    return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+}
+// same for a single element (b3 and the loss)
+__device__ __forceinline__ float dp_exchange1(const PeerSet &L, unsigned int epoch, int e, float g)
+{
+    ll_push(L, epoch, e, g);
+    const size_t par = epoch & 1u;
+    const int owner = e / L.chunk_f;
+    unsigned long long t0 = 0;
+    if (owner == L.rank) {
+        const unsigned long long *my_rs = L.rs[L.rank] + par * (size_t)L.world * L.chunk_f + (e - owner * L.chunk_f);
+        unsigned int val[P2P_MAX_WORLD], tag[P2P_MAX_WORLD];
+        for (;;) {
+            bool all = true;
+#pragma unroll
+            for (int r = 0; r < P2P_MAX_WORLD; r++)
+                if (r < L.world)
+                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(val[r]), "=r"(tag[r]) : "l"(my_rs + (size_t)r * L.chunk_f) : "memory");
+#pragma unroll
+            for (int r = 0; r < P2P_MAX_WORLD; r++)
+                if (r < L.world) all = all && tag[r] == epoch;
+            if (all || ll_timed_out(t0, L.err)) break;
+        }
+        float acc = __uint_as_float(val[0]);
+#pragma unroll
+        for (int r = 1; r < P2P_MAX_WORLD; r++)
+            if (r < L.world) acc += __uint_as_float(val[r]);
+        for (int r = 0; r < L.world; r++) ll_store(L.ag[r] + par * (size_t)L.world * L.chunk_f + e, acc, epoch);
+    }
+    const unsigned long long *my_ag = L.ag[L.rank] + par * (size_t)L.world * L.chunk_f + e;
+    unsigned int val, tag;
+    t0 = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(val), "=r"(tag) : "l"(my_ag) : "memory");
+        if (tag == epoch || ll_timed_out(t0, L.err)) break;
+    }
+    return __uint_as_float(val);
+}
+
 template <bool FUSE>
 __device__ __forceinline__ void finish4(const Dims &d, const Offsets &o, int i, float4 g, float *flat, float *theta,
                                         float *m, float *v, float4 w4, float4 m4, float4 v4, const AdamConsts &ac,
@@ -1066,20 +1164,23 @@ __device__ __forceinline__ void finish4(const Dims &d, const Offsets &o, int i, 
     }
 }
 
-template <bool FUSE>
-__global__ void __launch_bounds__(128)
+// (DP: at least 5 CTAs per SM, so that the whole grid -- 727 CTAs on the wide configuration -- is
+// resident while its threads wait on their peers)
+template <bool FUSE, bool DP = false>
+__global__ void __launch_bounds__(128, DP ? 5 : 0)
 wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count, float *__restrict__ flat,
                    float *__restrict__ theta, float *__restrict__ m, float *__restrict__ v, AdamConsts ac,
                    const StepDev *__restrict__ step, ShadowPtrs sp, float *__restrict__ loss_out, PeerSet push,
                    unsigned int epoch)
 {
-    // push.world > 0 (only with FUSE == false): the reduced local gradient goes to its owners' windows
+    // push.world > 0 (data-parallel group over peer memory, FUSE only): the locally reduced gradient is
+    // exchanged (dp_exchange*) and the update uses the global sum
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_launch_dependents();
     pdl_wait();
     if (FUSE && step) { ac.c1 = step->c1; ac.c2 = step->c2; }
     if (step) epoch = step->epoch;
-    const bool do_push = !FUSE && push.world > 0;
+    constexpr bool dp = FUSE && DP;      // (a separate instantiation: the exchange costs registers)
     if ((int)blockIdx.x < pl.blocksA) {
         // ---- A: weights ------------------------------------------------------------
         const int gidx = blockIdx.x * 128 + threadIdx.x;
@@ -1107,11 +1208,8 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
 #pragma unroll
             for (int u = 0; u < 8; u++) g = f4add(g, t[u]);
         }
-        if (do_push) {
-            ll_push4(push, epoch, i, g);
-        } else {
-            finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
-        }
+        if (dp) g = dp_exchange4(push, epoch, i, g);
+        finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
     } else if ((int)blockIdx.x < pl.blocksA + pl.blocksB) {
         // ---- B: biases of the hidden layers, warp per float4 group -------------------
         const int gidx = (blockIdx.x - pl.blocksA) * 4 + warp;
@@ -1146,11 +1244,8 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
                 m4 = *reinterpret_cast<const float4 *>(m + i);
                 v4 = *reinterpret_cast<const float4 *>(v + i);
             }
-            if (do_push) {
-                ll_push4(push, epoch, i, g);
-            } else {
-                finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
-            }
+            if (dp) g = dp_exchange4(push, epoch, i, g);
+            finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
         }
     } else {
         // ---- C: b3 and the loss, warp per scalar ---------------------------------------
@@ -1163,12 +1258,10 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) g += __shfl_xor_sync(0xffffffffu, g, off);
         if (lane == 0) {
-            if (i == o.P) {
-                g = __fdiv_rn(g, count);
-                if (loss_out) *loss_out = g;
-            }
-            if (do_push) ll_push(push, epoch, i, g);
-            else flat[i] = g;
+            if (i == o.P) g = __fdiv_rn(g, count);
+            if (dp) g = dp_exchange1(push, epoch, i, g);
+            if (i == o.P && loss_out) *loss_out = g;
+            flat[i] = g;
             if (FUSE && i < o.P) {
                 float wi = theta[i], mi = m[i], vi = v[i];
                 adam_update_w(wi, g, mi, vi, ac);
@@ -1426,123 +1519,6 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
     return 1;
 }
 
-// ---------------------------------------------------------------------------
-// Fused gradient all-reduce + Adam over NVLink peer memory (data-parallel tail; protocol in
-// wide.cuh at PeerSet).  One thread per float4 group of the flat vector [P + 1]:
-//   reduce  (threads whose group this rank owns) wait for the `world` pushed copies of each element,
-//           add them in rank order, write {sum, epoch} into every rank's all-gather window;
-//   apply   (all threads) wait for their group's sums in the local window, then Adam + shadow.
-// Blocks never wait on blocks of the same grid that might not be resident: the words an apply
-// thread waits for are produced by owner threads that wait only on pushes of the previous kernel.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-wide_p2p_apply_kernel(Dims d, Offsets o, PeerSet ps, unsigned int epoch, const StepDev *__restrict__ step,
-                      float *__restrict__ flat_out, float *__restrict__ theta, float *__restrict__ m,
-                      float *__restrict__ v, AdamConsts ac, ShadowPtrs sp, float *__restrict__ loss_out)
-{
-    if (step) { ac.c1 = step->c1; ac.c2 = step->c2; epoch = step->epoch; }
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i > o.P) return;
-    const size_t par = epoch & 1u;
-    const int nvalid = (o.P + 1 - i) < 4 ? (o.P + 1 - i) : 4;      // elements past the loss do not exist
-    const int lo = ps.rank * ps.chunk_f;
-    unsigned long long *my_ag = ps.ag[ps.rank] + par * (size_t)ps.world * ps.chunk_f;
-    // elements that do not exist (past the loss, last group only) count as arrived
-    const unsigned int need0 = nvalid > 0, need1 = nvalid > 1, need2 = nvalid > 2, need3 = nvalid > 3;
-    unsigned long long t0 = 0;
-    if (i >= lo && i < lo + ps.chunk_f) {
-        // ---- reduce: this rank owns the group.  All copies are polled together (independent loads).
-        const unsigned long long *my_rs = ps.rs[ps.rank] + par * (size_t)ps.world * ps.chunk_f + (i - lo);
-        uint4 a[P2P_MAX_WORLD], b[P2P_MAX_WORLD];
-        for (;;) {
-            bool all = true;
-#pragma unroll
-            for (int r = 0; r < P2P_MAX_WORLD; r++) {
-                if (r < ps.world) {
-                    a[r] = ll_load2(my_rs + (size_t)r * ps.chunk_f);
-                    b[r] = ll_load2(my_rs + (size_t)r * ps.chunk_f + 2);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < P2P_MAX_WORLD; r++) {
-                if (r < ps.world)
-                    all = all && (!need0 || a[r].y == epoch) && (!need1 || a[r].w == epoch) && (!need2 || b[r].y == epoch) &&
-                          (!need3 || b[r].w == epoch);
-            }
-            if (all) break;
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (!t0) t0 = t1;
-            if (t1 - t0 > 5000000000ull) { *ps.err = 1; break; }     // 5 s: a peer is gone; do not hang the GPU
-        }
-        float acc0 = __uint_as_float(a[0].x), acc1 = __uint_as_float(a[0].z), acc2 = __uint_as_float(b[0].x),
-              acc3 = __uint_as_float(b[0].z);
-#pragma unroll
-        for (int r = 1; r < P2P_MAX_WORLD; r++) {
-            if (r < ps.world) {
-                acc0 += __uint_as_float(a[r].x); acc1 += __uint_as_float(a[r].z);
-                acc2 += __uint_as_float(b[r].x); acc3 += __uint_as_float(b[r].z);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < P2P_MAX_WORLD; r++) {
-            if (r < ps.world) {
-                unsigned long long *dst = ps.ag[r] + par * (size_t)ps.world * ps.chunk_f + i;
-                ll_store2(dst, acc0, acc1, epoch);
-                ll_store2(dst + 2, acc2, acc3, epoch);
-            }
-        }
-    }
-    // ---- apply
-    float gs[4];
-    {
-        uint4 a, b;
-        t0 = 0;
-        for (;;) {
-            a = ll_load2(my_ag + i);
-            b = ll_load2(my_ag + i + 2);
-            if ((!need0 || a.y == epoch) && (!need1 || a.w == epoch) && (!need2 || b.y == epoch) && (!need3 || b.w == epoch)) break;
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (!t0) t0 = t1;
-            if (t1 - t0 > 5000000000ull) { *ps.err = 1; break; }
-        }
-        gs[0] = __uint_as_float(a.x); gs[1] = __uint_as_float(a.z); gs[2] = __uint_as_float(b.x); gs[3] = __uint_as_float(b.z);
-    }
-    if (i + 3 < o.P && (i + 3 < o.b1 || (i >= o.b1 && i + 3 < o.w2) || (i >= o.w2 && i + 3 < o.b2) ||
-                        (i >= o.b2 && i + 3 < o.w3) || (i >= o.w3 && i + 3 < o.b3))) {
-        float4 w4 = *reinterpret_cast<const float4 *>(theta + i);
-        float4 m4 = *reinterpret_cast<const float4 *>(m + i);
-        float4 v4 = *reinterpret_cast<const float4 *>(v + i);
-        const float4 g = make_float4(gs[0], gs[1], gs[2], gs[3]);
-        *reinterpret_cast<float4 *>(flat_out + i) = g;
-        finish4<true>(d, o, i, g, nullptr, theta, m, v, w4, m4, v4, ac, sp);
-    } else {
-        for (int k = 0; k < nvalid; k++) {
-            const int e = i + k;
-            const float g = gs[k];
-            flat_out[e] = g;
-            if (e == o.P) { *loss_out = g; break; }
-            float wi = theta[e], mi = m[e], vi = v[e];
-            adam_update_w(wi, g, mi, vi, ac);
-            theta[e] = wi; m[e] = mi; v[e] = vi;
-            shadow_store(d, o, sp, e, wi);
-        }
-    }
-}
-
-int wide_p2p_apply(WideState *w, const PeerSet &ps, unsigned int epoch, const StepDev *step, float *flat_out,
-                   float *theta, float *m, float *v, AdamConsts ac, float *loss_out, cudaStream_t st,
-                   std::string &err)
-{
-    const int groups = (w->o.P + 1 + 3) / 4;
-    wide_p2p_apply_kernel<<<(groups + 255) / 256, 256, 0, st>>>(w->d, w->o, ps, epoch, step, flat_out, theta, m, v, ac,
-                                                                shadow_ptrs(w, 0), loss_out);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { err = std::string("wide_p2p_apply_kernel: ") + cudaGetErrorString(e); return -1; }
-    return 1;
-}
-
 // floats owned per rank: an equal split of [P + 1] rounded up to whole 256-group blocks
 int wide_p2p_chunk_floats(const WideState *w, int world)
 {
@@ -1725,13 +1701,15 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     pl.blocksC = (pl.nC + 3) / 4;
     const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
     // (the update kernel follows cross-stream event waits: a full dependency, no PDL)
-    if (s.fuse_update)
+    if (s.fuse_update && s.push)
+        wide_update_kernel<true, true><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
+                                                               s.step, shadow_ptrs(w, 0), s.loss_out, *s.push, s.epoch);
+    else if (s.fuse_update)
         wide_update_kernel<true><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
                                                          s.step, shadow_ptrs(w, 0), s.loss_out, PeerSet{}, 0u);
     else
         wide_update_kernel<false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
-                                                          s.adam, s.step, shadow_ptrs(w, 0), nullptr,
-                                                          s.push ? *s.push : PeerSet{}, s.epoch);
+                                                          s.adam, s.step, shadow_ptrs(w, 0), nullptr, PeerSet{}, 0u);
     WCK(cudaGetLastError());
     mark("reduce + Adam + bf16 shadow (K5)");
     launches++;

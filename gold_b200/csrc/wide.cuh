@@ -11,11 +11,12 @@ struct WideState;
 // Data-parallel exchange over NVLink peer memory (one process per GPU, buffers opened through
 // CUDA IPC).  Every float travels as one 8-byte word {value, epoch}: an 8-byte store is atomic, so
 // the epoch tag IS the arrival flag -- no separate flag words, no fences, no pull round trips.
-//   push   the slice-reduction kernel of rank s writes its local gradient element e straight into
-//          the receive window of the rank that owns e:        rs[owner(e)][parity][s][e - lo(owner)]
-//   reduce the owner polls the `world` words of each of its elements, adds them in rank order (so
-//          the sum is bit-identical everywhere) and writes {sum, epoch} into EVERY rank's  ag[parity][e]
-//   apply  every rank polls its own ag words and runs Adam + the bf16 shadow refresh
+// All of it happens inside the update kernel (wide_update_kernel, dp_exchange4), per element e:
+//   push   rank s writes its locally reduced gradient straight into the receive window of the rank
+//          that owns e:                                        rs[owner(e)][parity][s][e - lo(owner)]
+//   reduce the owner polls the `world` words, adds them in rank order (so the sum is bit-identical
+//          everywhere) and writes {sum, epoch} into EVERY rank's                      ag[parity][e]
+//   apply  every rank polls its own ag word and runs Adam + the bf16 shadow refresh
 // Windows alternate by epoch parity; a rank cannot be more than one step ahead of a peer (it needs
 // every owner's sums of step e+1, which an owner produces only after finishing step e), so a word
 // of epoch e is never overwritten before it has been consumed.
@@ -48,8 +49,8 @@ struct WideStep {
     // next_step != nullptr: gather the next step's batch (seed from *next_step) into the other set
     int set, have;
     const StepDev *next_step;
-    const PeerSet *push;   // non-null (data-parallel, peer memory): the slice reduction pushes the local
-    unsigned int epoch;    // gradient to its owners instead of writing `flat`
+    const PeerSet *push;   // non-null (data-parallel group over peer memory, fuse_update = 1): the update
+    unsigned int epoch;    // kernel exchanges the gradient with the peers before applying it
     // profiling (goldq_step_breakdown): record an event after every launch, single stream
     cudaEvent_t *prof_evs;
     int *prof_n;
@@ -65,9 +66,6 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
                       const StepDev *step, cudaStream_t st, std::string &err);
 int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err);
 
-int wide_p2p_apply(WideState *w, const PeerSet &ps, unsigned int epoch, const StepDev *step, float *flat_out,
-                   float *theta, float *m, float *v, AdamConsts ac, float *loss_out, cudaStream_t st,
-                   std::string &err);
 int wide_p2p_chunk_floats(const WideState *w, int world);
 std::string wide_step_kernel_names(WideState *w);
 void wide_set_debug(WideState *w, bool on);
