@@ -409,7 +409,7 @@ def run_own(args):
                             "readback (sync); host wall clock, max over ranks"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "path": {1: "generic", 2: "narrow", 3: "wide"}[h.path], "last_loss": [float(x) for x in last[:4]],
-            "allreduce": {0: None, 1: "ncclAllReduce + update kernel", 2: "fused all-reduce + Adam kernel over NVLink peer memory (CUDA IPC)"}[h.dp_mode()],
+            "allreduce": {0: None, 1: "ncclAllReduce + update kernel", 2: "gradient exchange over NVLink peer memory (CUDA IPC) inside the update kernel"}[h.dp_mode()],
         }
         emit(line)
     h.close()

@@ -287,7 +287,7 @@ class Handle:
         self._ck(self._L.goldq_dp_init(self._h, buf, rank, world))
 
     def dp_mode(self):
-        """0: no group, 1: ncclAllReduce + update kernel, 2: fused peer-memory kernel."""
+        """0: no group, 1: ncclAllReduce + update kernel, 2: peer-memory exchange inside the update kernel."""
         return int(self._L.goldq_dp_mode(self._h))
 
     def last_error(self):

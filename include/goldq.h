@@ -179,8 +179,8 @@ int goldq_fit_batch(goldq_t *h, int64_t n, const float *x, const float *y);
 int goldq_dp_unique_id(uint8_t id[128]);
 int goldq_dp_init(goldq_t *h, const uint8_t id[128], int rank, int world);
 /* How the group sums gradients: 0 = no group, 1 = ncclAllReduce + update kernel,
- * 2 = one fused kernel over NVLink peer memory (wide path; buffers shared through CUDA
- * IPC at goldq_dp_init; GOLDQ_NO_P2P=1 in the environment selects 1). */
+ * 2 = exchanged over NVLink peer memory inside the update kernel (wide path; windows shared
+ * through CUDA IPC at goldq_dp_init; GOLDQ_NO_P2P=1 in the environment selects 1). */
 int goldq_dp_mode(const goldq_t *h);
 
 /* ---- plumbing ----------------------------------------------------------- */
