@@ -152,6 +152,20 @@ func (x *Handle) FitBatch(n int, in, y []float32) error {
 	return x.err(C.goldq_fit_batch(x.h, C.int64_t(n), f32(in), f32(y)))
 }
 
+// Data-parallel group (one Handle per GPU/process).  DpUniqueID on rank 0, distribute the 128 bytes
+// by any side channel, DpInit everywhere; DpMode: 0 none, 1 ncclAllReduce, 2 peer-memory exchange.
+func DpUniqueID() ([128]byte, error) {
+	var id [128]byte
+	if rc := C.goldq_dp_unique_id((*C.uint8_t)(unsafe.Pointer(&id[0]))); rc != 0 {
+		return id, fmt.Errorf("goldq_dp_unique_id: %s", C.GoString(C.goldq_last_error(nil)))
+	}
+	return id, nil
+}
+func (x *Handle) DpInit(id [128]byte, rank, world int) error {
+	return x.err(C.goldq_dp_init(x.h, (*C.uint8_t)(unsafe.Pointer(&id[0])), C.int(rank), C.int(world)))
+}
+func (x *Handle) DpMode() int { return int(C.goldq_dp_mode(x.h)) }
+
 func max1(n int) int {
 	if n < 1 {
 		return 1
