@@ -344,7 +344,7 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     // starts only after every layer-1 MMA (the readers of X) has retired
     uint8_t *sX = sH + (KH - KD) * FF_BOX;
     uint8_t *sW = sH + KH * FF_BOX;                     // weight ring
-    __shared__ uint64_t full_w[FF_WSTAGES], empty_w[FF_WSTAGES], x_full, acc_full[2], acc_free[2], h_ready;
+    __shared__ uint64_t full_w[FF_WSTAGES], empty_w[FF_WSTAGES], x_full, acc_full[2], acc_free[2], h_ready, h_lo;
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -362,6 +362,7 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
         mbar_init(&acc_free[0], FF_EPI_THREADS / 32); mbar_init(&acc_free[1], FF_EPI_THREADS / 32);
         mbar_init(&h_ready, 1);
+        mbar_init(&h_lo, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_slot, 512);
@@ -423,13 +424,20 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             if (elect_one()) mma_commit(&acc_full[half]);
             __syncwarp();
         }
-        // layer 2: A = H1 (written by the epilogue); both accumulator halves must be drained
-        mbar_wait(&h_ready, 0);
+        // layer 2: A = H1 (written by the epilogue).  Its first four k-blocks are the columns the
+        // epilogue of accumulator half 0 produced: they start while half 1 is still being drained.
+        mbar_wait(&h_lo, 0);
         mbar_wait(&acc_free[0], 0);
-        mbar_wait(&acc_free[1], 0);
         tc_fence_after();
         for (int half = 0; half < 2; half++) {
-            for (int kb = 0; kb < KH; kb++) mma_block(smem_u32(sH + kb * FF_BOX), tmem + half * 256, kb == 0);
+            for (int kb = 0; kb < KH; kb++) {
+                if (half == 0 && kb == KH / 2) {
+                    mbar_wait(&h_ready, 0);
+                    mbar_wait(&acc_free[1], 0);
+                    tc_fence_after();
+                }
+                mma_block(smem_u32(sH + kb * FF_BOX), tmem + half * 256, kb == 0);
+            }
             if (elect_one()) mma_commit(&acc_full[half]);
             __syncwarp();
         }
@@ -519,6 +527,11 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) arrive(&acc_free[half]);
+            if (half == 0) {           // boxes 0..3 of H1 are complete: layer 2 may start on them
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et == 0) arrive(&h_lo);
+            }
         }
         fence_proxy_async_smem();      // H1 complete: visible to the async proxy (layer-2 MMA, TMA store)
         asm volatile("bar.sync 1, 256;" ::: "memory");
