@@ -441,12 +441,17 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             if (elect_one()) mma_commit(&acc_full[half]);
             __syncwarp();
         }
-        // layer 3: A = H2, N = 64 (W3 padded); a ring stage holds four k-blocks
-        mbar_wait(&h_ready, 1);
+        // layer 3: A = H2, N = 64 (W3 padded); a ring stage holds four k-blocks.  The first stage needs
+        // only the first half of H2, which the epilogue writes out before it drains half 1.
+        mbar_wait(&h_lo, 1);
         mbar_wait(&acc_free[0], 1);
-        mbar_wait(&acc_free[1], 1);
         tc_fence_after();
         for (int kq = 0; kq < KH / 4; kq++) {
+            if (kq == 1) {
+                mbar_wait(&h_ready, 1);
+                mbar_wait(&acc_free[1], 1);
+                tc_fence_after();
+            }
             const int s = it % FF_WSTAGES;
             const uint32_t ph = (it / FF_WSTAGES) & 1;
             mbar_wait(&full_w[s], ph);
@@ -568,6 +573,10 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             tmem_ld_32x32(tq + (uint32_t)col0(1, 0), r);
 #pragma unroll
             for (int c = 0; c < 4; c++) store_chunk(col0(0, c), hold[c]);
+            // boxes 0..3 of H2 are complete: layer 3 may start on them
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) arrive(&h_lo);
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 if (c) tmem_ld_32x32(tq + (uint32_t)col0(1, c), r);
