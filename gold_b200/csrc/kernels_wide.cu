@@ -743,6 +743,7 @@ cudaError_t configure_all_gemms()
     // 128x256 tiles, two stages (two CTAs per SM: 2 x 97 KB smem, 2 x 256 TMEM columns)
     if (e == cudaSuccess) e = configure_gemm<MODE_KM, 256, EPI_BIAS_RELU_BF16, 1, 2>();
     if (e == cudaSuccess) e = configure_gemm<MODE_KK, 256, EPI_MASK_BF16, 1, 2>();
+    if (e == cudaSuccess) e = configure_gemm<MODE_KK, 256, EPI_MASK_BF16, 1, 4>();
     if (e == cudaSuccess) e = configure_gemm<MODE_KM, 256, EPI_F32_SLICE, 1, 2>();
     if (e == cudaSuccess) e = configure_gemm<MODE_KK, 256, EPI_F32_SLICE, 1, 2>();
     if (e == cudaSuccess)
@@ -1683,7 +1684,11 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g.M = B; g.N = d.H1; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = w->dz1; g.mask_src = w->h1; g.ldo = d.H1; g.n_store = d.H1;
     if (w->bn256)
-        WCK((launch_gemm<MODE_KK, 256, EPI_MASK_BF16, 1, 2>(w->tm_dz2_a, on.tm_w2_k256, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
+        // one CTA per SM here (B/128 x H1/256 tiles <= SMs): a 4-stage ring (192 KB) instead of 2
+        if (((B + BM - 1) / BM) * ((d.H1 + 255) / 256) <= w->sm_count)
+            WCK((launch_gemm<MODE_KK, 256, EPI_MASK_BF16, 1, 4>(w->tm_dz2_a, on.tm_w2_k256, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
+        else
+            WCK((launch_gemm<MODE_KK, 256, EPI_MASK_BF16, 1, 2>(w->tm_dz2_a, on.tm_w2_k256, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
     else if (w->mc_rows)
         WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16, 4>(w->tm_dz2_a, on.tm_w2_k_s4, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
     else
