@@ -1,14 +1,14 @@
 // Package deepq is a drop-in for github.com/aunum/gold/pkg/v1/agent/deepq whose
-// learn step runs on a B200 through libgoldq (cgo).  Exported names, argument
-// meaning and error behaviour follow the reference file by file
-// (pkg/v1/agent/deepq/agent.go, memory.go, policy.go).
+// learn step runs on a B200 through libgoldq (cgo).  The exported surface — type, field
+// and function names, argument meaning, error behaviour — is the reference's
+// (pkg/v1/agent/deepq/agent.go, memory.go, policy.go); everything behind it is new.
 //
 // NOT COMPILED HERE (no Go toolchain in the build image); its executable twin is
 // gold_b200/deepq.py, which tests/test_host_api.py drives through the same C ABI.
 package deepq
 
 import (
-	"fmt"
+	"errors"
 	"math/rand"
 
 	agentv1 "github.com/aunum/gold/pkg/v1/agent"
@@ -21,128 +21,116 @@ import (
 	"github.com/aunum/gold-b200/go/goldq"
 )
 
-// Agent is a dqn agent (reference: agent.go:19-42).
-type Agent struct {
-	*agentv1.Base
-	*Hyperparameters
-
-	// Policy and TargetPolicy satisfy the slice of model.Model the agent and its
-	// callers use; both are views of one device handle.
-	Policy       model.Model
-	TargetPolicy model.Model
-	Epsilon      common.Schedule
-
-	env               *envv1.Env
-	epsilon           float32
-	updateTargetSteps int
-	batchSize         int
-	memory            *Memory
-	steps             int
-	h                 *goldq.Handle
-}
-
-// Hyperparameters for the dqn agent (reference: agent.go:44-58).
+// Hyperparameters keeps the reference's exported fields (agent.go:44-58).
 type Hyperparameters struct {
-	Gamma             float32
-	Epsilon           common.Schedule
-	UpdateTargetSteps int
-	BufferSize        int
+	Gamma             float32         // discount of the TD target
+	Epsilon           common.Schedule // exploration rate, advanced once per Learn
+	UpdateTargetSteps int             // target <- online every this many Action calls
+	BufferSize        int             // replay capacity (device ring)
 }
 
-// DefaultHyperparameters (reference: agent.go:60-66).
-var DefaultHyperparameters = &Hyperparameters{
-	Epsilon:           common.DefaultDecaySchedule(),
-	Gamma:             0.95,
-	UpdateTargetSteps: 100,
-	BufferSize:        10e6,
-}
-
-// AgentConfig (reference: agent.go:68-78).
+// AgentConfig keeps the reference's exported fields (agent.go:68-78).
 type AgentConfig struct {
 	Base *agentv1.Base
 	*Hyperparameters
 	PolicyConfig *PolicyConfig
 }
 
-// DefaultAgentConfig (reference: agent.go:80-85).
-var DefaultAgentConfig = &AgentConfig{
-	Hyperparameters: DefaultHyperparameters,
-	PolicyConfig:    DefaultPolicyConfig,
-	Base:            agentv1.NewBase("DeepQ"),
+// Defaults: same values as the reference (agent.go:60-66, 80-85).
+var (
+	DefaultHyperparameters = &Hyperparameters{Gamma: 0.95, Epsilon: common.DefaultDecaySchedule(), UpdateTargetSteps: 100, BufferSize: 10e6}
+	DefaultAgentConfig     = &AgentConfig{Base: agentv1.NewBase("DeepQ"), Hyperparameters: DefaultHyperparameters, PolicyConfig: DefaultPolicyConfig}
+)
+
+// device is everything the agent keeps on the B200 side plus the counters that drive it.
+type device struct {
+	handle     *goldq.Handle
+	replay     *Memory
+	env        *envv1.Env
+	eps        float32 // current exploration rate
+	syncEvery  int     // = UpdateTargetSteps
+	batch      int     // = PolicyConfig.BatchSize
+	actionsRun int     // Action calls so far; the target sync is keyed on it, as in the reference
 }
 
-// NewAgent returns a new dqn agent (reference: agent.go:88-123).
-func NewAgent(c *AgentConfig, env *envv1.Env) (*Agent, error) {
+// Agent is a dqn agent with the reference's exported fields (agent.go:19-42).  Policy and
+// TargetPolicy are two views of ONE device handle.
+type Agent struct {
+	*agentv1.Base
+	*Hyperparameters
+	Policy, TargetPolicy model.Model
+	Epsilon              common.Schedule
+	device
+}
+
+// resolved returns c with the reference's fall-backs applied (nil config, nil Base, nil schedule).
+func resolved(c *AgentConfig) *AgentConfig {
 	if c == nil {
-		c = DefaultAgentConfig
+		return DefaultAgentConfig
 	}
 	if c.Base == nil {
 		c.Base = DefaultAgentConfig.Base
 	}
-	if env == nil {
-		return nil, fmt.Errorf("environment cannot be nil")
-	}
 	if c.Epsilon == nil {
 		c.Epsilon = common.DefaultDecaySchedule()
 	}
-	h, online, target, err := makePolicies(c.PolicyConfig, c.Hyperparameters, env)
+	return c
+}
+
+// NewAgent builds the device handle (both networks, replay ring, solver state) and wraps it.
+// Errors as the reference does for a missing environment (agent.go:88-123).
+func NewAgent(c *AgentConfig, env *envv1.Env) (*Agent, error) {
+	if env == nil {
+		return nil, errors.New("environment cannot be nil")
+	}
+	cfg := resolved(c)
+	handle, online, target, err := makePolicies(cfg.PolicyConfig, cfg.Hyperparameters, env)
 	if err != nil {
 		return nil, err
 	}
-	c.Base.Tracker.TrackValue("epsilon", c.Epsilon.Initial())
-	return &Agent{
-		Base:              c.Base,
-		Hyperparameters:   c.Hyperparameters,
-		memory:            NewMemory(h),
-		Policy:            online,
-		TargetPolicy:      target,
-		Epsilon:           c.Epsilon,
-		epsilon:           c.Epsilon.Initial(),
-		env:               env,
-		updateTargetSteps: c.UpdateTargetSteps,
-		batchSize:         c.PolicyConfig.BatchSize,
-		h:                 h,
-	}, nil
+	start := cfg.Epsilon.Initial()
+	cfg.Base.Tracker.TrackValue("epsilon", start)
+	agent := &Agent{Base: cfg.Base, Hyperparameters: cfg.Hyperparameters, Policy: online, TargetPolicy: target, Epsilon: cfg.Epsilon}
+	agent.device = device{handle: handle, replay: NewMemory(handle), env: env, eps: start,
+		syncEvery: cfg.UpdateTargetSteps, batch: cfg.PolicyConfig.BatchSize}
+	return agent, nil
 }
 
-// Learn the agent (reference: agent.go:126-178).  Sample, the two forwards per
-// event, the label, FitBatch and the Adam step run in libgoldq.
+// Learn runs one minibatch update.  The reference's body (sample, two forwards per event, label,
+// concat, FitBatch, Adam: agent.go:126-178) is one goldq_learn call; what stays in Go is the
+// "too few events yet" no-op, the epsilon decay and the target-sync cadence.
 func (a *Agent) Learn() error {
-	if err := a.memory.flush(); err != nil {
+	if err := a.replay.flush(); err != nil { // events remembered since the last Learn go to the device ring
 		return err
 	}
-	if a.memory.Len() < a.batchSize {
+	if a.replay.Len() < a.batch {
 		return nil
 	}
-	if err := a.h.Learn(nil, rand.Uint64()); err != nil {
-		if err == goldq.ErrNotReady {
-			return nil
-		}
+	switch err := a.handle.Learn(nil, rand.Uint64()); err {
+	case nil:
+	case goldq.ErrNotReady:
+		return nil
+	default:
 		return err
 	}
-	a.epsilon = a.Epsilon.Value()
-	return a.updateTarget()
-}
-
-// updateTarget (reference: agent.go:181-190).
-func (a *Agent) updateTarget() error {
-	if a.steps%a.updateTargetSteps == 0 {
-		return a.h.SyncTarget()
+	a.eps = a.Epsilon.Value()
+	if a.actionsRun%a.syncEvery != 0 { // agent.go:181-190: keyed on Action calls, checked after every Learn
+		return nil
 	}
-	return nil
+	return a.handle.SyncTarget()
 }
 
-// Action selects the best known action for the given state (reference: agent.go:193-205).
+// Action is epsilon-greedy; the greedy branch is the first-argmax of the online network's Q
+// (agent.go:193-221), evaluated on the device.
 func (a *Agent) Action(state *tensor.Dense) (action int, err error) {
-	a.steps++
-	a.Tracker.TrackValue("epsilon", a.epsilon)
-	if num.RandF32(0.0, 1.0) < a.epsilon {
+	a.actionsRun++
+	a.Tracker.TrackValue("epsilon", a.eps)
+	explore := num.RandF32(0.0, 1.0) < a.eps
+	if explore {
 		return a.env.SampleAction()
 	}
-	return a.h.GreedyAction(state.Data().([]float32))
+	return a.handle.GreedyAction(state.Data().([]float32))
 }
 
-// Remember an event (reference: agent.go:224-229).
-func (a *Agent) Remember(event *Event) {
-	a.memory.PushFront(event)
-}
+// Remember queues an event for the device replay ring (agent.go:224-229).
+func (a *Agent) Remember(event *Event) { a.replay.PushFront(event) }
