@@ -17,9 +17,10 @@ struct WideState;
 //   reduce the owner polls the `world` words, adds them in rank order (so the sum is bit-identical
 //          everywhere) and writes {sum, epoch} into EVERY rank's                      ag[parity][e]
 //   apply  every rank polls its own ag word and runs Adam + the bf16 shadow refresh
-// Windows alternate by epoch parity; a rank cannot be more than one step ahead of a peer (it needs
-// every owner's sums of step e+1, which an owner produces only after finishing step e), so a word
-// of epoch e is never overwritten before it has been consumed.
+// A rank cannot be more than one step ahead of a peer (it needs every owner's sums of step e+1,
+// which an owner produces only after every rank has pushed e+1, i.e. finished step e), so a word of
+// epoch e is never overwritten before it has been consumed; tests/test_dp_protocol.py checks this
+// over random interleavings.  The windows additionally alternate by epoch parity (margin only).
 constexpr int P2P_MAX_WORLD = 8;
 struct PeerSet {
     int world, rank;
