@@ -431,6 +431,9 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
 int run_learn(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev *step = nullptr)
 {
     if (h->rp.len < h->B) return fail(h, GOLDQ_ENOTREADY, "replay shorter than batch");
+    // a peer that stopped answering was detected by an earlier step: do not queue more 5 s waits
+    if (h->p2p.on && *(volatile int *)h->p2p.err_host)
+        return fail(h, GOLDQ_ENCCL, "data-parallel peer did not publish its gradient within 5 s");
     if (h->path == GOLDQ_PATH_NARROW) return learn_narrow(h, idx_dev, seed, step);
     if (h->path == GOLDQ_PATH_WIDE) return learn_wide(h, idx_dev, seed, step);
     if (!idx_dev) {
