@@ -68,8 +68,13 @@ func makePolicies(c *PolicyConfig, hp *Hyperparameters, env *envv1.Env) (*goldq.
 	x.EnsureBatch()
 	y := modelv1.NewInput("actionPotentials", envv1.PotentialsShape(env.ActionSpace))
 	y.EnsureBatch()
-	if _, ok := c.Loss.(*modelv1.MSELoss); !ok {
-		return nil, nil, nil, fmt.Errorf("goldq implements model.MSE only, got %T", c.Loss)
+	lossKind, delta := goldq.LossMSE, float32(1)
+	switch l := c.Loss.(type) {
+	case *modelv1.MSELoss:
+	case *modelv1.PseudoHuberLoss: // reduced by Mean on the device; the reference's Sum(.., 1) cannot be differentiated
+		lossKind, delta = goldq.LossPseudoHuber, l.Delta
+	default:
+		return nil, nil, nil, fmt.Errorf("goldq implements model.MSE and model.PseudoHuber, got %T", c.Loss)
 	}
 	layers := c.LayerBuilder(x, y)
 	if len(layers) != 3 {
@@ -83,14 +88,23 @@ func makePolicies(c *PolicyConfig, hp *Hyperparameters, env *envv1.Env) (*goldq.
 		}
 		fc[i] = f
 	}
-	eta, eps, b1, b2, err := adamFields(c.Optimizer)
-	if err != nil {
+	solver := goldq.SolverAdam
+	var eta, eps, b1, b2 float64
+	var err error
+	if rms, ok := c.Optimizer.(*g.RMSPropSolver); ok { // gold's Atari config (policy.go:41-47); unexported fields by reflection
+		v := reflect.ValueOf(rms).Elem()
+		if v.FieldByName("useClip").Bool() || v.FieldByName("useL2Reg").Bool() {
+			return nil, nil, nil, fmt.Errorf("goldq: RMSProp with clipping or L2 regularisation is not implemented")
+		}
+		solver, eta, eps, b2 = goldq.SolverRMSProp, v.FieldByName("eta").Float(), v.FieldByName("eps").Float(), v.FieldByName("decay").Float()
+	} else if eta, eps, b1, b2, err = adamFields(c.Optimizer); err != nil {
 		return nil, nil, nil, err
 	}
 	cfg := goldq.DefaultConfig()
 	cfg.ObsDim, cfg.Hidden1, cfg.Hidden2, cfg.NActions = fc[0].Input, fc[0].Output, fc[1].Output, fc[2].Output
 	cfg.BatchSize, cfg.ReplayCapacity, cfg.Gamma = c.BatchSize, int64(hp.BufferSize), hp.Gamma
 	cfg.LR, cfg.Eps, cfg.Beta1, cfg.Beta2 = eta, eps, b1, b2
+	cfg.Loss, cfg.HuberDelta, cfg.Solver = lossKind, delta, solver
 	h, err := goldq.New(cfg)
 	if err != nil {
 		return nil, nil, nil, err

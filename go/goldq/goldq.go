@@ -27,6 +27,11 @@ const (
 	NetTarget = int(C.GOLDQ_NET_TARGET)
 	PrecFP32  = int(C.GOLDQ_PREC_FP32)
 	PrecBF16  = int(C.GOLDQ_PREC_BF16)
+
+	LossMSE         = int(C.GOLDQ_LOSS_MSE)
+	LossPseudoHuber = int(C.GOLDQ_LOSS_PSEUDO_HUBER)
+	SolverAdam      = int(C.GOLDQ_SOLVER_ADAM)
+	SolverRMSProp   = int(C.GOLDQ_SOLVER_RMSPROP)
 )
 
 // ErrNotReady is returned by Learn when the replay holds fewer events than the
@@ -42,6 +47,8 @@ type Config struct {
 	Gamma                              float32
 	LR, Beta1, Beta2, Eps              float64
 	Precision, Path, Device, NReplicas int
+	Loss, Solver                       int     // GOLDQ_LOSS_* / GOLDQ_SOLVER_*; RMSProp reads LR, Beta2 (= rho), Eps
+	HuberDelta                         float32 // PseudoHuberLoss.Delta
 }
 
 // DefaultConfig returns gold's defaults (CartPole shape, B=20, gamma .95, Adam 5e-4).
@@ -53,6 +60,7 @@ func DefaultConfig() Config {
 		BatchSize: int(c.batch_size), GlobalBatch: int(c.global_batch), ReplayCapacity: int64(c.replay_capacity),
 		Gamma: float32(c.gamma), LR: float64(c.lr), Beta1: float64(c.beta1), Beta2: float64(c.beta2), Eps: float64(c.eps),
 		Precision: int(c.precision), Path: int(c.path), Device: int(c.device), NReplicas: int(c.n_replicas),
+		Loss: int(c.loss), Solver: int(c.solver), HuberDelta: float32(c.huber_delta),
 	}
 }
 
@@ -75,6 +83,7 @@ func New(cfg Config) (*Handle, error) {
 	c.gamma = C.float(cfg.Gamma)
 	c.lr, c.beta1, c.beta2, c.eps = C.double(cfg.LR), C.double(cfg.Beta1), C.double(cfg.Beta2), C.double(cfg.Eps)
 	c.precision, c.path, c.device, c.n_replicas = C.int32_t(cfg.Precision), C.int32_t(cfg.Path), C.int32_t(cfg.Device), C.int32_t(cfg.NReplicas)
+	c.loss, c.solver, c.huber_delta = C.int32_t(cfg.Loss), C.int32_t(cfg.Solver), C.float(cfg.HuberDelta)
 	h := C.goldq_create(&c)
 	if h == nil {
 		return nil, fmt.Errorf("goldq_create: %s", C.GoString(C.goldq_last_error(nil)))

@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libgoldq.so")
 
 OK, EINVAL, ECUDA, ENOTREADY, EUNSUPPORTED, ENCCL = 0, -1, -2, -3, -4, -5
 NET_ONLINE, NET_TARGET = 0, 1
-LOSS_MSE = 0
+LOSS_MSE, LOSS_PSEUDO_HUBER = 0, 1
+SOLVER_ADAM, SOLVER_RMSPROP = 0, 1
 PREC_FP32, PREC_BF16 = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_NARROW, PATH_WIDE = 0, 1, 2, 3
 DBG_Q_ONLINE, DBG_Q_TARGET, DBG_TD, DBG_GRADS, DBG_INDICES, DBG_BATCH_S, DBG_BATCH_A = range(7)
@@ -37,10 +38,10 @@ class GoldqConfig(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("obs_dim", C.c_int32), ("hidden1", C.c_int32),
         ("hidden2", C.c_int32), ("n_actions", C.c_int32), ("batch_size", C.c_int32),
-        ("global_batch", C.c_int32), ("replay_capacity", C.c_int64), ("gamma", C.c_float),
+        ("global_batch", C.c_int32), ("replay_capacity", C.c_int64), ("gamma", C.c_float), ("huber_delta", C.c_float),
         ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
         ("loss", C.c_int32), ("precision", C.c_int32), ("path", C.c_int32), ("device", C.c_int32),
-        ("n_replicas", C.c_int32), ("reserved0", C.c_int32), ("stream", C.c_void_p),
+        ("n_replicas", C.c_int32), ("solver", C.c_int32), ("stream", C.c_void_p),
     ]
 
 

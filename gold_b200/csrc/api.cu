@@ -212,7 +212,23 @@ StepScalars step_scalars(const goldq_t *h, int rows_global)
     s.gamma = h->cfg.gamma;
     s.count = (float)((int64_t)rows_global * h->dims.A);
     s.inv_count = 1.0f / s.count;
+    s.loss_kind = h->cfg.loss == GOLDQ_LOSS_PSEUDO_HUBER ? 1 : 0;
+    s.delta = h->cfg.huber_delta > 0.f ? h->cfg.huber_delta : 1.0f;
+    s.delta2 = s.delta * s.delta;      // Square of the float32 scalar (loss.go:139)
     return s;
+}
+
+// generic path: one solver step on the flat gradient (h->iter already counts this step)
+void generic_solver_step(goldq_t *h, const StepDev *step)
+{
+    if (h->cfg.solver == GOLDQ_SOLVER_RMSPROP) {
+        // float32(s.decay), float32(1.0 - s.decay), float32(s.eps), float32(-s.eta)  (solvers.go:286-293);
+        // the cache lives in `v` (goldq_get/set_adam_state: m unused, v = cache)
+        launch_rmsprop(h->theta, h->flat, h->v, h->P, (float)h->cfg.beta2, (float)(1.0 - h->cfg.beta2), (float)h->cfg.eps,
+                       (float)(-h->cfg.lr), h->st);
+        return;
+    }
+    launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), step, h->st);
 }
 
 int ensure_generic(goldq_t *h, int rows)
@@ -313,7 +329,7 @@ int learn_generic(goldq_t *h, const int32_t *idx_dev, const StepDev *step)
     rc = allreduce_flat(h);
     if (rc) return rc;
     h->iter += 1;
-    launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), step, h->st);
+    generic_solver_step(h, step);
     h->launches += 1;
     CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
     return check_launch(h, "learn_generic");
@@ -623,7 +639,9 @@ int goldq_default_config(goldq_config_t *c)
     c->beta1 = 0.9;       // solvers.go:425-426
     c->beta2 = 0.999;
     c->eps = 1e-8;
+    c->huber_delta = 1.0f; // loss.go:102-104
     c->loss = GOLDQ_LOSS_MSE;
+    c->solver = GOLDQ_SOLVER_ADAM;
     c->precision = GOLDQ_PREC_FP32;
     c->path = GOLDQ_PATH_AUTO;
     c->device = 0;
@@ -643,7 +661,14 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
         fail(nullptr, GOLDQ_EINVAL, "dimensions, batch_size, replay_capacity and n_replicas must be >= 1");
         return nullptr;
     }
-    if (cfg->loss != GOLDQ_LOSS_MSE) { fail(nullptr, GOLDQ_EUNSUPPORTED, "only model.MSE is implemented"); return nullptr; }
+    if (cfg->loss != GOLDQ_LOSS_MSE && cfg->loss != GOLDQ_LOSS_PSEUDO_HUBER) {
+        fail(nullptr, GOLDQ_EUNSUPPORTED, "loss: only model.MSE and model.PseudoHuber are implemented");
+        return nullptr;
+    }
+    if (cfg->solver != GOLDQ_SOLVER_ADAM && cfg->solver != GOLDQ_SOLVER_RMSPROP) {
+        fail(nullptr, GOLDQ_EUNSUPPORTED, "solver: only AdamSolver and RMSPropSolver are implemented");
+        return nullptr;
+    }
     if (cfg->replay_capacity > 0x7fffffffLL) { fail(nullptr, GOLDQ_EINVAL, "replay_capacity must fit int32 indices"); return nullptr; }
 
     goldq_t *h = new goldq();
@@ -675,7 +700,8 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
     // path selection
     int path = cfg->path;
     if (path == GOLDQ_PATH_AUTO) {
-        if (cfg->precision == GOLDQ_PREC_BF16) path = GOLDQ_PATH_WIDE;
+        if (cfg->solver == GOLDQ_SOLVER_RMSPROP) path = GOLDQ_PATH_GENERIC;      // the fused kernels carry Adam
+        else if (cfg->precision == GOLDQ_PREC_BF16) path = GOLDQ_PATH_WIDE;
         else if (narrow_supported(h->dims)) path = GOLDQ_PATH_NARROW;
         else path = GOLDQ_PATH_GENERIC;
     }
@@ -687,6 +713,8 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
         return bail("wide (tcgen05) path requires GOLDQ_PREC_BF16");
     if (path == GOLDQ_PATH_GENERIC && cfg->precision != GOLDQ_PREC_FP32)
         return bail("generic path computes in fp32");
+    if (cfg->solver == GOLDQ_SOLVER_RMSPROP && path != GOLDQ_PATH_GENERIC)
+        return bail("RMSPropSolver is implemented on the generic path only (fp32)");
     if (h->R > 1 && path != GOLDQ_PATH_NARROW)
         return bail("n_replicas > 1 is implemented on the narrow path only");
     h->path = path;
@@ -1198,8 +1226,7 @@ int goldq_fit_batch(goldq_t *h, int64_t n, const float *x, const float *y)
     CK(h, cudaMemcpyAsync(h->bs, x, (size_t)n * d.D * 4, cudaMemcpyHostToDevice, h->st));
     CK(h, cudaMemcpyAsync(h->ylab, y, (size_t)n * d.A * 4, cudaMemcpyHostToDevice, h->st));
     generic_forward(h, h->theta, h->bs, (int)n, h->h1, h->mk1, h->h2, h->mk2, h->q);
-    StepScalars sc;
-    sc.gamma = h->cfg.gamma;
+    StepScalars sc = step_scalars(h, 1);     // loss kind / delta; the divisor is this call's n * A
     sc.count = (float)(n * d.A);
     sc.inv_count = 1.0f / sc.count;
     int nlp = 0;
@@ -1209,7 +1236,7 @@ int goldq_fit_batch(goldq_t *h, int64_t n, const float *x, const float *y)
     launch_reduce_slices(h->gslice, h->P, h->nsplit, h->P, h->loss_part, nlp, sc.count, h->flat,
                          h->st);
     h->iter += 1;
-    launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), nullptr, h->st);
+    generic_solver_step(h, nullptr);
     h->launches += 2;
     CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
     if (h->wide) {

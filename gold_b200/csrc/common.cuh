@@ -66,7 +66,26 @@ struct StepScalars {
     float gamma;
     float count;      // float32(B_global * A)   (Mean's divisor)
     float inv_count;  // float32(1) / count
+    int loss_kind;    // 0: MSE (goro loss.go:28-42), 1: pseudo-Huber (loss.go:96-151, reduced by Mean)
+    float delta;      // pseudo-Huber delta
+    float delta2;     // delta * delta
 };
+
+// One residual d = q - y: its term of the loss sum and dLoss/dq (Mean's 1/count folded in).
+//   MSE           term = d^2                         dq = (d * 2) * (1/count)      (reference op order)
+//   pseudo-Huber  term = delta^2 (sqrt(1+(d/delta)^2) - 1)   dq = d / sqrt(1+(d/delta)^2) * (1/count)
+__device__ __forceinline__ void residual_loss(const StepScalars &sc, float d, float &term, float &dq)
+{
+    if (sc.loss_kind == 0) {
+        term = __fmul_rn(d, d);
+        dq = __fmul_rn(__fmul_rn(d, 2.f), sc.inv_count);
+    } else {
+        const float x = __fdiv_rn(d, sc.delta);
+        const float s = __fsqrt_rn(__fadd_rn(1.f, __fmul_rn(x, x)));
+        term = __fmul_rn(sc.delta2, __fsub_rn(s, 1.f));
+        dq = __fmul_rn(__fdiv_rn(d, s), sc.inv_count);
+    }
+}
 
 // ---- generic path (kernels_generic.cu) -----------------------------------
 void launch_sample_indices(int32_t *idx, int B, int64_t len, uint64_t seed, const StepDev *step,
@@ -96,6 +115,8 @@ void launch_reduce_slices(const float *gslice, int64_t slice_stride, int nsplit,
 // Fused Adam incl. the reference's double update; replicas laid out [R][P].
 void launch_adam(float *w, const float *g, float *m, float *v, int64_t n, AdamConsts c,
                  const StepDev *step, cudaStream_t st);
+void launch_rmsprop(float *w, const float *g, float *cache, int64_t n, float decay, float omdecay, float eps,
+                    float neg_eta, cudaStream_t st);
 void launch_argmax_rows(const float *q, int n, int A, int32_t *out, cudaStream_t st);
 
 // ---- narrow fused path (kernels_narrow.cu) --------------------------------

@@ -210,9 +210,10 @@ td_kernel(const float *__restrict__ q, const float *__restrict__ qt,
         td[b] = t;
         int a = act[b];
         float d = __fsub_rn(q[(int64_t)b * A + a], t);
-        sq = __fmul_rn(d, d);
+        float dqa;
+        residual_loss(sc, d, sq, dqa);
         for (int j = 0; j < A; j++) dq[(int64_t)b * A + j] = 0.f;
-        dq[(int64_t)b * A + a] = __fmul_rn(__fmul_rn(d, 2.f), sc.inv_count);
+        dq[(int64_t)b * A + a] = dqa;
     }
     float s = block_sum_256(sq, sh);
     if (threadIdx.x == 0) loss_part[blockIdx.x] = s;
@@ -236,8 +237,9 @@ label_loss_kernel(const float *__restrict__ q, const float *__restrict__ y, int 
     float sq = 0.f;
     if (i < total) {
         float d = __fsub_rn(q[i], y[i]);
-        sq = __fmul_rn(d, d);
-        dq[i] = __fmul_rn(__fmul_rn(d, 2.f), sc.inv_count);
+        float dqi;
+        residual_loss(sc, d, sq, dqi);
+        dq[i] = dqi;
     }
     float s = block_sum_256(sq, sh);
     if (threadIdx.x == 0) loss_part[blockIdx.x] = s;
@@ -474,6 +476,28 @@ void launch_adam(float *w, const float *g, float *m, float *v, int64_t n, AdamCo
                  const StepDev *step, cudaStream_t st)
 {
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, m, v, n, c, step);
+}
+
+// RMSPropSolver.Step, float32 branch, op for op (V/gorgonia.org/gorgonia/solvers.go:273-335): Square(g); cw *= decay;
+// g2 *= omdecay; cw += g2; upd = cw + eps; InvSqrt(upd) = 1/sqrt (tensor generic_unary.go:492-496); g *= -eta;
+// upd *= g; w += upd.  One rounding per op, no FMA.
+__global__ void __launch_bounds__(256)
+rmsprop_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restrict__ cache, int64_t n, float decay,
+               float omdecay, float eps, float neg_eta)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i];
+    const float c = __fadd_rn(__fmul_rn(cache[i], decay), __fmul_rn(__fmul_rn(gi, gi), omdecay));
+    cache[i] = c;
+    const float inv = __fdiv_rn(1.f, __fsqrt_rn(__fadd_rn(c, eps)));
+    w[i] = __fadd_rn(w[i], __fmul_rn(inv, __fmul_rn(gi, neg_eta)));
+}
+
+void launch_rmsprop(float *w, const float *g, float *cache, int64_t n, float decay, float omdecay, float eps,
+                    float neg_eta, cudaStream_t st)
+{
+    rmsprop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, cache, n, decay, omdecay, eps, neg_eta);
 }
 
 __global__ void argmax_rows_kernel(const float *__restrict__ q, int n, int A,

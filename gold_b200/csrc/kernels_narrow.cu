@@ -234,8 +234,10 @@ narrow_learn_kernel(NarrowArgs p)
             if (!dn[r]) t = __fadd_rn(rew[r], __fmul_rn(p.sc.gamma, f));   // agent.go:149
             const float qa = __shfl_sync(FULL, q[r], act[r]);
             const float d = __fsub_rn(qa, t);
-            dqv[r] = live[r] ? __fmul_rn(__fmul_rn(d, 2.f), p.sc.inv_count) : 0.f;
-            if (live[r]) lossacc = __fadd_rn(lossacc, __fmul_rn(d, d));
+            float term, dqr;
+            residual_loss(p.sc, d, term, dqr);
+            dqv[r] = live[r] ? dqr : 0.f;
+            if (live[r]) lossacc = __fadd_rn(lossacc, term);
             if (p.dbg_q && live[r]) {
                 const int b = b0 + r * total_warps;
                 if (inA) {

@@ -888,8 +888,7 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
             }
             td_out[b] = t;
             const float dd = __fsub_rn(qa, t);
-            dqv = __fmul_rn(__fmul_rn(dd, 2.f), sc.inv_count);
-            sq = __fmul_rn(dd, dd);
+            residual_loss(sc, dd, sq, dqv);
             const __nv_bfloat16 v = __float2bfloat16_rn(dqv), z = __float2bfloat16_rn(0.f);
             for (int i = 0; i < 32; i++) dqT[(int64_t)i * B + b] = (i == a) ? v : z;
         }

@@ -194,7 +194,26 @@ class AdamSolver:
         self.eta, self.eps, self.beta1, self.beta2 = learn_rate, eps, beta1, beta2
 
 
+class RMSPropSolver:
+    """gorgonia.RMSPropSolver's settable fields (solvers.go:216-246): the solver of gold's Atari policy
+    config (policy.go:41-47).  Runs on the generic CUDA path."""
+
+    def __init__(self, learn_rate=0.001, eps=1e-8, rho=0.999):
+        self.eta, self.eps, self.decay = learn_rate, eps, rho
+
+
 MSE = "mse"  # modelv1.MSE (goro model/loss.go:22)
+
+
+class PseudoHuberLoss:
+    """model.PseudoHuberLoss (goro model/loss.go:90-111).  Reduced by Mean on the device; the reference's
+    own Compute ends in Sum(.., 1) and cannot be differentiated (loss.go:94 "!blocked")."""
+
+    def __init__(self, delta=1.0):
+        self.delta = float(delta)
+
+
+PSEUDO_HUBER = PseudoHuberLoss(1.0)  # model.PseudoHuber (loss.go:101-104)
 
 
 class FC:
@@ -309,14 +328,22 @@ class Agent:
         if env is None:
             raise ValueError("environment cannot be nil")            # agent.go:96-98
         hp, pc = c.hyperparameters, c.policy_config
-        if not isinstance(pc.optimizer, AdamSolver) or pc.loss != MSE:
-            raise ValueError("the CUDA path implements model.MSE with gorgonia.AdamSolver; no CPU fallback exists")
+        if pc.loss != MSE and not isinstance(pc.loss, PseudoHuberLoss):
+            raise ValueError("the CUDA path implements model.MSE and model.PseudoHuber; no CPU fallback exists")
+        if isinstance(pc.optimizer, AdamSolver):
+            solver = dict(solver=G.SOLVER_ADAM, lr=pc.optimizer.eta, beta1=pc.optimizer.beta1, beta2=pc.optimizer.beta2,
+                          eps=pc.optimizer.eps)
+        elif isinstance(pc.optimizer, RMSPropSolver):
+            solver = dict(solver=G.SOLVER_RMSPROP, lr=pc.optimizer.eta, beta2=pc.optimizer.decay, eps=pc.optimizer.eps)
+        else:
+            raise ValueError("the CUDA path implements gorgonia.AdamSolver and RMSPropSolver; no CPU fallback exists")
+        loss = (dict(loss=G.LOSS_PSEUDO_HUBER, huber_delta=pc.loss.delta) if isinstance(pc.loss, PseudoHuberLoss)
+                else dict(loss=G.LOSS_MSE))
         dims = _dims_from_layers(pc.layer_builder(env.observation_space_shape()[0], env.n_actions))
         self._h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3],
                            batch_size=pc.batch_size, replay_capacity=hp.buffer_size, gamma=hp.gamma,
-                           lr=pc.optimizer.eta, beta1=pc.optimizer.beta1, beta2=pc.optimizer.beta2,
-                           eps=pc.optimizer.eps, device=c.device,
-                           precision=G.PREC_BF16 if c.precision == "bf16" else G.PREC_FP32)
+                           device=c.device, precision=G.PREC_BF16 if c.precision == "bf16" else G.PREC_FP32,
+                           **solver, **loss)
         # two independently initialised networks, GlorotN(1) (agent.go:101-109; goro fc.go:76-81);
         # the target is first synced when steps % UpdateTargetSteps == 0
         seed = c.seed if c.seed is not None else random.randrange(1 << 30)

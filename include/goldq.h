@@ -40,6 +40,16 @@ extern "C" {
 
 /* loss (V/github.com/aunum/goro/pkg/v1/model/loss.go) */
 #define GOLDQ_LOSS_MSE 0    /* model.MSE, loss.go:22-42 */
+#define GOLDQ_LOSS_PSEUDO_HUBER 1 /* model.PseudoHuber, loss.go:90-151: delta^2 (sqrt(1 + ((q-y)/delta)^2) - 1), reduced
+                                   * by Mean like MSE.  The reference version ends in Sum(.., 1), a vector, which
+                                   * gorgonia.Grad rejects (the "!blocked" note at loss.go:94), so there is no
+                                   * executable reference behaviour to match: this is the loss as it is meant. */
+
+/* solver (V/gorgonia.org/gorgonia/solvers.go) */
+#define GOLDQ_SOLVER_ADAM 0    /* AdamSolver.Step incl. v0.9.9's double weight update, solvers.go:440-617 */
+#define GOLDQ_SOLVER_RMSPROP 1 /* RMSPropSolver.Step, solvers.go:249-395 (gold's Atari config, policy.go:41-47):
+                                * c = c*rho + (1-rho)*g^2; w += (1/sqrt(c+eps)) * (g * -eta).  Hyper-parameters:
+                                * lr = eta, beta2 = rho, eps; beta1 unused.  Implemented on GOLDQ_PATH_GENERIC. */
 
 /* arithmetic of the forward/backward pass */
 #define GOLDQ_PREC_FP32 0   /* reference arithmetic: fp32, multiply then add, k-sequential */
@@ -74,6 +84,7 @@ typedef struct goldq_config {
     int32_t global_batch;     /* rows of the whole data-parallel job; 0 = batch_size */
     int64_t replay_capacity;  /* Hyperparameters.BufferSize                   (agent.go:57,64) */
     float gamma;              /* Hyperparameters.Gamma, a float32             (agent.go:48) */
+    float huber_delta;        /* PseudoHuberLoss.Delta (loss.go:98); <= 0 means 1.0 (fills what used to be padding) */
     double lr;                /* AdamSolver.eta                               (solvers.go:400) */
     double beta1, beta2, eps; /* AdamSolver.beta1/beta2/eps                   (solvers.go:401-403) */
     int32_t loss;             /* GOLDQ_LOSS_* */
@@ -81,7 +92,7 @@ typedef struct goldq_config {
     int32_t path;             /* GOLDQ_PATH_* */
     int32_t device;           /* CUDA device ordinal */
     int32_t n_replicas;       /* >= 1: independent agents (own weights, solver state, replay) in one grid */
-    int32_t reserved0;
+    int32_t solver;           /* GOLDQ_SOLVER_* (0 = Adam, as before this field had a meaning) */
     void *stream;             /* cudaStream_t to run on, or NULL to create one */
 } goldq_config_t;
 

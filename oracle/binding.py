@@ -21,7 +21,7 @@ class OqDims(C.Structure):
 class OqCfg(C.Structure):
     _fields_ = [("dims", OqDims), ("B", C.c_int32), ("gamma", C.c_float),
                 ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
-                ("eps", C.c_double)]
+                ("eps", C.c_double), ("loss", C.c_int32), ("solver", C.c_int32), ("delta", C.c_float)]
 
 
 def build(force=False):
@@ -108,7 +108,7 @@ def adam(w, g, m, v, it, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-8):
 
 
 def learn(dims, B, theta, theta_t, m, v, it, s, a, r, s2, done, gamma=0.95, lr=5e-4,
-          beta1=0.9, beta2=0.999, eps=1e-8, dtype=np.float32, want_debug=True):
+          beta1=0.9, beta2=0.999, eps=1e-8, dtype=np.float32, want_debug=True, loss=0, solver=0, delta=1.0):
     """One Agent.Learn on a sampled batch.  theta/m/v are updated IN PLACE.
 
     `it` = solver iteration count before the step.  Returns dict with the new
@@ -126,7 +126,7 @@ def learn(dims, B, theta, theta_t, m, v, it, s, a, r, s2, done, gamma=0.95, lr=5
     r = np.ascontiguousarray(r, dtype).reshape(B)
     a = np.ascontiguousarray(a, np.int32).reshape(B)
     done = np.ascontiguousarray(done, np.uint8).reshape(B)
-    cfg = OqCfg(OqDims(D, H1, H2, A), B, gamma, lr, beta1, beta2, eps)
+    cfg = OqCfg(OqDims(D, H1, H2, A), B, gamma, lr, beta1, beta2, eps, loss, solver, delta)
     out = {}
     if want_debug:
         out["q_online"] = np.zeros((B, A), dtype)
@@ -147,7 +147,8 @@ def learn(dims, B, theta, theta_t, m, v, it, s, a, r, s2, done, gamma=0.95, lr=5
     return out
 
 
-def fit(dims, theta, m, v, it, x, y, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-8, dtype=np.float32):
+def fit(dims, theta, m, v, it, x, y, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-8, dtype=np.float32, loss=0, solver=0,
+        delta=1.0):
     """Sequential.FitBatch on explicit labels; theta/m/v updated IN PLACE."""
     D, H1, H2, A = dims
     f32 = dtype == np.float32
@@ -159,7 +160,7 @@ def fit(dims, theta, m, v, it, x, y, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-8, 
     assert y.shape[0] == n
     for arr in (theta, m, v):
         assert arr.dtype == dtype and arr.flags.c_contiguous and arr.size == P
-    cfg = OqCfg(OqDims(D, H1, H2, A), n, 0.0, lr, beta1, beta2, eps)
+    cfg = OqCfg(OqDims(D, H1, H2, A), n, 0.0, lr, beta1, beta2, eps, loss, solver, delta)
     loss = np.zeros(1, dtype)
     grads = np.zeros(P, dtype)
     itc = C.c_int64(it)

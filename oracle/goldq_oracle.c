@@ -48,6 +48,9 @@ typedef struct {
     int32_t B;
     float gamma;
     double lr, beta1, beta2, eps; /* AdamSolver keeps float64 fields (solvers.go:399-415) */
+    int32_t loss;                 /* 0: MSE (loss.go:28-42); 1: pseudo-Huber (loss.go:96-151, reduced by Mean) */
+    int32_t solver;               /* 0: AdamSolver; 1: RMSPropSolver (lr = eta, beta2 = rho, eps) */
+    float delta;                  /* PseudoHuberLoss.Delta, a float32 (loss.go:98) */
 } oq_cfg_t;
 
 typedef struct { int64_t w1, b1, w2, b2, w3, b3, total; } oq_offsets_t;

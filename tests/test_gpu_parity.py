@@ -25,7 +25,11 @@ def make_pair(dims, B, N, path=G.PATH_AUTO, capacity=None, seed_data=synth.SEED_
                  replay_capacity=cap, path=path, **kw)
     h.set_params(G.NET_ONLINE, th)
     h.set_params(G.NET_TARGET, tt)
-    o = OracleAgent(dims, B, th, tt, capacity=cap)
+    okw = dict(loss=kw.get("loss", 0), solver=kw.get("solver", 0), delta=kw.get("huber_delta", 1.0))
+    for k in ("lr", "beta2", "eps"):
+        if k in kw:
+            okw[k] = kw[k]
+    o = OracleAgent(dims, B, th, tt, capacity=cap, **okw)
     data = synth.replay(dims, N, seed=seed_data)
     h.replay_push(*data)
     o.push(*data)
@@ -49,7 +53,7 @@ def check_step(h, o, idx, step_name=""):
     gs = np.abs(out64["grads"]).max()
     np.testing.assert_allclose(g, out64["grads"], rtol=1e-5, atol=1e-6 * gs, err_msg=f"{step_name} grads")
     w = h.get_params(G.NET_ONLINE)
-    frac = assert_params_close(w, out64["theta"], out64["grads"], lr=o.lr, what=f"{step_name} params")
+    frac = assert_params_close(w, out64["theta"], out64["grads"], lr=o.bound_lr, what=f"{step_name} params")
     assert frac < 0.02
     m, v, it = h.get_adam_state()
     assert it == o.iter
@@ -99,6 +103,33 @@ def test_generic_path(dims, B):
         np.testing.assert_array_equal(h.debug_fetch(G.DBG_BATCH_S), s)
         np.testing.assert_array_equal(h.debug_fetch(G.DBG_BATCH_A), a)
     h.close()
+
+
+@pytest.mark.parametrize("path,dims,B,delta", [(G.PATH_NARROW, synth.CARTPOLE, 512, 1.0), (G.PATH_NARROW, synth.CARTPOLE, 20, 0.25),
+                                               (G.PATH_GENERIC, (5, 17, 33, 3), 37, 1.0)])
+def test_pseudo_huber_loss(path, dims, B, delta):
+    """model.PseudoHuber (goro loss.go:90-151, reduced by Mean) on the fp32 paths: same bars as MSE."""
+    N = 4 * B
+    h, o = make_pair(dims, B, N, path=path, loss=G.LOSS_PSEUDO_HUBER, huber_delta=delta)
+    assert h.path == path
+    for step in range(2):
+        check_step(h, o, synth.sample_indices(N, B, step), f"huber step{step}")
+    h.close()
+
+
+@pytest.mark.parametrize("dims,B", [(synth.CARTPOLE, 20), ((5, 17, 33, 3), 37)])
+def test_rmsprop_solver_generic_path(dims, B):
+    """gorgonia.RMSPropSolver (solvers.go:249-335) on the generic path; PATH_AUTO must route there."""
+    N = 4 * B
+    h, o = make_pair(dims, B, N, solver=G.SOLVER_RMSPROP, lr=1e-3, beta2=0.999, eps=1e-8)
+    assert h.path == G.PATH_GENERIC
+    for step in range(3):
+        out = check_step(h, o, synth.sample_indices(N, B, step), f"rmsprop step{step}")
+    m, cache, _ = h.get_adam_state()
+    assert not m.any() and cache.any()
+    h.close()
+    with pytest.raises(G.GoldqError):          # the fused kernels carry Adam: asking for them with RMSProp is an error
+        G.Handle(batch_size=B, replay_capacity=N, path=G.PATH_NARROW, solver=G.SOLVER_RMSPROP)
 
 
 def test_free_running_without_resync():

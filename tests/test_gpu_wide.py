@@ -19,13 +19,14 @@ from util import OracleAgent
 pytestmark = pytest.mark.gpu
 
 
-def make(dims, B, N):
+def make(dims, B, N, huber_delta=None):
     th = synth.glorot_params(dims, 1); tt = synth.glorot_params(dims, 2)
+    kw = {} if huber_delta is None else dict(loss=G.LOSS_PSEUDO_HUBER, huber_delta=huber_delta)
     h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3], batch_size=B,
-                 replay_capacity=N, precision=G.PREC_BF16)
+                 replay_capacity=N, precision=G.PREC_BF16, **kw)
     assert h.path == G.PATH_WIDE
     h.set_params(G.NET_ONLINE, th); h.set_params(G.NET_TARGET, tt)
-    o = OracleAgent(dims, B, th, tt)
+    o = OracleAgent(dims, B, th, tt, loss=0 if huber_delta is None else 1, delta=huber_delta or 1.0)
     data = synth.replay(dims, N)
     h.replay_push(*data); o.push(*data)
     h.debug_enable(True)
@@ -80,6 +81,16 @@ def test_wide_bf16_learn_step(dims, B):
         check(h, o, synth.sample_indices(N, B, step))
         if step == 0:
             h.sync_target(); o.sync_target()
+    h.close()
+
+
+def test_wide_bf16_pseudo_huber():
+    """model.PseudoHuber on the tcgen05 path: the same stated bf16 tolerances as MSE."""
+    dims, B = (64, 256, 128, 6), 256
+    N = 1024
+    h, o = make(dims, B, N, huber_delta=0.5)
+    for step in range(2):
+        check(h, o, synth.sample_indices(N, B, step))
     h.close()
 
 

@@ -12,7 +12,7 @@ from oracle import binding as O
 from util import assert_params_close
 
 
-def _torch_step(dims, th, tt, s, a, r, s2, done, gamma):
+def _torch_step(dims, th, tt, s, a, r, s2, done, gamma, huber_delta=None):
     D, H1, H2, A = dims
     off = synth.offsets(dims)
 
@@ -38,7 +38,10 @@ def _torch_step(dims, th, tt, s, a, r, s2, done, gamma):
         y = fwd(th_t, S).clone()
         y[torch.arange(len(a)), torch.tensor(a, dtype=torch.long)] = td
     q = fwd(th_t, S)
-    loss = ((q - y) ** 2).mean()
+    if huber_delta is None:
+        loss = ((q - y) ** 2).mean()
+    else:           # pseudo-Huber as goro defines it (loss.go:113-145), reduced by the mean
+        loss = (huber_delta ** 2 * (torch.sqrt(1 + ((q - y) / huber_delta) ** 2) - 1)).mean()
     loss.backward()
     return q.detach().numpy(), td.numpy(), loss.item(), th_t.grad.numpy()
 
@@ -78,3 +81,40 @@ def test_oracle_f32_within_budget_of_f64(dims, B):
     np.testing.assert_allclose(o32["grads"], o64["grads"], rtol=1e-4, atol=1e-5 * gscale)
     frac = assert_params_close(w32, w64, o64["grads"])
     assert frac < 0.01
+
+
+@pytest.mark.parametrize("delta", [1.0, 0.25])
+def test_oracle_pseudo_huber_matches_autograd(delta):
+    dims, B = (16, 48, 32, 6), 96
+    th = synth.glorot_params(dims, 1).astype(np.float64)
+    tt = synth.glorot_params(dims, 2).astype(np.float64)
+    s, a, r, s2, done = synth.replay(dims, B, p_done=0.2)
+    P = synth.nparams(dims)
+    out = O.learn(dims, B, th.copy(), tt, np.zeros(P), np.zeros(P), 0, s.astype(np.float64), a, r.astype(np.float64),
+                  s2.astype(np.float64), done, gamma=0.95, dtype=np.float64, loss=1, delta=delta)
+    _, _, loss, grads = _torch_step(dims, th, tt, s, a, r, s2, done, float(np.float32(0.95)), huber_delta=delta)
+    assert abs(out["loss"] - loss) <= 1e-12 * abs(loss)
+    np.testing.assert_allclose(out["grads"], grads, rtol=1e-10, atol=1e-14)
+
+
+def test_oracle_rmsprop_is_the_reference_op_sequence():
+    """RMSPropSolver.Step, float32 branch (gorgonia solvers.go:273-335), replayed with numpy float32
+    scalars in the same order: Square, cw*=decay, g2*=omdecay, cw+=g2, +eps, 1/sqrt, g*=-eta, *, w+=."""
+    dims, B = synth.CARTPOLE, 20
+    th = synth.glorot_params(dims, 1); tt = synth.glorot_params(dims, 2)
+    s, a, r, s2, done = synth.replay(dims, B)
+    P = synth.nparams(dims)
+    f = np.float32
+    eta, rho, eps = 1e-3, 0.999, 1e-8
+    decay, omdecay, e32, step = f(rho), f(1.0 - rho), f(eps), f(-eta)
+    w = th.copy(); m = np.zeros(P, f); cache = np.zeros(P, f)
+    w_ref, c_ref = th.copy(), np.zeros(P, f)
+    for it in range(3):
+        out = O.learn(dims, B, w, tt, m, cache, it, s, a, r, s2, done, lr=eta, beta2=rho, eps=eps, solver=1)
+        g = out["grads"].astype(f)
+        c_ref = (c_ref * decay + (g * g) * omdecay).astype(f)
+        upd = (f(1) / np.sqrt((c_ref + e32).astype(f), dtype=f)).astype(f)
+        w_ref = (w_ref + upd * (g * step).astype(f)).astype(f)
+        np.testing.assert_array_equal(cache, c_ref)
+        np.testing.assert_array_equal(w, w_ref)
+    assert not m.any()                        # RMSProp keeps one cache; the Adam first moment stays untouched

@@ -40,10 +40,15 @@ class OracleAgent:
     Holds the reference-arithmetic state (fp32) and an fp64 shadow used only to
     budget the error of order-dependent sums (loss, gradients)."""
 
-    def __init__(self, dims, B, theta, theta_t, gamma=0.95, lr=5e-4, capacity=None):
+    def __init__(self, dims, B, theta, theta_t, gamma=0.95, lr=5e-4, capacity=None, loss=0, solver=0, delta=1.0,
+                 beta2=0.999, eps=1e-8):
         from oracle import binding as O
         self.O = O
         self.dims, self.B, self.gamma, self.lr = dims, B, gamma, lr
+        self.opt = dict(loss=loss, solver=solver, delta=delta, beta2=beta2, eps=eps)
+        # bound on one solver step for ill-conditioned elements: Adam moves <= 2*lr, RMSProp's first steps
+        # are -lr*sign(g)/sqrt(1-rho)
+        self.bound_lr = lr if solver == 0 else lr / np.sqrt(1.0 - beta2)
         P = O.nparams(*dims)
         self.theta = np.array(theta, np.float32).copy()
         self.theta_t = np.array(theta_t, np.float32).copy()
@@ -76,10 +81,10 @@ class OracleAgent:
             th64 = self.theta.astype(np.float64); m64 = self.m.astype(np.float64); v64 = self.v.astype(np.float64)
             out64 = self.O.learn(self.dims, self.B, th64, self.theta_t.astype(np.float64), m64, v64, self.iter,
                                  s.astype(np.float64), a, r.astype(np.float64), s2.astype(np.float64), done,
-                                 gamma=self.gamma, lr=self.lr, dtype=np.float64)
+                                 gamma=self.gamma, lr=self.lr, dtype=np.float64, **self.opt)
             out64["theta"] = th64
         out = self.O.learn(self.dims, self.B, self.theta, self.theta_t, self.m, self.v, self.iter,
-                           s, a, r, s2, done, gamma=self.gamma, lr=self.lr)
+                           s, a, r, s2, done, gamma=self.gamma, lr=self.lr, **self.opt)
         self.iter = out["iter"]
         out["done"] = done
         return out, out64
