@@ -157,6 +157,12 @@ func (x *Handle) GreedyAction(in []float32) (int, error) {
 	rc := C.goldq_greedy_action(x.h, 0, 1, f32(in), &a)
 	return int(a), x.err(rc)
 }
+// EpsilonGreedyAction is Agent.Action for n states at once (vectorised environments).
+func (x *Handle) EpsilonGreedyAction(n int, in []float32, epsilon float32, seed uint64) ([]int32, error) {
+	a := make([]int32, n)
+	rc := C.goldq_epsilon_greedy_action(x.h, 0, C.int64_t(n), f32(in), C.float(epsilon), C.uint64_t(seed), (*C.int32_t)(unsafe.Pointer(&a[0])))
+	return a, x.err(rc)
+}
 func (x *Handle) FitBatch(n int, in, y []float32) error {
 	return x.err(C.goldq_fit_batch(x.h, C.int64_t(n), f32(in), f32(y)))
 }

@@ -27,7 +27,8 @@ SYMBOLS = [
     "goldq_get_params", "goldq_set_adam_state", "goldq_get_adam_state", "goldq_replay_push",
     "goldq_replay_len", "goldq_replay_push_wait", "goldq_host_alloc", "goldq_host_free",
     "goldq_learn", "goldq_learn_device_indices", "goldq_learn_many", "goldq_sampler_indices", "goldq_sync_target",
-    "goldq_last_loss", "goldq_predict", "goldq_greedy_action", "goldq_fit_batch",
+    "goldq_last_loss", "goldq_predict", "goldq_greedy_action", "goldq_epsilon_greedy_action", "goldq_explore_plan",
+    "goldq_fit_batch",
     "goldq_dp_unique_id", "goldq_dp_init", "goldq_dp_mode", "goldq_sync", "goldq_stream", "goldq_launch_count",
     "goldq_debug_enable", "goldq_debug_fetch", "goldq_timer_start", "goldq_timer_stop",
     "goldq_selftest_umma", "goldq_step_breakdown",
@@ -90,6 +91,8 @@ def lib():
         "goldq_last_loss": (C.c_int, [vp, fp]),
         "goldq_predict": (C.c_int, [vp, C.c_int, C.c_int, i64, fp, fp]),
         "goldq_greedy_action": (C.c_int, [vp, C.c_int, i64, fp, ip]),
+        "goldq_epsilon_greedy_action": (C.c_int, [vp, C.c_int, i64, fp, C.c_float, u64, ip]),
+        "goldq_explore_plan": (C.c_int, [i64, i32, C.c_float, u64, up, ip]),
         "goldq_fit_batch": (C.c_int, [vp, i64, fp, fp]),
         "goldq_dp_unique_id": (C.c_int, [up]),
         "goldq_dp_init": (C.c_int, [vp, up, C.c_int, C.c_int]),
@@ -126,6 +129,17 @@ def default_config(**kw):
             raise TypeError(f"unknown config field {k}")
         setattr(cfg, k, v)
     return cfg
+
+
+def explore_plan(n, n_actions, epsilon, seed):
+    """Host mirror of the device's epsilon-greedy draws: (explore[n] bool, random_action[n] int32)."""
+    ex = np.empty(n, np.uint8)
+    ra = np.empty(n, np.int32)
+    rc = lib().goldq_explore_plan(n, n_actions, epsilon, seed, ex.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                  ra.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc:
+        raise GoldqError(rc, "explore_plan: bad argument")
+    return ex.astype(bool), ra
 
 
 def sampler_indices(length, batch, seed, replica=0):
@@ -265,6 +279,14 @@ class Handle:
         a = np.empty(x.shape[0], np.int32)
         self._ck(self._L.goldq_greedy_action(self._h, replica, x.shape[0], _f(x),
                                              a.ctypes.data_as(C.POINTER(C.c_int32))))
+        return a
+
+    def epsilon_greedy_action(self, x, epsilon, seed, replica=0):
+        """Agent.Action for a batch of states (vectorised environments)."""
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, self.D)
+        a = np.empty(x.shape[0], np.int32)
+        self._ck(self._L.goldq_epsilon_greedy_action(self._h, replica, x.shape[0], _f(x), epsilon, seed,
+                                                     a.ctypes.data_as(C.POINTER(C.c_int32))))
         return a
 
     def fit_batch(self, x, y):

@@ -1211,6 +1211,32 @@ int goldq_greedy_action(goldq_t *h, int replica, int64_t n, const float *x, int3
     return check_launch(h, "greedy_action");
 }
 
+int goldq_epsilon_greedy_action(goldq_t *h, int replica, int64_t n, const float *x, float epsilon, uint64_t seed,
+                                int32_t *action)
+{
+    if (!h || !x || !action || !(epsilon >= 0.f && epsilon <= 1.f))
+        return fail(h, GOLDQ_EINVAL, "epsilon_greedy_action: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    int rc = predict_dev(h, GOLDQ_NET_ONLINE, replica, n, x);
+    if (rc) return rc;
+    launch_eps_greedy_rows(h->pq, (int)n, h->dims.A, epsilon, seed, h->pact, h->st);
+    h->launches += 1;
+    CK(h, cudaMemcpyAsync(action, h->pact, (size_t)n * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    return check_launch(h, "epsilon_greedy_action");
+}
+
+int goldq_explore_plan(int64_t n, int32_t n_actions, float epsilon, uint64_t seed, uint8_t *explore, int32_t *random_action)
+{
+    if (n < 0 || n_actions < 1 || !explore || !random_action) return GOLDQ_EINVAL;
+    for (int64_t i = 0; i < n; i++) {
+        int ra;
+        explore[i] = explore_draw((uint32_t)i, seed, epsilon, n_actions, &ra) ? 1 : 0;
+        random_action[i] = ra;
+    }
+    return GOLDQ_OK;
+}
+
 int goldq_fit_batch(goldq_t *h, int64_t n, const float *x, const float *y)
 {
     if (!h || !x || !y) return fail(h, GOLDQ_EINVAL, "fit_batch: bad argument");

@@ -118,6 +118,7 @@ void launch_adam(float *w, const float *g, float *m, float *v, int64_t n, AdamCo
 void launch_rmsprop(float *w, const float *g, float *cache, int64_t n, float decay, float omdecay, float eps,
                     float neg_eta, cudaStream_t st);
 void launch_argmax_rows(const float *q, int n, int A, int32_t *out, cudaStream_t st);
+void launch_eps_greedy_rows(const float *q, int n, int A, float epsilon, uint64_t seed, int32_t *out, cudaStream_t st);
 
 // ---- narrow fused path (kernels_narrow.cu) --------------------------------
 #define NARROW_GROUP 8        // CTAs summed by one level-1 leader

@@ -512,4 +512,19 @@ void launch_argmax_rows(const float *q, int n, int A, int32_t *out, cudaStream_t
     argmax_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(q, n, A, out);
 }
 
+// batched epsilon-greedy: first-argmax of the online Q unless row i's draw explores
+__global__ void eps_greedy_rows_kernel(const float *__restrict__ q, int n, int A, float epsilon, uint64_t seed,
+                                       int32_t *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int ra;
+    out[i] = explore_draw((uint32_t)i, seed, epsilon, A, &ra) ? ra : first_argmax(q + (int64_t)i * A, A);
+}
+
+void launch_eps_greedy_rows(const float *q, int n, int A, float epsilon, uint64_t seed, int32_t *out, cudaStream_t st)
+{
+    eps_greedy_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(q, n, A, epsilon, seed, out);
+}
+
 }  // namespace gq

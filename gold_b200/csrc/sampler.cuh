@@ -45,4 +45,16 @@ __host__ __device__ inline uint32_t perm_index(uint32_t i, uint32_t n, uint64_t 
     return x;
 }
 
+// Epsilon-greedy draw for row i of a batched Action call (reference: agent.go:193-205 draws
+// num.RandF32(0,1) < epsilon per call and then env.SampleAction): a uniform in [0,1) with 24 bits
+// and, when exploring, a uniform action.  Counter based, so host and device agree for a given seed.
+__host__ __device__ inline bool explore_draw(uint32_t i, uint64_t seed, float epsilon, int n_actions, int *action)
+{
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint32_t u = mix32(mix32(i, k0), k1 ^ 0x5bd1e995u);
+    const float r = (float)(u >> 8) * (1.0f / 16777216.0f);
+    *action = (int)(mix32(u, k1 + 0x27d4eb2fu) % (uint32_t)n_actions);
+    return r < epsilon;
+}
+
 }  // namespace gq

@@ -362,6 +362,14 @@ class Agent:
         self._rng = random.Random(seed)
         self._learn_calls = 0
 
+    def action_batch(self, states):
+        """Agent.Action (agent.go:193-221) for a batch of states from vectorised environments: one
+        steps++ / epsilon track per state, exploration decided per row on the device (uniform random
+        action where the reference asks env.SampleAction), greedy = first-argmax of the online Q."""
+        states = np.ascontiguousarray(states, np.float32).reshape(-1, self._h.D)
+        self.steps += len(states)
+        return self._h.epsilon_greedy_action(states, float(self.epsilon), self._rng.getrandbits(63))
+
     def learn(self, indices=None):
         """Agent.Learn (agent.go:126-178).  `indices` injects Memory.Sample's draw (tests);
         by default the indices are drawn on the device."""

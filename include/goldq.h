@@ -176,6 +176,15 @@ int goldq_last_loss(goldq_t *h, float *out);
 int goldq_predict(goldq_t *h, int net, int replica, int64_t n, const float *x, float *q);
 /* Agent.action (agent.go:207-221): first-argmax of the online prediction. */
 int goldq_greedy_action(goldq_t *h, int replica, int64_t n, const float *x, int32_t *action);
+/* Agent.Action for n states at once (vectorised environments): row i explores when
+ * its own uniform draw is below epsilon (agent.go:196: num.RandF32(0,1) < a.epsilon) and then takes a
+ * uniform random action (the reference asks the environment, env.SampleAction, agent.go:197), else
+ * the first-argmax of the online network (agent.go:207-221).  Draws are counter based:
+ * goldq_explore_plan returns, on the host, which rows explore and what they take for a seed. */
+int goldq_epsilon_greedy_action(goldq_t *h, int replica, int64_t n, const float *x, float epsilon, uint64_t seed,
+                                int32_t *action);
+int goldq_explore_plan(int64_t n, int32_t n_actions, float epsilon, uint64_t seed, uint8_t *explore,
+                       int32_t *random_action);
 /* Sequential.FitBatch / Fit (model.go:528-573) on explicit labels: x [n][D],
  * y [n][A]; one MSE + Adam step on the ONLINE net of replica 0.  n must equal
  * batch_size (FitBatch) or 1 (Fit) — goro rejects other shapes (io.go:138-153). */

@@ -77,3 +77,17 @@ def test_bad_config_rejected_before_touching_the_device():
         G.Handle(batch_size=0)
     with pytest.raises(G.GoldqError):
         G.Handle(abi_version=99)
+
+
+def test_explore_plan_is_uniform_and_deterministic():
+    """Host mirror of the batched epsilon-greedy draws (goldq_explore_plan; no GPU needed)."""
+    from gold_b200 import _capi as G
+    ex, ra = G.explore_plan(200000, 6, 0.25, 12345)
+    ex2, ra2 = G.explore_plan(200000, 6, 0.25, 12345)
+    assert (ex == ex2).all() and (ra == ra2).all()
+    assert abs(ex.mean() - 0.25) < 5e-3                       # ~5 sigma of a Bernoulli(0.25) over 2e5 draws
+    counts = np.bincount(ra, minlength=6) / len(ra)
+    assert ra.min() >= 0 and ra.max() == 5 and np.abs(counts - 1 / 6).max() < 5e-3
+    assert abs(np.corrcoef(ex.astype(float), ra.astype(float))[0, 1]) < 0.01
+    assert not G.explore_plan(1000, 3, 0.0, 7)[0].any() and G.explore_plan(1000, 3, 1.0, 7)[0].all()
+    assert (G.explore_plan(1000, 3, 0.5, 7)[0] != G.explore_plan(1000, 3, 0.5, 8)[0]).any()

@@ -385,3 +385,23 @@ def test_learn_many_graph_replay_equals_single_steps(kind):
     for x, y in zip(a[:3], b[:3]):
         np.testing.assert_array_equal(x, y)
     np.testing.assert_array_equal(a[4], b[4])
+
+
+def test_batched_epsilon_greedy_action():
+    """goldq_epsilon_greedy_action: rows that do not explore take the oracle's first-argmax, rows that
+    explore take the planned uniform action; epsilon 0 is goldq_greedy_action."""
+    from oracle import binding as O
+    dims, n = (5, 17, 33, 3), 4000
+    th = synth.glorot_params(dims, 3)
+    h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3], batch_size=8, replay_capacity=64)
+    h.set_params(G.NET_ONLINE, th)
+    x = np.random.default_rng(5).uniform(-1, 1, (n, dims[0])).astype(np.float32)
+    _, greedy = O.predict(dims, th, x)
+    np.testing.assert_array_equal(h.greedy_action(x), greedy)
+    np.testing.assert_array_equal(h.epsilon_greedy_action(x, 0.0, 99), greedy)
+    act = h.epsilon_greedy_action(x, 0.3, 4242)
+    ex, ra = G.explore_plan(n, dims[3], 0.3, 4242)
+    assert 0.25 < ex.mean() < 0.35
+    np.testing.assert_array_equal(act[~ex], greedy[~ex])
+    np.testing.assert_array_equal(act[ex], ra[ex])
+    h.close()
