@@ -148,8 +148,22 @@ struct AdamSolver {
 
 // deepq.PolicyConfig (policy.go:14-38); the layer builder is DefaultFCLayerBuilder's shape:
 // FC(x,hidden1) -> FC(hidden1,hidden2) -> FC(hidden2,y, Linear) (policy.go:53-59)
+// gorgonia.RMSPropSolver's settable fields (solvers.go:216-246); Enabled selects it over Optimizer
+struct RMSPropSolver {
+    bool Enabled = false;
+    double eta = 0.001, eps = 1e-8, decay = 0.999;
+};
+
+// model.Loss: MSE (loss.go:22-42) or PseudoHuber with its Delta (loss.go:90-111; reduced by Mean)
+struct Loss {
+    bool PseudoHuber = false;
+    float Delta = 1.0f;
+};
+
 struct PolicyConfig {
     AdamSolver Optimizer{0.0005};
+    RMSPropSolver RMSProp;
+    Loss LossFn;
     int Hidden1 = 24, Hidden2 = 24;
     int BatchSize = 20;
     bool Track = true;
@@ -295,6 +309,16 @@ inline Error NewAgent(const AgentConfig &c, const Env *env, std::unique_ptr<Agen
     cfg.beta1 = c.policyConfig.Optimizer.beta1;
     cfg.beta2 = c.policyConfig.Optimizer.beta2;
     cfg.eps = c.policyConfig.Optimizer.eps;
+    if (c.policyConfig.RMSProp.Enabled) {          // runs on the generic CUDA path
+        cfg.solver = GOLDQ_SOLVER_RMSPROP;
+        cfg.lr = c.policyConfig.RMSProp.eta;
+        cfg.beta2 = c.policyConfig.RMSProp.decay;
+        cfg.eps = c.policyConfig.RMSProp.eps;
+    }
+    if (c.policyConfig.LossFn.PseudoHuber) {
+        cfg.loss = GOLDQ_LOSS_PSEUDO_HUBER;
+        cfg.huber_delta = c.policyConfig.LossFn.Delta;
+    }
     cfg.device = c.device;
     cfg.precision = c.bf16 ? GOLDQ_PREC_BF16 : GOLDQ_PREC_FP32;
     goldq_t *h = goldq_create(&cfg);
