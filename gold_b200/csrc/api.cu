@@ -555,6 +555,19 @@ int p2p_setup(goldq_t *h, std::string *why)
     };
     int ok = 1;
     if (W > P2P_MAX_WORLD || !g_nccl.AllGather) { ok = 0; *why = "world size above 8 or ncclAllGather missing"; }
+    {
+        // the exchange spin-waits inside the update kernel: its whole grid has to be co-resident
+        // (GOLDQ_P2P_RESIDENT_CAP overrides the device's capacity: test hook for the fallback)
+        int grid = 0, resident = 0;
+        const bool fits = wide_p2p_resident(h->wide, &grid, &resident);
+        const char *cap = getenv("GOLDQ_P2P_RESIDENT_CAP");
+        if (cap) resident = atoi(cap);
+        if (ok && (!fits || grid > resident)) {
+            ok = 0;
+            *why = "update grid of " + std::to_string(grid) + " CTAs is not co-resident (device holds " +
+                   std::to_string(resident) + "): the in-kernel exchange would wait on CTAs that cannot start";
+        }
+    }
     // exported allocation: reduce-scatter windows [2][W][chunk_f] + all-gather windows [2][W * chunk_f],
     // 8-byte {value, epoch} words, zeroed (epochs start at 1)
     pp.chunk_f = wide_p2p_chunk_floats(h->wide, W > 0 ? W : 1);

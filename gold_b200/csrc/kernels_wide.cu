@@ -1065,7 +1065,9 @@ __device__ __forceinline__ void ll_push4(const PeerSet &L, unsigned int epoch, i
 // every rank: push the local value to the owner; on the owner wait for the `world` copies, add
 // them in rank order and write the sums into every rank's all-gather window; wait for the sums.
 // A thread only ever waits on words produced by threads that wait on nothing but pushes, and the
-// whole grid is resident (<= 2368 CTAs of 128 threads), so no wait can starve its producer.
+// whole grid is resident (wide_p2p_resident, checked by goldq_dp_init: otherwise the group keeps
+// ncclAllReduce), so no wait can starve its producer.  A word that never arrives (5 s) sets the
+// host-visible error flag and the thread leaves parameters, moments and shadows untouched.
 __device__ __forceinline__ bool ll_timed_out(unsigned long long &t0, int *err)
 {
     unsigned long long t1;
@@ -1074,7 +1076,7 @@ __device__ __forceinline__ bool ll_timed_out(unsigned long long &t0, int *err)
     if (t1 - t0 > 5000000000ull) { *err = 1; return true; }      // 5 s: a peer is gone; do not hang the GPU
     return false;
 }
-__device__ __forceinline__ float4 dp_exchange4(const PeerSet &L, unsigned int epoch, int i, float4 g)
+__device__ __forceinline__ float4 dp_exchange4(const PeerSet &L, unsigned int epoch, int i, float4 g, bool &ok)
 {
     ll_push4(L, epoch, i, g);
     const size_t par = epoch & 1u;
@@ -1095,7 +1097,8 @@ __device__ __forceinline__ float4 dp_exchange4(const PeerSet &L, unsigned int ep
 #pragma unroll
             for (int r = 0; r < P2P_MAX_WORLD; r++)
                 if (r < L.world) all = all && a[r].y == epoch && a[r].w == epoch && b[r].y == epoch && b[r].w == epoch;
-            if (all || ll_timed_out(t0, L.err)) break;
+            if (all) break;
+            if (ll_timed_out(t0, L.err)) { ok = false; break; }
         }
         float4 acc = make_float4(__uint_as_float(a[0].x), __uint_as_float(a[0].z), __uint_as_float(b[0].x), __uint_as_float(b[0].z));
 #pragma unroll
@@ -1118,12 +1121,13 @@ __device__ __forceinline__ float4 dp_exchange4(const PeerSet &L, unsigned int ep
     for (;;) {
         a = ll_load2(my_ag);
         b = ll_load2(my_ag + 2);
-        if ((a.y == epoch && a.w == epoch && b.y == epoch && b.w == epoch) || ll_timed_out(t0, L.err)) break;
+        if (a.y == epoch && a.w == epoch && b.y == epoch && b.w == epoch) break;
+        if (ll_timed_out(t0, L.err)) { ok = false; break; }
     }
     return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
 }
 // same for a single element (b3 and the loss)
-__device__ __forceinline__ float dp_exchange1(const PeerSet &L, unsigned int epoch, int e, float g)
+__device__ __forceinline__ float dp_exchange1(const PeerSet &L, unsigned int epoch, int e, float g, bool &ok)
 {
     ll_push(L, epoch, e, g);
     const size_t par = epoch & 1u;
@@ -1141,7 +1145,8 @@ __device__ __forceinline__ float dp_exchange1(const PeerSet &L, unsigned int epo
 #pragma unroll
             for (int r = 0; r < P2P_MAX_WORLD; r++)
                 if (r < L.world) all = all && tag[r] == epoch;
-            if (all || ll_timed_out(t0, L.err)) break;
+            if (all) break;
+            if (ll_timed_out(t0, L.err)) { ok = false; break; }
         }
         float acc = __uint_as_float(val[0]);
 #pragma unroll
@@ -1154,7 +1159,8 @@ __device__ __forceinline__ float dp_exchange1(const PeerSet &L, unsigned int epo
     t0 = 0;
     for (;;) {
         asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(val), "=r"(tag) : "l"(my_ag) : "memory");
-        if (tag == epoch || ll_timed_out(t0, L.err)) break;
+        if (tag == epoch) break;
+        if (ll_timed_out(t0, L.err)) { ok = false; break; }
     }
     return __uint_as_float(val);
 }
@@ -1230,8 +1236,9 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
 #pragma unroll
             for (int u = 0; u < 8; u++) g = f4add(g, t[u]);
         }
-        if (dp) g = dp_exchange4(push, epoch, i, g);
-        finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
+        bool ok = true;     // false: a peer's word never arrived -- leave theta / m / v / shadows untouched
+        if (dp) g = dp_exchange4(push, epoch, i, g, ok);
+        if (ok) finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
     } else if ((int)blockIdx.x < pl.blocksA + pl.blocksB) {
         // ---- B: biases of the hidden layers, warp per float4 group -------------------
         const int gidx = (blockIdx.x - pl.blocksA) * 4 + warp;
@@ -1266,8 +1273,9 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
                 m4 = *reinterpret_cast<const float4 *>(m + i);
                 v4 = *reinterpret_cast<const float4 *>(v + i);
             }
-            if (dp) g = dp_exchange4(push, epoch, i, g);
-            finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
+            bool ok = true;
+            if (dp) g = dp_exchange4(push, epoch, i, g, ok);
+            if (ok) finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
         }
     } else {
         // ---- C: b3 and the loss, warp per scalar ---------------------------------------
@@ -1281,10 +1289,11 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
         for (int off = 16; off > 0; off >>= 1) g += __shfl_xor_sync(0xffffffffu, g, off);
         if (lane == 0) {
             if (i == o.P) g = __fdiv_rn(g, count);
-            if (dp) g = dp_exchange1(push, epoch, i, g);
+            bool ok = true;
+            if (dp) g = dp_exchange1(push, epoch, i, g, ok);
             if (i == o.P && loss_out) *loss_out = g;
             flat[i] = g;
-            if (FUSE && i < o.P) {
+            if (FUSE && i < o.P && ok) {
                 float wi = theta[i], mi = m[i], vi = v[i];
                 adam_update_w(wi, g, mi, vi, ac);
                 theta[i] = wi;
@@ -1541,6 +1550,34 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
     return 1;
 }
 
+static UpdatePlan make_update_plan(const Dims &d)
+{
+    UpdatePlan pl;
+    pl.nA = (d.D * d.H1 + d.H1 * d.H2 + d.H2 * d.A) >> 2;
+    pl.nB = (d.H1 + d.H2) >> 2;
+    pl.nC = d.A + 1;
+    pl.blocksA = (pl.nA + 127) / 128;
+    pl.blocksB = (pl.nB + 3) / 4;
+    pl.blocksC = (pl.nC + 3) / 4;
+    return pl;
+}
+
+// The in-kernel exchange spin-waits on words its peers' CTAs of the same index produce, so every
+// CTA of the update grid must be resident at once.  *grid = CTAs the update kernel launches for
+// this shape, *resident = CTAs the device holds concurrently (occupancy x SMs).
+bool wide_p2p_resident(const WideState *w, int *grid, int *resident)
+{
+    const UpdatePlan pl = make_update_plan(w->d);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_update_kernel<true, true>, 128, 0) != cudaSuccess) {
+        cudaGetLastError();
+        per_sm = 0;
+    }
+    *grid = pl.blocksA + pl.blocksB + pl.blocksC;
+    *resident = per_sm * w->sm_count;
+    return *grid <= *resident;
+}
+
 // floats owned per rank: an equal split of [P + 1] rounded up to whole 256-group blocks
 int wide_p2p_chunk_floats(const WideState *w, int world)
 {
@@ -1718,13 +1755,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
 
     PartialSrc ps{w->w1_slices, w->ns1, w->b1_part, w->nb1, w->w2_slices, w->ns2,
                   w->b2_part,   w->nb2, w->w3_slices, w->ns3, w->row_part, w->nrow};
-    UpdatePlan pl;
-    pl.nA = (d.D * d.H1 + d.H1 * d.H2 + d.H2 * d.A) >> 2;
-    pl.nB = (d.H1 + d.H2) >> 2;
-    pl.nC = d.A + 1;
-    pl.blocksA = (pl.nA + 127) / 128;
-    pl.blocksB = (pl.nB + 3) / 4;
-    pl.blocksC = (pl.nC + 3) / 4;
+    const UpdatePlan pl = make_update_plan(d);
     const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
     // (the update kernel follows cross-stream event waits: a full dependency, no PDL)
     if (s.fuse_update && s.push)

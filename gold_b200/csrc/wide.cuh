@@ -68,6 +68,7 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
 int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err);
 
 int wide_p2p_chunk_floats(const WideState *w, int world);
+bool wide_p2p_resident(const WideState *w, int *grid, int *resident);
 std::string wide_step_kernel_names(WideState *w);
 void wide_set_debug(WideState *w, bool on);
 void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const float **td);
