@@ -26,6 +26,7 @@ SYMBOLS = [
     "goldq_abi_version", "goldq_param_count", "goldq_selected_path", "goldq_set_params",
     "goldq_get_params", "goldq_set_adam_state", "goldq_get_adam_state", "goldq_replay_push",
     "goldq_replay_len", "goldq_replay_push_wait", "goldq_host_alloc", "goldq_host_free",
+    "goldq_replay_push_packed", "goldq_packed_bytes", "goldq_learn_prepare", "goldq_graph_builds",
     "goldq_learn", "goldq_learn_device_indices", "goldq_learn_many", "goldq_sampler_indices", "goldq_sync_target",
     "goldq_last_loss", "goldq_predict", "goldq_greedy_action", "goldq_epsilon_greedy_action", "goldq_explore_plan",
     "goldq_fit_batch",
@@ -79,6 +80,10 @@ def lib():
         "goldq_set_adam_state": (C.c_int, [vp, fp, fp, i64]),
         "goldq_get_adam_state": (C.c_int, [vp, fp, fp, C.POINTER(i64)]),
         "goldq_replay_push": (C.c_int, [vp, i64, vp, vp, vp, vp, vp]),
+        "goldq_replay_push_packed": (C.c_int, [vp, i64, vp]),
+        "goldq_packed_bytes": (i64, [vp, i64]),
+        "goldq_learn_prepare": (C.c_int, [vp]),
+        "goldq_graph_builds": (i64, [vp]),
         "goldq_replay_len": (i64, [vp]),
         "goldq_replay_push_wait": (C.c_int, [vp]),
         "goldq_host_alloc": (vp, [i64]),
@@ -234,6 +239,35 @@ class Handle:
 
     def replay_push_raw(self, n, s_ptr, a_ptr, r_ptr, s2_ptr, done_ptr):
         self._ck(self._L.goldq_replay_push(self._h, n, s_ptr, a_ptr, r_ptr, s2_ptr, done_ptr))
+
+    def packed_bytes(self, n):
+        return int(self._L.goldq_packed_bytes(self._h, n))
+
+    def replay_push_packed(self, n, packed_ptr):
+        """One contiguous host buffer s|s2|a|r|done (goldq.h): ONE H2D copy."""
+        self._ck(self._L.goldq_replay_push_packed(self._h, n, packed_ptr))
+
+    def pack(self, s, a, r, s2, done, out=None):
+        """Pack the five arrays of n transitions into the layout goldq_replay_push_packed takes."""
+        s = np.ascontiguousarray(s, np.float32).ravel(); s2 = np.ascontiguousarray(s2, np.float32).ravel()
+        a = np.ascontiguousarray(a, np.int32).ravel(); r = np.ascontiguousarray(r, np.float32).ravel()
+        done = np.ascontiguousarray(done, np.uint8).ravel()
+        parts = [s.view(np.uint8), s2.view(np.uint8), a.view(np.uint8), r.view(np.uint8), done]
+        total = sum(p.size for p in parts)
+        if out is None:
+            out = np.empty(total, np.uint8)
+        assert out.size == total
+        o = 0
+        for p in parts:
+            out[o:o + p.size] = p
+            o += p.size
+        return out
+
+    def learn_prepare(self):
+        self._ck(self._L.goldq_learn_prepare(self._h))
+
+    def graph_builds(self):
+        return int(self._L.goldq_graph_builds(self._h))
 
     def replay_push_wait(self):
         self._ck(self._L.goldq_replay_push_wait(self._h))

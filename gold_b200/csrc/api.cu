@@ -80,15 +80,17 @@ struct goldq {
     // double-buffered device staging, filled on a dedicated copy stream so that the H2D copy of
     // push i+1 overlaps the learn step enqueued after push i
     struct Staging {
-        float *s = nullptr, *s2 = nullptr, *r = nullptr;
-        int32_t *a = nullptr;
-        uint8_t *done = nullptr;
+        uint8_t *base = nullptr;        // one allocation, packed as goldq_replay_push_packed documents
         cudaEvent_t copied = nullptr, scattered = nullptr;
     } stg[2];
     int stg_cur = 0;
     int64_t stg_cap = 0;
     cudaStream_t copy_st = nullptr;
     cudaEvent_t ev_push = nullptr;      // = copied event of the latest push
+    // goldq_last_loss reads the scalar on its own stream, ordered after the latest learn step only: the
+    // readback does not wait for a replay push enqueued behind that step
+    cudaStream_t rb_st = nullptr;
+    cudaEvent_t ev_learned = nullptr;
 
     // reduced gradient + loss: [R][P+1]; loss per replica
     float *flat = nullptr, *loss = nullptr;
@@ -126,16 +128,19 @@ struct goldq {
 
     // CUDA-graph replay of learn steps (goldq_learn_many)
     static constexpr int GRAPH_MAX = 32;
-    static constexpr int GRAPH_CHUNK = 16;       // steps per graph launch
+    static constexpr int GRAPH_CHUNK = 16;       // largest number of steps per graph launch (then 8, 4, 2, 1)
+    static constexpr int STEP_RING = 8;          // pinned staging buffers for the per-step scalars
     int pf_set = 0, pf_have = 0;                 // batch double buffering while capturing (build_graph)
     const StepDev *pf_next = nullptr;
     StepDev *d_steps = nullptr;                  // [GRAPH_MAX] per-step scalars read by captured kernels
-    StepDev *h_steps[2] = {nullptr, nullptr};    // pinned staging, double buffered
-    cudaEvent_t ev_steps[2] = {nullptr, nullptr};
+    StepDev *h_steps[STEP_RING] = {};            // pinned staging ring
+    cudaEvent_t ev_steps[STEP_RING] = {};
     int steps_buf = 0;
+    // graph_exec[c]: c consecutive steps with device-drawn indices; graph_exec[0]: ONE step that reads the
+    // index list in d_idx (goldq_learn with host indices)
     cudaGraphExec_t graph_exec[GRAPH_MAX + 1] = {};
     int64_t graph_launches[GRAPH_MAX + 1] = {};
-    int64_t graph_head = -1, graph_len = -1;     // replay state the cached graphs were captured with
+    int64_t graph_builds = 0;                    // cudaGraphInstantiate calls so far (goldq_graph_builds)
     bool graph_debug = false;
 
     cudaGraphExec_t dp_graph = nullptr;          // phase 1 of one data-parallel wide step
@@ -313,7 +318,7 @@ int learn_generic(goldq_t *h, const int32_t *idx_dev, const StepDev *step)
     int rc = ensure_generic(h, h->B);
     if (rc) return rc;
     const Dims &d = h->dims;
-    launch_gather(h->rp, d.D, idx_dev, h->B, h->bs, h->bs2, h->ba, h->br, h->bdone, h->st);
+    launch_gather(h->rp, d.D, idx_dev, h->B, h->bs, h->bs2, h->ba, h->br, h->bdone, step, h->st);
     h->launches += 1;
     generic_forward(h, h->theta, h->bs, h->B, h->h1, h->mk1, h->h2, h->mk2, h->q);
     generic_forward(h, h->theta_t, h->bs2, h->B, h->t1, nullptr, h->t2, nullptr, h->qt);
@@ -468,10 +473,14 @@ void drop_graphs(goldq_t *h)
 }
 
 // Capture c consecutive learn steps (device sampler, per-step scalars from d_steps[i]) into
-// one executable graph.  Kernel arguments are frozen at capture time, so the cache is keyed
-// on everything they contain that can change: the replay ring position and the debug flag.
-int build_graph(goldq_t *h, int c)
+// one executable graph; c == 0: ONE step that reads its index list from d_idx.  Kernel arguments
+// are frozen at capture time; everything that changes from step to step (sampler seed, Adam's bias
+// corrections, the data-parallel epoch, the replay ring's head and length) is read from the
+// step's StepDev slot instead, so a graph survives goldq_replay_push.  The cache is dropped only
+// when the debug flag or the data-parallel group changes.
+int build_graph(goldq_t *h, int slot)
 {
+    const int c = slot == 0 ? 1 : slot;
     const int64_t iter0 = h->iter, launches0 = h->launches;
     cudaGraph_t graph = nullptr;
     CK(h, cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
@@ -485,46 +494,129 @@ int build_graph(goldq_t *h, int c)
             h->pf_have = i > 0;
             h->pf_next = i + 1 < c ? h->d_steps + i + 1 : nullptr;
         }
-        rc = run_learn(h, nullptr, 0, h->d_steps + i);
+        rc = run_learn(h, slot == 0 ? h->d_idx : nullptr, 0, h->d_steps + i);
     }
     h->pf_set = h->pf_have = 0;
     h->pf_next = nullptr;
     cudaError_t e = cudaStreamEndCapture(h->st, &graph);
-    h->graph_launches[c] = h->launches - launches0;
+    h->graph_launches[slot] = h->launches - launches0;
     h->iter = iter0;            // capturing executes nothing
     h->launches = launches0;
     h->p2p.epoch = epoch0;
     if (rc != GOLDQ_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return fail(h, GOLDQ_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&h->graph_exec[c], graph, 0);
+    e = cudaGraphInstantiate(&h->graph_exec[slot], graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(h, GOLDQ_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    h->graph_builds += 1;
     return GOLDQ_OK;
 }
 
-__global__ void replay_scatter_kernel(Replay rp, int D, int R, int64_t n, int64_t skip,
-                                      const float *__restrict__ s, const int32_t *__restrict__ a,
-                                      const float *__restrict__ r, const float *__restrict__ s2,
-                                      const uint8_t *__restrict__ done)
+// Replay the graph in `slot` (see build_graph) for steps seed, seed+1, ...: stage the steps' scalars,
+// copy them to the device slots in stream order, launch.
+int launch_graph(goldq_t *h, int slot, uint64_t seed)
 {
-    // item (rep, k), k in [skip, n): physical slot (head + k - skip) mod cap
+    const int c = slot == 0 ? 1 : slot;
+    // a peer that stopped answering was detected by an earlier step: do not queue more 5 s waits
+    if (h->p2p.on && *(volatile int *)h->p2p.err_host)
+        return fail(h, GOLDQ_ENCCL, "data-parallel peer did not publish its gradient within 5 s");
+    if (h->graph_debug != h->debug) { drop_graphs(h); h->graph_debug = h->debug; }
+    if (h->path == GOLDQ_PATH_GENERIC) {          // no allocation may happen under capture
+        int rc = ensure_generic(h, h->B);
+        if (rc) return rc;
+    }
+    if (!h->graph_exec[slot]) {
+        int rc = build_graph(h, slot);
+        if (rc) return rc;
+    }
+    const int b = h->steps_buf;
+    h->steps_buf = (b + 1) % goldq::STEP_RING;
+    CK(h, cudaEventSynchronize(h->ev_steps[b]));     // the staging buffer's previous copy has run
+    for (int i = 0; i < c; i++) {
+        AdamConsts ac = adam_consts(h->cfg, h->iter + 1 + i);
+        StepDev &sd = h->h_steps[b][i];
+        sd.seed = seed + (uint64_t)i;
+        sd.c1 = ac.c1;
+        sd.c2 = ac.c2;
+        sd.epoch = h->p2p.epoch + 1 + (uint32_t)i;
+        sd.pad_ = 0;
+        sd.head = h->rp.head;
+        sd.len = h->rp.len;
+    }
+    CK(h, cudaMemcpyAsync(h->d_steps, h->h_steps[b], sizeof(StepDev) * c, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaEventRecord(h->ev_steps[b], h->st));
+    CK(h, cudaGraphLaunch(h->graph_exec[slot], h->st));
+    if (h->p2p.on) h->p2p.epoch += (uint32_t)c;
+    h->iter += c;
+    h->launches += h->graph_launches[slot];
+    return GOLDQ_OK;
+}
+
+// steps are replayed from CUDA graphs unless the group sums gradients with ncclAllReduce (a captured
+// collective replays slower than the eager call) or GOLDQ_NO_GRAPH is set (diagnostic)
+bool use_graphs(const goldq_t *h)
+{
+    static const bool no_graph = getenv("GOLDQ_NO_GRAPH") != nullptr;
+    return !no_graph && (h->world <= 1 || h->p2p.on);
+}
+
+// every public entry that ran learn steps ends here: goldq_last_loss orders its readback after this point
+int learned(goldq_t *h, int rc)
+{
+    if (rc == GOLDQ_OK && cudaEventRecord(h->ev_learned, h->st) != cudaSuccess)
+        return fail(h, GOLDQ_ECUDA, "cudaEventRecord(ev_learned) failed");
+    return rc;
+}
+
+// Packed push layout (host and device staging): for R replicas and n items
+//   s [R][n][D] f32 | s2 [R][n][D] f32 | a [R][n] i32 | r [R][n] f32 | done [R][n] u8
+struct PackedView {
+    const float *s, *s2, *r;
+    const int32_t *a;
+    const uint8_t *done;
+};
+__host__ __device__ inline size_t packed_bytes(int64_t rows, int D) { return (size_t)rows * ((size_t)D * 8 + 9); }
+inline PackedView packed_view(const void *base, int64_t rows, int D)
+{
+    const uint8_t *p = (const uint8_t *)base;
+    PackedView v;
+    v.s = (const float *)p;
+    v.s2 = (const float *)(p + (size_t)rows * D * 4);
+    v.a = (const int32_t *)(p + (size_t)rows * D * 8);
+    v.r = (const float *)(p + (size_t)rows * D * 8 + (size_t)rows * 4);
+    v.done = p + (size_t)rows * D * 8 + (size_t)rows * 8;
+    return v;
+}
+
+// item (rep, k), k in [skip, n): physical slot (head + k - skip) mod cap.  VEC: one thread per
+// 16-byte granule of a row (D % 4 == 0 and 16-byte aligned staging), else one per float.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+replay_scatter_kernel(Replay rp, int D, int R, int64_t n, int64_t skip, PackedView src)
+{
+    const int per_row = VEC ? (D >> 2) : D;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t m = n - skip;
-    int64_t per = m * D;
+    int64_t per = m * per_row;
     if (t >= per * R) return;
     int rep = (int)(t / per);
     int64_t e = t - (int64_t)rep * per;
-    int64_t k = e / D;
-    int c = (int)(e - k * D);
+    int64_t k = e / per_row;
+    int c = (int)(e - k * per_row);
     int64_t slot = (rp.head + k) % rp.cap;
-    int64_t src = ((int64_t)rep * n + skip + k);
+    int64_t from = ((int64_t)rep * n + skip + k);
     int64_t dst = (int64_t)rep * rp.cap + slot;
-    rp.s[dst * D + c] = s[src * D + c];
-    rp.s2[dst * D + c] = s2[src * D + c];
+    if (VEC) {
+        reinterpret_cast<float4 *>(rp.s + dst * D)[c] = __ldg(reinterpret_cast<const float4 *>(src.s + from * D) + c);
+        reinterpret_cast<float4 *>(rp.s2 + dst * D)[c] = __ldg(reinterpret_cast<const float4 *>(src.s2 + from * D) + c);
+    } else {
+        rp.s[dst * D + c] = src.s[from * D + c];
+        rp.s2[dst * D + c] = src.s2[from * D + c];
+    }
     if (c == 0) {
-        rp.a[dst] = a[src];
-        rp.r[dst] = r[src];
-        rp.done[dst] = done[src];
+        rp.a[dst] = src.a[from];
+        rp.r[dst] = src.r[from];
+        rp.done[dst] = src.done[from];
     }
 }
 
@@ -741,11 +833,13 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
     cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->rb_st, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_learned, cudaEventDisableTiming);
     for (auto &g : h->stg) {
         cudaEventCreateWithFlags(&g.copied, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g.scattered, cudaEventDisableTiming);
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < goldq::STEP_RING; i++) {
         cudaEventCreateWithFlags(&h->ev_steps[i], cudaEventDisableTiming);
         if (cudaHostAlloc((void **)&h->h_steps[i], sizeof(StepDev) * goldq::GRAPH_MAX, cudaHostAllocDefault) != cudaSuccess)
             return bail("cudaHostAlloc failed (step slots)");
@@ -806,7 +900,7 @@ void goldq_destroy(goldq_t *h)
     cudaSetDevice(h->dev);
     if (h->st) cudaStreamSynchronize(h->st);
     drop_graphs(h);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < goldq::STEP_RING; i++) {
         if (h->h_steps[i]) cudaFreeHost(h->h_steps[i]);
         if (h->ev_steps[i]) cudaEventDestroy(h->ev_steps[i]);
     }
@@ -815,8 +909,7 @@ void goldq_destroy(goldq_t *h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->wide) wide_destroy(h->wide);
     void *ptrs[] = {h->theta, h->theta_t, h->m, h->v, h->flat, h->loss, h->d_idx, h->rp.s, h->rp.s2,
-                    h->rp.a, h->rp.r, h->rp.done, h->stg[0].s, h->stg[0].s2, h->stg[0].r, h->stg[0].a,
-                    h->stg[0].done, h->stg[1].s, h->stg[1].s2, h->stg[1].r, h->stg[1].a, h->stg[1].done, h->partial, h->ticket, h->bs, h->bs2, h->br, h->ba, h->bdone, h->h1,
+                    h->rp.a, h->rp.r, h->rp.done, h->stg[0].base, h->stg[1].base, h->partial, h->ticket, h->bs, h->bs2, h->br, h->ba, h->bdone, h->h1,
                     h->h2, h->q, h->t1, h->t2, h->qt, h->td, h->dq, h->dh2, h->dh1, h->ylab, h->mk1,
                     h->mk2, h->gslice, h->loss_part, h->px, h->ph1, h->ph2, h->pq, h->pact,
                     h->dbg_q, h->dbg_qt, h->dbg_td, h->dbg_idx};
@@ -829,6 +922,8 @@ void goldq_destroy(goldq_t *h)
         if (g.scattered) cudaEventDestroy(g.scattered);
     }
     if (h->copy_st) { cudaStreamSynchronize(h->copy_st); cudaStreamDestroy(h->copy_st); }
+    if (h->rb_st) { cudaStreamSynchronize(h->rb_st); cudaStreamDestroy(h->rb_st); }
+    if (h->ev_learned) cudaEventDestroy(h->ev_learned);
     if (h->own_stream && h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -899,12 +994,22 @@ int goldq_get_adam_state(goldq_t *h, float *m, float *v, int64_t *iter)
     return GOLDQ_OK;
 }
 
-int goldq_replay_push(goldq_t *h, int64_t n, const float *s, const int32_t *a, const float *r,
-                      const float *s2, const uint8_t *done)
+// shared tail of goldq_replay_push / goldq_replay_push_packed.  `packed` != NULL: one host buffer in
+// the packed layout (ONE H2D copy); else the five arrays (five copies into the same device layout).
+static int push_common(goldq_t *h, int64_t n, const void *packed, const float *s, const int32_t *a, const float *r,
+                       const float *s2, const uint8_t *done)
 {
-    if (!h || n < 0 || (n > 0 && (!s || !a || !r || !s2 || !done)))
-        return fail(h, GOLDQ_EINVAL, "replay_push: bad argument");
-    if (n == 0) return GOLDQ_OK;
+    // the learn step indexes Q rows, W3 columns and dQ with the stored action: an action outside
+    // [0, n_actions) would be an out-of-bounds device access (the reference panics in
+    // qValues.Set(event.Action, ...), agent.go:155); reject it here
+    {
+        const int64_t total = (int64_t)h->R * n;
+        const uint32_t A = (uint32_t)h->dims.A;
+        for (int64_t i = 0; i < total; i++)
+            if ((uint32_t)a[i] >= A)
+                return fail(h, GOLDQ_EINVAL, "replay_push: action " + std::to_string(a[i]) + " at item " +
+                                                 std::to_string(i) + " is outside [0, n_actions)");
+    }
     CK(h, cudaSetDevice(h->dev));
     const int D = h->dims.D, R = h->R;
     if (h->stg_cap < n) {
@@ -912,27 +1017,27 @@ int goldq_replay_push(goldq_t *h, int64_t n, const float *s, const int32_t *a, c
         CK(h, cudaStreamSynchronize(h->st));
         int64_t cap = n < 1024 ? 1024 : n;
         for (auto &g : h->stg) {
-            void *old[] = {g.s, g.s2, g.r, g.a, g.done};
-            for (void *p : old)
-                if (p) cudaFree(p);
-            CK(h, dalloc(&g.s, (size_t)R * cap * D));
-            CK(h, dalloc(&g.s2, (size_t)R * cap * D));
-            CK(h, dalloc(&g.r, (size_t)R * cap));
-            CK(h, dalloc(&g.a, (size_t)R * cap));
-            CK(h, dalloc(&g.done, (size_t)R * cap));
+            if (g.base) cudaFree(g.base);
+            g.base = nullptr;
+            CK(h, dalloc(&g.base, packed_bytes((int64_t)R * cap, D)));
         }
         h->stg_cap = cap;
     }
     goldq::Staging &g = h->stg[h->stg_cur];
     h->stg_cur ^= 1;
-    size_t rows = (size_t)R * n;
+    const int64_t rows = (int64_t)R * n;
+    const PackedView dv = packed_view(g.base, rows, D);
     // copy stream: wait until the scatter that last read this staging set is done, then copy
     CK(h, cudaStreamWaitEvent(h->copy_st, g.scattered, 0));
-    CK(h, cudaMemcpyAsync(g.s, s, rows * D * 4, cudaMemcpyHostToDevice, h->copy_st));
-    CK(h, cudaMemcpyAsync(g.s2, s2, rows * D * 4, cudaMemcpyHostToDevice, h->copy_st));
-    CK(h, cudaMemcpyAsync(g.a, a, rows * 4, cudaMemcpyHostToDevice, h->copy_st));
-    CK(h, cudaMemcpyAsync(g.r, r, rows * 4, cudaMemcpyHostToDevice, h->copy_st));
-    CK(h, cudaMemcpyAsync(g.done, done, rows, cudaMemcpyHostToDevice, h->copy_st));
+    if (packed) {
+        CK(h, cudaMemcpyAsync(g.base, packed, packed_bytes(rows, D), cudaMemcpyHostToDevice, h->copy_st));
+    } else {
+        CK(h, cudaMemcpyAsync((void *)dv.s, s, (size_t)rows * D * 4, cudaMemcpyHostToDevice, h->copy_st));
+        CK(h, cudaMemcpyAsync((void *)dv.s2, s2, (size_t)rows * D * 4, cudaMemcpyHostToDevice, h->copy_st));
+        CK(h, cudaMemcpyAsync((void *)dv.a, a, (size_t)rows * 4, cudaMemcpyHostToDevice, h->copy_st));
+        CK(h, cudaMemcpyAsync((void *)dv.r, r, (size_t)rows * 4, cudaMemcpyHostToDevice, h->copy_st));
+        CK(h, cudaMemcpyAsync((void *)dv.done, done, (size_t)rows, cudaMemcpyHostToDevice, h->copy_st));
+    }
     CK(h, cudaEventRecord(g.copied, h->copy_st));
     h->ev_push = g.copied;
     // main stream: the ring is updated after everything enqueued so far (in stream order)
@@ -940,14 +1045,41 @@ int goldq_replay_push(goldq_t *h, int64_t n, const float *s, const int32_t *a, c
     // only the newest `cap` of the n items survive (PushFront + PopBack, agent.go:224-229)
     int64_t skip = n > h->rp.cap ? n - h->rp.cap : 0;
     int64_t mcount = n - skip;
-    int64_t total = mcount * D * R;
-    replay_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->st>>>(h->rp, D, R, n, skip, g.s, g.a, g.r,
-                                                                             g.s2, g.done);
+    if ((D & 3) == 0 && (((size_t)rows * D * 4) & 15) == 0) {
+        int64_t total = mcount * (D >> 2) * R;
+        replay_scatter_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, h->st>>>(h->rp, D, R, n, skip, dv);
+    } else {
+        int64_t total = mcount * D * R;
+        replay_scatter_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, h->st>>>(h->rp, D, R, n, skip, dv);
+    }
     CK(h, cudaEventRecord(g.scattered, h->st));
     h->launches += 1;
     h->rp.head = (h->rp.head + mcount) % h->rp.cap;
     h->rp.len = h->rp.len + mcount > h->rp.cap ? h->rp.cap : h->rp.len + mcount;
     return check_launch(h, "replay_scatter_kernel");
+}
+
+int goldq_replay_push(goldq_t *h, int64_t n, const float *s, const int32_t *a, const float *r,
+                      const float *s2, const uint8_t *done)
+{
+    if (!h || n < 0 || (n > 0 && (!s || !a || !r || !s2 || !done)))
+        return fail(h, GOLDQ_EINVAL, "replay_push: bad argument");
+    if (n == 0) return GOLDQ_OK;
+    return push_common(h, n, nullptr, s, a, r, s2, done);
+}
+
+int64_t goldq_packed_bytes(const goldq_t *h, int64_t n)
+{
+    if (!h || n < 0) return 0;
+    return (int64_t)packed_bytes((int64_t)h->R * n, h->dims.D);
+}
+
+int goldq_replay_push_packed(goldq_t *h, int64_t n, const void *packed)
+{
+    if (!h || n < 0 || (n > 0 && !packed)) return fail(h, GOLDQ_EINVAL, "replay_push_packed: bad argument");
+    if (n == 0) return GOLDQ_OK;
+    const PackedView hv = packed_view(packed, (int64_t)h->R * n, h->dims.D);
+    return push_common(h, n, packed, hv.s, hv.a, hv.r, hv.s2, hv.done);
 }
 
 int goldq_replay_push_wait(goldq_t *h)
@@ -984,30 +1116,53 @@ int goldq_learn(goldq_t *h, const int32_t *idx, uint64_t seed)
         CK(h, cudaMemcpyAsync(h->d_idx, idx, n * 4, cudaMemcpyHostToDevice, h->st));
         idx_dev = h->d_idx;
     }
-    return run_learn(h, idx_dev, seed);
+    // one launch instead of the step's kernels, events and cross-stream waits: Agent.Learn after
+    // every Remember replays the same one-step graph (the ring position travels in the step slot)
+    if (use_graphs(h)) return learned(h, launch_graph(h, idx ? 0 : 1, seed));
+    return learned(h, run_learn(h, idx_dev, seed));
 }
+
+int goldq_learn_prepare(goldq_t *h)
+{
+    if (!h) return GOLDQ_EINVAL;
+    CK(h, cudaSetDevice(h->dev));
+    if (h->rp.len < h->B) return fail(h, GOLDQ_ENOTREADY, "replay shorter than batch");
+    if (!use_graphs(h)) return GOLDQ_OK;
+    if (h->path == GOLDQ_PATH_GENERIC) {          // no allocation may happen under capture
+        int rc = ensure_generic(h, h->B);
+        if (rc) return rc;
+    }
+    if (h->graph_debug != h->debug) { drop_graphs(h); h->graph_debug = h->debug; }
+    for (int slot = 0; slot <= goldq::GRAPH_CHUNK; slot = slot ? slot * 2 : 1) {
+        if (h->graph_exec[slot]) continue;
+        int rc = build_graph(h, slot);
+        if (rc) return rc;
+    }
+    return GOLDQ_OK;
+}
+
+int64_t goldq_graph_builds(const goldq_t *h) { return h ? h->graph_builds : 0; }
 
 int goldq_learn_device_indices(goldq_t *h, const int32_t *idx_dev)
 {
     if (!h || !idx_dev) return fail(h, GOLDQ_EINVAL, "learn_device_indices: bad argument");
     CK(h, cudaSetDevice(h->dev));
-    return run_learn(h, idx_dev, 0);
+    return learned(h, run_learn(h, idx_dev, 0));
 }
 
+static int learn_many_impl(goldq_t *h, int32_t n, uint64_t seed);
 int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
 {
     if (!h || n < 0) return fail(h, GOLDQ_EINVAL, "learn_many: bad argument");
+    return learned(h, learn_many_impl(h, n, seed));
+}
+static int learn_many_impl(goldq_t *h, int32_t n, uint64_t seed)
+{
     CK(h, cudaSetDevice(h->dev));
     if (h->rp.len < h->B) return fail(h, GOLDQ_ENOTREADY, "replay shorter than batch");
     if (h->path == GOLDQ_PATH_GENERIC) {          // no allocation may happen under capture
         int rc = ensure_generic(h, h->B);
         if (rc) return rc;
-    }
-    if (h->graph_head != h->rp.head || h->graph_len != h->rp.len || h->graph_debug != h->debug) {
-        drop_graphs(h);
-        h->graph_head = h->rp.head;
-        h->graph_len = h->rp.len;
-        h->graph_debug = h->debug;
     }
     static const bool no_graph = getenv("GOLDQ_NO_GRAPH") != nullptr;   // diagnostic: eager launches
     // Data-parallel steps: an ncclAllReduce captured into a CUDA graph replays ~80 us slower per
@@ -1032,13 +1187,15 @@ int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
         while (n > 0) {
             const int c = n < goldq::GRAPH_MAX ? n : goldq::GRAPH_MAX;
             const int b = h->steps_buf;
-            h->steps_buf ^= 1;
+            h->steps_buf = (b + 1) % goldq::STEP_RING;
             CK(h, cudaEventSynchronize(h->ev_steps[b]));
             for (int i = 0; i < c; i++) {
                 AdamConsts ac = adam_consts(h->cfg, h->iter + 1 + i);
                 h->h_steps[b][i].seed = seed + (uint64_t)i;
                 h->h_steps[b][i].c1 = ac.c1;
                 h->h_steps[b][i].c2 = ac.c2;
+                h->h_steps[b][i].head = h->rp.head;
+                h->h_steps[b][i].len = h->rp.len;
             }
             for (int i = 0; i < c; i++) {
                 // slot 0 is rewritten in stream order, after the previous step's kernels read it
@@ -1062,37 +1219,13 @@ int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed)
         }
         return GOLDQ_OK;
     }
-    // One graph size only (GRAPH_CHUNK steps): building a graph costs milliseconds, so a call
-    // never instantiates more than this one; the remainder (< GRAPH_CHUNK steps) is launched eagerly.
+    // Graphs of 16, 8, 4, 2 and 1 steps (each instantiated once, on first use or by
+    // goldq_learn_prepare): any step count is replayed from graphs, largest first.
     while (n > 0) {
-        const int c = goldq::GRAPH_CHUNK;
-        if (n < c) {
-            for (int i = 0; i < n; i++) {
-                int rc = run_learn(h, nullptr, seed + (uint64_t)i);
-                if (rc) return rc;
-            }
-            return GOLDQ_OK;
-        }
-        if (!h->graph_exec[c]) {
-            int rc = build_graph(h, c);
-            if (rc) return rc;
-        }
-        const int b = h->steps_buf;
-        h->steps_buf ^= 1;
-        CK(h, cudaEventSynchronize(h->ev_steps[b]));     // the staging buffer's previous copy has run
-        for (int i = 0; i < c; i++) {
-            AdamConsts ac = adam_consts(h->cfg, h->iter + 1 + i);
-            h->h_steps[b][i].seed = seed + (uint64_t)i;
-            h->h_steps[b][i].c1 = ac.c1;
-            h->h_steps[b][i].c2 = ac.c2;
-            h->h_steps[b][i].epoch = h->p2p.epoch + 1 + (uint32_t)i;
-        }
-        CK(h, cudaMemcpyAsync(h->d_steps, h->h_steps[b], sizeof(StepDev) * c, cudaMemcpyHostToDevice, h->st));
-        CK(h, cudaEventRecord(h->ev_steps[b], h->st));
-        CK(h, cudaGraphLaunch(h->graph_exec[c], h->st));
-        if (h->p2p.on) h->p2p.epoch += (uint32_t)c;
-        h->iter += c;
-        h->launches += h->graph_launches[c];
+        int c = goldq::GRAPH_CHUNK;
+        while (c > n) c >>= 1;
+        int rc = launch_graph(h, c, seed);
+        if (rc) return rc;
         seed += (uint64_t)c;
         n -= c;
     }
@@ -1134,6 +1267,7 @@ int goldq_step_breakdown(goldq_t *h, uint64_t seed, int32_t max_kernels, float *
         cudaError_t e = cudaStreamSynchronize(h->st);
         if (e != cudaSuccess) rc = fail(h, GOLDQ_ECUDA, cudaGetErrorString(e));
     }
+    rc = learned(h, rc);
     int n = h->prof_n < max_kernels ? h->prof_n : max_kernels;
     if (rc == GOLDQ_OK)
         for (int i = 0; i < n; i++) cudaEventElapsedTime(&ms[i], evs[i], evs[i + 1]);
@@ -1162,8 +1296,10 @@ int goldq_last_loss(goldq_t *h, float *out)
 {
     if (!h || !out) return fail(h, GOLDQ_EINVAL, "last_loss: bad argument");
     CK(h, cudaSetDevice(h->dev));
-    CK(h, cudaMemcpyAsync(out, h->loss, (size_t)h->R * 4, cudaMemcpyDeviceToHost, h->st));
-    CK(h, cudaStreamSynchronize(h->st));
+    // ordered after the latest learn step (ev_learned), not after whatever was enqueued behind it
+    CK(h, cudaStreamWaitEvent(h->rb_st, h->ev_learned, 0));
+    CK(h, cudaMemcpyAsync(out, h->loss, (size_t)h->R * 4, cudaMemcpyDeviceToHost, h->rb_st));
+    CK(h, cudaStreamSynchronize(h->rb_st));
     if (h->p2p.on && *(volatile int *)h->p2p.err_host)
         return fail(h, GOLDQ_ENCCL, "data-parallel peer did not publish its gradient within 5 s");
     return GOLDQ_OK;
@@ -1284,7 +1420,7 @@ int goldq_fit_batch(goldq_t *h, int64_t n, const float *x, const float *y)
         if (k < 0) return fail(h, GOLDQ_ECUDA, err);
         h->launches += k;
     }
-    return check_launch(h, "fit_batch");
+    return learned(h, check_launch(h, "fit_batch"));
 }
 
 int goldq_dp_unique_id(uint8_t id[128])

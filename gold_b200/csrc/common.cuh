@@ -59,6 +59,8 @@ struct StepDev {
     float c1, c2;
     unsigned int epoch;     // data-parallel step counter (peer-memory all-reduce handshake)
     unsigned int pad_;
+    long long head, len;    // replay ring position at this step: a Remember between two replays of a
+                            // captured step moves the ring without invalidating the graph
 };
 
 // Scalars of one learn step.
@@ -91,7 +93,7 @@ __device__ __forceinline__ void residual_loss(const StepScalars &sc, float d, fl
 void launch_sample_indices(int32_t *idx, int B, int64_t len, uint64_t seed, const StepDev *step,
                            int replicas, cudaStream_t st);
 void launch_gather(const Replay &rp, int D, const int32_t *idx, int B, float *bs, float *bs2,
-                   int32_t *ba, float *br, uint8_t *bdone, cudaStream_t st);
+                   int32_t *ba, float *br, uint8_t *bdone, const StepDev *step, cudaStream_t st);
 void launch_fc_forward(const float *X, const float *W, const float *bias, float *Y,
                        uint8_t *mask, int n, int in, int out, bool relu, cudaStream_t st);
 // TD label + dQ: dq is dense [B][A] (zero off-action), loss partials per block.

@@ -21,7 +21,7 @@ __global__ void sample_indices_kernel(int32_t *__restrict__ idx, int B, uint32_t
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * replicas) return;
-    if (step) seed = step->seed;
+    if (step) { seed = step->seed; len = (uint32_t)step->len; }
     int rep = t / B, b = t - rep * B;
     idx[t] = (int32_t)perm_index((uint32_t)b, len, seed + 0x9E3779B97F4A7C15ull * (uint64_t)rep);
 }
@@ -42,13 +42,13 @@ template <bool VEC4>
 __global__ void gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx, int B,
                               float *__restrict__ bs, float *__restrict__ bs2,
                               int32_t *__restrict__ ba, float *__restrict__ br,
-                              uint8_t *__restrict__ bdone)
+                              uint8_t *__restrict__ bdone, const StepDev *__restrict__ step)
 {
     const int chunks = VEC4 ? (D >> 2) : D;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * chunks) return;
     int b = t / chunks, c = t - b * chunks;
-    int64_t phys = rp.head - 1 - (int64_t)idx[b];
+    int64_t phys = (step ? (int64_t)step->head : rp.head) - 1 - (int64_t)idx[b];
     if (phys < 0) phys += rp.cap;
     if (VEC4) {
         const float4 *src = reinterpret_cast<const float4 *>(rp.s + phys * D);
@@ -67,14 +67,14 @@ __global__ void gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx,
 }
 
 void launch_gather(const Replay &rp, int D, const int32_t *idx, int B, float *bs, float *bs2,
-                   int32_t *ba, float *br, uint8_t *bdone, cudaStream_t st)
+                   int32_t *ba, float *br, uint8_t *bdone, const StepDev *step, cudaStream_t st)
 {
     if ((D & 3) == 0) {
         int n = B * (D >> 2);
-        gather_kernel<true><<<(n + 255) / 256, 256, 0, st>>>(rp, D, idx, B, bs, bs2, ba, br, bdone);
+        gather_kernel<true><<<(n + 255) / 256, 256, 0, st>>>(rp, D, idx, B, bs, bs2, ba, br, bdone, step);
     } else {
         int n = B * D;
-        gather_kernel<false><<<(n + 255) / 256, 256, 0, st>>>(rp, D, idx, B, bs, bs2, ba, br, bdone);
+        gather_kernel<false><<<(n + 255) / 256, 256, 0, st>>>(rp, D, idx, B, bs, bs2, ba, br, bdone, step);
     }
 }
 

@@ -73,6 +73,8 @@ narrow_learn_kernel(NarrowArgs p)
         p.seed = p.step->seed;
         p.adam.c1 = p.step->c1;
         p.adam.c2 = p.step->c2;
+        p.rp.head = p.step->head;
+        p.rp.len = p.step->len;
     }
     const int rep = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31;

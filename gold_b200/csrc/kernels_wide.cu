@@ -784,7 +784,7 @@ wide_gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx, uint64_t s
     pdl_wait();                 // x/x2/ba/... are still being read by the previous step's kernels
     if (t >= B * chunks) return;
     int b = t / chunks, c = t - b * chunks;
-    if (step) seed = step->seed;
+    if (step) { seed = step->seed; rp.head = step->head; rp.len = step->len; }
     const int32_t li = idx ? idx[b] : (int32_t)perm_index((uint32_t)b, (uint32_t)rp.len, seed);
     int64_t phys = rp.head - 1 - (int64_t)li;
     if (phys < 0) phys += rp.cap;

@@ -128,6 +128,15 @@ int goldq_get_adam_state(goldq_t *h, float *m, float *v, int64_t *iter);
  * [n_replicas][n][D] floats; a, r, done are [n_replicas][n]. */
 int goldq_replay_push(goldq_t *h, int64_t n, const float *s, const int32_t *a,
                       const float *r, const float *s2, const uint8_t *done);
+/* Actions must lie in [0, n_actions): the learn step indexes Q rows and W3 columns with them, so an
+ * out-of-range action is rejected here with GOLDQ_EINVAL and nothing is pushed (the reference
+ * panics later, in qValues.Set(event.Action, ...), agent.go:155). */
+/* Same, from ONE contiguous host buffer (ONE host-to-device copy instead of five):
+ *   s [R][n][D] f32 | s2 [R][n][D] f32 | a [R][n] i32 | r [R][n] f32 | done [R][n] u8
+ * with R = n_replicas and no padding; goldq_packed_bytes(h, n) is its size.  The Go layer packs
+ * Events into such a pinned buffer as they are Remembered. */
+int goldq_replay_push_packed(goldq_t *h, int64_t n, const void *packed);
+int64_t goldq_packed_bytes(const goldq_t *h, int64_t n);
 int64_t goldq_replay_len(const goldq_t *h);                  /* Memory.Len() */
 /* Pageable host buffers are consumed before goldq_replay_push returns.  Buffers
  * from goldq_host_alloc (pinned) are copied asynchronously: do not overwrite them
@@ -150,12 +159,18 @@ void goldq_host_free(void *p);
 int goldq_learn(goldq_t *h, const int32_t *idx, uint64_t seed);
 /* Same, with the index list already in device memory (no host traffic). */
 int goldq_learn_device_indices(goldq_t *h, const int32_t *idx_dev);
-/* n consecutive learn steps with device-drawn indices (step i uses seed + i), enqueued as
- * ONE CUDA graph launch per 16 steps (a remainder below 16 is launched step by step): the
- * same work as n calls of goldq_learn(h, NULL, seed + i), without n times the launch overhead.  No target sync
+/* n consecutive learn steps with device-drawn indices (step i uses seed + i), replayed from CUDA
+ * graphs of 16, 8, 4, 2 and 1 steps (largest first): the same work as n calls of
+ * goldq_learn(h, NULL, seed + i), without n times the launch overhead.  No target sync
  * happens inside; the host layer keeps calling it between its goldq_sync_target calls
- * (agent.go:173,181-190). */
+ * (agent.go:173,181-190).  The graphs read the replay ring's position from per-step device
+ * slots, so goldq_replay_push between calls does not invalidate them. */
 int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed);
+/* Instantiate every step graph now (16/8/4/2/1-step and the host-index step of goldq_learn)
+ * instead of on first use; executes nothing.  Needs Len >= batch_size. */
+int goldq_learn_prepare(goldq_t *h);
+/* Diagnostic: graphs instantiated so far (a Remember/Learn loop must not grow it). */
+int64_t goldq_graph_builds(const goldq_t *h);
 /* Host mirror of the device sampler: the indices goldq_learn(h, NULL, seed) draws
  * for `replica` when the replay holds `len` events (lets the host layer fill
  * Event.i as Memory.Sample does, memory.go:63).  Pure CPU integer code. */

@@ -356,35 +356,109 @@ def test_learn_many_graph_replay_equals_single_steps(kind):
     more = [synth.replay(dims, 100, seed=70 + r) for r in range(R)]
     more = [np.concatenate([p[k] for p in more]) for k in range(5)]
 
-    def run(many):
+    def run(mode):
         h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3], batch_size=B,
                      replay_capacity=N, **kw)
         h.set_params(G.NET_ONLINE, th); h.set_params(G.NET_TARGET, tt)
         h.replay_push(*data)
-        seed = 1000
-        for n in (5, 37, 2):                       # 37 > 32: two graph chunks
-            if many:
+
+        def steps(n, seed):
+            if mode == "many":                     # graphs of 16/8/4/2/1 steps
                 h.learn_many(n, seed)
-            else:
+            elif mode == "single":                 # the one-step graph, n times
                 for i in range(n):
                     h.learn(None, seed + i)
+            else:                                  # eager launches (the profiling entry runs a real step)
+                for i in range(n):
+                    h.step_breakdown(seed + i)
+
+        seed = 1000
+        for n in (5, 37, 2):                       # 37 = 16 + 16 + 4 + 1
+            steps(n, seed)
             seed += n
             h.sync_target()
-        h.replay_push(*more)                       # moves the ring: cached graphs must be rebuilt
-        if many:
-            h.learn_many(4, seed)
-        else:
-            for i in range(4):
-                h.learn(None, seed + i)
+        builds = h.graph_builds()
+        h.replay_push(*more)                       # moves the ring: the step slots carry head/len, no rebuild
+        steps(4, seed)
+        assert h.graph_builds() == builds, "a replay push invalidated the step graphs"
         w = h.get_params(G.NET_ONLINE); m, v, it = h.get_adam_state(); loss = h.last_loss()
         h.close()
         return w, m, v, it, loss
 
-    a, b = run(False), run(True)
-    assert a[3] == b[3] == 48
-    for x, y in zip(a[:3], b[:3]):
+    a, b, c = run("single"), run("many"), run("eager")
+    assert a[3] == b[3] == c[3] == 48
+    for other in (b, c):
+        for x, y in zip(a[:3], other[:3]):
+            np.testing.assert_array_equal(x, y)
+        np.testing.assert_array_equal(a[4], other[4])
+
+
+@pytest.mark.parametrize("kind", ["narrow", "wide"])
+def test_remember_learn_loop_never_rebuilds_graphs(kind):
+    """Agent.Learn's real loop -- Remember one event, Learn once -- and learn_many between pushes replay
+    the graphs instantiated by goldq_learn_prepare: zero instantiations afterwards, and the ring
+    position that travels in the step slot selects the rows the host mirror of the sampler predicts."""
+    if kind == "wide":
+        dims, B, N, kw = (64, 256, 128, 6), 256, 1024, dict(precision=G.PREC_BF16)
+    else:
+        dims, B, N, kw = synth.CARTPOLE, 64, 300, {}
+    h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3], batch_size=B,
+                 replay_capacity=N, **kw)
+    h.set_params(G.NET_ONLINE, synth.glorot_params(dims, 1)); h.set_params(G.NET_TARGET, synth.glorot_params(dims, 2))
+    h.replay_push(*synth.replay(dims, N - 50, seed=9))
+    h.debug_enable(True)
+    h.learn_prepare()
+    builds = h.graph_builds()
+    assert builds == 6                              # 16, 8, 4, 2, 1 steps + the host-index step
+    ev = synth.replay(dims, 120, seed=10)
+    for i in range(120):                            # wraps the ring (capacity N)
+        h.replay_push(*[x[i:i + 1] for x in ev])
+        if i % 3 == 0:
+            h.learn(None, 5000 + i)
+            want = G.sampler_indices(h.replay_len(), B, 5000 + i)
+            np.testing.assert_array_equal(h.debug_fetch(G.DBG_INDICES), want)
+        elif i % 3 == 1:
+            h.learn_many(7, 9000 + 7 * i)
+        else:
+            h.learn(synth.sample_indices(h.replay_len(), B, i))
+    h.sync()
+    assert h.graph_builds() == builds
+    assert np.isfinite(h.last_loss()).all()
+    h.close()
+
+
+def test_packed_push_equals_unpacked_and_bad_actions_are_rejected():
+    dims, B, N = synth.CARTPOLE, 32, 256
+    data = synth.replay(dims, 200, seed=3)
+    hs = []
+    for packed in (False, True):
+        h = G.Handle(batch_size=B, replay_capacity=N)
+        h.set_params(G.NET_ONLINE, synth.glorot_params(dims, 1)); h.set_params(G.NET_TARGET, synth.glorot_params(dims, 2))
+        for lo in (0, 77, 150):                     # ragged chunk sizes
+            hi = min(200, lo + 77) if lo else 77
+            chunk = [x[lo:hi] for x in data]
+            if packed:
+                buf = h.pack(*chunk)
+                assert buf.size == h.packed_bytes(hi - lo)
+                h.replay_push_packed(hi - lo, buf.ctypes.data)
+                h.sync()
+            else:
+                h.replay_push(*chunk)
+        h.debug_enable(True)
+        h.learn(synth.sample_indices(h.replay_len(), B, 1))
+        hs.append((h.debug_fetch(G.DBG_Q_ONLINE), h.debug_fetch(G.DBG_TD), h.get_params(G.NET_ONLINE), h))
+    for x, y in zip(hs[0][:3], hs[1][:3]):
         np.testing.assert_array_equal(x, y)
-    np.testing.assert_array_equal(a[4], b[4])
+    h = hs[0][3]
+    n0 = h.replay_len()
+    bad = [x[:5].copy() for x in data]
+    for wrong in (-1, dims[3]):                     # the reference panics in qValues.Set (agent.go:155)
+        bad[1][3] = wrong
+        with pytest.raises(G.GoldqError) as e:
+            h.replay_push(*bad)
+        assert e.value.code == G.EINVAL and h.replay_len() == n0
+    for _, _, _, hh in hs:
+        hh.close()
 
 
 def test_batched_epsilon_greedy_action():
