@@ -6,9 +6,13 @@
 
 A "step" is one Agent.Learn over one sampled batch.  Default workload = the wide
 DQN config the metric's target is quoted on (BASELINE.json configs[2]: MLP
-128->512->512->18, batch 8192 per GPU, bf16 tcgen05 GEMMs, fp32 master weights);
-N > 1 = batch-sharded data parallelism (configs[3]), weak scaling: 8192 rows per
-GPU, one gradient all-reduce per step.  Prints ONE JSON line on rank 0.
+128->512->512->18, batch 8192, bf16 tcgen05 GEMMs, fp32 master weights);
+N > 1 = batch-sharded data parallelism at configs[3]'s stated shape: global batch
+65536 split over the ranks (strong scaling: 32768 / 16384 / 8192 rows per GPU at
+N = 2 / 4 / 8), one gradient exchange per step; `--scaling weak` keeps 8192 rows
+per GPU instead.  Prints ONE JSON line on rank 0; at N = 1 the line also carries
+the CartPole batch-4096 and replica-sweep workloads (configs[1], configs[4]) under
+"configs".
 """
 import argparse
 import ctypes as C
@@ -158,7 +162,13 @@ def run_reference(args):
         return
     from oracle import binding as O
     dims, B, _, replicas, prec = WORKLOADS[args.workload]
-    threads = O.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1, so omp_get_max_threads() would say 1 on a 24-core box: take the
+    # cores this process may run on and set the team size explicitly
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    threads = max(1, min(threads, 64))
     if replicas:
         rows = 20
     else:
@@ -167,8 +177,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "dqn_transitions_trained_per_sec", "value": rate, "unit": "transitions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, dims, B, replicas, prec),
+        "higher_is_better": True, "scaling": scaling_of(args), "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, dims, rows_per_gpu(args, B, replicas), replicas, prec),
         "cpu_baseline": {"value": rate, "unit": "transitions/s", "cores": threads, "kind": "port",
                          "sample": f"{rows}-row learn steps of the same workload (oracle port of the Gorgonia "
                                    f"learn step: per-event Predicts + FitBatch + multi-pass Adam), OpenMP over rows; "
@@ -178,13 +188,30 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(args, dims, B, replicas, prec):
+def scaling_of(args):
+    """N = 1: nothing to scale ("weak" by convention).  N > 1, wide workload: strong by default (configs[3]:
+    global batch 65536 over the ranks); the other workloads keep a fixed per-GPU batch (weak)."""
+    if args.gpus > 1 and args.workload == "wide":
+        return args.scaling or "strong"
+    return "weak"
+
+
+def rows_per_gpu(args, B, replicas):
+    if not replicas and scaling_of(args) == "strong":
+        if args.global_batch % args.gpus:
+            raise SystemExit("--global-batch must divide evenly over the GPUs")
+        return args.global_batch // args.gpus
+    return B
+
+
+def workload_config(args, dims, B, replicas, prec, name=None):
     n = args.gpus
+    name = name or args.workload
     cfg = {"workload": {"wide": "wide DQN MLP 128->512->512->18, learn step (BASELINE configs[2]; N>1: configs[3] data-parallel)",
                         "cartpole4096": "CartPole DQN 4->24->24->2 learn step, batch 4096 (BASELINE configs[1])",
-                        "replicas": "independent CartPole DQN replicas, batch 20 each (BASELINE configs[4])"}[args.workload],
+                        "replicas": "independent CartPole DQN replicas, batch 20 each (BASELINE configs[4])"}[name],
            "dims": list(dims), "batch_per_gpu": B, "global_batch": B * n * max(replicas, 1),
-           "replay_rows_per_gpu": WORKLOADS[args.workload][2], "precision": prec,
+           "replay_rows_per_gpu": WORKLOADS[name][2], "precision": prec,
            "parallelism": (f"dp{n}" if not replicas else f"replicas{replicas}x{n}"),
            "target_sync_every": TARGET_SYNC_EVERY,
            "l2": "inputs larger than L2: rows are drawn at random from a replay ring far above 126 MB"
@@ -218,6 +245,181 @@ def build_handle(G, args, dims, B, N, replicas, prec, rank, world, local_rank):
     return h
 
 
+class Workload:
+    """One handle + the three measurements of it: resident steps (value), host-buffer steps (e2e),
+    per-kernel breakdown (roofline)."""
+
+    def __init__(self, G, args, name, rank, world, local_rank, dist, torch):
+        self.G, self.args, self.name, self.rank, self.world = G, args, name, rank, world
+        self.dist, self.torch = dist, torch
+        dims, B, N, replicas, prec = WORKLOADS[name]
+        if name == args.workload:
+            B = rows_per_gpu(args, B, replicas)
+            prec = args.precision or prec
+            N = args.replay_rows or N
+        self.dims, self.B, self.N, self.replicas, self.prec = dims, B, N, replicas, prec
+        self.R = max(replicas, 1)
+        self.rows = B * self.R                     # transitions per step on this GPU
+        self.h = build_handle(G, args, dims, B, N, replicas, prec, rank, world, local_rank)
+        if world > 1 and not replicas:
+            uid = [G.Handle.dp_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            self.h.dp_init(uid[0], rank, world)
+        # every step graph (16/8/4/2/1 steps, host-index step) is instantiated here, before any warm-up, so
+        # that --warmup is honoured as given and no instantiation lands in a timed region
+        self.h.learn_prepare()
+        self.seed0 = 1_000_003 * (rank + 1)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def run_resident(self, first, count):
+        """steps [first, first+count): replay indices drawn on the device (nothing crosses PCIe),
+        enqueued through goldq_learn_many in chunks that end at the target-sync cadence."""
+        h, i = self.h, first
+        while i < first + count:
+            n = min(first + count - i, TARGET_SYNC_EVERY - (i % TARGET_SYNC_EVERY), self.args.chunk)
+            h.learn_many(n, self.seed0 + i)
+            i += n
+            if i % TARGET_SYNC_EVERY == 0:
+                h.sync_target()
+
+    def resident(self, K, W, sampler=None):
+        """value: K steps with inputs resident in HBM; CUDA events on the handle's stream, max over ranks."""
+        h = self.h
+        self.run_resident(0, W)
+        h.sync()
+        self.barrier()
+        if sampler:
+            sampler.start()
+            time.sleep(0.25)
+        self.barrier()
+        l0 = h.launch_count()
+        h.timer_start()
+        self.run_resident(W, K)
+        ms = h.timer_stop()
+        self.barrier()
+        launches = h.launch_count() - l0
+        ms = self.max_over_ranks(ms)
+        clocks = sampler.stop() if sampler else None
+        return self.rows * self.world * K / (ms * 1e-3), ms, launches, clocks
+
+    def e2e(self, K):
+        """The same metric through the public C ABI with HOST buffers.  Every step: B fresh transitions
+        pushed from ONE pinned host buffer (goldq_replay_push_packed: one H2D copy on the library's copy
+        stream, overlapping the previous step), the sampled index list from pinned host memory (H2D),
+        the step (goldq_learn), the loss read back (goldq_last_loss: D2H + sync).  Host wall clock."""
+        G, h, dims, B, R, N = self.G, self.h, self.dims, self.B, self.R, self.N
+        D = dims[0]
+        nbytes = h.packed_bytes(B)
+        bufs = []
+        for k in range(2):
+            arr, ptr = pinned_array(G, (nbytes,), np.uint8)
+            parts = [synth.replay(dims, B, seed=4242 + k + 31 * r) for r in range(R)]
+            fresh = [np.concatenate([p[j] for p in parts]) for j in range(5)]
+            h.pack(*fresh, out=arr)
+            bufs.append(ptr)
+        idx_host = []
+        for i in range(8):
+            arr, ptr = pinned_array(G, (R, B), np.int32)
+            arr[...] = np.stack([synth.sample_indices(N, B, 7 * i + r) for r in range(R)])
+            idx_host.append(ptr)
+        h2d = nbytes + R * B * 4
+        d2h = 4 * R
+
+        def step(i):
+            # the batch of step i was pushed during step i-1 (double-buffered staging): its copy overlaps
+            # that step's kernels; every byte still crosses PCIe inside the timed region
+            h.learn_raw(idx_host[i % len(idx_host)])          # H2D of the index list + the step
+            h.replay_push_packed(B, bufs[(i + 1) & 1])        # H2D of the next batch (copy stream)
+            loss = h.last_loss()                              # D2H + sync on the step
+            if (i + 1) % TARGET_SYNC_EVERY == 0:
+                h.sync_target()
+            return loss
+
+        h.replay_push_packed(B, bufs[0])
+        for i in range(3):
+            step(i)
+        self.barrier()
+        t0 = time.perf_counter()
+        for i in range(3, 3 + K):
+            last = step(i)
+        self.barrier()
+        sec = self.max_over_ranks(time.perf_counter() - t0)
+        return self.rows * self.world * K / sec, h2d, d2h, last
+
+    def breakdown(self):
+        """[(label, us)] of one eager, serialised learn step (mean of 10), after 3 warm-up steps."""
+        h = self.h
+        for i in range(3):
+            h.step_breakdown(self.seed0 + 10_000_000 + i)
+        reps = [h.step_breakdown(self.seed0 + 20_000_000 + i) for i in range(10)]
+        labels = [l for l, _ in reps[0]]
+        kms = np.array([[t for _, t in r] for r in reps]).mean(axis=0)
+        return labels, kms
+
+    def close(self):
+        self.h.close()
+
+
+def wide_kernel_flops(dims, B):
+    """algorithmic FLOPs of each tensor-core launch of the wide step (2 per MAC; online and target share
+    the forward launch)"""
+    D_, H1_, H2_, A_ = dims
+    fwd = 2 * 2.0 * B * (D_ * H1_ + H1_ * H2_ + H2_ * A_)
+    return {"fused forward L1-L3 online+target (tcgen05)": fwd,
+            "fused forward L1-L3 online+target, CTA pairs (tcgen05 cta_group::2)": fwd,
+            "fwd L1 online+target (tcgen05)": 2 * 2.0 * B * D_ * H1_,
+            "fwd L2 online+target (tcgen05)": 2 * 2.0 * B * H1_ * H2_,
+            "fwd L3 online+target (tcgen05)": 2 * 2.0 * B * H2_ * A_,
+            "dW3 (tcgen05)": 2.0 * B * H2_ * A_, "dW2 split-K (tcgen05)": 2.0 * B * H1_ * H2_,
+            "dX -> dZ1 (tcgen05)": 2.0 * B * H1_ * H2_, "dW1 split-K (tcgen05)": 2.0 * B * D_ * H1_}
+
+
+def roofline_of(w, ms_per_step, pk, floor_us):
+    G, h, dims, B, R = w.G, w.h, w.dims, w.B, w.R
+    bytes_step, flops_step = algorithmic_work(dims, B, R)
+    step_s = ms_per_step * 1e-3
+    labels, kms = w.breakdown()
+    breakdown = {labels[i]: round(float(kms[i]) * 1e3, 2) for i in range(len(labels))}   # us per launch
+    if h.path == G.PATH_WIDE:
+        kflops = wide_kernel_flops(dims, B)
+        cand = [i for i, l in enumerate(labels) if l in kflops]
+        top = max(cand, key=lambda i: kms[i])        # dominant = the tensor-core launch with the most time
+        ach = kflops[labels[top]] / (kms[top] * 1e-3) / 1e12
+        peak = pk["bf16_tflops"]      # burst figure: this kernel is timed alone, between events
+        # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
+        # (dram__bytes_read.sum + dram__bytes_write.sum); only valid for the configuration profiled
+        traffic = NCU_TRAFFIC.get((labels[top], tuple(dims), B))
+        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": traffic, "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
+                "kernel": labels[top], "kernel_us": float(kms[top]) * 1e3,
+                "flops_per_launch": kflops[labels[top]],
+                "peak_source": pk["source"] + " bf16_tflops (burst: kernel timed alone between CUDA events)",
+                "step": {"flops_per_step": flops_step, "achieved_tflops": flops_step / step_s / 1e12,
+                         "frac_of_sustained_peak": flops_step / step_s / 1e12 / pk["bf16_tflops_sustained"]},
+                "kernels_us": breakdown}
+    top = int(np.argmax(kms))
+    ach = bytes_step / (kms[top] * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+            "traffic": None, "kernel": labels[top], "kernel_us": float(kms[top]) * 1e3,
+            "bytes_per_launch": bytes_step, "peak_source": pk["source"] + " hbm_gbs",
+            "launch_floor_us": floor_us,
+            "frac_of_launch_floor": (floor_us / (step_s * 1e6)) if floor_us else None,
+            "note": "launch-latency bound by construction: the step's algorithmic bytes take < 0.1 us at HBM "
+                    "speed; launch_floor_us = one empty kernel per graph node, replayed from a 16-node graph",
+            "kernels_us": breakdown}
+
+
 def run_own(args):
     import torch
     import torch.distributed as dist
@@ -233,160 +435,24 @@ def run_own(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner out of it
-        os.environ["NCCL_DEBUG"] = os.environ.get("GOLDQ_NCCL_DEBUG", "NONE")
+        # (NCCL_DEBUG is left as the caller set it: stdout was diverted to stderr in main(), so NCCL's
+        # banner cannot reach the one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    dims, B, N, replicas, prec = WORKLOADS[args.workload]
-    if args.precision:
-        prec = args.precision
-    if args.replay_rows:
-        N = args.replay_rows
-    h = build_handle(G, args, dims, B, N, replicas, prec, rank, world, local_rank)
-    if world > 1 and not replicas:
-        uid = [G.Handle.dp_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        h.dp_init(uid[0], rank, world)
-    R = max(replicas, 1)
-    rows_per_step_gpu = B * R
-    # warm-up covers at least one 16-step graph launch so that the step graph is built before timing
-    K, W = args.steps, max(args.warmup, 32)
-
-    seed0 = 1_000_003 * (rank + 1)
-
-    def run_resident(first, count):
-        """steps [first, first+count): replay indices drawn on the device (nothing crosses PCIe),
-        enqueued through goldq_learn_many in chunks that end at the target-sync cadence."""
-        i = first
-        while i < first + count:
-            n = min(first + count - i, TARGET_SYNC_EVERY - (i % TARGET_SYNC_EVERY), args.chunk)
-            h.learn_many(n, seed0 + i)
-            i += n
-            if i % TARGET_SYNC_EVERY == 0:
-                h.sync_target()
-
-    # ---------------- value: inputs resident in HBM --------------------------------
-    run_resident(0, W)
-    h.sync()
-    barrier()
-    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.25)
-    barrier()
-    l0 = h.launch_count()
-    h.timer_start()
-    run_resident(W, K)
-    ms = h.timer_stop()
-    barrier()
-    launches = h.launch_count() - l0
-    ms = max_over_ranks(ms)
-    clocks = sampler.stop() if sampler else None
-    value = rows_per_step_gpu * world * K / (ms * 1e-3)
-
-    # ---------------- e2e: host buffers through the public C ABI ---------------------
-    # every step: B fresh transitions pushed from pinned host memory (H2D), the sampled
-    # index list from host memory (H2D), loss read back (D2H + sync).
-    D = dims[0]
-    bufs = []
-    for k in range(2):
-        arrs = [pinned_array(G, (R * B, D), np.float32), pinned_array(G, (R * B,), np.int32),
-                pinned_array(G, (R * B,), np.float32), pinned_array(G, (R * B, D), np.float32),
-                pinned_array(G, (R * B,), np.uint8)]
-        parts = [synth.replay(dims, B, seed=4242 + k + 31 * r) for r in range(R)]
-        fresh = [np.concatenate([p[j] for p in parts]) for j in range(5)]
-        for (a, _), src in zip(arrs, (fresh[0], fresh[1], fresh[2], fresh[3], fresh[4])):
-            a[...] = src.reshape(a.shape)
-        bufs.append(arrs)
-    idx_host = [np.stack([synth.sample_indices(N, B, 7 * i + r) for r in range(R)]).astype(np.int32)
-                for i in range(8)]
-    h2d = R * B * (8 * D + 9) + R * B * 4
-    d2h = 4 * R
-
-    def push(i):
-        h.replay_push_raw(B, *[p for _, p in bufs[i & 1]])    # H2D on the library's copy stream
-
-    def step_e2e(i):
-        # the batch of step i was pushed during step i-1 (double-buffered staging): its copy
-        # overlaps that step's kernels; every byte still crosses PCIe inside the timed region
-        ix = idx_host[i % len(idx_host)]
-        h.learn_raw(ix.ctypes.data)                           # H2D of the index list + the step
-        push(i + 1)
-        loss = h.last_loss()                                  # D2H + stream sync
-        if (i + 1) % TARGET_SYNC_EVERY == 0:
-            h.sync_target()
-        return loss
-
-    Ke = max(3, min(K, args.e2e_steps))
-    push(0)
-    for i in range(3):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(3, 3 + Ke):
-        last = step_e2e(i)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = rows_per_step_gpu * world * Ke / e2e_s
-
-    # ---------------- roofline of the dominant kernel, timed live with CUDA events ---------
     pk = peaks()
-    bytes_step, flops_step = algorithmic_work(dims, B, R)
-    step_s = ms * 1e-3 / K
-    for i in range(3):
-        h.step_breakdown(seed0 + 10_000_000 + i)
-    reps = [h.step_breakdown(seed0 + 20_000_000 + i) for i in range(10)]
-    labels = [l for l, _ in reps[0]]
-    kms = np.array([[t for _, t in r] for r in reps]).mean(axis=0)
-    top = int(np.argmax(kms))
-    breakdown = {labels[i]: round(float(kms[i]) * 1e3, 2) for i in range(len(labels))}   # us per launch
-    D_, H1_, H2_, A_ = dims
-    if h.path == G.PATH_WIDE:
-        # algorithmic FLOPs of each tensor-core launch (2 per MAC; online and target share a launch)
-        kflops = {"fused forward L1-L3 online+target (tcgen05)": 2 * 2.0 * B * (D_ * H1_ + H1_ * H2_ + H2_ * A_),
-                  "fwd L1 online+target (tcgen05)": 2 * 2.0 * B * D_ * H1_,
-                  "fwd L2 online+target (tcgen05)": 2 * 2.0 * B * H1_ * H2_,
-                  "fwd L3 online+target (tcgen05)": 2 * 2.0 * B * H2_ * A_,
-                  "dW3 (tcgen05)": 2.0 * B * H2_ * A_, "dW2 split-K (tcgen05)": 2.0 * B * H1_ * H2_,
-                  "dX -> dZ1 (tcgen05)": 2.0 * B * H1_ * H2_, "dW1 split-K (tcgen05)": 2.0 * B * D_ * H1_}
-        # dominant = the tensor-core launch with the most time
-        cand = [i for i, l in enumerate(labels) if l in kflops]
-        top = max(cand, key=lambda i: kms[i])
-        ach = kflops[labels[top]] / (kms[top] * 1e-3) / 1e12
-        peak = pk["bf16_tflops"]      # burst figure: this kernel is timed alone, between events
-        # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
-        # (dram__bytes_read.sum + dram__bytes_write.sum); only valid for the configuration profiled
-        traffic = NCU_TRAFFIC.get((labels[top], tuple(dims), B))
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": traffic, "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
-                "kernel": labels[top], "kernel_us": float(kms[top]) * 1e3,
-                "flops_per_launch": kflops[labels[top]],
-                "peak_source": pk["source"] + " bf16_tflops (burst: kernel timed alone between CUDA events)",
-                "step": {"flops_per_step": flops_step, "achieved_tflops": flops_step / step_s / 1e12,
-                         "frac_of_sustained_peak": flops_step / step_s / 1e12 / pk["bf16_tflops_sustained"]},
-                "kernels_us": breakdown}
-    else:
-        ach = bytes_step / (kms[top] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                "traffic": None, "kernel": labels[top], "kernel_us": float(kms[top]) * 1e3,
-                "bytes_per_launch": bytes_step, "peak_source": pk["source"] + " hbm_gbs",
-                "note": "launch-latency bound by construction: the step's algorithmic bytes take < 0.1 us at HBM speed",
-                "kernels_us": breakdown}
+    K, W = args.steps, args.warmup
+    w = Workload(G, args, args.workload, rank, world, local_rank, dist, torch)
+    h = w.h
+    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
+    value, ms, launches, clocks = w.resident(K, W, sampler)
+    Ke = max(3, min(K, args.e2e_steps))
+    e2e_value, h2d, d2h, last = w.e2e(Ke)
+    floor_us = h.launch_floor_us() if rank == 0 else None
+    roof = roofline_of(w, ms / K, pk, floor_us)
 
     # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------
     cpu = None
+    dims, B, replicas, prec = w.dims, w.B, w.replicas, w.prec
     if rank == 0 and world == 1 and not args.no_cpu:
         reps = 5 if dims == synth.WIDE else 20
         rows = 20 if replicas else (args.cpu_rows or cpu_rows_for_budget(dims, B, reps + 1, 1, 15.0))
@@ -394,25 +460,44 @@ def run_own(args):
         cpu = {"value": rate, "unit": "transitions/s", "cores": 1, "kind": "port",
                "sample": f"{reps} learn steps of {rows} rows of the same workload, single thread (the Gorgonia VM is "
                          f"single-threaded); oracle port, the Go reference cannot run here"}
+    path = {1: "generic", 2: "narrow", 3: "wide"}[h.path]
+    mode = {0: None, 1: "ncclAllReduce + update kernel",
+            2: "gradient exchange over NVLink peer memory (CUDA IPC) inside the update kernel"}[h.dp_mode()]
+    w.close()
+
+    # ---------------- the other single-GPU BASELINE configs, on the same record -----------
+    extra = None
+    if rank == 0 and world == 1 and args.workload == "wide" and not args.no_extra:
+        extra = {}
+        for name, key in (("cartpole4096", "configs[1]"), ("replicas", "configs[4] (one GPU's share: 128 of 1024 replicas)")):
+            x = Workload(G, args, name, 0, 1, local_rank, dist, torch)
+            Kx = max(K, 200)                      # microsecond steps: 200 of them are still a few ms
+            v, msx, lx, _ = x.resident(Kx, max(W, 3))
+            ev, h2dx, d2hx, _ = x.e2e(max(3, min(Kx, args.e2e_steps)))
+            rf = roofline_of(x, msx / Kx, pk, floor_us)
+            extra[name] = {"baseline_config": key, "value": v, "unit": "transitions/s", "us_per_step": msx / Kx * 1e3,
+                           "steps": Kx, "gpu_launches": int(lx), "e2e": {"value": ev, "h2d_bytes_per_step": h2dx,
+                                                                          "d2h_bytes_per_step": d2hx},
+                           "config": workload_config(args, x.dims, x.B, x.replicas, x.prec, name=name), "roofline": rf}
+            x.close()
 
     if rank == 0:
         line = {
             "metric": "dqn_transitions_trained_per_sec", "value": value, "unit": "transitions/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32",
+            "scaling": scaling_of(args), "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32",
             "data": "synthetic", "config": workload_config(args, dims, B, replicas, prec),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "what": "per step: goldq_replay_push of a fresh batch from pinned host memory (copy stream, "
-                            "overlapping the previous step) + goldq_learn with host indices + goldq_last_loss "
-                            "readback (sync); host wall clock, max over ranks"},
+                    "what": "per step: goldq_replay_push_packed of a fresh batch from ONE pinned host buffer (copy "
+                            "stream, overlapping the previous step) + goldq_learn with pinned host indices + "
+                            "goldq_last_loss readback (sync); host wall clock, max over ranks"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "path": {1: "generic", 2: "narrow", 3: "wide"}[h.path], "last_loss": [float(x) for x in last[:4]],
-            "allreduce": {0: None, 1: "ncclAllReduce + update kernel", 2: "gradient exchange over NVLink peer memory (CUDA IPC) inside the update kernel"}[h.dp_mode()],
+            "path": path, "last_loss": [float(x) for x in last[:4]], "allreduce": mode,
+            "configs": extra,
         }
         emit(line)
-    h.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -450,6 +535,10 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--chunk", type=int, default=64, help="learn steps per goldq_learn_many call")
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="N > 1, wide workload: strong (default) = --global-batch rows over the ranks; weak = 8192 rows per GPU")
+    ap.add_argument("--global-batch", type=int, default=65536, help="configs[3]: global batch of the data-parallel step")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[1] / configs[4] workloads on the N=1 line")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample nvidia-smi during the timed region")
     ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for --impl reference")

@@ -1535,6 +1535,37 @@ int goldq_debug_fetch(goldq_t *h, int what, void *out, int64_t out_bytes)
     return GOLDQ_OK;
 }
 
+__global__ void empty_kernel() {}
+
+/* Diagnostic: the launch-latency floor the latency-bound configurations are compared with.  One
+ * empty kernel per node of a 16-node CUDA graph (the shape of a goldq_learn_many chunk of the
+ * single-launch narrow path), replayed `reps` times on the handle's stream; *us_per_launch = device
+ * time per node between CUDA events. */
+int goldq_launch_floor(goldq_t *h, int32_t reps, float *us_per_launch)
+{
+    if (!h || !us_per_launch || reps < 1) return fail(h, GOLDQ_EINVAL, "launch_floor: bad argument");
+    CK(h, cudaSetDevice(h->dev));
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CK(h, cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < 16; i++) empty_kernel<<<1, 32, 0, h->st>>>();
+    cudaError_t e = cudaStreamEndCapture(h->st, &graph);
+    if (e != cudaSuccess) return fail(h, GOLDQ_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(h, GOLDQ_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    for (int i = 0; i < 3; i++) cudaGraphLaunch(exec, h->st);
+    CK(h, cudaEventRecord(h->ev0, h->st));
+    for (int i = 0; i < reps; i++) cudaGraphLaunch(exec, h->st);
+    CK(h, cudaEventRecord(h->ev1, h->st));
+    CK(h, cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    cudaGraphExecDestroy(exec);
+    *us_per_launch = ms * 1e3f / (16.f * (float)reps);
+    return GOLDQ_OK;
+}
+
 int goldq_timer_start(goldq_t *h)
 {
     if (!h) return GOLDQ_EINVAL;

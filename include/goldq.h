@@ -224,6 +224,9 @@ void *goldq_stream(goldq_t *h);                              /* the cudaStream_t
 int64_t goldq_launch_count(const goldq_t *h);                /* kernels launched so far by this handle */
 int goldq_debug_enable(goldq_t *h, int on);                  /* keep Q/TD/grad snapshots of each step */
 int goldq_debug_fetch(goldq_t *h, int what, void *out, int64_t out_bytes);
+/* Diagnostic: device time per node of a 16-node graph of empty kernels replayed `reps` times -- the
+ * launch-latency floor that the latency-bound CartPole configurations are reported against. */
+int goldq_launch_floor(goldq_t *h, int32_t reps, float *us_per_launch);
 /* CUDA-event timer on the handle's stream (bench.py): start; ...; stop → ms. */
 int goldq_timer_start(goldq_t *h);
 int goldq_timer_stop(goldq_t *h, float *ms);
