@@ -38,3 +38,20 @@ def test_own_arm_fails_loudly_without_a_gpu():
     assert p.returncode != 0
     assert not [l for l in p.stdout.splitlines() if l.strip().startswith("{")]
     assert "CUDA" in (p.stderr + p.stdout) or "GPU" in (p.stderr + p.stdout)
+
+
+def test_reference_arm_under_torchrun_env_uses_all_cores_and_the_stated_global_batch():
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm must still use the box's cores (round 1's
+    N>1 ratios were void because it did not), rank 0 alone reports, and N>1 is configs[3] at its
+    stated global batch of 65536 (strong scaling)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+                        "--warmup", "1", "--cpu-budget", "2"], cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    j = json.loads([l for l in p.stdout.splitlines() if l.strip()][0])
+    assert j["cpu_baseline"]["cores"] == min(len(os.sched_getaffinity(0)), 64)
+    assert j["scaling"] == "strong" and j["config"]["global_batch"] == 65536 and j["config"]["batch_per_gpu"] == 32768
+    env["RANK"] = "1"
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+                        "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0 and not p.stdout.strip()
