@@ -65,16 +65,40 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed regions (B200_PROFILING.md).  The resident leg lasts
+    a few milliseconds, far below nvidia-smi's sampling period, so NVML is polled directly from a thread
+    (about every millisecond); samples are kept for the spans marked with begin()/end() only.  Falls back
+    to `nvidia-smi -lms` (all samples of the run) when pynvml is unavailable."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv, self.spans, self.samples = index, [], None, None, [], []
+        self._stop = False
+        self._in = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # the process may see a subset of the box's GPUs: resolve the CUDA device through its UUID/visible list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    phys = int(ids[self.index])
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -84,11 +108,43 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self._in = True
+
+    def end(self):
+        self._in = False
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+                self.samples.append((self._in, mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv:
+            self._stop = True
+            self.t.join(timeout=2)
+            inside = [x for x in self.samples if x[0]] or self.samples
+            sm = [x[1] for x in inside]
+            bits = 0
+            for x in inside:
+                bits |= x[2]
+            reasons = sorted(name for bit, name in self.REASONS.items() if bits & bit)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "samples": len(sm),
+                    "samples_total": len(self.samples), "reasons": reasons,
+                    "how": "NVML polled from a thread, samples inside the timed regions (resident + e2e legs)"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -106,7 +162,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "how": "nvidia-smi -lms 100 over the whole run"}
 
 
 def pinned_array(G, shape, dtype):
@@ -299,21 +355,20 @@ class Workload:
         self.run_resident(0, W)
         h.sync()
         self.barrier()
-        if sampler:
-            sampler.start()
-            time.sleep(0.25)
-        self.barrier()
         l0 = h.launch_count()
+        if sampler:
+            sampler.begin()
         h.timer_start()
         self.run_resident(W, K)
         ms = h.timer_stop()
+        if sampler:
+            sampler.end()
         self.barrier()
         launches = h.launch_count() - l0
         ms = self.max_over_ranks(ms)
-        clocks = sampler.stop() if sampler else None
-        return self.rows * self.world * K / (ms * 1e-3), ms, launches, clocks
+        return self.rows * self.world * K / (ms * 1e-3), ms, launches
 
-    def e2e(self, K):
+    def e2e(self, K, sampler=None):
         """The same metric through the public C ABI with HOST buffers.  Every step: B fresh transitions
         pushed from ONE pinned host buffer (goldq_replay_push_packed: one H2D copy on the library's copy
         stream, overlapping the previous step), the sampled index list from pinned host memory (H2D),
@@ -350,11 +405,15 @@ class Workload:
         for i in range(3):
             step(i)
         self.barrier()
+        if sampler:
+            sampler.begin()
         t0 = time.perf_counter()
         for i in range(3, 3 + K):
             last = step(i)
         self.barrier()
         sec = self.max_over_ranks(time.perf_counter() - t0)
+        if sampler:
+            sampler.end()
         return self.rows * self.world * K / sec, h2d, d2h, last
 
     def breakdown(self):
@@ -444,9 +503,12 @@ def run_own(args):
     w = Workload(G, args, args.workload, rank, world, local_rank, dist, torch)
     h = w.h
     sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
-    value, ms, launches, clocks = w.resident(K, W, sampler)
+    if sampler:
+        sampler.start()
+    value, ms, launches = w.resident(K, W, sampler)
     Ke = max(3, min(K, args.e2e_steps))
-    e2e_value, h2d, d2h, last = w.e2e(Ke)
+    e2e_value, h2d, d2h, last = w.e2e(Ke, sampler)
+    clocks = sampler.stop() if sampler else None
     floor_us = h.launch_floor_us() if rank == 0 else None
     roof = roofline_of(w, ms / K, pk, floor_us)
 
@@ -472,7 +534,7 @@ def run_own(args):
         for name, key in (("cartpole4096", "configs[1]"), ("replicas", "configs[4] (one GPU's share: 128 of 1024 replicas)")):
             x = Workload(G, args, name, 0, 1, local_rank, dist, torch)
             Kx = max(K, 200)                      # microsecond steps: 200 of them are still a few ms
-            v, msx, lx, _ = x.resident(Kx, max(W, 3))
+            v, msx, lx = x.resident(Kx, max(W, 3))
             ev, h2dx, d2hx, _ = x.e2e(max(3, min(Kx, args.e2e_steps)))
             rf = roofline_of(x, msx / Kx, pk, floor_us)
             extra[name] = {"baseline_config": key, "value": v, "unit": "transitions/s", "us_per_step": msx / Kx * 1e3,

@@ -636,6 +636,345 @@ constexpr size_t ff_smem_bytes()
 }
 
 // ---------------------------------------------------------------------------
+// Fused forward on CTA PAIRS (cta_group::2).  Same dataflow as ff_forward_kernel, but two CTAs of a
+// cluster -- two SMs of one TPC -- share every tcgen05.mma: M = 256 (each CTA's 128-row slab is the
+// A operand for its own half of the rows and its own TMEM holds its rows of D), and the B operand's
+// N columns are SPLIT between the two CTAs' shared memory.  Each SM therefore ingests HALF of every
+// weight tile (16 KB instead of 32 KB per k-block): the measured limiter of the single-CTA kernel
+// was the SM's L2 ingest of the re-streamed weights (98.8 MB L2->SM per launch).
+//
+// Protocol (leader = cluster rank 0):
+//   TMA       both CTAs load their X tile and their half of each weight tile; all completion bytes
+//             are counted on the LEADER's full barriers (cp.async.bulk.tensor .cta_group::2)
+//   MMA       one thread of the leader issues tcgen05.mma.cta_group::2; tcgen05.commit multicasts
+//             "stage free" / "accumulator ready" to the barriers of BOTH CTAs
+//   epilogue  8 warps per CTA drain their own TMEM, write H (bf16, K-major SW128 boxes) into their
+//             own shared memory and arrive (release.cluster) on the LEADER's h_lo / h_ready /
+//             acc_free barriers, which the leader's MMA thread acquires at cluster scope
+// Epilogue arithmetic per element pair: two fp32 bias adds (bias staged in shared memory, read as
+// broadcast float4), one cvt.rn.bf16x2, one max.bf16x2 against -0.0 (Rectify keeps the sign of a*0,
+// nn.go:162-189: the sign bit is the mask) -- about half the instructions of the single-CTA version.
+// Layer 3 uses W3 padded to 128 columns (N = 128: 64 from each CTA; only columns < A are read back).
+// ---------------------------------------------------------------------------
+constexpr int FF2_WSTAGES = 5;
+constexpr uint32_t FF2_WSTAGE_BYTES = 16384;   // this CTA's half of a [64 k][256 n] tile: [2 n-groups][64 k-rows][128 B]
+
+template <int KD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FF_THREADS, 1)
+ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+                   const __grid_constant__ CUtensorMap tmW1_0, const __grid_constant__ CUtensorMap tmW1_1,
+                   const __grid_constant__ CUtensorMap tmW2_0, const __grid_constant__ CUtensorMap tmW2_1,
+                   const __grid_constant__ CUtensorMap tmW3_0, const __grid_constant__ CUtensorMap tmW3_1,
+                   const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmH2,
+                   const FFArgs g)
+{
+    constexpr uint32_t X_BYTES = KD * FF_BOX;
+    constexpr uint32_t IDESC_256 = make_idesc_bf16(256, 256, false, true);
+    constexpr uint32_t IDESC_128 = make_idesc_bf16(256, 128, false, true);
+    constexpr int KH = FF_H / 64;                       // 8 k-blocks of layers 2 and 3
+    constexpr uint16_t BOTH = 3;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sH = smem;                                 // 8 boxes: H1, then H2
+    uint8_t *sX = sH + (KH - KD) * FF_BOX;              // aliases the last boxes of H (see ff_forward_kernel)
+    uint8_t *sW = sH + KH * FF_BOX;                     // weight ring
+    __shared__ uint64_t full_w[FF2_WSTAGES], empty_w[FF2_WSTAGES], x_full, acc_full[2], acc_free[2], h_ready, h_lo;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float s_bias[2 * FF_H + 32];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int net = blockIdx.y;
+    const int m0 = blockIdx.x * BM;
+    const uint32_t rank = cluster_ctarank();            // 0 = leader
+    const CUtensorMap *tmX = net ? &tmX1 : &tmX0;
+    const CUtensorMap *tmW1 = net ? &tmW1_1 : &tmW1_0;
+    const CUtensorMap *tmW2 = net ? &tmW2_1 : &tmW2_0;
+    const CUtensorMap *tmW3 = net ? &tmW3_1 : &tmW3_0;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(tmX); prefetch_tmap(tmW1); prefetch_tmap(tmW2); prefetch_tmap(tmW3);
+        for (int s = 0; s < FF2_WSTAGES; s++) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 1); }
+        mbar_init(&x_full, 1);
+        mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+        // the leader's copies collect the arrivals of both CTAs
+        mbar_init(&acc_free[0], 2 * (FF_EPI_THREADS / 32)); mbar_init(&acc_free[1], 2 * (FF_EPI_THREADS / 32));
+        mbar_init(&h_ready, 2);
+        mbar_init(&h_lo, 2);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(&tmem_base_slot, 512);
+    pdl_launch_dependents();
+    tc_fence_before();
+    cluster_sync();          // both CTAs' barriers are initialised and both TMEM allocations exist
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own X tile, own half of every weight tile =====
+        if (elect_one()) {
+            const uint32_t x_full_leader = mapa_u32(&x_full, 0);
+            if (rank == 0) mbar_expect_tx(&x_full, 2 * X_BYTES);
+            for (int kb = 0; kb < KD; kb++) tma_load_2d_pair(sX + kb * FF_BOX, tmX, kb * 64, m0, x_full_leader);
+            int it = 0;
+            // one ring stage = 2 boxes of [64 k][64 n]
+            auto load_w = [&](const CUtensorMap *tm, int n0, int k0, int n1, int k1) {
+                const int s = it % FF2_WSTAGES;
+                const uint32_t ph = (it / FF2_WSTAGES) & 1;
+                mbar_wait_bounded<false>(&empty_w[s], ph ^ 1);                    // own ring slot free (leader's commit reaches both CTAs)
+                if (rank == 0) mbar_expect_tx(&full_w[s], 2 * FF2_WSTAGE_BYTES);
+                const uint32_t bar = mapa_u32(&full_w[s], 0);
+                tma_load_2d_pair(sW + s * FF2_WSTAGE_BYTES, tm, n0, k0, bar);
+                tma_load_2d_pair(sW + s * FF2_WSTAGE_BYTES + 8192, tm, n1, k1, bar);
+                it++;
+            };
+            const int nr = (int)rank * 128;                        // this CTA's half of a 256-column tile
+            for (int half = 0; half < 2; half++)
+                for (int kb = 0; kb < KD; kb++) load_w(tmW1, half * 256 + nr, kb * 64, half * 256 + nr + 64, kb * 64);
+            for (int half = 0; half < 2; half++)
+                for (int kb = 0; kb < KH; kb++) load_w(tmW2, half * 256 + nr, kb * 64, half * 256 + nr + 64, kb * 64);
+            // layer 3: N = 128, this CTA's 64 columns; a ring stage holds two k-blocks
+            for (int kq = 0; kq < KH / 2; kq++) load_w(tmW3, (int)rank * 64, kq * 128, (int)rank * 64, kq * 128 + 64);
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===== MMA issuer (leader only) =====
+            int it = 0;
+            auto mma_block = [&](uint32_t a_box_addr, uint32_t d_tmem, bool first) {
+                const int s = it % FF2_WSTAGES;
+                const uint32_t ph = (it / FF2_WSTAGES) & 1;
+                mbar_wait_cluster(&full_w[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t baddr = smem_u32(sW + s * FF2_WSTAGE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / UK; kk++)
+                        mma_bf16_pair(d_tmem, make_smem_desc(a_box_addr + kk * 32, 16, 1024),
+                                      make_smem_desc(baddr + kk * 2048, 8192, 1024), IDESC_256, (!first || kk) ? 1u : 0u);
+                    mma_commit_pair(&empty_w[s], BOTH);
+                }
+                __syncwarp();
+                it++;
+            };
+            // layer 1: A = X
+            mbar_wait_cluster(&x_full, 0);
+            for (int half = 0; half < 2; half++) {
+                for (int kb = 0; kb < KD; kb++) mma_block(smem_u32(sX + kb * FF_BOX), tmem + half * 256, kb == 0);
+                if (elect_one()) mma_commit_pair(&acc_full[half], BOTH);
+                __syncwarp();
+            }
+            // layer 2: A = H1.  Its first four k-blocks need only what the epilogues of accumulator half 0
+            // wrote: they start while half 1 is still being drained (in both CTAs).
+            mbar_wait_cluster(&h_lo, 0);
+            mbar_wait_cluster(&acc_free[0], 0);
+            tc_fence_after();
+            for (int half = 0; half < 2; half++) {
+                for (int kb = 0; kb < KH; kb++) {
+                    if (half == 0 && kb == KH / 2) {
+                        mbar_wait_cluster(&h_ready, 0);
+                        mbar_wait_cluster(&acc_free[1], 0);
+                        tc_fence_after();
+                    }
+                    mma_block(smem_u32(sH + kb * FF_BOX), tmem + half * 256, kb == 0);
+                }
+                if (elect_one()) mma_commit_pair(&acc_full[half], BOTH);
+                __syncwarp();
+            }
+            // layer 3: A = H2, N = 128; the first two ring stages (k-blocks 0..3) need only the first half of H2
+            mbar_wait_cluster(&h_lo, 1);
+            mbar_wait_cluster(&acc_free[0], 1);
+            tc_fence_after();
+            for (int kq = 0; kq < KH / 2; kq++) {
+                if (kq == KH / 4) {
+                    mbar_wait_cluster(&h_ready, 1);
+                    mbar_wait_cluster(&acc_free[1], 1);
+                    tc_fence_after();
+                }
+                const int s = it % FF2_WSTAGES;
+                const uint32_t ph = (it / FF2_WSTAGES) & 1;
+                mbar_wait_cluster(&full_w[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t baddr = smem_u32(sW + s * FF2_WSTAGE_BYTES);
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+#pragma unroll
+                        for (int kk = 0; kk < BK / UK; kk++)
+                            mma_bf16_pair(tmem, make_smem_desc(smem_u32(sH + (kq * 2 + h) * FF_BOX) + kk * 32, 16, 1024),
+                                          make_smem_desc(baddr + h * 8192 + kk * 2048, 8192, 1024), IDESC_128,
+                                          (kq || h || kk) ? 1u : 0u);
+                    mma_commit_pair(&empty_w[s], BOTH);
+                }
+                __syncwarp();
+                it++;
+            }
+            if (elect_one()) mma_commit_pair(&acc_full[0], BOTH);
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue warps (both CTAs, own rows) =====
+        const int q = warp & 3;                 // TMEM lane quarter
+        const int cg = (warp - 2) >> 2;         // column group within a half: chunks cg*4 .. cg*4+3
+        const int rt = q * 32 + lane;           // row within the slab
+        const int et = threadIdx.x - 64;        // 0..255
+        const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+        const uint32_t acc_free_leader0 = mapa_u32(&acc_free[0], 0), acc_free_leader1 = mapa_u32(&acc_free[1], 0);
+        const uint32_t h_lo_leader = mapa_u32(&h_lo, 0), h_ready_leader = mapa_u32(&h_ready, 0);
+        // biases of the three layers -> shared memory (read back as broadcast float4)
+        for (int i = et; i < 2 * FF_H + 32; i += FF_EPI_THREADS) {
+            float v = 0.f;
+            if (i < FF_H) v = __ldg(g.bias[net][0] + i);
+            else if (i < 2 * FF_H) v = __ldg(g.bias[net][1] + i - FF_H);
+            else if (i - 2 * FF_H < g.A) v = __ldg(g.bias[net][2] + i - 2 * FF_H);
+            s_bias[i] = v;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+
+        const __nv_bfloat162 neg0 = __floats2bfloat162_rn(-0.0f, -0.0f);
+        auto pack_chunk = [&](const uint32_t(&r)[32], const float *bias32, uint32_t(&packed)[16]) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b = *reinterpret_cast<const float4 *>(bias32 + j);
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
+                p0 = __hmax2(p0, neg0);         // Rectify: negative (and NaN) -> -0.0, sign bit = mask
+                p1 = __hmax2(p1, neg0);
+                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&p0);
+                packed[(j >> 1) + 1] = *reinterpret_cast<uint32_t *>(&p1);
+            }
+        };
+        auto store_chunk = [&](int c0, const uint32_t(&packed)[16]) {
+            uint8_t *dst = sH + (c0 >> 6) * FF_BOX + rt * 128;
+            const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+                *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
+                    make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+        };
+        auto col0 = [&](int half, int c) { return half * 256 + (cg * 4 + c) * 32; };
+
+        // ---- layer 1 -> H1.  The TMEM load of chunk c+1 is in flight while chunk c is packed.
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            mbar_wait_bounded<false>(&acc_full[half], 0);
+            tc_fence_after();
+            uint32_t r[2][32];
+            tmem_ld_32x32(tq + (uint32_t)col0(half, 0), r[0]);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                tmem_ld_wait();
+                if (c < 3) tmem_ld_32x32(tq + (uint32_t)col0(half, c + 1), r[(c + 1) & 1]);
+                uint32_t packed[16];
+                pack_chunk(r[c & 1], s_bias + col0(half, c), packed);
+                store_chunk(col0(half, c), packed);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(half ? acc_free_leader1 : acc_free_leader0);
+            if (half == 0) {           // boxes 0..3 of H1 are complete in this CTA
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et == 0) mbar_arrive_cluster(h_lo_leader);
+            }
+        }
+        fence_proxy_async_smem();      // H1 complete: visible to the async proxy (layer-2 MMA, TMA store)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+            if (net == 0) {            // the backward pass needs the online network's activations
+                for (int b = 0; b < KH; b++) tma_store_2d(&tmH1, sH + b * FF_BOX, 64 * b, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            mbar_arrive_cluster(h_ready_leader);
+        }
+
+        // ---- layer 2 -> H2, which overwrites H1 in place.  Accumulator half 0 is drained into
+        // registers while the MMAs of half 1 still read H1; it is written out once they retire.
+        {
+            uint32_t hold[4][16];
+            uint32_t r[32];
+            mbar_wait_bounded<false>(&acc_full[0], 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                tmem_ld_32x32(tq + (uint32_t)col0(0, c), r);
+                tmem_ld_wait();
+                pack_chunk(r, s_bias + FF_H + col0(0, c), hold[c]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_free_leader0);
+            // every layer-2 MMA (of the pair) has read H1 once acc_full[1] fires; the H1 TMA store must
+            // also have finished reading this CTA's tile
+            mbar_wait_bounded<false>(&acc_full[1], 1);
+            tc_fence_after();
+            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            tmem_ld_32x32(tq + (uint32_t)col0(1, 0), r);
+#pragma unroll
+            for (int c = 0; c < 4; c++) store_chunk(col0(0, c), hold[c]);
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) mbar_arrive_cluster(h_lo_leader);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (c) tmem_ld_32x32(tq + (uint32_t)col0(1, c), r);
+                tmem_ld_wait();
+                uint32_t packed[16];
+                pack_chunk(r, s_bias + FF_H + col0(1, c), packed);
+                store_chunk(col0(1, c), packed);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_free_leader1);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+            if (net == 0) {
+                for (int b = 0; b < KH; b++) tma_store_2d(&tmH2, sH + b * FF_BOX, 64 * b, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            mbar_arrive_cluster(h_ready_leader);
+        }
+
+        // ---- layer 3: Q = acc + b3 -> fp32 [B][A] (A <= 32: one chunk), staged in the idle weight ring
+        // and copied out coalesced (the rows of a slab are contiguous in Q)
+        if (cg == 0) {
+            mbar_wait_bounded<false>(&acc_full[0], 0);          // third completion of acc_full[0]: parity 0 again
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld_32x32(tq, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            float *sQ = reinterpret_cast<float *>(sW);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const float v = __uint_as_float(r[j]) + s_bias[2 * FF_H + j];
+                if (j < g.A) sQ[rt * g.A + j] = v;
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            const int rows = (g.B - m0 < BM) ? g.B - m0 : BM;
+            float *dst = g.q[net] + (size_t)m0 * g.A;
+            for (int i = et; i < rows * g.A; i += 128) dst[i] = sQ[i];
+        }
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync();          // nobody leaves while the pair's MMAs, commits or remote arrives may still touch it
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem, 512);
+    }
+}
+
+template <int KD>
+constexpr size_t ff2_smem_bytes()
+{
+    return (size_t)8 * FF_BOX + FF2_WSTAGES * FF2_WSTAGE_BYTES + 1024;
+}
+
+// ---------------------------------------------------------------------------
 // host: tensor maps
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -750,6 +1089,10 @@ cudaError_t configure_all_gemms()
         e = cudaFuncSetAttribute(ff_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<1>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(ff_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<2>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(ff_forward2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff2_smem_bytes<1>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(ff_forward2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff2_smem_bytes<2>());
     return e;
 }
 
@@ -809,7 +1152,7 @@ wide_gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx, uint64_t s
 // and W2 [H1][H2] are MN-major B operands of the forward GEMMs as stored (W2 is also the
 // K-major B operand of dX); W3 is padded to 64 columns for the forward tile, and kept
 // transposed [32][H2] for the dZ2 kernel's contiguous column reads.
-constexpr int W3_PAD = 64;
+constexpr int W3_PAD = 128;   // columns of the padded W3 shadow (the pair kernel runs layer 3 at N = 128)
 struct ShadowPtrs {
     __nv_bfloat16 *w1, *w2, *w3p, *w3t;
 };
@@ -1354,6 +1697,7 @@ struct WideState {
     cudaEvent_t ev_dz2 = nullptr, ev_dx = nullptr, ev_s1 = nullptr, ev_s2 = nullptr, ev_fork = nullptr, ev_gather = nullptr;
     bool pdl = true;
     bool ff = false;                       // fused three-layer forward kernel usable
+    bool ff2 = false;                      // ... on CTA pairs (cta_group::2): needs an even number of 128-row slabs
     bool bn256 = false;                    // 128x256 output tiles for the N = H GEMMs
     std::vector<const char *> prof_names;  // labels of the launches of the last profiled step
     bool mc_rows = false, mc_h1 = false;   // B-tile multicast usable: row tiles / H1 tiles divide by 4
@@ -1437,6 +1781,7 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     ok = ok && make_tmap(&w->net[0].tm_w2_k_s4, w->net[0].w2, d.H1, d.H2, d.H2, 32, err);
     ok = ok && make_tmap(&w->net[0].tm_w2_k256, w->net[0].w2, d.H1, d.H2, d.H2, 256, err);
     w->ff = getenv("GOLDQ_NO_FF") == nullptr && d.H1 == FF_H && d.H2 == FF_H && (d.D == 64 || d.D == 128) && d.A <= W3_PAD;
+    w->ff2 = w->ff && getenv("GOLDQ_NO_FF2") == nullptr && B % (2 * BM) == 0;
     w->bn256 = getenv("GOLDQ_NO_BN256") == nullptr && d.H1 % 256 == 0 && d.H2 % 256 == 0;   // 82.3 -> 79.7 us/step
     // measured on B200 (round 1): with 128x128 tiles the cluster's lock-step costs more than the
     // saved L2->SM traffic (95 vs 87 us/step), so B-tile multicast is opt-in
@@ -1648,7 +1993,15 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         fa.bias[1][0] = s.theta_t + o.b1; fa.bias[1][1] = s.theta_t + o.b2; fa.bias[1][2] = s.theta_t + o.b3;
         fa.q[0] = w->q; fa.q[1] = w->qt;
         dim3 grid((B + BM - 1) / BM, 2);
-        if (d.D == 128)
+        if (w->ff2 && d.D == 128)
+            WCK(launch_k(ff_forward2_kernel<2>, grid, dim3(FF_THREADS), ff2_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
+                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
+                         w->tm_h2_a, fa));
+        else if (w->ff2)
+            WCK(launch_k(ff_forward2_kernel<1>, grid, dim3(FF_THREADS), ff2_smem_bytes<1>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
+                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
+                         w->tm_h2_a, fa));
+        else if (d.D == 128)
             WCK(launch_k(ff_forward_kernel<2>, grid, dim3(FF_THREADS), ff_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
                          on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
                          w->tm_h2_a, fa));
@@ -1657,7 +2010,8 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
                          on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
                          w->tm_h2_a, fa));
         launches += 1;
-        mark("fused forward L1-L3 online+target (tcgen05)");
+        mark(w->ff2 ? "fused forward L1-L3 online+target, CTA pairs (tcgen05 cta_group::2)"
+                    : "fused forward L1-L3 online+target (tcgen05)");
     } else {
     // forward, online (problem 0) and target (problem 1) in one launch per layer
     g.M = B; g.N = d.H1; g.K = d.D; g.k_per_split = ((d.D + BK - 1) / BK) * BK;
@@ -1680,7 +2034,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     else
         WCK((launch_gemm<MODE_KM, 128, EPI_BIAS_RELU_BF16>(w->tm_h1_a, on.tm_w2_mn, g, 1, st, &w->tm_t1_a, &tg.tm_w2_mn, pdl, &w->tm_h2_a, &w->tm_t2_a)));
     mark("fwd L2 online+target (tcgen05)");
-    g.N = W3_PAD; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
+    g.N = 64; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;     // the first 64 of W3's padded columns
     g.out_bf16 = g.out_bf16_1 = nullptr; g.out_f32 = w->q; g.out_f32_1 = w->qt;
     g.bias = s.theta + o.b3; g.bias_1 = s.theta_t + o.b3; g.ldo = d.A; g.n_store = d.A;
     WCK((launch_gemm<MODE_KM, 64, EPI_BIAS_F32>(w->tm_h2_a, on.tm_w3p_mn, g, 1, st, &w->tm_t2_a, &tg.tm_w3p_mn, pdl)));

@@ -68,6 +68,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
+// Bounded variants: a wait that does not complete within ~2^26 polls (seconds) traps, so that a protocol
+// error surfaces as a launch failure instead of hanging the GPU.  CLUSTER: acquire at cluster scope
+// (the arrival came from the peer CTA and publishes its shared-memory writes).
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t i = 0; i < (1u << 26); i++) {
+        uint32_t ok;
+        if (CLUSTER)
+            asm volatile(
+                "{\n\t"
+                ".reg .pred P1;\n\t"
+                "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+                "selp.b32 %0, 1, 0, P1;\n\t"
+                "}\n"
+                : "=r"(ok)
+                : "r"(addr), "r"(parity)
+                : "memory");
+        else
+            asm volatile(
+                "{\n\t"
+                ".reg .pred P1;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+                "selp.b32 %0, 1, 0, P1;\n\t"
+                "}\n"
+                : "=r"(ok)
+                : "r"(addr), "r"(parity)
+                : "memory");
+        if (ok) return;
+    }
+    asm volatile("trap;");
+}
+
 // ---- TMA ----------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m)
 {
@@ -124,6 +158,69 @@ __device__ __forceinline__ void cluster_sync()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster whose ranks differ in bit 0 share one MMA ----
+// shared::cluster address of `p` (an address in THIS CTA's shared memory) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void *p, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+// arrive on a barrier anywhere in the cluster; release at cluster scope orders this thread's earlier
+// writes (and, through bar.sync, its CTA's) before the waiter's acquire
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) { mbar_wait_bounded<true>(bar, parity); }
+// TMA load into THIS CTA's shared memory whose completion bytes are counted on a barrier that may
+// live in the peer CTA of the pair (the leader's): `bar_cluster_addr` from mapa_u32
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *m, int c0, int c1,
+                                                 uint32_t bar_cluster_addr)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+// TMEM allocation of a CTA pair: issued by the same warp of BOTH CTAs, same shared-memory slot offset
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *smem_slot, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B over the pair: M = 256 (128 rows from each CTA's A tile), B's N columns
+// split between the two CTAs' shared memory (N/2 each); issued by ONE thread of the leader CTA
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all MMAs issued so far by this thread have completed) on the barrier at `bar`'s offset in
+// every CTA of `cta_mask`
+__device__ __forceinline__ void mma_commit_pair(uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
 }
 
 // ---- tcgen05 --------------------------------------------------------------------

@@ -73,7 +73,9 @@ def check(h, o, idx):
     h.set_adam_state(o.m, o.v, o.iter)
 
 
-@pytest.mark.parametrize("dims,B", [(synth.WIDE, 256), (synth.WIDE, 8192), ((64, 256, 128, 6), 200)])
+@pytest.mark.parametrize("dims,B", [(synth.WIDE, 256), (synth.WIDE, 8192), ((64, 256, 128, 6), 200),
+                                    ((64, 512, 512, 6), 512),      # fused forward on CTA pairs, one k-block in layer 1
+                                    (synth.WIDE, 384)])            # odd number of 128-row slabs: single-CTA fused forward
 def test_wide_bf16_learn_step(dims, B):
     N = max(2 * B, 1024)
     h, o = make(dims, B, N)
@@ -142,7 +144,7 @@ def _emulate_bf16_step(dims, th, tt, s, a, r, s2, done, gamma, count):
     return q, qt, td, loss, grads
 
 
-@pytest.mark.parametrize("dims,B", [(synth.WIDE, 512), ((64, 256, 128, 6), 200)])
+@pytest.mark.parametrize("dims,B", [(synth.WIDE, 512), ((64, 256, 128, 6), 200), ((64, 512, 512, 6), 256), (synth.WIDE, 384)])
 def test_wide_matches_bf16_emulation(dims, B):
     """Correctness independent of precision: against a numpy restatement that rounds to bf16
     at the same points, every gradient block must agree to accumulation-order noise."""
