@@ -17,7 +17,7 @@ LOSS_MSE, LOSS_PSEUDO_HUBER = 0, 1
 SOLVER_ADAM, SOLVER_RMSPROP = 0, 1
 PREC_FP32, PREC_BF16 = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_NARROW, PATH_WIDE = 0, 1, 2, 3
-DBG_Q_ONLINE, DBG_Q_TARGET, DBG_TD, DBG_GRADS, DBG_INDICES, DBG_BATCH_S, DBG_BATCH_A = range(7)
+DBG_Q_ONLINE, DBG_Q_TARGET, DBG_TD, DBG_GRADS, DBG_INDICES, DBG_BATCH_S, DBG_BATCH_A, DBG_FF_STAMPS = range(8)
 ABI_VERSION = 1
 
 # every symbol include/goldq.h declares (tests/test_abi.py checks header <-> list <-> .so)
@@ -370,7 +370,7 @@ class Handle:
             DBG_Q_ONLINE: ((RB, self.A), np.float32), DBG_Q_TARGET: ((RB, self.A), np.float32),
             DBG_TD: ((RB,), np.float32), DBG_GRADS: ((self.R * self.P,), np.float32),
             DBG_INDICES: ((RB,), np.int32), DBG_BATCH_S: ((RB, self.D), np.float32),
-            DBG_BATCH_A: ((RB,), np.int32),
+            DBG_BATCH_A: ((RB,), np.int32), DBG_FF_STAMPS: ((self.B // 128 * 2, 32), np.int64),
         }[what]
         out = np.empty(shape, dt)
         self._ck(self._L.goldq_debug_fetch(self._h, what, out.ctypes.data, out.nbytes))

@@ -1520,6 +1520,9 @@ int goldq_debug_fetch(goldq_t *h, int what, void *out, int64_t out_bytes)
     case GOLDQ_DBG_INDICES: src = narrow ? h->dbg_idx : h->d_idx; bytes = RB * 4; break;
     case GOLDQ_DBG_BATCH_S: src = h->bs; bytes = RB * d.D * 4; break;
     case GOLDQ_DBG_BATCH_A: src = h->ba; bytes = RB * 4; break;
+    case GOLDQ_DBG_FF_STAMPS:
+        if (h->wide) src = wide_ff_stamps(h->wide, &bytes);
+        break;
     default: return fail(h, GOLDQ_EINVAL, "debug_fetch: unknown selector");
     }
     if (!src) return fail(h, GOLDQ_EINVAL, "debug_fetch: not available on this path / before any step");

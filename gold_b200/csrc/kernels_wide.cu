@@ -316,10 +316,13 @@ constexpr int FF_WSTAGES = 3;
 constexpr uint32_t FF_BOX = 16384;            // [128 rows][64 bf16] swizzled box
 constexpr uint32_t FF_WSTAGE_BYTES = 32768;   // [4 n-groups][64 k-rows][128 B]
 
+constexpr int FF_NSTAMPS = 32;
 struct FFArgs {
     int B, D, A;
     const float *bias[2][3];     // [net][layer]
     float *q[2];                 // [net]: Q / Q' fp32 [B][A]
+    __nv_bfloat16 *h1, *h2;      // online network's activations [B][512] (pair kernel: stored from registers)
+    long long *stamps;           // diagnostic (GOLDQ_FF_STAMPS): [CTAs][FF_NSTAMPS] clock64 values, else nullptr
 };
 
 template <int KD>   // KD = D / 64 k-blocks of layer 1
@@ -687,6 +690,9 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     const int net = blockIdx.y;
     const int m0 = blockIdx.x * BM;
     const uint32_t rank = cluster_ctarank();            // 0 = leader
+    long long *const stp = g.stamps ? g.stamps + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * FF_NSTAMPS : nullptr;
+#define FF_STAMP(i) do { if (stp) stp[i] = clock64(); } while (0)
+    if (threadIdx.x == 0) FF_STAMP(0);
     const CUtensorMap *tmX = net ? &tmX1 : &tmX0;
     const CUtensorMap *tmW1 = net ? &tmW1_1 : &tmW1_0;
     const CUtensorMap *tmW2 = net ? &tmW2_1 : &tmW2_0;
@@ -710,6 +716,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
     pdl_wait();
+    if (threadIdx.x == 0) FF_STAMP(1);
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own X tile, own half of every weight tile =====
@@ -740,11 +747,16 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     } else if (warp == 1) {
         if (rank == 0) {
             // ===== MMA issuer (leader only) =====
+            // All waits are CTA-scope acquires.  A cluster-scope acquire on every poll costs ~850 cycles even
+            // on a completed barrier (measured: tools/ff_stamps.py, 16 k-blocks in 3.9 k cycles instead of
+            // 2.2 k), and it is not needed: operands arrive through the async proxy (TMA), and the peer's
+            // epilogue publishes H with fence.proxy.async + bar.sync before its release.cluster arrive --
+            // the data is read by the tensor core through the async proxy of the SM that wrote it.
             int it = 0;
             auto mma_block = [&](uint32_t a_box_addr, uint32_t d_tmem, bool first) {
                 const int s = it % FF2_WSTAGES;
                 const uint32_t ph = (it / FF2_WSTAGES) & 1;
-                mbar_wait_cluster(&full_w[s], ph);
+                mbar_wait_bounded<false>(&full_w[s], ph);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t baddr = smem_u32(sW + s * FF2_WSTAGE_BYTES);
@@ -758,42 +770,55 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 it++;
             };
             // layer 1: A = X
-            mbar_wait_cluster(&x_full, 0);
+            mbar_wait_bounded<false>(&x_full, 0);
+            if (lane == 0) FF_STAMP(2);
             for (int half = 0; half < 2; half++) {
                 for (int kb = 0; kb < KD; kb++) mma_block(smem_u32(sX + kb * FF_BOX), tmem + half * 256, kb == 0);
                 if (elect_one()) mma_commit_pair(&acc_full[half], BOTH);
                 __syncwarp();
             }
+            if (lane == 0) FF_STAMP(3);
             // layer 2: A = H1.  Its first four k-blocks need only what the epilogues of accumulator half 0
             // wrote: they start while half 1 is still being drained (in both CTAs).
-            mbar_wait_cluster(&h_lo, 0);
-            mbar_wait_cluster(&acc_free[0], 0);
+            mbar_wait_bounded<false>(&h_lo, 0);
+            if (lane == 0) FF_STAMP(21);
+            mbar_wait_bounded<false>(&acc_free[0], 0);
             tc_fence_after();
+            if (lane == 0) FF_STAMP(4);
             for (int half = 0; half < 2; half++) {
                 for (int kb = 0; kb < KH; kb++) {
                     if (half == 0 && kb == KH / 2) {
-                        mbar_wait_cluster(&h_ready, 0);
-                        mbar_wait_cluster(&acc_free[1], 0);
+                        if (lane == 0) FF_STAMP(17);
+                        mbar_wait_bounded<false>(&h_ready, 0);
+                        if (lane == 0) FF_STAMP(22);
+                        mbar_wait_bounded<false>(&acc_free[1], 0);
                         tc_fence_after();
+                        if (lane == 0) FF_STAMP(5);
                     }
                     mma_block(smem_u32(sH + kb * FF_BOX), tmem + half * 256, kb == 0);
                 }
                 if (elect_one()) mma_commit_pair(&acc_full[half], BOTH);
                 __syncwarp();
             }
+            if (lane == 0) FF_STAMP(6);
             // layer 3: A = H2, N = 128; the first two ring stages (k-blocks 0..3) need only the first half of H2
-            mbar_wait_cluster(&h_lo, 1);
-            mbar_wait_cluster(&acc_free[0], 1);
+            mbar_wait_bounded<false>(&h_lo, 1);
+            if (lane == 0) FF_STAMP(23);
+            mbar_wait_bounded<false>(&acc_free[0], 1);
             tc_fence_after();
+            if (lane == 0) FF_STAMP(7);
             for (int kq = 0; kq < KH / 2; kq++) {
                 if (kq == KH / 4) {
-                    mbar_wait_cluster(&h_ready, 1);
-                    mbar_wait_cluster(&acc_free[1], 1);
+                    if (lane == 0) FF_STAMP(18);
+                    mbar_wait_bounded<false>(&h_ready, 1);
+                    if (lane == 0) FF_STAMP(24);
+                    mbar_wait_bounded<false>(&acc_free[1], 1);
                     tc_fence_after();
+                    if (lane == 0) FF_STAMP(8);
                 }
                 const int s = it % FF2_WSTAGES;
                 const uint32_t ph = (it / FF2_WSTAGES) & 1;
-                mbar_wait_cluster(&full_w[s], ph);
+                mbar_wait_bounded<false>(&full_w[s], ph);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t baddr = smem_u32(sW + s * FF2_WSTAGE_BYTES);
@@ -811,6 +836,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
             }
             if (elect_one()) mma_commit_pair(&acc_full[0], BOTH);
             __syncwarp();
+            if (lane == 0) FF_STAMP(9);
         }
     } else {
         // ===== epilogue warps (both CTAs, own rows) =====
@@ -853,12 +879,24 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                     make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
         };
         auto col0 = [&](int half, int c) { return half * 256 + (cg * 4 + c) * 32; };
+        // The online network's H1 / H2 also go to global memory for the backward pass, straight from the
+        // packed registers (64 contiguous bytes per row and chunk): a TMA store of the 128 KB tile would
+        // queue on the same TMA unit as the weight stream and stall the MMAs behind it (measured: the k-blocks
+        // after each store took 2x their MMA time)
+        const bool keep = (net == 0) && (m0 + rt < g.B);
+        auto store_global = [&](__nv_bfloat16 *base, int c0, const uint32_t(&packed)[16]) {
+            if (!keep) return;
+            uint4 *dst = reinterpret_cast<uint4 *>(base + (size_t)(m0 + rt) * FF_H + c0);
+#pragma unroll
+            for (int v = 0; v < 4; v++) dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+        };
 
         // ---- layer 1 -> H1.  The TMEM load of chunk c+1 is in flight while chunk c is packed.
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             mbar_wait_bounded<false>(&acc_full[half], 0);
             tc_fence_after();
+            if (et == 0 && half == 0) FF_STAMP(10);
             uint32_t r[2][32];
             tmem_ld_32x32(tq + (uint32_t)col0(half, 0), r[0]);
 #pragma unroll
@@ -868,23 +906,23 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 uint32_t packed[16];
                 pack_chunk(r[c & 1], s_bias + col0(half, c), packed);
                 store_chunk(col0(half, c), packed);
+                store_global(g.h1, col0(half, c), packed);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(half ? acc_free_leader1 : acc_free_leader0);
             if (half == 0) {           // boxes 0..3 of H1 are complete in this CTA
+                if (et == 0) FF_STAMP(25);
                 fence_proxy_async_smem();
+                if (et == 0) FF_STAMP(26);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (et == 0) mbar_arrive_cluster(h_lo_leader);
+                if (et == 0) { FF_STAMP(27); mbar_arrive_cluster(h_lo_leader); FF_STAMP(28); }
             }
         }
         fence_proxy_async_smem();      // H1 complete: visible to the async proxy (layer-2 MMA, TMA store)
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
-            if (net == 0) {            // the backward pass needs the online network's activations
-                for (int b = 0; b < KH; b++) tma_store_2d(&tmH1, sH + b * FF_BOX, 64 * b, m0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+            FF_STAMP(11);
             mbar_arrive_cluster(h_ready_leader);
         }
 
@@ -895,6 +933,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
             uint32_t r[32];
             mbar_wait_bounded<false>(&acc_full[0], 1);
             tc_fence_after();
+            if (et == 0) FF_STAMP(12);
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 tmem_ld_32x32(tq + (uint32_t)col0(0, c), r);
@@ -906,13 +945,17 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
             if (lane == 0) mbar_arrive_cluster(acc_free_leader0);
             // every layer-2 MMA (of the pair) has read H1 once acc_full[1] fires; the H1 TMA store must
             // also have finished reading this CTA's tile
+            if (et == 0) FF_STAMP(19);
             mbar_wait_bounded<false>(&acc_full[1], 1);
             tc_fence_after();
-            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) FF_STAMP(13);
             tmem_ld_32x32(tq + (uint32_t)col0(1, 0), r);
 #pragma unroll
-            for (int c = 0; c < 4; c++) store_chunk(col0(0, c), hold[c]);
+            for (int c = 0; c < 4; c++) {
+                store_chunk(col0(0, c), hold[c]);
+                store_global(g.h2, col0(0, c), hold[c]);
+            }
+            if (et == 0) FF_STAMP(20);
             fence_proxy_async_smem();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et == 0) mbar_arrive_cluster(h_lo_leader);
@@ -923,6 +966,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 uint32_t packed[16];
                 pack_chunk(r, s_bias + FF_H + col0(1, c), packed);
                 store_chunk(col0(1, c), packed);
+                store_global(g.h2, col0(1, c), packed);
             }
             tc_fence_before();
             __syncwarp();
@@ -931,10 +975,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
-            if (net == 0) {
-                for (int b = 0; b < KH; b++) tma_store_2d(&tmH2, sH + b * FF_BOX, 64 * b, m0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+            FF_STAMP(14);
             mbar_arrive_cluster(h_ready_leader);
         }
 
@@ -943,6 +984,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         if (cg == 0) {
             mbar_wait_bounded<false>(&acc_full[0], 0);          // third completion of acc_full[0]: parity 0 again
             tc_fence_after();
+            if (et == 0) FF_STAMP(15);
             uint32_t r[32];
             tmem_ld_32x32(tq, r);
             tmem_ld_wait();
@@ -958,8 +1000,9 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
             float *dst = g.q[net] + (size_t)m0 * g.A;
             for (int i = et; i < rows * g.A; i += 128) dst[i] = sQ[i];
         }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (et == 0) FF_STAMP(16);
     }
+#undef FF_STAMP
     tc_fence_before();
     cluster_sync();          // nobody leaves while the pair's MMAs, commits or remote arrives may still touch it
     if (warp == 1) {
@@ -1697,6 +1740,7 @@ struct WideState {
     cudaEvent_t ev_dz2 = nullptr, ev_dx = nullptr, ev_s1 = nullptr, ev_s2 = nullptr, ev_fork = nullptr, ev_gather = nullptr;
     bool pdl = true;
     bool ff = false;                       // fused three-layer forward kernel usable
+    long long *ff_stamps = nullptr;        // GOLDQ_FF_STAMPS: in-kernel clock stamps of the fused forward (diagnostic)
     bool ff2 = false;                      // ... on CTA pairs (cta_group::2): needs an even number of 128-row slabs
     bool bn256 = false;                    // 128x256 output tiles for the N = H GEMMs
     std::vector<const char *> prof_names;  // labels of the launches of the last profiled step
@@ -1782,6 +1826,10 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     ok = ok && make_tmap(&w->net[0].tm_w2_k256, w->net[0].w2, d.H1, d.H2, d.H2, 256, err);
     w->ff = getenv("GOLDQ_NO_FF") == nullptr && d.H1 == FF_H && d.H2 == FF_H && (d.D == 64 || d.D == 128) && d.A <= W3_PAD;
     w->ff2 = w->ff && getenv("GOLDQ_NO_FF2") == nullptr && B % (2 * BM) == 0;
+    if (w->ff2 && getenv("GOLDQ_FF_STAMPS")) {
+        const size_t n = (size_t)(B / BM) * 2 * FF_NSTAMPS;
+        if (dmalloc(&w->ff_stamps, n, err)) cudaMemset(w->ff_stamps, 0, n * sizeof(long long));
+    }
     w->bn256 = getenv("GOLDQ_NO_BN256") == nullptr && d.H1 % 256 == 0 && d.H2 % 256 == 0;   // 82.3 -> 79.7 us/step
     // measured on B200 (round 1): with 128x128 tiles the cluster's lock-step costs more than the
     // saved L2->SM traffic (95 vs 87 us/step), so B-tile multicast is opt-in
@@ -1825,7 +1873,7 @@ void wide_destroy(WideState *w)
         for (void *q : p)
             if (q) cudaFree(q);
     }
-    void *p[] = {w->h1, w->h2, w->t1, w->t2, w->dz2, w->dz1, w->dqT, w->q, w->qt, w->td, w->dqv, w->w1_slices, w->w2_slices, w->w3_slices, w->b1_part, w->b2_part, w->row_part};
+    void *p[] = {w->ff_stamps, w->h1, w->h2, w->t1, w->t2, w->dz2, w->dz1, w->dqT, w->q, w->qt, w->td, w->dqv, w->w1_slices, w->w2_slices, w->w3_slices, w->b1_part, w->b2_part, w->row_part};
     for (void *q : p)
         if (q) cudaFree(q);
     if (w->s1) cudaStreamDestroy(w->s1);
@@ -1992,6 +2040,8 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         fa.bias[0][0] = s.theta + o.b1; fa.bias[0][1] = s.theta + o.b2; fa.bias[0][2] = s.theta + o.b3;
         fa.bias[1][0] = s.theta_t + o.b1; fa.bias[1][1] = s.theta_t + o.b2; fa.bias[1][2] = s.theta_t + o.b3;
         fa.q[0] = w->q; fa.q[1] = w->qt;
+        fa.stamps = w->ff_stamps;
+        fa.h1 = w->h1; fa.h2 = w->h2;
         dim3 grid((B + BM - 1) / BM, 2);
         if (w->ff2 && d.D == 128)
             WCK(launch_k(ff_forward2_kernel<2>, grid, dim3(FF_THREADS), ff2_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
@@ -2138,6 +2188,11 @@ std::string wide_step_kernel_names(WideState *w)
 }
 
 void wide_set_debug(WideState *w, bool on) { w->debug = on; }
+const long long *wide_ff_stamps(WideState *w, size_t *bytes)
+{
+    *bytes = w->ff_stamps ? (size_t)(w->B / BM) * 2 * FF_NSTAMPS * sizeof(long long) : 0;
+    return w->ff_stamps;
+}
 void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const float **td)
 {
     *q = w->q; *qt = w->qt; *td = w->td;

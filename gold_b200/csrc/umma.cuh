@@ -168,11 +168,11 @@ __device__ __forceinline__ uint32_t mapa_u32(const void *p, uint32_t rank)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
     return r;
 }
-// arrive on a barrier anywhere in the cluster; release at cluster scope orders this thread's earlier
-// writes (and, through bar.sync, its CTA's) before the waiter's acquire
+// arrive on a barrier anywhere in the cluster (the form CUTLASS uses for cross-CTA pipeline releases).  What
+// the waiter consumes was made visible before this point by fence.proxy.async + bar.sync in the writing CTA
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) { mbar_wait_bounded<true>(bar, parity); }
 // TMA load into THIS CTA's shared memory whose completion bytes are counted on a barrier that may
