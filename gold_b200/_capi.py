@@ -370,7 +370,7 @@ class Handle:
             DBG_Q_ONLINE: ((RB, self.A), np.float32), DBG_Q_TARGET: ((RB, self.A), np.float32),
             DBG_TD: ((RB,), np.float32), DBG_GRADS: ((self.R * self.P,), np.float32),
             DBG_INDICES: ((RB,), np.int32), DBG_BATCH_S: ((RB, self.D), np.float32),
-            DBG_BATCH_A: ((RB,), np.int32), DBG_FF_STAMPS: ((self.B // 128 * 2, 32), np.int64),
+            DBG_BATCH_A: ((RB,), np.int32), DBG_FF_STAMPS: ((self.B // 128 * 2, 96), np.int64),
         }[what]
         out = np.empty(shape, dt)
         self._ck(self._L.goldq_debug_fetch(self._h, what, out.ctypes.data, out.nbytes))

@@ -316,7 +316,7 @@ constexpr int FF_WSTAGES = 3;
 constexpr uint32_t FF_BOX = 16384;            // [128 rows][64 bf16] swizzled box
 constexpr uint32_t FF_WSTAGE_BYTES = 32768;   // [4 n-groups][64 k-rows][128 B]
 
-constexpr int FF_NSTAMPS = 32;
+constexpr int FF_NSTAMPS = 96;
 struct FFArgs {
     int B, D, A;
     const float *bias[2][3];     // [net][layer]
@@ -662,6 +662,12 @@ constexpr size_t ff_smem_bytes()
 constexpr int FF2_WSTAGES = 5;
 constexpr uint32_t FF2_WSTAGE_BYTES = 16384;   // this CTA's half of a [64 k][256 n] tile: [2 n-groups][64 k-rows][128 B]
 
+// CODE SIZE MATTERS HERE.  The first version of this kernel was fully unrolled (6 000 SASS instructions,
+// 97 KB, most of them executed exactly once): in-kernel clock stamps (tools/ff_stamps.py) showed the
+// single-thread roles -- TMA producer, MMA issuer -- losing 1-2.5 k cycles at every phase change to cold
+// instruction fetches (the first k-block after each gate took 2.5 k cycles, the following ones 450).  Every
+// role is therefore ONE rolled loop over a schedule computed arithmetically from the iteration index, so
+// that its instructions are fetched once and re-executed.
 template <int KD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FF_THREADS, 1)
 ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
@@ -675,6 +681,8 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     constexpr uint32_t IDESC_256 = make_idesc_bf16(256, 256, false, true);
     constexpr uint32_t IDESC_128 = make_idesc_bf16(256, 128, false, true);
     constexpr int KH = FF_H / 64;                       // 8 k-blocks of layers 2 and 3
+    constexpr int NB1 = 2 * KD, NB2 = 2 * KH, NB3 = KH / 2;   // ring stages consumed by layers 1, 2, 3
+    constexpr int NB = NB1 + NB2 + NB3;
     constexpr uint16_t BOTH = 3;
 
     extern __shared__ uint8_t smem_raw[];
@@ -682,7 +690,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     uint8_t *sH = smem;                                 // 8 boxes: H1, then H2
     uint8_t *sX = sH + (KH - KD) * FF_BOX;              // aliases the last boxes of H (see ff_forward_kernel)
     uint8_t *sW = sH + KH * FF_BOX;                     // weight ring
-    __shared__ uint64_t full_w[FF2_WSTAGES], empty_w[FF2_WSTAGES], x_full, acc_full[2], acc_free[2], h_ready, h_lo;
+    __shared__ uint64_t full_w[FF2_WSTAGES], empty_w[FF2_WSTAGES], x_full, acc_full[2], acc_free[2], h_ready, h_lo, lo_free;
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_bias[2 * FF_H + 32];
 
@@ -692,7 +700,10 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     const uint32_t rank = cluster_ctarank();            // 0 = leader
     long long *const stp = g.stamps ? g.stamps + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * FF_NSTAMPS : nullptr;
 #define FF_STAMP(i) do { if (stp) stp[i] = clock64(); } while (0)
-    if (threadIdx.x == 0) FF_STAMP(0);
+    if (threadIdx.x == 0) {
+        FF_STAMP(0);
+        if (stp) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); stp[30] = (long long)t; }
+    }
     const CUtensorMap *tmX = net ? &tmX1 : &tmX0;
     const CUtensorMap *tmW1 = net ? &tmW1_1 : &tmW1_0;
     const CUtensorMap *tmW2 = net ? &tmW2_1 : &tmW2_0;
@@ -703,6 +714,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         for (int s = 0; s < FF2_WSTAGES; s++) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 1); }
         mbar_init(&x_full, 1);
         mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+        mbar_init(&lo_free, 1);
         // the leader's copies collect the arrivals of both CTAs
         mbar_init(&acc_free[0], 2 * (FF_EPI_THREADS / 32)); mbar_init(&acc_free[1], 2 * (FF_EPI_THREADS / 32));
         mbar_init(&h_ready, 2);
@@ -723,119 +735,89 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         if (elect_one()) {
             const uint32_t x_full_leader = mapa_u32(&x_full, 0);
             if (rank == 0) mbar_expect_tx(&x_full, 2 * X_BYTES);
+#pragma unroll
             for (int kb = 0; kb < KD; kb++) tma_load_2d_pair(sX + kb * FF_BOX, tmX, kb * 64, m0, x_full_leader);
-            int it = 0;
-            // one ring stage = 2 boxes of [64 k][64 n]
-            auto load_w = [&](const CUtensorMap *tm, int n0, int k0, int n1, int k1) {
+            const uint32_t full_leader0 = mapa_u32(&full_w[0], 0);
+            const int nr = (int)rank * 128;                        // this CTA's half of a 256-column tile
+            // ring stage `it` = two boxes of [64 k][64 n]: layers 1-2 -> two n-groups of one k-block,
+            // layer 3 (N = 128, this CTA's 64 columns) -> two consecutive k-blocks
+#pragma unroll 1
+            for (int it = 0; it < NB; it++) {
+                const CUtensorMap *tm;
+                int n0, k0, n1, k1;
+                if (it < NB1 + NB2) {
+                    const bool l1 = it < NB1;
+                    const int j = l1 ? it : it - NB1, per = l1 ? KD : KH;
+                    const int half = j >= per ? 1 : 0, kb = j - half * per;
+                    tm = l1 ? tmW1 : tmW2;
+                    n0 = half * 256 + nr; k0 = kb * 64; n1 = n0 + 64; k1 = k0;
+                } else {
+                    const int j = it - NB1 - NB2;
+                    tm = tmW3;
+                    n0 = (int)rank * 64; k0 = j * 128; n1 = n0; k1 = k0 + 64;
+                }
                 const int s = it % FF2_WSTAGES;
                 const uint32_t ph = (it / FF2_WSTAGES) & 1;
-                mbar_wait_bounded<false>(&empty_w[s], ph ^ 1);                    // own ring slot free (leader's commit reaches both CTAs)
+                mbar_wait_bounded<false>(&empty_w[s], ph ^ 1);     // own ring slot free (the leader's commit reaches both CTAs)
+                if (80 + it < FF_NSTAMPS) FF_STAMP(80 + it);
                 if (rank == 0) mbar_expect_tx(&full_w[s], 2 * FF2_WSTAGE_BYTES);
-                const uint32_t bar = mapa_u32(&full_w[s], 0);
+                const uint32_t bar = full_leader0 + (uint32_t)s * 8u;
                 tma_load_2d_pair(sW + s * FF2_WSTAGE_BYTES, tm, n0, k0, bar);
                 tma_load_2d_pair(sW + s * FF2_WSTAGE_BYTES + 8192, tm, n1, k1, bar);
-                it++;
-            };
-            const int nr = (int)rank * 128;                        // this CTA's half of a 256-column tile
-            for (int half = 0; half < 2; half++)
-                for (int kb = 0; kb < KD; kb++) load_w(tmW1, half * 256 + nr, kb * 64, half * 256 + nr + 64, kb * 64);
-            for (int half = 0; half < 2; half++)
-                for (int kb = 0; kb < KH; kb++) load_w(tmW2, half * 256 + nr, kb * 64, half * 256 + nr + 64, kb * 64);
-            // layer 3: N = 128, this CTA's 64 columns; a ring stage holds two k-blocks
-            for (int kq = 0; kq < KH / 2; kq++) load_w(tmW3, (int)rank * 64, kq * 128, (int)rank * 64, kq * 128 + 64);
+            }
         }
     } else if (warp == 1) {
         if (rank == 0) {
-            // ===== MMA issuer (leader only) =====
-            // All waits are CTA-scope acquires.  A cluster-scope acquire on every poll costs ~850 cycles even
-            // on a completed barrier (measured: tools/ff_stamps.py, 16 k-blocks in 3.9 k cycles instead of
-            // 2.2 k), and it is not needed: operands arrive through the async proxy (TMA), and the peer's
-            // epilogue publishes H with fence.proxy.async + bar.sync before its release.cluster arrive --
-            // the data is read by the tensor core through the async proxy of the SM that wrote it.
-            int it = 0;
-            auto mma_block = [&](uint32_t a_box_addr, uint32_t d_tmem, bool first) {
-                const int s = it % FF2_WSTAGES;
-                const uint32_t ph = (it / FF2_WSTAGES) & 1;
-                mbar_wait_bounded<false>(&full_w[s], ph);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t baddr = smem_u32(sW + s * FF2_WSTAGE_BYTES);
-#pragma unroll
-                    for (int kk = 0; kk < BK / UK; kk++)
-                        mma_bf16_pair(d_tmem, make_smem_desc(a_box_addr + kk * 32, 16, 1024),
-                                      make_smem_desc(baddr + kk * 2048, 8192, 1024), IDESC_256, (!first || kk) ? 1u : 0u);
-                    mma_commit_pair(&empty_w[s], BOTH);
-                }
-                __syncwarp();
-                it++;
-            };
-            // layer 1: A = X
+            // ===== MMA issuer (leader only): one loop over the NB ring stages =====
+            // All waits are CTA-scope acquires: operands arrive through the async proxy (TMA), and the peer's
+            // epilogue publishes H with fence.proxy.async + bar.sync before it arrives on the leader's barrier.
             mbar_wait_bounded<false>(&x_full, 0);
             if (lane == 0) FF_STAMP(2);
-            for (int half = 0; half < 2; half++) {
-                for (int kb = 0; kb < KD; kb++) mma_block(smem_u32(sX + kb * FF_BOX), tmem + half * 256, kb == 0);
-                if (elect_one()) mma_commit_pair(&acc_full[half], BOTH);
-                __syncwarp();
-            }
-            if (lane == 0) FF_STAMP(3);
-            // layer 2: A = H1.  Its first four k-blocks need only what the epilogues of accumulator half 0
-            // wrote: they start while half 1 is still being drained (in both CTAs).
-            mbar_wait_bounded<false>(&h_lo, 0);
-            if (lane == 0) FF_STAMP(21);
-            mbar_wait_bounded<false>(&acc_free[0], 0);
-            tc_fence_after();
-            if (lane == 0) FF_STAMP(4);
-            for (int half = 0; half < 2; half++) {
-                for (int kb = 0; kb < KH; kb++) {
-                    if (half == 0 && kb == KH / 2) {
-                        if (lane == 0) FF_STAMP(17);
-                        mbar_wait_bounded<false>(&h_ready, 0);
-                        if (lane == 0) FF_STAMP(22);
-                        mbar_wait_bounded<false>(&acc_free[1], 0);
-                        tc_fence_after();
-                        if (lane == 0) FF_STAMP(5);
-                    }
-                    mma_block(smem_u32(sH + kb * FF_BOX), tmem + half * 256, kb == 0);
-                }
-                if (elect_one()) mma_commit_pair(&acc_full[half], BOTH);
-                __syncwarp();
-            }
-            if (lane == 0) FF_STAMP(6);
-            // layer 3: A = H2, N = 128; the first two ring stages (k-blocks 0..3) need only the first half of H2
-            mbar_wait_bounded<false>(&h_lo, 1);
-            if (lane == 0) FF_STAMP(23);
-            mbar_wait_bounded<false>(&acc_free[0], 1);
-            tc_fence_after();
-            if (lane == 0) FF_STAMP(7);
-            for (int kq = 0; kq < KH / 2; kq++) {
-                if (kq == KH / 4) {
-                    if (lane == 0) FF_STAMP(18);
-                    mbar_wait_bounded<false>(&h_ready, 1);
-                    if (lane == 0) FF_STAMP(24);
-                    mbar_wait_bounded<false>(&acc_free[1], 1);
+#pragma unroll 1
+            for (int b = 0; b < NB; b++) {
+                // what this stage feeds
+                const int layer = b < NB1 ? 0 : (b < NB1 + NB2 ? 1 : 2);
+                const int j = b - (layer == 0 ? 0 : (layer == 1 ? NB1 : NB1 + NB2));
+                const int per = layer == 0 ? KD : KH;
+                const int half = (layer < 2 && j >= per) ? 1 : 0;
+                const int kb = layer < 2 ? j - half * per : 2 * j;         // first k-block of the stage
+                // gates: the A operand of layers 2 / 3 is written by the epilogues of both CTAs.  The first half
+                // of the k-blocks needs only what the epilogue of accumulator half 0 produced.
+                if (layer > 0 && half == 0 && (kb == 0 || kb == KH / 2)) {
+                    const uint32_t par = layer == 1 ? 0u : 1u;
+                    if (kb == 0) { mbar_wait_bounded<false>(&h_lo, par); mbar_wait_bounded<false>(&acc_free[0], par); }
+                    else { mbar_wait_bounded<false>(&h_ready, par); mbar_wait_bounded<false>(&acc_free[1], par); }
                     tc_fence_after();
-                    if (lane == 0) FF_STAMP(8);
                 }
-                const int s = it % FF2_WSTAGES;
-                const uint32_t ph = (it / FF2_WSTAGES) & 1;
+                const int s = b % FF2_WSTAGES;
+                const uint32_t ph = (b / FF2_WSTAGES) & 1;
                 mbar_wait_bounded<false>(&full_w[s], ph);
                 tc_fence_after();
+                if (lane == 0 && 32 + 2 * b + 1 < 80) FF_STAMP(32 + 2 * b);
                 if (elect_one()) {
                     const uint32_t baddr = smem_u32(sW + s * FF2_WSTAGE_BYTES);
+                    const uint32_t aaddr = smem_u32(layer == 0 ? sX : sH) + (uint32_t)kb * FF_BOX;
+                    const uint32_t d_tmem = tmem + (uint32_t)half * 256u;
+                    const uint32_t idesc = layer == 2 ? IDESC_128 : IDESC_256;
+                    const int nkb = layer == 2 ? 2 : 1;
+                    uint32_t acc = kb == 0 ? 0u : 1u;
+                    for (int h = 0; h < nkb; h++) {
 #pragma unroll
-                    for (int h = 0; h < 2; h++)
-#pragma unroll
-                        for (int kk = 0; kk < BK / UK; kk++)
-                            mma_bf16_pair(tmem, make_smem_desc(smem_u32(sH + (kq * 2 + h) * FF_BOX) + kk * 32, 16, 1024),
-                                          make_smem_desc(baddr + h * 8192 + kk * 2048, 8192, 1024), IDESC_128,
-                                          (kq || h || kk) ? 1u : 0u);
+                        for (int kk = 0; kk < BK / UK; kk++) {
+                            mma_bf16_pair(d_tmem, make_smem_desc(aaddr + h * FF_BOX + kk * 32, 16, 1024),
+                                          make_smem_desc(baddr + h * 8192 + kk * 2048, 8192, 1024), idesc, acc);
+                            acc = 1u;
+                        }
+                    }
                     mma_commit_pair(&empty_w[s], BOTH);
+                    // accumulator (half) complete / the first four H1 boxes are no longer read
+                    if (layer < 2 && kb == per - 1) mma_commit_pair(&acc_full[half], BOTH);
+                    if (layer == 2 && j == NB3 - 1) mma_commit_pair(&acc_full[0], BOTH);
+                    if (layer == 1 && half == 1 && kb == KH / 2 - 1) mma_commit_pair(&lo_free, BOTH);
                 }
                 __syncwarp();
-                it++;
+                if (lane == 0 && 32 + 2 * b + 1 < 80) FF_STAMP(32 + 2 * b + 1);
             }
-            if (elect_one()) mma_commit_pair(&acc_full[0], BOTH);
-            __syncwarp();
             if (lane == 0) FF_STAMP(9);
         }
     } else {
@@ -845,7 +827,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         const int rt = q * 32 + lane;           // row within the slab
         const int et = threadIdx.x - 64;        // 0..255
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
-        const uint32_t acc_free_leader0 = mapa_u32(&acc_free[0], 0), acc_free_leader1 = mapa_u32(&acc_free[1], 0);
+        const uint32_t acc_free_leader0 = mapa_u32(&acc_free[0], 0);
         const uint32_t h_lo_leader = mapa_u32(&h_lo, 0), h_ready_leader = mapa_u32(&h_ready, 0);
         // biases of the three layers -> shared memory (read back as broadcast float4)
         for (int i = et; i < 2 * FF_H + 32; i += FF_EPI_THREADS) {
@@ -858,125 +840,65 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         asm volatile("bar.sync 1, 256;" ::: "memory");
 
         const __nv_bfloat162 neg0 = __floats2bfloat162_rn(-0.0f, -0.0f);
-        auto pack_chunk = [&](const uint32_t(&r)[32], const float *bias32, uint32_t(&packed)[16]) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 b = *reinterpret_cast<const float4 *>(bias32 + j);
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y);
-                __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
-                p0 = __hmax2(p0, neg0);         // Rectify: negative (and NaN) -> -0.0, sign bit = mask
-                p1 = __hmax2(p1, neg0);
-                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&p0);
-                packed[(j >> 1) + 1] = *reinterpret_cast<uint32_t *>(&p1);
-            }
-        };
-        auto store_chunk = [&](int c0, const uint32_t(&packed)[16]) {
-            uint8_t *dst = sH + (c0 >> 6) * FF_BOX + rt * 128;
-            const int ch0 = (c0 & 63) >> 3;
-#pragma unroll
-            for (int v = 0; v < 4; v++)
-                *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
-                    make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
-        };
-        auto col0 = [&](int half, int c) { return half * 256 + (cg * 4 + c) * 32; };
-        // The online network's H1 / H2 also go to global memory for the backward pass, straight from the
-        // packed registers (64 contiguous bytes per row and chunk): a TMA store of the 128 KB tile would
-        // queue on the same TMA unit as the weight stream and stall the MMAs behind it (measured: the k-blocks
-        // after each store took 2x their MMA time)
-        const bool keep = (net == 0) && (m0 + rt < g.B);
-        auto store_global = [&](__nv_bfloat16 *base, int c0, const uint32_t(&packed)[16]) {
-            if (!keep) return;
-            uint4 *dst = reinterpret_cast<uint4 *>(base + (size_t)(m0 + rt) * FF_H + c0);
-#pragma unroll
-            for (int v = 0; v < 4; v++) dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
-        };
-
-        // ---- layer 1 -> H1.  The TMEM load of chunk c+1 is in flight while chunk c is packed.
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            mbar_wait_bounded<false>(&acc_full[half], 0);
-            tc_fence_after();
-            if (et == 0 && half == 0) FF_STAMP(10);
-            uint32_t r[2][32];
-            tmem_ld_32x32(tq + (uint32_t)col0(half, 0), r[0]);
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                tmem_ld_wait();
-                if (c < 3) tmem_ld_32x32(tq + (uint32_t)col0(half, c + 1), r[(c + 1) & 1]);
-                uint32_t packed[16];
-                pack_chunk(r[c & 1], s_bias + col0(half, c), packed);
-                store_chunk(col0(half, c), packed);
-                store_global(g.h1, col0(half, c), packed);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(half ? acc_free_leader1 : acc_free_leader0);
-            if (half == 0) {           // boxes 0..3 of H1 are complete in this CTA
-                if (et == 0) FF_STAMP(25);
-                fence_proxy_async_smem();
-                if (et == 0) FF_STAMP(26);
+        // phases: (layer 1, half 0), (layer 1, half 1), (layer 2, half 0), (layer 2, half 1) -- one loop body.
+        // H2 overwrites H1 in place: its first half may be written once the layer-2 MMAs of accumulator half 1
+        // have consumed H1 boxes 0..3 (lo_free), its second half once every layer-2 MMA has retired.
+#pragma unroll 1
+        for (int p = 0; p < 4; p++) {
+            const int layer = p >> 1, half = p & 1;
+            mbar_wait_bounded<false>(&acc_full[half], (uint32_t)layer);
+            if (p == 2) {
+                mbar_wait_bounded<false>(&lo_free, 0);
+                // the TMA store of H1 must have finished reading the tile before H2 lands on it
+                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (et == 0) { FF_STAMP(27); mbar_arrive_cluster(h_lo_leader); FF_STAMP(28); }
             }
-        }
-        fence_proxy_async_smem();      // H1 complete: visible to the async proxy (layer-2 MMA, TMA store)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0) {
-            FF_STAMP(11);
-            mbar_arrive_cluster(h_ready_leader);
-        }
-
-        // ---- layer 2 -> H2, which overwrites H1 in place.  Accumulator half 0 is drained into
-        // registers while the MMAs of half 1 still read H1; it is written out once they retire.
-        {
-            uint32_t hold[4][16];
-            uint32_t r[32];
-            mbar_wait_bounded<false>(&acc_full[0], 1);
+            if (p == 3) mbar_wait_bounded<false>(&acc_full[1], 1);   // (same barrier as above; kept for symmetry of the listing)
             tc_fence_after();
-            if (et == 0) FF_STAMP(12);
+            if (et == 0) FF_STAMP(10 + p);
+            const int cbase = half * 256 + cg * 128;                 // first column of this warp's four chunks
+            const float *bias = s_bias + layer * FF_H + cbase;
+            uint32_t r[2][32];
+            tmem_ld_32x32(tq + (uint32_t)cbase, r[0]);
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                tmem_ld_32x32(tq + (uint32_t)col0(0, c), r);
                 tmem_ld_wait();
-                pack_chunk(r, s_bias + FF_H + col0(0, c), hold[c]);
+                if (c < 3) tmem_ld_32x32(tq + (uint32_t)(cbase + 32 * (c + 1)), r[(c + 1) & 1]);
+                uint32_t packed[16];
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 4) {
+                    const float4 bv = *reinterpret_cast<const float4 *>(bias + 32 * c + jj);
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(r[c & 1][jj]) + bv.x, __uint_as_float(r[c & 1][jj + 1]) + bv.y);
+                    __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(r[c & 1][jj + 2]) + bv.z, __uint_as_float(r[c & 1][jj + 3]) + bv.w);
+                    p0 = __hmax2(p0, neg0);         // Rectify: negative (and NaN) -> -0.0, sign bit = mask (nn.go:162-189)
+                    p1 = __hmax2(p1, neg0);
+                    packed[jj >> 1] = *reinterpret_cast<uint32_t *>(&p0);
+                    packed[(jj >> 1) + 1] = *reinterpret_cast<uint32_t *>(&p1);
+                }
+                const int c0 = cbase + 32 * c;
+                uint8_t *dst = sH + (c0 >> 6) * FF_BOX + rt * 128;
+                const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+                    *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
+                        make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc_free_leader0);
-            // every layer-2 MMA (of the pair) has read H1 once acc_full[1] fires; the H1 TMA store must
-            // also have finished reading this CTA's tile
-            if (et == 0) FF_STAMP(19);
-            mbar_wait_bounded<false>(&acc_full[1], 1);
-            tc_fence_after();
-            if (et == 0) FF_STAMP(13);
-            tmem_ld_32x32(tq + (uint32_t)col0(1, 0), r);
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                store_chunk(col0(0, c), hold[c]);
-                store_global(g.h2, col0(0, c), hold[c]);
-            }
-            if (et == 0) FF_STAMP(20);
+            if (lane == 0) mbar_arrive_cluster(acc_free_leader0 + (uint32_t)half * 8u);
+            // this half of H is complete in this CTA: visible to the async proxy (MMA of the next layer, TMA store)
             fence_proxy_async_smem();
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (et == 0) mbar_arrive_cluster(h_lo_leader);
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                if (c) tmem_ld_32x32(tq + (uint32_t)col0(1, c), r);
-                tmem_ld_wait();
-                uint32_t packed[16];
-                pack_chunk(r, s_bias + FF_H + col0(1, c), packed);
-                store_chunk(col0(1, c), packed);
-                store_global(g.h2, col0(1, c), packed);
+            if (et == 0) {
+                if (half == 1 && net == 0) {   // the backward pass needs the online network's activations
+                    const CUtensorMap *tmH = layer == 0 ? &tmH1 : &tmH2;
+#pragma unroll 1
+                    for (int b = 0; b < KH; b++) tma_store_2d(tmH, sH + b * FF_BOX, 64 * b, m0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                mbar_arrive_cluster(half == 0 ? h_lo_leader : h_ready_leader);
+                FF_STAMP(14 + p);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc_free_leader1);
-        }
-        fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0) {
-            FF_STAMP(14);
-            mbar_arrive_cluster(h_ready_leader);
         }
 
         // ---- layer 3: Q = acc + b3 -> fp32 [B][A] (A <= 32: one chunk), staged in the idle weight ring
@@ -984,7 +906,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         if (cg == 0) {
             mbar_wait_bounded<false>(&acc_full[0], 0);          // third completion of acc_full[0]: parity 0 again
             tc_fence_after();
-            if (et == 0) FF_STAMP(15);
+            if (et == 0) FF_STAMP(18);
             uint32_t r[32];
             tmem_ld_32x32(tq, r);
             tmem_ld_wait();
@@ -1000,7 +922,8 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
             float *dst = g.q[net] + (size_t)m0 * g.A;
             for (int i = et; i < rows * g.A; i += 128) dst[i] = sQ[i];
         }
-        if (et == 0) FF_STAMP(16);
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (et == 0) FF_STAMP(19);
     }
 #undef FF_STAMP
     tc_fence_before();
@@ -1009,6 +932,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         tc_fence_after();
         tmem_dealloc_pair(tmem, 512);
     }
+    if (threadIdx.x == 32 && stp) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); stp[31] = (long long)t; }
 }
 
 template <int KD>

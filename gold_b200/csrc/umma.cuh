@@ -75,6 +75,7 @@ template <bool CLUSTER>
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t i = 0; i < (1u << 26); i++) {
         uint32_t ok;
         if (CLUSTER)

@@ -9,13 +9,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["GOLDQ_FF_STAMPS"] = "1"
 from gold_b200 import _capi as G, synth  # noqa: E402
 
-NAMES = ["entry", "after cluster_sync+pdl_wait", "MMA: x_full seen", "MMA: L1 issued", "MMA: L2 start (h_lo)",
-         "MMA: L2 kb4 gate passed", "MMA: L2 issued", "MMA: L3 start", "MMA: L3 gate passed", "MMA: L3 issued",
-         "EPI: acc_full[0] L1", "EPI: H1 complete", "EPI: acc_full[0] L2", "EPI: acc_full[1] L2 (all L2 MMAs done)",
-         "EPI: H2 complete", "EPI: acc_full[0] L3", "EPI: Q written", "MMA: reached L2 kb4 gate", "MMA: reached L3 gate",
-         "EPI: half0 held, waiting L2 end", "EPI: H2 half0 stored", "MMA: h_lo(L2) seen", "MMA: h_ready(L2) seen",
-         "MMA: h_lo(L3) seen", "MMA: h_ready(L3) seen", "EPI: L1 half0 chunks done", "EPI: L1 h0 proxy fence done",
-         "EPI: L1 h0 bar.sync done", "EPI: L1 h0 h_lo arrived", "", "", ""]
+NAMES = [""] * 96
+NAMES[0], NAMES[1], NAMES[2], NAMES[9] = "entry", "after cluster_sync+pdl_wait", "MMA: x_full seen", "MMA: all issued"
+for p_, nm in enumerate(["L1 half0", "L1 half1", "L2 half0", "L2 half1"]):
+    NAMES[10 + p_] = f"EPI: {nm} accumulator ready"
+    NAMES[14 + p_] = f"EPI: {nm} written, arrived"
+NAMES[18], NAMES[19] = "EPI: Q accumulator ready", "EPI: Q written"
+for blk in range(24):
+    NAMES[32 + 2 * blk], NAMES[33 + 2 * blk] = f"MMA: stage {blk} operands ready", f"MMA: stage {blk} issued"
+for i in range(16):
+    NAMES[80 + i] = f"TMA: load {i} slot free, issuing"
 dims, B, N = synth.WIDE, 8192, 1 << 16
 h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3], batch_size=B, replay_capacity=N,
              precision=G.PREC_BF16)
@@ -24,14 +27,19 @@ h.replay_push(*synth.replay(dims, N))
 for i in range(5):
     h.learn(None, i)
 h.sync()
+for i in range(3):
+    bd = h.step_breakdown(100 + i)
+print("eager breakdown (us):", {k: round(v * 1e3, 2) for k, v in bd})
 st = h.debug_fetch(G.DBG_FF_STAMPS).astype(np.int64)
 nx = B // 128
-st = st.reshape(2, nx, 32)
-for label, sel in (("ONLINE net, leader CTAs", st[0:1, 0::2]), ("ONLINE net, peer CTAs", st[0:1, 1::2]),
-                   ("TARGET net, leader CTAs", st[1:2, 0::2])):
+g0, g1 = st[:, 30], st[:, 31]
+print(f"globaltimer: first CTA entry -> last CTA exit {(g1.max() - g0.min()) / 1e3:.2f} us; entry skew {(g0.max() - g0.min()) / 1e3:.2f} us; "
+      f"exit skew {(g1.max() - g1.min()) / 1e3:.2f} us; median CTA lifetime {np.median(g1 - g0) / 1e3:.2f} us")
+st = st.reshape(2, nx, 96)
+for label, sel in (("ONLINE net, leader CTAs", st[0:1, 0::2]), ("TARGET net, leader CTAs", st[1:2, 0::2])):
     rel = sel - sel[..., 1:2]
     print(label)
-    order = np.argsort(np.median(rel.reshape(-1, 32), axis=0))
+    order = np.argsort(np.median(rel.reshape(-1, 96), axis=0))
     for i in order:
         col = rel[..., i].ravel()
         if (sel[..., i] == 0).all():
