@@ -1664,6 +1664,7 @@ struct WideState {
     cudaEvent_t ev_dz2 = nullptr, ev_dx = nullptr, ev_s1 = nullptr, ev_s2 = nullptr, ev_fork = nullptr, ev_gather = nullptr;
     bool pdl = true;
     bool ff = false;                       // fused three-layer forward kernel usable
+    int skip = 0;                          // GOLDQ_SKIP bit mask (diagnostic): launches left out of the step, see wide_step
     long long *ff_stamps = nullptr;        // GOLDQ_FF_STAMPS: in-kernel clock stamps of the fused forward (diagnostic)
     bool ff2 = false;                      // ... on CTA pairs (cta_group::2): needs an even number of 128-row slabs
     bool bn256 = false;                    // 128x256 output tiles for the N = H GEMMs
@@ -1750,6 +1751,9 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     ok = ok && make_tmap(&w->net[0].tm_w2_k256, w->net[0].w2, d.H1, d.H2, d.H2, 256, err);
     w->ff = getenv("GOLDQ_NO_FF") == nullptr && d.H1 == FF_H && d.H2 == FF_H && (d.D == 64 || d.D == 128) && d.A <= W3_PAD;
     w->ff2 = w->ff && getenv("GOLDQ_NO_FF2") == nullptr && B % (2 * BM) == 0;
+    // diagnostic only (results are garbage): leave launches out of the step to read their share of the
+    // critical path off the step time.  1 gather, 2 forward, 4 TD/dZ2, 8 dW3, 16 dW2, 32 dX, 64 db1, 128 dW1, 256 update
+    if (const char *sk = getenv("GOLDQ_SKIP")) w->skip = atoi(sk);
     if (w->ff2 && getenv("GOLDQ_FF_STAMPS")) {
         const size_t n = (size_t)(B / BM) * 2 * FF_NSTAMPS;
         if (dmalloc(&w->ff_stamps, n, err)) cudaMemset(w->ff_stamps, 0, n * sizeof(long long));
@@ -1935,15 +1939,15 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     WideState::BatchSet &bt = w->bs[s.set & 1];
     w->last_set = s.set & 1;
     const int gather_threads = B * (d.D >> 2);
-    if (!s.have) {
+    if (!s.have && !(w->skip & 1)) {
         WCK(launch_k(wide_gather_kernel, dim3((gather_threads + 255) / 256), dim3(256), 0, st, pdl, s.rp, d.D, s.idx, s.seed,
                      s.step, s.idx_out, B, bt.x, bt.x2, bt.ba, bt.br, bt.bdone));
         launches++;
         mark("gather+cast (K1)");
-    } else {
+    } else if (s.have && !(w->skip & 1)) {
         WCK(cudaStreamWaitEvent(st, w->ev_gather, 0));   // this step's batch was gathered by the previous step's side branch
     }
-    if (s.next_step) {
+    if (s.next_step && !(w->skip & 1)) {
         // gather the NEXT step's batch into the other buffer set while this step computes.  The fork
         // follows everything the previous step launched, i.e. every reader of that buffer set.
         WideState::BatchSet &nx = w->bs[(s.set & 1) ^ 1];
@@ -1957,7 +1961,8 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     }
     WideNet &on = w->net[0], &tg = w->net[1];
     GemmArgs g{};
-    if (w->ff) {
+    if (w->skip & 2) {
+    } else if (w->ff) {
         // forward of both networks, all three layers, one launch
         FFArgs fa{};
         fa.B = B; fa.D = d.D; fa.A = d.A;
@@ -2016,6 +2021,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     launches += 3;
     }
 
+    if (!(w->skip & 4))
     WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), sizeof(float) * 4 * d.H2, st, pdl, w->q, w->qt, bt.ba, bt.br,
                  bt.bdone, B, d.H2, d.A, s.sc, w->h2, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part));
     mark("TD + dZ2 + db2/db3 (K3)");
@@ -2031,13 +2037,15 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g = GemmArgs{};
     g.M = d.H2; g.N = 32; g.K = B; g.k_per_split = w->kps3;
     g.out_f32 = w->w3_slices; g.ldo = d.A; g.n_store = d.A; g.slice_stride = (long long)d.H2 * d.A;
+    if (!(w->skip & 8))
     WCK((launch_gemm<MODE_MK, 32, EPI_F32_SLICE>(w->tm_h2_mm, w->tm_dqT_b, g, w->ns3, s2)));
     mark("dW3 (tcgen05)");
     // dW2 = H1^T dZ2 : M = H1, N = H2, K = B
     g = GemmArgs{};
     g.M = d.H1; g.N = d.H2; g.K = B; g.k_per_split = w->kps2;
     g.out_f32 = w->w2_slices; g.ldo = d.H2; g.n_store = d.H2; g.slice_stride = (long long)d.H1 * d.H2;
-    if (w->mc_h1)
+    if (w->skip & 16) {
+    } else if (w->mc_h1)
         WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE, 4>(w->tm_h1_mm, w->tm_dz2_mm_s4, g, w->ns2, s1)));
     else
         WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, s1)));
@@ -2047,7 +2055,8 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g = GemmArgs{};
     g.M = B; g.N = d.H1; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = w->dz1; g.mask_src = w->h1; g.ldo = d.H1; g.n_store = d.H1;
-    if (w->bn256)
+    if (w->skip & 32) {
+    } else if (w->bn256)
         // one CTA per SM here (B/128 x H1/256 tiles <= SMs): a 4-stage ring (192 KB) instead of 2
         if (((B + BM - 1) / BM) * ((d.H1 + 255) / 256) <= w->sm_count)
             WCK((launch_gemm<MODE_KK, 256, EPI_MASK_BF16, 1, 4>(w->tm_dz2_a, on.tm_w2_k256, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
@@ -2062,7 +2071,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         WCK(cudaEventRecord(w->ev_dx, st));
         WCK(cudaStreamWaitEvent(s2, w->ev_dx, 0));
     }
-    {
+    if (!(w->skip & 64)) {
         dim3 grid((d.H1 + 63) / 64, w->nb1);
         wide_colsum_kernel<<<grid, 256, 0, s2>>>(w->dz1, B, d.H1, w->b1_part);
         WCK(cudaGetLastError());
@@ -2073,6 +2082,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g = GemmArgs{};
     g.M = d.D; g.N = d.H1; g.K = B; g.k_per_split = w->kps1;
     g.out_f32 = w->w1_slices; g.ldo = d.H1; g.n_store = d.H1; g.slice_stride = (long long)d.D * d.H1;
+    if (!(w->skip & 128))
     WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(bt.tm_x_mm, w->tm_dz1_mm, g, w->ns1, st, nullptr, nullptr, pdl)));
     mark("dW1 split-K (tcgen05)");
     if (!prof) {
@@ -2086,7 +2096,8 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     const UpdatePlan pl = make_update_plan(d);
     const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
     // (the update kernel follows cross-stream event waits: a full dependency, no PDL)
-    if (s.fuse_update && s.push)
+    if (w->skip & 256) {
+    } else if (s.fuse_update && s.push)
         wide_update_kernel<true, true><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
                                                                s.step, shadow_ptrs(w, 0), s.loss_out, *s.push, s.epoch);
     else if (s.fuse_update)
