@@ -26,7 +26,7 @@ SYMBOLS = [
     "goldq_abi_version", "goldq_param_count", "goldq_selected_path", "goldq_set_params",
     "goldq_get_params", "goldq_set_adam_state", "goldq_get_adam_state", "goldq_replay_push",
     "goldq_replay_len", "goldq_replay_push_wait", "goldq_host_alloc", "goldq_host_free",
-    "goldq_replay_push_packed", "goldq_packed_bytes", "goldq_learn_prepare", "goldq_graph_builds", "goldq_launch_floor",
+    "goldq_replay_push_packed", "goldq_packed_bytes", "goldq_learn_prepare", "goldq_graph_builds", "goldq_launch_floor", "goldq_time_forward",
     "goldq_learn", "goldq_learn_device_indices", "goldq_learn_many", "goldq_sampler_indices", "goldq_sync_target",
     "goldq_last_loss", "goldq_predict", "goldq_greedy_action", "goldq_epsilon_greedy_action", "goldq_explore_plan",
     "goldq_fit_batch",
@@ -85,6 +85,7 @@ def lib():
         "goldq_learn_prepare": (C.c_int, [vp]),
         "goldq_graph_builds": (i64, [vp]),
         "goldq_launch_floor": (C.c_int, [vp, i32, fp]),
+        "goldq_time_forward": (C.c_int, [vp, i32, fp]),
         "goldq_replay_len": (i64, [vp]),
         "goldq_replay_push_wait": (C.c_int, [vp]),
         "goldq_host_alloc": (vp, [i64]),
@@ -388,6 +389,11 @@ class Handle:
     def launch_floor_us(self, reps=50):
         us = C.c_float(0)
         self._ck(self._L.goldq_launch_floor(self._h, reps, C.byref(us)))
+        return us.value
+
+    def time_forward_us(self, reps=20):
+        us = C.c_float(0)
+        self._ck(self._L.goldq_time_forward(self._h, reps, C.byref(us)))
         return us.value
 
     def timer_start(self):

@@ -1542,6 +1542,21 @@ int goldq_debug_fetch(goldq_t *h, int what, void *out, int64_t out_bytes)
     return GOLDQ_OK;
 }
 
+/* Diagnostic (bench.py roofline): average launch duration of the dominant tensor-core kernel of the wide
+ * step -- the fused forward -- over `reps` back-to-back launches on the handle's stream, CUDA events around the
+ * sequence; inputs are the batch of the last learn step (run one first). */
+int goldq_time_forward(goldq_t *h, int32_t reps, float *us_per_launch)
+{
+    if (!h || !us_per_launch || reps < 1) return fail(h, GOLDQ_EINVAL, "time_forward: bad argument");
+    if (!h->wide) return fail(h, GOLDQ_EUNSUPPORTED, "time_forward: wide (tcgen05) path only");
+    CK(h, cudaSetDevice(h->dev));
+    std::string err;
+    int n = wide_time_forward(h->wide, h->theta, h->theta_t, h->st, reps, us_per_launch, err);
+    if (n < 0) return fail(h, GOLDQ_EUNSUPPORTED, err);
+    h->launches += n;
+    return GOLDQ_OK;
+}
+
 __global__ void empty_kernel() {}
 
 /* Diagnostic: the launch-latency floor the latency-bound configurations are compared with.  One

@@ -918,9 +918,18 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 if (j < g.A) sQ[rt * g.A + j] = v;
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
-            const int rows = (g.B - m0 < BM) ? g.B - m0 : BM;
+            const int nq = ((g.B - m0 < BM) ? g.B - m0 : BM) * g.A;
             float *dst = g.q[net] + (size_t)m0 * g.A;
-            for (int i = et; i < rows * g.A; i += 128) dst[i] = sQ[i];
+            // (A <= 32: at most 32 floats per thread; eight independent loads in flight)
+#pragma unroll 1
+            for (int i0 = et; i0 < nq; i0 += 8 * 128) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = (i0 + 128 * u < nq) ? sQ[i0 + 128 * u] : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + 128 * u < nq) dst[i0 + 128 * u] = v[u];
+            }
         }
         if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         if (et == 0) FF_STAMP(19);
@@ -1923,6 +1932,59 @@ int wide_sync_target(WideState *w, cudaStream_t st, std::string &err)
         if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return -1; } \
     } while (0)
 
+// the fused forward of both networks on batch set `bt` (pair kernel when the slab count is even)
+static cudaError_t launch_fused_forward(WideState *w, WideState::BatchSet &bt, const float *theta, const float *theta_t,
+                                        cudaStream_t st, bool pdl)
+{
+    const Dims &d = w->d;
+    const Offsets &o = w->o;
+    const int B = w->B;
+    WideNet &on = w->net[0], &tg = w->net[1];
+    FFArgs fa{};
+    fa.B = B; fa.D = d.D; fa.A = d.A;
+    fa.bias[0][0] = theta + o.b1; fa.bias[0][1] = theta + o.b2; fa.bias[0][2] = theta + o.b3;
+    fa.bias[1][0] = theta_t + o.b1; fa.bias[1][1] = theta_t + o.b2; fa.bias[1][2] = theta_t + o.b3;
+    fa.q[0] = w->q; fa.q[1] = w->qt;
+    fa.stamps = w->ff_stamps;
+    fa.h1 = w->h1; fa.h2 = w->h2;
+    dim3 grid((B + BM - 1) / BM, 2);
+    if (w->ff2 && d.D == 128)
+        return launch_k(ff_forward2_kernel<2>, grid, dim3(FF_THREADS), ff2_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
+                        on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a, w->tm_h2_a, fa);
+    if (w->ff2)
+        return launch_k(ff_forward2_kernel<1>, grid, dim3(FF_THREADS), ff2_smem_bytes<1>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
+                        on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a, w->tm_h2_a, fa);
+    if (d.D == 128)
+        return launch_k(ff_forward_kernel<2>, grid, dim3(FF_THREADS), ff_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
+                        on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a, w->tm_h2_a, fa);
+    return launch_k(ff_forward_kernel<1>, grid, dim3(FF_THREADS), ff_smem_bytes<1>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
+                    on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a, w->tm_h2_a, fa);
+}
+
+// Diagnostic (bench.py roofline): average duration of the fused forward over `reps` back-to-back launches on
+// `st` (inputs = the batch of the last step), CUDA events around the whole sequence.  Returns -1 when the fused
+// forward is not in use for this shape.
+int wide_time_forward(WideState *w, const float *theta, const float *theta_t, cudaStream_t st, int reps, float *us,
+                      std::string &err)
+{
+    if (!w->ff) { err = "the fused forward kernel is not used for this shape"; return -1; }
+    cudaEvent_t e0, e1;
+    WCK(cudaEventCreate(&e0));
+    WCK(cudaEventCreate(&e1));
+    WideState::BatchSet &bt = w->bs[w->last_set];
+    for (int i = 0; i < 3; i++) WCK(launch_fused_forward(w, bt, theta, theta_t, st, w->pdl));
+    WCK(cudaEventRecord(e0, st));
+    for (int i = 0; i < reps; i++) WCK(launch_fused_forward(w, bt, theta, theta_t, st, w->pdl));
+    WCK(cudaEventRecord(e1, st));
+    WCK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    WCK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *us = ms * 1e3f / (float)reps;
+    return reps + 3;
+}
+
 int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err)
 {
     const Dims &d = w->d;
@@ -1964,30 +2026,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     if (w->skip & 2) {
     } else if (w->ff) {
         // forward of both networks, all three layers, one launch
-        FFArgs fa{};
-        fa.B = B; fa.D = d.D; fa.A = d.A;
-        fa.bias[0][0] = s.theta + o.b1; fa.bias[0][1] = s.theta + o.b2; fa.bias[0][2] = s.theta + o.b3;
-        fa.bias[1][0] = s.theta_t + o.b1; fa.bias[1][1] = s.theta_t + o.b2; fa.bias[1][2] = s.theta_t + o.b3;
-        fa.q[0] = w->q; fa.q[1] = w->qt;
-        fa.stamps = w->ff_stamps;
-        fa.h1 = w->h1; fa.h2 = w->h2;
-        dim3 grid((B + BM - 1) / BM, 2);
-        if (w->ff2 && d.D == 128)
-            WCK(launch_k(ff_forward2_kernel<2>, grid, dim3(FF_THREADS), ff2_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
-                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
-                         w->tm_h2_a, fa));
-        else if (w->ff2)
-            WCK(launch_k(ff_forward2_kernel<1>, grid, dim3(FF_THREADS), ff2_smem_bytes<1>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
-                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
-                         w->tm_h2_a, fa));
-        else if (d.D == 128)
-            WCK(launch_k(ff_forward_kernel<2>, grid, dim3(FF_THREADS), ff_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
-                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
-                         w->tm_h2_a, fa));
-        else
-            WCK(launch_k(ff_forward_kernel<1>, grid, dim3(FF_THREADS), ff_smem_bytes<1>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
-                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a,
-                         w->tm_h2_a, fa));
+        WCK(launch_fused_forward(w, bt, s.theta, s.theta_t, st, pdl));
         launches += 1;
         mark(w->ff2 ? "fused forward L1-L3 online+target, CTA pairs (tcgen05 cta_group::2)"
                     : "fused forward L1-L3 online+target (tcgen05)");
@@ -2178,6 +2217,53 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int naccs, 
     if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// ---------------------------------------------------------------------------
+// Diagnostic: how fast can ONE thread of a CTA stream L2-resident data into shared memory (selftest modes
+// 40..43)?  A ring of `SLOTS` 16 KB slots; every slot is refilled as soon as its previous load has landed.
+//   kind 0: two TMA 2D boxes of [64 rows][128 B] per slot out of a row-major matrix with a 1 KB pitch, the
+//           SAME boxes in every CTA (the weight stream of the fused forward)
+//   kind 1: the same boxes, but every CTA reads its own rows (activation tiles)
+//   kind 2: one contiguous 16 KB bulk copy per slot (cp.async.bulk), the same bytes in every CTA
+//   kind 3: contiguous 16 KB bulk copies, own region per CTA
+// out[2*cta] = bytes per SM clock, out[2*cta+1] = cycles from first issue to last completion.
+// ---------------------------------------------------------------------------
+constexpr int IG_SLOTS = 6;
+__global__ void __launch_bounds__(128, 1)
+ingest_probe_kernel(const __grid_constant__ CUtensorMap tm, const uint8_t *flat, int kind, int iters, int rows_total, float *out)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[IG_SLOTS];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < IG_SLOTS; s++) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int own = (kind & 1) ? (int)blockIdx.x : 0;
+        const long long t0 = clock64();
+        for (int i = 0; i < iters + IG_SLOTS; i++) {
+            const int s = i % IG_SLOTS;
+            if (i >= IG_SLOTS) mbar_wait_bounded<false>(&full[s], ((i / IG_SLOTS) - 1) & 1);
+            if (i < iters) {
+                mbar_expect_tx(&full[s], 16384);
+                if (kind < 2) {
+                    // matrix [rows_total][512 bf16]: slot i = rows [64 * (i % 8) + 512 * own, +64), columns 128 * (i / 8 % 4) ...
+                    const int r0 = (64 * (i & 7) + 512 * own) % rows_total, c0 = 128 * ((i >> 3) & 3);
+                    tma_load_2d(smem + s * 16384, &tm, c0, r0, &full[s]);
+                    tma_load_2d(smem + s * 16384 + 8192, &tm, c0 + 64, r0, &full[s]);
+                } else {
+                    const size_t off = ((size_t)(i & 31) * 16384 + (size_t)own * 524288) % ((size_t)rows_total * 1024);
+                    bulk_load_1d(smem + s * 16384, flat + off, 16384, &full[s]);
+                }
+            }
+        }
+        const long long t1 = clock64();
+        out[2 * blockIdx.x] = (float)((double)iters * 16384.0 / (double)(t1 - t0));
+        out[2 * blockIdx.x + 1] = (float)(t1 - t0);
+    }
+}
+
 template <int N, bool B_MN>
 static cudaError_t run_mma_rate(int ctas, int iters, int naccs, float *dout)
 {
@@ -2198,6 +2284,28 @@ int wide_selftest_gemm(int mode, int M, int N, int K, int nsplit, const uint16_t
     if (!load_encode(err)) return -1;
     WCK(configure_all_gemms());
     if (nsplit < 1) nsplit = 1;
+    if (mode >= 40 && mode <= 43) {
+        // ingest probe: M/128 CTAs, K = 16 KB slots per CTA; C[2*cta] = bytes per clock, C[2*cta+1] = cycles
+        const int ctas = M / 128, rows_total = 512 * ctas;
+        if (ctas < 1 || K < 1) { err = "selftest: ingest probe needs M >= 128, K >= 1"; return -1; }
+        __nv_bfloat16 *dsrc = nullptr;
+        float *dout = nullptr;
+        if (!dmalloc(&dsrc, (size_t)rows_total * 512, err) || !dmalloc(&dout, (size_t)ctas * 2, err)) return -1;
+        WCK(cudaMemset(dsrc, 0, (size_t)rows_total * 1024));
+        CUtensorMap tm;
+        if (!make_tmap(&tm, dsrc, rows_total, 512, 512, 64, err)) return -1;
+        WCK(cudaFuncSetAttribute(ingest_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SLOTS * 16384 + 1024));
+        for (int rep = 0; rep < 2; rep++) {      // the second run reads from a warm L2
+            ingest_probe_kernel<<<ctas, 128, IG_SLOTS * 16384 + 1024>>>(tm, reinterpret_cast<const uint8_t *>(dsrc), mode - 40, K,
+                                                                        rows_total, dout);
+            WCK(cudaGetLastError());
+            WCK(cudaDeviceSynchronize());
+        }
+        WCK(cudaMemcpy(C, dout, (size_t)ctas * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+        cudaFree(dsrc);
+        cudaFree(dout);
+        return 0;
+    }
     if (mode == 30 || mode == 31) {
         // MMA rate probe: M/128 CTAs, N = MMA width, K = iterations, nsplit = accumulators cycled
         // through; mode 30: B MN-major, 31: B K-major.  C[0] = issue cycles per MMA, C[1] = issue +

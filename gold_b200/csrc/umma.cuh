@@ -120,6 +120,15 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// 1D bulk copy global -> shared (contiguous bytes, multiple of 16), completion on `bar`
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // Same, multicast: the tile lands at the same CTA-relative shared-memory offset of every CTA
 // in `cta_mask` of the cluster and signals the mbarrier at `bar`'s offset in each of them.
 __device__ __forceinline__ void tma_load_2d_mc(void *smem_dst, const CUtensorMap *m, int c0, int c1,

@@ -225,6 +225,9 @@ void *goldq_stream(goldq_t *h);                              /* the cudaStream_t
 int64_t goldq_launch_count(const goldq_t *h);                /* kernels launched so far by this handle */
 int goldq_debug_enable(goldq_t *h, int on);                  /* keep Q/TD/grad snapshots of each step */
 int goldq_debug_fetch(goldq_t *h, int what, void *out, int64_t out_bytes);
+/* Diagnostic: average launch duration (us) of the wide step's dominant tensor-core kernel, the fused forward,
+ * over `reps` back-to-back launches between two CUDA events on the handle's stream. */
+int goldq_time_forward(goldq_t *h, int32_t reps, float *us_per_launch);
 /* Diagnostic: device time per node of a 16-node graph of empty kernels replayed `reps` times -- the
  * launch-latency floor that the latency-bound CartPole configurations are reported against. */
 int goldq_launch_floor(goldq_t *h, int32_t reps, float *us_per_launch);
