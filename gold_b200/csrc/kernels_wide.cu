@@ -951,6 +951,219 @@ constexpr size_t ff2_smem_bytes()
 }
 
 // ---------------------------------------------------------------------------
+// GEMM on CTA pairs (cta_group::2) for the backward pass: one 256 x 256 output tile per pair, each CTA owning
+// 128 rows of A / D and loading 128 of the tile's 256 B columns, so a k-block costs each SM 32 KB of L2->SM
+// traffic instead of 48 KB (single-CTA 128 x 256 tile) or 2 x 32 KB (two 128 x 128 tiles).  The measured
+// L2->SM rate is 33-35 B/clk per SM whatever the access pattern (tools/ingest_probe.py); at this problem size
+// every backward GEMM is bound by it, not by the tensor pipe.
+//   PG_DX   dZ1 = (dZ2 W2^T) * mask1 : A = dZ2 [B][H2] K-major, B = W2 [H1][H2] K-major; epilogue = ReLU mask
+//           from H1's sign bits -> bf16 -> TMA store, plus the tile's column sums (db1 partials) read back
+//           from the staged tile -- the separate column-sum kernel and its 8 MB re-read are gone
+//   PG_DW   dW = A^T-form split-K : A [K][M] MN-major, B [K][N] MN-major (activations as stored);
+//           epilogue = fp32 partial tile -> slice `split`
+// All roles are rolled loops (see ff_forward2_kernel on why code size matters).
+// ---------------------------------------------------------------------------
+enum { PG_DX = 0, PG_DW = 1 };
+constexpr int PG_STAGES = 3;                  // 3 x 32 KB: two CTAs (of different kernels / tiles) share an SM and interleave their phases
+constexpr uint32_t PG_STAGE_BYTES = 32768;      // A [128 x 64] + this CTA's half of B [128 x 64], bf16
+constexpr int PG_THREADS = 320;                 // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
+
+struct PairGemmArgs {
+    int M, N, K;                  // logical problem; K = full reduction length
+    int k_per_split;              // multiple of 64
+    // PG_DX
+    __nv_bfloat16 *out_bf16;      // (unused: the tile leaves by TMA store through tmC)
+    const __nv_bfloat16 *mask_src;   // [M][ldo], sign bit set <=> masked
+    float *colsum;                // [M / 128][N] column sums of the stored (rounded) tile rows
+    // PG_DW
+    float *out_f32;               // [nsplit][M][ldo]
+    long long slice_stride;
+    int ldo;
+};
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PG_THREADS, 2)
+pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const PairGemmArgs g)
+{
+    constexpr bool MN = (KIND == PG_DW);          // both operands MN-major (A [K][M], B [K][N]) or both K-major
+    constexpr uint32_t IDESC = make_idesc_bf16(256, 256, MN, MN);
+    constexpr uint16_t BOTH = 3;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full_bar[PG_STAGES], empty_bar[PG_STAGES], acc_full;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int m0 = blockIdx.x * BM;                       // this CTA's 128 rows of the 256-row tile
+    const int n0 = blockIdx.y * 256;                      // the pair's 256 columns
+    const int nb = n0 + (int)rank * 128;                  // ... of which this CTA loads 128
+    const int split = blockIdx.z;
+    const int k_begin = split * g.k_per_split;
+    const int k_end = min(g.K, k_begin + g.k_per_split);
+    const int nkb = (k_end - k_begin + BK - 1) / BK;      // same in both CTAs of the pair
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        for (int s = 0; s < PG_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(&tmem_base_slot, 256);
+    pdl_launch_dependents();
+    tc_fence_before();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (elect_one()) {
+            const uint32_t full_leader0 = mapa_u32(&full_bar[0], 0);
+#pragma unroll 1
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % PG_STAGES;
+                const uint32_t ph = (kb / PG_STAGES) & 1;
+                mbar_wait_bounded<false>(&empty_bar[s], ph ^ 1);
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * PG_STAGE_BYTES);
+                const uint32_t bar = full_leader0 + (uint32_t)s * 8u;
+                uint8_t *sA = smem + s * PG_STAGE_BYTES, *sB = sA + 16384;
+                const int k = k_begin + kb * BK;
+                if (!MN) {      // K-major: box {64 k, 128 rows}
+                    tma_load_2d_pair(sA, &tmA, k, m0, bar);
+                    tma_load_2d_pair(sB, &tmB, k, nb, bar);
+                } else {        // MN-major: boxes {64 mn, 64 k-rows}, 8 KB each
+                    tma_load_2d_pair(sA, &tmA, m0, k, bar);
+                    tma_load_2d_pair(sA + 8192, &tmA, m0 + 64, k, bar);
+                    tma_load_2d_pair(sB, &tmB, nb, k, bar);
+                    tma_load_2d_pair(sB + 8192, &tmB, nb + 64, k, bar);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===== MMA issuer (leader) =====
+#pragma unroll 1
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % PG_STAGES;
+                const uint32_t ph = (kb / PG_STAGES) & 1;
+                mbar_wait_bounded<false>(&full_bar[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t aaddr = smem_u32(smem + s * PG_STAGE_BYTES), baddr = aaddr + 16384;
+#pragma unroll
+                    for (int kk = 0; kk < BK / UK; kk++) {
+                        const uint64_t ad = MN ? make_smem_desc(aaddr + kk * 2048, 8192, 1024) : make_smem_desc(aaddr + kk * 32, 16, 1024);
+                        const uint64_t bd = MN ? make_smem_desc(baddr + kk * 2048, 8192, 1024) : make_smem_desc(baddr + kk * 32, 16, 1024);
+                        mma_bf16_pair(tmem, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
+                    }
+                    mma_commit_pair(&empty_bar[s], BOTH);
+                    if (kb == nkb - 1) mma_commit_pair(&acc_full, BOTH);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs, own 128 rows x 256 columns) =====
+        const int q = warp & 3, cg = (warp - 2) >> 2;
+        const int rt = q * 32 + lane;
+        const int row = m0 + rt;
+        const int et = threadIdx.x - 64;
+        const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+        const int cbase = cg * 128;                        // this warp's four 32-column chunks
+        if (KIND == PG_DX) {
+            // the ReLU mask (sign bits of H1) of this thread's 128 columns, one 32-column chunk ahead of its use;
+            // the first chunk's loads are issued before the accumulator is ready
+            uint4 mk[2][4];
+            const uint4 *mp = reinterpret_cast<const uint4 *>(g.mask_src + (size_t)row * g.ldo + n0 + cbase);
+#pragma unroll
+            for (int v = 0; v < 4; v++) mk[0][v] = (row < g.M) ? __ldg(mp + v) : make_uint4(0, 0, 0, 0);
+            if (nkb > 0) mbar_wait_bounded<false>(&acc_full, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t r[32];
+                tmem_ld_32x32(tq + (uint32_t)(cbase + 32 * c), r);
+                if (c < 3) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) mk[(c + 1) & 1][v] = (row < g.M) ? __ldg(mp + 4 * (c + 1) + v) : make_uint4(0, 0, 0, 0);
+                }
+                tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const uint4 m4 = mk[c & 1][j >> 3];
+                    const uint32_t mm = ((j >> 1) & 3) == 0 ? m4.x : (((j >> 1) & 3) == 1 ? m4.y : (((j >> 1) & 3) == 2 ? m4.z : m4.w));
+                    const float v0 = (mm & 0x8000u) ? 0.f : __uint_as_float(r[j]);
+                    const float v1 = (mm & 0x80000000u) ? 0.f : __uint_as_float(r[j + 1]);
+                    __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+                    packed[j >> 1] = *reinterpret_cast<uint32_t *>(&pk);
+                }
+                // staged tile = the first 64 KB of the (now idle) ring: [4 boxes of 64 columns][128 rows][128 B], SW128
+                const int c0 = cbase + 32 * c;
+                uint8_t *dst = smem + (c0 >> 6) * 16384 + rt * 128;
+                const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+                    *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
+                        make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) {
+                for (int b = 0; b < 4; b++) tma_store_2d(&tmC, smem + b * 16384, n0 + 64 * b, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            // db1 partials of this 128-row slab: warp w < 4 sums box w, lane = one bf16 pair of the 64-column row
+            if (et < 128) {
+                const int bx = et >> 5;
+                const uint8_t *box = smem + bx * 16384;
+                float sx = 0.f, sy = 0.f;
+#pragma unroll 8
+                for (int rr = 0; rr < BM; rr++) {
+                    const uint32_t wv = *reinterpret_cast<const uint32_t *>(box + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
+                    if (m0 + rr < g.M) { sx += __uint_as_float(wv << 16); sy += __uint_as_float(wv & 0xffff0000u); }
+                }
+                float2 *cs = reinterpret_cast<float2 *>(g.colsum + (size_t)blockIdx.x * g.N + n0 + bx * 64 + lane * 2);
+                *cs = make_float2(sx, sy);
+            }
+            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        } else {
+            if (nkb > 0) mbar_wait_bounded<false>(&acc_full, 0);
+            tc_fence_after();
+            float *o = g.out_f32 + (size_t)split * g.slice_stride + (size_t)row * g.ldo + n0 + cbase;
+#pragma unroll 1
+            for (int c = 0; c < 4; c++) {
+                uint32_t r[32];
+                if (nkb > 0) { tmem_ld_32x32(tq + (uint32_t)(cbase + 32 * c), r); tmem_ld_wait(); }
+                else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) r[j] = 0u;
+                }
+                if (row < g.M) {
+#pragma unroll
+                    for (int v = 0; v < 8; v++)
+                        reinterpret_cast<float4 *>(o + 32 * c)[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                                                              __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    cluster_sync();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem, 256);
+    }
+}
+
+constexpr size_t pair_gemm_smem_bytes() { return (size_t)PG_STAGES * PG_STAGE_BYTES + 1024; }
+
+// ---------------------------------------------------------------------------
 // host: tensor maps
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -1065,6 +1278,8 @@ cudaError_t configure_all_gemms()
         e = cudaFuncSetAttribute(ff_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<1>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(ff_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes<2>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pair_gemm_kernel<PG_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_gemm_smem_bytes());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pair_gemm_kernel<PG_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_gemm_smem_bytes());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(ff_forward2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff2_smem_bytes<1>());
     if (e == cudaSuccess)
@@ -1513,7 +1728,12 @@ __device__ __forceinline__ void finish4(const Dims &d, const Offsets &o, int i, 
 
 // (DP: at least 5 CTAs per SM, so that the whole grid -- 727 CTAs on the wide configuration -- is
 // resident while its threads wait on their peers)
-template <bool FUSE, bool DP = false>
+// LPG = lanes per float4 group in part A.  With one lane per group a group with 32 split-K slices needs four
+// dependent rounds of eight loads (four L2 round trips: the tail of the whole step); with four lanes each lane
+// sums a quarter of the slices in ONE round and the quarters are combined in a fixed shuffle tree (so the sum
+// stays deterministic).  The data-parallel instantiation keeps one lane per group: its grid has to be
+// co-resident (wide_p2p_resident).
+template <bool FUSE, bool DP = false, int LPG = 1>
 __global__ void __launch_bounds__(128, DP ? 5 : 0)
 wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count, float *__restrict__ flat,
                    float *__restrict__ theta, float *__restrict__ m, float *__restrict__ v, AdamConsts ac,
@@ -1530,8 +1750,11 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
     constexpr bool dp = FUSE && DP;      // (a separate instantiation: the exchange costs registers)
     if ((int)blockIdx.x < pl.blocksA) {
         // ---- A: weights ------------------------------------------------------------
-        const int gidx = blockIdx.x * 128 + threadIdx.x;
-        if (gidx >= pl.nA) return;
+        int gidx = (blockIdx.x * 128 + threadIdx.x) / LPG;
+        const int sub = threadIdx.x % LPG;
+        const bool live = gidx < pl.nA;  // (every lane stays for the shuffles below)
+        if (LPG == 1 && !live) return;
+        if (!live) gidx = 0;
         const int n1g = (d.D * d.H1) >> 2, n2g = (d.H1 * d.H2) >> 2;
         int i, n;
         const float *base;
@@ -1540,20 +1763,31 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
         else if (gidx < n1g + n2g) { const int u = (gidx - n1g) * 4; i = o.w2 + u; base = ps.w2_slices + u; n = ps.n2; stride = (int64_t)d.H1 * d.H2; }
         else { const int u = (gidx - n1g - n2g) * 4; i = o.w3 + u; base = ps.w3_slices + u; n = ps.n3; stride = (int64_t)d.H2 * d.A; }
         float4 w4 = make_float4(0, 0, 0, 0), m4 = w4, v4 = w4;
-        if (FUSE) {
+        if (!live) n = 0;
+        if (FUSE && sub == 0 && live) {
             w4 = *reinterpret_cast<const float4 *>(theta + i);
             m4 = *reinterpret_cast<const float4 *>(m + i);
             v4 = *reinterpret_cast<const float4 *>(v + i);
         }
         float4 g = make_float4(0, 0, 0, 0);
-        for (int z = 0; z < n; z += 8) {
+        for (int z = sub; z < n; z += 8 * LPG) {     // lane `sub` takes slices sub, sub + LPG, ...
             float4 t[8];
 #pragma unroll
             for (int u = 0; u < 8; u++)
-                t[u] = (z + u < n) ? __ldg(reinterpret_cast<const float4 *>(base + (int64_t)(z + u) * stride))
-                                   : make_float4(0, 0, 0, 0);
+                t[u] = (z + u * LPG < n) ? __ldg(reinterpret_cast<const float4 *>(base + (int64_t)(z + u * LPG) * stride))
+                                         : make_float4(0, 0, 0, 0);
 #pragma unroll
             for (int u = 0; u < 8; u++) g = f4add(g, t[u]);
+        }
+        if (LPG > 1) {
+#pragma unroll
+            for (int off = 1; off < LPG; off <<= 1) {
+                g.x += __shfl_xor_sync(0xffffffffu, g.x, off);
+                g.y += __shfl_xor_sync(0xffffffffu, g.y, off);
+                g.z += __shfl_xor_sync(0xffffffffu, g.z, off);
+                g.w += __shfl_xor_sync(0xffffffffu, g.w, off);
+            }
+            if (sub != 0 || !live) return;
         }
         bool ok = true;     // false: a peer's word never arrived -- leave theta / m / v / shadows untouched
         if (dp) g = dp_exchange4(push, epoch, i, g, ok);
@@ -1673,6 +1907,7 @@ struct WideState {
     cudaEvent_t ev_dz2 = nullptr, ev_dx = nullptr, ev_s1 = nullptr, ev_s2 = nullptr, ev_fork = nullptr, ev_gather = nullptr;
     bool pdl = true;
     bool ff = false;                       // fused three-layer forward kernel usable
+    bool pair_dx = false, pair_dw2 = false;   // backward GEMMs on CTA pairs (pair_gemm_kernel); pair_dx also produces the db1 partials
     int skip = 0;                          // GOLDQ_SKIP bit mask (diagnostic): launches left out of the step, see wide_step
     long long *ff_stamps = nullptr;        // GOLDQ_FF_STAMPS: in-kernel clock stamps of the fused forward (diagnostic)
     bool ff2 = false;                      // ... on CTA pairs (cta_group::2): needs an even number of 128-row slabs
@@ -1734,6 +1969,22 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     w->ns2 = split_for(tiles2, B, sm_count, &w->kps2);
     w->ns3 = split_for(tiles3, B, sm_count, &w->kps3);
     w->nb1 = (B + CS_ROWS - 1) / CS_ROWS;
+    const bool no_pair = getenv("GOLDQ_NO_PAIR_GEMM") != nullptr;
+    // dX on CTA pairs: 256 x 256 tiles need whole 256-row / 256-column tiles; it writes one db1 partial per 128-row slab
+    w->pair_dx = !no_pair && B % 256 == 0 && d.H1 % 256 == 0 && d.H2 % 64 == 0;
+    if (w->pair_dx) w->nb1 = B / BM;
+    // dW2 on CTA pairs: (H1/256) x (H2/256) pair tiles, split-K so that about one CTA lands on every SM
+    w->pair_dw2 = !no_pair && d.H1 % 256 == 0 && d.H2 % 256 == 0 && B % 64 == 0;
+    if (w->pair_dw2) {
+        // never more CTAs than SMs (one CTA per SM: a few CTAs left for a second wave would double the time)
+        const int tiles = (d.H1 / BM) * (d.H2 / 256), kblocks = B / BK;
+        int want = sm_count / tiles;
+        if (want < 1) want = 1;
+        if (want > kblocks) want = kblocks;
+        const int per = (kblocks + want - 1) / want;
+        w->kps2 = per * BK;
+        w->ns2 = (kblocks + per - 1) / per;
+    }
     w->nb2 = (B + DZ_ROWS - 1) / DZ_ROWS;
     w->nrow = w->nb2;   // db3 / loss partials come from the same blocks as db2
     ok = ok && dmalloc(&w->w1_slices, (size_t)w->ns1 * d.D * d.H1, err) &&
@@ -1880,13 +2131,13 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
     return 1;
 }
 
-static UpdatePlan make_update_plan(const Dims &d)
+static UpdatePlan make_update_plan(const Dims &d, int lpg = 1)
 {
     UpdatePlan pl;
     pl.nA = (d.D * d.H1 + d.H1 * d.H2 + d.H2 * d.A) >> 2;
     pl.nB = (d.H1 + d.H2) >> 2;
     pl.nC = d.A + 1;
-    pl.blocksA = (pl.nA + 127) / 128;
+    pl.blocksA = (pl.nA * lpg + 127) / 128;
     pl.blocksB = (pl.nB + 3) / 4;
     pl.blocksC = (pl.nC + 3) / 4;
     return pl;
@@ -1931,6 +2182,15 @@ int wide_sync_target(WideState *w, cudaStream_t st, std::string &err)
         cudaError_t e_ = (expr);                                                     \
         if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return -1; } \
     } while (0)
+
+template <int KIND>
+static cudaError_t launch_pair_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const PairGemmArgs &g,
+                                    int nsplit, cudaStream_t st, bool pdl)
+{
+    dim3 grid((g.M + BM - 1) / BM, (g.N + 255) / 256, nsplit);
+    if (grid.x & 1) return cudaErrorInvalidConfiguration;       // pairs along M
+    return launch_k(pair_gemm_kernel<KIND>, grid, dim3(PG_THREADS), pair_gemm_smem_bytes(), st, pdl, ta, tb, tc, g);
+}
 
 // the fused forward of both networks on batch set `bt` (pair kernel when the slab count is even)
 static cudaError_t launch_fused_forward(WideState *w, WideState::BatchSet &bt, const float *theta, const float *theta_t,
@@ -1993,7 +2253,9 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     int launches = 0;
     const bool prof = s.prof_evs != nullptr;
     const bool pdl = w->pdl && !prof;   // programmatic dependent launch along the st chain
-    cudaStream_t s1 = prof ? st : w->s1, s2 = prof ? st : w->s2;
+    static const bool serial = getenv("GOLDQ_SERIAL") != nullptr;   // diagnostic: no parallel backward branches
+    const bool one_stream = prof || serial;
+    cudaStream_t s1 = one_stream ? st : w->s1, s2 = one_stream ? st : w->s2;
     if (prof) w->prof_names.clear();
     auto mark = [&](const char *name) {
         if (prof) { cudaEventRecord(s.prof_evs[(*s.prof_n)++], st); w->prof_names.push_back(name); }
@@ -2067,7 +2329,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     launches += 1;
 
     // backward: three independent chains after dZ2 —  s1: dW2 | s2: dW3, db1 | st: dX -> dW1
-    if (!prof) {
+    if (!one_stream) {
         WCK(cudaEventRecord(w->ev_dz2, st));
         WCK(cudaStreamWaitEvent(s1, w->ev_dz2, 0));
         WCK(cudaStreamWaitEvent(s2, w->ev_dz2, 0));
@@ -2084,17 +2346,27 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g.M = d.H1; g.N = d.H2; g.K = B; g.k_per_split = w->kps2;
     g.out_f32 = w->w2_slices; g.ldo = d.H2; g.n_store = d.H2; g.slice_stride = (long long)d.H1 * d.H2;
     if (w->skip & 16) {
+    } else if (w->pair_dw2) {
+        PairGemmArgs pg{};
+        pg.M = d.H1; pg.N = d.H2; pg.K = B; pg.k_per_split = w->kps2;
+        pg.out_f32 = w->w2_slices; pg.ldo = d.H2; pg.slice_stride = (long long)d.H1 * d.H2;
+        WCK(launch_pair_gemm<PG_DW>(w->tm_h1_mm, w->tm_dz2_mm, w->tm_dz2_mm, pg, w->ns2, s1, false));
     } else if (w->mc_h1)
         WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE, 4>(w->tm_h1_mm, w->tm_dz2_mm_s4, g, w->ns2, s1)));
     else
         WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, s1)));
-    mark("dW2 split-K (tcgen05)");
-    if (!prof) WCK(cudaEventRecord(w->ev_s1, s1));
+    mark(w->pair_dw2 ? "dW2 split-K, CTA pairs (tcgen05 cta_group::2)" : "dW2 split-K (tcgen05)");
+    if (!one_stream) WCK(cudaEventRecord(w->ev_s1, s1));
     // dZ1 = (dZ2 W2^T) * mask1 : M = B, N = H1, K = H2 ; B operand = W2 [H1 rows][H2 cols]
     g = GemmArgs{};
     g.M = B; g.N = d.H1; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = w->dz1; g.mask_src = w->h1; g.ldo = d.H1; g.n_store = d.H1;
     if (w->skip & 32) {
+    } else if (w->pair_dx) {
+        PairGemmArgs pg{};
+        pg.M = B; pg.N = d.H1; pg.K = d.H2; pg.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
+        pg.mask_src = w->h1; pg.ldo = d.H1; pg.colsum = w->b1_part;
+        WCK(launch_pair_gemm<PG_DX>(w->tm_dz2_a, on.tm_w2_k, w->tm_dz1_a, pg, 1, st, pdl));
     } else if (w->bn256)
         // one CTA per SM here (B/128 x H1/256 tiles <= SMs): a 4-stage ring (192 KB) instead of 2
         if (((B + BM - 1) / BM) * ((d.H1 + 255) / 256) <= w->sm_count)
@@ -2105,18 +2377,19 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16, 4>(w->tm_dz2_a, on.tm_w2_k_s4, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
     else
         WCK((launch_gemm<MODE_KK, 128, EPI_MASK_BF16>(w->tm_dz2_a, on.tm_w2_k, g, 1, st, nullptr, nullptr, pdl, &w->tm_dz1_a)));
-    mark("dX -> dZ1 (tcgen05)");
-    if (!prof) {
+    mark(w->pair_dx ? "dX -> dZ1 + db1, CTA pairs (tcgen05 cta_group::2)" : "dX -> dZ1 (tcgen05)");
+    if (!one_stream) {
         WCK(cudaEventRecord(w->ev_dx, st));
         WCK(cudaStreamWaitEvent(s2, w->ev_dx, 0));
     }
-    if (!(w->skip & 64)) {
+    if (!(w->skip & 64) && !w->pair_dx) {
         dim3 grid((d.H1 + 63) / 64, w->nb1);
         wide_colsum_kernel<<<grid, 256, 0, s2>>>(w->dz1, B, d.H1, w->b1_part);
         WCK(cudaGetLastError());
         mark("db1 colsum");
+        launches++;
     }
-    if (!prof) WCK(cudaEventRecord(w->ev_s2, s2));
+    if (!one_stream) WCK(cudaEventRecord(w->ev_s2, s2));
     // dW1 = X^T dZ1 : M = D, N = H1, K = B
     g = GemmArgs{};
     g.M = d.D; g.N = d.H1; g.K = B; g.k_per_split = w->kps1;
@@ -2124,15 +2397,17 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     if (!(w->skip & 128))
     WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(bt.tm_x_mm, w->tm_dz1_mm, g, w->ns1, st, nullptr, nullptr, pdl)));
     mark("dW1 split-K (tcgen05)");
-    if (!prof) {
+    if (!one_stream) {
         WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
         WCK(cudaStreamWaitEvent(st, w->ev_s2, 0));
     }
-    launches += 5;
+    launches += 4;
 
     PartialSrc ps{w->w1_slices, w->ns1, w->b1_part, w->nb1, w->w2_slices, w->ns2,
                   w->b2_part,   w->nb2, w->w3_slices, w->ns3, w->row_part, w->nrow};
-    const UpdatePlan pl = make_update_plan(d);
+    constexpr int LPG = 1;      // (4 lanes per group measured slower: 15.5 vs 12.9 us for the launch, 66.4 vs 62.1 us/step)
+    const bool lanes4 = !(s.fuse_update && s.push);      // every launch but the data-parallel one
+    const UpdatePlan pl = make_update_plan(d, lanes4 ? LPG : 1);
     const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
     // (the update kernel follows cross-stream event waits: a full dependency, no PDL)
     if (w->skip & 256) {
@@ -2140,10 +2415,10 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         wide_update_kernel<true, true><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
                                                                s.step, shadow_ptrs(w, 0), s.loss_out, *s.push, s.epoch);
     else if (s.fuse_update)
-        wide_update_kernel<true><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
+        wide_update_kernel<true, false, LPG><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
                                                          s.step, shadow_ptrs(w, 0), s.loss_out, PeerSet{}, 0u);
     else
-        wide_update_kernel<false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
+        wide_update_kernel<false, false, LPG><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
                                                           s.adam, s.step, shadow_ptrs(w, 0), nullptr, PeerSet{}, 0u);
     WCK(cudaGetLastError());
     mark("reduce + Adam + bf16 shadow (K5)");

@@ -144,7 +144,8 @@ def _emulate_bf16_step(dims, th, tt, s, a, r, s2, done, gamma, count):
     return q, qt, td, loss, grads
 
 
-@pytest.mark.parametrize("dims,B", [(synth.WIDE, 512), ((64, 256, 128, 6), 200), ((64, 512, 512, 6), 256), (synth.WIDE, 384)])
+@pytest.mark.parametrize("dims,B", [(synth.WIDE, 512), ((64, 256, 128, 6), 200), ((64, 512, 512, 6), 256), (synth.WIDE, 384),
+                                    ((64, 256, 128, 6), 256)])     # dX on CTA pairs with one 256-column tile, dW2 single-CTA
 def test_wide_matches_bf16_emulation(dims, B):
     """Correctness independent of precision: against a numpy restatement that rounds to bf16
     at the same points, every gradient block must agree to accumulation-order noise."""
