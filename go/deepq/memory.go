@@ -3,19 +3,25 @@ package deepq
 import (
 	"fmt"
 	"math/rand"
+	"time"
 
 	envv1 "github.com/aunum/gold/pkg/v1/env"
+	"github.com/aunum/log"
+	"github.com/gammazero/deque"
 	"gorgonia.org/tensor"
-
-	"github.com/aunum/gold-b200/go/goldq"
 )
 
 // Event is an event that occurred (reference: memory.go:15-25).
 type Event struct {
 	*envv1.Outcome
-	State  *tensor.Dense
+
+	// State by which the action was taken.
+	State *tensor.Dense
+
+	// Action that was taken.
 	Action int
-	i      int
+
+	i int
 }
 
 // NewEvent returns a new event (reference: memory.go:28-34).
@@ -23,55 +29,51 @@ func NewEvent(state *tensor.Dense, action int, outcome *envv1.Outcome) *Event {
 	return &Event{State: state, Action: action, Outcome: outcome}
 }
 
-// Memory for the dqn agent (reference: memory.go:41-51).  The events live in the
-// device replay ring; PushFront buffers them on the host until the next Learn.
-type Memory struct {
-	h       *goldq.Handle
-	pending []*Event
+// Print the event (reference: memory.go:37-39).
+func (e *Event) Print() {
+	log.Infof("event --> \n state: %v \n action: %v \n reward: %v \n done: %v \n obv: %v\n\n",
+		e.State, e.Action, e.Reward, e.Done, e.Observation)
 }
 
-// NewMemory returns a new Memory store.
-func NewMemory(h *goldq.Handle) *Memory { return &Memory{h: h} }
+// Memory for the dqn agent (reference: memory.go:41-51).  As in the reference it IS a deque of
+// *Event (PushFront / PopBack / At / Len come from the embedded type), so code written against
+// gold's Memory keeps compiling.  The agent additionally mirrors every remembered event into the
+// device replay ring (Agent.Remember), which is what Learn samples from; the host deque only
+// serves callers that want the Events back.
+type Memory struct {
+	*deque.Deque
+}
 
-// Len of the memory (deque.Len).
-func (m *Memory) Len() int { return m.h.ReplayLen() + len(m.pending) }
+// NewMemory returns a new Memory store (reference: memory.go:46-51).
+func NewMemory() *Memory {
+	return &Memory{Deque: &deque.Deque{}}
+}
 
-// PushFront makes the event logical index 0 (deque.PushFront).
-func (m *Memory) PushFront(e *Event) { m.pending = append(m.pending, e) }
-
-// Sample returns batchsize distinct logical indices (reference: memory.go:54-69;
-// the reference returns the events, which here live on the device).
-func (m *Memory) Sample(batchsize int) ([]int32, error) {
-	if m.Len() < batchsize {
-		return nil, fmt.Errorf("queue size %d is less than batch size %d", m.Len(), batchsize)
+// Sample from the memory with the given batch size (reference: memory.go:54-69): an error when
+// fewer than batchsize events are held, otherwise batchsize distinct events, uniformly, each with
+// its logical index (0 = newest) recorded in the unexported field i.
+func (m *Memory) Sample(batchsize int) ([]*Event, error) {
+	n := m.Len()
+	if n < batchsize {
+		return nil, fmt.Errorf("queue size %d is less than batch size %d", n, batchsize)
 	}
-	perm := rand.Perm(m.Len())[:batchsize]
-	out := make([]int32, batchsize)
-	for i, v := range perm {
-		out[i] = int32(v)
+	rng := rand.New(rand.NewSource(time.Now().UnixNano()))
+	picked := rng.Perm(n)[:batchsize]
+	out := make([]*Event, 0, batchsize)
+	for _, at := range picked {
+		ev := m.At(at).(*Event)
+		ev.i = at
+		out = append(out, ev)
 	}
 	return out, nil
 }
 
-func (m *Memory) flush() error {
-	n := len(m.pending)
-	if n == 0 {
-		return nil
+// indices returns the logical indices of a sampled batch (what the device learn step takes when
+// the host, not the device, draws the sample).
+func indices(batch []*Event) []int32 {
+	out := make([]int32, len(batch))
+	for k, ev := range batch {
+		out[k] = int32(ev.i)
 	}
-	var s, s2, r []float32
-	var a []int32
-	var d []uint8
-	for _, e := range m.pending {
-		s = append(s, e.State.Data().([]float32)...)
-		s2 = append(s2, e.Observation.Data().([]float32)...)
-		a = append(a, int32(e.Action))
-		r = append(r, e.Reward)
-		if e.Done {
-			d = append(d, 1)
-		} else {
-			d = append(d, 0)
-		}
-	}
-	m.pending = m.pending[:0]
-	return m.h.ReplayPush(n, s, a, r, s2, d)
+	return out
 }

@@ -129,6 +129,31 @@ func (x *Handle) ReplayPush(n int, s []float32, a []int32, r []float32, s2 []flo
 }
 func (x *Handle) ReplayLen() int { return int(C.goldq_replay_len(x.h)) }
 
+// PackedBytes is the size of the one-buffer layout s|s2|a|r|done for n transitions (goldq.h).
+func (x *Handle) PackedBytes(n int) int { return int(C.goldq_packed_bytes(x.h, C.int64_t(n))) }
+
+// ReplayPushPacked appends n transitions from ONE contiguous buffer: one host-to-device copy instead of five.
+func (x *Handle) ReplayPushPacked(n int, packed []byte) error {
+	return x.err(C.goldq_replay_push_packed(x.h, C.int64_t(n), unsafe.Pointer(&packed[0])))
+}
+
+// ResizeBatch is Sequential.ResizeBatch: scratch sized by the batch is re-allocated, parameters, solver state
+// and replay are kept.
+func (x *Handle) ResizeBatch(n int) error {
+	if err := x.err(C.goldq_resize_batch(x.h, C.int32_t(n))); err != nil {
+		return err
+	}
+	x.c.BatchSize = n
+	return nil
+}
+func (x *Handle) BatchSize() int { return int(C.goldq_batch_size(x.h)) }
+
+// LearnPrepare instantiates the step graphs now instead of on the first Learn.
+func (x *Handle) LearnPrepare() error { return x.err(C.goldq_learn_prepare(x.h)) }
+
+// Config returns the configuration the handle was created with (batch size kept current).
+func (x *Handle) Config() Config { return x.c }
+
 // Learn runs one learn step; idx == nil draws the indices on the device from seed.
 func (x *Handle) Learn(idx []int32, seed uint64) error {
 	if idx == nil {

@@ -26,7 +26,7 @@ SYMBOLS = [
     "goldq_abi_version", "goldq_param_count", "goldq_selected_path", "goldq_set_params",
     "goldq_get_params", "goldq_set_adam_state", "goldq_get_adam_state", "goldq_replay_push",
     "goldq_replay_len", "goldq_replay_push_wait", "goldq_host_alloc", "goldq_host_free",
-    "goldq_replay_push_packed", "goldq_packed_bytes", "goldq_learn_prepare", "goldq_graph_builds", "goldq_launch_floor", "goldq_time_forward",
+    "goldq_replay_push_packed", "goldq_packed_bytes", "goldq_learn_prepare", "goldq_graph_builds", "goldq_launch_floor", "goldq_time_forward", "goldq_resize_batch", "goldq_batch_size",
     "goldq_learn", "goldq_learn_device_indices", "goldq_learn_many", "goldq_sampler_indices", "goldq_sync_target",
     "goldq_last_loss", "goldq_predict", "goldq_greedy_action", "goldq_epsilon_greedy_action", "goldq_explore_plan",
     "goldq_fit_batch",
@@ -86,6 +86,8 @@ def lib():
         "goldq_graph_builds": (i64, [vp]),
         "goldq_launch_floor": (C.c_int, [vp, i32, fp]),
         "goldq_time_forward": (C.c_int, [vp, i32, fp]),
+        "goldq_resize_batch": (C.c_int, [vp, i32]),
+        "goldq_batch_size": (i32, [vp]),
         "goldq_replay_len": (i64, [vp]),
         "goldq_replay_push_wait": (C.c_int, [vp]),
         "goldq_host_alloc": (vp, [i64]),
@@ -264,6 +266,12 @@ class Handle:
             out[o:o + p.size] = p
             o += p.size
         return out
+
+    def resize_batch(self, n):
+        """Sequential.ResizeBatch: new batch size, same parameters / solver state / replay."""
+        self._ck(self._L.goldq_resize_batch(self._h, int(n)))
+        self.B = int(self._L.goldq_batch_size(self._h))
+        self.cfg.batch_size = self.B
 
     def learn_prepare(self):
         self._ck(self._L.goldq_learn_prepare(self._h))

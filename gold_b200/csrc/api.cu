@@ -1126,6 +1126,75 @@ int goldq_learn(goldq_t *h, const int32_t *idx, uint64_t seed)
     return learned(h, run_learn(h, idx_dev, seed));
 }
 
+/* Sequential.ResizeBatch (goro model.go:485-497): re-allocate everything sized by the batch -- index list,
+ * narrow-path partials, the wide path's activations / tensor maps / split-K plan, debug snapshots -- for a new
+ * batch size.  Parameters, solver state and the replay ring are untouched; cached step graphs are dropped. */
+int goldq_resize_batch(goldq_t *h, int32_t n)
+{
+    if (!h || n < 1) return fail(h, GOLDQ_EINVAL, "resize_batch: batch size must be >= 1");
+    if (h->world > 1) return fail(h, GOLDQ_EUNSUPPORTED, "resize_batch: not inside a data-parallel group (global_batch is fixed)");
+    if (n == h->B) return GOLDQ_OK;
+    CK(h, cudaSetDevice(h->dev));
+    CK(h, cudaStreamSynchronize(h->st));
+    CK(h, cudaStreamSynchronize(h->copy_st));
+    drop_graphs(h);
+    const int oldB = h->B;
+    WideState *nw = nullptr;
+    if (h->path == GOLDQ_PATH_WIDE) {        // build the new state first: a shape error leaves the handle as it was
+        std::string err;
+        nw = wide_create(h->dims, n, h->sm_count, err);
+        if (!nw) return fail(h, GOLDQ_EINVAL, "resize_batch (wide path): " + err);
+    }
+    int32_t *idx = nullptr;
+    if (dalloc(&idx, (size_t)h->R * n) != cudaSuccess) { if (nw) wide_destroy(nw); return fail(h, GOLDQ_ECUDA, "cudaMalloc failed (index list)"); }
+    cudaFree(h->d_idx);
+    h->d_idx = idx;
+    h->B = n;
+    h->Bglobal = n;
+    h->cfg.batch_size = n;
+    h->cfg.global_batch = 0;
+    if (h->path == GOLDQ_PATH_NARROW) {
+        NarrowArgs a{};
+        a.B = h->B;
+        a.replicas = h->R;
+        narrow_plan(a, h->sm_count);
+        h->n_ctas = a.ctas_per_replica;
+        h->n_warps = a.warps_per_cta;
+        narrow_configure(h->dims, h->n_warps);
+        if (h->partial) cudaFree(h->partial);
+        h->partial = nullptr;
+        CK(h, dalloc(&h->partial, (size_t)h->R * narrow_partial_floats(h->n_ctas, h->P)));
+        CK(h, cudaMemsetAsync(h->ticket, 0, (size_t)h->R * (NARROW_MAX_GROUPS + 1) * sizeof(unsigned), h->st));
+    } else if (h->path == GOLDQ_PATH_WIDE) {
+        wide_destroy(h->wide);
+        h->wide = nw;
+        wide_set_debug(h->wide, h->debug);
+        std::string err;
+        for (int net = 0; net < 2; net++) {      // bf16 shadows of the (unchanged) fp32 master parameters
+            int k = wide_set_params(h->wide, net, net == GOLDQ_NET_ONLINE ? h->theta : h->theta_t, h->st, err);
+            if (k < 0) return fail(h, GOLDQ_ECUDA, err);
+            h->launches += k;
+        }
+    }
+    // (the generic path's scratch grows on demand: ensure_generic)
+    if (h->dbg_q) {
+        void *old[] = {h->dbg_q, h->dbg_qt, h->dbg_td, h->dbg_idx};
+        for (void *p : old) cudaFree(p);
+        h->dbg_q = h->dbg_qt = h->dbg_td = nullptr;
+        h->dbg_idx = nullptr;
+        size_t RB = (size_t)h->R * h->B;
+        CK(h, dalloc(&h->dbg_q, RB * h->dims.A));
+        CK(h, dalloc(&h->dbg_qt, RB * h->dims.A));
+        CK(h, dalloc(&h->dbg_td, RB));
+        CK(h, dalloc(&h->dbg_idx, RB));
+    }
+    (void)oldB;
+    CK(h, cudaStreamSynchronize(h->st));
+    return GOLDQ_OK;
+}
+
+int32_t goldq_batch_size(const goldq_t *h) { return h ? h->B : 0; }
+
 int goldq_learn_prepare(goldq_t *h)
 {
     if (!h) return GOLDQ_EINVAL;

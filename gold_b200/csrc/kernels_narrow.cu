@@ -403,8 +403,12 @@ void launch_t(const NarrowArgs &a, cudaStream_t st)
 template <int D, int H1, int H2, int A>
 void configure_t(int warps)
 {
+    // The attribute belongs to the function, not to the handle: a later handle with fewer warps must not
+    // lower it below what an earlier handle launches with, so always opt in to the 16-warp maximum.
+    (void)warps;
     constexpr int P = D * H1 + H1 + H1 * H2 + H2 + H2 * A + A;
-    size_t smem = sizeof(float) * (4 * ((P + 3) & ~3) + H1 * H2 + (size_t)warps * (P + 1));
+    constexpr int MAX_WARPS = 16;
+    size_t smem = sizeof(float) * (4 * ((P + 3) & ~3) + H1 * H2 + (size_t)MAX_WARPS * (P + 1));
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(narrow_learn_kernel<D, H1, H2, A>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -132,7 +132,11 @@ class Memory:
         self._rng = random.Random()
 
     def len(self):
-        return self._h.replay_len() + len(self._pending) if self._h else self._len
+        """Memory.Len(): events on the device ring plus those remembered since the last flush, never more
+        than the ring holds (Remember pops the back past BufferSize, agent.go:226-228)."""
+        if not self._h:
+            return self._len
+        return min(self._h.replay_len() + len(self._pending), int(self._h.cfg.replay_capacity))
 
     def __len__(self):
         return self.len()
@@ -175,11 +179,17 @@ class Memory:
     def sample(self, batchsize):
         """Memory.Sample: errors when Len < batchsize (memory.go:55-57), otherwise returns
         `batchsize` distinct events with event.i set (memory.go:62-64)."""
-        idx = self.sample_indices(batchsize)
+        n = self.len()
+        if n < batchsize:
+            raise ValueError(f"queue size {n} is less than batch size {batchsize}")
+        # Events older than the host-side mirror exist only on the device: the Events handed back are drawn
+        # from the mirrored range (the newest `host_events`).  Learn never goes through here -- it samples on
+        # the device over the whole ring.
+        m = min(n, len(self._events))
+        if m < batchsize:
+            raise IndexError(f"only {m} events are mirrored on the host (host_events) for a sample of {batchsize}")
         out = []
-        for i in idx:
-            if i >= len(self._events):
-                raise IndexError("event older than the host-side mirror (host_events)")
+        for i in self._rng.sample(range(m), batchsize):
             e = self._events[int(i)]
             e.i = int(i)
             out.append(e)
@@ -273,6 +283,10 @@ class Sequential:
         self._need_online()
         self._h.fit_batch(x, y)
 
+    def resize_batch(self, n):
+        """Sequential.ResizeBatch (model.go:485-497): both networks of the agent share the scratch."""
+        self._h.resize_batch(n)
+
     def learnables(self):
         """Flat [W1,b1,W2,b2,W3,b3] host copy of the parameters."""
         P = self._h.P
@@ -287,6 +301,25 @@ class Sequential:
     def _need_online(self):
         if self._net != G.NET_ONLINE:
             raise ValueError("the target network is never fitted (agent.go:167 fits Policy only)")
+
+
+def handle_options(pc):
+    """PolicyConfig.Loss / .Optimizer -> goldq_config fields (shared by deepq.Agent and her.Agent).  Anything the
+    CUDA path does not implement is an error: there is no CPU fallback."""
+    if pc.loss != MSE and not isinstance(pc.loss, PseudoHuberLoss):
+        raise ValueError("the CUDA path implements model.MSE and model.PseudoHuber; no CPU fallback exists")
+    if isinstance(pc.optimizer, AdamSolver):
+        opts = dict(solver=G.SOLVER_ADAM, lr=pc.optimizer.eta, beta1=pc.optimizer.beta1, beta2=pc.optimizer.beta2,
+                    eps=pc.optimizer.eps)
+    elif isinstance(pc.optimizer, RMSPropSolver):
+        opts = dict(solver=G.SOLVER_RMSPROP, lr=pc.optimizer.eta, beta2=pc.optimizer.decay, eps=pc.optimizer.eps)
+    else:
+        raise ValueError("the CUDA path implements gorgonia.AdamSolver and RMSPropSolver; no CPU fallback exists")
+    if isinstance(pc.loss, PseudoHuberLoss):
+        opts.update(loss=G.LOSS_PSEUDO_HUBER, huber_delta=pc.loss.delta)
+    else:
+        opts.update(loss=G.LOSS_MSE)
+    return opts
 
 
 def _dims_from_layers(layers):
@@ -328,22 +361,12 @@ class Agent:
         if env is None:
             raise ValueError("environment cannot be nil")            # agent.go:96-98
         hp, pc = c.hyperparameters, c.policy_config
-        if pc.loss != MSE and not isinstance(pc.loss, PseudoHuberLoss):
-            raise ValueError("the CUDA path implements model.MSE and model.PseudoHuber; no CPU fallback exists")
-        if isinstance(pc.optimizer, AdamSolver):
-            solver = dict(solver=G.SOLVER_ADAM, lr=pc.optimizer.eta, beta1=pc.optimizer.beta1, beta2=pc.optimizer.beta2,
-                          eps=pc.optimizer.eps)
-        elif isinstance(pc.optimizer, RMSPropSolver):
-            solver = dict(solver=G.SOLVER_RMSPROP, lr=pc.optimizer.eta, beta2=pc.optimizer.decay, eps=pc.optimizer.eps)
-        else:
-            raise ValueError("the CUDA path implements gorgonia.AdamSolver and RMSPropSolver; no CPU fallback exists")
-        loss = (dict(loss=G.LOSS_PSEUDO_HUBER, huber_delta=pc.loss.delta) if isinstance(pc.loss, PseudoHuberLoss)
-                else dict(loss=G.LOSS_MSE))
+        opts = handle_options(pc)
         dims = _dims_from_layers(pc.layer_builder(env.observation_space_shape()[0], env.n_actions))
         self._h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3],
                            batch_size=pc.batch_size, replay_capacity=hp.buffer_size, gamma=hp.gamma,
                            device=c.device, precision=G.PREC_BF16 if c.precision == "bf16" else G.PREC_FP32,
-                           **solver, **loss)
+                           **opts)
         # two independently initialised networks, GlorotN(1) (agent.go:101-109; goro fc.go:76-81);
         # the target is first synced when steps % UpdateTargetSteps == 0
         seed = c.seed if c.seed is not None else random.randrange(1 << 30)
@@ -361,6 +384,7 @@ class Agent:
         self.steps = 0
         self._rng = random.Random(seed)
         self._learn_calls = 0
+        self._sync_mark = 0            # steps // update_target_steps at the last updateTarget check
 
     def action_batch(self, states):
         """Agent.Action (agent.go:193-221) for a batch of states from vectorised environments: one
@@ -386,8 +410,13 @@ class Agent:
         return None
 
     def _update_target(self):
-        if self.steps % self.update_target_steps == 0:             # agent.go:182
+        """agent.go:181-190: sync when steps lands on a multiple of UpdateTargetSteps.  action_batch advances
+        steps by a whole batch of states, so a multiple that was stepped OVER since the last check counts too
+        (with one Action per Learn this is exactly the reference's `steps % N == 0`)."""
+        mark = self.steps // self.update_target_steps
+        if self.steps % self.update_target_steps == 0 or mark != self._sync_mark:   # agent.go:182
             self.policy.clone_learnables_to(self.target_policy)
+        self._sync_mark = mark
 
     def action(self, state):
         """Agent.Action (agent.go:193-205): epsilon-greedy; steps is counted here."""

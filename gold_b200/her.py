@@ -12,7 +12,7 @@ import numpy as np
 from . import _capi as G
 from . import synth
 from .deepq import (AdamSolver, DecaySchedule, MSE, PolicyConfig, Sequential, _dims_from_layers,  # noqa: F401
-                    default_decay_schedule, default_policy_config)
+                    default_decay_schedule, default_policy_config, handle_options)
 
 
 class Event:
@@ -60,10 +60,10 @@ class Agent:
         hp, pc = c.hyperparameters, c.policy_config
         self.state_dim, self.goal_dim = int(state_dim), int(goal_dim)
         dims = _dims_from_layers(pc.layer_builder(self.state_dim + self.goal_dim, n_actions))
+        # loss / solver mapping and validation shared with deepq.Agent (PseudoHuber and RMSProp included)
         self._h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3],
                            batch_size=pc.batch_size, replay_capacity=c.memory_size, gamma=hp.gamma,
-                           lr=pc.optimizer.eta, beta1=pc.optimizer.beta1, beta2=pc.optimizer.beta2,
-                           eps=pc.optimizer.eps, device=c.device)
+                           device=c.device, **handle_options(pc))
         seed = c.seed if c.seed is not None else random.randrange(1 << 30)
         self._h.set_params(G.NET_ONLINE, synth.glorot_params(dims, seed))
         self._h.set_params(G.NET_TARGET, synth.glorot_params(dims, seed + 1))
@@ -107,7 +107,10 @@ class Agent:
         if indices is None:
             self._h.learn(None, seed=self._rng.getrandbits(63))
         else:
-            self._h.learn(indices)
+            # her.Memory indexes OLDEST first (events[value], her/memory.go:75-117); the device ring counts
+            # from the newest event (deepq's deque.At): convert
+            idx = np.asarray(indices, np.int64)
+            self._h.learn((self._len - 1 - idx).astype(np.int32))
         self.episodes += 1                                                           # agent.go:180
         if self.episodes % self.hyperparameters.update_target_episodes == 0:         # agent.go:192
             self._h.sync_target()

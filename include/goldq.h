@@ -167,6 +167,10 @@ int goldq_learn_device_indices(goldq_t *h, const int32_t *idx_dev);
  * (agent.go:173,181-190).  The graphs read the replay ring's position from per-step device
  * slots, so goldq_replay_push between calls does not invalidate them. */
 int goldq_learn_many(goldq_t *h, int32_t n, uint64_t seed);
+/* Sequential.ResizeBatch (goro model.go:485-497): change the batch size of an existing agent.  Scratch sized by
+ * the batch is re-allocated; parameters, solver state and replay are kept.  Not inside a data-parallel group. */
+int goldq_resize_batch(goldq_t *h, int32_t n);
+int32_t goldq_batch_size(const goldq_t *h);
 /* Instantiate every step graph now (16/8/4/2/1-step and the host-index step of goldq_learn)
  * instead of on first use; executes nothing.  Needs Len >= batch_size. */
 int goldq_learn_prepare(goldq_t *h);

@@ -118,8 +118,8 @@ def test_her_learn_step_is_deepq_on_state_goal():
     agent._h.debug_enable(True)
     idx = np.arange(20, dtype=np.int32) * 3
     agent.learn(indices=idx)
-    # oracle on the same rows: logical index i = i-th newest
-    rows = [events[len(events) - 1 - i] for i in idx]
+    # her.Memory indexes its events oldest first (events[value], her/memory.go:75-117)
+    rows = [events[i] for i in idx]
     s = np.stack([np.concatenate([e.state, e.goal]) for e in rows])
     s2 = np.stack([np.concatenate([e.observation, e.goal]) for e in rows])
     P = th.size
@@ -137,3 +137,72 @@ def test_her_learn_step_is_deepq_on_state_goal():
     a = agent.action(events[0].state, events[0].goal)
     assert a in (0, 1) and agent.epsilon < 1.0
     agent.close()
+
+
+@pytest.mark.gpu
+def test_her_accepts_pseudo_huber_and_rmsprop_like_deepq():
+    """her.Agent shares deepq's loss / solver mapping: a PseudoHuber + RMSProp config reaches the device as
+    such (it used to train with MSE silently / fail on .beta1), and unknown kinds fail loudly."""
+    from gold_b200 import _capi as G, her
+    pc = deepq.PolicyConfig(loss=deepq.PseudoHuberLoss(0.5), optimizer=deepq.RMSPropSolver(learn_rate=1e-3), batch_size=8)
+    agent = her.Agent(her.AgentConfig(policy_config=pc, seed=1), 2, 2, 2)
+    assert agent._h.cfg.loss == G.LOSS_PSEUDO_HUBER and agent._h.cfg.solver == G.SOLVER_RMSPROP
+    assert abs(agent._h.cfg.huber_delta - 0.5) < 1e-7
+    agent.close()
+    with pytest.raises(ValueError):
+        her.Agent(her.AgentConfig(policy_config=deepq.PolicyConfig(optimizer=object())), 2, 2, 2)
+
+
+@pytest.mark.gpu
+def test_batched_acting_syncs_the_target_when_a_multiple_is_stepped_over():
+    """Agent.updateTarget (agent.go:181-190) with action_batch: 64 environments and a period of 100 used to sync
+    only every 1600 steps; a multiple stepped over between two Learns now triggers the sync."""
+    hp = deepq.Hyperparameters(update_target_steps=100)
+    agent = deepq.Agent(deepq.AgentConfig(hyperparameters=hp, policy_config=deepq.PolicyConfig(batch_size=8), seed=2), deepq.ShapesEnv(4, 2))
+    rng = np.random.Generator(np.random.PCG64(0))
+    for _ in range(16):
+        agent.remember(deepq.new_event(rng.uniform(-1, 1, 4).astype(np.float32), 0,
+                                   deepq.Outcome(rng.uniform(-1, 1, 4).astype(np.float32), 0, 1.0, False)))
+    states = rng.uniform(-1, 1, (64, 4)).astype(np.float32)
+    synced = []
+    for it in range(4):                           # steps: 64, 128, 192, 256 -> multiples 100 and 200 are stepped over
+        agent.action_batch(states)
+        before = agent.target_policy.learnables().copy()
+        agent.learn()
+        synced.append(not np.array_equal(before, agent.target_policy.learnables()))
+    assert synced == [False, True, False, True]
+    agent.close()
+
+
+@pytest.mark.gpu
+def test_resize_batch_keeps_parameters_and_learns_at_the_new_size():
+    """Sequential.ResizeBatch (goro model.go:485-497) on the narrow and the wide path: same parameters, solver
+    state and replay; the next step runs at the new batch size and matches the oracle."""
+    from gold_b200 import _capi as G, synth
+    from util import OracleAgent
+    for dims, B0, B1, kw, tol in ((synth.CARTPOLE, 20, 64, {}, 1e-5), ((64, 256, 128, 6), 256, 512, dict(precision=G.PREC_BF16), 2e-2)):
+        N = 1024
+        th, tt = synth.glorot_params(dims, 1), synth.glorot_params(dims, 2)
+        h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3], batch_size=B0, replay_capacity=N, **kw)
+        h.set_params(G.NET_ONLINE, th); h.set_params(G.NET_TARGET, tt)
+        data = synth.replay(dims, N)
+        h.replay_push(*data)
+        o = OracleAgent(dims, B0, th, tt)
+        o.push(*data)
+        idx = synth.sample_indices(N, B0, 0)
+        h.learn(idx); o.learn(idx, with64=False)
+        w_before = h.get_params(G.NET_ONLINE)
+        h.resize_batch(B1)
+        assert h.B == B1 and h.replay_len() == N
+        np.testing.assert_array_equal(h.get_params(G.NET_ONLINE), w_before)
+        o.B = B1
+        o.theta[:] = w_before                      # (the bf16 path's parameters differ from the fp32 oracle's by its tolerance)
+        m, v, it = h.get_adam_state(); o.m[:] = m; o.v[:] = v; o.iter = it
+        idx = synth.sample_indices(N, B1, 1)
+        out, _ = o.learn(idx, with64=False)
+        h.learn(idx)
+        loss = float(h.last_loss()[0])
+        assert abs(loss - out["loss"]) <= tol * abs(out["loss"]), (dims, loss, out["loss"])
+        with pytest.raises((G.GoldqError, AssertionError)):
+            h.learn(synth.sample_indices(N, B0, 2))        # the old batch size is now a shape error for the index list
+        h.close()
