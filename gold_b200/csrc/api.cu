@@ -200,6 +200,7 @@ AdamConsts adam_consts(const goldq_config_t &c, int64_t iter)
     double correction1 = 1.0 - pow(c.beta1, (double)iter);
     double correction2 = 1.0 - pow(c.beta2, (double)iter);
     AdamConsts a;
+    a.kind = c.solver;
     a.beta1 = (float)c.beta1;
     a.beta2 = (float)c.beta2;
     a.omb1 = 1.0f - (float)c.beta1;
@@ -208,6 +209,12 @@ AdamConsts adam_consts(const goldq_config_t &c, int64_t iter)
     a.neg_eta = (float)(-c.lr);
     a.c1 = 1.0f / (float)correction1;
     a.c2 = 1.0f / (float)correction2;
+    if (c.solver == GOLDQ_SOLVER_RMSPROP) {
+        // float32(s.decay), float32(1.0 - s.decay), float32(s.eps), float32(-s.eta)  (solvers.go:286-293);
+        // the cache lives in `v` (goldq_get/set_adam_state: m unused, v = cache); no bias corrections
+        a.omb2 = (float)(1.0 - c.beta2);
+        a.c1 = a.c2 = 1.0f;
+    }
     return a;
 }
 
@@ -226,13 +233,7 @@ StepScalars step_scalars(const goldq_t *h, int rows_global)
 // generic path: one solver step on the flat gradient (h->iter already counts this step)
 void generic_solver_step(goldq_t *h, const StepDev *step)
 {
-    if (h->cfg.solver == GOLDQ_SOLVER_RMSPROP) {
-        // float32(s.decay), float32(1.0 - s.decay), float32(s.eps), float32(-s.eta)  (solvers.go:286-293);
-        // the cache lives in `v` (goldq_get/set_adam_state: m unused, v = cache)
-        launch_rmsprop(h->theta, h->flat, h->v, h->P, (float)h->cfg.beta2, (float)(1.0 - h->cfg.beta2), (float)h->cfg.eps,
-                       (float)(-h->cfg.lr), h->st);
-        return;
-    }
+    // (Adam or RMSProp: solver_update in common.cuh switches on AdamConsts::kind)
     launch_adam(h->theta, h->flat, h->m, h->v, h->P, adam_consts(h->cfg, h->iter), step, h->st);
 }
 
@@ -809,8 +810,7 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
     // path selection
     int path = cfg->path;
     if (path == GOLDQ_PATH_AUTO) {
-        if (cfg->solver == GOLDQ_SOLVER_RMSPROP) path = GOLDQ_PATH_GENERIC;      // the fused kernels carry Adam
-        else if (cfg->precision == GOLDQ_PREC_BF16) path = GOLDQ_PATH_WIDE;
+        if (cfg->precision == GOLDQ_PREC_BF16) path = GOLDQ_PATH_WIDE;
         else if (narrow_supported(h->dims)) path = GOLDQ_PATH_NARROW;
         else path = GOLDQ_PATH_GENERIC;
     }
@@ -822,8 +822,6 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
         return bail("wide (tcgen05) path requires GOLDQ_PREC_BF16");
     if (path == GOLDQ_PATH_GENERIC && cfg->precision != GOLDQ_PREC_FP32)
         return bail("generic path computes in fp32");
-    if (cfg->solver == GOLDQ_SOLVER_RMSPROP && path != GOLDQ_PATH_GENERIC)
-        return bail("RMSPropSolver is implemented on the generic path only (fp32)");
     if (h->R > 1 && path != GOLDQ_PATH_NARROW)
         return bail("n_replicas > 1 is implemented on the narrow path only");
     h->path = path;
@@ -1404,6 +1402,15 @@ static int predict_dev(goldq_t *h, int net, int replica, int64_t n, const float 
     if (rc) return rc;
     CK(h, cudaMemcpyAsync(h->px, x, (size_t)n * h->dims.D * 4, cudaMemcpyHostToDevice, h->st));
     const float *theta = (net == GOLDQ_NET_ONLINE ? h->theta : h->theta_t) + (size_t)replica * h->P;
+    // bf16 handles: batches of 128 rows and more (vectorised environments, PredictBatch) go through the fused
+    // tcgen05 forward and the bf16 weight shadows the learn step trains with, so acting and learning see the
+    // same arithmetic; a single state (Agent.Action) keeps the fp32 reference-arithmetic kernels
+    if (h->wide && n >= 128) {
+        std::string err;
+        int k = wide_predict(h->wide, net, h->px, n, h->theta, h->theta_t, h->pq, h->st, err);
+        if (k < 0) return fail(h, GOLDQ_ECUDA, err);
+        if (k > 0) { h->launches += k; return check_launch(h, "predict (tcgen05)"); }
+    }
     generic_forward(h, theta, h->px, (int)n, h->ph1, nullptr, h->ph2, nullptr, h->pq);
     return check_launch(h, "predict");
 }

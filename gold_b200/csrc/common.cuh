@@ -49,7 +49,35 @@ struct Replay {
 // in float64, then cast.
 struct AdamConsts {
     float beta1, beta2, omb1, omb2, eps, neg_eta, c1, c2;
+    int kind;       // GOLDQ_SOLVER_ADAM / GOLDQ_SOLVER_RMSPROP (then beta2 = decay, omb2 = float32(1 - decay); cache in v)
 };
+
+// One element of Solver.Step, op for op, one rounding per op and no FMA (shared by the fused narrow kernel, the
+// wide update kernels and the generic path).
+//   Adam     vendor/gorgonia.org/gorgonia/solvers.go:551-615, including v0.9.9's double weight update
+//   RMSProp  solvers.go:273-335: Square(g); cw *= decay; g2 *= (1 - decay); cw += g2; upd = cw + eps;
+//            InvSqrt(upd) = 1/sqrt (tensor generic_unary.go:492-496); g *= -eta; upd *= g; w += upd
+__device__ __forceinline__ void solver_update(float &w, float g, float &m, float &v, const AdamConsts &c)
+{
+    if (c.kind == GOLDQ_SOLVER_RMSPROP) {
+        const float cw = __fadd_rn(__fmul_rn(v, c.beta2), __fmul_rn(__fmul_rn(g, g), c.omb2));
+        v = cw;
+        const float inv = __fdiv_rn(1.f, __fsqrt_rn(__fadd_rn(cw, c.eps)));
+        w = __fadd_rn(w, __fmul_rn(inv, __fmul_rn(g, c.neg_eta)));
+        return;
+    }
+    const float t1 = __fmul_rn(g, c.omb1);
+    const float g2 = __fmul_rn(__fmul_rn(g, g), c.omb2);
+    m = __fadd_rn(t1, __fmul_rn(c.beta1, m));
+    v = __fadd_rn(g2, __fmul_rn(c.beta2, v));
+    const float mh = __fmul_rn(m, c.c1);
+    const float vh = __fmul_rn(v, c.c2);
+    const float den = __fadd_rn(__fsqrt_rn(vh), c.eps);
+    const float u = __fmul_rn(mh, c.neg_eta);
+    if (den == 0.f) w = __int_as_float(0x7f800000);     // vecf32 DivIncr stores +Inf (incr.go:36-38)
+    else w = __fadd_rn(w, __fdiv_rn(u, den));
+    w = __fadd_rn(w, u);
+}
 
 // Per-step scalars that live in DEVICE memory when a step is replayed from a CUDA graph
 // (goldq_learn_many): the kernel arguments of a captured step are frozen, so the sampler
@@ -117,8 +145,6 @@ void launch_reduce_slices(const float *gslice, int64_t slice_stride, int nsplit,
 // Fused Adam incl. the reference's double update; replicas laid out [R][P].
 void launch_adam(float *w, const float *g, float *m, float *v, int64_t n, AdamConsts c,
                  const StepDev *step, cudaStream_t st);
-void launch_rmsprop(float *w, const float *g, float *cache, int64_t n, float decay, float omdecay, float eps,
-                    float neg_eta, cudaStream_t st);
 void launch_argmax_rows(const float *q, int n, int A, int32_t *out, cudaStream_t st);
 void launch_eps_greedy_rows(const float *q, int n, int A, float epsilon, uint64_t seed, int32_t *out, cudaStream_t st);
 

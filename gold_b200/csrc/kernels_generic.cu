@@ -442,22 +442,6 @@ void launch_reduce_slices(const float *gslice, int64_t slice_stride, int nsplit,
 // u = -eta*mhat.  Every operation is a separately rounded fp32 op, as in the
 // reference's whole-tensor passes.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void adam_update(float &w, float g, float &m, float &v,
-                                            const AdamConsts &c)
-{
-    float t1 = __fmul_rn(g, c.omb1);
-    float g2 = __fmul_rn(__fmul_rn(g, g), c.omb2);
-    m = __fadd_rn(t1, __fmul_rn(c.beta1, m));
-    v = __fadd_rn(g2, __fmul_rn(c.beta2, v));
-    float mh = __fmul_rn(m, c.c1);
-    float vh = __fmul_rn(v, c.c2);
-    float den = __fadd_rn(__fsqrt_rn(vh), c.eps);
-    float u = __fmul_rn(mh, c.neg_eta);
-    if (den == 0.f) w = __int_as_float(0x7f800000);  // vecf32/incr.go:36-38
-    else w = __fadd_rn(w, __fdiv_rn(u, den));
-    w = __fadd_rn(w, u);
-}
-
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restrict__ m,
             float *__restrict__ v, int64_t n, AdamConsts c, const StepDev *__restrict__ step)
@@ -466,7 +450,7 @@ adam_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restric
     if (i >= n) return;
     if (step) { c.c1 = step->c1; c.c2 = step->c2; }
     float wi = w[i], mi = m[i], vi = v[i];
-    adam_update(wi, g[i], mi, vi, c);
+    solver_update(wi, g[i], mi, vi, c);
     w[i] = wi;
     m[i] = mi;
     v[i] = vi;
@@ -476,28 +460,6 @@ void launch_adam(float *w, const float *g, float *m, float *v, int64_t n, AdamCo
                  const StepDev *step, cudaStream_t st)
 {
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, m, v, n, c, step);
-}
-
-// RMSPropSolver.Step, float32 branch, op for op (V/gorgonia.org/gorgonia/solvers.go:273-335): Square(g); cw *= decay;
-// g2 *= omdecay; cw += g2; upd = cw + eps; InvSqrt(upd) = 1/sqrt (tensor generic_unary.go:492-496); g *= -eta;
-// upd *= g; w += upd.  One rounding per op, no FMA.
-__global__ void __launch_bounds__(256)
-rmsprop_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restrict__ cache, int64_t n, float decay,
-               float omdecay, float eps, float neg_eta)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float gi = g[i];
-    const float c = __fadd_rn(__fmul_rn(cache[i], decay), __fmul_rn(__fmul_rn(gi, gi), omdecay));
-    cache[i] = c;
-    const float inv = __fdiv_rn(1.f, __fsqrt_rn(__fadd_rn(c, eps)));
-    w[i] = __fadd_rn(w[i], __fmul_rn(inv, __fmul_rn(gi, neg_eta)));
-}
-
-void launch_rmsprop(float *w, const float *g, float *cache, int64_t n, float decay, float omdecay, float eps,
-                    float neg_eta, cudaStream_t st)
-{
-    rmsprop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, cache, n, decay, omdecay, eps, neg_eta);
 }
 
 __global__ void argmax_rows_kernel(const float *__restrict__ q, int n, int A,

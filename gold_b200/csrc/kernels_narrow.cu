@@ -27,23 +27,6 @@ namespace gq {
 
 namespace {
 
-__device__ __forceinline__ void adam_update_n(float &w, float g, float &m, float &v,
-                                              const AdamConsts &c)
-{
-    // reference: vendor/gorgonia.org/gorgonia/solvers.go:551-615 (see kernels_generic.cu K5)
-    float t1 = __fmul_rn(g, c.omb1);
-    float g2 = __fmul_rn(__fmul_rn(g, g), c.omb2);
-    m = __fadd_rn(t1, __fmul_rn(c.beta1, m));
-    v = __fadd_rn(g2, __fmul_rn(c.beta2, v));
-    float mh = __fmul_rn(m, c.c1);
-    float vh = __fmul_rn(v, c.c2);
-    float den = __fadd_rn(__fsqrt_rn(vh), c.eps);
-    float u = __fmul_rn(mh, c.neg_eta);
-    if (den == 0.f) w = __int_as_float(0x7f800000);
-    else w = __fadd_rn(w, __fdiv_rn(u, den));
-    w = __fadd_rn(w, u);
-}
-
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NR = 2;          // rows in flight per warp
 constexpr int MIN_WARPS = 4;   // the tail keeps ELEMS sums per thread in registers
@@ -382,7 +365,7 @@ narrow_learn_kernel(NarrowArgs p)
             flat[i] = g;
             if (p.fuse_adam) {
                 float w = sOn[i], m = sM[i], v = sV[i];
-                adam_update_n(w, g, m, v, p.adam);
+                solver_update(w, g, m, v, p.adam);
                 p.theta[pofs + i] = w;
                 p.m[pofs + i] = m;
                 p.v[pofs + i] = v;

@@ -321,7 +321,9 @@ struct FFArgs {
     int B, D, A;
     const float *bias[2][3];     // [net][layer]
     float *q[2];                 // [net]: Q / Q' fp32 [B][A]
-    __nv_bfloat16 *h1, *h2;      // online network's activations [B][512] (pair kernel: stored from registers)
+    __nv_bfloat16 *h1, *h2;      // (unused)
+    int net0;                    // network of blockIdx.y == 0 (predict launches one network: grid.y = 1)
+    int keep_h;                  // store the online network's H1 / H2 for the backward pass (learn step) or not (predict)
     long long *stamps;           // diagnostic (GOLDQ_FF_STAMPS): [CTAs][FF_NSTAMPS] clock64 values, else nullptr
 };
 
@@ -351,7 +353,7 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int net = blockIdx.y;
+    const int net = blockIdx.y + g.net0;
     const int m0 = blockIdx.x * BM;
     const CUtensorMap *tmX = net ? &tmX1 : &tmX0;
     const CUtensorMap *tmW1 = net ? &tmW1_1 : &tmW1_0;
@@ -544,7 +546,7 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         fence_proxy_async_smem();      // H1 complete: visible to the async proxy (layer-2 MMA, TMA store)
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
-            if (net == 0) {            // the backward pass needs the online network's activations
+            if (net == 0 && g.keep_h) {            // the backward pass needs the online network's activations
                 for (int b = 0; b < KH; b++) tma_store_2d(&tmH1, sH + b * FF_BOX, 64 * b, m0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -595,7 +597,7 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
-            if (net == 0) {
+            if (net == 0 && g.keep_h) {
                 for (int b = 0; b < KH; b++) tma_store_2d(&tmH2, sH + b * FF_BOX, 64 * b, m0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -695,7 +697,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     __shared__ __align__(16) float s_bias[2 * FF_H + 32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int net = blockIdx.y;
+    const int net = blockIdx.y + g.net0;
     const int m0 = blockIdx.x * BM;
     const uint32_t rank = cluster_ctarank();            // 0 = leader
     long long *const stp = g.stamps ? g.stamps + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * FF_NSTAMPS : nullptr;
@@ -890,7 +892,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
             fence_proxy_async_smem();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et == 0) {
-                if (half == 1 && net == 0) {   // the backward pass needs the online network's activations
+                if (half == 1 && net == 0 && g.keep_h) {   // the backward pass needs the online network's activations
                     const CUtensorMap *tmH = layer == 0 ? &tmH1 : &tmH2;
 #pragma unroll 1
                     for (int b = 0; b < KH; b++) tma_store_2d(tmH, sH + b * FF_BOX, 64 * b, m0);
@@ -1530,22 +1532,6 @@ struct PartialSrc {
     const float *row_part;  int nrow;   // [nrow][A+1]: db3, loss
 };
 
-__device__ __forceinline__ void adam_update_w(float &w, float g, float &m, float &v, const AdamConsts &c)
-{
-    // vendor/gorgonia.org/gorgonia/solvers.go:551-615, incl. the double weight update
-    float t1 = __fmul_rn(g, c.omb1);
-    float g2 = __fmul_rn(__fmul_rn(g, g), c.omb2);
-    m = __fadd_rn(t1, __fmul_rn(c.beta1, m));
-    v = __fadd_rn(g2, __fmul_rn(c.beta2, v));
-    float mh = __fmul_rn(m, c.c1);
-    float vh = __fmul_rn(v, c.c2);
-    float den = __fadd_rn(__fsqrt_rn(vh), c.eps);
-    float u = __fmul_rn(mh, c.neg_eta);
-    if (den == 0.f) w = __int_as_float(0x7f800000);
-    else w = __fadd_rn(w, __fdiv_rn(u, den));
-    w = __fadd_rn(w, u);
-}
-
 // Work decomposition of the update kernel (one launch, three block ranges):
 //   A  thread per float4 group of W1 / W2 / W3: few partials (split-K slices), batches of 8
 //      independent 16-byte loads;
@@ -1706,10 +1692,10 @@ __device__ __forceinline__ void finish4(const Dims &d, const Offsets &o, int i, 
 {
     if (flat) *reinterpret_cast<float4 *>(flat + i) = g;
     if (!FUSE) return;
-    adam_update_w(w4.x, g.x, m4.x, v4.x, ac);
-    adam_update_w(w4.y, g.y, m4.y, v4.y, ac);
-    adam_update_w(w4.z, g.z, m4.z, v4.z, ac);
-    adam_update_w(w4.w, g.w, m4.w, v4.w, ac);
+    solver_update(w4.x, g.x, m4.x, v4.x, ac);
+    solver_update(w4.y, g.y, m4.y, v4.y, ac);
+    solver_update(w4.z, g.z, m4.z, v4.z, ac);
+    solver_update(w4.w, g.w, m4.w, v4.w, ac);
     *reinterpret_cast<float4 *>(theta + i) = w4;
     *reinterpret_cast<float4 *>(m + i) = m4;
     *reinterpret_cast<float4 *>(v + i) = v4;
@@ -1848,7 +1834,7 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
             flat[i] = g;
             if (FUSE && i < o.P && ok) {
                 float wi = theta[i], mi = m[i], vi = v[i];
-                adam_update_w(wi, g, mi, vi, ac);
+                solver_update(wi, g, mi, vi, ac);
                 theta[i] = wi;
                 m[i] = mi;
                 v[i] = vi;
@@ -1892,6 +1878,8 @@ struct WideState {
         CUtensorMap tm_x_a, tm_x2_a, tm_x_mm;
     } bs[2];
     int last_set = 0;
+    BatchSet pred;                         // predict: bf16 states [B][D] (tm_x_a, tm_x2_a both describe it)
+    float *pred_q = nullptr;               // predict: Q [B][A]
     __nv_bfloat16 *h1 = nullptr, *h2 = nullptr, *t1 = nullptr, *t2 = nullptr;
     __nv_bfloat16 *dz2 = nullptr, *dz1 = nullptr, *dqT = nullptr;
     float *q = nullptr, *qt = nullptr, *td = nullptr, *dqv = nullptr;
@@ -1956,6 +1944,8 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     for (int k = 0; k < 2; k++)
         ok = ok && dmalloc(&w->bs[k].x, n * d.D, err) && dmalloc(&w->bs[k].x2, n * d.D, err) && dmalloc(&w->bs[k].br, n, err) &&
              dmalloc(&w->bs[k].ba, n, err) && dmalloc(&w->bs[k].bdone, n, err);
+    ok = ok && dmalloc(&w->pred.x, n * d.D, err) && dmalloc(&w->pred_q, n * d.A, err);
+    if (ok) cudaMemset(w->pred.x, 0, n * d.D * 2);
     ok = ok && dmalloc(&w->h1, n * d.H1, err) &&
          dmalloc(&w->h2, n * d.H2, err) && dmalloc(&w->t1, n * d.H1, err) && dmalloc(&w->t2, n * d.H2, err) &&
          dmalloc(&w->dz2, n * d.H2, err) && dmalloc(&w->dz1, n * d.H1, err) && dmalloc(&w->dqT, n * 32, err) &&
@@ -2028,6 +2018,7 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
         ok = ok && make_tmap(&w->bs[k].tm_x_a, w->bs[k].x, B, d.D, d.D, BM, err) &&
              make_tmap(&w->bs[k].tm_x2_a, w->bs[k].x2, B, d.D, d.D, BM, err) &&
              make_tmap(&w->bs[k].tm_x_mm, w->bs[k].x, B, d.D, d.D, 64, err);
+    ok = ok && make_tmap(&w->pred.tm_x_a, w->pred.x, B, d.D, d.D, BM, err) && make_tmap(&w->pred.tm_x2_a, w->pred.x, B, d.D, d.D, BM, err);
     ok = ok && make_tmap(&w->tm_h1_a, w->h1, B, d.H1, d.H1, BM, err) && make_tmap(&w->tm_t1_a, w->t1, B, d.H1, d.H1, BM, err) &&
          make_tmap(&w->tm_h2_a, w->h2, B, d.H2, d.H2, BM, err) && make_tmap(&w->tm_t2_a, w->t2, B, d.H2, d.H2, BM, err) &&
          make_tmap(&w->tm_dz2_a, w->dz2, B, d.H2, d.H2, BM, err) && make_tmap(&w->tm_dz1_a, w->dz1, B, d.H1, d.H1, BM, err);
@@ -2061,7 +2052,7 @@ void wide_destroy(WideState *w)
         for (void *q : p)
             if (q) cudaFree(q);
     }
-    void *p[] = {w->ff_stamps, w->h1, w->h2, w->t1, w->t2, w->dz2, w->dz1, w->dqT, w->q, w->qt, w->td, w->dqv, w->w1_slices, w->w2_slices, w->w3_slices, w->b1_part, w->b2_part, w->row_part};
+    void *p[] = {w->pred.x, w->pred_q, w->ff_stamps, w->h1, w->h2, w->t1, w->t2, w->dz2, w->dz1, w->dqT, w->q, w->qt, w->td, w->dqv, w->w1_slices, w->w2_slices, w->w3_slices, w->b1_part, w->b2_part, w->row_part};
     for (void *q : p)
         if (q) cudaFree(q);
     if (w->s1) cudaStreamDestroy(w->s1);
@@ -2114,7 +2105,7 @@ wide_apply_kernel(Dims d, Offsets o, const float *__restrict__ flat, float *__re
     } else {
         for (int e = i; e < i + 4 && e < o.P; e++) {
             float wi = theta[e], mi = m[e], vi = v[e];
-            adam_update_w(wi, flat[e], mi, vi, ac);
+            solver_update(wi, flat[e], mi, vi, ac);
             theta[e] = wi; m[e] = mi; v[e] = vi;
             shadow_store(d, o, sp, e, wi);
         }
@@ -2194,8 +2185,10 @@ static cudaError_t launch_pair_gemm(const CUtensorMap &ta, const CUtensorMap &tb
 
 // the fused forward of both networks on batch set `bt` (pair kernel when the slab count is even)
 static cudaError_t launch_fused_forward(WideState *w, WideState::BatchSet &bt, const float *theta, const float *theta_t,
-                                        cudaStream_t st, bool pdl)
+                                        cudaStream_t st, bool pdl, int only_net = -1, float *q_out = nullptr)
 {
+    // only_net < 0: the learn step's launch (both networks, online activations kept); else one network of a
+    // predict launch (bt.tm_x_a = the states, Q -> q_out)
     const Dims &d = w->d;
     const Offsets &o = w->o;
     const int B = w->B;
@@ -2205,9 +2198,11 @@ static cudaError_t launch_fused_forward(WideState *w, WideState::BatchSet &bt, c
     fa.bias[0][0] = theta + o.b1; fa.bias[0][1] = theta + o.b2; fa.bias[0][2] = theta + o.b3;
     fa.bias[1][0] = theta_t + o.b1; fa.bias[1][1] = theta_t + o.b2; fa.bias[1][2] = theta_t + o.b3;
     fa.q[0] = w->q; fa.q[1] = w->qt;
-    fa.stamps = w->ff_stamps;
-    fa.h1 = w->h1; fa.h2 = w->h2;
-    dim3 grid((B + BM - 1) / BM, 2);
+    fa.stamps = only_net < 0 ? w->ff_stamps : nullptr;
+    fa.net0 = only_net < 0 ? 0 : only_net;
+    fa.keep_h = only_net < 0 ? 1 : 0;
+    if (only_net >= 0) fa.q[only_net] = q_out;
+    dim3 grid((B + BM - 1) / BM, only_net < 0 ? 2 : 1);
     if (w->ff2 && d.D == 128)
         return launch_k(ff_forward2_kernel<2>, grid, dim3(FF_THREADS), ff2_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a, w->tm_h2_a, fa);
@@ -2219,6 +2214,38 @@ static cudaError_t launch_fused_forward(WideState *w, WideState::BatchSet &bt, c
                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a, w->tm_h2_a, fa);
     return launch_k(ff_forward_kernel<1>, grid, dim3(FF_THREADS), ff_smem_bytes<1>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
                     on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a, w->tm_h2_a, fa);
+}
+
+__global__ void __launch_bounds__(256)
+wide_cast_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, long long n4)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<uint2 *>(out)[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+}
+
+// Sequential.PredictBatch / batched acting on the tensor cores: Q = net(x) for n rows of fp32 states in device
+// memory, through the SAME fused bf16 forward kernel (and bf16 weight shadows) the learn step trains with, in
+// chunks of the handle's batch size.  Returns launches, or -1 (err set), or 0 when the fused forward does not
+// exist for this shape (the caller then uses the generic fp32 kernels).
+int wide_predict(WideState *w, int net, const float *x, long long n, const float *theta, const float *theta_t, float *q,
+                 cudaStream_t st, std::string &err)
+{
+    if (!w->ff) return 0;
+    const Dims &d = w->d;
+    int launches = 0;
+    for (long long r0 = 0; r0 < n; r0 += w->B) {
+        const long long rows = (n - r0 < w->B) ? n - r0 : w->B;
+        const long long n4 = rows * d.D / 4;
+        wide_cast_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x + r0 * d.D, w->pred.x, n4);
+        WCK(cudaGetLastError());
+        WCK(launch_fused_forward(w, w->pred, theta, theta_t, st, false, net, w->pred_q));
+        WCK(cudaMemcpyAsync(q + r0 * d.A, w->pred_q, (size_t)rows * d.A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        launches += 2;
+    }
+    return launches;
 }
 
 // Diagnostic (bench.py roofline): average duration of the fused forward over `reps` back-to-back launches on

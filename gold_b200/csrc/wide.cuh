@@ -67,6 +67,8 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
                       const StepDev *step, cudaStream_t st, std::string &err);
 int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err);
 
+int wide_predict(WideState *w, int net, const float *x, long long n, const float *theta, const float *theta_t, float *q,
+                 cudaStream_t st, std::string &err);
 int wide_time_forward(WideState *w, const float *theta, const float *theta_t, cudaStream_t st, int reps, float *us,
                       std::string &err);
 int wide_p2p_chunk_floats(const WideState *w, int world);

@@ -117,19 +117,22 @@ def test_pseudo_huber_loss(path, dims, B, delta):
     h.close()
 
 
-@pytest.mark.parametrize("dims,B", [(synth.CARTPOLE, 20), ((5, 17, 33, 3), 37)])
-def test_rmsprop_solver_generic_path(dims, B):
-    """gorgonia.RMSPropSolver (solvers.go:249-335) on the generic path; PATH_AUTO must route there."""
+@pytest.mark.parametrize("dims,B,path", [(synth.CARTPOLE, 20, G.PATH_NARROW), (synth.CARTPOLE, 20, G.PATH_GENERIC),
+                                         ((5, 17, 33, 3), 37, G.PATH_GENERIC), (synth.CARTPOLE, 4096, G.PATH_NARROW)])
+def test_rmsprop_solver(dims, B, path):
+    """gorgonia.RMSPropSolver (solvers.go:249-335), the solver of gold's Atari config (policy.go:41-47): in the
+    fused narrow kernel's tail and on the generic path (PATH_AUTO picks the fused kernel where it exists)."""
     N = 4 * B
-    h, o = make_pair(dims, B, N, solver=G.SOLVER_RMSPROP, lr=1e-3, beta2=0.999, eps=1e-8)
-    assert h.path == G.PATH_GENERIC
+    h, o = make_pair(dims, B, N, path=path, solver=G.SOLVER_RMSPROP, lr=1e-3, beta2=0.999, eps=1e-8)
+    assert h.path == path
     for step in range(3):
         out = check_step(h, o, synth.sample_indices(N, B, step), f"rmsprop step{step}")
     m, cache, _ = h.get_adam_state()
     assert not m.any() and cache.any()
     h.close()
-    with pytest.raises(G.GoldqError):          # the fused kernels carry Adam: asking for them with RMSProp is an error
-        G.Handle(batch_size=B, replay_capacity=N, path=G.PATH_NARROW, solver=G.SOLVER_RMSPROP)
+    h = G.Handle(batch_size=20, replay_capacity=64, solver=G.SOLVER_RMSPROP)
+    assert h.path == G.PATH_NARROW             # no longer routed to the unfused path
+    h.close()
 
 
 def test_free_running_without_resync():

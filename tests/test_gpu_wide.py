@@ -19,9 +19,10 @@ from util import OracleAgent
 pytestmark = pytest.mark.gpu
 
 
-def make(dims, B, N, huber_delta=None):
+def make(dims, B, N, huber_delta=None, **extra):
     th = synth.glorot_params(dims, 1); tt = synth.glorot_params(dims, 2)
     kw = {} if huber_delta is None else dict(loss=G.LOSS_PSEUDO_HUBER, huber_delta=huber_delta)
+    kw.update(extra)
     h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3], batch_size=B,
                  replay_capacity=N, precision=G.PREC_BF16, **kw)
     assert h.path == G.PATH_WIDE
@@ -93,6 +94,29 @@ def test_wide_bf16_pseudo_huber():
     h, o = make(dims, B, N, huber_delta=0.5)
     for step in range(2):
         check(h, o, synth.sample_indices(N, B, step))
+    h.close()
+
+
+@pytest.mark.parametrize("dims,B", [(synth.WIDE, 512), ((64, 256, 128, 6), 200)])
+def test_wide_rmsprop_in_the_fused_update_kernel(dims, B):
+    """RMSPropSolver inside wide_update_kernel (gold's Atari solver, policy.go:43): the fused kernel applied to the
+    GPU's own gradient must reproduce solvers.go:273-335 op for op (numpy float32 replay, one rounding per op),
+    the cache lives in `v`, `m` stays zero, and the bf16 shadows follow (the next step's Q moves)."""
+    N = 2 * B
+    lr, decay, eps = 1e-3, 0.999, 1e-8
+    h, o = make(dims, B, N, solver=G.SOLVER_RMSPROP, lr=lr, beta2=decay, eps=eps)
+    w = o.theta.copy(); cache = np.zeros_like(w)
+    f = np.float32
+    for step in range(3):
+        h.learn(synth.sample_indices(N, B, step))
+        g = h.debug_fetch(G.DBG_GRADS)
+        cache = (cache * f(decay) + (g * g) * f(1.0 - decay)).astype(np.float32)
+        inv = (f(1) / np.sqrt(cache + f(eps))).astype(np.float32)
+        w = (w + inv * (g * f(-lr))).astype(np.float32)
+        np.testing.assert_allclose(h.get_params(G.NET_ONLINE), w, rtol=1e-6, atol=1e-8)
+        m, v, it = h.get_adam_state()
+        assert it == step + 1 and not m.any()
+        np.testing.assert_allclose(v, cache, rtol=1e-6, atol=1e-12)
     h.close()
 
 
@@ -171,16 +195,41 @@ def test_wide_matches_bf16_emulation(dims, B):
     h.close()
 
 
-def test_wide_greedy_actions_match_outside_ties():
+def test_wide_predict_and_acting_run_on_the_tensor_cores():
+    """goldq_predict / greedy / epsilon-greedy on a bf16 handle: 128 rows and more go through the fused tcgen05
+    forward on the bf16 weight shadows (the arithmetic the learn step trains with): Q within the stated 1e-2 of the
+    fp64 oracle, greedy actions equal wherever the oracle's top-2 gap exceeds that tolerance; fewer rows (one
+    Agent.Action state) keep the fp32 reference-arithmetic kernels and are bit-exact."""
     from oracle import binding as O
     dims = synth.WIDE
     h, o = make(dims, 256, 1024)
-    x = synth.replay(dims, 512, seed=3)[0]
+    x = synth.replay(dims, 700, seed=3)[0]                      # 700 rows: three chunks of the batch size, the last ragged
     q64 = O.predict64(dims, o.theta.astype(np.float64), x.astype(np.float64))
-    a_gpu = h.greedy_action(x)            # predict runs the fp32 reference-arithmetic kernels
-    q32, a_ref = O.predict(dims, o.theta, x)
-    np.testing.assert_array_equal(a_gpu, a_ref)
-    h.close()
+    l0 = h.launch_count()
+    q = h.predict(G.NET_ONLINE, x)
+    assert h.launch_count() - l0 == 6                           # (cast + fused forward) x 3 chunks, not 3 fp32 layers
+    tol = 1e-2 * np.abs(q64).max()
+    assert np.abs(q - q64).max() <= tol
+    qt64 = O.predict64(dims, o.theta_t.astype(np.float64), x.astype(np.float64))
+    assert np.abs(h.predict(G.NET_TARGET, x) - qt64).max() <= 1e-2 * np.abs(qt64).max()
+    a_gpu = h.greedy_action(x)
+    top2 = np.sort(q64, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 2 * tol
+    assert clear.mean() > 0.5
+    np.testing.assert_array_equal(a_gpu[clear], q64.argmax(axis=1)[clear])
+    np.testing.assert_array_equal(h.epsilon_greedy_action(x, 0.0, 5)[clear], a_gpu[clear])
+    # a handful of states: fp32 kernels, bit-exact against the oracle's reference arithmetic
+    q32, a_ref = O.predict(dims, o.theta, x[:64])
+    np.testing.assert_array_equal(h.predict(G.NET_ONLINE, x[:64]), q32)
+    np.testing.assert_array_equal(h.greedy_action(x[:64]), a_ref)
+    # the learn step is not disturbed by predicts in between
+    idx = synth.sample_indices(1024, 256, 0)
+    h.learn(idx); h.predict(G.NET_ONLINE, x); h.learn(synth.sample_indices(1024, 256, 1))
+    w_a = h.get_params(G.NET_ONLINE)
+    h2, _ = make(dims, 256, 1024)
+    h2.learn(idx); h2.learn(synth.sample_indices(1024, 256, 1))
+    np.testing.assert_array_equal(w_a, h2.get_params(G.NET_ONLINE))
+    h.close(); h2.close()
 
 
 def test_wide_free_running_loss_tracks_oracle():
