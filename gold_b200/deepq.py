@@ -384,14 +384,17 @@ class Agent:
         self.steps = 0
         self._rng = random.Random(seed)
         self._learn_calls = 0
-        self._sync_mark = 0            # steps // update_target_steps at the last updateTarget check
+        self._stepped_over = False     # action_batch advanced `steps` past a multiple of update_target_steps
 
     def action_batch(self, states):
         """Agent.Action (agent.go:193-221) for a batch of states from vectorised environments: one
         steps++ / epsilon track per state, exploration decided per row on the device (uniform random
         action where the reference asks env.SampleAction), greedy = first-argmax of the online Q."""
         states = np.ascontiguousarray(states, np.float32).reshape(-1, self._h.D)
+        before = self.steps
         self.steps += len(states)
+        if before // self.update_target_steps != self.steps // self.update_target_steps:
+            self._stepped_over = True   # the reference's steps++ would have landed on the multiple (see _update_target)
         return self._h.epsilon_greedy_action(states, float(self.epsilon), self._rng.getrandbits(63))
 
     def learn(self, indices=None):
@@ -410,13 +413,13 @@ class Agent:
         return None
 
     def _update_target(self):
-        """agent.go:181-190: sync when steps lands on a multiple of UpdateTargetSteps.  action_batch advances
-        steps by a whole batch of states, so a multiple that was stepped OVER since the last check counts too
-        (with one Action per Learn this is exactly the reference's `steps % N == 0`)."""
-        mark = self.steps // self.update_target_steps
-        if self.steps % self.update_target_steps == 0 or mark != self._sync_mark:   # agent.go:182
+        """agent.go:181-190: sync when steps sits on a multiple of UpdateTargetSteps at Learn time.  action_batch
+        advances steps by a whole batch of states, so a multiple it stepped OVER counts too -- with 64 environments
+        and a period of 100 the exact multiple is hit only every 1600 steps.  With one Action per Learn this is
+        exactly the reference's `steps % N == 0`."""
+        if self.steps % self.update_target_steps == 0 or self._stepped_over:   # agent.go:182
             self.policy.clone_learnables_to(self.target_policy)
-        self._sync_mark = mark
+        self._stepped_over = False
 
     def action(self, state):
         """Agent.Action (agent.go:193-205): epsilon-greedy; steps is counted here."""
