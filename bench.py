@@ -550,6 +550,19 @@ def run_own(args):
                                                                           "d2h_bytes_per_step": d2hx},
                            "config": workload_config(args, x.dims, x.B, x.replicas, x.prec, name=name), "roofline": rf}
             x.close()
+    elif world > 1 and args.workload == "wide" and not args.no_extra:
+        # configs[4]: independent CartPole replicas sharded over the GPUs, 128 per GPU (1024 on 8 B200), no
+        # collective on the data path: every rank trains its own replicas, the timing is the max over ranks
+        x = Workload(G, args, "replicas", rank, world, local_rank, dist, torch)
+        Kx = max(K, 200)
+        v, msx, lx = x.resident(Kx, max(W, 3))
+        x.close()
+        if rank == 0:
+            extra = {"replicas": {"baseline_config": f"configs[4]: {128 * world} independent replicas over {world} GPUs (128 per GPU)",
+                                  "value": v, "unit": "transitions/s", "us_per_step": msx / Kx * 1e3, "steps": Kx,
+                                  "gpu_launches": int(lx), "n_gpus": world, "replicas_total": 128 * world,
+                                  "scaling": "weak", "collective": None,
+                                  "config": workload_config(args, x.dims, x.B, x.replicas, x.prec, name="replicas")}}
 
     if rank == 0:
         line = {
