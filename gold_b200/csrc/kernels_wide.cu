@@ -1308,7 +1308,9 @@ cudaError_t launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, GemmArgs g
 // CUDA-core helpers of the wide path
 // ---------------------------------------------------------------------------
 // K1: sample (optional) + gather + fp32 -> bf16.  The replay stays fp32 in HBM; index
-// generation and the cast are fused into the gather.  One thread per 16-byte granule.
+// generation and the cast are fused into the gather.  One thread per 16-byte granule.  (Four rows per thread,
+// eight loads in flight each, measured SLOWER -- 19 vs 13 us: random 512-byte rows want more threads in
+// flight, not fewer.)
 __global__ void __launch_bounds__(256)
 wide_gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx, uint64_t seed,
                    const StepDev *__restrict__ step, int32_t *__restrict__ idx_out, int B, __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ x2, int32_t *__restrict__ ba,
@@ -1372,13 +1374,19 @@ wide_shadow_kernel(const float *__restrict__ theta, Dims d, Offsets o, ShadowPtr
     // the padding of W3 stays zero from allocation time (cudaMemset in wide_create)
 }
 
-// K3 + layer-3 backward, one kernel.  Block = DZ_ROWS rows.
-//   warp 0, lane = row: first-max over Q'(s') (ArgmaxF32 rules), TD target (agent.go:149),
-//     d = q[a] - t, dqv = (2 d) / count; dQ^T [32][B] bf16 (one non-zero per column b) is the
-//     K-major B operand of the dW3 GEMM; db3 / loss partials of the block in a fixed order.
-//   all warps: dZ2[b][j] = dqv[b] * W3[j][a_b] * mask2[b][j] (bf16 out, operand of dW2 / dX)
-//     and the db2 partial.  Thread (x, y): 8 columns (16-byte vectors), rows y, y+4, ...
+// K3 + layer-3 backward, one kernel.  Block = DZ_ROWS = 32 rows = 8 warps x 4 rows; everything about a row
+// happens inside ONE warp, so the only block-level synchronisation is the final sum of the eight warps' partials
+// (round 1's version computed the TD rows in warp 0 while the other seven waited at a barrier: ncu showed it
+// stalled on that barrier, 6.1 per issue).
+//   lanes 0..3 of a warp, one row each: first-max over Q'(s') (ArgmaxF32 rules), TD target (agent.go:149),
+//     d = q[a] - t, dqv = (2 d) / count, loss term; broadcast by shuffle
+//   all lanes: dQ^T [32][B] bf16 (one non-zero per column b; the K-major B operand of the dW3 GEMM), lane = action
+//     row, four consecutive b per 8-byte store
+//   all lanes: dZ2[b][j] = dqv[b] * W3[j][a_b] * mask2[b][j] (bf16 out, operand of dW2 / dX): lane l takes the
+//     16-byte column chunks l, l + 32, ...; every load of the warp's four rows is issued before the first use
+//   partials per block in a fixed order: db2 (column sums of the ROUNDED dZ2), db3 by action, loss
 constexpr int DZ_ROWS = 32;
+constexpr int DZ_MAXCH = 2;      // 16-byte chunks per lane and row: H2 <= 32 * 8 * DZ_MAXCH = 512 (more: chunk loop)
 __global__ void __launch_bounds__(256)
 wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, const int32_t *__restrict__ act,
                    const float *__restrict__ rew, const uint8_t *__restrict__ done, int B, int H2, int A, StepScalars sc,
@@ -1386,96 +1394,132 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
                    float *__restrict__ td_out, __nv_bfloat16 *__restrict__ dqT, __nv_bfloat16 *__restrict__ dz2,
                    float *__restrict__ b2_part /* [blocks][H2] */, float *__restrict__ row_part /* [blocks][A+1] */)
 {
-    extern __shared__ float sm[];            // [4][H2] column-sum staging
-    __shared__ float sDq[DZ_ROWS];
-    __shared__ int sAct[DZ_ROWS];
-    const int x = threadIdx.x & 63, y = threadIdx.x >> 6;
-    const int r0 = blockIdx.x * DZ_ROWS;
+    extern __shared__ float sm[];            // [8 warps][H2] column sums, then [8][33] row partials
+    float *sRow = sm + 8 * H2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rw0 = blockIdx.x * DZ_ROWS + warp * 4;      // this warp's four rows
     pdl_launch_dependents();
     pdl_wait();
-    if (threadIdx.x < DZ_ROWS) {
-        const int lane = threadIdx.x;
-        const int b = r0 + lane;
-        float dqv = 0.f, sq = 0.f;
-        int a = -1;
-        if (b < B) {
-            // all loads of the row first (A <= 32), then the scan
-            const float *row = qt + (int64_t)b * A;
-            float rv[32];
+    // ---- TD label of row rw0 + lane (lanes 0..3) ------------------------------------------------------
+    float dqv = 0.f, sq = 0.f;
+    int a = 0;
+    if (lane < 4 && rw0 + lane < B) {
+        const int b = rw0 + lane;
+        const float *row = qt + (int64_t)b * A;
+        float rv[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) rv[i] = (i < A) ? __ldg(row + i) : 0.f;
-            a = act[b];
-            const float rwd = rew[b];
-            const int dn = done[b];
-            const float qa = __ldg(q + (int64_t)b * A + a);
-            float t = rwd;
-            if (!dn) {
-                float f = rv[0];
-                bool decided = false;
+        for (int i = 0; i < 32; i++) rv[i] = (i < A) ? __ldg(row + i) : 0.f;
+        a = act[b];
+        const float rwd = rew[b];
+        const int dn = done[b];
+        const float qa = __ldg(q + (int64_t)b * A + a);
+        float t = rwd;
+        if (!dn) {
+            float f = rv[0];
+            bool decided = false;
 #pragma unroll
-                for (int i = 1; i < 32; i++) {
-                    if (i < A && !decided) {
-                        const float v = rv[i];
-                        if (isnan(v) || (isinf(v) && v > 0.f)) { f = v; decided = true; }
-                        else if (v > f) f = v;
-                    }
+            for (int i = 1; i < 32; i++) {
+                if (i < A && !decided) {
+                    const float v = rv[i];
+                    if (isnan(v) || (isinf(v) && v > 0.f)) { f = v; decided = true; }
+                    else if (v > f) f = v;
                 }
-                t = __fadd_rn(rwd, __fmul_rn(sc.gamma, f));
             }
-            td_out[b] = t;
-            const float dd = __fsub_rn(qa, t);
-            residual_loss(sc, dd, sq, dqv);
-            const __nv_bfloat16 v = __float2bfloat16_rn(dqv), z = __float2bfloat16_rn(0.f);
-            for (int i = 0; i < 32; i++) dqT[(int64_t)i * B + b] = (i == a) ? v : z;
+            t = __fadd_rn(rwd, __fmul_rn(sc.gamma, f));
         }
-        sDq[lane] = dqv;
-        sAct[lane] = a < 0 ? 0 : a;
-        // db3[i] = sum of dqv over the block's rows with act == i; slot A = loss partial
-        for (int i = 0; i <= A; i++) {
-            float v = (i == A) ? sq : ((a == i) ? dqv : 0.f);
+        td_out[b] = t;
+        residual_loss(sc, __fsub_rn(qa, t), sq, dqv);
+    }
+    float dq4[4];
+    int a4[4];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) row_part[(int64_t)blockIdx.x * (A + 1) + i] = v;
+    for (int k = 0; k < 4; k++) {
+        dq4[k] = __shfl_sync(0xffffffffu, dqv, k);
+        a4[k] = __shfl_sync(0xffffffffu, a, k);
+    }
+    // ---- dQ^T: lane = action row i, columns rw0 .. rw0 + 3 in one 8-byte store (B % 8 == 0, rw0 % 4 == 0) ----
+    {
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(a4[0] == lane ? dq4[0] : 0.f, a4[1] == lane ? dq4[1] : 0.f);
+        const __nv_bfloat162 p1 = __floats2bfloat162_rn(a4[2] == lane ? dq4[2] : 0.f, a4[3] == lane ? dq4[3] : 0.f);
+        if (rw0 + 3 < B)
+            *reinterpret_cast<uint2 *>(dqT + (int64_t)lane * B + rw0) =
+                make_uint2(*reinterpret_cast<const uint32_t *>(&p0), *reinterpret_cast<const uint32_t *>(&p1));
+        else {
+            const float v[4] = {a4[0] == lane ? dq4[0] : 0.f, a4[1] == lane ? dq4[1] : 0.f, a4[2] == lane ? dq4[2] : 0.f,
+                                a4[3] == lane ? dq4[3] : 0.f};
+            for (int k = 0; k < 4; k++)
+                if (rw0 + k < B) dqT[(int64_t)lane * B + rw0 + k] = __float2bfloat16_rn(v[k]);
+        }
+    }
+    // ---- row partials of this warp: db3[i] (lane i), loss (lane A) --------------------------------------
+    {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float sqk = __shfl_sync(0xffffffffu, sq, k);
+            if (lane < A) v += (a4[k] == lane && rw0 + k < B) ? dq4[k] : 0.f;
+            else if (lane == A) v += sqk;
+        }
+        sRow[warp * 33 + lane] = v;
+    }
+    // ---- dZ2 of the four rows + column sums ----------------------------------------------------------------
+    const int nch = H2 >> 3;
+    for (int c0 = 0; c0 < nch; c0 += 32 * DZ_MAXCH) {
+        uint4 hv[4][DZ_MAXCH], wv[4][DZ_MAXCH];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int u = 0; u < DZ_MAXCH; u++) {
+                const int c = c0 + lane + 32 * u;
+                const bool live = c < nch && rw0 + k < B;
+                hv[k][u] = live ? __ldg(reinterpret_cast<const uint4 *>(h2 + (int64_t)(rw0 + k) * H2) + c) : make_uint4(0, 0, 0, 0);
+                wv[k][u] = live ? __ldg(reinterpret_cast<const uint4 *>(w3t + (int64_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+        for (int u = 0; u < DZ_MAXCH; u++) {
+            const int c = c0 + lane + 32 * u;
+            float cs[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) cs[e] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t hw[4] = {hv[k][u].x, hv[k][u].y, hv[k][u].z, hv[k][u].w};
+                const uint32_t ww[4] = {wv[k][u].x, wv[k][u].y, wv[k][u].z, wv[k][u].w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float w0 = __uint_as_float(ww[e] << 16), w1 = __uint_as_float(ww[e] & 0xffff0000u);
+                    const float z0 = (hw[e] & 0x8000u) ? 0.f : dq4[k] * w0;
+                    const float z1 = (hw[e] & 0x80000000u) ? 0.f : dq4[k] * w1;
+                    __nv_bfloat162 pk = __floats2bfloat162_rn(z0, z1);
+                    ow[e] = *reinterpret_cast<uint32_t *>(&pk);
+                    // sum the ROUNDED values so that db2 matches the bf16 operand of dW2 / dX
+                    cs[2 * e] += __uint_as_float(ow[e] << 16);
+                    cs[2 * e + 1] += __uint_as_float(ow[e] & 0xffff0000u);
+                }
+                if (c < nch && rw0 + k < B) reinterpret_cast<uint4 *>(dz2 + (int64_t)(rw0 + k) * H2)[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+            if (c < nch) {
+                float4 *dst = reinterpret_cast<float4 *>(sm + warp * H2 + c * 8);
+                dst[0] = make_float4(cs[0], cs[1], cs[2], cs[3]);
+                dst[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
+            }
         }
     }
     __syncthreads();
-    for (int c = x; c < (H2 >> 3); c += 64) {
-        float cs[8];
+    // ---- block partials, warps summed in order ------------------------------------------------------------------
+    for (int j = threadIdx.x; j < H2; j += blockDim.x) {
+        float v = sm[j];
 #pragma unroll
-        for (int e = 0; e < 8; e++) cs[e] = 0.f;
-        uint4 hv[DZ_ROWS / 4], wv[DZ_ROWS / 4];
-#pragma unroll
-        for (int u = 0; u < DZ_ROWS / 4; u++) {
-            const int rr = y + 4 * u, b = r0 + rr;
-            hv[u] = b < B ? __ldg(reinterpret_cast<const uint4 *>(h2 + (int64_t)b * H2) + c) : make_uint4(0, 0, 0, 0);
-            wv[u] = __ldg(reinterpret_cast<const uint4 *>(w3t + (int64_t)sAct[rr] * H2) + c);
-        }
-#pragma unroll
-        for (int u = 0; u < DZ_ROWS / 4; u++) {
-            const int rr = y + 4 * u, b = r0 + rr;
-            const float dq = sDq[rr];
-            const uint32_t hw[4] = {hv[u].x, hv[u].y, hv[u].z, hv[u].w};
-            const uint32_t ww[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
-            uint32_t ow[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const float w0 = __uint_as_float(ww[e] << 16), w1 = __uint_as_float(ww[e] & 0xffff0000u);
-                const float z0 = (hw[e] & 0x8000u) ? 0.f : dq * w0;
-                const float z1 = (hw[e] & 0x80000000u) ? 0.f : dq * w1;
-                __nv_bfloat162 pk = __floats2bfloat162_rn(z0, z1);
-                ow[e] = *reinterpret_cast<uint32_t *>(&pk);
-                // sum the ROUNDED values so that db2 matches the bf16 operand of dW2 / dX
-                cs[2 * e] += __uint_as_float(ow[e] << 16);
-                cs[2 * e + 1] += __uint_as_float(ow[e] & 0xffff0000u);
-            }
-            if (b < B) reinterpret_cast<uint4 *>(dz2 + (int64_t)b * H2)[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        }
-#pragma unroll
-        for (int e = 0; e < 8; e++) sm[y * H2 + c * 8 + e] = cs[e];
+        for (int w = 1; w < 8; w++) v += sm[w * H2 + j];
+        b2_part[(int64_t)blockIdx.x * H2 + j] = v;
     }
-    __syncthreads();
-    for (int j = threadIdx.x; j < H2; j += blockDim.x)
-        b2_part[(int64_t)blockIdx.x * H2 + j] = ((sm[j] + sm[H2 + j]) + sm[2 * H2 + j]) + sm[3 * H2 + j];
+    if (threadIdx.x <= A) {
+        float v = sRow[threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < 8; w++) v += sRow[w * 33 + threadIdx.x];
+        row_part[(int64_t)blockIdx.x * (A + 1) + threadIdx.x] = v;
+    }
 }
 
 // db1 partials: column sums of dZ1 (bf16 [B][H1]) over CS_ROWS-row ranges.  A warp covers
@@ -1961,10 +2005,11 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     w->nb1 = (B + CS_ROWS - 1) / CS_ROWS;
     const bool no_pair = getenv("GOLDQ_NO_PAIR_GEMM") != nullptr;
     // dX on CTA pairs: 256 x 256 tiles need whole 256-row / 256-column tiles; it writes one db1 partial per 128-row slab
-    w->pair_dx = !no_pair && B % 256 == 0 && d.H1 % 256 == 0 && d.H2 % 64 == 0;
+    w->pair_dx = !no_pair && getenv("GOLDQ_NO_PAIR_DX") == nullptr && B % 256 == 0 && d.H1 % 256 == 0 && d.H2 % 64 == 0;
     if (w->pair_dx) w->nb1 = B / BM;
     // dW2 on CTA pairs: (H1/256) x (H2/256) pair tiles, split-K so that about one CTA lands on every SM
-    w->pair_dw2 = !no_pair && d.H1 % 256 == 0 && d.H2 % 256 == 0 && B % 64 == 0;
+    // (opt-in: measured no faster inside the step -- 64.3 vs 63.4 us -- and its 16 split-K slices are 16 MB against 10 MB)
+    w->pair_dw2 = !no_pair && getenv("GOLDQ_PAIR_DW2") != nullptr && d.H1 % 256 == 0 && d.H2 % 256 == 0 && B % 64 == 0;
     if (w->pair_dw2) {
         // never more CTAs than SMs (one CTA per SM: a few CTAs left for a second wave would double the time)
         const int tiles = (d.H1 / BM) * (d.H2 / 256), kblocks = B / BK;
@@ -2350,7 +2395,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     }
 
     if (!(w->skip & 4))
-    WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), sizeof(float) * 4 * d.H2, st, pdl, w->q, w->qt, bt.ba, bt.br,
+    WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), sizeof(float) * (8 * d.H2 + 8 * 33), st, pdl, w->q, w->qt, bt.ba, bt.br,
                  bt.bdone, B, d.H2, d.A, s.sc, w->h2, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part));
     mark("TD + dZ2 + db2/db3 (K3)");
     launches += 1;

@@ -15,7 +15,7 @@ for f in sys.argv[1:]:
           ('step frac %.3f' % r['step']['frac_of_sustained_peak']) if 'step' in r else '')
     print('  kernels:', r['kernels_us'])
     for k, v in (j.get('configs') or {}).items():
-        print('  ', k, '%.1fM' % (v['value'] / 1e6), '%.2f us/step' % v['us_per_step'], 'e2e %.1fM' % (v['e2e']['value'] / 1e6),
-              'floor', v['roofline'].get('launch_floor_us'))
+        print('  ', k, '%.1fM' % (v['value'] / 1e6), '%.2f us/step' % v['us_per_step'], ('e2e %.1fM' % (v['e2e']['value'] / 1e6)) if 'e2e' in v else '',
+              'floor', v.get('roofline', {}).get('launch_floor_us'))
     if j.get('cpu_baseline'):
         print('  cpu:', j['cpu_baseline']['value'], j['cpu_baseline']['cores'])
