@@ -16,9 +16,10 @@ NET_ONLINE, NET_TARGET = 0, 1
 LOSS_MSE, LOSS_PSEUDO_HUBER = 0, 1
 SOLVER_ADAM, SOLVER_RMSPROP = 0, 1
 PREC_FP32, PREC_BF16 = 0, 1
-PATH_AUTO, PATH_GENERIC, PATH_NARROW, PATH_WIDE = 0, 1, 2, 3
+PATH_AUTO, PATH_GENERIC, PATH_NARROW, PATH_WIDE, PATH_CONV = 0, 1, 2, 3, 4
+ARCH_MLP, ARCH_ATARI_CONV = 0, 1
 DBG_Q_ONLINE, DBG_Q_TARGET, DBG_TD, DBG_GRADS, DBG_INDICES, DBG_BATCH_S, DBG_BATCH_A, DBG_FF_STAMPS = range(8)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/goldq.h declares (tests/test_abi.py checks header <-> list <-> .so)
 SYMBOLS = [
@@ -44,6 +45,7 @@ class GoldqConfig(C.Structure):
         ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
         ("loss", C.c_int32), ("precision", C.c_int32), ("path", C.c_int32), ("device", C.c_int32),
         ("n_replicas", C.c_int32), ("solver", C.c_int32), ("stream", C.c_void_p),
+        ("arch", C.c_int32), ("in_channels", C.c_int32), ("in_height", C.c_int32), ("in_width", C.c_int32),
     ]
 
 

@@ -114,6 +114,13 @@ struct goldq {
     int32_t *pact = nullptr;
     // wide (tcgen05) path
     WideState *wide = nullptr;
+    // Atari conv policy (GOLDQ_PATH_CONV): activations [rows][O][OH][OW] of the online (y*, masks mk*) and the target
+    // (u*) network, FC-512 activations, and the gradients flowing back through the stack
+    AtariNet atari{};
+    int conv_rows = 0;
+    float *cy1 = nullptr, *cy2 = nullptr, *cy3 = nullptr, *ch4 = nullptr, *cu1 = nullptr, *cu2 = nullptr, *cu3 = nullptr, *cu4 = nullptr;
+    uint8_t *cm1 = nullptr, *cm2 = nullptr, *cm3 = nullptr, *cm4 = nullptr;
+    float *cdy1 = nullptr, *cdy2 = nullptr, *cdy3 = nullptr, *cdh4 = nullptr;
 
     bool debug = false;
     float *dbg_q = nullptr, *dbg_qt = nullptr, *dbg_td = nullptr;
@@ -450,6 +457,83 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
     return check_launch(h, "learn_wide");
 }
 
+// ---- Atari conv policy (fp32, kernels_conv.cu) ------------------------------------------------------------------
+int ensure_conv(goldq_t *h, int rows)
+{
+    if (h->conv_rows >= rows) return GOLDQ_OK;
+    const AtariNet &t = h->atari;
+    void *old[] = {h->cy1, h->cy2, h->cy3, h->ch4, h->cu1, h->cu2, h->cu3, h->cu4, h->cm1, h->cm2, h->cm3, h->cm4, h->cdy1, h->cdy2,
+                   h->cdy3, h->cdh4, h->bs, h->bs2, h->br, h->ba, h->bdone, h->q, h->qt, h->td, h->dq, h->gslice, h->loss_part};
+    for (void *p : old)
+        if (p) cudaFree(p);
+    const size_t n = rows, s1 = (size_t)32 * t.c1.OH * t.c1.OW, s2 = (size_t)64 * t.c2.OH * t.c2.OW, s3 = t.F;
+    CK(h, dalloc(&h->cy1, n * s1)); CK(h, dalloc(&h->cu1, n * s1)); CK(h, dalloc(&h->cm1, n * s1)); CK(h, dalloc(&h->cdy1, n * s1));
+    CK(h, dalloc(&h->cy2, n * s2)); CK(h, dalloc(&h->cu2, n * s2)); CK(h, dalloc(&h->cm2, n * s2)); CK(h, dalloc(&h->cdy2, n * s2));
+    CK(h, dalloc(&h->cy3, n * s3)); CK(h, dalloc(&h->cu3, n * s3)); CK(h, dalloc(&h->cm3, n * s3)); CK(h, dalloc(&h->cdy3, n * s3));
+    CK(h, dalloc(&h->ch4, n * t.HID)); CK(h, dalloc(&h->cu4, n * t.HID)); CK(h, dalloc(&h->cm4, n * t.HID)); CK(h, dalloc(&h->cdh4, n * t.HID));
+    CK(h, dalloc(&h->bs, n * h->dims.D)); CK(h, dalloc(&h->bs2, n * h->dims.D));
+    CK(h, dalloc(&h->br, n)); CK(h, dalloc(&h->ba, n)); CK(h, dalloc(&h->bdone, n));
+    CK(h, dalloc(&h->q, n * t.A)); CK(h, dalloc(&h->qt, n * t.A)); CK(h, dalloc(&h->td, n)); CK(h, dalloc(&h->dq, n * t.A));
+    h->nsplit = rows / 512;
+    if (h->nsplit < 1) h->nsplit = 1;
+    if (h->nsplit > 4) h->nsplit = 4;          // P is ~3.3 M floats for 84 x 84 inputs: keep the slice buffer small
+    CK(h, dalloc(&h->gslice, (size_t)h->nsplit * h->P));
+    CK(h, dalloc(&h->loss_part, (size_t)(rows * t.A + 255) / 256 + 1));
+    h->conv_rows = rows;
+    return GOLDQ_OK;
+}
+
+// forward of the conv policy over n states; masks are kept for the online pass of a learn step only
+void conv_forward(goldq_t *h, const float *theta, const float *x, int n, float *y1, uint8_t *m1, float *y2, uint8_t *m2,
+                  float *y3, uint8_t *m3, float *h4, uint8_t *m4, float *q)
+{
+    const AtariNet &t = h->atari;
+    launch_conv_forward(t.c1, n, x, theta + t.f1, y1, m1, h->st);
+    launch_conv_forward(t.c2, n, y1, theta + t.f2, y2, m2, h->st);
+    launch_conv_forward(t.c3, n, y2, theta + t.f3, y3, m3, h->st);
+    // Flatten is a reshape of the NCHW tensor (goro layer/flatten.go:44-61): y3 as stored
+    launch_fc_forward(y3, theta + t.w4, theta + t.b4, h4, m4, n, t.F, t.HID, true, h->st);
+    launch_fc_forward(h4, theta + t.w5, theta + t.b5, q, nullptr, n, t.HID, t.A, false, h->st);
+    h->launches += 5;
+}
+
+int learn_conv(goldq_t *h, const int32_t *idx_dev, const StepDev *step)
+{
+    int rc = ensure_conv(h, h->B);
+    if (rc) return rc;
+    const AtariNet &t = h->atari;
+    const int B = h->B;
+    launch_gather(h->rp, h->dims.D, idx_dev, B, h->bs, h->bs2, h->ba, h->br, h->bdone, step, h->st);
+    h->launches += 1;
+    conv_forward(h, h->theta, h->bs, B, h->cy1, h->cm1, h->cy2, h->cm2, h->cy3, h->cm3, h->ch4, h->cm4, h->q);
+    conv_forward(h, h->theta_t, h->bs2, B, h->cu1, nullptr, h->cu2, nullptr, h->cu3, nullptr, h->cu4, nullptr, h->qt);
+    int nlp = 0;
+    StepScalars sc = step_scalars(h, h->Bglobal);
+    launch_td(h->q, h->qt, h->ba, h->br, h->bdone, B, t.A, sc, h->td, h->dq, h->loss_part, &nlp, h->st);
+    const float *th = h->theta;
+    const int ns = h->nsplit;
+    // FC A, FC 512 (the generic dense kernels), then the three convolutions; every conv kernel applies its own
+    // layer's Rectify mask to the gradient it receives
+    launch_grad_w(h->ch4, h->dq, B, t.HID, t.A, h->gslice, h->P, ns, (int)t.w5, (int)t.b5, h->st);
+    launch_grad_x(h->dq, th + t.w5, h->cm4, h->cdh4, B, t.HID, t.A, h->st);
+    launch_grad_w(h->cy3, h->cdh4, B, t.F, t.HID, h->gslice, h->P, ns, (int)t.w4, (int)t.b4, h->st);
+    launch_grad_x(h->cdh4, th + t.w4, h->cm3, h->cdy3, B, t.F, t.HID, h->st);
+    launch_conv_backward_filter(t.c3, B, ns, h->cy2, h->cdy3, h->cm3, h->gslice, h->P, t.f3, h->st);
+    launch_conv_backward_data(t.c3, B, h->cdy3, h->cm3, th + t.f3, h->cdy2, h->st);
+    launch_conv_backward_filter(t.c2, B, ns, h->cy1, h->cdy2, h->cm2, h->gslice, h->P, t.f2, h->st);
+    launch_conv_backward_data(t.c2, B, h->cdy2, h->cm2, th + t.f2, h->cdy1, h->st);
+    launch_conv_backward_filter(t.c1, B, ns, h->bs, h->cdy1, h->cm1, h->gslice, h->P, t.f1, h->st);
+    launch_reduce_slices(h->gslice, h->P, ns, h->P, h->loss_part, nlp, sc.count, h->flat, h->st);
+    h->launches += 11;
+    rc = allreduce_flat(h);
+    if (rc) return rc;
+    h->iter += 1;
+    generic_solver_step(h, step);
+    h->launches += 1;
+    CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+    return check_launch(h, "learn_conv");
+}
+
 int run_learn(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev *step = nullptr)
 {
     if (h->rp.len < h->B) return fail(h, GOLDQ_ENOTREADY, "replay shorter than batch");
@@ -463,6 +547,7 @@ int run_learn(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev *
         h->launches += 1;
         idx_dev = h->d_idx;
     }
+    if (h->path == GOLDQ_PATH_CONV) return learn_conv(h, idx_dev, step);
     return learn_generic(h, idx_dev, step);
 }
 
@@ -526,8 +611,8 @@ int launch_graph(goldq_t *h, int slot, uint64_t seed)
     if (h->p2p.on && *(volatile int *)h->p2p.err_host)
         return fail(h, GOLDQ_ENCCL, "data-parallel peer did not publish its gradient within 5 s");
     if (h->graph_debug != h->debug) { drop_graphs(h); h->graph_debug = h->debug; }
-    if (h->path == GOLDQ_PATH_GENERIC) {          // no allocation may happen under capture
-        int rc = ensure_generic(h, h->B);
+    if (h->path == GOLDQ_PATH_GENERIC || h->path == GOLDQ_PATH_CONV) {          // no allocation may happen under capture
+        int rc = h->path == GOLDQ_PATH_CONV ? ensure_conv(h, h->B) : ensure_generic(h, h->B);
         if (rc) return rc;
     }
     if (!h->graph_exec[slot]) {
@@ -757,6 +842,8 @@ int goldq_default_config(goldq_config_t *c)
     c->device = 0;
     c->n_replicas = 1;
     c->stream = nullptr;
+    c->arch = GOLDQ_ARCH_MLP;
+    c->in_channels = c->in_height = c->in_width = 0;
     return GOLDQ_OK;
 }
 
@@ -781,11 +868,32 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
     }
     if (cfg->replay_capacity > 0x7fffffffLL) { fail(nullptr, GOLDQ_EINVAL, "replay_capacity must fit int32 indices"); return nullptr; }
 
+    const bool conv = cfg->arch == GOLDQ_ARCH_ATARI_CONV;
+    if (cfg->arch != GOLDQ_ARCH_MLP && !conv) { fail(nullptr, GOLDQ_EUNSUPPORTED, "arch: FC-FC-FC and the Atari conv stack are implemented"); return nullptr; }
+    AtariNet atari{};
+    if (conv) {
+        if (cfg->in_channels < 1 || cfg->in_height < 8 || cfg->in_width < 8 ||
+            (int64_t)cfg->in_channels * cfg->in_height * cfg->in_width != cfg->obs_dim) {
+            fail(nullptr, GOLDQ_EINVAL, "conv policy: obs_dim must equal in_channels * in_height * in_width (each dimension >= 8)");
+            return nullptr;
+        }
+        atari = make_atari_net(cfg->in_channels, cfg->in_height, cfg->in_width, cfg->n_actions);
+        if (atari.c3.OH < 1 || atari.c3.OW < 1) { fail(nullptr, GOLDQ_EINVAL, "conv policy: input too small for the 8/4, 4/2, 3/1 stack"); return nullptr; }
+        if (cfg->n_replicas != 1 || cfg->precision != GOLDQ_PREC_FP32 || (cfg->path != GOLDQ_PATH_AUTO && cfg->path != GOLDQ_PATH_CONV)) {
+            fail(nullptr, GOLDQ_EUNSUPPORTED, "conv policy: one replica, GOLDQ_PREC_FP32, GOLDQ_PATH_AUTO or GOLDQ_PATH_CONV");
+            return nullptr;
+        }
+    } else if (cfg->path == GOLDQ_PATH_CONV) {
+        fail(nullptr, GOLDQ_EINVAL, "GOLDQ_PATH_CONV needs arch = GOLDQ_ARCH_ATARI_CONV");
+        return nullptr;
+    }
+
     goldq_t *h = new goldq();
     h->cfg = *cfg;
-    h->dims = Dims{cfg->obs_dim, cfg->hidden1, cfg->hidden2, cfg->n_actions};
+    h->dims = Dims{cfg->obs_dim, conv ? atari.HID : cfg->hidden1, conv ? atari.HID : cfg->hidden2, cfg->n_actions};
     h->off = make_offsets(h->dims);
-    h->P = h->off.P;
+    h->P = conv ? (int)atari.P : h->off.P;
+    h->atari = atari;
     h->R = cfg->n_replicas;
     h->B = cfg->batch_size;
     h->Bglobal = cfg->global_batch > 0 ? cfg->global_batch : cfg->batch_size;
@@ -809,6 +917,7 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
 
     // path selection
     int path = cfg->path;
+    if (conv) path = GOLDQ_PATH_CONV;
     if (path == GOLDQ_PATH_AUTO) {
         if (cfg->precision == GOLDQ_PREC_BF16) path = GOLDQ_PATH_WIDE;
         else if (narrow_supported(h->dims)) path = GOLDQ_PATH_NARROW;
@@ -820,7 +929,7 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
         return bail("narrow path computes in fp32");
     if (path == GOLDQ_PATH_WIDE && cfg->precision != GOLDQ_PREC_BF16)
         return bail("wide (tcgen05) path requires GOLDQ_PREC_BF16");
-    if (path == GOLDQ_PATH_GENERIC && cfg->precision != GOLDQ_PREC_FP32)
+    if ((path == GOLDQ_PATH_GENERIC || path == GOLDQ_PATH_CONV) && cfg->precision != GOLDQ_PREC_FP32)
         return bail("generic path computes in fp32");
     if (h->R > 1 && path != GOLDQ_PATH_NARROW)
         return bail("n_replicas > 1 is implemented on the narrow path only");
@@ -914,7 +1023,8 @@ void goldq_destroy(goldq_t *h)
                     h->rp.a, h->rp.r, h->rp.done, h->stg[0].base, h->stg[1].base, h->partial, h->ticket, h->bs, h->bs2, h->br, h->ba, h->bdone, h->h1,
                     h->h2, h->q, h->t1, h->t2, h->qt, h->td, h->dq, h->dh2, h->dh1, h->ylab, h->mk1,
                     h->mk2, h->gslice, h->loss_part, h->px, h->ph1, h->ph2, h->pq, h->pact,
-                    h->dbg_q, h->dbg_qt, h->dbg_td, h->dbg_idx};
+                    h->dbg_q, h->dbg_qt, h->dbg_td, h->dbg_idx, h->cy1, h->cy2, h->cy3, h->ch4, h->cu1, h->cu2, h->cu3, h->cu4,
+                    h->cm1, h->cm2, h->cm3, h->cm4, h->cdy1, h->cdy2, h->cdy3, h->cdh4};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1199,8 +1309,8 @@ int goldq_learn_prepare(goldq_t *h)
     CK(h, cudaSetDevice(h->dev));
     if (h->rp.len < h->B) return fail(h, GOLDQ_ENOTREADY, "replay shorter than batch");
     if (!use_graphs(h)) return GOLDQ_OK;
-    if (h->path == GOLDQ_PATH_GENERIC) {          // no allocation may happen under capture
-        int rc = ensure_generic(h, h->B);
+    if (h->path == GOLDQ_PATH_GENERIC || h->path == GOLDQ_PATH_CONV) {          // no allocation may happen under capture
+        int rc = h->path == GOLDQ_PATH_CONV ? ensure_conv(h, h->B) : ensure_generic(h, h->B);
         if (rc) return rc;
     }
     if (h->graph_debug != h->debug) { drop_graphs(h); h->graph_debug = h->debug; }
@@ -1231,8 +1341,8 @@ static int learn_many_impl(goldq_t *h, int32_t n, uint64_t seed)
 {
     CK(h, cudaSetDevice(h->dev));
     if (h->rp.len < h->B) return fail(h, GOLDQ_ENOTREADY, "replay shorter than batch");
-    if (h->path == GOLDQ_PATH_GENERIC) {          // no allocation may happen under capture
-        int rc = ensure_generic(h, h->B);
+    if (h->path == GOLDQ_PATH_GENERIC || h->path == GOLDQ_PATH_CONV) {          // no allocation may happen under capture
+        int rc = h->path == GOLDQ_PATH_CONV ? ensure_conv(h, h->B) : ensure_generic(h, h->B);
         if (rc) return rc;
     }
     static const bool no_graph = getenv("GOLDQ_NO_GRAPH") != nullptr;   // diagnostic: eager launches
@@ -1411,6 +1521,12 @@ static int predict_dev(goldq_t *h, int net, int replica, int64_t n, const float 
         if (k < 0) return fail(h, GOLDQ_ECUDA, err);
         if (k > 0) { h->launches += k; return check_launch(h, "predict (tcgen05)"); }
     }
+    if (h->path == GOLDQ_PATH_CONV) {
+        rc = ensure_conv(h, (int)n > h->B ? (int)n : h->B);
+        if (rc) return rc;
+        conv_forward(h, theta, h->px, (int)n, h->cu1, nullptr, h->cu2, nullptr, h->cu3, nullptr, h->cu4, nullptr, h->pq);
+        return check_launch(h, "predict (conv)");
+    }
     generic_forward(h, theta, h->px, (int)n, h->ph1, nullptr, h->ph2, nullptr, h->pq);
     return check_launch(h, "predict");
 }
@@ -1474,6 +1590,7 @@ int goldq_fit_batch(goldq_t *h, int64_t n, const float *x, const float *y)
     if (n != h->B && n != 1)
         return fail(h, GOLDQ_EINVAL, "fit_batch: rows must equal batch_size (FitBatch) or 1 (Fit)");
     if (h->world > 1) return fail(h, GOLDQ_EUNSUPPORTED, "fit_batch is single-GPU");
+    if (h->path == GOLDQ_PATH_CONV) return fail(h, GOLDQ_EUNSUPPORTED, "fit_batch on explicit labels is not implemented for the conv policy (Learn is)");
     CK(h, cudaSetDevice(h->dev));
     int rc = ensure_generic(h, h->B > 1 ? h->B : 1);
     if (rc) return rc;

@@ -148,6 +148,26 @@ void launch_adam(float *w, const float *g, float *m, float *v, int64_t n, AdamCo
 void launch_argmax_rows(const float *q, int n, int A, int32_t *out, cudaStream_t st);
 void launch_eps_greedy_rows(const float *q, int n, int A, float epsilon, uint64_t seed, int32_t *out, cudaStream_t st);
 
+// ---- Atari conv policy, fp32 (kernels_conv.cu) -------------------------------
+struct ConvShape {
+    int C, H, W, O, KH, KW, pad, stride, OH, OW;
+};
+// Learnable order = layer order (goro layer/chain.go:38-44): the three filters (O,I,H,W; no bias), then W, b of FC 512
+// and FC A.
+struct AtariNet {
+    ConvShape c1, c2, c3;
+    int F, HID, A;
+    int64_t f1, f2, f3, w4, b4, w5, b5, P;
+};
+ConvShape make_conv_shape(int C, int H, int W, int O, int KH, int KW, int pad, int stride);
+AtariNet make_atari_net(int C, int H, int W, int A);
+void launch_conv_forward(const ConvShape &c, int n, const float *x, const float *f, float *y, uint8_t *mask, cudaStream_t st);
+// gslice[z][f_off + e] = partial filter gradient of batch slice z (summed later with the other slices, fixed order)
+void launch_conv_backward_filter(const ConvShape &c, int n, int nslice, const float *x, const float *dy, const uint8_t *mask,
+                                 float *gslice, int64_t slice_stride, int64_t f_off, cudaStream_t st);
+void launch_conv_backward_data(const ConvShape &c, int n, const float *dy, const uint8_t *mask, const float *f, float *dx,
+                               cudaStream_t st);
+
 // ---- narrow fused path (kernels_narrow.cu) --------------------------------
 #define NARROW_GROUP 8        // CTAs summed by one level-1 leader
 #define NARROW_MAX_GROUPS 64  // => at most 512 CTAs per replica

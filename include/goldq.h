@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GOLDQ_ABI_VERSION 1
+#define GOLDQ_ABI_VERSION 2
 
 /* error codes */
 #define GOLDQ_OK 0
@@ -49,7 +49,8 @@ extern "C" {
 #define GOLDQ_SOLVER_ADAM 0    /* AdamSolver.Step incl. v0.9.9's double weight update, solvers.go:440-617 */
 #define GOLDQ_SOLVER_RMSPROP 1 /* RMSPropSolver.Step, solvers.go:249-395 (gold's Atari config, policy.go:41-47):
                                 * c = c*rho + (1-rho)*g^2; w += (1/sqrt(c+eps)) * (g * -eta).  Hyper-parameters:
-                                * lr = eta, beta2 = rho, eps; beta1 unused.  Implemented on GOLDQ_PATH_GENERIC. */
+                                * lr = eta, beta2 = rho, eps; beta1 unused.  On every path (fused narrow / wide update
+                                * kernels included). */
 
 /* arithmetic of the forward/backward pass */
 #define GOLDQ_PREC_FP32 0   /* reference arithmetic: fp32, multiply then add, k-sequential */
@@ -60,6 +61,13 @@ extern "C" {
 #define GOLDQ_PATH_GENERIC 1 /* tiled CUDA-core kernels, any shape */
 #define GOLDQ_PATH_NARROW 2  /* one fused warp-per-row kernel, classic-control shapes (H<=32) */
 #define GOLDQ_PATH_WIDE 3    /* tcgen05 GEMM tiles (requires GOLDQ_PREC_BF16) */
+#define GOLDQ_PATH_CONV 4    /* the Atari conv policy (arch = GOLDQ_ARCH_ATARI_CONV), fp32 CUDA-core kernels */
+
+/* network architecture */
+#define GOLDQ_ARCH_MLP 0         /* FC-FC-FC, deepq.DefaultFCLayerBuilder (policy.go:53-59) */
+#define GOLDQ_ARCH_ATARI_CONV 1  /* deepq.DefaultAtariLayerBuilder (policy.go:62-71): Conv2D 32x8x8/4, 64x4x4/2, 64x3x3/1
+                                  * (pad 1, ReLU, no bias), Flatten, FC 512, FC A.  obs_dim = in_channels*in_height*in_width,
+                                  * states are NCHW; hidden1 / hidden2 are ignored */
 
 /* goldq_debug_fetch selectors: state of the LAST learn step (parity tests) */
 #define GOLDQ_DBG_Q_ONLINE 0  /* float[B*A]  online Q(s)            */
@@ -95,6 +103,8 @@ typedef struct goldq_config {
     int32_t n_replicas;       /* >= 1: independent agents (own weights, solver state, replay) in one grid */
     int32_t solver;           /* GOLDQ_SOLVER_* (0 = Adam, as before this field had a meaning) */
     void *stream;             /* cudaStream_t to run on, or NULL to create one */
+    int32_t arch;             /* GOLDQ_ARCH_* (ABI 2) */
+    int32_t in_channels, in_height, in_width;   /* GOLDQ_ARCH_ATARI_CONV: state shape (1, 84, 84 for gold's Atari wrapper) */
 } goldq_config_t;
 
 /* ---- lifetime ---------------------------------------------------------- */

@@ -5,6 +5,7 @@ bench.py's cpu_baseline / --impl reference legs.  The product package
 (gold_b200/) must never import this module.
 """
 import ctypes as C
+C_ = C
 import os
 import subprocess
 
@@ -26,7 +27,7 @@ class OqCfg(C.Structure):
 
 def build(force=False):
     """Compile the oracle in place (gcc; a second or two)."""
-    src = [os.path.join(_HERE, f) for f in ("goldq_oracle.c", "learn_core.inc", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("goldq_oracle.c", "learn_core.inc", "conv_core.inc", "Makefile")]
     if (not force and os.path.exists(_SO)
             and os.path.getmtime(_SO) >= max(os.path.getmtime(s) for s in src)):
         return _SO
@@ -192,3 +193,54 @@ def gather(D, order_s, order_a, order_r, order_s2, order_done, idx):
                         _p(a, C.c_int32), _p(r, C.c_float), _p(s2, C.c_float),
                         _p(done, C.c_uint8))
     return s, a, r, s2, done
+
+
+# ---- the Atari (convolutional) policy (conv_core.inc) ------------------------------------------------------
+def atari_nparams(C, H, W, A):
+    lib().oq_atari_nparams.restype = C_.c_int64
+    return int(lib().oq_atari_nparams(C, H, W, A))
+
+
+def atari_features(C, H, W):
+    return int(lib().oq_atari_features(C, H, W))
+
+
+def atari_predict(shape, A, theta, x, dtype=np.float32):
+    """q [n][A] of the conv policy for n states [n][C][H][W]."""
+    C, H, W = shape
+    ct = C_.c_float if dtype == np.float32 else C_.c_double
+    theta = np.ascontiguousarray(theta, dtype)
+    x = np.ascontiguousarray(x, dtype).reshape(-1, C * H * W)
+    q = np.empty((x.shape[0], A), dtype)
+    fn = lib().oq_atari_predict_f32 if dtype == np.float32 else lib().oq_atari_predict_f64
+    fn(C, H, W, A, _p(theta, ct), x.shape[0], _p(x, ct), _p(q, ct))
+    return q
+
+
+def atari_learn(shape, A, B, theta, theta_t, m, v, it, s, a, r, s2, done, gamma=0.95, lr=5e-4, beta1=0.9, beta2=0.999,
+                eps=1e-8, dtype=np.float32, solver=0):
+    """One Agent.Learn of the conv policy on a sampled batch; theta/m/v updated IN PLACE."""
+    C, H, W = shape
+    f32 = dtype == np.float32
+    ct = C_.c_float if f32 else C_.c_double
+    P = atari_nparams(C, H, W, A)
+    for arr in (theta, m, v):
+        assert arr.dtype == dtype and arr.flags.c_contiguous and arr.size == P
+    theta_t = np.ascontiguousarray(theta_t, dtype)
+    s = np.ascontiguousarray(s, dtype).reshape(B, -1)
+    s2 = np.ascontiguousarray(s2, dtype).reshape(B, -1)
+    r = np.ascontiguousarray(r, dtype).reshape(B)
+    a = np.ascontiguousarray(a, np.int32).reshape(B)
+    done = np.ascontiguousarray(done, np.uint8).reshape(B)
+    cfg = OqCfg(OqDims(C * H * W, 0, 0, A), B, gamma, lr, beta1, beta2, eps, 0, solver, 1.0)
+    out = {"q_online": np.zeros((B, A), dtype), "q_target": np.zeros((B, A), dtype), "td": np.zeros(B, dtype),
+           "loss": np.zeros(1, dtype), "grads": np.zeros(P, dtype)}
+    itc = C_.c_int64(it)
+    fn = lib().oq_atari_learn_f32 if f32 else lib().oq_atari_learn_f64
+    rc = fn(C_.byref(cfg), C, H, W, _p(theta, ct), _p(theta_t, ct), _p(m, ct), _p(v, ct), C_.byref(itc), _p(s, ct),
+            _p(a, C_.c_int32), _p(r, ct), _p(s2, ct), _p(done, C_.c_uint8), _p(out["q_online"], ct), _p(out["q_target"], ct),
+            _p(out["td"], ct), _p(out["loss"], ct), _p(out["grads"], ct))
+    assert rc == 0
+    out["iter"] = itc.value
+    out["loss"] = out["loss"][0]
+    return out

@@ -119,6 +119,7 @@ static void colsum_f64(int n, int c, const double *x, double *out)
 #define FN(name) name##_f32
 #define SQRT(x) sqrtf(x)
 #include "learn_core.inc"
+#include "conv_core.inc"
 #undef REAL
 #undef FN
 #undef SQRT
@@ -127,6 +128,7 @@ static void colsum_f64(int n, int c, const double *x, double *out)
 #define FN(name) name##_f64
 #define SQRT(x) sqrt(x)
 #include "learn_core.inc"
+#include "conv_core.inc"
 #undef REAL
 #undef FN
 #undef SQRT
@@ -244,4 +246,37 @@ void oq_gather_f32(int D, int64_t len, const float *order_s, const int32_t *orde
         r[b] = order_r[src];
         done[b] = order_done[src];
     }
+}
+
+/* ---- the Atari (convolutional) policy: pkg/v1/agent/deepq/policy.go:41-47,62-71 (conv_core.inc) -------------- */
+int64_t oq_atari_nparams(int C, int H, int W, int A) { return atari_make_f32(C, H, W, A).total; }
+int oq_atari_features(int C, int H, int W) { return atari_make_f32(C, H, W, 2).F; }
+
+void oq_atari_predict_f32(int C, int H, int W, int A, const float *theta, int n, const float *x, float *q)
+{
+    atari_t_f32 t = atari_make_f32(C, H, W, A);
+    atari_acts_f32 a = atari_alloc_f32(&t, n);
+    atari_forward_f32(&t, theta, n, x, &a, q);
+    atari_free_f32(&a);
+}
+void oq_atari_predict_f64(int C, int H, int W, int A, const double *theta, int n, const double *x, double *q)
+{
+    atari_t_f64 t = atari_make_f64(C, H, W, A);
+    atari_acts_f64 a = atari_alloc_f64(&t, n);
+    atari_forward_f64(&t, theta, n, x, &a, q);
+    atari_free_f64(&a);
+}
+int oq_atari_learn_f32(const oq_cfg_t *cfg, int C, int H, int W, float *theta, const float *theta_t, float *m, float *v,
+                       int64_t *iter, const float *s, const int32_t *act, const float *rew, const float *s2,
+                       const uint8_t *done, float *q_online, float *q_target, float *td, float *loss, float *grads)
+{
+    *iter += 1;
+    return atari_learn_f32(cfg, C, H, W, theta, theta_t, m, v, *iter, s, act, rew, s2, done, q_online, q_target, td, loss, grads);
+}
+int oq_atari_learn_f64(const oq_cfg_t *cfg, int C, int H, int W, double *theta, const double *theta_t, double *m, double *v,
+                       int64_t *iter, const double *s, const int32_t *act, const double *rew, const double *s2,
+                       const uint8_t *done, double *q_online, double *q_target, double *td, double *loss, double *grads)
+{
+    *iter += 1;
+    return atari_learn_f64(cfg, C, H, W, theta, theta_t, m, v, *iter, s, act, rew, s2, done, q_online, q_target, td, loss, grads);
 }
