@@ -151,7 +151,7 @@ func makePolicies(config *PolicyConfig, hp *Hyperparameters, base *agentv1.Base,
 	if err != nil {
 		return nil, nil, nil, err
 	}
-	cfg, err := models[0].deviceConfig(c)
+	cfg, err := models[0].deviceConfig(c, x.Shape())
 	if err != nil {
 		return nil, nil, nil, err
 	}

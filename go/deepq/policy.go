@@ -44,8 +44,7 @@ var DefaultPolicyConfig = &PolicyConfig{
 }
 
 // DefaultAtariPolicyConfig is the default policy config for atari environments (reference:
-// policy.go:41-47).  Its convolutional LayerBuilder is not implemented on the device path yet:
-// MakePolicy panics with that message, as the reference panics on any build failure.
+// policy.go:41-47).  The device path implements exactly its layer stack (GOLDQ_ARCH_ATARI_CONV, fp32).
 var DefaultAtariPolicyConfig = &PolicyConfig{
 	Loss:         modelv1.MSE,
 	Optimizer:    g.NewRMSPropSolver(g.WithBatchSize(20)),
@@ -225,10 +224,61 @@ func solverConfig(s g.Solver, cfg *goldq.Config) error {
 	return nil
 }
 
+// atariConfig recognises deepq.DefaultAtariLayerBuilder's stack (policy.go:62-71): Conv2D 32x8x8/4, 64x4x4/2,
+// 64x3x3/1 with the layer's defaults (pad 1, ReLU, no bias), Flatten, FC 512 (ReLU), FC A (linear).  in is the
+// input shape with its batch dimension, (1, C, H, W).
+func (s *Sequential) atariConfig(cfg *goldq.Config, in tensor.Shape) error {
+	bad := fmt.Errorf("goldq implements deepq.DefaultAtariLayerBuilder's convolutional stack only")
+	if len(s.layers) != 6 || len(in) < 3 {
+		return bad
+	}
+	want := [3][4]int{{32, 8, 8, 4}, {64, 4, 4, 2}, {64, 3, 3, 1}}
+	for i := 0; i < 3; i++ {
+		c, ok := s.layers[i].(layer.Conv2D)
+		if !ok || c.Output != want[i][0] || c.Height != want[i][1] || c.Width != want[i][2] {
+			return bad
+		}
+		if len(c.Stride) != 2 || c.Stride[0] != want[i][3] || c.Stride[1] != want[i][3] {
+			return bad
+		}
+		if (len(c.Pad) != 0 && (c.Pad[0] != 1 || c.Pad[1] != 1)) || len(c.Dilation) != 0 {
+			return bad
+		}
+		if _, relu := c.Activation.(*layer.ReLUActivation); c.Activation != nil && !relu {
+			return bad
+		}
+	}
+	if _, ok := s.layers[3].(layer.Flatten); !ok {
+		return bad
+	}
+	f1, ok1 := s.layers[4].(layer.FC)
+	f2, ok2 := s.layers[5].(layer.FC)
+	if !ok1 || !ok2 || f1.Output != 512 || f2.Input != 512 || f1.NoBias || f2.NoBias {
+		return bad
+	}
+	if _, lin := f2.Activation.(*layer.LinearActivation); !lin {
+		return bad
+	}
+	n := len(in)
+	cfg.Arch = goldq.ArchAtariConv
+	cfg.InChannels, cfg.InHeight, cfg.InWidth = in[n-3], in[n-2], in[n-1]
+	cfg.ObsDim = cfg.InChannels * cfg.InHeight * cfg.InWidth
+	cfg.Hidden1, cfg.Hidden2, cfg.NActions = 512, 512, f2.Output
+	return nil
+}
+
 // deviceConfig turns layers + options into the handle configuration, rejecting what the device
-// path does not implement.
-func (s *Sequential) deviceConfig(c compiled) (goldq.Config, error) {
+// path does not implement.  in is the model's input shape (used by the convolutional stack only).
+func (s *Sequential) deviceConfig(c compiled, in tensor.Shape) (goldq.Config, error) {
 	cfg := goldq.DefaultConfig()
+	if len(s.layers) > 0 {
+		if _, conv := s.layers[0].(layer.Conv2D); conv {
+			if err := s.atariConfig(&cfg, in); err != nil {
+				return cfg, err
+			}
+			return s.lossAndSolver(c, cfg)
+		}
+	}
 	if len(s.layers) != 3 {
 		return cfg, fmt.Errorf("goldq implements FC-FC-FC policies (DefaultFCLayerBuilder), got %d layers", len(s.layers))
 	}
@@ -259,6 +309,11 @@ func (s *Sequential) deviceConfig(c compiled) (goldq.Config, error) {
 		return cfg, fmt.Errorf("goldq: layer shapes do not chain")
 	}
 	cfg.ObsDim, cfg.Hidden1, cfg.Hidden2, cfg.NActions = fc[0].Input, fc[0].Output, fc[1].Output, fc[2].Output
+	return s.lossAndSolver(c, cfg)
+}
+
+// lossAndSolver fills the batch size, loss and solver fields from the compiled options.
+func (s *Sequential) lossAndSolver(c compiled, cfg goldq.Config) (goldq.Config, error) {
 	cfg.BatchSize = c.batchSize
 	switch l := c.loss.(type) {
 	case nil, *modelv1.MSELoss:
@@ -284,7 +339,7 @@ func (s *Sequential) Compile(x modelv1.InputOr, y *modelv1.Input, opts ...modelv
 	if err != nil {
 		return err
 	}
-	cfg, err := s.deviceConfig(c)
+	cfg, err := s.deviceConfig(c, x.Input().Shape())
 	if err != nil {
 		return err
 	}
@@ -314,9 +369,22 @@ func (s *Sequential) attach(h *goldq.Handle, net int) {
 	s.h, s.net, s.shared, s.cfg = h, net, true, h.Config()
 }
 
-// glorot draws GlorotN(1) weights and biases in learnable order (goro layer/fc.go:76-81).
+// glorot draws the initial parameters in learnable order: FC weights and biases GlorotN(1) (goro layer/fc.go:76-81),
+// convolution filters GlorotU(1) (layer/conv2d.go:104-106).
 func glorot(c goldq.Config) []float32 {
 	var out []float32
+	if c.Arch == goldq.ArchAtariConv {
+		h1, w1 := (c.InHeight+2-8)/4+1, (c.InWidth+2-8)/4+1
+		h2, w2 := (h1+2-4)/2+1, (w1+2-4)/2+1
+		for _, f := range [][4]int{{32, c.InChannels, 8, 8}, {64, 32, 4, 4}, {64, 64, 3, 3}} {
+			out = append(out, g.GlorotU(1)(tensor.Float32, f[0], f[1], f[2], f[3]).([]float32)...)
+		}
+		for _, s := range [][2]int{{64 * h2 * w2, 512}, {512, c.NActions}} {
+			out = append(out, g.GlorotEtAlN32(1, s[0], s[1])...)
+			out = append(out, g.GlorotEtAlN32(1, 1, s[1])...)
+		}
+		return out
+	}
 	for _, s := range [][2]int{{c.ObsDim, c.Hidden1}, {c.Hidden1, c.Hidden2}, {c.Hidden2, c.NActions}} {
 		out = append(out, g.GlorotEtAlN32(1, s[0], s[1])...)
 		out = append(out, g.GlorotEtAlN32(1, 1, s[1])...)
@@ -467,7 +535,20 @@ func (s *Sequential) Learnables() g.Nodes {
 		s.graph = g.NewGraph()
 		s.mirror = make([]float32, len(theta))
 		off := 0
-		for l, sh := range [][2]int{{c.ObsDim, c.Hidden1}, {c.Hidden1, c.Hidden2}, {c.Hidden2, c.NActions}} {
+		dense := [][2]int{{c.ObsDim, c.Hidden1}, {c.Hidden1, c.Hidden2}, {c.Hidden2, c.NActions}}
+		if c.Arch == goldq.ArchAtariConv { // three filters (O, I, H, W), then the two FC layers
+			h1, w1 := (c.InHeight+2-8)/4+1, (c.InWidth+2-8)/4+1
+			h2, w2 := (h1+2-4)/2+1, (w1+2-4)/2+1
+			for l, f := range [][4]int{{32, c.InChannels, 8, 8}, {64, 32, 4, 4}, {64, 64, 3, 3}} {
+				n := f[0] * f[1] * f[2] * f[3]
+				w := tensor.New(tensor.WithShape(f[0], f[1], f[2], f[3]), tensor.WithBacking(s.mirror[off:off+n]))
+				off += n
+				s.nodes = append(s.nodes, g.NewTensor(s.graph, tensor.Float32, 4, g.WithShape(f[0], f[1], f[2], f[3]),
+					g.WithName(fmt.Sprintf("%s_conv%d_filter", s.name, l)), g.WithValue(w)))
+			}
+			dense = [][2]int{{64 * h2 * w2, 512}, {512, c.NActions}}
+		}
+		for l, sh := range dense {
 			w := tensor.New(tensor.WithShape(sh[0], sh[1]), tensor.WithBacking(s.mirror[off:off+sh[0]*sh[1]]))
 			off += sh[0] * sh[1]
 			b := tensor.New(tensor.WithShape(1, sh[1]), tensor.WithBacking(s.mirror[off:off+sh[1]]))

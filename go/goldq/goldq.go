@@ -28,6 +28,9 @@ const (
 	PrecFP32  = int(C.GOLDQ_PREC_FP32)
 	PrecBF16  = int(C.GOLDQ_PREC_BF16)
 
+	ArchMLP       = int(C.GOLDQ_ARCH_MLP)
+	ArchAtariConv = int(C.GOLDQ_ARCH_ATARI_CONV)
+
 	LossMSE         = int(C.GOLDQ_LOSS_MSE)
 	LossPseudoHuber = int(C.GOLDQ_LOSS_PSEUDO_HUBER)
 	SolverAdam      = int(C.GOLDQ_SOLVER_ADAM)
@@ -49,6 +52,9 @@ type Config struct {
 	Precision, Path, Device, NReplicas int
 	Loss, Solver                       int     // GOLDQ_LOSS_* / GOLDQ_SOLVER_*; RMSProp reads LR, Beta2 (= rho), Eps
 	HuberDelta                         float32 // PseudoHuberLoss.Delta
+	// Arch == ArchAtariConv: deepq.DefaultAtariLayerBuilder's stack on (InChannels, InHeight, InWidth) states;
+	// ObsDim = InChannels*InHeight*InWidth, Hidden1 / Hidden2 ignored
+	Arch, InChannels, InHeight, InWidth int
 }
 
 // DefaultConfig returns gold's defaults (CartPole shape, B=20, gamma .95, Adam 5e-4).
@@ -61,6 +67,7 @@ func DefaultConfig() Config {
 		Gamma: float32(c.gamma), LR: float64(c.lr), Beta1: float64(c.beta1), Beta2: float64(c.beta2), Eps: float64(c.eps),
 		Precision: int(c.precision), Path: int(c.path), Device: int(c.device), NReplicas: int(c.n_replicas),
 		Loss: int(c.loss), Solver: int(c.solver), HuberDelta: float32(c.huber_delta),
+		Arch: int(c.arch), InChannels: int(c.in_channels), InHeight: int(c.in_height), InWidth: int(c.in_width),
 	}
 }
 
@@ -84,6 +91,7 @@ func New(cfg Config) (*Handle, error) {
 	c.lr, c.beta1, c.beta2, c.eps = C.double(cfg.LR), C.double(cfg.Beta1), C.double(cfg.Beta2), C.double(cfg.Eps)
 	c.precision, c.path, c.device, c.n_replicas = C.int32_t(cfg.Precision), C.int32_t(cfg.Path), C.int32_t(cfg.Device), C.int32_t(cfg.NReplicas)
 	c.loss, c.solver, c.huber_delta = C.int32_t(cfg.Loss), C.int32_t(cfg.Solver), C.float(cfg.HuberDelta)
+	c.arch, c.in_channels, c.in_height, c.in_width = C.int32_t(cfg.Arch), C.int32_t(cfg.InChannels), C.int32_t(cfg.InHeight), C.int32_t(cfg.InWidth)
 	h := C.goldq_create(&c)
 	if h == nil {
 		return nil, fmt.Errorf("goldq_create: %s", C.GoString(C.goldq_last_error(nil)))

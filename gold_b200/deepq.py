@@ -78,11 +78,13 @@ class ShapesEnv:
     (env.go:161-168).  No gym server involved (BASELINE configs: "no Sphere env")."""
 
     def __init__(self, obs_dim, n_actions, seed=None):
-        self.obs_dim, self.n_actions = int(obs_dim), int(n_actions)
+        """obs_dim: an int (flat observations) or a (C, H, W) tuple (image observations of the Atari wrapper)."""
+        self.obs_shape = [int(obs_dim)] if np.isscalar(obs_dim) else [int(v) for v in obs_dim]
+        self.obs_dim, self.n_actions = int(np.prod(self.obs_shape)), int(n_actions)
         self._rng = random.Random(seed)
 
     def observation_space_shape(self):
-        return [self.obs_dim]
+        return list(self.obs_shape)
 
     def sample_action(self):
         return self._rng.randrange(self.n_actions)
@@ -236,6 +238,25 @@ class FC:
 LINEAR = "linear"
 
 
+class Conv2D:
+    """layer.Conv2D (goro layer/conv2d.go:14-50): Input/Output channels, kernel Height x Width, Stride; the defaults the
+    layer applies -- pad (1, 1), ReLU, no bias -- are the only ones the device path implements."""
+
+    def __init__(self, input, output, width, height, stride=(1, 1), pad=(1, 1), activation=None):
+        self.input, self.output, self.width, self.height = int(input), int(output), int(width), int(height)
+        self.stride, self.pad, self.activation = tuple(stride), tuple(pad), activation
+
+
+class Flatten:
+    """layer.Flatten (goro layer/flatten.go): reshape (batch, C*H*W)."""
+
+
+def default_atari_layer_builder(x_dim, y_dim):
+    """deepq.DefaultAtariLayerBuilder (policy.go:62-71)."""
+    return [Conv2D(1, 32, 8, 8, stride=(4, 4)), Conv2D(32, 64, 4, 4, stride=(2, 2)), Conv2D(64, 64, 3, 3, stride=(1, 1)),
+            Flatten(), FC(6400, 512), FC(512, y_dim, activation=LINEAR)]
+
+
 def default_fc_layer_builder(x_dim, y_dim):
     """deepq.DefaultFCLayerBuilder (policy.go:53-59)."""
     return [FC(x_dim, 24), FC(24, 24), FC(24, y_dim, activation=LINEAR)]
@@ -250,6 +271,12 @@ class PolicyConfig:
         self.layer_builder = layer_builder
         self.batch_size = batch_size
         self.track = track
+
+
+def default_atari_policy_config():
+    """deepq.DefaultAtariPolicyConfig (policy.go:41-47): MSE, RMSPropSolver with gorgonia's defaults
+    (eta 0.001, rho 0.999, eps 1e-8; WithBatchSize(20) does nothing for RMSProp), the conv layer builder, batch 20."""
+    return PolicyConfig(loss=MSE, optimizer=RMSPropSolver(), layer_builder=default_atari_layer_builder, batch_size=20)
 
 
 def default_policy_config():
@@ -322,6 +349,31 @@ def handle_options(pc):
     return opts
 
 
+def _atari_from_layers(layers, obs_shape):
+    """The conv stack the device implements is exactly DefaultAtariLayerBuilder's: three Conv2D (32x8x8/4, 64x4x4/2,
+    64x3x3/1, pad 1, ReLU), Flatten, FC(F, 512, ReLU), FC(512, A, linear).  Returns (C, H, W, A) or None when the
+    layers are not convolutional; anything else convolutional is an error (no CPU fallback)."""
+    if not layers or not isinstance(layers[0], Conv2D):
+        return None
+    want = [(32, 8, 8, (4, 4)), (64, 4, 4, (2, 2)), (64, 3, 3, (1, 1))]
+    ok = (len(layers) == 6 and all(isinstance(l, Conv2D) for l in layers[:3]) and isinstance(layers[3], Flatten)
+          and isinstance(layers[4], FC) and isinstance(layers[5], FC))
+    if ok:
+        for l, (o, hh, ww, st) in zip(layers[:3], want):
+            ok = ok and (l.output, l.height, l.width, l.stride) == (o, hh, ww, st) and l.pad == (1, 1) and l.activation in (None, "relu")
+        ok = ok and layers[1].input == 32 and layers[2].input == 64 and layers[4].output == 512 and layers[5].input == 512
+        ok = ok and layers[4].activation in (None, "relu") and layers[5].activation == LINEAR
+    if not ok or len(obs_shape) != 3 or obs_shape[0] != layers[0].input:
+        raise ValueError("the CUDA path implements deepq.DefaultAtariLayerBuilder's stack on (C, H, W) states only; "
+                         "no CPU fallback exists for other convolutional graphs")
+    C, H, W = (int(v) for v in obs_shape)
+    h1, w1 = (H + 2 - 8) // 4 + 1, (W + 2 - 8) // 4 + 1
+    h2, w2 = (h1 + 2 - 4) // 2 + 1, (w1 + 2 - 4) // 2 + 1
+    if layers[4].input != 64 * h2 * w2:          # conv 3 keeps the size (3x3, stride 1, pad 1)
+        raise ValueError(f"FC input {layers[4].input} does not match the {64 * h2 * w2} features of a {H}x{W} state")
+    return C, H, W, layers[5].output
+
+
 def _dims_from_layers(layers):
     if (len(layers) != 3 or layers[0].activation not in (None, "relu") or layers[1].activation not in (None, "relu")
             or layers[2].activation != LINEAR or layers[0].output != layers[1].input
@@ -362,16 +414,27 @@ class Agent:
             raise ValueError("environment cannot be nil")            # agent.go:96-98
         hp, pc = c.hyperparameters, c.policy_config
         opts = handle_options(pc)
-        dims = _dims_from_layers(pc.layer_builder(env.observation_space_shape()[0], env.n_actions))
-        self._h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3],
-                           batch_size=pc.batch_size, replay_capacity=hp.buffer_size, gamma=hp.gamma,
-                           device=c.device, precision=G.PREC_BF16 if c.precision == "bf16" else G.PREC_FP32,
-                           **opts)
-        # two independently initialised networks, GlorotN(1) (agent.go:101-109; goro fc.go:76-81);
-        # the target is first synced when steps % UpdateTargetSteps == 0
+        obs_shape = tuple(env.observation_space_shape())
+        layers = pc.layer_builder(obs_shape[0], env.n_actions)
         seed = c.seed if c.seed is not None else random.randrange(1 << 30)
-        self._h.set_params(G.NET_ONLINE, synth.glorot_params(dims, seed))
-        self._h.set_params(G.NET_TARGET, synth.glorot_params(dims, seed + 1))
+        atari = _atari_from_layers(layers, obs_shape)
+        if atari is not None:
+            C, H, W, A = atari
+            self._h = G.Handle(arch=G.ARCH_ATARI_CONV, in_channels=C, in_height=H, in_width=W, obs_dim=C * H * W, n_actions=A,
+                               batch_size=pc.batch_size, replay_capacity=hp.buffer_size, gamma=hp.gamma, device=c.device,
+                               **opts)
+            self._h.set_params(G.NET_ONLINE, synth.atari_params(C, H, W, A, seed))
+            self._h.set_params(G.NET_TARGET, synth.atari_params(C, H, W, A, seed + 1))
+        else:
+            dims = _dims_from_layers(layers)
+            self._h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3],
+                               batch_size=pc.batch_size, replay_capacity=hp.buffer_size, gamma=hp.gamma,
+                               device=c.device, precision=G.PREC_BF16 if c.precision == "bf16" else G.PREC_FP32,
+                               **opts)
+            # two independently initialised networks, GlorotN(1) (agent.go:101-109; goro fc.go:76-81);
+            # the target is first synced when steps % UpdateTargetSteps == 0
+            self._h.set_params(G.NET_ONLINE, synth.glorot_params(dims, seed))
+            self._h.set_params(G.NET_TARGET, synth.glorot_params(dims, seed + 1))
         self.hyperparameters = hp
         self.policy = Sequential("online", self._h, G.NET_ONLINE)
         self.target_policy = Sequential("target", self._h, G.NET_TARGET)

@@ -66,3 +66,21 @@ def sample_indices(n, batch, step):
         # same distribution, O(batch) instead of O(n)
         return rng.choice(n, size=batch, replace=False).astype(np.int32)
     return rng.permutation(n)[:batch].astype(np.int32)
+
+
+def atari_params(C, H, W, A, seed):
+    """Initial parameters of gold's Atari conv policy in learnable order [f1, f2, f3, W4, b4, W5, b5]: the filters
+    GlorotU(1) (goro layer/conv2d.go:104-106: uniform on +-sqrt(6 / (fan_in + fan_out)) with gorgonia's fans for a
+    4-d shape, weights.go:266-293), the FC layers GlorotN(1) as in glorot_params."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    h1, w1 = (H + 2 - 8) // 4 + 1, (W + 2 - 8) // 4 + 1
+    h2, w2 = (h1 + 2 - 4) // 2 + 1, (w1 + 2 - 4) // 2 + 1
+    F = 64 * h2 * w2
+    out = []
+    for o, i, k in ((32, C, 8), (64, 32, 4), (64, 64, 3)):
+        lim = np.sqrt(6.0 / (i * k * k + o * k * k))
+        out.append(rng.uniform(-lim, lim, o * i * k * k))
+    for fin, fout in ((F, 512), (512, A)):
+        out.append(rng.standard_normal(fin * fout) * np.sqrt(2.0 / (fin + fout)))
+        out.append(rng.standard_normal(fout) * np.sqrt(2.0 / (1 + fout)))
+    return np.concatenate(out).astype(np.float32)

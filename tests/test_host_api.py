@@ -206,3 +206,28 @@ def test_resize_batch_keeps_parameters_and_learns_at_the_new_size():
         with pytest.raises((G.GoldqError, AssertionError)):
             h.learn(synth.sample_indices(N, B0, 2))        # the old batch size is now a shape error for the index list
         h.close()
+
+
+@pytest.mark.gpu
+def test_atari_policy_config_builds_the_conv_agent():
+    """deepq.DefaultAtariPolicyConfig (policy.go:41-47, 62-71) through the host layer: the conv stack is recognised,
+    runs on GOLDQ_PATH_CONV with RMSProp, learns, acts; a different convolutional graph fails loudly."""
+    from gold_b200 import _capi as G
+    env = deepq.ShapesEnv((1, 84, 84), 6, seed=3)
+    agent = deepq.Agent(deepq.AgentConfig(hyperparameters=deepq.Hyperparameters(buffer_size=64),
+                                          policy_config=deepq.default_atari_policy_config(), seed=4), env)
+    assert agent._h.path == G.PATH_CONV and agent._h.cfg.solver == G.SOLVER_RMSPROP and agent.batch_size == 20
+    rng = np.random.Generator(np.random.PCG64(0))
+    for t in range(24):
+        s = rng.uniform(0, 1, (1, 84, 84)).astype(np.float32)
+        a = agent.action(s)
+        assert 0 <= a < 6
+        agent.remember(deepq.new_event(s, a, deepq.Outcome(rng.uniform(0, 1, (1, 84, 84)).astype(np.float32), a, 1.0, t % 7 == 6)))
+        agent.learn()
+    assert np.isfinite(agent.last_loss()) and agent.last_loss() > 0
+    q = agent.policy.predict(s)
+    assert q.shape == (1, 6) and np.isfinite(q).all()
+    agent.close()
+    bad = deepq.PolicyConfig(layer_builder=lambda x, y: [deepq.Conv2D(1, 16, 8, 8, stride=(4, 4)), deepq.Flatten(), deepq.FC(64, y, activation=deepq.LINEAR)])
+    with pytest.raises(ValueError):
+        deepq.Agent(deepq.AgentConfig(policy_config=bad), env)
