@@ -120,6 +120,25 @@ def test_wide_rmsprop_in_the_fused_update_kernel(dims, B):
     h.close()
 
 
+def test_pair_gemm_dw2_opt_in_matches_the_default_kernel(monkeypatch):
+    """The split-K weight-gradient variant of pair_gemm_kernel (PG_DW, opt-in with GOLDQ_PAIR_DW2=1: measured no faster
+    inside the step) computes the same dW2 as the single-CTA GEMM up to the different split of the batch sum."""
+    dims, B, N = synth.WIDE, 512, 1024
+    idx = synth.sample_indices(N, B, 0)
+    grads = []
+    for on in (False, True):
+        if on:
+            monkeypatch.setenv("GOLDQ_PAIR_DW2", "1")
+        h, o = make(dims, B, N)
+        h.learn(idx)
+        grads.append(h.debug_fetch(G.DBG_GRADS).astype(np.float64))
+        h.close()
+    off = synth.offsets(dims)
+    lo, hi = off["w2"]
+    assert np.linalg.norm(grads[0][lo:hi] - grads[1][lo:hi]) <= 1e-5 * np.linalg.norm(grads[0][lo:hi])
+    np.testing.assert_array_equal(np.delete(grads[0], np.s_[lo:hi]), np.delete(grads[1], np.s_[lo:hi]))
+
+
 def _bf(x):
     """round-to-nearest-even to bf16, returned as float64 values"""
     u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
