@@ -370,14 +370,15 @@ class Workload:
 
     def e2e(self, K, sampler=None):
         """The same metric through the public C ABI with HOST buffers.  Every step: B fresh transitions
-        pushed from ONE pinned host buffer (goldq_replay_push_packed: one H2D copy on the library's copy
-        stream, overlapping the previous step), the sampled index list from pinned host memory (H2D),
-        the step (goldq_learn), the loss read back (goldq_last_loss: D2H + sync).  Host wall clock."""
+        from ONE pinned host buffer (goldq_replay_stage_packed: one H2D copy on the library's copy stream,
+        started two steps ahead like an actor thread would; goldq_replay_commit appends the batch behind the
+        step), the sampled index list from host memory (read by the device over PCIe), the step (goldq_learn),
+        the loss read back (goldq_last_loss: the step's store into mapped host memory + sync).  Host wall clock."""
         G, h, dims, B, R, N = self.G, self.h, self.dims, self.B, self.R, self.N
         D = dims[0]
         nbytes = h.packed_bytes(B)
         bufs = []
-        for k in range(2):
+        for k in range(3):
             arr, ptr = pinned_array(G, (nbytes,), np.uint8)
             parts = [synth.replay(dims, B, seed=4242 + k + 31 * r) for r in range(R)]
             fresh = [np.concatenate([p[j] for p in parts]) for j in range(5)]
@@ -392,16 +393,18 @@ class Workload:
         d2h = 4 * R
 
         def step(i):
-            # the batch of step i was pushed during step i-1 (double-buffered staging): its copy overlaps
-            # that step's kernels; every byte still crosses PCIe inside the timed region
-            h.learn_raw(idx_host[i % len(idx_host)])          # H2D of the index list + the step
-            h.replay_push_packed(B, bufs[(i + 1) & 1])        # H2D of the next batch (copy stream)
-            loss = h.last_loss()                              # D2H + sync on the step
+            # batch i+1 was staged during step i-1 and batch i+2 is staged now (three staging sets): the copies
+            # overlap the steps' kernels; every byte still crosses PCIe inside the timed region, one batch per step
+            h.learn_raw(idx_host[i % len(idx_host)])          # index list (host memory) + the step
+            h.replay_commit()                                 # batch i+1 -> replay memory, behind step i
+            h.replay_stage_packed(B, bufs[(i + 2) % 3])       # H2D of batch i+2 (copy stream)
+            loss = h.last_loss()                              # the step's loss (mapped host memory) + sync
             if (i + 1) % TARGET_SYNC_EVERY == 0:
                 h.sync_target()
             return loss
 
         h.replay_push_packed(B, bufs[0])
+        h.replay_stage_packed(B, bufs[1])
         for i in range(3):
             step(i)
         self.barrier()
@@ -573,9 +576,9 @@ def run_own(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "what": "per step: goldq_replay_push_packed of a fresh batch from ONE pinned host buffer (copy "
-                            "stream, overlapping the previous step) + goldq_learn with pinned host indices + "
-                            "goldq_last_loss readback (sync); host wall clock, max over ranks"},
+                    "what": "per step: one fresh batch from ONE pinned host buffer (goldq_replay_stage_packed: H2D on the "
+                            "copy stream, started two steps ahead; goldq_replay_commit behind the step) + goldq_learn "
+                            "with host indices + goldq_last_loss readback (sync); host wall clock, max over ranks"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "path": path, "last_loss": [float(x) for x in last[:4]], "allreduce": mode,
             "configs": extra,
@@ -588,8 +591,9 @@ def run_own(args):
 _REAL_STDOUT = None
 
 # ff_forward_kernel, wide config, B=8192: 5.739 MB read + 0.024 MB written per launch
-NCU_TRAFFIC = {("fused forward L1-L3 online+target (tcgen05)", (128, 512, 512, 18), 8192): 5739264 + 24320}
-NCU_TRAFFIC_SOURCE = "profiles/r01_wide_v3_ncu_full_raw.csv"
+NCU_TRAFFIC = {("fused forward L1-L3 online+target, CTA pairs (tcgen05 cta_group::2)", (128, 512, 512, 18), 8192):
+               5805568 + 8448}
+NCU_TRAFFIC_SOURCE = "profiles/r02_ff_forward2_ncu_full_raw.csv"
 
 
 def emit(line):

@@ -145,6 +145,13 @@ func (x *Handle) ReplayPushPacked(n int, packed []byte) error {
 	return x.err(C.goldq_replay_push_packed(x.h, C.int64_t(n), unsafe.Pointer(&packed[0])))
 }
 
+// ReplayStagePacked starts the host-to-device copy of a packed batch without touching the replay memory;
+// ReplayCommit appends the oldest staged batch (see include/goldq.h).  ReplayPushPacked = both.
+func (x *Handle) ReplayStagePacked(n int, packed []byte) error {
+	return x.err(C.goldq_replay_stage_packed(x.h, C.int64_t(n), unsafe.Pointer(&packed[0])))
+}
+func (x *Handle) ReplayCommit() error { return x.err(C.goldq_replay_commit(x.h)) }
+
 // ResizeBatch is Sequential.ResizeBatch: scratch sized by the batch is re-allocated, parameters, solver state
 // and replay are kept.
 func (x *Handle) ResizeBatch(n int) error {

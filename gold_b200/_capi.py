@@ -26,7 +26,7 @@ SYMBOLS = [
     "goldq_default_config", "goldq_create", "goldq_destroy", "goldq_last_error",
     "goldq_abi_version", "goldq_param_count", "goldq_selected_path", "goldq_set_params",
     "goldq_get_params", "goldq_set_adam_state", "goldq_get_adam_state", "goldq_replay_push",
-    "goldq_replay_len", "goldq_replay_push_wait", "goldq_host_alloc", "goldq_host_free",
+    "goldq_replay_len", "goldq_replay_push_wait", "goldq_replay_stage_packed", "goldq_replay_commit", "goldq_host_alloc", "goldq_host_free",
     "goldq_replay_push_packed", "goldq_packed_bytes", "goldq_learn_prepare", "goldq_graph_builds", "goldq_launch_floor", "goldq_time_forward", "goldq_resize_batch", "goldq_batch_size",
     "goldq_learn", "goldq_learn_device_indices", "goldq_learn_many", "goldq_sampler_indices", "goldq_sync_target",
     "goldq_last_loss", "goldq_predict", "goldq_greedy_action", "goldq_epsilon_greedy_action", "goldq_explore_plan",
@@ -92,6 +92,8 @@ def lib():
         "goldq_batch_size": (i32, [vp]),
         "goldq_replay_len": (i64, [vp]),
         "goldq_replay_push_wait": (C.c_int, [vp]),
+        "goldq_replay_stage_packed": (C.c_int, [vp, C.c_int64, vp]),
+        "goldq_replay_commit": (C.c_int, [vp]),
         "goldq_host_alloc": (vp, [i64]),
         "goldq_host_free": (None, [vp]),
         "goldq_learn": (C.c_int, [vp, vp, u64]),
@@ -252,6 +254,14 @@ class Handle:
     def replay_push_packed(self, n, packed_ptr):
         """One contiguous host buffer s|s2|a|r|done (goldq.h): ONE H2D copy."""
         self._ck(self._L.goldq_replay_push_packed(self._h, n, packed_ptr))
+
+    def replay_stage_packed(self, n, packed_ptr):
+        """Start the H2D copy of a packed batch; the replay memory changes at replay_commit()."""
+        self._ck(self._L.goldq_replay_stage_packed(self._h, n, packed_ptr))
+
+    def replay_commit(self):
+        """Append the oldest staged batch to the replay memory (in stream order on the learn stream)."""
+        self._ck(self._L.goldq_replay_commit(self._h))
 
     def pack(self, s, a, r, s2, done, out=None):
         """Pack the five arrays of n transitions into the layout goldq_replay_push_packed takes."""

@@ -82,8 +82,10 @@ struct goldq {
     struct Staging {
         uint8_t *base = nullptr;        // one allocation, packed as goldq_replay_push_packed documents
         cudaEvent_t copied = nullptr, scattered = nullptr;
-    } stg[2];
-    int stg_cur = 0;
+        int64_t n = 0;                  // items per replica of the staged, not yet committed batch
+    } stg[3];
+    int stg_cur = 0;                    // next set to fill
+    int stg_pending = 0;                // staged batches not yet scattered into the ring (oldest = stg_cur - stg_pending)
     int64_t stg_cap = 0;
     cudaStream_t copy_st = nullptr;
     cudaEvent_t ev_push = nullptr;      // = copied event of the latest push
@@ -140,7 +142,8 @@ struct goldq {
     int pf_set = 0, pf_have = 0;                 // batch double buffering while capturing (build_graph)
     const StepDev *pf_next = nullptr;
     StepDev *d_steps = nullptr;                  // [GRAPH_MAX] per-step scalars read by captured kernels
-    StepDev *h_steps[STEP_RING] = {};            // pinned staging ring
+    StepDev *h_steps[STEP_RING] = {};            // pinned (mapped) staging ring
+    int32_t *h_idx[STEP_RING] = {};              // pinned (mapped) copies of goldq_learn's host index lists, [R][B] each
     cudaEvent_t ev_steps[STEP_RING] = {};
     int steps_buf = 0;
     // graph_exec[c]: c consecutive steps with device-drawn indices; graph_exec[0]: ONE step that reads the
@@ -344,7 +347,7 @@ int learn_generic(goldq_t *h, const int32_t *idx_dev, const StepDev *step)
     h->iter += 1;
     generic_solver_step(h, step);
     h->launches += 1;
-    CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDefault, h->st));
     return check_launch(h, "learn_generic");
 }
 
@@ -387,7 +390,7 @@ int learn_narrow(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDe
         if (rc) return rc;
         launch_adam(h->theta, h->flat, h->m, h->v, h->P, a.adam, step, h->st);
         h->launches += 1;
-        CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice,
+        CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDefault,
                               h->st));
     }
     return check_launch(h, "learn_narrow");
@@ -452,7 +455,7 @@ int learn_wide(goldq_t *h, const int32_t *idx_dev, uint64_t seed, const StepDev 
         if (n < 0) return fail(h, GOLDQ_ECUDA, err);
         h->launches += n;
         if (h->prof_evs) cudaEventRecord(h->prof_evs[h->prof_n++], h->st);
-        CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+        CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDefault, h->st));
     }
     return check_launch(h, "learn_wide");
 }
@@ -530,7 +533,7 @@ int learn_conv(goldq_t *h, const int32_t *idx_dev, const StepDev *step)
     h->iter += 1;
     generic_solver_step(h, step);
     h->launches += 1;
-    CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDefault, h->st));
     return check_launch(h, "learn_conv");
 }
 
@@ -557,6 +560,20 @@ void drop_graphs(goldq_t *h)
     for (int i = 0; i <= goldq::GRAPH_MAX; i++)
         if (h->graph_exec[i]) { cudaGraphExecDestroy(h->graph_exec[i]); h->graph_exec[i] = nullptr; }
 }
+
+// Per-step scalars (and goldq_learn's host index list) travel to the device through THIS kernel reading mapped
+// pinned host memory, not through cudaMemcpyAsync: a small host-to-device copy on the learn stream shares the
+// copy engine's queue with goldq_replay_push's 8.5 MB copy on the copy stream, and because the small copy is
+// stream-ordered behind the previous push's scatter the next big copy queued behind IT could not start
+// (tools/e2e_probe.py: 215 us per Remember+Learn against the 156 us the copy alone needs).
+__global__ void stage_steps_kernel(const uint2 *__restrict__ ssrc, uint2 *__restrict__ sdst, int nsteps16,
+                                   const int32_t *__restrict__ isrc, int32_t *__restrict__ idst, int nidx)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nsteps16) sdst[t] = ssrc[t];
+    if (t < nidx) idst[t] = isrc[t];
+}
+static_assert(sizeof(StepDev) % 8 == 0, "StepDev is staged in 8-byte words");
 
 // Capture c consecutive learn steps (device sampler, per-step scalars from d_steps[i]) into
 // one executable graph; c == 0: ONE step that reads its index list from d_idx.  Kernel arguments
@@ -604,7 +621,7 @@ int build_graph(goldq_t *h, int slot)
 
 // Replay the graph in `slot` (see build_graph) for steps seed, seed+1, ...: stage the steps' scalars,
 // copy them to the device slots in stream order, launch.
-int launch_graph(goldq_t *h, int slot, uint64_t seed)
+int launch_graph(goldq_t *h, int slot, uint64_t seed, const int32_t *host_idx = nullptr)
 {
     const int c = slot == 0 ? 1 : slot;
     // a peer that stopped answering was detected by an earlier step: do not queue more 5 s waits
@@ -633,7 +650,16 @@ int launch_graph(goldq_t *h, int slot, uint64_t seed)
         sd.head = h->rp.head;
         sd.len = h->rp.len;
     }
-    CK(h, cudaMemcpyAsync(h->d_steps, h->h_steps[b], sizeof(StepDev) * c, cudaMemcpyHostToDevice, h->st));
+    const int n16 = (int)(sizeof(StepDev) / 8) * c;
+    int nidx = 0;
+    if (host_idx) {
+        nidx = h->R * h->B;
+        memcpy(h->h_idx[b], host_idx, (size_t)nidx * 4);
+    }
+    const int nthr = n16 > nidx ? n16 : nidx;
+    stage_steps_kernel<<<(nthr + 255) / 256, 256, 0, h->st>>>((const uint2 *)h->h_steps[b], (uint2 *)h->d_steps, n16,
+                                                            h->h_idx[b], h->d_idx, nidx);
+    h->launches += 1;
     CK(h, cudaEventRecord(h->ev_steps[b], h->st));
     CK(h, cudaGraphLaunch(h->graph_exec[slot], h->st));
     if (h->p2p.on) h->p2p.epoch += (uint32_t)c;
@@ -952,7 +978,9 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
     }
     for (int i = 0; i < goldq::STEP_RING; i++) {
         cudaEventCreateWithFlags(&h->ev_steps[i], cudaEventDisableTiming);
-        if (cudaHostAlloc((void **)&h->h_steps[i], sizeof(StepDev) * goldq::GRAPH_MAX, cudaHostAllocDefault) != cudaSuccess)
+        if (cudaHostAlloc((void **)&h->h_idx[i], (size_t)(h->R > 0 ? h->R : 1) * h->B * 4, cudaHostAllocMapped) != cudaSuccess)
+            return bail("cudaHostAlloc failed (index staging)");
+        if (cudaHostAlloc((void **)&h->h_steps[i], sizeof(StepDev) * goldq::GRAPH_MAX, cudaHostAllocMapped) != cudaSuccess)
             return bail("cudaHostAlloc failed (step slots)");
     }
     if (dalloc(&h->d_steps, (size_t)goldq::GRAPH_MAX) != cudaSuccess) return bail("cudaMalloc failed (step slots)");
@@ -964,7 +992,10 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
     ok &= dalloc(&h->m, RP) == cudaSuccess;
     ok &= dalloc(&h->v, RP) == cudaSuccess;
     ok &= dalloc(&h->flat, (size_t)h->R * (h->P + 1)) == cudaSuccess;
-    ok &= dalloc(&h->loss, (size_t)h->R) == cudaSuccess;
+    // the loss lives in mapped pinned host memory: the kernels' (posted) 4-byte store IS the readback, so
+    // goldq_last_loss is an event wait plus a host load -- no copy, no copy-engine queue, no second stream
+    ok &= cudaHostAlloc((void **)&h->loss, (size_t)h->R * 4, cudaHostAllocMapped) == cudaSuccess;
+    if (ok) memset(h->loss, 0, (size_t)h->R * 4);
     ok &= dalloc(&h->d_idx, (size_t)h->R * h->B) == cudaSuccess;
     size_t cap = (size_t)cfg->replay_capacity, RC = (size_t)h->R * cap;
     ok &= dalloc(&h->rp.s, RC * h->dims.D) == cudaSuccess;
@@ -980,7 +1011,6 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
     cudaMemsetAsync(h->theta_t, 0, RP * 4, h->st);
     cudaMemsetAsync(h->m, 0, RP * 4, h->st);
     cudaMemsetAsync(h->v, 0, RP * 4, h->st);
-    cudaMemsetAsync(h->loss, 0, (size_t)h->R * 4, h->st);
 
     if (path == GOLDQ_PATH_NARROW) {
         NarrowArgs a{};
@@ -1013,14 +1043,16 @@ void goldq_destroy(goldq_t *h)
     drop_graphs(h);
     for (int i = 0; i < goldq::STEP_RING; i++) {
         if (h->h_steps[i]) cudaFreeHost(h->h_steps[i]);
+        if (h->h_idx[i]) cudaFreeHost(h->h_idx[i]);
         if (h->ev_steps[i]) cudaEventDestroy(h->ev_steps[i]);
     }
     if (h->d_steps) cudaFree(h->d_steps);
     p2p_teardown(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->wide) wide_destroy(h->wide);
-    void *ptrs[] = {h->theta, h->theta_t, h->m, h->v, h->flat, h->loss, h->d_idx, h->rp.s, h->rp.s2,
-                    h->rp.a, h->rp.r, h->rp.done, h->stg[0].base, h->stg[1].base, h->partial, h->ticket, h->bs, h->bs2, h->br, h->ba, h->bdone, h->h1,
+    if (h->loss) cudaFreeHost(h->loss);
+    void *ptrs[] = {h->theta, h->theta_t, h->m, h->v, h->flat, h->d_idx, h->rp.s, h->rp.s2,
+                    h->rp.a, h->rp.r, h->rp.done, h->stg[0].base, h->stg[1].base, h->stg[2].base, h->partial, h->ticket, h->bs, h->bs2, h->br, h->ba, h->bdone, h->h1,
                     h->h2, h->q, h->t1, h->t2, h->qt, h->td, h->dq, h->dh2, h->dh1, h->ylab, h->mk1,
                     h->mk2, h->gslice, h->loss_part, h->px, h->ph1, h->ph2, h->pq, h->pact,
                     h->dbg_q, h->dbg_qt, h->dbg_td, h->dbg_idx, h->cy1, h->cy2, h->cy3, h->ch4, h->cu1, h->cu2, h->cu3, h->cu4,
@@ -1106,52 +1138,21 @@ int goldq_get_adam_state(goldq_t *h, float *m, float *v, int64_t *iter)
     return GOLDQ_OK;
 }
 
-// shared tail of goldq_replay_push / goldq_replay_push_packed.  `packed` != NULL: one host buffer in
-// the packed layout (ONE H2D copy); else the five arrays (five copies into the same device layout).
-static int push_common(goldq_t *h, int64_t n, const void *packed, const float *s, const int32_t *a, const float *r,
-                       const float *s2, const uint8_t *done)
+// Two halves of a push.  stage_batch: validate, then start the H2D copy into a free staging set on the copy
+// stream (`packed` != NULL: one host buffer in the packed layout, ONE copy; else the five arrays, five copies
+// into the same device layout).  commit_batch: scatter the OLDEST staged batch into the ring, in stream order
+// on the learn stream.  goldq_replay_push* = stage + commit; goldq_replay_stage_packed / goldq_replay_commit let a
+// caller start the copy of batch t+2 before it waits for learn step t, so that the copy engine always has the
+// next copy queued (tools/e2e_probe.py).
+constexpr int NSTG = 3;
+static int commit_batch(goldq_t *h)
 {
-    // the learn step indexes Q rows, W3 columns and dQ with the stored action: an action outside
-    // [0, n_actions) would be an out-of-bounds device access (the reference panics in
-    // qValues.Set(event.Action, ...), agent.go:155); reject it here
-    {
-        const int64_t total = (int64_t)h->R * n;
-        const uint32_t A = (uint32_t)h->dims.A;
-        for (int64_t i = 0; i < total; i++)
-            if ((uint32_t)a[i] >= A)
-                return fail(h, GOLDQ_EINVAL, "replay_push: action " + std::to_string(a[i]) + " at item " +
-                                                 std::to_string(i) + " is outside [0, n_actions)");
-    }
-    CK(h, cudaSetDevice(h->dev));
+    if (h->stg_pending < 1) return fail(h, GOLDQ_EINVAL, "replay_commit: no staged batch");
+    goldq::Staging &g = h->stg[(h->stg_cur + NSTG - h->stg_pending) % NSTG];
+    h->stg_pending -= 1;
     const int D = h->dims.D, R = h->R;
-    if (h->stg_cap < n) {
-        CK(h, cudaStreamSynchronize(h->copy_st));
-        CK(h, cudaStreamSynchronize(h->st));
-        int64_t cap = n < 1024 ? 1024 : n;
-        for (auto &g : h->stg) {
-            if (g.base) cudaFree(g.base);
-            g.base = nullptr;
-            CK(h, dalloc(&g.base, packed_bytes((int64_t)R * cap, D)));
-        }
-        h->stg_cap = cap;
-    }
-    goldq::Staging &g = h->stg[h->stg_cur];
-    h->stg_cur ^= 1;
-    const int64_t rows = (int64_t)R * n;
+    const int64_t n = g.n, rows = (int64_t)R * n;
     const PackedView dv = packed_view(g.base, rows, D);
-    // copy stream: wait until the scatter that last read this staging set is done, then copy
-    CK(h, cudaStreamWaitEvent(h->copy_st, g.scattered, 0));
-    if (packed) {
-        CK(h, cudaMemcpyAsync(g.base, packed, packed_bytes(rows, D), cudaMemcpyHostToDevice, h->copy_st));
-    } else {
-        CK(h, cudaMemcpyAsync((void *)dv.s, s, (size_t)rows * D * 4, cudaMemcpyHostToDevice, h->copy_st));
-        CK(h, cudaMemcpyAsync((void *)dv.s2, s2, (size_t)rows * D * 4, cudaMemcpyHostToDevice, h->copy_st));
-        CK(h, cudaMemcpyAsync((void *)dv.a, a, (size_t)rows * 4, cudaMemcpyHostToDevice, h->copy_st));
-        CK(h, cudaMemcpyAsync((void *)dv.r, r, (size_t)rows * 4, cudaMemcpyHostToDevice, h->copy_st));
-        CK(h, cudaMemcpyAsync((void *)dv.done, done, (size_t)rows, cudaMemcpyHostToDevice, h->copy_st));
-    }
-    CK(h, cudaEventRecord(g.copied, h->copy_st));
-    h->ev_push = g.copied;
     // main stream: the ring is updated after everything enqueued so far (in stream order)
     CK(h, cudaStreamWaitEvent(h->st, g.copied, 0));
     // only the newest `cap` of the n items survive (PushFront + PopBack, agent.go:224-229)
@@ -1169,6 +1170,75 @@ static int push_common(goldq_t *h, int64_t n, const void *packed, const float *s
     h->rp.head = (h->rp.head + mcount) % h->rp.cap;
     h->rp.len = h->rp.len + mcount > h->rp.cap ? h->rp.cap : h->rp.len + mcount;
     return check_launch(h, "replay_scatter_kernel");
+}
+
+static int stage_batch(goldq_t *h, int64_t n, const void *packed, const float *s, const int32_t *a, const float *r,
+                       const float *s2, const uint8_t *done)
+{
+    // the learn step indexes Q rows, W3 columns and dQ with the stored action: an action outside
+    // [0, n_actions) would be an out-of-bounds device access (the reference panics in
+    // qValues.Set(event.Action, ...), agent.go:155); reject it here
+    {
+        const int64_t total = (int64_t)h->R * n;
+        const uint32_t A = (uint32_t)h->dims.A;
+        uint32_t worst = 0;
+        for (int64_t i = 0; i < total; i++) worst = (uint32_t)a[i] > worst ? (uint32_t)a[i] : worst;
+        if (worst >= A)
+            for (int64_t i = 0; i < total; i++)
+                if ((uint32_t)a[i] >= A)
+                    return fail(h, GOLDQ_EINVAL, "replay_push: action " + std::to_string(a[i]) + " at item " +
+                                                     std::to_string(i) + " is outside [0, n_actions)");
+    }
+    CK(h, cudaSetDevice(h->dev));
+    const int D = h->dims.D, R = h->R;
+    if (h->stg_pending >= NSTG - 1)
+        return fail(h, GOLDQ_EINVAL, "replay_stage: two batches are staged already; goldq_replay_commit one first");
+    if (h->stg_cap < n) {
+        while (h->stg_pending > 0) {     // staged batches keep their order: into the ring before the sets are replaced
+            int rc = commit_batch(h);
+            if (rc) return rc;
+        }
+        CK(h, cudaStreamSynchronize(h->copy_st));
+        CK(h, cudaStreamSynchronize(h->st));
+        int64_t cap = n < 1024 ? 1024 : n;
+        for (auto &g : h->stg) {
+            if (g.base) cudaFree(g.base);
+            g.base = nullptr;
+            CK(h, dalloc(&g.base, packed_bytes((int64_t)R * cap, D)));
+        }
+        h->stg_cap = cap;
+    }
+    goldq::Staging &g = h->stg[h->stg_cur];
+    h->stg_cur = (h->stg_cur + 1) % NSTG;
+    h->stg_pending += 1;
+    g.n = n;
+    const int64_t rows = (int64_t)R * n;
+    const PackedView dv = packed_view(g.base, rows, D);
+    // copy stream: wait until the scatter that last read this staging set is done, then copy
+    CK(h, cudaStreamWaitEvent(h->copy_st, g.scattered, 0));
+    if (packed) {
+        CK(h, cudaMemcpyAsync(g.base, packed, packed_bytes(rows, D), cudaMemcpyHostToDevice, h->copy_st));
+    } else {
+        CK(h, cudaMemcpyAsync((void *)dv.s, s, (size_t)rows * D * 4, cudaMemcpyHostToDevice, h->copy_st));
+        CK(h, cudaMemcpyAsync((void *)dv.s2, s2, (size_t)rows * D * 4, cudaMemcpyHostToDevice, h->copy_st));
+        CK(h, cudaMemcpyAsync((void *)dv.a, a, (size_t)rows * 4, cudaMemcpyHostToDevice, h->copy_st));
+        CK(h, cudaMemcpyAsync((void *)dv.r, r, (size_t)rows * 4, cudaMemcpyHostToDevice, h->copy_st));
+        CK(h, cudaMemcpyAsync((void *)dv.done, done, (size_t)rows, cudaMemcpyHostToDevice, h->copy_st));
+    }
+    CK(h, cudaEventRecord(g.copied, h->copy_st));
+    h->ev_push = g.copied;
+    return GOLDQ_OK;
+}
+
+static int push_common(goldq_t *h, int64_t n, const void *packed, const float *s, const int32_t *a, const float *r,
+                       const float *s2, const uint8_t *done)
+{
+    while (h->stg_pending > 0) {         // batches staged earlier go into the ring first
+        int rc = commit_batch(h);
+        if (rc) return rc;
+    }
+    int rc = stage_batch(h, n, packed, s, a, r, s2, done);
+    return rc ? rc : commit_batch(h);
 }
 
 int goldq_replay_push(goldq_t *h, int64_t n, const float *s, const int32_t *a, const float *r,
@@ -1192,6 +1262,21 @@ int goldq_replay_push_packed(goldq_t *h, int64_t n, const void *packed)
     if (n == 0) return GOLDQ_OK;
     const PackedView hv = packed_view(packed, (int64_t)h->R * n, h->dims.D);
     return push_common(h, n, packed, hv.s, hv.a, hv.r, hv.s2, hv.done);
+}
+
+int goldq_replay_stage_packed(goldq_t *h, int64_t n, const void *packed)
+{
+    if (!h || n < 0 || (n > 0 && !packed)) return fail(h, GOLDQ_EINVAL, "replay_stage_packed: bad argument");
+    if (n == 0) return GOLDQ_OK;
+    const PackedView hv = packed_view(packed, (int64_t)h->R * n, h->dims.D);
+    return stage_batch(h, n, packed, hv.s, hv.a, hv.r, hv.s2, hv.done);
+}
+
+int goldq_replay_commit(goldq_t *h)
+{
+    if (!h) return GOLDQ_EINVAL;
+    CK(h, cudaSetDevice(h->dev));
+    return commit_batch(h);
 }
 
 int goldq_replay_push_wait(goldq_t *h)
@@ -1222,15 +1307,17 @@ int goldq_learn(goldq_t *h, const int32_t *idx, uint64_t seed)
     const int32_t *idx_dev = nullptr;
     if (idx) {
         size_t n = (size_t)h->R * h->B;
-        for (size_t i = 0; i < n; i++)
-            if (idx[i] < 0 || idx[i] >= h->rp.len)
-                return fail(h, GOLDQ_EINVAL, "learn: sampled index out of range");
+        uint32_t worst = 0;      // (branch-free so that the compiler vectorises it: this loop is on the e2e path)
+        for (size_t i = 0; i < n; i++) worst = (uint32_t)idx[i] > worst ? (uint32_t)idx[i] : worst;
+        if ((int64_t)worst >= h->rp.len) return fail(h, GOLDQ_EINVAL, "learn: sampled index out of range");
+        // one launch instead of the step's kernels, events and cross-stream waits: Agent.Learn after
+        // every Remember replays the same one-step graph (the ring position and the index list travel
+        // through the step's staging slot)
+        if (use_graphs(h)) return learned(h, launch_graph(h, 0, seed, idx));
         CK(h, cudaMemcpyAsync(h->d_idx, idx, n * 4, cudaMemcpyHostToDevice, h->st));
         idx_dev = h->d_idx;
     }
-    // one launch instead of the step's kernels, events and cross-stream waits: Agent.Learn after
-    // every Remember replays the same one-step graph (the ring position travels in the step slot)
-    if (use_graphs(h)) return learned(h, launch_graph(h, idx ? 0 : 1, seed));
+    if (use_graphs(h)) return learned(h, launch_graph(h, 1, seed));
     return learned(h, run_learn(h, idx_dev, seed));
 }
 
@@ -1257,6 +1344,11 @@ int goldq_resize_batch(goldq_t *h, int32_t n)
     if (dalloc(&idx, (size_t)h->R * n) != cudaSuccess) { if (nw) wide_destroy(nw); return fail(h, GOLDQ_ECUDA, "cudaMalloc failed (index list)"); }
     cudaFree(h->d_idx);
     h->d_idx = idx;
+    for (int i = 0; i < goldq::STEP_RING; i++) {
+        if (h->h_idx[i]) cudaFreeHost(h->h_idx[i]);
+        h->h_idx[i] = nullptr;
+        CK(h, cudaHostAlloc((void **)&h->h_idx[i], (size_t)h->R * n * 4, cudaHostAllocMapped));
+    }
     h->B = n;
     h->Bglobal = n;
     h->cfg.batch_size = n;
@@ -1477,10 +1569,10 @@ int goldq_last_loss(goldq_t *h, float *out)
 {
     if (!h || !out) return fail(h, GOLDQ_EINVAL, "last_loss: bad argument");
     CK(h, cudaSetDevice(h->dev));
-    // ordered after the latest learn step (ev_learned), not after whatever was enqueued behind it
-    CK(h, cudaStreamWaitEvent(h->rb_st, h->ev_learned, 0));
-    CK(h, cudaMemcpyAsync(out, h->loss, (size_t)h->R * 4, cudaMemcpyDeviceToHost, h->rb_st));
-    CK(h, cudaStreamSynchronize(h->rb_st));
+    // wait for the latest learn step (ev_learned), not for whatever was enqueued behind it; the loss was
+    // stored into mapped host memory by the step itself (see goldq_create)
+    CK(h, cudaEventSynchronize(h->ev_learned));
+    memcpy(out, h->loss, (size_t)h->R * 4);
     if (h->p2p.on && *(volatile int *)h->p2p.err_host)
         return fail(h, GOLDQ_ENCCL, "data-parallel peer did not publish its gradient within 5 s");
     return GOLDQ_OK;
@@ -1610,7 +1702,7 @@ int goldq_fit_batch(goldq_t *h, int64_t n, const float *x, const float *y)
     h->iter += 1;
     generic_solver_step(h, nullptr);
     h->launches += 2;
-    CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDeviceToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->loss, h->flat + h->P, sizeof(float), cudaMemcpyDefault, h->st));
     if (h->wide) {
         std::string err;
         int k = wide_after_update(h->wide, h->theta, h->st, err);

@@ -148,6 +148,17 @@ int goldq_replay_push(goldq_t *h, int64_t n, const float *s, const int32_t *a,
  * Events into such a pinned buffer as they are Remembered. */
 int goldq_replay_push_packed(goldq_t *h, int64_t n, const void *packed);
 int64_t goldq_packed_bytes(const goldq_t *h, int64_t n);
+/* The two halves of goldq_replay_push_packed, for callers that produce transitions ahead of the learner
+ * (an actor thread filling the next pinned buffer while Agent.Learn runs, agent.go:224-229 + 126):
+ *   goldq_replay_stage_packed  validates the batch and STARTS its host-to-device copy on the copy stream;
+ *                              the replay memory does not change.  At most two batches may be staged.
+ *   goldq_replay_commit        appends the OLDEST staged batch to the replay memory, ordered after every learn
+ *                              step enqueued so far (exactly where goldq_replay_push_packed would have put it).
+ * Staging batch t+2 before waiting for learn step t keeps a copy queued behind the one in flight, so the
+ * link never idles while the host is between calls.  A later goldq_replay_push* commits anything still
+ * staged first (order is kept).  GOLDQ_EINVAL: nothing staged / two batches staged already. */
+int goldq_replay_stage_packed(goldq_t *h, int64_t n, const void *packed);
+int goldq_replay_commit(goldq_t *h);
 int64_t goldq_replay_len(const goldq_t *h);                  /* Memory.Len() */
 /* Pageable host buffers are consumed before goldq_replay_push returns.  Buffers
  * from goldq_host_alloc (pinned) are copied asynchronously: do not overwrite them

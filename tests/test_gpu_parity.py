@@ -464,6 +464,54 @@ def test_packed_push_equals_unpacked_and_bad_actions_are_rejected():
         hh.close()
 
 
+def test_staged_push_commits_in_order_and_leaves_the_memory_alone_until_then():
+    """goldq_replay_stage_packed starts the copy only; goldq_replay_commit appends the oldest staged batch; a third
+    stage is refused; a later push commits what is still staged first.  The resulting memory (and a learn step and
+    its loss on it) equals three plain pushes; a learn step enqueued BEFORE the commit does not see the batch."""
+    dims, B, N = synth.CARTPOLE, 32, 256
+    data = synth.replay(dims, 180, seed=9)
+    chunks = [[x[lo:lo + 60] for x in data] for lo in (0, 60, 120)]
+    idx = synth.sample_indices(60, B, 1)
+    out = []
+    for staged in (False, True):
+        h = G.Handle(batch_size=B, replay_capacity=N)
+        h.set_params(G.NET_ONLINE, synth.glorot_params(dims, 1)); h.set_params(G.NET_TARGET, synth.glorot_params(dims, 2))
+        bufs = [h.pack(*c) for c in chunks]
+        if staged:
+            h.replay_push_packed(60, bufs[0].ctypes.data)
+            h.replay_stage_packed(60, bufs[1].ctypes.data)
+            assert h.replay_len() == 60
+            h.learn(idx)                              # before the commit: trains on the first batch only
+            h.replay_stage_packed(60, bufs[2].ctypes.data)
+            with pytest.raises(G.GoldqError) as e:
+                h.replay_stage_packed(60, bufs[0].ctypes.data)
+            assert e.value.code == G.EINVAL
+            h.replay_commit()
+            assert h.replay_len() == 120
+            h.replay_commit()
+            assert h.replay_len() == 180
+            with pytest.raises(G.GoldqError) as e:
+                h.replay_commit()
+            assert e.value.code == G.EINVAL
+        else:
+            h.replay_push_packed(60, bufs[0].ctypes.data)
+            h.learn(idx)
+            h.replay_push_packed(60, bufs[1].ctypes.data)
+            h.replay_push_packed(60, bufs[2].ctypes.data)
+        l1 = h.last_loss().copy()
+        h.learn(synth.sample_indices(180, B, 2))
+        out.append((l1, h.last_loss().copy(), h.get_params(G.NET_ONLINE)))
+        # a push with something still staged: order is kept
+        h.replay_stage_packed(60, bufs[0].ctypes.data)
+        h.replay_push_packed(60, bufs[1].ctypes.data)
+        assert h.replay_len() == 256
+        h.sync()
+        h.close()
+    for x, y in zip(out[0], out[1]):
+        np.testing.assert_array_equal(x, y)
+    assert np.isfinite(out[0][0]).all() and out[0][0][0] != out[0][1][0]
+
+
 def test_batched_epsilon_greedy_action():
     """goldq_epsilon_greedy_action: rows that do not explore take the oracle's first-argmax, rows that
     explore take the planned uniform action; epsilon 0 is goldq_greedy_action."""

@@ -53,4 +53,9 @@ timed("learn only (host indices, graph), no sync", lambda i: h.learn_raw(idx_ptr
 timed("learn + last_loss (sync)", lambda i: (h.learn_raw(idx_ptr), h.last_loss()))
 timed("learn, push next, last_loss (bench.py's e2e step)", lambda i: (h.learn_raw(idx_ptr), h.replay_push_packed(B, bufs[(i + 1) & 1]), h.last_loss()))
 timed("push next, learn, last_loss", lambda i: (h.replay_push_packed(B, bufs[(i + 1) & 1]), h.learn_raw(idx_ptr), h.last_loss()))
+timed("learn, push next, NO per-step sync", lambda i: (h.learn_raw(idx_ptr), h.replay_push_packed(B, bufs[(i + 1) & 1])))
+timed("learn (device sampler), push next, last_loss", lambda i: (h.learn(None, seed=i), h.replay_push_packed(B, bufs[(i + 1) & 1]), h.last_loss()))
+timed("learn, push next, sync()", lambda i: (h.learn_raw(idx_ptr), h.replay_push_packed(B, bufs[(i + 1) & 1]), h.sync()))
+h.replay_stage_packed(B, bufs[0])
+timed("learn, commit, stage next-but-one, last_loss", lambda i: (h.learn_raw(idx_ptr), h.replay_commit(), h.replay_stage_packed(B, bufs[(i + 1) & 1]), h.last_loss()))
 h.close()
