@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgoldq.so")
+# GOLDQ_LIB: another build of the same library (diagnostics: lib/libgoldq_trace.so from `make trace`)
+LIB_PATH = os.environ.get("GOLDQ_LIB") or os.path.join(_HERE, "lib", "libgoldq.so")
 
 OK, EINVAL, ECUDA, ENOTREADY, EUNSUPPORTED, ENCCL = 0, -1, -2, -3, -4, -5
 NET_ONLINE, NET_TARGET = 0, 1
@@ -18,7 +19,7 @@ SOLVER_ADAM, SOLVER_RMSPROP = 0, 1
 PREC_FP32, PREC_BF16 = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_NARROW, PATH_WIDE, PATH_CONV = 0, 1, 2, 3, 4
 ARCH_MLP, ARCH_ATARI_CONV = 0, 1
-DBG_Q_ONLINE, DBG_Q_TARGET, DBG_TD, DBG_GRADS, DBG_INDICES, DBG_BATCH_S, DBG_BATCH_A, DBG_FF_STAMPS = range(8)
+DBG_Q_ONLINE, DBG_Q_TARGET, DBG_TD, DBG_GRADS, DBG_INDICES, DBG_BATCH_S, DBG_BATCH_A, DBG_FF_STAMPS, DBG_TRACE = range(9)
 ABI_VERSION = 2
 
 # every symbol include/goldq.h declares (tests/test_abi.py checks header <-> list <-> .so)
@@ -392,6 +393,7 @@ class Handle:
             DBG_TD: ((RB,), np.float32), DBG_GRADS: ((self.R * self.P,), np.float32),
             DBG_INDICES: ((RB,), np.int32), DBG_BATCH_S: ((RB, self.D), np.float32),
             DBG_BATCH_A: ((RB,), np.int32), DBG_FF_STAMPS: ((self.B // 128 * 2, 96), np.int64),
+            DBG_TRACE: ((4 + (1 << 17) * 12,), np.uint64),
         }[what]
         out = np.empty(shape, dt)
         self._ck(self._L.goldq_debug_fetch(self._h, what, out.ctypes.data, out.nbytes))

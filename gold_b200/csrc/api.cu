@@ -963,7 +963,9 @@ goldq_t *goldq_create(const goldq_config_t *cfg)
 
     if (cfg->stream) h->st = (cudaStream_t)cfg->stream;
     else {
-        e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, getenv("GOLDQ_PRIO") ? hi : 0);
         if (e != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
         h->own_stream = true;
     }
@@ -1808,11 +1810,15 @@ int goldq_debug_fetch(goldq_t *h, int what, void *out, int64_t out_bytes)
     case GOLDQ_DBG_FF_STAMPS:
         if (h->wide) src = wide_ff_stamps(h->wide, &bytes);
         break;
+    case GOLDQ_DBG_TRACE:
+        if (h->wide) src = wide_trace(h->wide, &bytes);
+        break;
     default: return fail(h, GOLDQ_EINVAL, "debug_fetch: unknown selector");
     }
     if (!src) return fail(h, GOLDQ_EINVAL, "debug_fetch: not available on this path / before any step");
     if ((size_t)out_bytes < bytes) return fail(h, GOLDQ_EINVAL, "debug_fetch: buffer too small");
     CK(h, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, h->st));
+    if (what == GOLDQ_DBG_TRACE) wide_trace_reset(h->wide, h->st);      // the next fetch starts a new log
     CK(h, cudaStreamSynchronize(h->st));
     if (what == GOLDQ_DBG_Q_TARGET && !narrow) {
         // rows of terminal events are never evaluated by the reference (agent.go:138); report 0

@@ -49,7 +49,63 @@ constexpr int GEMM_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, war
 enum { MODE_KK = 0, MODE_MM = 1, MODE_MK = 2, MODE_KM = 3 };
 enum { EPI_BIAS_RELU_BF16 = 0, EPI_BIAS_F32 = 1, EPI_MASK_BF16 = 2, EPI_F32_SLICE = 3 };
 
+// ---- block trace (diagnostic, GOLDQ_TRACE=1 at create; tools/trace_step.py) ---------------------------------
+// Thread 0 of every block of the step's kernels appends {kernel id, block, globaltimer at entry and exit} to a log:
+// the poor man's timeline (no nsys in this image) of a graph-replayed step with its parallel branches.
+// c_trace == nullptr (the default): one constant-bank load and a predicated-off branch per block.
+constexpr int TRACE_MARKS = 8;
+struct TraceRec { unsigned long long t0, t1; int id, block; unsigned long long pad_; unsigned long long mark[TRACE_MARKS]; };
+constexpr int TRACE_CAP = 1 << 17;
+#ifndef GOLDQ_TRACE_BUILD
+struct BlockTrace {      // the product build: nothing (`make trace` builds libgoldq_trace.so with the real one)
+    __device__ __forceinline__ explicit BlockTrace(int, unsigned long long * = nullptr) {}
+};
+#define TRACE_MARKS_DECL
+#define TRACE_MARKS_PTR nullptr
+#define TRACE_MARK(i) do { } while (0)
+#else
+__constant__ unsigned long long *c_trace = nullptr;      // [0] = record counter, records start at 32 bytes
+__device__ __forceinline__ unsigned long long trace_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// optional in-kernel marks: any thread stores globaltimer into the block's shared array; thread 0 copies them out
+#define TRACE_MARKS_DECL __shared__ unsigned long long tr_marks_[TRACE_MARKS];
+#define TRACE_MARKS_PTR tr_marks_
+#define TRACE_MARK(i) do { if (c_trace != nullptr) tr_marks_[i] = trace_now(); } while (0)
+struct BlockTrace {
+    unsigned long long t0;
+    unsigned long long *marks;
+    int id;
+    __device__ __forceinline__ explicit BlockTrace(int id_, unsigned long long *marks_ = nullptr) : t0(0), marks(marks_), id(id_)
+    {
+        if (c_trace != nullptr && threadIdx.x == 0) {
+            t0 = trace_now();
+            if (marks)
+                for (int i = 0; i < TRACE_MARKS; i++) marks[i] = 0;
+        }
+    }
+    __device__ __forceinline__ ~BlockTrace()
+    {
+        if (t0) {
+            const unsigned long long slot = atomicAdd(c_trace, 1ull);
+            if (slot < (unsigned long long)TRACE_CAP) {
+                TraceRec *r = reinterpret_cast<TraceRec *>(c_trace + 4) + slot;
+                r->t0 = t0; r->t1 = trace_now(); r->id = id;
+                r->block = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+                r->pad_ = 0;
+                for (int i = 0; i < TRACE_MARKS; i++) r->mark[i] = marks ? marks[i] : 0;
+            }
+        }
+    }
+};
+#endif
+enum { TR_GATHER = 1, TR_FORWARD, TR_TD, TR_DW3, TR_DW2, TR_DX, TR_COLSUM, TR_DW1, TR_UPDATE, TR_OTHER };
+
 struct GemmArgs {
+    int trace_id;         // TR_* (diagnostic)
     int M, N, K;          // logical problem (K = full reduction length)
     int k_per_split;      // multiple of BK
     int nsplit;           // blockIdx.z = problem * nsplit + split
@@ -72,6 +128,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1,
                  const GemmArgs g)
 {
+    TRACE_MARKS_DECL
+    BlockTrace trace_(g.trace_id, TRACE_MARKS_PTR);
     // bf16 outputs leave through shared memory + TMA store (full 128-byte lines; rows and
     // columns outside the tensor are clipped by the hardware); tmC* = box {64 cols, 128 rows}
     constexpr bool TMA_OUT = (EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_MASK_BF16);
@@ -123,6 +181,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_acc = tmem_base_slot;
     pdl_wait();                  // operands / bias / mask come from the previous kernels
+    if (threadIdx.x == 0) TRACE_MARK(0);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -162,6 +221,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t ph = (kb / STAGES) & 1;
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
+            if (kb == 0 && lane == 0) TRACE_MARK(1);
             if (elect_one()) {
                 const uint32_t aaddr = smem_u32(smem + s * STAGE_BYTES), baddr = aaddr + A_BYTES;
 #pragma unroll
@@ -183,6 +243,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             __syncwarp();
         }
+        if (lane == 0) TRACE_MARK(2);
     } else {
         // ===== epilogue: TMEM -> registers -> global =====
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
@@ -199,6 +260,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_wait(&tmem_full_bar, 0);
             tc_fence_after();
         }
+        if (threadIdx.x == 64) TRACE_MARK(3);
+        // fp32 split-K slices of full tiles leave through shared memory: the tile is staged in the (idle) operand ring
+        // with the 16-byte chunks of a row XOR-swizzled by the row, then every warp writes whole 512-byte rows.  (Stored
+        // straight from the accumulator registers, a warp's store instruction touched 32 different rows, 16 bytes each.)
+        constexpr bool SLICE_STAGED = (EPI == EPI_F32_SLICE) && BN == 128 && STAGES * STAGE_BYTES >= BM * BN * 4;
+        const bool slice_staged = SLICE_STAGED && n0 + BN <= g.n_store && m0 + BM <= g.M && (g.ldo & 3) == 0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
@@ -254,6 +321,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         const int c = col0 + j;
                         if (c < g.n_store) out_f32[(size_t)row * g.ldo + c] = __uint_as_float(r[j]) + s_bias[c0 + j];
                     }
+                } else if (SLICE_STAGED && slice_staged) {
+                    const int rt = q * 32 + lane;
+                    uint8_t *dst = smem + rt * (BN * 4);
+#pragma unroll
+                    for (int v = 0; v < 8; v++)
+                        *reinterpret_cast<uint4 *>(dst + ((((c0 >> 2) + v) ^ (rt & 7)) << 4)) =
+                            make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
                 } else {  // EPI_F32_SLICE
                     float *o = out_f32 + (size_t)split * g.slice_stride + (size_t)row * g.ldo + col0;
                     if (col0 + 32 <= g.n_store && (g.ldo & 3) == 0) {
@@ -270,6 +344,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
             }
         }
+        if (SLICE_STAGED && slice_staged) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // warp w of the four writes rows w, w + 4, ...: lane = 16-byte chunk of the 512-byte row
+            float *o = out_f32 + (size_t)split * g.slice_stride + (size_t)m0 * g.ldo + n0;
+            const int ew = warp - 2;
+#pragma unroll 8
+            for (int rr = ew; rr < BM; rr += 4) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(smem + rr * (BN * 4) + ((lane ^ (rr & 7)) << 4));
+                *reinterpret_cast<uint4 *>(o + (size_t)rr * g.ldo + lane * 4) = v;
+            }
+        }
+        if (threadIdx.x == 64) TRACE_MARK(4);
         if (TMA_OUT) {
             fence_proxy_async_smem();
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -324,6 +410,10 @@ struct FFArgs {
     __nv_bfloat16 *h1, *h2;      // (unused)
     int net0;                    // network of blockIdx.y == 0 (predict launches one network: grid.y = 1)
     int keep_h;                  // store the online network's H1 / H2 for the backward pass (learn step) or not (predict)
+    int late_trigger;            // release the dependent grid from the epilogue instead of the prologue
+    uint32_t *maskbits[2];       // [layer]: Rectify masks of the online network, one bit per unit, [B][FF_H / 32] words; word w
+                                 // covers units 32 w .. 32 w + 31: bit m = unit 32 w + 2 m, bit 16 + m = unit 32 w + 2 m + 1
+                                 // (even units in the low half, odd units in the high half).  The backward pass reads these instead of the sign bits of H.
     long long *stamps;           // diagnostic (GOLDQ_FF_STAMPS): [CTAs][FF_NSTAMPS] clock64 values, else nullptr
 };
 
@@ -336,6 +426,7 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
                   const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmH2,
                   const FFArgs g)
 {
+    BlockTrace trace_(TR_FORWARD);
     constexpr uint32_t X_BYTES = KD * FF_BOX;
     constexpr uint32_t IDESC_256 = make_idesc_bf16(BM, 256, false, true);
     constexpr uint32_t IDESC_64 = make_idesc_bf16(BM, 64, false, true);
@@ -679,6 +770,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                    const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmH2,
                    const FFArgs g)
 {
+    BlockTrace trace_(TR_FORWARD);
     constexpr uint32_t X_BYTES = KD * FF_BOX;
     constexpr uint32_t IDESC_256 = make_idesc_bf16(256, 256, false, true);
     constexpr uint32_t IDESC_128 = make_idesc_bf16(256, 128, false, true);
@@ -724,7 +816,10 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_pair(&tmem_base_slot, 512);
-    pdl_launch_dependents();
+    // (the dependent grid -- TD/dZ2 -- is released late, from the epilogue: released here, its blocks would sit on the
+    // idle SMs from the start, and the blocks that do not fit stall the block scheduler's queue, so that the NEXT
+    // step's gather on the side branch cannot run under this kernel: tools/trace_step.py)
+    if (!g.late_trigger) pdl_launch_dependents();
     tc_fence_before();
     cluster_sync();          // both CTAs' barriers are initialised and both TMEM allocations exist
     tc_fence_after();
@@ -861,12 +956,14 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
             const int cbase = half * 256 + cg * 128;                 // first column of this warp's four chunks
             const float *bias = s_bias + layer * FF_H + cbase;
             uint32_t r[2][32];
+            uint32_t mw[4];
             tmem_ld_32x32(tq + (uint32_t)cbase, r[0]);
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 tmem_ld_wait();
                 if (c < 3) tmem_ld_32x32(tq + (uint32_t)(cbase + 32 * (c + 1)), r[(c + 1) & 1]);
                 uint32_t packed[16];
+                uint32_t mlo = 0u, mhi = 0u;
 #pragma unroll
                 for (int jj = 0; jj < 32; jj += 4) {
                     const float4 bv = *reinterpret_cast<const float4 *>(bias + 32 * c + jj);
@@ -876,7 +973,12 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                     p1 = __hmax2(p1, neg0);
                     packed[jj >> 1] = *reinterpret_cast<uint32_t *>(&p0);
                     packed[(jj >> 1) + 1] = *reinterpret_cast<uint32_t *>(&p1);
+                    // sign bits (= Rectify mask) of the four units, shifted in from the top: after the eight rounds
+                    // mlo / mhi hold the even / odd units of the chunk in their upper 16 bits
+                    mlo = (mlo >> 2) | ((packed[jj >> 1] << 15) & 0x40000000u) | ((packed[(jj >> 1) + 1] << 16) & 0x80000000u);
+                    mhi = (mhi >> 2) | ((packed[jj >> 1] >> 1) & 0x40000000u) | (packed[(jj >> 1) + 1] & 0x80000000u);
                 }
+                mw[c] = (mlo >> 16) | (mhi & 0xffff0000u);     // bits 0..15: units 0, 2, .. 30; bits 16..31: units 1, 3, .. 31
                 const int c0 = cbase + 32 * c;
                 uint8_t *dst = sH + (c0 >> 6) * FF_BOX + rt * 128;
                 const int ch0 = (c0 & 63) >> 3;
@@ -885,6 +987,9 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                     *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
                         make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
             }
+            if (net == 0 && g.keep_h && m0 + rt < g.B)
+                *reinterpret_cast<uint4 *>(g.maskbits[layer] + (size_t)(m0 + rt) * (FF_H / 32) + (cbase >> 5)) =
+                    make_uint4(mw[0], mw[1], mw[2], mw[3]);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc_free_leader0 + (uint32_t)half * 8u);
@@ -905,6 +1010,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
 
         // ---- layer 3: Q = acc + b3 -> fp32 [B][A] (A <= 32: one chunk), staged in the idle weight ring
         // and copied out coalesced (the rows of a slab are contiguous in Q)
+        if (g.late_trigger && et == 0) pdl_launch_dependents();
         if (cg == 0) {
             mbar_wait_bounded<false>(&acc_full[0], 0);          // third completion of acc_full[0]: parity 0 again
             tc_fence_after();
@@ -971,11 +1077,14 @@ constexpr uint32_t PG_STAGE_BYTES = 32768;      // A [128 x 64] + this CTA's hal
 constexpr int PG_THREADS = 320;                 // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
 
 struct PairGemmArgs {
+    int trace_id;                 // TR_* (diagnostic)
+    int late_trigger;             // release the dependent grid after the main loop instead of in the prologue
     int M, N, K;                  // logical problem; K = full reduction length
     int k_per_split;              // multiple of 64
     // PG_DX
     __nv_bfloat16 *out_bf16;      // (unused: the tile leaves by TMA store through tmC)
-    const __nv_bfloat16 *mask_src;   // [M][ldo], sign bit set <=> masked
+    const __nv_bfloat16 *mask_src;   // [M][ldo], sign bit set <=> masked (used when mask_bits is null)
+    const uint32_t *mask_bits;       // [M][N / 32] mask words of the fused forward (FFArgs::maskbits)
     float *colsum;                // [M / 128][N] column sums of the stored (rounded) tile rows
     // PG_DW
     float *out_f32;               // [nsplit][M][ldo]
@@ -988,6 +1097,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PG_THREADS, 2)
 pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const PairGemmArgs g)
 {
+    TRACE_MARKS_DECL
+    BlockTrace trace_(g.trace_id, TRACE_MARKS_PTR);
     constexpr bool MN = (KIND == PG_DW);          // both operands MN-major (A [K][M], B [K][N]) or both K-major
     constexpr uint32_t IDESC = make_idesc_bf16(256, 256, MN, MN);
     constexpr uint16_t BOTH = 3;
@@ -1013,12 +1124,13 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_pair(&tmem_base_slot, 256);
-    pdl_launch_dependents();
+    if (!g.late_trigger) pdl_launch_dependents();
     tc_fence_before();
     cluster_sync();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
     pdl_wait();
+    if (threadIdx.x == 0) TRACE_MARK(0);
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs) =====
@@ -1053,6 +1165,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t ph = (kb / PG_STAGES) & 1;
                 mbar_wait_bounded<false>(&full_bar[s], ph);
                 tc_fence_after();
+                if (kb == 0 && lane == 0) TRACE_MARK(1);
                 if (elect_one()) {
                     const uint32_t aaddr = smem_u32(smem + s * PG_STAGE_BYTES), baddr = aaddr + 16384;
 #pragma unroll
@@ -1066,6 +1179,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 __syncwarp();
             }
+            if (lane == 0) TRACE_MARK(2);
         }
     } else {
         // ===== epilogue (both CTAs, own 128 rows x 256 columns) =====
@@ -1076,30 +1190,50 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
         const int cbase = cg * 128;                        // this warp's four 32-column chunks
         if (KIND == PG_DX) {
-            // the ReLU mask (sign bits of H1) of this thread's 128 columns, one 32-column chunk ahead of its use;
-            // the first chunk's loads are issued before the accumulator is ready
-            uint4 mk[2][4];
-            const uint4 *mp = reinterpret_cast<const uint4 *>(g.mask_src + (size_t)row * g.ldo + n0 + cbase);
+            // the ReLU mask (sign bits of H1) of this thread's 128 columns, compressed to one bit per column and loaded
+            // WHILE THE MAIN LOOP RUNS (these warps are idle until the accumulator is ready).  The first version
+            // fetched the mask one 32-column chunk ahead of its use: every chunk then waited a whole L2 round trip
+            // (in-kernel marks, tools/trace_step.py: 5.7 us for the four chunks -- more than the main loop).
+            uint32_t mbits[4] = {0u, 0u, 0u, 0u};
+            if (g.mask_bits) {       // one 16-byte load: the four mask words of this thread's 128 columns
+                if (row < g.M) {
+                    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(g.mask_bits + (size_t)row * (g.N >> 5) + ((n0 + cbase) >> 5)));
+                    mbits[0] = t.x; mbits[1] = t.y; mbits[2] = t.z; mbits[3] = t.w;
+                }
+            } else {
+                const uint4 *mp = reinterpret_cast<const uint4 *>(g.mask_src + (size_t)row * g.ldo + n0 + cbase);
 #pragma unroll
-            for (int v = 0; v < 4; v++) mk[0][v] = (row < g.M) ? __ldg(mp + v) : make_uint4(0, 0, 0, 0);
+                for (int hb = 0; hb < 2; hb++) {             // two batches of eight 16-byte loads
+                    uint4 t[8];
+#pragma unroll
+                    for (int v = 0; v < 8; v++) t[v] = (row < g.M) ? __ldg(mp + 8 * hb + v) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int v = 0; v < 8; v++) {            // same word layout as the forward's (FFArgs::maskbits)
+                        const uint32_t ev = ((t[v].x >> 15) & 1u) | (((t[v].y >> 15) & 1u) << 1) | (((t[v].z >> 15) & 1u) << 2) |
+                                            (((t[v].w >> 15) & 1u) << 3);
+                        const uint32_t od = (t[v].x >> 31) | ((t[v].y >> 31) << 1) | ((t[v].z >> 31) << 2) | ((t[v].w >> 31) << 3);
+                        const int sh = ((8 * hb + v) & 3) * 4;
+                        mbits[(8 * hb + v) >> 2] |= (ev << sh) | (od << (16 + sh));
+                    }
+                }
+            }
             if (nkb > 0) mbar_wait_bounded<false>(&acc_full, 0);
             tc_fence_after();
+            // the dependent grid (dW1) is released when the main loop is over: released in the prologue, its CTAs held
+            // their shared memory idle for the whole of this kernel while dW2's CTAs waited for a slot
+            if (g.late_trigger && et == 0) pdl_launch_dependents();
+            if (et == 0) TRACE_MARK(3);
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 uint32_t r[32];
                 tmem_ld_32x32(tq + (uint32_t)(cbase + 32 * c), r);
-                if (c < 3) {
-#pragma unroll
-                    for (int v = 0; v < 4; v++) mk[(c + 1) & 1][v] = (row < g.M) ? __ldg(mp + 4 * (c + 1) + v) : make_uint4(0, 0, 0, 0);
-                }
                 tmem_ld_wait();
                 uint32_t packed[16];
+                const uint32_t mb = mbits[c];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const uint4 m4 = mk[c & 1][j >> 3];
-                    const uint32_t mm = ((j >> 1) & 3) == 0 ? m4.x : (((j >> 1) & 3) == 1 ? m4.y : (((j >> 1) & 3) == 2 ? m4.z : m4.w));
-                    const float v0 = (mm & 0x8000u) ? 0.f : __uint_as_float(r[j]);
-                    const float v1 = (mm & 0x80000000u) ? 0.f : __uint_as_float(r[j + 1]);
+                    const float v0 = ((mb >> (j >> 1)) & 1u) ? 0.f : __uint_as_float(r[j]);
+                    const float v1 = ((mb >> (16 + (j >> 1))) & 1u) ? 0.f : __uint_as_float(r[j + 1]);
                     __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
                     packed[j >> 1] = *reinterpret_cast<uint32_t *>(&pk);
                 }
@@ -1116,23 +1250,53 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             fence_proxy_async_smem();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et == 0) {
+                TRACE_MARK(4);
                 for (int b = 0; b < 4; b++) tma_store_2d(&tmC, smem + b * 16384, n0 + 64 * b, m0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-            // db1 partials of this 128-row slab: warp w < 4 sums box w, lane = one bf16 pair of the 64-column row
-            if (et < 128) {
-                const int bx = et >> 5;
+            // db1 partials of this 128-row slab, all eight warps: warp = (box of 64 columns, half of the rows); a lane
+            // owns one 16-byte chunk (8 columns) of every fourth row of its half, so that a warp reads 512 contiguous
+            // bytes per step; the four row phases are folded by shuffles, the two halves through shared memory --
+            // every sum in a fixed order.
+            {
+                const int ew = et >> 5, bx = ew & 3, hf = ew >> 2;
                 const uint8_t *box = smem + bx * 16384;
-                float sx = 0.f, sy = 0.f;
-#pragma unroll 8
-                for (int rr = 0; rr < BM; rr++) {
-                    const uint32_t wv = *reinterpret_cast<const uint32_t *>(box + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
-                    if (m0 + rr < g.M) { sx += __uint_as_float(wv << 16); sy += __uint_as_float(wv & 0xffff0000u); }
+                const int ro = lane >> 3, ch = lane & 7;
+                float acc[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc[u] = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < 16; i++) {
+                    const int rr = 64 * hf + 4 * i + ro;
+                    const uint4 wv = *reinterpret_cast<const uint4 *>(box + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                    if (m0 + rr < g.M) {
+                        acc[0] += __uint_as_float(wv.x << 16); acc[1] += __uint_as_float(wv.x & 0xffff0000u);
+                        acc[2] += __uint_as_float(wv.y << 16); acc[3] += __uint_as_float(wv.y & 0xffff0000u);
+                        acc[4] += __uint_as_float(wv.z << 16); acc[5] += __uint_as_float(wv.z & 0xffff0000u);
+                        acc[6] += __uint_as_float(wv.w << 16); acc[7] += __uint_as_float(wv.w & 0xffff0000u);
+                    }
                 }
-                float2 *cs = reinterpret_cast<float2 *>(g.colsum + (size_t)blockIdx.x * g.N + n0 + bx * 64 + lane * 2);
-                *cs = make_float2(sx, sy);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], 8);
+                    acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], 16);
+                }
+                float *fold = reinterpret_cast<float *>(smem + 4 * 16384);     // [4 boxes][64 columns], behind the staged tile
+                if (hf == 1 && ro == 0) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) fold[bx * 64 + ch * 8 + u] = acc[u];
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (hf == 0 && ro == 0) {
+                    float *cs = g.colsum + (size_t)blockIdx.x * g.N + n0 + bx * 64 + ch * 8;
+                    const float *fo = fold + bx * 64 + ch * 8;
+                    *reinterpret_cast<float4 *>(cs) = make_float4(acc[0] + fo[0], acc[1] + fo[1], acc[2] + fo[2], acc[3] + fo[3]);
+                    *reinterpret_cast<float4 *>(cs + 4) = make_float4(acc[4] + fo[4], acc[5] + fo[5], acc[6] + fo[6], acc[7] + fo[7]);
+                }
             }
+            if (et == 0) TRACE_MARK(5);
             if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (et == 0) TRACE_MARK(6);
         } else {
             if (nkb > 0) mbar_wait_bounded<false>(&acc_full, 0);
             tc_fence_after();
@@ -1316,6 +1480,7 @@ wide_gather_kernel(Replay rp, int D, const int32_t *__restrict__ idx, uint64_t s
                    const StepDev *__restrict__ step, int32_t *__restrict__ idx_out, int B, __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ x2, int32_t *__restrict__ ba,
                    float *__restrict__ br, uint8_t *__restrict__ bdone)
 {
+    BlockTrace trace_(TR_GATHER);
     const int chunks = D >> 2;  // float4 granules per row (D % 8 == 0 is required by the path)
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_launch_dependents();
@@ -1390,10 +1555,11 @@ constexpr int DZ_MAXCH = 2;      // 16-byte chunks per lane and row: H2 <= 32 * 
 __global__ void __launch_bounds__(256)
 wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, const int32_t *__restrict__ act,
                    const float *__restrict__ rew, const uint8_t *__restrict__ done, int B, int H2, int A, StepScalars sc,
-                   const __nv_bfloat16 *__restrict__ h2, const __nv_bfloat16 *__restrict__ w3t /* [32][H2] */,
-                   float *__restrict__ td_out, __nv_bfloat16 *__restrict__ dqT, __nv_bfloat16 *__restrict__ dz2,
+                   const __nv_bfloat16 *__restrict__ h2, const uint32_t *__restrict__ m2bits /* [B][H2/32] or null */,
+                   const __nv_bfloat16 *__restrict__ w3t /* [32][H2] */, float *__restrict__ td_out, __nv_bfloat16 *__restrict__ dqT, __nv_bfloat16 *__restrict__ dz2,
                    float *__restrict__ b2_part /* [blocks][H2] */, float *__restrict__ row_part /* [blocks][A+1] */)
 {
+    BlockTrace trace_(TR_TD);
     extern __shared__ float sm[];            // [8 warps][H2] column sums, then [8][33] row partials
     float *sRow = sm + 8 * H2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1465,14 +1631,23 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
     // ---- dZ2 of the four rows + column sums ----------------------------------------------------------------
     const int nch = H2 >> 3;
     for (int c0 = 0; c0 < nch; c0 += 32 * DZ_MAXCH) {
-        uint4 hv[4][DZ_MAXCH], wv[4][DZ_MAXCH];
+        uint4 wv[4][DZ_MAXCH];
+        uint32_t mk[4][DZ_MAXCH];      // masks of the chunk's 8 units: bit e = unit 2e masked, bit 4 + e = unit 2e + 1 masked
 #pragma unroll
         for (int k = 0; k < 4; k++)
 #pragma unroll
             for (int u = 0; u < DZ_MAXCH; u++) {
                 const int c = c0 + lane + 32 * u;
                 const bool live = c < nch && rw0 + k < B;
-                hv[k][u] = live ? __ldg(reinterpret_cast<const uint4 *>(h2 + (int64_t)(rw0 + k) * H2) + c) : make_uint4(0, 0, 0, 0);
+                if (m2bits) {        // the forward's mask words (FFArgs::maskbits): 4 bytes instead of the 16 bytes of H2
+                    const uint32_t wd = live ? __ldg(m2bits + (int64_t)(rw0 + k) * (H2 >> 5) + (c >> 2)) : 0u;
+                    const int sh = (c & 3) * 4;
+                    mk[k][u] = ((wd >> sh) & 0xfu) | (((wd >> (16 + sh)) & 0xfu) << 4);
+                } else {
+                    const uint4 hv = live ? __ldg(reinterpret_cast<const uint4 *>(h2 + (int64_t)(rw0 + k) * H2) + c) : make_uint4(0, 0, 0, 0);
+                    mk[k][u] = ((hv.x >> 15) & 1u) | (((hv.y >> 15) & 1u) << 1) | (((hv.z >> 15) & 1u) << 2) | (((hv.w >> 15) & 1u) << 3) |
+                               ((hv.x >> 31) << 4) | ((hv.y >> 31) << 5) | ((hv.z >> 31) << 6) | ((hv.w >> 31) << 7);
+                }
                 wv[k][u] = live ? __ldg(reinterpret_cast<const uint4 *>(w3t + (int64_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
@@ -1483,14 +1658,13 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
             for (int e = 0; e < 8; e++) cs[e] = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint32_t hw[4] = {hv[k][u].x, hv[k][u].y, hv[k][u].z, hv[k][u].w};
                 const uint32_t ww[4] = {wv[k][u].x, wv[k][u].y, wv[k][u].z, wv[k][u].w};
                 uint32_t ow[4];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const float w0 = __uint_as_float(ww[e] << 16), w1 = __uint_as_float(ww[e] & 0xffff0000u);
-                    const float z0 = (hw[e] & 0x8000u) ? 0.f : dq4[k] * w0;
-                    const float z1 = (hw[e] & 0x80000000u) ? 0.f : dq4[k] * w1;
+                    const float z0 = ((mk[k][u] >> e) & 1u) ? 0.f : dq4[k] * w0;
+                    const float z1 = ((mk[k][u] >> (4 + e)) & 1u) ? 0.f : dq4[k] * w1;
                     __nv_bfloat162 pk = __floats2bfloat162_rn(z0, z1);
                     ow[e] = *reinterpret_cast<uint32_t *>(&pk);
                     // sum the ROUNDED values so that db2 matches the bf16 operand of dW2 / dX
@@ -1529,6 +1703,7 @@ constexpr int CS_ROWS = 256;
 __global__ void __launch_bounds__(256)
 wide_colsum_kernel(const __nv_bfloat16 *__restrict__ dz, int B, int H, float *__restrict__ part /* [blocks.y][H] */)
 {
+    BlockTrace trace_(TR_COLSUM);
     __shared__ float2 sh[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_launch_dependents();
@@ -1770,6 +1945,7 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
                    const StepDev *__restrict__ step, ShadowPtrs sp, float *__restrict__ loss_out, PeerSet push,
                    unsigned int epoch)
 {
+    BlockTrace trace_(TR_UPDATE);
     // push.world > 0 (data-parallel group over peer memory, FUSE only): the locally reduced gradient is
     // exchanged (dp_exchange*) and the update uses the global sum
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1926,6 +2102,7 @@ struct WideState {
     float *pred_q = nullptr;               // predict: Q [B][A]
     __nv_bfloat16 *h1 = nullptr, *h2 = nullptr, *t1 = nullptr, *t2 = nullptr;
     __nv_bfloat16 *dz2 = nullptr, *dz1 = nullptr, *dqT = nullptr;
+    uint32_t *m1bits = nullptr, *m2bits = nullptr;      // Rectify masks of the online network as bits (fused pair forward only)
     float *q = nullptr, *qt = nullptr, *td = nullptr, *dqv = nullptr;
     float *w1_slices = nullptr, *w2_slices = nullptr, *w3_slices = nullptr, *b1_part = nullptr, *b2_part = nullptr,
           *row_part = nullptr;
@@ -1942,6 +2119,7 @@ struct WideState {
     bool pair_dx = false, pair_dw2 = false;   // backward GEMMs on CTA pairs (pair_gemm_kernel); pair_dx also produces the db1 partials
     int skip = 0;                          // GOLDQ_SKIP bit mask (diagnostic): launches left out of the step, see wide_step
     long long *ff_stamps = nullptr;        // GOLDQ_FF_STAMPS: in-kernel clock stamps of the fused forward (diagnostic)
+    unsigned long long *trace = nullptr;   // GOLDQ_TRACE: block log of the step's kernels (BlockTrace, diagnostic)
     bool ff2 = false;                      // ... on CTA pairs (cta_group::2): needs an even number of 128-row slabs
     bool bn256 = false;                    // 128x256 output tiles for the N = H GEMMs
     std::vector<const char *> prof_names;  // labels of the launches of the last profiled step
@@ -1993,6 +2171,7 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     ok = ok && dmalloc(&w->h1, n * d.H1, err) &&
          dmalloc(&w->h2, n * d.H2, err) && dmalloc(&w->t1, n * d.H1, err) && dmalloc(&w->t2, n * d.H2, err) &&
          dmalloc(&w->dz2, n * d.H2, err) && dmalloc(&w->dz1, n * d.H1, err) && dmalloc(&w->dqT, n * 32, err) &&
+         dmalloc(&w->m1bits, n * (d.H1 / 32 + 1), err) && dmalloc(&w->m2bits, n * (d.H2 / 32 + 1), err) &&
          dmalloc(&w->q, n * d.A, err) && dmalloc(&w->qt, n * d.A, err) && dmalloc(&w->td, n, err) &&
          dmalloc(&w->dqv, n, err);
     if (!ok) { wide_destroy(w); return nullptr; }
@@ -2044,6 +2223,15 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     }
     ok = ok && make_tmap(&w->net[0].tm_w2_k_s4, w->net[0].w2, d.H1, d.H2, d.H2, 32, err);
     ok = ok && make_tmap(&w->net[0].tm_w2_k256, w->net[0].w2, d.H1, d.H2, d.H2, 256, err);
+#ifdef GOLDQ_TRACE_BUILD
+    if (getenv("GOLDQ_TRACE")) {
+        const size_t n = 4 + (size_t)TRACE_CAP * (sizeof(TraceRec) / 8);
+        if (dmalloc(&w->trace, n, err)) {
+            cudaMemset(w->trace, 0, n * 8);
+            cudaMemcpyToSymbol(c_trace, &w->trace, sizeof(w->trace));
+        }
+    }
+#endif
     w->ff = getenv("GOLDQ_NO_FF") == nullptr && d.H1 == FF_H && d.H2 == FF_H && (d.D == 64 || d.D == 128) && d.A <= W3_PAD;
     w->ff2 = w->ff && getenv("GOLDQ_NO_FF2") == nullptr && B % (2 * BM) == 0;
     // diagnostic only (results are garbage): leave launches out of the step to read their share of the
@@ -2076,9 +2264,16 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     ok = ok && make_tmap(&w->tm_dqT_b, w->dqT, 32, B, B, 32, err);
     if (!ok) { wide_destroy(w); return nullptr; }
     w->pdl = getenv("GOLDQ_NO_PDL") == nullptr;
-    cudaStreamCreateWithFlags(&w->s1, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&w->s2, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&w->s3, cudaStreamNonBlocking);
+    {
+        // GOLDQ_PRIO (experiment): the side branches (dW2 | dW3 | next step's gather) at the lowest priority, so that the
+        // block scheduler prefers the critical chain dX -> dW1 on the learn stream when slots free up
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const int side = getenv("GOLDQ_PRIO") ? lo : 0;
+        cudaStreamCreateWithPriority(&w->s1, cudaStreamNonBlocking, side);
+        cudaStreamCreateWithPriority(&w->s2, cudaStreamNonBlocking, side);
+        cudaStreamCreateWithPriority(&w->s3, cudaStreamNonBlocking, side);
+    }
     cudaEvent_t *evs[] = {&w->ev_dz2, &w->ev_dx, &w->ev_s1, &w->ev_s2, &w->ev_fork, &w->ev_gather};
     for (cudaEvent_t *e : evs) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
     return w;
@@ -2097,7 +2292,7 @@ void wide_destroy(WideState *w)
         for (void *q : p)
             if (q) cudaFree(q);
     }
-    void *p[] = {w->pred.x, w->pred_q, w->ff_stamps, w->h1, w->h2, w->t1, w->t2, w->dz2, w->dz1, w->dqT, w->q, w->qt, w->td, w->dqv, w->w1_slices, w->w2_slices, w->w3_slices, w->b1_part, w->b2_part, w->row_part};
+    void *p[] = {w->pred.x, w->pred_q, w->ff_stamps, w->m1bits, w->m2bits, w->trace, w->h1, w->h2, w->t1, w->t2, w->dz2, w->dz1, w->dqT, w->q, w->qt, w->td, w->dqv, w->w1_slices, w->w2_slices, w->w3_slices, w->b1_part, w->b2_part, w->row_part};
     for (void *q : p)
         if (q) cudaFree(q);
     if (w->s1) cudaStreamDestroy(w->s1);
@@ -2244,8 +2439,11 @@ static cudaError_t launch_fused_forward(WideState *w, WideState::BatchSet &bt, c
     fa.bias[1][0] = theta_t + o.b1; fa.bias[1][1] = theta_t + o.b2; fa.bias[1][2] = theta_t + o.b3;
     fa.q[0] = w->q; fa.q[1] = w->qt;
     fa.stamps = only_net < 0 ? w->ff_stamps : nullptr;
+    static const bool early = getenv("GOLDQ_EARLY_TRIGGER") != nullptr;      // diagnostic: round-2's first placement
+    fa.late_trigger = early ? 0 : 1;
     fa.net0 = only_net < 0 ? 0 : only_net;
     fa.keep_h = only_net < 0 ? 1 : 0;
+    fa.maskbits[0] = w->m1bits; fa.maskbits[1] = w->m2bits;
     if (only_net >= 0) fa.q[only_net] = q_out;
     dim3 grid((B + BM - 1) / BM, only_net < 0 ? 2 : 1);
     if (w->ff2 && d.D == 128)
@@ -2357,6 +2555,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     }
     WideNet &on = w->net[0], &tg = w->net[1];
     GemmArgs g{};
+    g.trace_id = TR_FORWARD;
     if (w->skip & 2) {
     } else if (w->ff) {
         // forward of both networks, all three layers, one launch
@@ -2394,50 +2593,67 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     launches += 3;
     }
 
+    // the pair forward leaves the online network's Rectify masks as bit words: the backward pass reads those instead of
+    // the sign bits of H1 / H2 (8 MB each)
+    const bool bits = w->ff && w->ff2 && !(w->skip & 2) && getenv("GOLDQ_NO_MASKBITS") == nullptr;
     if (!(w->skip & 4))
     WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), sizeof(float) * (8 * d.H2 + 8 * 33), st, pdl, w->q, w->qt, bt.ba, bt.br,
-                 bt.bdone, B, d.H2, d.A, s.sc, w->h2, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part));
+                 bt.bdone, B, d.H2, d.A, s.sc, w->h2, bits ? w->m2bits : nullptr, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part));
     mark("TD + dZ2 + db2/db3 (K3)");
     launches += 1;
 
     // backward: three independent chains after dZ2 —  s1: dW2 | s2: dW3, db1 | st: dX -> dW1
-    if (!one_stream) {
+    // (GOLDQ_DX_FIRST, experiment: dW2 and dW3 start when dX is done instead of next to it)
+    static const bool dx_first = getenv("GOLDQ_DX_FIRST") != nullptr;
+    if (!one_stream && !dx_first) {
         WCK(cudaEventRecord(w->ev_dz2, st));
         WCK(cudaStreamWaitEvent(s1, w->ev_dz2, 0));
         WCK(cudaStreamWaitEvent(s2, w->ev_dz2, 0));
     }
-    // dW3 = H2^T dQ : M = H2, N = 32 (A stored), K = B ; A MN-major (h2 as stored), B = dQ^T K-major
-    g = GemmArgs{};
-    g.M = d.H2; g.N = 32; g.K = B; g.k_per_split = w->kps3;
-    g.out_f32 = w->w3_slices; g.ldo = d.A; g.n_store = d.A; g.slice_stride = (long long)d.H2 * d.A;
-    if (!(w->skip & 8))
-    WCK((launch_gemm<MODE_MK, 32, EPI_F32_SLICE>(w->tm_h2_mm, w->tm_dqT_b, g, w->ns3, s2)));
-    mark("dW3 (tcgen05)");
-    // dW2 = H1^T dZ2 : M = H1, N = H2, K = B
-    g = GemmArgs{};
-    g.M = d.H1; g.N = d.H2; g.K = B; g.k_per_split = w->kps2;
-    g.out_f32 = w->w2_slices; g.ldo = d.H2; g.n_store = d.H2; g.slice_stride = (long long)d.H1 * d.H2;
-    if (w->skip & 16) {
-    } else if (w->pair_dw2) {
-        PairGemmArgs pg{};
-        pg.M = d.H1; pg.N = d.H2; pg.K = B; pg.k_per_split = w->kps2;
-        pg.out_f32 = w->w2_slices; pg.ldo = d.H2; pg.slice_stride = (long long)d.H1 * d.H2;
-        WCK(launch_pair_gemm<PG_DW>(w->tm_h1_mm, w->tm_dz2_mm, w->tm_dz2_mm, pg, w->ns2, s1, false));
-    } else if (w->mc_h1)
-        WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE, 4>(w->tm_h1_mm, w->tm_dz2_mm_s4, g, w->ns2, s1)));
-    else
-        WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, s1)));
-    mark(w->pair_dw2 ? "dW2 split-K, CTA pairs (tcgen05 cta_group::2)" : "dW2 split-K (tcgen05)");
-    if (!one_stream) WCK(cudaEventRecord(w->ev_s1, s1));
+    auto side_gemms = [&]() -> int {
+        // dW3 = H2^T dQ : M = H2, N = 32 (A stored), K = B ; A MN-major (h2 as stored), B = dQ^T K-major
+        g = GemmArgs{};
+        g.trace_id = TR_DW3;
+        g.M = d.H2; g.N = 32; g.K = B; g.k_per_split = w->kps3;
+        g.out_f32 = w->w3_slices; g.ldo = d.A; g.n_store = d.A; g.slice_stride = (long long)d.H2 * d.A;
+        if (!(w->skip & 8))
+        WCK((launch_gemm<MODE_MK, 32, EPI_F32_SLICE>(w->tm_h2_mm, w->tm_dqT_b, g, w->ns3, s2)));
+        mark("dW3 (tcgen05)");
+        // dW2 = H1^T dZ2 : M = H1, N = H2, K = B
+        g = GemmArgs{};
+        g.trace_id = TR_DW2;
+        g.M = d.H1; g.N = d.H2; g.K = B; g.k_per_split = w->kps2;
+        g.out_f32 = w->w2_slices; g.ldo = d.H2; g.n_store = d.H2; g.slice_stride = (long long)d.H1 * d.H2;
+        if (w->skip & 16) {
+        } else if (w->pair_dw2) {
+            PairGemmArgs pg{};
+            pg.trace_id = TR_DW2;
+            pg.M = d.H1; pg.N = d.H2; pg.K = B; pg.k_per_split = w->kps2;
+            pg.out_f32 = w->w2_slices; pg.ldo = d.H2; pg.slice_stride = (long long)d.H1 * d.H2;
+            WCK(launch_pair_gemm<PG_DW>(w->tm_h1_mm, w->tm_dz2_mm, w->tm_dz2_mm, pg, w->ns2, s1, false));
+        } else if (w->mc_h1)
+            WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE, 4>(w->tm_h1_mm, w->tm_dz2_mm_s4, g, w->ns2, s1)));
+        else
+            WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(w->tm_h1_mm, w->tm_dz2_mm, g, w->ns2, s1)));
+        mark(w->pair_dw2 ? "dW2 split-K, CTA pairs (tcgen05 cta_group::2)" : "dW2 split-K (tcgen05)");
+        if (!one_stream) WCK(cudaEventRecord(w->ev_s1, s1));
+        return 0;
+    };
+    if (!dx_first && side_gemms() < 0) return -1;
     // dZ1 = (dZ2 W2^T) * mask1 : M = B, N = H1, K = H2 ; B operand = W2 [H1 rows][H2 cols]
     g = GemmArgs{};
+    g.trace_id = TR_DX;
     g.M = B; g.N = d.H1; g.K = d.H2; g.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
     g.out_bf16 = w->dz1; g.mask_src = w->h1; g.ldo = d.H1; g.n_store = d.H1;
     if (w->skip & 32) {
     } else if (w->pair_dx) {
         PairGemmArgs pg{};
+        pg.trace_id = TR_DX;
         pg.M = B; pg.N = d.H1; pg.K = d.H2; pg.k_per_split = ((d.H2 + BK - 1) / BK) * BK;
         pg.mask_src = w->h1; pg.ldo = d.H1; pg.colsum = w->b1_part;
+        pg.mask_bits = bits ? w->m1bits : nullptr;
+        static const bool early = getenv("GOLDQ_EARLY_TRIGGER") != nullptr;
+        pg.late_trigger = early ? 0 : 1;
         WCK(launch_pair_gemm<PG_DX>(w->tm_dz2_a, on.tm_w2_k, w->tm_dz1_a, pg, 1, st, pdl));
     } else if (w->bn256)
         // one CTA per SM here (B/128 x H1/256 tiles <= SMs): a 4-stage ring (192 KB) instead of 2
@@ -2454,6 +2670,10 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         WCK(cudaEventRecord(w->ev_dx, st));
         WCK(cudaStreamWaitEvent(s2, w->ev_dx, 0));
     }
+    if (dx_first) {
+        if (!one_stream) WCK(cudaStreamWaitEvent(s1, w->ev_dx, 0));      // (s2 waits for ev_dx above)
+        if (side_gemms() < 0) return -1;
+    }
     if (!(w->skip & 64) && !w->pair_dx) {
         dim3 grid((d.H1 + 63) / 64, w->nb1);
         wide_colsum_kernel<<<grid, 256, 0, s2>>>(w->dz1, B, d.H1, w->b1_part);
@@ -2464,10 +2684,14 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     if (!one_stream) WCK(cudaEventRecord(w->ev_s2, s2));
     // dW1 = X^T dZ1 : M = D, N = H1, K = B
     g = GemmArgs{};
+    g.trace_id = TR_DW1;
     g.M = d.D; g.N = d.H1; g.K = B; g.k_per_split = w->kps1;
     g.out_f32 = w->w1_slices; g.ldo = d.H1; g.n_store = d.H1; g.slice_stride = (long long)d.D * d.H1;
+    // (GOLDQ_DW1_NOPDL, experiment: launched programmatically, dW1's CTAs become resident as soon as dX's CTAs have
+    // started and then hold their shared memory idle until dX is done, while dW2's CTAs wait for a slot)
+    static const bool dw1_nopdl = getenv("GOLDQ_DW1_NOPDL") != nullptr;
     if (!(w->skip & 128))
-    WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(bt.tm_x_mm, w->tm_dz1_mm, g, w->ns1, st, nullptr, nullptr, pdl)));
+    WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(bt.tm_x_mm, w->tm_dz1_mm, g, w->ns1, st, nullptr, nullptr, pdl && !dw1_nopdl)));
     mark("dW1 split-K (tcgen05)");
     if (!one_stream) {
         WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
@@ -2509,6 +2733,17 @@ std::string wide_step_kernel_names(WideState *w)
 }
 
 void wide_set_debug(WideState *w, bool on) { w->debug = on; }
+// the block log since the last call: [0] = number of records, records from word 4 on (TraceRec = 4 words)
+const unsigned long long *wide_trace(WideState *w, size_t *bytes)
+{
+    *bytes = w->trace ? (4 + (size_t)TRACE_CAP * (sizeof(TraceRec) / 8)) * 8 : 0;
+    return w->trace;
+}
+void wide_trace_reset(WideState *w, cudaStream_t st)
+{
+    if (w->trace) cudaMemsetAsync(w->trace, 0, 8, st);
+}
+
 const long long *wide_ff_stamps(WideState *w, size_t *bytes)
 {
     *bytes = w->ff_stamps ? (size_t)(w->B / BM) * 2 * FF_NSTAMPS * sizeof(long long) : 0;

@@ -75,6 +75,8 @@ int wide_p2p_chunk_floats(const WideState *w, int world);
 bool wide_p2p_resident(const WideState *w, int *grid, int *resident);
 std::string wide_step_kernel_names(WideState *w);
 void wide_set_debug(WideState *w, bool on);
+const unsigned long long *wide_trace(WideState *w, size_t *bytes);   // nullptr unless GOLDQ_TRACE was set at create time
+void wide_trace_reset(WideState *w, cudaStream_t st);
 const long long *wide_ff_stamps(WideState *w, size_t *bytes);   // nullptr unless GOLDQ_FF_STAMPS was set at create time
 void wide_debug_ptrs(WideState *w, const float **q, const float **qt, const float **td);
 const uint8_t *wide_done_ptr(WideState *w);

@@ -77,6 +77,7 @@ extern "C" {
 #define GOLDQ_DBG_INDICES 4   /* int32[B]    sampled logical indices */
 #define GOLDQ_DBG_BATCH_S 5   /* float[B*D]  gathered states        */
 #define GOLDQ_DBG_BATCH_A 6   /* int32[B]    gathered actions       */
+#define GOLDQ_DBG_TRACE 8     /* uint64[4 + 2^17 * 12]: block log of the wide step's kernels (GOLDQ_TRACE=1 at create; tools/trace_step.py) */
 #define GOLDQ_DBG_FF_STAMPS 7 /* int64[B/128*2][96]: clock64 stamps inside the fused forward (GOLDQ_FF_STAMPS=1 at create) */
 
 typedef struct goldq goldq_t;
