@@ -49,6 +49,16 @@ constexpr int GEMM_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, war
 enum { MODE_KK = 0, MODE_MM = 1, MODE_MK = 2, MODE_KM = 3 };
 enum { EPI_BIAS_RELU_BF16 = 0, EPI_BIAS_F32 = 1, EPI_MASK_BF16 = 2, EPI_F32_SLICE = 3 };
 
+// Loads of data that the PREVIOUS kernel of a programmatic-dependent-launch chain produced (activations, Q, masks, the
+// parameters the update kernel has just written).  They must not be `__ldg` / `const __restrict__` loads: those compile to
+// ld.global.nc, which the compiler treats as invariant and may schedule ABOVE griddepcontrol.wait, i.e. before the producer
+// has finished -- seen in SASS (eight LDG.E.CONSTANT in front of ACQBULK in the TD kernel) and in wrong TD targets / losses.
+// ld.global.cg is an ordinary load for the compiler (it stays behind the wait's memory clobber) and skips the L1 these
+// single-use values do not need.
+template <typename T>
+__device__ __forceinline__ T ld_dep(const T *p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned char ld_dep(const unsigned char *p) { return __ldcg(p); }
+
 // ---- block trace (diagnostic, GOLDQ_TRACE=1 at create; tools/trace_step.py) ---------------------------------
 // Thread 0 of every block of the step's kernels appends {kernel id, block, globaltimer at entry and exit} to a log:
 // the poor man's timeline (no nsys in this image) of a graph-replayed step with its parallel branches.
@@ -253,7 +263,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             // stage this tile's bias once (one coalesced load), while the mainloop runs
             const float *const bias = prob ? g.bias_1 : g.bias;
             for (int t = threadIdx.x - 64; t < BN; t += 128)
-                s_bias[t] = (n0 + t < g.N && n0 + t < g.n_store) ? __ldg(bias + n0 + t) : 0.f;
+                s_bias[t] = (n0 + t < g.N && n0 + t < g.n_store) ? ld_dep(bias + n0 + t) : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         if (nkb > 0) {
@@ -285,7 +295,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         const uint4 *mp = reinterpret_cast<const uint4 *>(g.mask_src + (size_t)row * g.ldo + col0);
 #pragma unroll
                         for (int v = 0; v < 4; v++) {
-                            uint4 t = (col0 + 8 * v < g.n_store) ? __ldg(mp + v) : make_uint4(0, 0, 0, 0);
+                            uint4 t = (col0 + 8 * v < g.n_store) ? ld_dep(mp + v) : make_uint4(0, 0, 0, 0);
                             msk[4 * v] = t.x; msk[4 * v + 1] = t.y; msk[4 * v + 2] = t.z; msk[4 * v + 3] = t.w;
                         }
                     }
@@ -583,8 +593,8 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
 #pragma unroll
         for (int l = 0; l < 2; l++)
 #pragma unroll
-            for (int i = 0; i < 8; i++) bl[l][i] = __ldg(g.bias[net][l] + (i >> 2) * 256 + (cg * 4 + (i & 3)) * 32 + lane);
-        const float b3 = (lane < g.A) ? __ldg(g.bias[net][2] + lane) : 0.f;
+            for (int i = 0; i < 8; i++) bl[l][i] = ld_dep(g.bias[net][l] + (i >> 2) * 256 + (cg * 4 + (i & 3)) * 32 + lane);
+        const float b3 = (lane < g.A) ? ld_dep(g.bias[net][2] + lane) : 0.f;
 
         auto pack_chunk = [&](const uint32_t(&r)[32], float bme, uint32_t(&packed)[16]) {
 #pragma unroll
@@ -929,9 +939,9 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         // biases of the three layers -> shared memory (read back as broadcast float4)
         for (int i = et; i < 2 * FF_H + 32; i += FF_EPI_THREADS) {
             float v = 0.f;
-            if (i < FF_H) v = __ldg(g.bias[net][0] + i);
-            else if (i < 2 * FF_H) v = __ldg(g.bias[net][1] + i - FF_H);
-            else if (i - 2 * FF_H < g.A) v = __ldg(g.bias[net][2] + i - 2 * FF_H);
+            if (i < FF_H) v = ld_dep(g.bias[net][0] + i);
+            else if (i < 2 * FF_H) v = ld_dep(g.bias[net][1] + i - FF_H);
+            else if (i - 2 * FF_H < g.A) v = ld_dep(g.bias[net][2] + i - 2 * FF_H);
             s_bias[i] = v;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -1197,7 +1207,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t mbits[4] = {0u, 0u, 0u, 0u};
             if (g.mask_bits) {       // one 16-byte load: the four mask words of this thread's 128 columns
                 if (row < g.M) {
-                    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(g.mask_bits + (size_t)row * (g.N >> 5) + ((n0 + cbase) >> 5)));
+                    const uint4 t = ld_dep(reinterpret_cast<const uint4 *>(g.mask_bits + (size_t)row * (g.N >> 5) + ((n0 + cbase) >> 5)));
                     mbits[0] = t.x; mbits[1] = t.y; mbits[2] = t.z; mbits[3] = t.w;
                 }
             } else {
@@ -1206,7 +1216,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int hb = 0; hb < 2; hb++) {             // two batches of eight 16-byte loads
                     uint4 t[8];
 #pragma unroll
-                    for (int v = 0; v < 8; v++) t[v] = (row < g.M) ? __ldg(mp + 8 * hb + v) : make_uint4(0, 0, 0, 0);
+                    for (int v = 0; v < 8; v++) t[v] = (row < g.M) ? ld_dep(mp + 8 * hb + v) : make_uint4(0, 0, 0, 0);
 #pragma unroll
                     for (int v = 0; v < 8; v++) {            // same word layout as the forward's (FFArgs::maskbits)
                         const uint32_t ev = ((t[v].x >> 15) & 1u) | (((t[v].y >> 15) & 1u) << 1) | (((t[v].z >> 15) & 1u) << 2) |
@@ -1559,50 +1569,113 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
                    const __nv_bfloat16 *__restrict__ w3t /* [32][H2] */, float *__restrict__ td_out, __nv_bfloat16 *__restrict__ dqT, __nv_bfloat16 *__restrict__ dz2,
                    float *__restrict__ b2_part /* [blocks][H2] */, float *__restrict__ row_part /* [blocks][A+1] */)
 {
-    BlockTrace trace_(TR_TD);
+    TRACE_MARKS_DECL
+    BlockTrace trace_(TR_TD, TRACE_MARKS_PTR);
     extern __shared__ float sm[];            // [8 warps][H2] column sums, then [8][33] row partials
     float *sRow = sm + 8 * H2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rw0 = blockIdx.x * DZ_ROWS + warp * 4;      // this warp's four rows
     pdl_launch_dependents();
     pdl_wait();
-    // ---- TD label of row rw0 + lane (lanes 0..3) ------------------------------------------------------
-    float dqv = 0.f, sq = 0.f;
-    int a = 0;
+    if (threadIdx.x == 0) TRACE_MARK(0);
+    // ---- every global load of the TD phase, and the first dZ2 chunk's, issued up front: ONE L2 round trip for
+    // Q'(s') / Q(s) / action / reward / done, a second one only for the W3 rows picked by the actions (the first
+    // version went row -> action -> Q(s)[a] -> W3 row, three dependent round trips: 2.7 + 3.2 us in the block trace)
+    int a = 0, dn = 0;
+    float rwd = 0.f;
     if (lane < 4 && rw0 + lane < B) {
-        const int b = rw0 + lane;
-        const float *row = qt + (int64_t)b * A;
-        float rv[32];
-#pragma unroll
-        for (int i = 0; i < 32; i++) rv[i] = (i < A) ? __ldg(row + i) : 0.f;
-        a = act[b];
-        const float rwd = rew[b];
-        const int dn = done[b];
-        const float qa = __ldg(q + (int64_t)b * A + a);
-        float t = rwd;
-        if (!dn) {
-            float f = rv[0];
-            bool decided = false;
-#pragma unroll
-            for (int i = 1; i < 32; i++) {
-                if (i < A && !decided) {
-                    const float v = rv[i];
-                    if (isnan(v) || (isinf(v) && v > 0.f)) { f = v; decided = true; }
-                    else if (v > f) f = v;
-                }
-            }
-            t = __fadd_rn(rwd, __fmul_rn(sc.gamma, f));
-        }
-        td_out[b] = t;
-        residual_loss(sc, __fsub_rn(qa, t), sq, dqv);
+        a = ld_dep(act + rw0 + lane);
+        rwd = ld_dep(rew + rw0 + lane);
+        dn = ld_dep(done + rw0 + lane);
     }
-    float dq4[4];
-    int a4[4];
+    float qtv[4], qv[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        dq4[k] = __shfl_sync(0xffffffffu, dqv, k);
-        a4[k] = __shfl_sync(0xffffffffu, a, k);
+        const bool ok = rw0 + k < B && lane < A;
+        qtv[k] = ok ? ld_dep(qt + (int64_t)(rw0 + k) * A + lane) : -INFINITY;
+        qv[k] = ok ? ld_dep(q + (int64_t)(rw0 + k) * A + lane) : 0.f;
     }
+    const int nch = H2 >> 3;
+    uint4 wv[4][DZ_MAXCH];
+    uint32_t mk[4][DZ_MAXCH];      // masks of the chunk's 8 units: bit e = unit 2e masked, bit 4 + e = unit 2e + 1 masked
+    int a4[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) a4[k] = __shfl_sync(0xffffffffu, a, k);
+#ifdef GOLDQ_TRACE_BUILD
+    if (threadIdx.x == 0 && a4[0] >= 0) TRACE_MARK(5);
+#endif
+    // (all loads first, decoding afterwards: decoded inside the load loop, every mask word's shift waited for its own
+    // load -- eight serial L2 round trips, 2.8 us in the block trace)
+    auto load_chunks = [&](int c0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int u = 0; u < DZ_MAXCH; u++) {
+                const int c = c0 + lane + 32 * u;
+                const bool live = c < nch && rw0 + k < B;
+                wv[k][u] = live ? ld_dep(reinterpret_cast<const uint4 *>(w3t + (int64_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
+            }
+        if (m2bits) {            // the forward's mask words (FFArgs::maskbits): 4 bytes instead of the 16 bytes of H2
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int u = 0; u < DZ_MAXCH; u++) {
+                    const int c = c0 + lane + 32 * u;
+                    mk[k][u] = (c < nch && rw0 + k < B) ? ld_dep(m2bits + (int64_t)(rw0 + k) * (H2 >> 5) + (c >> 2)) : 0u;
+                }
+            // (decoded where it is used, below: nothing waits for these loads here)
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint4 hv[DZ_MAXCH];
+#pragma unroll
+                for (int u = 0; u < DZ_MAXCH; u++) {
+                    const int c = c0 + lane + 32 * u;
+                    hv[u] = (c < nch && rw0 + k < B) ? ld_dep(reinterpret_cast<const uint4 *>(h2 + (int64_t)(rw0 + k) * H2) + c) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < DZ_MAXCH; u++)
+                    mk[k][u] = ((hv[u].x >> 15) & 1u) | (((hv[u].y >> 15) & 1u) << 1) | (((hv[u].z >> 15) & 1u) << 2) |
+                               (((hv[u].w >> 15) & 1u) << 3) | ((hv[u].x >> 31) << 4) | ((hv[u].y >> 31) << 5) |
+                               ((hv[u].z >> 31) << 6) | ((hv[u].w >> 31) << 7);
+            }
+        }
+    };
+    load_chunks(0);
+    // ---- TD label: first-max over Q'(s') with ArgmaxF32's rules, lane = action, one row at a time; lane k keeps row k's.
+    //   sequential rule (dense/op.go:42-62 over gonum floats.MaxIdx): f = v[0]; for i >= 1: the first NaN or +Inf ends
+    //   the scan with f = v[i]; otherwise f = v[i] if v[i] > f.  In parallel: the lowest special lane if any, else a
+    //   shuffle tree that takes the higher lane's value only if it is strictly greater (so the first maximum wins and a
+    //   NaN in v[0] survives, as `v > NaN` is false).
+    float fmine = 0.f, qamine = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float v = qtv[k];
+        const bool special = lane >= 1 && lane < A && (isnan(v) || (isinf(v) && v > 0.f));
+        const unsigned bal = __ballot_sync(0xffffffffu, special);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float o = __shfl_down_sync(0xffffffffu, v, off);
+            v = (lane + off < 32 && o > v) ? o : v;
+        }
+        const float fmax_ = __shfl_sync(0xffffffffu, v, 0);
+        const float fsp = __shfl_sync(0xffffffffu, qtv[k], bal ? (__ffs(bal) - 1) : 0);
+        const float qa = __shfl_sync(0xffffffffu, qv[k], a4[k]);
+        if (lane == k) { fmine = bal ? fsp : fmax_; qamine = qa; }
+    }
+#ifdef GOLDQ_TRACE_BUILD
+    if (threadIdx.x == 0 && fmine == fmine) TRACE_MARK(6);
+#endif
+    float dqv = 0.f, sq = 0.f;
+    if (lane < 4 && rw0 + lane < B) {
+        const float t = dn ? rwd : __fadd_rn(rwd, __fmul_rn(sc.gamma, fmine));
+        td_out[rw0 + lane] = t;
+        residual_loss(sc, __fsub_rn(qamine, t), sq, dqv);
+    }
+    if (threadIdx.x == 0) TRACE_MARK(1);
+    float dq4[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) dq4[k] = __shfl_sync(0xffffffffu, dqv, k);
     // ---- dQ^T: lane = action row i, columns rw0 .. rw0 + 3 in one 8-byte store (B % 8 == 0, rw0 % 4 == 0) ----
     {
         const __nv_bfloat162 p0 = __floats2bfloat162_rn(a4[0] == lane ? dq4[0] : 0.f, a4[1] == lane ? dq4[1] : 0.f);
@@ -1619,37 +1692,28 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
     }
     // ---- row partials of this warp: db3[i] (lane i), loss (lane A) --------------------------------------
     {
-        float v = 0.f;
+        float v = 0.f, ls = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const float sqk = __shfl_sync(0xffffffffu, sq, k);
+            ls += __shfl_sync(0xffffffffu, sq, k);
             if (lane < A) v += (a4[k] == lane && rw0 + k < B) ? dq4[k] : 0.f;
-            else if (lane == A) v += sqk;
         }
-        sRow[warp * 33 + lane] = v;
+        if (lane < A) sRow[warp * 33 + lane] = v;
+        if (lane == 0) sRow[warp * 33 + A] = ls;      // (slot A <= 32: also right for 32 actions)
     }
+    if (threadIdx.x == 0) TRACE_MARK(2);
     // ---- dZ2 of the four rows + column sums ----------------------------------------------------------------
-    const int nch = H2 >> 3;
     for (int c0 = 0; c0 < nch; c0 += 32 * DZ_MAXCH) {
-        uint4 wv[4][DZ_MAXCH];
-        uint32_t mk[4][DZ_MAXCH];      // masks of the chunk's 8 units: bit e = unit 2e masked, bit 4 + e = unit 2e + 1 masked
+        if (c0 > 0) load_chunks(c0);
+        if (m2bits) {
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+            for (int k = 0; k < 4; k++)
 #pragma unroll
-            for (int u = 0; u < DZ_MAXCH; u++) {
-                const int c = c0 + lane + 32 * u;
-                const bool live = c < nch && rw0 + k < B;
-                if (m2bits) {        // the forward's mask words (FFArgs::maskbits): 4 bytes instead of the 16 bytes of H2
-                    const uint32_t wd = live ? __ldg(m2bits + (int64_t)(rw0 + k) * (H2 >> 5) + (c >> 2)) : 0u;
-                    const int sh = (c & 3) * 4;
-                    mk[k][u] = ((wd >> sh) & 0xfu) | (((wd >> (16 + sh)) & 0xfu) << 4);
-                } else {
-                    const uint4 hv = live ? __ldg(reinterpret_cast<const uint4 *>(h2 + (int64_t)(rw0 + k) * H2) + c) : make_uint4(0, 0, 0, 0);
-                    mk[k][u] = ((hv.x >> 15) & 1u) | (((hv.y >> 15) & 1u) << 1) | (((hv.z >> 15) & 1u) << 2) | (((hv.w >> 15) & 1u) << 3) |
-                               ((hv.x >> 31) << 4) | ((hv.y >> 31) << 5) | ((hv.z >> 31) << 6) | ((hv.w >> 31) << 7);
+                for (int u = 0; u < DZ_MAXCH; u++) {
+                    const int sh = ((c0 + lane + 32 * u) & 3) * 4;
+                    mk[k][u] = ((mk[k][u] >> sh) & 0xfu) | (((mk[k][u] >> (16 + sh)) & 0xfu) << 4);
                 }
-                wv[k][u] = live ? __ldg(reinterpret_cast<const uint4 *>(w3t + (int64_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
-            }
+        }
 #pragma unroll
         for (int u = 0; u < DZ_MAXCH; u++) {
             const int c = c0 + lane + 32 * u;
@@ -1680,7 +1744,9 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
             }
         }
     }
+    if (threadIdx.x == 0) TRACE_MARK(3);
     __syncthreads();
+    if (threadIdx.x == 0) TRACE_MARK(4);
     // ---- block partials, warps summed in order ------------------------------------------------------------------
     for (int j = threadIdx.x; j < H2; j += blockDim.x) {
         float v = sm[j];
@@ -1717,7 +1783,7 @@ wide_colsum_kernel(const __nv_bfloat16 *__restrict__ dz, int B, int H, float *__
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int bb = b + 8 * u;
-                v[u] = (bb < r1) ? *reinterpret_cast<const __nv_bfloat162 *>(dz + (int64_t)bb * H + j)
+                v[u] = (bb < r1) ? ld_dep(reinterpret_cast<const __nv_bfloat162 *>(dz + (int64_t)bb * H + j))
                                  : __floats2bfloat162_rn(0.f, 0.f);
             }
 #pragma unroll
@@ -1762,6 +1828,9 @@ struct UpdatePlan {
     int nB;        // float4 groups in b1, b2
     int nC;        // A + 1 scalars
     int blocksA, blocksB, blocksC;
+    int lp[3];     // lanes per float4 group of W1 / W2 / W3 (1, 2 or 4): a range with many split-K slices gives each group
+                   // several lanes, so that every lane sums its share of the slices in ONE round of loads
+    int bA[3];     // blocks of the three ranges (blocksA = their sum)
 };
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -1938,7 +2007,7 @@ __device__ __forceinline__ void finish4(const Dims &d, const Offsets &o, int i, 
 // sums a quarter of the slices in ONE round and the quarters are combined in a fixed shuffle tree (so the sum
 // stays deterministic).  The data-parallel instantiation keeps one lane per group: its grid has to be
 // co-resident (wide_p2p_resident).
-template <bool FUSE, bool DP = false, int LPG = 1>
+template <bool FUSE, bool DP = false>
 __global__ void __launch_bounds__(128, DP ? 5 : 0)
 wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count, float *__restrict__ flat,
                    float *__restrict__ theta, float *__restrict__ m, float *__restrict__ v, AdamConsts ac,
@@ -1956,18 +2025,21 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
     constexpr bool dp = FUSE && DP;      // (a separate instantiation: the exchange costs registers)
     if ((int)blockIdx.x < pl.blocksA) {
         // ---- A: weights ------------------------------------------------------------
-        int gidx = (blockIdx.x * 128 + threadIdx.x) / LPG;
-        const int sub = threadIdx.x % LPG;
-        const bool live = gidx < pl.nA;  // (every lane stays for the shuffles below)
-        if (LPG == 1 && !live) return;
-        if (!live) gidx = 0;
-        const int n1g = (d.D * d.H1) >> 2, n2g = (d.H1 * d.H2) >> 2;
+        const int n1g = (d.D * d.H1) >> 2, n2g = (d.H1 * d.H2) >> 2, n3g = (d.H2 * d.A) >> 2;
+        int bi = blockIdx.x, range = 0;
+        if (bi >= pl.bA[0]) { bi -= pl.bA[0]; range = 1; }
+        if (range == 1 && bi >= pl.bA[1]) { bi -= pl.bA[1]; range = 2; }
+        const int lpg = pl.lp[range];
+        int gl = (bi * 128 + threadIdx.x) / lpg;              // group within its range
+        const int sub = threadIdx.x & (lpg - 1);
+        const bool live = gl < (range == 0 ? n1g : (range == 1 ? n2g : n3g));   // (every lane stays for the shuffles below)
+        if (!live) gl = 0;
         int i, n;
         const float *base;
         int64_t stride;
-        if (gidx < n1g) { i = o.w1 + gidx * 4; base = ps.w1_slices + gidx * 4; n = ps.n1; stride = (int64_t)d.D * d.H1; }
-        else if (gidx < n1g + n2g) { const int u = (gidx - n1g) * 4; i = o.w2 + u; base = ps.w2_slices + u; n = ps.n2; stride = (int64_t)d.H1 * d.H2; }
-        else { const int u = (gidx - n1g - n2g) * 4; i = o.w3 + u; base = ps.w3_slices + u; n = ps.n3; stride = (int64_t)d.H2 * d.A; }
+        if (range == 0) { i = o.w1 + gl * 4; base = ps.w1_slices + gl * 4; n = ps.n1; stride = (int64_t)d.D * d.H1; }
+        else if (range == 1) { i = o.w2 + gl * 4; base = ps.w2_slices + gl * 4; n = ps.n2; stride = (int64_t)d.H1 * d.H2; }
+        else { i = o.w3 + gl * 4; base = ps.w3_slices + gl * 4; n = ps.n3; stride = (int64_t)d.H2 * d.A; }
         float4 w4 = make_float4(0, 0, 0, 0), m4 = w4, v4 = w4;
         if (!live) n = 0;
         if (FUSE && sub == 0 && live) {
@@ -1976,25 +2048,22 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
             v4 = *reinterpret_cast<const float4 *>(v + i);
         }
         float4 g = make_float4(0, 0, 0, 0);
-        for (int z = sub; z < n; z += 8 * LPG) {     // lane `sub` takes slices sub, sub + LPG, ...
+        for (int z = sub; z < n; z += 8 * lpg) {     // lane `sub` takes slices sub, sub + lpg, ...
             float4 t[8];
 #pragma unroll
             for (int u = 0; u < 8; u++)
-                t[u] = (z + u * LPG < n) ? __ldg(reinterpret_cast<const float4 *>(base + (int64_t)(z + u * LPG) * stride))
+                t[u] = (z + u * lpg < n) ? __ldg(reinterpret_cast<const float4 *>(base + (int64_t)(z + u * lpg) * stride))
                                          : make_float4(0, 0, 0, 0);
 #pragma unroll
             for (int u = 0; u < 8; u++) g = f4add(g, t[u]);
         }
-        if (LPG > 1) {
-#pragma unroll
-            for (int off = 1; off < LPG; off <<= 1) {
-                g.x += __shfl_xor_sync(0xffffffffu, g.x, off);
-                g.y += __shfl_xor_sync(0xffffffffu, g.y, off);
-                g.z += __shfl_xor_sync(0xffffffffu, g.z, off);
-                g.w += __shfl_xor_sync(0xffffffffu, g.w, off);
-            }
-            if (sub != 0 || !live) return;
+        for (int off = 1; off < lpg; off <<= 1) {    // fixed tree: the sum does not depend on timing
+            g.x += __shfl_xor_sync(0xffffffffu, g.x, off);
+            g.y += __shfl_xor_sync(0xffffffffu, g.y, off);
+            g.z += __shfl_xor_sync(0xffffffffu, g.z, off);
+            g.w += __shfl_xor_sync(0xffffffffu, g.w, off);
         }
+        if (sub != 0 || !live) return;
         bool ok = true;     // false: a peer's word never arrived -- leave theta / m / v / shadows untouched
         if (dp) g = dp_exchange4(push, epoch, i, g, ok);
         if (ok) finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
@@ -2362,13 +2431,24 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
     return 1;
 }
 
-static UpdatePlan make_update_plan(const Dims &d, int lpg = 1)
+// many_lanes: ranges with more than 8 split-K slices get 2 or 4 lanes per group (one round of loads per lane instead of
+// up to four dependent rounds: the block trace showed the 32-slice groups of W1 and W3 finishing 5 us after the 10-slice
+// groups of W2 -- the tail of the whole step).  The data-parallel instantiation keeps one lane per group: its grid has
+// to stay co-resident (wide_p2p_resident).
+static UpdatePlan make_update_plan(const Dims &d, int n1 = 1, int n2 = 1, int n3 = 1, bool many_lanes = false)
 {
     UpdatePlan pl;
-    pl.nA = (d.D * d.H1 + d.H1 * d.H2 + d.H2 * d.A) >> 2;
+    const int ng[3] = {(d.D * d.H1) >> 2, (d.H1 * d.H2) >> 2, (d.H2 * d.A) >> 2};
+    const int ns[3] = {n1, n2, n3};
+    pl.nA = ng[0] + ng[1] + ng[2];
     pl.nB = (d.H1 + d.H2) >> 2;
     pl.nC = d.A + 1;
-    pl.blocksA = (pl.nA * lpg + 127) / 128;
+    pl.blocksA = 0;
+    for (int r = 0; r < 3; r++) {
+        pl.lp[r] = !many_lanes ? 1 : (ns[r] > 16 ? 4 : (ns[r] > 10 ? 2 : 1));
+        pl.bA[r] = (ng[r] * pl.lp[r] + 127) / 128;
+        pl.blocksA += pl.bA[r];
+    }
     pl.blocksB = (pl.nB + 3) / 4;
     pl.blocksC = (pl.nC + 3) / 4;
     return pl;
@@ -2701,21 +2781,21 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
 
     PartialSrc ps{w->w1_slices, w->ns1, w->b1_part, w->nb1, w->w2_slices, w->ns2,
                   w->b2_part,   w->nb2, w->w3_slices, w->ns3, w->row_part, w->nrow};
-    constexpr int LPG = 1;      // (4 lanes per group measured slower: 15.5 vs 12.9 us for the launch, 66.4 vs 62.1 us/step)
-    const bool lanes4 = !(s.fuse_update && s.push);      // every launch but the data-parallel one
-    const UpdatePlan pl = make_update_plan(d, lanes4 ? LPG : 1);
+    static const bool one_lane = getenv("GOLDQ_UPDATE_ONE_LANE") != nullptr;      // diagnostic: round-1 decomposition
+    const bool dp_launch = s.fuse_update && s.push;
+    const UpdatePlan pl = make_update_plan(d, w->ns1, w->ns2, w->ns3, !dp_launch && !one_lane);
     const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
     // (the update kernel follows cross-stream event waits: a full dependency, no PDL)
     if (w->skip & 256) {
-    } else if (s.fuse_update && s.push)
+    } else if (dp_launch)
         wide_update_kernel<true, true><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
                                                                s.step, shadow_ptrs(w, 0), s.loss_out, *s.push, s.epoch);
     else if (s.fuse_update)
-        wide_update_kernel<true, false, LPG><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
-                                                         s.step, shadow_ptrs(w, 0), s.loss_out, PeerSet{}, 0u);
+        wide_update_kernel<true, false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
+                                                                s.step, shadow_ptrs(w, 0), s.loss_out, PeerSet{}, 0u);
     else
-        wide_update_kernel<false, false, LPG><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
-                                                          s.adam, s.step, shadow_ptrs(w, 0), nullptr, PeerSet{}, 0u);
+        wide_update_kernel<false, false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
+                                                                 s.adam, s.step, shadow_ptrs(w, 0), nullptr, PeerSet{}, 0u);
     WCK(cudaGetLastError());
     mark("reduce + Adam + bf16 shadow (K5)");
     launches++;

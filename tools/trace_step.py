@@ -33,7 +33,7 @@ h.timer_start()
 h.learn_many(steps, 100)
 ms = h.timer_stop()
 raw = h.debug_fetch(G.DBG_TRACE)
-n = int(raw[0])
+n = min(int(raw[0]), (len(raw) - 4) // 12)       # (records past the buffer's capacity were dropped)
 rec = raw[4:4 + 12 * n].reshape(n, 12)
 marks = rec[:, 4:12].astype(np.int64)
 t0, t1 = rec[:, 0].astype(np.int64), rec[:, 1].astype(np.int64)
@@ -75,6 +75,7 @@ if len(ups) >= 6:
                  "EPI: column sums done", "EPI: TMA store read out"]}
     GEMM = ["after pdl_wait", "MMA: first stage landed", "MMA: all issued", "EPI: accumulator ready", "EPI: tile written"]
     MARKS.update({4: GEMM, 5: GEMM, 8: GEMM})
+    MARKS[3] = ["after pdl_wait", "TD rows done (warp 0)", "dQ^T + row partials stored", "dZ2 stored (warp 0)", "block barrier passed", "(actions arrived)", "(first-max done)"]
     marks -= base
     for k, names in MARKS.items():
         sel = np.where((kid == k) & (t1 > lo) & (t1 <= hi + 3000) & (marks[:, 0] > 0))[0]
@@ -89,4 +90,19 @@ if len(ups) >= 6:
                 print(f"  {nm:28s} {np.median(v):7.2f} {v.min():7.2f} {v.max():7.2f}")
         v = (t1[sel] - marks[sel, 0]) / 1e3
         print(f"  {'block exit':28s} {np.median(v):7.2f} {v.min():7.2f} {v.max():7.2f}")
+    # update kernel: per block range (W1 | W2 | W3 groups, bias warps, scalars), start after the kernel's first block and duration
+    blk = (rec[:, 2] >> np.uint64(32)).astype(np.int64)
+    sel = np.where((kid == 9) & (t1 > lo + 5000) & (t1 <= hi + 100))[0]
+    if len(sel):
+        s0 = t0[sel].min()
+        n1, n2, n3 = dims[0] * dims[1] // 4, dims[1] * dims[2] // 4, dims[2] * dims[3] // 4
+        bA = (n1 + n2 + n3 + 127) // 128
+        edges = [("W1 groups", 0, n1 // 128), ("W2 groups", n1 // 128, (n1 + n2) // 128), ("W3 groups", (n1 + n2) // 128, bA),
+                 ("b1/b2 warps", bA, bA + (dims[1] + dims[2]) // 16), ("b3 + loss", bA + (dims[1] + dims[2]) // 16, 1 << 30)]
+        print(f"\nupdate kernel, {len(sel)} blocks: start after the first block / duration, us (median, max)")
+        for nm, a, b in edges:
+            q = sel[(blk[sel] >= a) & (blk[sel] < b)]
+            if len(q):
+                st, du = (t0[q] - s0) / 1e3, (t1[q] - t0[q]) / 1e3
+                print(f"  {nm:12s} {len(q):4d} blocks   start {np.median(st):6.2f} {st.max():6.2f}   duration {np.median(du):6.2f} {du.max():6.2f}   last out {((t1[q] - s0) / 1e3).max():6.2f}")
 h.close()
