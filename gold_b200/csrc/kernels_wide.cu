@@ -323,8 +323,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     const int ch0 = (c0 & 63) >> 3;
 #pragma unroll
                     for (int v = 0; v < 4; v++)
-                        *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
-                            make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+                        sts128(dst + (((ch0 + v) ^ (rt & 7)) << 4),
+                                   make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]));
                 } else if (EPI == EPI_BIAS_F32) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
@@ -336,8 +336,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     uint8_t *dst = smem + rt * (BN * 4);
 #pragma unroll
                     for (int v = 0; v < 8; v++)
-                        *reinterpret_cast<uint4 *>(dst + ((((c0 >> 2) + v) ^ (rt & 7)) << 4)) =
-                            make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+                        sts128(dst + ((((c0 >> 2) + v) ^ (rt & 7)) << 4),
+                                   make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]));
                 } else {  // EPI_F32_SLICE
                     float *o = out_f32 + (size_t)split * g.slice_stride + (size_t)row * g.ldo + col0;
                     if (col0 + 32 <= g.n_store && (g.ldo & 3) == 0) {
@@ -361,7 +361,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int ew = warp - 2;
 #pragma unroll 8
             for (int rr = ew; rr < BM; rr += 4) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(smem + rr * (BN * 4) + ((lane ^ (rr & 7)) << 4));
+                const uint4 v = lds128(smem + rr * (BN * 4) + ((lane ^ (rr & 7)) << 4));
                 *reinterpret_cast<uint4 *>(o + (size_t)rr * g.ldo + lane * 4) = v;
             }
         }
@@ -612,8 +612,8 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             const int ch0 = (c0 & 63) >> 3;
 #pragma unroll
             for (int v = 0; v < 4; v++)
-                *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
-                    make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+                sts128(dst + (((ch0 + v) ^ (rt & 7)) << 4),
+                           make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]));
         };
         auto arrive = [&](uint64_t *bar) {
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -719,12 +719,12 @@ ff_forward_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 const float v = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, b3, j);
-                if (j < g.A) sQ[rt * g.A + j] = v;
+                if (j < g.A) sts32(sQ + rt * g.A + j, v);
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
             const int rows = (g.B - m0 < BM) ? g.B - m0 : BM;
             float *dst = g.q[net] + (size_t)m0 * g.A;
-            for (int i = et; i < rows * g.A; i += 128) dst[i] = sQ[i];
+            for (int i = et; i < rows * g.A; i += 128) dst[i] = lds32(sQ + i);
         }
         if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
@@ -994,8 +994,8 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 const int ch0 = (c0 & 63) >> 3;
 #pragma unroll
                 for (int v = 0; v < 4; v++)
-                    *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
-                        make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+                    sts128(dst + (((ch0 + v) ^ (rt & 7)) << 4),
+                               make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]));
             }
             if (net == 0 && g.keep_h && m0 + rt < g.B)
                 *reinterpret_cast<uint4 *>(g.maskbits[layer] + (size_t)(m0 + rt) * (FF_H / 32) + (cbase >> 5)) =
@@ -1033,7 +1033,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 const float v = __uint_as_float(r[j]) + s_bias[2 * FF_H + j];
-                if (j < g.A) sQ[rt * g.A + j] = v;
+                if (j < g.A) sts32(sQ + rt * g.A + j, v);
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
             const int nq = ((g.B - m0 < BM) ? g.B - m0 : BM) * g.A;
@@ -1043,7 +1043,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
             for (int i0 = et; i0 < nq; i0 += 8 * 128) {
                 float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = (i0 + 128 * u < nq) ? sQ[i0 + 128 * u] : 0.f;
+                for (int u = 0; u < 8; u++) v[u] = (i0 + 128 * u < nq) ? lds32(sQ + i0 + 128 * u) : 0.f;
 #pragma unroll
                 for (int u = 0; u < 8; u++)
                     if (i0 + 128 * u < nq) dst[i0 + 128 * u] = v[u];
@@ -1253,8 +1253,8 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int ch0 = (c0 & 63) >> 3;
 #pragma unroll
                 for (int v = 0; v < 4; v++)
-                    *reinterpret_cast<uint4 *>(dst + (((ch0 + v) ^ (rt & 7)) << 4)) =
-                        make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+                    sts128(dst + (((ch0 + v) ^ (rt & 7)) << 4),
+                               make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]));
             }
             tc_fence_before();
             fence_proxy_async_smem();
@@ -1275,17 +1275,26 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 float acc[8];
 #pragma unroll
                 for (int u = 0; u < 8; u++) acc[u] = 0.f;
-#pragma unroll 4
-                for (int i = 0; i < 16; i++) {
-                    const int rr = 64 * hf + 4 * i + ro;
-                    const uint4 wv = *reinterpret_cast<const uint4 *>(box + rr * 128 + ((ch ^ (rr & 7)) << 4));
-                    if (m0 + rr < g.M) {
-                        acc[0] += __uint_as_float(wv.x << 16); acc[1] += __uint_as_float(wv.x & 0xffff0000u);
-                        acc[2] += __uint_as_float(wv.y << 16); acc[3] += __uint_as_float(wv.y & 0xffff0000u);
-                        acc[4] += __uint_as_float(wv.z << 16); acc[5] += __uint_as_float(wv.z & 0xffff0000u);
-                        acc[6] += __uint_as_float(wv.w << 16); acc[7] += __uint_as_float(wv.w & 0xffff0000u);
+#pragma unroll
+                for (int i0 = 0; i0 < 16; i0 += 8) {          // eight independent 16-byte shared loads in flight
+                    uint4 wv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int rr = 64 * hf + 4 * (i0 + i) + ro;
+                        wv[i] = lds128(box + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int rr = 64 * hf + 4 * (i0 + i) + ro;
+                        if (m0 + rr < g.M) {
+                            acc[0] += __uint_as_float(wv[i].x << 16); acc[1] += __uint_as_float(wv[i].x & 0xffff0000u);
+                            acc[2] += __uint_as_float(wv[i].y << 16); acc[3] += __uint_as_float(wv[i].y & 0xffff0000u);
+                            acc[4] += __uint_as_float(wv[i].z << 16); acc[5] += __uint_as_float(wv[i].z & 0xffff0000u);
+                            acc[6] += __uint_as_float(wv[i].w << 16); acc[7] += __uint_as_float(wv[i].w & 0xffff0000u);
+                        }
                     }
                 }
+                if (et == 0) TRACE_MARK(7);
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], 8);
@@ -1294,14 +1303,17 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 float *fold = reinterpret_cast<float *>(smem + 4 * 16384);     // [4 boxes][64 columns], behind the staged tile
                 if (hf == 1 && ro == 0) {
 #pragma unroll
-                    for (int u = 0; u < 8; u++) fold[bx * 64 + ch * 8 + u] = acc[u];
+                    for (int u = 0; u < 8; u++) sts32(fold + bx * 64 + ch * 8 + u, acc[u]);
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (hf == 0 && ro == 0) {
                     float *cs = g.colsum + (size_t)blockIdx.x * g.N + n0 + bx * 64 + ch * 8;
                     const float *fo = fold + bx * 64 + ch * 8;
-                    *reinterpret_cast<float4 *>(cs) = make_float4(acc[0] + fo[0], acc[1] + fo[1], acc[2] + fo[2], acc[3] + fo[3]);
-                    *reinterpret_cast<float4 *>(cs + 4) = make_float4(acc[4] + fo[4], acc[5] + fo[5], acc[6] + fo[6], acc[7] + fo[7]);
+                    const uint4 f0 = lds128(fo), f1 = lds128(fo + 4);
+                    *reinterpret_cast<float4 *>(cs) = make_float4(acc[0] + __uint_as_float(f0.x), acc[1] + __uint_as_float(f0.y),
+                                                                  acc[2] + __uint_as_float(f0.z), acc[3] + __uint_as_float(f0.w));
+                    *reinterpret_cast<float4 *>(cs + 4) = make_float4(acc[4] + __uint_as_float(f1.x), acc[5] + __uint_as_float(f1.y),
+                                                                      acc[6] + __uint_as_float(f1.z), acc[7] + __uint_as_float(f1.w));
                 }
             }
             if (et == 0) TRACE_MARK(5);
@@ -2247,9 +2259,11 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     int tiles1 = ((d.D + BM - 1) / BM) * ((d.H1 + 127) / 128);
     int tiles2 = ((d.H1 + BM - 1) / BM) * ((d.H2 + 127) / 128);
     int tiles3 = (d.H2 + BM - 1) / BM;
-    w->ns1 = split_for(tiles1, B, sm_count, &w->kps1);
-    w->ns2 = split_for(tiles2, B, sm_count, &w->kps2);
-    w->ns3 = split_for(tiles3, B, sm_count, &w->kps3);
+    // CTAs each split-K GEMM aims for (GOLDQ_CTAS1/2/3: tuning knobs; default = one per SM for dW1 and dW2)
+    auto ctas_for = [&](const char *name, int dflt) { const char *e = getenv(name); return e && atoi(e) > 0 ? atoi(e) : dflt; };
+    w->ns1 = split_for(tiles1, B, ctas_for("GOLDQ_CTAS1", sm_count), &w->kps1);
+    w->ns2 = split_for(tiles2, B, ctas_for("GOLDQ_CTAS2", sm_count), &w->kps2);
+    w->ns3 = split_for(tiles3, B, ctas_for("GOLDQ_CTAS3", sm_count), &w->kps3);
     w->nb1 = (B + CS_ROWS - 1) / CS_ROWS;
     const bool no_pair = getenv("GOLDQ_NO_PAIR_GEMM") != nullptr;
     // dX on CTA pairs: 256 x 256 tiles need whole 256-row / 256-column tiles; it writes one db1 partial per 128-row slab

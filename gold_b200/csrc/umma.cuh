@@ -32,6 +32,27 @@ __device__ __forceinline__ bool elect_one()
 }
 
 // ---- programmatic dependent launch ---------------------------------------------
+// Explicit shared-space accesses.  The tile pointers of these kernels are computed from an aligned uintptr_t, so the
+// compiler no longer knows their address space and emits GENERIC LD.E / ST.E for `*ptr` (seen in SASS): longer, unknown
+// latency, and in the column-sum loop of the dX epilogue sixteen serialised round trips (2.2 us for 16 loads).
+__device__ __forceinline__ void sts128(void *p, uint4 v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(void *p, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds32(const void *p)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
 // its predecessor in the stream is still draining; pdl_wait() blocks until the predecessor
 // has completed and its writes are visible (no-op without the attribute).  Every kernel of

@@ -72,7 +72,7 @@ if len(ups) >= 6:
             print(f"{NAMES.get(k, k):10s} {(s - lo) / 1e3:14.2f} {(e - lo) / 1e3:15.2f} {(e - s) / 1e3:7.2f} {c:7d} {busy / c / 1e3:11.2f}")
     # in-kernel marks (dX): relative to mark 0 (= after griddepcontrol.wait), blocks of the instances inside the window
     MARKS = {6: ["after pdl_wait", "MMA: first stage landed", "MMA: all issued", "EPI: accumulator ready", "EPI: tile staged",
-                 "EPI: column sums done", "EPI: TMA store read out"]}
+                 "EPI: column sums done", "EPI: TMA store read out", "(EPI: column-sum loop done)"]}
     GEMM = ["after pdl_wait", "MMA: first stage landed", "MMA: all issued", "EPI: accumulator ready", "EPI: tile written"]
     MARKS.update({4: GEMM, 5: GEMM, 8: GEMM})
     MARKS[3] = ["after pdl_wait", "TD rows done (warp 0)", "dQ^T + row partials stored", "dZ2 stored (warp 0)", "block barrier passed", "(actions arrived)", "(first-max done)"]
