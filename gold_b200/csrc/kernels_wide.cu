@@ -946,7 +946,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
 
-        const __nv_bfloat162 neg0 = __floats2bfloat162_rn(-0.0f, -0.0f);
+        const __nv_bfloat162 neg0 = __floats2bfloat162_rn(-0.0f, -0.0f), zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
         // phases: (layer 1, half 0), (layer 1, half 1), (layer 2, half 0), (layer 2, half 1) -- one loop body.
         // H2 overwrites H1 in place: its first half may be written once the layer-2 MMAs of accumulator half 1
         // have consumed H1 boxes 0..3 (lo_free), its second half once every layer-2 MMA has retired.
@@ -973,22 +973,22 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 tmem_ld_wait();
                 if (c < 3) tmem_ld_32x32(tq + (uint32_t)(cbase + 32 * (c + 1)), r[(c + 1) & 1]);
                 uint32_t packed[16];
-                uint32_t mlo = 0u, mhi = 0u;
+                uint32_t mwc = 0u;
 #pragma unroll
                 for (int jj = 0; jj < 32; jj += 4) {
                     const float4 bv = *reinterpret_cast<const float4 *>(bias + 32 * c + jj);
                     __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(r[c & 1][jj]) + bv.x, __uint_as_float(r[c & 1][jj + 1]) + bv.y);
                     __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(r[c & 1][jj + 2]) + bv.z, __uint_as_float(r[c & 1][jj + 3]) + bv.w);
-                    p0 = __hmax2(p0, neg0);         // Rectify: negative (and NaN) -> -0.0, sign bit = mask (nn.go:162-189)
+                    // Rectify mask of the four units = "pre-activation < 0 or NaN" (a * (a >= 0), nn.go:162-189): one packed
+                    // compare per pair (0xffff per true half) and one and-or into the chunk's mask word
+                    mwc |= __hltu2_mask(p0, zero2) & (0x00010001u << (jj >> 1));
+                    mwc |= __hltu2_mask(p1, zero2) & (0x00010001u << ((jj >> 1) + 1));
+                    p0 = __hmax2(p0, neg0);         // Rectify: negative (and NaN) -> -0.0
                     p1 = __hmax2(p1, neg0);
                     packed[jj >> 1] = *reinterpret_cast<uint32_t *>(&p0);
                     packed[(jj >> 1) + 1] = *reinterpret_cast<uint32_t *>(&p1);
-                    // sign bits (= Rectify mask) of the four units, shifted in from the top: after the eight rounds
-                    // mlo / mhi hold the even / odd units of the chunk in their upper 16 bits
-                    mlo = (mlo >> 2) | ((packed[jj >> 1] << 15) & 0x40000000u) | ((packed[(jj >> 1) + 1] << 16) & 0x80000000u);
-                    mhi = (mhi >> 2) | ((packed[jj >> 1] >> 1) & 0x40000000u) | (packed[(jj >> 1) + 1] & 0x80000000u);
                 }
-                mw[c] = (mlo >> 16) | (mhi & 0xffff0000u);     // bits 0..15: units 0, 2, .. 30; bits 16..31: units 1, 3, .. 31
+                mw[c] = mwc;                                   // bits 0..15: units 0, 2, .. 30; bits 16..31: units 1, 3, .. 31
                 const int c0 = cbase + 32 * c;
                 uint8_t *dst = sH + (c0 >> 6) * FF_BOX + rt * 128;
                 const int ch0 = (c0 & 63) >> 3;
