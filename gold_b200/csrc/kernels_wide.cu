@@ -2641,6 +2641,9 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         WideState::BatchSet &nx = w->bs[(s.set & 1) ^ 1];
         WCK(cudaEventRecord(w->ev_fork, st));
         WCK(cudaStreamWaitEvent(w->s3, w->ev_fork, 0));
+        // (a few big blocks that ask for 100 KB of shared memory, so that they land only on the SMs the forward leaves
+        // idle, did take the gather off the forward's SMs -- forward 19.3 -> 18.3 us -- but needed 35-53 us themselves:
+        // random 512-byte rows want hundreds of thousands of threads in flight, not 40 k.  Measured 51.9 / 62.0 vs 49.5 us/step.)
         wide_gather_kernel<<<(gather_threads + 255) / 256, 256, 0, w->s3>>>(s.rp, d.D, nullptr, 0, s.next_step, s.idx_out, B,
                                                                             nx.x, nx.x2, nx.ba, nx.br, nx.bdone);
         WCK(cudaGetLastError());
