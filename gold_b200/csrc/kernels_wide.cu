@@ -2026,14 +2026,17 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
                    const StepDev *__restrict__ step, ShadowPtrs sp, float *__restrict__ loss_out, PeerSet push,
                    unsigned int epoch)
 {
-    BlockTrace trace_(TR_UPDATE);
+    TRACE_MARKS_DECL
+    BlockTrace trace_(TR_UPDATE, TRACE_MARKS_PTR);
     // push.world > 0 (data-parallel group over peer memory, FUSE only): the locally reduced gradient is
     // exchanged (dp_exchange*) and the update uses the global sum
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) TRACE_MARK(0);
     if (FUSE && step) { ac.c1 = step->c1; ac.c2 = step->c2; }
     if (step) epoch = step->epoch;
+    if (threadIdx.x == 0 && epoch != 0xffffffffu) TRACE_MARK(1);
     constexpr bool dp = FUSE && DP;      // (a separate instantiation: the exchange costs registers)
     if ((int)blockIdx.x < pl.blocksA) {
         // ---- A: weights ------------------------------------------------------------
@@ -2069,6 +2072,7 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
 #pragma unroll
             for (int u = 0; u < 8; u++) g = f4add(g, t[u]);
         }
+        if (threadIdx.x == 0 && g.x == g.x) TRACE_MARK(2);
         for (int off = 1; off < lpg; off <<= 1) {    // fixed tree: the sum does not depend on timing
             g.x += __shfl_xor_sync(0xffffffffu, g.x, off);
             g.y += __shfl_xor_sync(0xffffffffu, g.y, off);
@@ -2079,6 +2083,7 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
         bool ok = true;     // false: a peer's word never arrived -- leave theta / m / v / shadows untouched
         if (dp) g = dp_exchange4(push, epoch, i, g, ok);
         if (ok) finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
+        if (threadIdx.x == 0) TRACE_MARK(3);
     } else if ((int)blockIdx.x < pl.blocksA + pl.blocksB) {
         // ---- B: biases of the hidden layers, warp per float4 group -------------------
         const int gidx = (blockIdx.x - pl.blocksA) * 4 + warp;

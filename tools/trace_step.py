@@ -75,6 +75,7 @@ if len(ups) >= 6:
                  "EPI: column sums done", "EPI: TMA store read out", "(EPI: column-sum loop done)"]}
     GEMM = ["after pdl_wait", "MMA: first stage landed", "MMA: all issued", "EPI: accumulator ready", "EPI: tile written"]
     MARKS.update({4: GEMM, 5: GEMM, 8: GEMM})
+    MARKS[9] = ["after pdl_wait", "step scalars arrived", "slices summed (thread 0)", "Adam + stores issued"]
     MARKS[3] = ["after pdl_wait", "TD rows done (warp 0)", "dQ^T + row partials stored", "dZ2 stored (warp 0)", "block barrier passed", "(actions arrived)", "(first-max done)"]
     marks -= base
     for k, names in MARKS.items():
