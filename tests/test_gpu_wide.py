@@ -1,10 +1,12 @@
 """bf16 tcgen05 path (BASELINE configs[2]) against the fp32/fp64 oracle.
 
-Stated tolerance (north_star: "bf16 wide configs within a stated 1e-2"):
-  Q(s), Q'(s'), TD targets : |x - ref| <= 1e-2 * max|ref|      (bf16 operands, fp32 accumulate)
-  loss                      : 2e-2 relative
-  gradients                 : ||g - ref||_2 <= 3e-2 ||ref||_2 and elementwise 2e-2 * max|ref|
-  post-Adam parameters      : |w - ref| <= 1e-2 * max|ref| and inside Adam's hard bound 2*lr*(1+max|g|)
+Stated tolerance (north_star: "bf16 wide configs within a stated 1e-2"; the bars asserted below are tighter, about
+1.5x the worst value observed on a B200 over every shape of this file):
+  Q(s), Q'(s'), TD targets : |x - ref| <= 7e-3 / 6e-3 / 4e-3 * max|ref|   (bf16 operands, fp32 accumulate)
+  loss                      : 2e-3 relative
+  gradients                 : ||g - ref||_2 <= 3e-2 ||ref||_2 (observed 2.7e-2: bf16 activations) and elementwise
+                              2e-2 * max|ref|; per block W1 1e-1, b1 / W2 5e-2, b2 4e-2, W3 4e-3, b3 2e-3
+  post-Adam parameters      : |w - ref| <= 4e-3 * max|ref| and inside Adam's hard bound 2*lr*(1+max|g|)
                               everywhere, > 50 % of elements within 1e-5 relative (small batches leave many near-zero gradients, where Adam is sign-like); the Adam kernel
                               applied to the GPU's own gradient reproduces the reference solver to 1e-6
   greedy actions            : equal wherever the oracle's top-2 Q gap exceeds the Q tolerance
@@ -39,14 +41,16 @@ def check(h, o, idx):
     out, out64 = o.learn(idx)
     h.learn(idx)
     q = h.debug_fetch(G.DBG_Q_ONLINE); qt = h.debug_fetch(G.DBG_Q_TARGET); td = h.debug_fetch(G.DBG_TD)
+    # Stated bf16 bars = about 1.5x the worst value observed over every shape of this file on a B200 (tools: the ratios
+    # printed by the round-2 sweep were q 4.6e-3, q' 3.9e-3, td 2.6e-3, loss 6.4e-4, |g - ref| / |ref| 2.7e-2, params 2.2e-3)
     qs = np.abs(out64["q_online"]).max()
-    assert np.abs(q - out64["q_online"]).max() <= 1e-2 * qs, np.abs(q - out64["q_online"]).max() / qs
+    assert np.abs(q - out64["q_online"]).max() <= 7e-3 * qs, np.abs(q - out64["q_online"]).max() / qs
     nd = out["done"] == 0
-    assert np.abs(qt[nd] - out64["q_target"][nd]).max() <= 1e-2 * np.abs(out64["q_target"]).max()
+    assert np.abs(qt[nd] - out64["q_target"][nd]).max() <= 6e-3 * np.abs(out64["q_target"]).max()
     assert (qt[~nd] == 0).all()
-    assert np.abs(td - out64["td"]).max() <= 1e-2 * np.abs(out64["td"]).max()
+    assert np.abs(td - out64["td"]).max() <= 4e-3 * np.abs(out64["td"]).max()
     loss = float(h.last_loss()[0])
-    assert abs(loss - out64["loss"]) <= 2e-2 * abs(out64["loss"]), (loss, out64["loss"])
+    assert abs(loss - out64["loss"]) <= 2e-3 * abs(out64["loss"]), (loss, out64["loss"])
     g = h.debug_fetch(G.DBG_GRADS).astype(np.float64)
     ref = out64["grads"]
     assert np.linalg.norm(g - ref) <= 3e-2 * np.linalg.norm(ref), np.linalg.norm(g - ref) / np.linalg.norm(ref)
@@ -54,9 +58,10 @@ def check(h, o, idx):
     # per-block sanity so that a broken small block (biases, W3) cannot hide in the norm; the
     # exact per-block check is test_wide_matches_bf16_emulation
     off = synth.offsets(o.dims)
+    bars = {"w1": 1e-1, "b1": 5e-2, "w2": 5e-2, "b2": 4e-2, "w3": 4e-3, "b3": 2e-3}      # observed 8.4e-2 .. 7e-4
     for name, (a, b) in off.items():
         nr = np.linalg.norm(ref[a:b])
-        assert np.linalg.norm(g[a:b] - ref[a:b]) <= 1e-1 * nr + 1e-12, (name, np.linalg.norm(g[a:b] - ref[a:b]) / nr)
+        assert np.linalg.norm(g[a:b] - ref[a:b]) <= bars[name] * nr + 1e-12, (name, np.linalg.norm(g[a:b] - ref[a:b]) / nr)
     w = h.get_params(G.NET_ONLINE)
     # (i) the Adam kernel itself: applied to the GPU's own gradient it must reproduce the
     #     reference solver (double update included) to fp32 rounding
@@ -65,10 +70,10 @@ def check(h, o, idx):
     O.adam(w_chk, h.debug_fetch(G.DBG_GRADS).copy(), m_chk, v_chk, it0 + 1, lr=o.lr)
     np.testing.assert_allclose(w, w_chk, rtol=1e-6, atol=1e-8)
     # (ii) against the fp64 oracle: every element inside Adam's hard bound, and within the
-    #      stated 1e-2 (relative to the weight scale); the bulk agrees to 1e-5
+    #      4e-3 of the weight scale (observed 2.2e-3); the bulk agrees to 1e-5
     dw = np.abs(w - out64["theta"])
     assert dw.max() <= 2 * o.lr * (1 + np.abs(ref).max()) + 1e-7      # both sides moved by at most lr*(1+|mhat|)
-    assert dw.max() <= 1e-2 * np.abs(out64["theta"]).max()
+    assert dw.max() <= 4e-3 * np.abs(out64["theta"]).max()
     assert np.mean(dw <= 1e-5 * np.abs(out64["theta"]) + 1e-7) > 0.50
     h.set_params(G.NET_ONLINE, o.theta)
     h.set_adam_state(o.m, o.v, o.iter)
