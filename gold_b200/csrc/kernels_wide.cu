@@ -2264,11 +2264,14 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     int tiles1 = ((d.D + BM - 1) / BM) * ((d.H1 + 127) / 128);
     int tiles2 = ((d.H1 + BM - 1) / BM) * ((d.H2 + 127) / 128);
     int tiles3 = (d.H2 + BM - 1) / BM;
-    // CTAs each split-K GEMM aims for (GOLDQ_CTAS1/2/3: tuning knobs; default = one per SM for dW1 and dW2)
+    // CTAs each split-K GEMM aims for (GOLDQ_CTAS1/2/3: tuning knobs).  dW2 (the big one): one per SM.  dW1 and dW3 are
+    // small GEMMs with few output tiles: a CTA per SM meant 32 split-K slices each, i.e. four dependent rounds of loads
+    // in the update kernel's one-lane (data-parallel) form; 64 / 32 CTAs (16 / 8 slices on the wide configuration) cost
+    // the GEMMs nothing measurable (49.8 vs 50.6 us/step) and halve / quarter what the update kernel reads.
     auto ctas_for = [&](const char *name, int dflt) { const char *e = getenv(name); return e && atoi(e) > 0 ? atoi(e) : dflt; };
-    w->ns1 = split_for(tiles1, B, ctas_for("GOLDQ_CTAS1", sm_count), &w->kps1);
+    w->ns1 = split_for(tiles1, B, ctas_for("GOLDQ_CTAS1", sm_count * 7 / 16), &w->kps1);
     w->ns2 = split_for(tiles2, B, ctas_for("GOLDQ_CTAS2", sm_count), &w->kps2);
-    w->ns3 = split_for(tiles3, B, ctas_for("GOLDQ_CTAS3", sm_count), &w->kps3);
+    w->ns3 = split_for(tiles3, B, ctas_for("GOLDQ_CTAS3", sm_count * 7 / 32), &w->kps3);
     w->nb1 = (B + CS_ROWS - 1) / CS_ROWS;
     const bool no_pair = getenv("GOLDQ_NO_PAIR_GEMM") != nullptr;
     // dX on CTA pairs: 256 x 256 tiles need whole 256-row / 256-column tiles; it writes one db1 partial per 128-row slab
