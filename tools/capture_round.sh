@@ -4,8 +4,10 @@
 #   gpurun -- 'bash tools/capture_round.sh r3a'
 out=gpurun_out/${1:-cap}; mkdir -p $out
 timeout 900 python -m pytest tests -m gpu -q > $out/gpu_tests.log 2>&1; echo "pytest rc=$?" >> $out/gpu_tests.log; tail -3 $out/gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $out/smoke.log 2>&1; tail -1 $out/smoke.log
 timeout 400 python bench.py --steps 20 --warmup 5 > $out/bench20.json 2> $out/bench20.err; echo "bench rc=$?"
 timeout 400 python bench.py --impl reference --steps 20 --warmup 5 > $out/ref.json 2> $out/ref.err; echo "ref rc=$?"
+timeout 300 python bench.py --steps 200 --warmup 10 --no-extra --no-cpu > $out/bench200.json 2> $out/bench200.err
 timeout 200 python tools/trace_step.py 32 > $out/trace_step.log 2>&1
 timeout 200 python tools/skip_probe.py > $out/skip_probe.log 2>&1
 timeout 300 python tools/run_steps.py 12 > $out/plain_steps.log 2>&1 && \

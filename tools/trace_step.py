@@ -91,19 +91,15 @@ if len(ups) >= 6:
                 print(f"  {nm:28s} {np.median(v):7.2f} {v.min():7.2f} {v.max():7.2f}")
         v = (t1[sel] - marks[sel, 0]) / 1e3
         print(f"  {'block exit':28s} {np.median(v):7.2f} {v.min():7.2f} {v.max():7.2f}")
-    # update kernel: per block range (W1 | W2 | W3 groups, bias warps, scalars), start after the kernel's first block and duration
+    # update kernel: duration by block (the block ranges depend on the lanes-per-group plan: report quantiles over all blocks
+    # and the slowest tenth's block indices instead of guessing the ranges)
     blk = (rec[:, 2] >> np.uint64(32)).astype(np.int64)
     sel = np.where((kid == 9) & (t1 > lo + 5000) & (t1 <= hi + 100))[0]
     if len(sel):
         s0 = t0[sel].min()
-        n1, n2, n3 = dims[0] * dims[1] // 4, dims[1] * dims[2] // 4, dims[2] * dims[3] // 4
-        bA = (n1 + n2 + n3 + 127) // 128
-        edges = [("W1 groups", 0, n1 // 128), ("W2 groups", n1 // 128, (n1 + n2) // 128), ("W3 groups", (n1 + n2) // 128, bA),
-                 ("b1/b2 warps", bA, bA + (dims[1] + dims[2]) // 16), ("b3 + loss", bA + (dims[1] + dims[2]) // 16, 1 << 30)]
-        print(f"\nupdate kernel, {len(sel)} blocks: start after the first block / duration, us (median, max)")
-        for nm, a, b in edges:
-            q = sel[(blk[sel] >= a) & (blk[sel] < b)]
-            if len(q):
-                st, du = (t0[q] - s0) / 1e3, (t1[q] - t0[q]) / 1e3
-                print(f"  {nm:12s} {len(q):4d} blocks   start {np.median(st):6.2f} {st.max():6.2f}   duration {np.median(du):6.2f} {du.max():6.2f}   last out {((t1[q] - s0) / 1e3).max():6.2f}")
+        du, out_ = (t1[sel] - t0[sel]) / 1e3, (t1[sel] - s0) / 1e3
+        print(f"\nupdate kernel, {len(sel)} blocks: duration us min / median / p90 / max = {du.min():.2f} / {np.median(du):.2f} / "
+              f"{np.quantile(du, 0.9):.2f} / {du.max():.2f}; last block out {out_.max():.2f} us after the first block in")
+        late = sel[np.argsort(t1[sel])[-max(1, len(sel) // 10):]]
+        print(f"  blocks that finish last (index range {blk[late].min()}..{blk[late].max()}, median index {int(np.median(blk[late]))})")
 h.close()
