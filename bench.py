@@ -321,7 +321,7 @@ class Workload:
             uid = [G.Handle.dp_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             self.h.dp_init(uid[0], rank, world)
-        # every step graph (16/8/4/2/1 steps, host-index step) is instantiated here, before any warm-up, so
+        # every step graph (32/28/../8/4/2/1 steps, host-index step) is instantiated here, before any warm-up, so
         # that --warmup is honoured as given and no instantiation lands in a timed region
         self.h.learn_prepare()
         self.seed0 = 1_000_003 * (rank + 1)

@@ -137,7 +137,7 @@ struct goldq {
 
     // CUDA-graph replay of learn steps (goldq_learn_many)
     static constexpr int GRAPH_MAX = 32;
-    static constexpr int GRAPH_CHUNK = 16;       // largest number of steps per graph launch (then 8, 4, 2, 1)
+    static constexpr int GRAPH_CHUNK = 32;       // largest number of steps per graph launch; sizes: multiples of 4, then 2, 1
     static constexpr int STEP_RING = 8;          // pinned staging buffers for the per-step scalars
     int pf_set = 0, pf_have = 0;                 // batch double buffering while capturing (build_graph)
     const StepDev *pf_next = nullptr;
@@ -559,6 +559,14 @@ void drop_graphs(goldq_t *h)
     if (h->dp_graph) { cudaGraphExecDestroy(h->dp_graph); h->dp_graph = nullptr; }
     for (int i = 0; i <= goldq::GRAPH_MAX; i++)
         if (h->graph_exec[i]) { cudaGraphExecDestroy(h->graph_exec[i]); h->graph_exec[i] = nullptr; }
+}
+
+// graph sizes: 1, 2, then the multiples of 4 up to GRAPH_CHUNK (slot 0 = the one-step graph with host indices)
+inline int graph_next_size(int c) { return c == 0 ? 1 : (c < 4 ? c * 2 : c + 4); }
+inline int graph_size_for(int n)
+{
+    if (n >= goldq::GRAPH_CHUNK) return goldq::GRAPH_CHUNK;
+    return n >= 4 ? (n & ~3) : (n >= 2 ? 2 : 1);
 }
 
 // Per-step scalars (and goldq_learn's host index list) travel to the device through THIS kernel reading mapped
@@ -1408,7 +1416,7 @@ int goldq_learn_prepare(goldq_t *h)
         if (rc) return rc;
     }
     if (h->graph_debug != h->debug) { drop_graphs(h); h->graph_debug = h->debug; }
-    for (int slot = 0; slot <= goldq::GRAPH_CHUNK; slot = slot ? slot * 2 : 1) {
+    for (int slot = 0; slot <= goldq::GRAPH_CHUNK; slot = graph_next_size(slot)) {
         if (h->graph_exec[slot]) continue;
         int rc = build_graph(h, slot);
         if (rc) return rc;
@@ -1494,11 +1502,11 @@ static int learn_many_impl(goldq_t *h, int32_t n, uint64_t seed)
         }
         return GOLDQ_OK;
     }
-    // Graphs of 16, 8, 4, 2 and 1 steps (each instantiated once, on first use or by
-    // goldq_learn_prepare): any step count is replayed from graphs, largest first.
+    // Graphs of 32, 28, ... 8, 4, 2 and 1 steps (each instantiated once, on first use or by goldq_learn_prepare): any
+    // step count is replayed from graphs, largest first.  A graph start costs about 16 us (step scalars staged, no
+    // prefetched batch for its first step), so 20 steps are one graph, not 16 + 4.
     while (n > 0) {
-        int c = goldq::GRAPH_CHUNK;
-        while (c > n) c >>= 1;
+        const int c = graph_size_for(n);
         int rc = launch_graph(h, c, seed);
         if (rc) return rc;
         seed += (uint64_t)c;

@@ -366,7 +366,7 @@ def test_learn_many_graph_replay_equals_single_steps(kind):
         h.replay_push(*data)
 
         def steps(n, seed):
-            if mode == "many":                     # graphs of 16/8/4/2/1 steps
+            if mode == "many":                     # graphs of 32/28/../4/2/1 steps
                 h.learn_many(n, seed)
             elif mode == "single":                 # the one-step graph, n times
                 for i in range(n):
@@ -376,7 +376,7 @@ def test_learn_many_graph_replay_equals_single_steps(kind):
                     h.step_breakdown(seed + i)
 
         seed = 1000
-        for n in (5, 37, 2):                       # 37 = 16 + 16 + 4 + 1
+        for n in (5, 37, 2):                       # 37 = 32 + 4 + 1 (graph sizes 32, 28, .. 4, 2, 1)
             steps(n, seed)
             seed += n
             h.sync_target()
@@ -412,7 +412,7 @@ def test_remember_learn_loop_never_rebuilds_graphs(kind):
     h.debug_enable(True)
     h.learn_prepare()
     builds = h.graph_builds()
-    assert builds == 6                              # 16, 8, 4, 2, 1 steps + the host-index step
+    assert builds == 11                             # 32, 28, .. 8, 4, 2, 1 steps + the host-index step
     ev = synth.replay(dims, 120, seed=10)
     for i in range(120):                            # wraps the ring (capacity N)
         h.replay_push(*[x[i:i + 1] for x in ev])
