@@ -2082,6 +2082,7 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
         if (sub != 0 || !live) return;
         bool ok = true;     // false: a peer's word never arrived -- leave theta / m / v / shadows untouched
         if (dp) g = dp_exchange4(push, epoch, i, g, ok);
+        if (dp && threadIdx.x == 0 && g.x == g.x) TRACE_MARK(4);
         if (ok) finish4<FUSE>(d, o, i, g, flat, theta, m, v, w4, m4, v4, ac, sp);
         if (threadIdx.x == 0) TRACE_MARK(3);
     } else if ((int)blockIdx.x < pl.blocksA + pl.blocksB) {
