@@ -419,6 +419,7 @@ struct FFArgs {
     float *q[2];                 // [net]: Q / Q' fp32 [B][A]
     __nv_bfloat16 *h1, *h2;      // (unused)
     int net0;                    // network of blockIdx.y == 0 (predict launches one network: grid.y = 1)
+    int x_ready;                 // the batch tile may be loaded before griddepcontrol.wait (ff_forward2_kernel)
     int keep_h;                  // store the online network's H1 / H2 for the backward pass (learn step) or not (predict)
     int late_trigger;            // release the dependent grid from the epilogue instead of the prologue
     uint32_t *maskbits[2];       // [layer]: Rectify masks of the online network, one bit per unit, [B][FF_H / 32] words; word w
@@ -755,7 +756,7 @@ constexpr size_t ff_smem_bytes()
 //   MMA       one thread of the leader issues tcgen05.mma.cta_group::2; tcgen05.commit multicasts
 //             "stage free" / "accumulator ready" to the barriers of BOTH CTAs
 //   epilogue  8 warps per CTA drain their own TMEM, write H (bf16, K-major SW128 boxes) into their
-//             own shared memory and arrive (release.cluster) on the LEADER's h_lo / h_ready /
+//             own shared memory and arrive (release.cluster) on the LEADER's h_lo / h_box /
 //             acc_free barriers, which the leader's MMA thread acquires at cluster scope
 // Epilogue arithmetic per element pair: two fp32 bias adds (bias staged in shared memory, read as
 // broadcast float4), one cvt.rn.bf16x2, one max.bf16x2 against -0.0 (Rectify keeps the sign of a*0,
@@ -763,6 +764,9 @@ constexpr size_t ff_smem_bytes()
 // Layer 3 uses W3 padded to 128 columns (N = 128: 64 from each CTA; only columns < A are read back).
 // ---------------------------------------------------------------------------
 constexpr int FF2_WSTAGES = 5;
+// order in which layer 3 consumes the k-blocks (= boxes of H2): the two column groups of the epilogue complete boxes
+// 4 and 6 first, then 5 and 7
+__host__ __device__ constexpr int ff2_kperm(int kb) { return (kb == 5 || kb == 6) ? (kb ^ 3) : kb; }
 constexpr uint32_t FF2_WSTAGE_BYTES = 16384;   // this CTA's half of a [64 k][256 n] tile: [2 n-groups][64 k-rows][128 B]
 
 // CODE SIZE MATTERS HERE.  The first version of this kernel was fully unrolled (6 000 SASS instructions,
@@ -794,7 +798,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     uint8_t *sH = smem;                                 // 8 boxes: H1, then H2
     uint8_t *sX = sH + (KH - KD) * FF_BOX;              // aliases the last boxes of H (see ff_forward_kernel)
     uint8_t *sW = sH + KH * FF_BOX;                     // weight ring
-    __shared__ uint64_t full_w[FF2_WSTAGES], empty_w[FF2_WSTAGES], x_full, acc_full[2], acc_free[2], h_ready, h_lo, lo_free;
+    __shared__ uint64_t full_w[FF2_WSTAGES], empty_w[FF2_WSTAGES], x_full, acc_full[2], acc_free[2], h_box[4], h_lo, lo_free;
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_bias[2 * FF_H + 32];
 
@@ -821,7 +825,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         mbar_init(&lo_free, 1);
         // the leader's copies collect the arrivals of both CTAs
         mbar_init(&acc_free[0], 2 * (FF_EPI_THREADS / 32)); mbar_init(&acc_free[1], 2 * (FF_EPI_THREADS / 32));
-        mbar_init(&h_ready, 2);
+        for (int b = 0; b < 4; b++) mbar_init(&h_box[b], 2);     // boxes 4..7 of H: one arrival per CTA
         mbar_init(&h_lo, 2);
         fence_barrier_init();
     }
@@ -834,6 +838,17 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     cluster_sync();          // both CTAs' barriers are initialised and both TMEM allocations exist
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
+    // the gathered batch does not come from the kernel this one is launched behind (x_ready: it was gathered on the
+    // previous step's side branch, a full dependency): its tile is requested before the wait
+    if (warp == 0 && g.x_ready) {
+        if (elect_one()) {
+            const uint32_t x_full_leader = mapa_u32(&x_full, 0);
+            if (rank == 0) mbar_expect_tx(&x_full, 2 * X_BYTES);
+#pragma unroll
+            for (int kb = 0; kb < KD; kb++) tma_load_2d_pair(sX + kb * FF_BOX, tmX, kb * 64, m0, x_full_leader);
+        }
+        __syncwarp();
+    }
     pdl_wait();
     if (threadIdx.x == 0) FF_STAMP(1);
 
@@ -841,9 +856,11 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         // ===== TMA producer (both CTAs): own X tile, own half of every weight tile =====
         if (elect_one()) {
             const uint32_t x_full_leader = mapa_u32(&x_full, 0);
-            if (rank == 0) mbar_expect_tx(&x_full, 2 * X_BYTES);
+            if (!g.x_ready) {
+                if (rank == 0) mbar_expect_tx(&x_full, 2 * X_BYTES);
 #pragma unroll
-            for (int kb = 0; kb < KD; kb++) tma_load_2d_pair(sX + kb * FF_BOX, tmX, kb * 64, m0, x_full_leader);
+                for (int kb = 0; kb < KD; kb++) tma_load_2d_pair(sX + kb * FF_BOX, tmX, kb * 64, m0, x_full_leader);
+            }
             const uint32_t full_leader0 = mapa_u32(&full_w[0], 0);
             const int nr = (int)rank * 128;                        // this CTA's half of a 256-column tile
             // ring stage `it` = two boxes of [64 k][64 n]: layers 1-2 -> two n-groups of one k-block,
@@ -861,7 +878,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 } else {
                     const int j = it - NB1 - NB2;
                     tm = tmW3;
-                    n0 = (int)rank * 64; k0 = j * 128; n1 = n0; k1 = k0 + 64;
+                    n0 = (int)rank * 64; k0 = ff2_kperm(2 * j) * 64; n1 = n0; k1 = ff2_kperm(2 * j + 1) * 64;
                 }
                 const int s = it % FF2_WSTAGES;
                 const uint32_t ph = (it / FF2_WSTAGES) & 1;
@@ -875,57 +892,106 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         }
     } else if (warp == 1) {
         if (rank == 0) {
-            // ===== MMA issuer (leader only): one loop over the NB ring stages =====
+            // ===== MMA issuer: the leader's warp 1, three loop nests (one per layer) =====
             // All waits are CTA-scope acquires: operands arrive through the async proxy (TMA), and the peer's
             // epilogue publishes H with fence.proxy.async + bar.sync before it arrives on the leader's barrier.
-            mbar_wait_bounded<false>(&x_full, 0);
-            if (lane == 0) FF_STAMP(2);
-#pragma unroll 1
-            for (int b = 0; b < NB; b++) {
-                // what this stage feeds
-                const int layer = b < NB1 ? 0 : (b < NB1 + NB2 ? 1 : 2);
-                const int j = b - (layer == 0 ? 0 : (layer == 1 ? NB1 : NB1 + NB2));
-                const int per = layer == 0 ? KD : KH;
-                const int half = (layer < 2 && j >= per) ? 1 : 0;
-                const int kb = layer < 2 ? j - half * per : 2 * j;         // first k-block of the stage
-                // gates: the A operand of layers 2 / 3 is written by the epilogues of both CTAs.  The first half
-                // of the k-blocks needs only what the epilogue of accumulator half 0 produced.
-                if (layer > 0 && half == 0 && (kb == 0 || kb == KH / 2)) {
-                    const uint32_t par = layer == 1 ? 0u : 1u;
-                    if (kb == 0) { mbar_wait_bounded<false>(&h_lo, par); mbar_wait_bounded<false>(&acc_free[0], par); }
-                    else { mbar_wait_bounded<false>(&h_ready, par); mbar_wait_bounded<false>(&acc_free[1], par); }
+            //
+            // THIS THREAD HAS NO SLACK.  tcgen05.mma issue blocks until the previous MMA has started, so of a stage's
+            // 4 x 139 cycles only the last ~280 are left for everything else the thread does before the next stage's
+            // first MMA must be in the queue; whatever exceeds that is added to EVERY stage (tools/ff_stamps.py: the
+            // single rolled loop that derived layer / half / k-block / ring slot from its index ran at 566 cycles per
+            // stage, 636 with three more selects in it and 856 with one more barrier test).  Hence: no index
+            // arithmetic (nested loops, ring slot and phase carried), descriptors advanced by adding to their low word,
+            // gates only where a layer really has to wait.  The WHOLE WARP runs the loops and one elected lane issues:
+            // tcgen05.mma takes its operands from uniform registers, and inside an `if (lane == 0)` region the compiler
+            // has to move every descriptor there with an ELECT / R2UR.BROADCAST loop (671 cycles per stage).  Layer 2
+            // waits once for the second half of H1 (the last box of each column group), layer 3 -- stages twice as
+            // long -- box by box, in the order the epilogue completes them (ff2_kperm).
+            {
+                mbar_wait_bounded<false>(&x_full, 0);
+                if (lane == 0) FF_STAMP(2);
+                constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | ((uint32_t)SW128 << 29);   // SBO 1024, bit 46, SWIZZLE_128B
+                const uint32_t ax_lo = ((smem_u32(sX) & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);       // A: LBO 16
+                const uint32_t ah_lo = ((smem_u32(sH) & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);
+                const uint32_t bw_lo = ((smem_u32(sW) & 0x3FFFFu) >> 4) | ((8192u >> 4) << 16);     // B: LBO 8192
+                uint32_t slot = 0, ph = 0;
+                int nst = 0;                                    // (stage counter, stamps only)
+                // one ring stage: wait for its weights, 4 MMAs per k-block (nkb = 1 or 2 boxes of A), free the slot
+                auto stage = [&](uint32_t a0_lo, uint32_t a1_lo, int nkb, uint32_t d_tmem, uint32_t idesc, uint32_t acc) {
+                    mbar_wait_bounded<false>(&full_w[slot], ph);
                     tc_fence_after();
-                }
-                const int s = b % FF2_WSTAGES;
-                const uint32_t ph = (b / FF2_WSTAGES) & 1;
-                mbar_wait_bounded<false>(&full_w[s], ph);
-                tc_fence_after();
-                if (lane == 0 && 32 + 2 * b + 1 < 80) FF_STAMP(32 + 2 * b);
-                if (elect_one()) {
-                    const uint32_t baddr = smem_u32(sW + s * FF2_WSTAGE_BYTES);
-                    const uint32_t aaddr = smem_u32(layer == 0 ? sX : sH) + (uint32_t)kb * FF_BOX;
-                    const uint32_t d_tmem = tmem + (uint32_t)half * 256u;
-                    const uint32_t idesc = layer == 2 ? IDESC_128 : IDESC_256;
-                    const int nkb = layer == 2 ? 2 : 1;
-                    uint32_t acc = kb == 0 ? 0u : 1u;
-                    for (int h = 0; h < nkb; h++) {
+                    if (lane == 0 && 32 + 2 * nst + 1 < 80) FF_STAMP(32 + 2 * nst);
+                    if (elect_one()) {
+                        const uint32_t b_lo = bw_lo + slot * (FF2_WSTAGE_BYTES >> 4);
 #pragma unroll
                         for (int kk = 0; kk < BK / UK; kk++) {
-                            mma_bf16_pair(d_tmem, make_smem_desc(aaddr + h * FF_BOX + kk * 32, 16, 1024),
-                                          make_smem_desc(baddr + h * 8192 + kk * 2048, 8192, 1024), idesc, acc);
+                            mma_bf16_pair_lohi(d_tmem, a0_lo + kk * (32 >> 4), DESC_HI, b_lo + kk * (2048 >> 4), DESC_HI, idesc, acc);
                             acc = 1u;
                         }
+                        if (nkb == 2) {
+#pragma unroll
+                            for (int kk = 0; kk < BK / UK; kk++)
+                                mma_bf16_pair_lohi(d_tmem, a1_lo + kk * (32 >> 4), DESC_HI, b_lo + (8192 >> 4) + kk * (2048 >> 4), DESC_HI, idesc, 1u);
+                        }
+                        mma_commit_pair(&empty_w[slot], BOTH);
                     }
-                    mma_commit_pair(&empty_w[s], BOTH);
-                    // accumulator (half) complete / the first four H1 boxes are no longer read
-                    if (layer < 2 && kb == per - 1) mma_commit_pair(&acc_full[half], BOTH);
-                    if (layer == 2 && j == NB3 - 1) mma_commit_pair(&acc_full[0], BOTH);
-                    if (layer == 1 && half == 1 && kb == KH / 2 - 1) mma_commit_pair(&lo_free, BOTH);
+                    __syncwarp();
+                    if (++slot == FF2_WSTAGES) { slot = 0; ph ^= 1u; }
+                };
+                auto commit = [&](uint64_t *bar) {
+                    if (elect_one()) mma_commit_pair(bar, BOTH);
+                    __syncwarp();
+                };
+                // ---- layer 1: A = X
+#pragma unroll 1
+                for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+                    for (int kb = 0; kb < KD; kb++) {
+                        stage(ax_lo + kb * (FF_BOX >> 4), 0u, 1, tmem + half * 256u, IDESC_256, kb ? 1u : 0u);
+                        if (lane == 0 && 32 + 2 * nst + 1 < 80) FF_STAMP(32 + 2 * nst + 1);
+                        nst++;
+                    }
+                    commit(&acc_full[half]);
                 }
-                __syncwarp();
-                if (lane == 0 && 32 + 2 * b + 1 < 80) FF_STAMP(32 + 2 * b + 1);
+                // ---- layer 2: A = H1 (boxes 0..3 after h_lo, 4..7 after the last boxes of both column groups)
+#pragma unroll 1
+                for (int half = 0; half < 2; half++) {
+                    if (half == 0) { mbar_wait_bounded<false>(&h_lo, 0); mbar_wait_bounded<false>(&acc_free[0], 0); }
+                    else mbar_wait_bounded<false>(&acc_free[1], 0);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int kb = 0; kb < KH; kb++) {
+                        if (half == 0 && kb == KH / 2) {
+                            mbar_wait_bounded<false>(&h_box[1], 0); mbar_wait_bounded<false>(&h_box[3], 0);
+                            tc_fence_after();
+                        }
+                        stage(ah_lo + kb * (FF_BOX >> 4), 0u, 1, tmem + half * 256u, IDESC_256, kb ? 1u : 0u);
+                        // the first four H1 boxes are no longer read: H2 may land on them
+                        if (half == 1 && kb == KH / 2 - 1) commit(&lo_free);
+                        if (lane == 0 && 32 + 2 * nst + 1 < 80) FF_STAMP(32 + 2 * nst + 1);
+                        nst++;
+                    }
+                    commit(&acc_full[half]);
+                }
+                // ---- layer 3: A = H2, two boxes per stage, N = 128
+                mbar_wait_bounded<false>(&h_lo, 1); mbar_wait_bounded<false>(&acc_free[0], 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int j = 0; j < NB3; j++) {
+                    const int b0 = ff2_kperm(2 * j), b1 = ff2_kperm(2 * j + 1);
+                    if (j >= NB3 / 2) {
+                        mbar_wait_bounded<false>(&h_box[b0 - KH / 2], 1); mbar_wait_bounded<false>(&h_box[b1 - KH / 2], 1);
+                        tc_fence_after();
+                    }
+                    stage(ah_lo + b0 * (FF_BOX >> 4), ah_lo + b1 * (FF_BOX >> 4), 2, tmem, IDESC_128, j ? 1u : 0u);
+                    if (lane == 0 && 32 + 2 * nst + 1 < 80) FF_STAMP(32 + 2 * nst + 1);
+                    nst++;
+                }
+                commit(&acc_full[0]);
+                if (lane == 0) FF_STAMP(9);
+                mbar_wait_bounded<false>(&acc_free[1], 1);     // (every remote arrival is consumed before the pair may exit)
             }
-            if (lane == 0) FF_STAMP(9);
+            __syncwarp();
         }
     } else {
         // ===== epilogue warps (both CTAs, own rows) =====
@@ -935,7 +1001,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         const int et = threadIdx.x - 64;        // 0..255
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t acc_free_leader0 = mapa_u32(&acc_free[0], 0);
-        const uint32_t h_lo_leader = mapa_u32(&h_lo, 0), h_ready_leader = mapa_u32(&h_ready, 0);
+        const uint32_t h_lo_leader = mapa_u32(&h_lo, 0), h_box_leader0 = mapa_u32(&h_box[0], 0);
         // biases of the three layers -> shared memory (read back as broadcast float4)
         for (int i = et; i < 2 * FF_H + 32; i += FF_EPI_THREADS) {
             float v = 0.f;
@@ -947,6 +1013,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         asm volatile("bar.sync 1, 256;" ::: "memory");
 
         const __nv_bfloat162 neg0 = __floats2bfloat162_rn(-0.0f, -0.0f), zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+        const bool store_early = net == 0 && g.keep_h == 1;
         // phases: (layer 1, half 0), (layer 1, half 1), (layer 2, half 0), (layer 2, half 1) -- one loop body.
         // H2 overwrites H1 in place: its first half may be written once the layer-2 MMAs of accumulator half 1
         // have consumed H1 boxes 0..3 (lo_free), its second half once every layer-2 MMA has retired.
@@ -956,8 +1023,8 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
             mbar_wait_bounded<false>(&acc_full[half], (uint32_t)layer);
             if (p == 2) {
                 mbar_wait_bounded<false>(&lo_free, 0);
-                // the TMA store of H1 must have finished reading the tile before H2 lands on it
-                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                // the TMA stores of H1 must have finished reading the tile before H2 lands on it
+                if ((et & 127) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             if (p == 3) mbar_wait_bounded<false>(&acc_full[1], 1);   // (same barrier as above; kept for symmetry of the listing)
@@ -996,6 +1063,23 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 for (int v = 0; v < 4; v++)
                     sts128(dst + (((ch0 + v) ^ (rt & 7)) << 4),
                                make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]));
+                // The online network's activations leave box by box, as soon as the four warps of this column group
+                // have written one: a single 128 KB burst at the end of a layer kept the TMA unit and the shared-memory
+                // port busy for ~2.6 k cycles, during which the weight ring ran dry (tools/ff_stamps.py; 17.8 -> 16.3 us).
+                // The same point releases the boxes of the second half to the MMA thread one by one.
+                if ((c & 1) && (store_early || half == 1)) {
+                    fence_proxy_async_smem();
+                    if (cg == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+                    else asm volatile("bar.sync 4, 128;" ::: "memory");
+                    if ((et & 127) == 0) {
+                        const int box = c0 >> 6;
+                        if (half == 1) mbar_arrive_cluster(h_box_leader0 + (uint32_t)(box - KH / 2) * 8u);
+                        if (store_early) {
+                            tma_store_2d(layer == 0 ? &tmH1 : &tmH2, sH + box * FF_BOX, 64 * box, m0);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                }
             }
             if (net == 0 && g.keep_h && m0 + rt < g.B)
                 *reinterpret_cast<uint4 *>(g.maskbits[layer] + (size_t)(m0 + rt) * (FF_H / 32) + (cbase >> 5)) =
@@ -1003,19 +1087,13 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc_free_leader0 + (uint32_t)half * 8u);
-            // this half of H is complete in this CTA: visible to the async proxy (MMA of the next layer, TMA store)
-            fence_proxy_async_smem();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (et == 0) {
-                if (half == 1 && net == 0 && g.keep_h) {   // the backward pass needs the online network's activations
-                    const CUtensorMap *tmH = layer == 0 ? &tmH1 : &tmH2;
-#pragma unroll 1
-                    for (int b = 0; b < KH; b++) tma_store_2d(tmH, sH + b * FF_BOX, 64 * b, m0);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                mbar_arrive_cluster(half == 0 ? h_lo_leader : h_ready_leader);
-                FF_STAMP(14 + p);
+            if (half == 0) {
+                // the first half of H is complete in this CTA: visible to the async proxy (MMA of the next layer)
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et == 0) mbar_arrive_cluster(h_lo_leader);
             }
+            if (et == 0) FF_STAMP(14 + p);
         }
 
         // ---- layer 3: Q = acc + b3 -> fp32 [B][A] (A <= 32: one chunk), staged in the idle weight ring
@@ -1025,36 +1103,40 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
             mbar_wait_bounded<false>(&acc_full[0], 0);          // third completion of acc_full[0]: parity 0 again
             tc_fence_after();
             if (et == 0) FF_STAMP(18);
-            uint32_t r[32];
-            tmem_ld_32x32(tq, r);
-            tmem_ld_wait();
-            tc_fence_before();
+            // (rolled loops: this code runs once per CTA, and straight-line code executed once costs its own
+            // instruction fetch -- the 32-column unrolled version took 1 900 cycles from "accumulator ready" to "staged")
             float *sQ = reinterpret_cast<float *>(sW);
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const float v = __uint_as_float(r[j]) + s_bias[2 * FF_H + j];
-                if (j < g.A) sts32(sQ + rt * g.A + j, v);
-            }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            const int nq = ((g.B - m0 < BM) ? g.B - m0 : BM) * g.A;
-            float *dst = g.q[net] + (size_t)m0 * g.A;
-            // (A <= 32: at most 32 floats per thread; eight independent loads in flight)
 #pragma unroll 1
-            for (int i0 = et; i0 < nq; i0 += 8 * 128) {
-                float v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = (i0 + 128 * u < nq) ? lds32(sQ + i0 + 128 * u) : 0.f;
+            for (int j0 = 0; j0 < g.A; j0 += 8) {
+                uint32_t r8[8];
+                tmem_ld_32x32_x8(tq + (uint32_t)j0, r8);
+                tmem_ld_wait();
 #pragma unroll
                 for (int u = 0; u < 8; u++)
+                    if (j0 + u < g.A) sts32(sQ + rt * g.A + j0 + u, __uint_as_float(r8[u]) + s_bias[2 * FF_H + j0 + u]);
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (et == 0) FF_STAMP(20);
+            const int nq = ((g.B - m0 < BM) ? g.B - m0 : BM) * g.A;
+            float *dst = g.q[net] + (size_t)m0 * g.A;
+#pragma unroll 1
+            for (int i0 = et; i0 < nq; i0 += 4 * 128) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = (i0 + 128 * u < nq) ? lds32(sQ + i0 + 128 * u) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
                     if (i0 + 128 * u < nq) dst[i0 + 128 * u] = v[u];
             }
+            if (et == 0) FF_STAMP(21);
         }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if ((et & 127) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         if (et == 0) FF_STAMP(19);
     }
 #undef FF_STAMP
     tc_fence_before();
-    cluster_sync();          // nobody leaves while the pair's MMAs, commits or remote arrives may still touch it
+    cluster_sync_exit();     // nobody leaves while the pair's MMAs, commits or remote arrives may still touch it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_pair(tmem, 512);
@@ -1342,7 +1424,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     }
     tc_fence_before();
-    cluster_sync();
+    cluster_sync_exit();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_pair(tmem, 256);
@@ -1625,7 +1707,9 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
             for (int u = 0; u < DZ_MAXCH; u++) {
                 const int c = c0 + lane + 32 * u;
                 const bool live = c < nch && rw0 + k < B;
-                wv[k][u] = live ? ld_dep(reinterpret_cast<const uint4 *>(w3t + (int64_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
+                // (W3^T is not written by the kernel this one follows, and only A of its rows are ever read: through L1,
+                // 18 KB per SM instead of 8 MB of L2 -> SM traffic; the address depends on a load behind the wait)
+                wv[k][u] = live ? __ldca(reinterpret_cast<const uint4 *>(w3t + (int64_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
             }
         if (m2bits) {            // the forward's mask words (FFArgs::maskbits): 4 bytes instead of the 16 bytes of H2
 #pragma unroll
@@ -2234,6 +2318,18 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     if (!load_encode(err)) return nullptr;
     {
         cudaError_t e = configure_all_gemms();
+        // The small kernels between the GEMMs ask for the same shared-memory carve-out as the GEMMs: an SM re-partitions
+        // its L1 / shared memory only when it is idle, so a dependent GEMM CTA (200 KB) could not become resident next to
+        // the last blocks of a predecessor that ran with the default (small) carve-out, and its prologue (TMEM
+        // allocation, barrier set-up, cluster sync) was not hidden by the programmatic launch.  (GOLDQ_NO_CARVEOUT: off)
+        if (getenv("GOLDQ_NO_CARVEOUT") == nullptr) {
+            const int mx = (int)cudaSharedmemCarveoutMaxShared;
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_update_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_update_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_update_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_td_dz2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        }
         if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return nullptr; }
     }
     WideState *w = new WideState();
@@ -2528,7 +2624,7 @@ static cudaError_t launch_pair_gemm(const CUtensorMap &ta, const CUtensorMap &tb
 
 // the fused forward of both networks on batch set `bt` (pair kernel when the slab count is even)
 static cudaError_t launch_fused_forward(WideState *w, WideState::BatchSet &bt, const float *theta, const float *theta_t,
-                                        cudaStream_t st, bool pdl, int only_net = -1, float *q_out = nullptr)
+                                        cudaStream_t st, bool pdl, int only_net = -1, float *q_out = nullptr, bool x_ready = false)
 {
     // only_net < 0: the learn step's launch (both networks, online activations kept); else one network of a
     // predict launch (bt.tm_x_a = the states, Q -> q_out)
@@ -2545,7 +2641,11 @@ static cudaError_t launch_fused_forward(WideState *w, WideState::BatchSet &bt, c
     static const bool early = getenv("GOLDQ_EARLY_TRIGGER") != nullptr;      // diagnostic: round-2's first placement
     fa.late_trigger = early ? 0 : 1;
     fa.net0 = only_net < 0 ? 0 : only_net;
-    fa.keep_h = only_net < 0 ? 1 : 0;
+    // (GOLDQ_FF_KEEPH=0, diagnostic: the activations are not stored -- results garbage)
+    static const int keeph = getenv("GOLDQ_FF_KEEPH") ? atoi(getenv("GOLDQ_FF_KEEPH")) : 1;
+    fa.keep_h = only_net < 0 ? keeph : 0;
+    static const bool no_xpre = getenv("GOLDQ_NO_XPREFETCH") != nullptr;
+    fa.x_ready = (x_ready && !no_xpre) ? 1 : 0;
     fa.maskbits[0] = w->m1bits; fa.maskbits[1] = w->m2bits;
     if (only_net >= 0) fa.q[only_net] = q_out;
     dim3 grid((B + BM - 1) / BM, only_net < 0 ? 2 : 1);
@@ -2605,9 +2705,10 @@ int wide_time_forward(WideState *w, const float *theta, const float *theta_t, cu
     WCK(cudaEventCreate(&e0));
     WCK(cudaEventCreate(&e1));
     WideState::BatchSet &bt = w->bs[w->last_set];
-    for (int i = 0; i < 3; i++) WCK(launch_fused_forward(w, bt, theta, theta_t, st, w->pdl));
+    // (the batch was gathered long before: as in a graph-replayed step, its tile may be requested ahead of the wait)
+    for (int i = 0; i < 3; i++) WCK(launch_fused_forward(w, bt, theta, theta_t, st, w->pdl, -1, nullptr, true));
     WCK(cudaEventRecord(e0, st));
-    for (int i = 0; i < reps; i++) WCK(launch_fused_forward(w, bt, theta, theta_t, st, w->pdl));
+    for (int i = 0; i < reps; i++) WCK(launch_fused_forward(w, bt, theta, theta_t, st, w->pdl, -1, nullptr, true));
     WCK(cudaEventRecord(e1, st));
     WCK(cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -2665,7 +2766,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     if (w->skip & 2) {
     } else if (w->ff) {
         // forward of both networks, all three layers, one launch
-        WCK(launch_fused_forward(w, bt, s.theta, s.theta_t, st, pdl));
+        WCK(launch_fused_forward(w, bt, s.theta, s.theta_t, st, pdl, -1, nullptr, s.have && !(w->skip & 1)));
         launches += 1;
         mark(w->ff2 ? "fused forward L1-L3 online+target, CTA pairs (tcgen05 cta_group::2)"
                     : "fused forward L1-L3 online+target (tcgen05)");

@@ -14,7 +14,8 @@ NAMES[0], NAMES[1], NAMES[2], NAMES[9] = "entry", "after cluster_sync+pdl_wait",
 for p_, nm in enumerate(["L1 half0", "L1 half1", "L2 half0", "L2 half1"]):
     NAMES[10 + p_] = f"EPI: {nm} accumulator ready"
     NAMES[14 + p_] = f"EPI: {nm} written, arrived"
-NAMES[18], NAMES[19] = "EPI: Q accumulator ready", "EPI: Q written"
+NAMES[18], NAMES[19] = "EPI: Q accumulator ready", "EPI: Q written, H stores read out"
+NAMES[20], NAMES[21] = "EPI: Q staged", "EPI: Q copied out"
 for blk in range(24):
     NAMES[32 + 2 * blk], NAMES[33 + 2 * blk] = f"MMA: stage {blk} operands ready", f"MMA: stage {blk} issued"
 for i in range(16):
