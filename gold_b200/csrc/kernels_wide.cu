@@ -775,8 +775,8 @@ constexpr uint32_t FF2_WSTAGE_BYTES = 16384;   // this CTA's half of a [64 k][25
 // instruction fetches (the first k-block after each gate took 2.5 k cycles, the following ones 450).  Every
 // role is therefore ONE rolled loop over a schedule computed arithmetically from the iteration index, so
 // that its instructions are fetched once and re-executed.
-template <int KD>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FF_THREADS, 1)
+template <int KD, int EW>   // EW = epilogue warps per CTA: 8 (two column groups of 128 per accumulator half) or 16 (four of 64)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
                    const __grid_constant__ CUtensorMap tmW1_0, const __grid_constant__ CUtensorMap tmW1_1,
                    const __grid_constant__ CUtensorMap tmW2_0, const __grid_constant__ CUtensorMap tmW2_1,
@@ -792,6 +792,8 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     constexpr int NB1 = 2 * KD, NB2 = 2 * KH, NB3 = KH / 2;   // ring stages consumed by layers 1, 2, 3
     constexpr int NB = NB1 + NB2 + NB3;
     constexpr uint16_t BOTH = 3;
+    constexpr int EPI_THREADS = 32 * EW, NCG = EW / 4, NC = 8 / NCG;   // column groups per half, 32-column chunks per thread and phase
+    static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -824,7 +826,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
         mbar_init(&lo_free, 1);
         // the leader's copies collect the arrivals of both CTAs
-        mbar_init(&acc_free[0], 2 * (FF_EPI_THREADS / 32)); mbar_init(&acc_free[1], 2 * (FF_EPI_THREADS / 32));
+        mbar_init(&acc_free[0], 2 * EW); mbar_init(&acc_free[1], 2 * EW);
         for (int b = 0; b < 4; b++) mbar_init(&h_box[b], 2);     // boxes 4..7 of H: one arrival per CTA
         mbar_init(&h_lo, 2);
         fence_barrier_init();
@@ -871,8 +873,12 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 int n0, k0, n1, k1;
                 if (it < NB1 + NB2) {
                     const bool l1 = it < NB1;
-                    const int j = l1 ? it : it - NB1, per = l1 ? KD : KH;
-                    const int half = j >= per ? 1 : 0, kb = j - half * per;
+                    const int j = l1 ? it : it - NB1;
+                    // layer 1: half 0, half 1.  Layer 2 in four groups of KH/2 stages (see the MMA issuer):
+                    // (half 0, k-blocks 0..3), (half 1, 0..3), (half 0, 4..7), (half 1, 4..7)
+                    const int grp = j / (KH / 2);
+                    const int half = l1 ? (j >= KD ? 1 : 0) : (grp & 1);
+                    const int kb = l1 ? j - half * KD : (grp >> 1) * (KH / 2) + j % (KH / 2);
                     tm = l1 ? tmW1 : tmW2;
                     n0 = half * 256 + nr; k0 = kb * 64; n1 = n0 + 64; k1 = k0;
                 } else {
@@ -953,25 +959,30 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                     }
                     commit(&acc_full[half]);
                 }
-                // ---- layer 2: A = H1 (boxes 0..3 after h_lo, 4..7 after the last boxes of both column groups)
+                // ---- layer 2: A = H1, in four groups of KH/2 stages:
+                //   (half 0, k-blocks 0..3) after h_lo | (half 1, 0..3) once accumulator half 1 is drained | (half 0, 4..7)
+                //   after the last H1 boxes of both column groups | (half 1, 4..7).
+                // H2's first half is written IN PLACE over H1 boxes 0..3: in this order they have been read by both
+                // halves after 8 of the 16 stages (lo_free), so the epilogue of half 0 starts when its accumulator is
+                // complete (12 stages) instead of waiting for stage 12 of the old order (half 0 first, then half 1).
 #pragma unroll 1
-                for (int half = 0; half < 2; half++) {
-                    if (half == 0) { mbar_wait_bounded<false>(&h_lo, 0); mbar_wait_bounded<false>(&acc_free[0], 0); }
-                    else mbar_wait_bounded<false>(&acc_free[1], 0);
+                for (int grp = 0; grp < 4; grp++) {
+                    const int half = grp & 1, kb0 = (grp >> 1) * (KH / 2);
+                    if (grp == 0) { mbar_wait_bounded<false>(&h_lo, 0); mbar_wait_bounded<false>(&acc_free[0], 0); }
+                    else if (grp == 1) mbar_wait_bounded<false>(&acc_free[1], 0);
+                    else if (grp == 2) {
+                        mbar_wait_bounded<false>(&h_box[1], 0); mbar_wait_bounded<false>(&h_box[3], 0);
+                        if (NCG == 4) { mbar_wait_bounded<false>(&h_box[0], 0); mbar_wait_bounded<false>(&h_box[2], 0); }
+                    }
                     tc_fence_after();
 #pragma unroll 1
-                    for (int kb = 0; kb < KH; kb++) {
-                        if (half == 0 && kb == KH / 2) {
-                            mbar_wait_bounded<false>(&h_box[1], 0); mbar_wait_bounded<false>(&h_box[3], 0);
-                            tc_fence_after();
-                        }
+                    for (int kb = kb0; kb < kb0 + KH / 2; kb++) {
                         stage(ah_lo + kb * (FF_BOX >> 4), 0u, 1, tmem + half * 256u, IDESC_256, kb ? 1u : 0u);
-                        // the first four H1 boxes are no longer read: H2 may land on them
-                        if (half == 1 && kb == KH / 2 - 1) commit(&lo_free);
                         if (lane == 0 && 32 + 2 * nst + 1 < 80) FF_STAMP(32 + 2 * nst + 1);
                         nst++;
                     }
-                    commit(&acc_full[half]);
+                    if (grp == 1) commit(&lo_free);      // the first four H1 boxes are no longer read: H2 may land on them
+                    if (grp >= 2) commit(&acc_full[half]);
                 }
                 // ---- layer 3: A = H2, two boxes per stage, N = 128
                 mbar_wait_bounded<false>(&h_lo, 1); mbar_wait_bounded<false>(&acc_free[0], 1);
@@ -996,21 +1007,21 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     } else {
         // ===== epilogue warps (both CTAs, own rows) =====
         const int q = warp & 3;                 // TMEM lane quarter
-        const int cg = (warp - 2) >> 2;         // column group within a half: chunks cg*4 .. cg*4+3
+        const int cg = (warp - 2) >> 2;         // column group within a half: chunks cg*NC .. cg*NC+NC-1
         const int rt = q * 32 + lane;           // row within the slab
-        const int et = threadIdx.x - 64;        // 0..255
+        const int et = threadIdx.x - 64;        // 0..EPI_THREADS-1
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t acc_free_leader0 = mapa_u32(&acc_free[0], 0);
         const uint32_t h_lo_leader = mapa_u32(&h_lo, 0), h_box_leader0 = mapa_u32(&h_box[0], 0);
         // biases of the three layers -> shared memory (read back as broadcast float4)
-        for (int i = et; i < 2 * FF_H + 32; i += FF_EPI_THREADS) {
+        for (int i = et; i < 2 * FF_H + 32; i += EPI_THREADS) {
             float v = 0.f;
             if (i < FF_H) v = ld_dep(g.bias[net][0] + i);
             else if (i < 2 * FF_H) v = ld_dep(g.bias[net][1] + i - FF_H);
             else if (i - 2 * FF_H < g.A) v = ld_dep(g.bias[net][2] + i - 2 * FF_H);
             s_bias[i] = v;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 
         const __nv_bfloat162 neg0 = __floats2bfloat162_rn(-0.0f, -0.0f), zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
         const bool store_early = net == 0 && g.keep_h == 1;
@@ -1025,20 +1036,20 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 mbar_wait_bounded<false>(&lo_free, 0);
                 // the TMA stores of H1 must have finished reading the tile before H2 lands on it
                 if ((et & 127) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             }
             if (p == 3) mbar_wait_bounded<false>(&acc_full[1], 1);   // (same barrier as above; kept for symmetry of the listing)
             tc_fence_after();
             if (et == 0) FF_STAMP(10 + p);
-            const int cbase = half * 256 + cg * 128;                 // first column of this warp's four chunks
+            const int cbase = half * 256 + cg * (32 * NC);           // first column of this warp's NC chunks
             const float *bias = s_bias + layer * FF_H + cbase;
             uint32_t r[2][32];
-            uint32_t mw[4];
+            uint32_t mw[NC];
             tmem_ld_32x32(tq + (uint32_t)cbase, r[0]);
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < NC; c++) {
                 tmem_ld_wait();
-                if (c < 3) tmem_ld_32x32(tq + (uint32_t)(cbase + 32 * (c + 1)), r[(c + 1) & 1]);
+                if (c < NC - 1) tmem_ld_32x32(tq + (uint32_t)(cbase + 32 * (c + 1)), r[(c + 1) & 1]);
                 uint32_t packed[16];
                 uint32_t mwc = 0u;
 #pragma unroll
@@ -1069,8 +1080,7 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 // The same point releases the boxes of the second half to the MMA thread one by one.
                 if ((c & 1) && (store_early || half == 1)) {
                     fence_proxy_async_smem();
-                    if (cg == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
-                    else asm volatile("bar.sync 4, 128;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(3 + cg) : "memory");
                     if ((et & 127) == 0) {
                         const int box = c0 >> 6;
                         if (half == 1) mbar_arrive_cluster(h_box_leader0 + (uint32_t)(box - KH / 2) * 8u);
@@ -1082,15 +1092,18 @@ ff_forward2_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
                 }
             }
             if (net == 0 && g.keep_h && m0 + rt < g.B)
-                *reinterpret_cast<uint4 *>(g.maskbits[layer] + (size_t)(m0 + rt) * (FF_H / 32) + (cbase >> 5)) =
-                    make_uint4(mw[0], mw[1], mw[2], mw[3]);
+            {
+                uint32_t *mdst = g.maskbits[layer] + (size_t)(m0 + rt) * (FF_H / 32) + (cbase >> 5);
+                if (NC == 4) *reinterpret_cast<uint4 *>(mdst) = make_uint4(mw[0], mw[1], mw[NC - 2], mw[NC - 1]);
+                else *reinterpret_cast<uint2 *>(mdst) = make_uint2(mw[0], mw[1]);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc_free_leader0 + (uint32_t)half * 8u);
             if (half == 0) {
                 // the first half of H is complete in this CTA: visible to the async proxy (MMA of the next layer)
                 fence_proxy_async_smem();
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 if (et == 0) mbar_arrive_cluster(h_lo_leader);
             }
             if (et == 0) FF_STAMP(14 + p);
@@ -1551,9 +1564,11 @@ cudaError_t configure_all_gemms()
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pair_gemm_kernel<PG_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_gemm_smem_bytes());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pair_gemm_kernel<PG_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_gemm_smem_bytes());
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(ff_forward2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff2_smem_bytes<1>());
+        e = cudaFuncSetAttribute(ff_forward2_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff2_smem_bytes<1>());
+
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(ff_forward2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff2_smem_bytes<2>());
+        e = cudaFuncSetAttribute(ff_forward2_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff2_smem_bytes<2>());
+
     return e;
 }
 
@@ -2649,11 +2664,13 @@ static cudaError_t launch_fused_forward(WideState *w, WideState::BatchSet &bt, c
     fa.maskbits[0] = w->m1bits; fa.maskbits[1] = w->m2bits;
     if (only_net >= 0) fa.q[only_net] = q_out;
     dim3 grid((B + BM - 1) / BM, only_net < 0 ? 2 : 1);
+    // (8 epilogue warps.  16 -- four column groups of 64, 96 registers -- measured SLOWER, 15.9 vs 14.7 us: a phase drains
+    // 128 KB of accumulator through the 64 B/clk TMEM read path, 2 048 cycles whatever the number of warps)
     if (w->ff2 && d.D == 128)
-        return launch_k(ff_forward2_kernel<2>, grid, dim3(FF_THREADS), ff2_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
+        return launch_k(ff_forward2_kernel<2, 8>, grid, dim3(64 + 32 * 8), ff2_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a, w->tm_h2_a, fa);
     if (w->ff2)
-        return launch_k(ff_forward2_kernel<1>, grid, dim3(FF_THREADS), ff2_smem_bytes<1>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
+        return launch_k(ff_forward2_kernel<1, 8>, grid, dim3(64 + 32 * 8), ff2_smem_bytes<1>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
                         on.tm_w1_mn, tg.tm_w1_mn, on.tm_w2_mn, tg.tm_w2_mn, on.tm_w3p_mn, tg.tm_w3p_mn, w->tm_h1_a, w->tm_h2_a, fa);
     if (d.D == 128)
         return launch_k(ff_forward_kernel<2>, grid, dim3(FF_THREADS), ff_smem_bytes<2>(), st, pdl, bt.tm_x_a, bt.tm_x2_a,
