@@ -1676,16 +1676,32 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
                    const float *__restrict__ rew, const uint8_t *__restrict__ done, int B, int H2, int A, StepScalars sc,
                    const __nv_bfloat16 *__restrict__ h2, const uint32_t *__restrict__ m2bits /* [B][H2/32] or null */,
                    const __nv_bfloat16 *__restrict__ w3t /* [32][H2] */, float *__restrict__ td_out, __nv_bfloat16 *__restrict__ dqT, __nv_bfloat16 *__restrict__ dz2,
-                   float *__restrict__ b2_part /* [blocks][H2] */, float *__restrict__ row_part /* [blocks][A+1] */)
+                   float *__restrict__ b2_part /* [blocks][H2] */, float *__restrict__ row_part /* [blocks][A+1] */, int w3_smem)
 {
     TRACE_MARKS_DECL
     BlockTrace trace_(TR_TD, TRACE_MARKS_PTR);
-    extern __shared__ float sm[];            // [8 warps][H2] column sums, then [8][33] row partials
+    extern __shared__ float sm[];            // [8 warps][H2] column sums, [8][33] row partials, then (w3_smem) W3^T bf16 [A][H2]
     float *sRow = sm + 8 * H2;
+    const __nv_bfloat16 *sW3 = reinterpret_cast<const __nv_bfloat16 *>(sRow + 8 * 33);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rw0 = blockIdx.x * DZ_ROWS + warp * 4;      // this warp's four rows
+    // W3^T (the rows the actions pick, 1 KB each) does not come from the kernel this one is launched behind: it is
+    // staged in shared memory BEFORE the wait, which takes the dependent round trip action -> W3 row (0.9 us in the
+    // block trace) off the step's critical path.  cp.async, not a load: nothing the compiler could treat as invariant.
+    if (w3_smem == 1) {
+        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(sW3);
+        for (int i = threadIdx.x; i < (A * H2) >> 3; i += blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * (uint32_t)i), "l"(w3t + 8 * (size_t)i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     pdl_launch_dependents();
     pdl_wait();
+    if (w3_smem == 2) {      // (variant: the same copy issued behind the wait, with the first round of loads)
+        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(sW3);
+        for (int i = threadIdx.x; i < (A * H2) >> 3; i += blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * (uint32_t)i), "l"(w3t + 8 * (size_t)i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     if (threadIdx.x == 0) TRACE_MARK(0);
     // ---- every global load of the TD phase, and the first dZ2 chunk's, issued up front: ONE L2 round trip for
     // Q'(s') / Q(s) / action / reward / done, a second one only for the W3 rows picked by the actions (the first
@@ -1707,25 +1723,9 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
     const int nch = H2 >> 3;
     uint4 wv[4][DZ_MAXCH];
     uint32_t mk[4][DZ_MAXCH];      // masks of the chunk's 8 units: bit e = unit 2e masked, bit 4 + e = unit 2e + 1 masked
-    int a4[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) a4[k] = __shfl_sync(0xffffffffu, a, k);
-#ifdef GOLDQ_TRACE_BUILD
-    if (threadIdx.x == 0 && a4[0] >= 0) TRACE_MARK(5);
-#endif
     // (all loads first, decoding afterwards: decoded inside the load loop, every mask word's shift waited for its own
     // load -- eight serial L2 round trips, 2.8 us in the block trace)
-    auto load_chunks = [&](int c0) {
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-#pragma unroll
-            for (int u = 0; u < DZ_MAXCH; u++) {
-                const int c = c0 + lane + 32 * u;
-                const bool live = c < nch && rw0 + k < B;
-                // (W3^T is not written by the kernel this one follows, and only A of its rows are ever read: through L1,
-                // 18 KB per SM instead of 8 MB of L2 -> SM traffic; the address depends on a load behind the wait)
-                wv[k][u] = live ? __ldca(reinterpret_cast<const uint4 *>(w3t + (int64_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
-            }
+    auto load_masks = [&](int c0) {          // independent of the actions: issued with the first round of loads
         if (m2bits) {            // the forward's mask words (FFArgs::maskbits): 4 bytes instead of the 16 bytes of H2
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -1752,7 +1752,31 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
             }
         }
     };
-    load_chunks(0);
+    load_masks(0);
+    int a4[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) a4[k] = __shfl_sync(0xffffffffu, a, k);
+#ifdef GOLDQ_TRACE_BUILD
+    if (threadIdx.x == 0 && a4[0] >= 0) TRACE_MARK(5);
+#endif
+    if (w3_smem) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
+    auto load_w = [&](int c0) {              // the W3 rows picked by the actions
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int u = 0; u < DZ_MAXCH; u++) {
+                const int c = c0 + lane + 32 * u;
+                const bool live = c < nch && rw0 + k < B;
+                // (without the staged copy: through L1 -- only A rows are ever read, 18 KB per SM instead of 8 MB of
+                // L2 -> SM traffic; the address depends on a load behind the wait)
+                if (w3_smem) wv[k][u] = live ? *(reinterpret_cast<const uint4 *>(sW3 + (size_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
+                else wv[k][u] = live ? __ldca(reinterpret_cast<const uint4 *>(w3t + (int64_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
+            }
+    };
+    load_w(0);
     // ---- TD label: first-max over Q'(s') with ArgmaxF32's rules, lane = action, one row at a time; lane k keeps row k's.
     //   sequential rule (dense/op.go:42-62 over gonum floats.MaxIdx): f = v[0]; for i >= 1: the first NaN or +Inf ends
     //   the scan with f = v[i]; otherwise f = v[i] if v[i] > f.  In parallel: the lowest special lane if any, else a
@@ -1815,7 +1839,7 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
     if (threadIdx.x == 0) TRACE_MARK(2);
     // ---- dZ2 of the four rows + column sums ----------------------------------------------------------------
     for (int c0 = 0; c0 < nch; c0 += 32 * DZ_MAXCH) {
-        if (c0 > 0) load_chunks(c0);
+        if (c0 > 0) { load_masks(c0); load_w(c0); }
         if (m2bits) {
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -2821,8 +2845,15 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     // the sign bits of H1 / H2 (8 MB each)
     const bool bits = w->ff && w->ff2 && !(w->skip & 2) && getenv("GOLDQ_NO_MASKBITS") == nullptr;
     if (!(w->skip & 4))
-    WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), sizeof(float) * (8 * d.H2 + 8 * 33), st, pdl, w->q, w->qt, bt.ba, bt.br,
-                 bt.bdone, B, d.H2, d.A, s.sc, w->h2, bits ? w->m2bits : nullptr, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part));
+    {
+        size_t td_smem = sizeof(float) * (8 * d.H2 + 8 * 33);
+        const size_t w3_bytes = (size_t)d.A * d.H2 * 2;
+        static const int w3s = getenv("GOLDQ_TD_W3_SMEM") ? atoi(getenv("GOLDQ_TD_W3_SMEM")) : 0;
+        const int w3_smem = (td_smem + w3_bytes <= 48 * 1024) ? w3s : 0;      // (the default dynamic shared memory limit)
+        if (w3_smem) td_smem += w3_bytes;
+        WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), td_smem, st, pdl, w->q, w->qt, bt.ba, bt.br, bt.bdone, B, d.H2,
+                     d.A, s.sc, w->h2, bits ? w->m2bits : nullptr, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part, w3_smem));
+    }
     mark("TD + dZ2 + db2/db3 (K3)");
     launches += 1;
 
@@ -2929,18 +2960,22 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     const bool dp_launch = s.fuse_update && s.push;
     const UpdatePlan pl = make_update_plan(d, w->ns1, w->ns2, w->ns3, !dp_launch && !one_lane);
     const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
-    // (the update kernel follows cross-stream event waits: a full dependency, no PDL)
+    // The update kernel joins three branches: a full dependency.  (GOLDQ_UPDATE_PDL, experiment: launched programmatically
+    // behind dW1 -- the last branch to finish -- its blocks and then the next forward's CTAs become resident 5-10 us early
+    // and hold registers / shared memory next to dW1 and dW2; the step did not get shorter, 44.2 us either way.)
+    static const bool upd_pdl_on = getenv("GOLDQ_UPDATE_PDL") != nullptr;
+    const bool upd_pdl = pdl && upd_pdl_on;
+    float *nop = nullptr;
     if (w->skip & 256) {
     } else if (dp_launch)
-        wide_update_kernel<true, true><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
-                                                               s.step, shadow_ptrs(w, 0), s.loss_out, *s.push, s.epoch);
+        WCK(launch_k(wide_update_kernel<true, true>, dim3(blocks), dim3(128), 0, st, upd_pdl, d, o, ps, pl, s.sc.count, s.flat,
+                     s.theta_rw, s.m, s.v, s.adam, s.step, shadow_ptrs(w, 0), s.loss_out, *s.push, s.epoch));
     else if (s.fuse_update)
-        wide_update_kernel<true, false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, s.theta_rw, s.m, s.v, s.adam,
-                                                                s.step, shadow_ptrs(w, 0), s.loss_out, PeerSet{}, 0u);
+        WCK(launch_k(wide_update_kernel<true, false>, dim3(blocks), dim3(128), 0, st, upd_pdl, d, o, ps, pl, s.sc.count, s.flat,
+                     s.theta_rw, s.m, s.v, s.adam, s.step, shadow_ptrs(w, 0), s.loss_out, PeerSet{}, 0u));
     else
-        wide_update_kernel<false, false><<<blocks, 128, 0, st>>>(d, o, ps, pl, s.sc.count, s.flat, nullptr, nullptr, nullptr,
-                                                                 s.adam, s.step, shadow_ptrs(w, 0), nullptr, PeerSet{}, 0u);
-    WCK(cudaGetLastError());
+        WCK(launch_k(wide_update_kernel<false, false>, dim3(blocks), dim3(128), 0, st, upd_pdl, d, o, ps, pl, s.sc.count, s.flat,
+                     nop, nop, nop, s.adam, s.step, shadow_ptrs(w, 0), nop, PeerSet{}, 0u));
     mark("reduce + Adam + bf16 shadow (K5)");
     launches++;
     return launches;
