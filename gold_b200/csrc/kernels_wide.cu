@@ -57,7 +57,6 @@ enum { EPI_BIAS_RELU_BF16 = 0, EPI_BIAS_F32 = 1, EPI_MASK_BF16 = 2, EPI_F32_SLIC
 // single-use values do not need.
 template <typename T>
 __device__ __forceinline__ T ld_dep(const T *p) { return __ldcg(p); }
-__device__ __forceinline__ unsigned char ld_dep(const unsigned char *p) { return __ldcg(p); }
 
 // ---- block trace (diagnostic, GOLDQ_TRACE=1 at create; tools/trace_step.py) ---------------------------------
 // Thread 0 of every block of the step's kernels appends {kernel id, block, globaltimer at entry and exit} to a log:
@@ -1671,48 +1670,52 @@ wide_shadow_kernel(const float *__restrict__ theta, Dims d, Offsets o, ShadowPtr
 //   partials per block in a fixed order: db2 (column sums of the ROUNDED dZ2), db3 by action, loss
 constexpr int DZ_ROWS = 32;
 constexpr int DZ_MAXCH = 2;      // 16-byte chunks per lane and row: H2 <= 32 * 8 * DZ_MAXCH = 512 (more: chunk loop)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)   // two blocks per SM: all 256 blocks of the headline shape in one wave
 wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, const int32_t *__restrict__ act,
                    const float *__restrict__ rew, const uint8_t *__restrict__ done, int B, int H2, int A, StepScalars sc,
                    const __nv_bfloat16 *__restrict__ h2, const uint32_t *__restrict__ m2bits /* [B][H2/32] or null */,
                    const __nv_bfloat16 *__restrict__ w3t /* [32][H2] */, float *__restrict__ td_out, __nv_bfloat16 *__restrict__ dqT, __nv_bfloat16 *__restrict__ dz2,
-                   float *__restrict__ b2_part /* [blocks][H2] */, float *__restrict__ row_part /* [blocks][A+1] */, int w3_smem)
+                   float *__restrict__ b2_part /* [blocks][H2] */, float *__restrict__ row_part /* [blocks][A+1] */)
 {
     TRACE_MARKS_DECL
     BlockTrace trace_(TR_TD, TRACE_MARKS_PTR);
-    extern __shared__ float sm[];            // [8 warps][H2] column sums, [8][33] row partials, then (w3_smem) W3^T bf16 [A][H2]
+    extern __shared__ float sm[];            // [8 warps][H2] column sums, then [8][33] row partials
     float *sRow = sm + 8 * H2;
-    const __nv_bfloat16 *sW3 = reinterpret_cast<const __nv_bfloat16 *>(sRow + 8 * 33);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rw0 = blockIdx.x * DZ_ROWS + warp * 4;      // this warp's four rows
-    // W3^T (the rows the actions pick, 1 KB each) does not come from the kernel this one is launched behind: it is
-    // staged in shared memory BEFORE the wait, which takes the dependent round trip action -> W3 row (0.9 us in the
-    // block trace) off the step's critical path.  cp.async, not a load: nothing the compiler could treat as invariant.
-    if (w3_smem == 1) {
-        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(sW3);
-        for (int i = threadIdx.x; i < (A * H2) >> 3; i += blockDim.x)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * (uint32_t)i), "l"(w3t + 8 * (size_t)i) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
+    // ---- Ahead of the wait: what does NOT come from the forward this kernel is launched behind.  Actions, rewards and
+    // done flags were written by the gather (a full dependency of the forward, complete before its first CTA ran), W3^T by
+    // the previous update.  Loading them here -- and the W3 rows the actions pick, a dependent round trip -- leaves ONE L2
+    // round trip behind the wait (Q, Q', mask words).  These are plain cached loads issued in program order in front of an
+    // `asm volatile` with a memory clobber: nothing the compiler may move; tests/test_sass_invariants.py holds this kernel
+    // to exactly these early loads and to none of the invariant (.CONSTANT) kind.
     pdl_launch_dependents();
-    pdl_wait();
-    if (w3_smem == 2) {      // (variant: the same copy issued behind the wait, with the first round of loads)
-        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(sW3);
-        for (int i = threadIdx.x; i < (A * H2) >> 3; i += blockDim.x)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * (uint32_t)i), "l"(w3t + 8 * (size_t)i) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    if (threadIdx.x == 0) TRACE_MARK(0);
-    // ---- every global load of the TD phase, and the first dZ2 chunk's, issued up front: ONE L2 round trip for
-    // Q'(s') / Q(s) / action / reward / done, a second one only for the W3 rows picked by the actions (the first
-    // version went row -> action -> Q(s)[a] -> W3 row, three dependent round trips: 2.7 + 3.2 us in the block trace)
     int a = 0, dn = 0;
     float rwd = 0.f;
     if (lane < 4 && rw0 + lane < B) {
-        a = ld_dep(act + rw0 + lane);
-        rwd = ld_dep(rew + rw0 + lane);
-        dn = ld_dep(done + rw0 + lane);
+        a = __ldca(act + rw0 + lane);
+        rwd = __ldca(rew + rw0 + lane);
+        dn = __ldca(done + rw0 + lane);
     }
+    const int nch = H2 >> 3;
+    uint4 wv[4][DZ_MAXCH];
+    int a4[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) a4[k] = __shfl_sync(0xffffffffu, a, k);
+    auto load_w = [&](int c0) {              // the W3 rows picked by the actions (only A rows are ever read: through L1)
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int u = 0; u < DZ_MAXCH; u++) {
+                const int c = c0 + lane + 32 * u;
+                const bool live = c < nch && rw0 + k < B;
+                wv[k][u] = live ? __ldca(reinterpret_cast<const uint4 *>(w3t + (int64_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
+            }
+    };
+    load_w(0);
+    pdl_wait();
+    if (threadIdx.x == 0) TRACE_MARK(0);
+    // ---- behind the wait: Q'(s'), Q(s) and the mask words of the four rows, all issued before the first use
     float qtv[4], qv[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -1720,12 +1723,10 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
         qtv[k] = ok ? ld_dep(qt + (int64_t)(rw0 + k) * A + lane) : -INFINITY;
         qv[k] = ok ? ld_dep(q + (int64_t)(rw0 + k) * A + lane) : 0.f;
     }
-    const int nch = H2 >> 3;
-    uint4 wv[4][DZ_MAXCH];
     uint32_t mk[4][DZ_MAXCH];      // masks of the chunk's 8 units: bit e = unit 2e masked, bit 4 + e = unit 2e + 1 masked
     // (all loads first, decoding afterwards: decoded inside the load loop, every mask word's shift waited for its own
     // load -- eight serial L2 round trips, 2.8 us in the block trace)
-    auto load_masks = [&](int c0) {          // independent of the actions: issued with the first round of loads
+    auto load_masks = [&](int c0) {
         if (m2bits) {            // the forward's mask words (FFArgs::maskbits): 4 bytes instead of the 16 bytes of H2
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -1753,30 +1754,9 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
         }
     };
     load_masks(0);
-    int a4[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) a4[k] = __shfl_sync(0xffffffffu, a, k);
 #ifdef GOLDQ_TRACE_BUILD
     if (threadIdx.x == 0 && a4[0] >= 0) TRACE_MARK(5);
 #endif
-    if (w3_smem) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-    }
-    auto load_w = [&](int c0) {              // the W3 rows picked by the actions
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-#pragma unroll
-            for (int u = 0; u < DZ_MAXCH; u++) {
-                const int c = c0 + lane + 32 * u;
-                const bool live = c < nch && rw0 + k < B;
-                // (without the staged copy: through L1 -- only A rows are ever read, 18 KB per SM instead of 8 MB of
-                // L2 -> SM traffic; the address depends on a load behind the wait)
-                if (w3_smem) wv[k][u] = live ? *(reinterpret_cast<const uint4 *>(sW3 + (size_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
-                else wv[k][u] = live ? __ldca(reinterpret_cast<const uint4 *>(w3t + (int64_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
-            }
-    };
-    load_w(0);
     // ---- TD label: first-max over Q'(s') with ArgmaxF32's rules, lane = action, one row at a time; lane k keeps row k's.
     //   sequential rule (dense/op.go:42-62 over gonum floats.MaxIdx): f = v[0]; for i >= 1: the first NaN or +Inf ends
     //   the scan with f = v[i]; otherwise f = v[i] if v[i] > f.  In parallel: the lowest special lane if any, else a
@@ -2357,18 +2337,22 @@ WideState *wide_create(const Dims &d, int B, int sm_count, std::string &err)
     if (!load_encode(err)) return nullptr;
     {
         cudaError_t e = configure_all_gemms();
-        // (GOLDQ_CARVEOUT, experiment: the small kernels between the GEMMs ask for the GEMMs' shared-memory carve-out.  An SM
-        // re-partitions L1 / shared memory only when idle, so without it a dependent GEMM CTA (200 KB) cannot become resident
-        // next to the last blocks of a small predecessor and its prologue is not hidden.  Measured: the forward enters 0.7 us
-        // earlier, the single-GPU step is unchanged -- and the data-parallel step gets 3 us LONGER: the next forward's
-        // CTAs, resident early, take registers from the update grid, which must stay co-resident for its exchange.)
-        if (getenv("GOLDQ_CARVEOUT") != nullptr) {
-            const int mx = (int)cudaSharedmemCarveoutMaxShared;
+        // The small kernels INSIDE the step (TD/dZ2, gather) ask for the shared-memory carve-out of the GEMMs around them.
+        // An SM re-partitions L1 / shared memory only when it is idle: with the default carve-out the TD blocks that did not
+        // fit next to the forward's CTAs started a full wave late (block trace: TD ended 8.9 us after the forward instead of
+        // 6.0).  NOT the update kernel: with the same carve-out the next forward's CTAs become resident next to its last
+        // blocks and take registers from the data-parallel instantiation, whose grid must stay co-resident for the exchange
+        // (N=2: 56.9 vs 53.9 us/step).  GOLDQ_CARVEOUT=0: none; =2: the update kernels too.
+        const int cv = getenv("GOLDQ_CARVEOUT") ? atoi(getenv("GOLDQ_CARVEOUT")) : 1;
+        const int mx = (int)cudaSharedmemCarveoutMaxShared;
+        if (cv >= 1) {
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_td_dz2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        }
+        if (cv >= 2) {
             if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_update_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_update_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_update_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_td_dz2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(wide_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         }
         if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return nullptr; }
     }
@@ -2846,15 +2830,10 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     // the sign bits of H1 / H2 (8 MB each)
     const bool bits = w->ff && w->ff2 && !(w->skip & 2) && getenv("GOLDQ_NO_MASKBITS") == nullptr;
     if (!(w->skip & 4))
-    {
-        size_t td_smem = sizeof(float) * (8 * d.H2 + 8 * 33);
-        const size_t w3_bytes = (size_t)d.A * d.H2 * 2;
-        static const int w3s = getenv("GOLDQ_TD_W3_SMEM") ? atoi(getenv("GOLDQ_TD_W3_SMEM")) : 0;
-        const int w3_smem = (td_smem + w3_bytes <= 48 * 1024) ? w3s : 0;      // (the default dynamic shared memory limit)
-        if (w3_smem) td_smem += w3_bytes;
-        WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), td_smem, st, pdl, w->q, w->qt, bt.ba, bt.br, bt.bdone, B, d.H2,
-                     d.A, s.sc, w->h2, bits ? w->m2bits : nullptr, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part, w3_smem));
-    }
+    // (W3^T staged in shared memory ahead of the wait was tried first: block 4.8 -> 3.9 us, but 35 KB blocks made the step
+    // longer; loading the rows themselves ahead of the wait needs no shared memory)
+    WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), sizeof(float) * (8 * d.H2 + 8 * 33), st, pdl, w->q, w->qt, bt.ba, bt.br,
+                 bt.bdone, B, d.H2, d.A, s.sc, w->h2, bits ? w->m2bits : nullptr, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part));
     mark("TD + dZ2 + db2/db3 (K3)");
     launches += 1;
 

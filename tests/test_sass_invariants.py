@@ -45,6 +45,14 @@ def test_no_global_load_precedes_the_dependency_wait(kernels):
             continue
         checked += 1
         early = [x for x in ins[:waits[0]] if re.search(r"\b(LDG|LD)\.", x) and "LDGSTS" not in x]
+        if "wide_td_dz2_kernel" in name:
+            # The one deliberate exception: TD/dZ2 reads what the forward it is launched behind does NOT produce -- the
+            # batch's actions / rewards / done flags (3 loads; written by the gather, a full dependency of the forward)
+            # and the W3^T rows those actions pick (8 loads; written by the previous update) -- ahead of the wait.  They
+            # are ordinary cached loads (ld.global.ca), never the invariant kind the compiler may move.
+            assert len(early) == 11, (name, early)
+            assert all(".STRONG.SM" in x and "CONSTANT" not in x for x in early), (name, early)
+            continue
         assert not early, f"{name}: global loads in front of griddepcontrol.wait: {early[:4]}"
     assert checked >= 6, checked      # forward(s), pair GEMMs, GEMMs, gather, TD, column sums, update
 

@@ -91,6 +91,17 @@ if len(ups) >= 6:
                 print(f"  {nm:28s} {np.median(v):7.2f} {v.min():7.2f} {v.max():7.2f}")
         v = (t1[sel] - marks[sel, 0]) / 1e3
         print(f"  {'block exit':28s} {np.median(v):7.2f} {v.min():7.2f} {v.max():7.2f}")
+    # when the blocks of the critical chain start and end (deciles, us in the window): shows waves
+    for k in (3, 6, 8):
+        sel = np.where((kid == k) & (t1 > lo) & (t1 <= hi + 3000))[0]
+        if len(sel):
+            qs = [0, 0.1, 0.25, 0.5, 0.75, 0.9, 1.0]
+            print(f"\n{NAMES[k]}: block start quantiles (0, .1, .25, .5, .75, .9, 1) {np.round(np.quantile((t0[sel] - lo) / 1e3, qs), 2)}")
+            print(f"  block end quantiles {np.round(np.quantile((t1[sel] - lo) / 1e3, qs), 2)}")
+            v = marks[sel, 0]
+            v = v[v > 0]
+            if len(v):
+                print(f"  griddepcontrol.wait passed, quantiles {np.round(np.quantile((v - lo) / 1e3, qs), 2)}")
     # update kernel: duration by block (the block ranges depend on the lanes-per-group plan: report quantiles over all blocks
     # and the slowest tenth's block indices instead of guessing the ranges)
     blk = (rec[:, 2] >> np.uint64(32)).astype(np.int64)
