@@ -1940,7 +1940,8 @@ struct PartialSrc {
 //   C  warp per scalar of b3 and the loss.
 struct UpdatePlan {
     int nA;        // float4 groups in W1, W2, W3 (in parameter order)
-    int nB;        // float4 groups in b1, b2
+    int nB;        // float4 groups in b1, b2 (this launch's: gB0 .. gB0 + nB - 1)
+    int gB0;       // first bias group of this launch (0, or H1 / 4 when only b2 is updated)
     int nC;        // A + 1 scalars
     int blocksA, blocksB, blocksC;
     int lp[3];     // lanes per float4 group of W1 / W2 / W3 (1, 2 or 4): a range with many split-K slices gives each group
@@ -2190,8 +2191,8 @@ wide_update_kernel(Dims d, Offsets o, PartialSrc ps, UpdatePlan pl, float count,
         if (threadIdx.x == 0) TRACE_MARK(3);
     } else if ((int)blockIdx.x < pl.blocksA + pl.blocksB) {
         // ---- B: biases of the hidden layers, warp per float4 group -------------------
-        const int gidx = (blockIdx.x - pl.blocksA) * 4 + warp;
-        if (gidx >= pl.nB) return;
+        const int gidx = pl.gB0 + (blockIdx.x - pl.blocksA) * 4 + warp;
+        if (gidx >= pl.gB0 + pl.nB) return;
         const int nb1g = d.H1 >> 2;
         int i, n;
         const float *base;
@@ -2578,18 +2579,23 @@ int wide_apply_update(WideState *w, const float *flat, float *theta, float *m, f
 // up to four dependent rounds: the block trace showed the 32-slice groups of W1 and W3 finishing 5 us after the 10-slice
 // groups of W2 -- the tail of the whole step).  The data-parallel instantiation keeps one lane per group: its grid has
 // to stay co-resident (wide_p2p_resident).
-static UpdatePlan make_update_plan(const Dims &d, int n1 = 1, int n2 = 1, int n3 = 1, bool many_lanes = false)
+// part 0: every parameter in one launch.  The single-GPU step splits the update in two launches that join different
+// branches of the backward pass: part 1 = W1, b1 (behind dW1 and dX), part 2 = W2, b2, W3, b3 and the loss (behind dW2,
+// dW3 and TD/dZ2) -- a range with no blocks simply drops out of the kernel's block -> range arithmetic.
+static UpdatePlan make_update_plan(const Dims &d, int n1 = 1, int n2 = 1, int n3 = 1, bool many_lanes = false, int part = 0)
 {
     UpdatePlan pl;
     const int ng[3] = {(d.D * d.H1) >> 2, (d.H1 * d.H2) >> 2, (d.H2 * d.A) >> 2};
     const int ns[3] = {n1, n2, n3};
     pl.nA = ng[0] + ng[1] + ng[2];
-    pl.nB = (d.H1 + d.H2) >> 2;
-    pl.nC = d.A + 1;
+    pl.nB = (part == 1 ? d.H1 : (part == 2 ? d.H2 : d.H1 + d.H2)) >> 2;
+    pl.gB0 = part == 2 ? (d.H1 >> 2) : 0;
+    pl.nC = part == 1 ? 0 : d.A + 1;
     pl.blocksA = 0;
     for (int r = 0; r < 3; r++) {
         pl.lp[r] = !many_lanes ? 1 : (ns[r] > 16 ? 4 : (ns[r] > 10 ? 2 : 1));
-        pl.bA[r] = (ng[r] * pl.lp[r] + 127) / 128;
+        const bool in = part == 0 || (part == 1) == (r == 0);
+        pl.bA[r] = in ? (ng[r] * pl.lp[r] + 127) / 128 : 0;
         pl.blocksA += pl.bA[r];
     }
     pl.blocksB = (pl.nB + 3) / 4;
@@ -2903,7 +2909,9 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     mark(w->pair_dx ? "dX -> dZ1 + db1, CTA pairs (tcgen05 cta_group::2)" : "dX -> dZ1 (tcgen05)");
     if (!one_stream) {
         WCK(cudaEventRecord(w->ev_dx, st));
-        WCK(cudaStreamWaitEvent(s2, w->ev_dx, 0));
+        // (s2 continues with the db1 column sums of dZ1 -- or, with the pair dX that produces them itself, with nothing:
+        // then dW3's branch does not have to wait for dX)
+        if (!w->pair_dx || dx_first) WCK(cudaStreamWaitEvent(s2, w->ev_dx, 0));
     }
     if (dx_first) {
         if (!one_stream) WCK(cudaStreamWaitEvent(s1, w->ev_dx, 0));      // (s2 waits for ev_dx above)
@@ -2928,34 +2936,49 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     if (!(w->skip & 128))
     WCK((launch_gemm<MODE_MM, 128, EPI_F32_SLICE>(bt.tm_x_mm, w->tm_dz1_mm, g, w->ns1, st, nullptr, nullptr, pdl && !dw1_nopdl)));
     mark("dW1 split-K (tcgen05)");
-    if (!one_stream) {
-        WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
-        WCK(cudaStreamWaitEvent(st, w->ev_s2, 0));
-    }
     launches += 4;
 
     PartialSrc ps{w->w1_slices, w->ns1, w->b1_part, w->nb1, w->w2_slices, w->ns2,
                   w->b2_part,   w->nb2, w->w3_slices, w->ns3, w->row_part, w->nrow};
     static const bool one_lane = getenv("GOLDQ_UPDATE_ONE_LANE") != nullptr;      // diagnostic: round-1 decomposition
+    static const bool one_update = getenv("GOLDQ_UPDATE_ONE") != nullptr;         // diagnostic: the update as one launch
     const bool dp_launch = s.fuse_update && s.push;
-    const UpdatePlan pl = make_update_plan(d, w->ns1, w->ns2, w->ns3, !dp_launch && !one_lane);
-    const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
-    // The update kernel joins three branches: a full dependency.  (GOLDQ_UPDATE_PDL, experiment: launched programmatically
-    // behind dW1 -- the last branch to finish -- its blocks and then the next forward's CTAs become resident 5-10 us early
-    // and hold registers / shared memory next to dW1 and dW2; the step did not get shorter, 44.2 us either way.)
-    static const bool upd_pdl_on = getenv("GOLDQ_UPDATE_PDL") != nullptr;
-    const bool upd_pdl = pdl && upd_pdl_on;
     float *nop = nullptr;
-    if (w->skip & 256) {
-    } else if (dp_launch)
-        WCK(launch_k(wide_update_kernel<true, true>, dim3(blocks), dim3(128), 0, st, upd_pdl, d, o, ps, pl, s.sc.count, s.flat,
-                     s.theta_rw, s.m, s.v, s.adam, s.step, shadow_ptrs(w, 0), s.loss_out, *s.push, s.epoch));
-    else if (s.fuse_update)
-        WCK(launch_k(wide_update_kernel<true, false>, dim3(blocks), dim3(128), 0, st, upd_pdl, d, o, ps, pl, s.sc.count, s.flat,
-                     s.theta_rw, s.m, s.v, s.adam, s.step, shadow_ptrs(w, 0), s.loss_out, PeerSet{}, 0u));
-    else
-        WCK(launch_k(wide_update_kernel<false, false>, dim3(blocks), dim3(128), 0, st, upd_pdl, d, o, ps, pl, s.sc.count, s.flat,
-                     nop, nop, nop, s.adam, s.step, shadow_ptrs(w, 0), nop, PeerSet{}, 0u));
+    // The update as TWO launches on the single-GPU step, each joining only the branches it needs:
+    //   part 2 (W2, b2, W3, b3, loss) on dW2's branch, behind dW2, dW3 and TD/dZ2 -- next to dW1;
+    //   part 1 (W1, b1) on the main chain behind dW1: 66 k of the 338 k parameters, 4 of the 18 MB of split-K slices.
+    // As one launch behind the join of all three branches it was the last 6 us of the step (L2 bandwidth: 18.5 MB).
+    // The data-parallel instantiation stays one launch (its exchange pairs blocks of equal index across ranks).
+    const bool split = !dp_launch && !one_stream && !one_update && !(w->skip & 256);
+    auto launch_update = [&](int part, cudaStream_t us, bool upd_pdl = false) -> cudaError_t {
+        const UpdatePlan pl = make_update_plan(d, w->ns1, w->ns2, w->ns3, !dp_launch && !one_lane, part);
+        const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
+        if (dp_launch)
+            return launch_k(wide_update_kernel<true, true>, dim3(blocks), dim3(128), 0, us, upd_pdl, d, o, ps, pl, s.sc.count, s.flat,
+                            s.theta_rw, s.m, s.v, s.adam, s.step, shadow_ptrs(w, 0), s.loss_out, *s.push, s.epoch);
+        if (s.fuse_update)
+            return launch_k(wide_update_kernel<true, false>, dim3(blocks), dim3(128), 0, us, upd_pdl, d, o, ps, pl, s.sc.count, s.flat,
+                            s.theta_rw, s.m, s.v, s.adam, s.step, shadow_ptrs(w, 0), s.loss_out, PeerSet{}, 0u);
+        return launch_k(wide_update_kernel<false, false>, dim3(blocks), dim3(128), 0, us, upd_pdl, d, o, ps, pl, s.sc.count, s.flat,
+                        nop, nop, nop, s.adam, s.step, shadow_ptrs(w, 0), nop, PeerSet{}, 0u);
+    };
+    if (split) {
+        WCK(cudaStreamWaitEvent(s1, w->ev_s2, 0));          // dW3 (and, without the pair dX, the db1 column sums)
+        // (GOLDQ_UPDATE_PDL, experiment: 1 = part 1 launched programmatically behind dW1, 2 = part 2 behind dW2 as well)
+        static const int upd_pdl = getenv("GOLDQ_UPDATE_PDL") ? atoi(getenv("GOLDQ_UPDATE_PDL")) : 0;
+        WCK(launch_update(2, s1, pdl && upd_pdl >= 2));
+        WCK(cudaEventRecord(w->ev_s1, s1));                  // (re-recorded: the branch now ends with its half of the update)
+        if (!w->pair_dx) WCK(cudaStreamWaitEvent(st, w->ev_s2, 0));
+        WCK(launch_update(1, st, pdl && upd_pdl >= 1));
+        WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
+        launches++;
+    } else {
+        if (!one_stream) {
+            WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
+            WCK(cudaStreamWaitEvent(st, w->ev_s2, 0));
+        }
+        if (!(w->skip & 256)) WCK(launch_update(0, st));
+    }
     mark("reduce + Adam + bf16 shadow (K5)");
     launches++;
     return launches;
