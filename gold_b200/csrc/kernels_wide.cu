@@ -126,6 +126,7 @@ struct GemmArgs {
     int ldo;                                // row pitch of the output in elements
     int n_store;                            // columns actually stored (<= N tile coverage)
     long long slice_stride;
+    int late_trigger;                       // release the dependent grid from the epilogue instead of the prologue
 };
 
 // CM > 1: clusters of CM CTAs along M (blockIdx.y) share the B tile — each CTA loads 1/CM of
@@ -183,7 +184,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_slot, TMEM_COLS);
-    pdl_launch_dependents();     // the next kernel may begin its own prologue
+    if (!g.late_trigger) pdl_launch_dependents();     // the next kernel may begin its own prologue
     tc_fence_before();
     if (CM > 1) cluster_sync();  // peers' barriers are initialised before anything is multicast
     else __syncthreads();
@@ -269,6 +270,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_wait(&tmem_full_bar, 0);
             tc_fence_after();
         }
+        // (late trigger: a dependent released from the prologue is resident for this kernel's whole main loop and holds
+        // registers next to the GEMM CTAs that have not started yet)
+        if (g.late_trigger && threadIdx.x == 64) pdl_launch_dependents();
         if (threadIdx.x == 64) TRACE_MARK(3);
         // fp32 split-K slices of full tiles leave through shared memory: the tile is staged in the (idle) operand ring
         // with the 16-byte chunks of a row XOR-swizzled by the row, then every warp writes whole 512-byte rows.  (Stored
@@ -2835,6 +2839,9 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     // the pair forward leaves the online network's Rectify masks as bit words: the backward pass reads those instead of
     // the sign bits of H1 / H2 (8 MB each)
     const bool bits = w->ff && w->ff2 && !(w->skip & 2) && getenv("GOLDQ_NO_MASKBITS") == nullptr;
+    // (Tried: dW2 / dW3 as PROGRAMMATIC dependents of TD/dZ2 across streams, through an event recorded by TD's launch
+    // (cudaLaunchAttributeProgrammaticEvent, triggerAtBlockStart) -- it captures, but the step went from 42.2 to 49.6 us.)
+    static const bool dx_first = getenv("GOLDQ_DX_FIRST") != nullptr;
     if (!(w->skip & 4))
     // (W3^T staged in shared memory ahead of the wait was tried first: block 4.8 -> 3.9 us, but 35 KB blocks made the step
     // longer; loading the rows themselves ahead of the wait needs no shared memory)
@@ -2845,12 +2852,16 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
 
     // backward: three independent chains after dZ2 —  s1: dW2 | s2: dW3, db1 | st: dX -> dW1
     // (GOLDQ_DX_FIRST, experiment: dW2 and dW3 start when dX is done instead of next to it)
-    static const bool dx_first = getenv("GOLDQ_DX_FIRST") != nullptr;
     if (!one_stream && !dx_first) {
         WCK(cudaEventRecord(w->ev_dz2, st));
         WCK(cudaStreamWaitEvent(s1, w->ev_dz2, 0));
         WCK(cudaStreamWaitEvent(s2, w->ev_dz2, 0));
     }
+    // GOLDQ_UPDATE_PDL: 0 = both parts of the update are plain launches (2 us behind the GEMM they follow), 1 = part 1 is
+    // launched programmatically behind dW1, 2 (default) = part 2 behind dW2 as well.  dW1 / dW2 then release their
+    // dependent from the EPILOGUE: released from the prologue, the update's blocks sat on the SMs for the whole GEMM and
+    // the step did not get shorter (42.8 vs 42.6 us); released late, 42.1.
+    static const int upd_pdl_mode = getenv("GOLDQ_UPDATE_PDL") ? atoi(getenv("GOLDQ_UPDATE_PDL")) : 2;
     auto side_gemms = [&]() -> int {
         // dW3 = H2^T dQ : M = H2, N = 32 (A stored), K = B ; A MN-major (h2 as stored), B = dQ^T K-major
         g = GemmArgs{};
@@ -2865,6 +2876,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
         g.trace_id = TR_DW2;
         g.M = d.H1; g.N = d.H2; g.K = B; g.k_per_split = w->kps2;
         g.out_f32 = w->w2_slices; g.ldo = d.H2; g.n_store = d.H2; g.slice_stride = (long long)d.H1 * d.H2;
+        g.late_trigger = upd_pdl_mode >= 2 ? 1 : 0;
         if (w->skip & 16) {
         } else if (w->pair_dw2) {
             PairGemmArgs pg{};
@@ -2930,6 +2942,7 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     g.trace_id = TR_DW1;
     g.M = d.D; g.N = d.H1; g.K = B; g.k_per_split = w->kps1;
     g.out_f32 = w->w1_slices; g.ldo = d.H1; g.n_store = d.H1; g.slice_stride = (long long)d.D * d.H1;
+    g.late_trigger = upd_pdl_mode >= 1 ? 1 : 0;
     // (GOLDQ_DW1_NOPDL, experiment: launched programmatically, dW1's CTAs become resident as soon as dX's CTAs have
     // started and then hold their shared memory idle until dX is done, while dW2's CTAs wait for a slot)
     static const bool dw1_nopdl = getenv("GOLDQ_DW1_NOPDL") != nullptr;
@@ -2964,12 +2977,10 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     };
     if (split) {
         WCK(cudaStreamWaitEvent(s1, w->ev_s2, 0));          // dW3 (and, without the pair dX, the db1 column sums)
-        // (GOLDQ_UPDATE_PDL, experiment: 1 = part 1 launched programmatically behind dW1, 2 = part 2 behind dW2 as well)
-        static const int upd_pdl = getenv("GOLDQ_UPDATE_PDL") ? atoi(getenv("GOLDQ_UPDATE_PDL")) : 0;
-        WCK(launch_update(2, s1, pdl && upd_pdl >= 2));
+        WCK(launch_update(2, s1, pdl && upd_pdl_mode >= 2));
         WCK(cudaEventRecord(w->ev_s1, s1));                  // (re-recorded: the branch now ends with its half of the update)
         if (!w->pair_dx) WCK(cudaStreamWaitEvent(st, w->ev_s2, 0));
-        WCK(launch_update(1, st, pdl && upd_pdl >= 1));
+        WCK(launch_update(1, st, pdl && upd_pdl_mode >= 1));
         WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
         launches++;
     } else {
