@@ -1679,7 +1679,7 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
                    const float *__restrict__ rew, const uint8_t *__restrict__ done, int B, int H2, int A, StepScalars sc,
                    const __nv_bfloat16 *__restrict__ h2, const uint32_t *__restrict__ m2bits /* [B][H2/32] or null */,
                    const __nv_bfloat16 *__restrict__ w3t /* [32][H2] */, float *__restrict__ td_out, __nv_bfloat16 *__restrict__ dqT, __nv_bfloat16 *__restrict__ dz2,
-                   float *__restrict__ b2_part /* [blocks][H2] */, float *__restrict__ row_part /* [blocks][A+1] */)
+                   float *__restrict__ b2_part /* [blocks][H2] */, float *__restrict__ row_part /* [blocks][A+1] */, int early_ok)
 {
     TRACE_MARKS_DECL
     BlockTrace trace_(TR_TD, TRACE_MARKS_PTR);
@@ -1693,19 +1693,26 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
     // round trip behind the wait (Q, Q', mask words).  These are plain cached loads issued in program order in front of an
     // `asm volatile` with a memory clobber: nothing the compiler may move; tests/test_sass_invariants.py holds this kernel
     // to exactly these early loads and to none of the invariant (.CONSTANT) kind.
+    // early_ok = the host's promise that the gather HAS completed when this grid starts: true behind the fused forward,
+    // which releases its dependent only after its own wait (on the gather, or on a step whose batch was prefetched).  The
+    // per-layer GEMM forward releases dependents from its prologue, down the whole chain: there this kernel can start
+    // while the gather still runs, and loads everything behind the wait.
     pdl_launch_dependents();
     int a = 0, dn = 0;
     float rwd = 0.f;
-    if (lane < 4 && rw0 + lane < B) {
-        a = __ldca(act + rw0 + lane);
-        rwd = __ldca(rew + rw0 + lane);
-        dn = __ldca(done + rw0 + lane);
-    }
     const int nch = H2 >> 3;
     uint4 wv[4][DZ_MAXCH];
     int a4[4];
+    auto load_batch = [&]() {
+        if (lane < 4 && rw0 + lane < B) {
+            a = __ldca(act + rw0 + lane);
+            rwd = __ldca(rew + rw0 + lane);
+            dn = __ldca(done + rw0 + lane);
+        }
 #pragma unroll
-    for (int k = 0; k < 4; k++) a4[k] = __shfl_sync(0xffffffffu, a, k);
+        for (int k = 0; k < 4; k++) a4[k] = __shfl_sync(0xffffffffu, a, k);
+    };
+    if (early_ok) load_batch();
     auto load_w = [&](int c0) {              // the W3 rows picked by the actions (only A rows are ever read: through L1)
 #pragma unroll
         for (int k = 0; k < 4; k++)
@@ -1716,9 +1723,10 @@ wide_td_dz2_kernel(const float *__restrict__ q, const float *__restrict__ qt, co
                 wv[k][u] = live ? __ldca(reinterpret_cast<const uint4 *>(w3t + (int64_t)a4[k] * H2) + c) : make_uint4(0, 0, 0, 0);
             }
     };
-    load_w(0);
+    if (early_ok) load_w(0);
     pdl_wait();
     if (threadIdx.x == 0) TRACE_MARK(0);
+    if (!early_ok) { load_batch(); load_w(0); }
     // ---- behind the wait: Q'(s'), Q(s) and the mask words of the four rows, all issued before the first use
     float qtv[4], qv[4];
 #pragma unroll
@@ -2839,6 +2847,10 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     // the pair forward leaves the online network's Rectify masks as bit words: the backward pass reads those instead of
     // the sign bits of H1 / H2 (8 MB each)
     const bool bits = w->ff && w->ff2 && !(w->skip & 2) && getenv("GOLDQ_NO_MASKBITS") == nullptr;
+    // TD/dZ2 may read the batch's actions / rewards / done flags ahead of its wait only behind the fused forward with its
+    // late trigger (see the kernel)
+    static const bool early_trig = getenv("GOLDQ_EARLY_TRIGGER") != nullptr, td_noearly = getenv("GOLDQ_TD_NO_EARLY") != nullptr;
+    const bool td_early = w->ff && w->ff2 && !(w->skip & 2) && !early_trig && !td_noearly;     // (ff_forward2_kernel only)
     // (Tried: dW2 / dW3 as PROGRAMMATIC dependents of TD/dZ2 across streams, through an event recorded by TD's launch
     // (cudaLaunchAttributeProgrammaticEvent, triggerAtBlockStart) -- it captures, but the step went from 42.2 to 49.6 us.)
     static const bool dx_first = getenv("GOLDQ_DX_FIRST") != nullptr;
@@ -2846,7 +2858,8 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     // (W3^T staged in shared memory ahead of the wait was tried first: block 4.8 -> 3.9 us, but 35 KB blocks made the step
     // longer; loading the rows themselves ahead of the wait needs no shared memory)
     WCK(launch_k(wide_td_dz2_kernel, dim3(w->nb2), dim3(256), sizeof(float) * (8 * d.H2 + 8 * 33), st, pdl, w->q, w->qt, bt.ba, bt.br,
-                 bt.bdone, B, d.H2, d.A, s.sc, w->h2, bits ? w->m2bits : nullptr, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part));
+                 bt.bdone, B, d.H2, d.A, s.sc, w->h2, bits ? w->m2bits : nullptr, on.w3t, w->td, w->dqT, w->dz2, w->b2_part, w->row_part,
+                 td_early ? 1 : 0));
     mark("TD + dZ2 + db2/db3 (K3)");
     launches += 1;
 
