@@ -590,10 +590,11 @@ def run_own(args):
 
 _REAL_STDOUT = None
 
-# ff_forward_kernel, wide config, B=8192: 5.739 MB read + 0.024 MB written per launch
+# ff_forward2_kernel<2, 8>, wide config, B=8192: dram__bytes_read.sum 5.812736 MB + dram__bytes_write.sum 0 per launch
+# (one `ncu --set full` capture of the end-of-round build; its activations and mask words stay in the 126 MB L2)
 NCU_TRAFFIC = {("fused forward L1-L3 online+target, CTA pairs (tcgen05 cta_group::2)", (128, 512, 512, 18), 8192):
-               5805568 + 8448}
-NCU_TRAFFIC_SOURCE = "profiles/r02_ff_forward2_ncu_full_raw.csv"
+               5812736}
+NCU_TRAFFIC_SOURCE = "profiles/r02_step_kernels_ncu_full_raw.csv"
 
 
 def emit(line):
