@@ -2975,7 +2975,11 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     //   part 1 (W1, b1) on the main chain behind dW1: 66 k of the 338 k parameters, 4 of the 18 MB of split-K slices.
     // As one launch behind the join of all three branches it was the last 6 us of the step (L2 bandwidth: 18.5 MB).
     // The data-parallel instantiation stays one launch (its exchange pairs blocks of equal index across ranks).
-    const bool split = !dp_launch && !one_stream && !one_update && !(w->skip & 256);
+    // (GOLDQ_DP_SPLIT: the data-parallel step split the same way -- blocks of equal index still pair across ranks, launch by
+    // launch, and the two grids together are the one grid whose co-residency wide_p2p_resident checks; 80 % of the
+    // gradient is then exchanged under dW1)
+    static const bool dp_split = getenv("GOLDQ_DP_SPLIT") != nullptr;
+    const bool split = (!dp_launch || dp_split) && !one_stream && !one_update && !(w->skip & 256);
     auto launch_update = [&](int part, cudaStream_t us, bool upd_pdl = false) -> cudaError_t {
         const UpdatePlan pl = make_update_plan(d, w->ns1, w->ns2, w->ns3, !dp_launch && !one_lane, part);
         const int blocks = pl.blocksA + pl.blocksB + pl.blocksC;
@@ -2990,10 +2994,10 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     };
     if (split) {
         WCK(cudaStreamWaitEvent(s1, w->ev_s2, 0));          // dW3 (and, without the pair dX, the db1 column sums)
-        WCK(launch_update(2, s1, pdl && upd_pdl_mode >= 2));
+        WCK(launch_update(2, s1, pdl && upd_pdl_mode >= 2 && !dp_launch));
         WCK(cudaEventRecord(w->ev_s1, s1));                  // (re-recorded: the branch now ends with its half of the update)
         if (!w->pair_dx) WCK(cudaStreamWaitEvent(st, w->ev_s2, 0));
-        WCK(launch_update(1, st, pdl && upd_pdl_mode >= 1));
+        WCK(launch_update(1, st, pdl && upd_pdl_mode >= 1 && !dp_launch));
         WCK(cudaStreamWaitEvent(st, w->ev_s1, 0));
         launches++;
     } else {
