@@ -269,3 +269,48 @@ def test_wide_free_running_loss_tracks_oracle():
             h.sync_target(); o.sync_target()
     np.testing.assert_allclose(lg, lo, rtol=3e-2)
     h.close()
+
+
+_VARIANT_SNIPPET = r"""
+import hashlib, sys
+import numpy as np
+from gold_b200 import _capi as G, synth
+dims, B, N = synth.WIDE, 8192, 1 << 15
+h = G.Handle(obs_dim=dims[0], hidden1=dims[1], hidden2=dims[2], n_actions=dims[3], batch_size=B, replay_capacity=N,
+             precision=G.PREC_BF16)
+h.set_params(G.NET_ONLINE, synth.glorot_params(dims, 1)); h.set_params(G.NET_TARGET, synth.glorot_params(dims, 2))
+h.replay_push(*synth.replay(dims, N))
+h.learn_many(37, 4242)                       # graphs of 32 + 4 + 1 steps
+for i in range(3):
+    h.learn(None, 9000 + i)                  # one-step graphs
+idx = synth.sample_indices(N, B, 5)
+h.learn(idx)                                 # host indices: the gather runs inline, in front of the forward
+m, v, it = h.get_adam_state()
+d = hashlib.sha256()
+for x in (h.get_params(G.NET_ONLINE), m, v, h.last_loss()):
+    d.update(np.ascontiguousarray(x).tobytes())
+print("DIGEST", d.hexdigest(), it)
+h.close()
+"""
+
+
+def test_step_variants_are_bit_identical():
+    """The switches that only change WHEN and in how many launches the step's work happens (update in one or two launches,
+    plain or programmatic; TD/dZ2's loads ahead of or behind its wait; batch tile ahead of or behind the forward's wait;
+    shared-memory carve-out) must not change a bit of the result at the headline shape: what differs is scheduling, so a
+    difference is a race.  (The switches are read once per process: one subprocess per variant.)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for name, env in [("default", {}), ("one update launch", {"GOLDQ_UPDATE_ONE": "1"}), ("plain update launches", {"GOLDQ_UPDATE_PDL": "0"}),
+                      ("TD loads behind the wait", {"GOLDQ_TD_NO_EARLY": "1"}), ("batch tile behind the wait", {"GOLDQ_NO_XPREFETCH": "1"}),
+                      ("no carve-out", {"GOLDQ_CARVEOUT": "0"}), ("no programmatic launches", {"GOLDQ_NO_PDL": "1"})]:
+        e = dict(os.environ); e.update(env); e["PYTHONPATH"] = root + os.pathsep + e.get("PYTHONPATH", "")
+        out = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET], env=e, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, (name, out.stderr[-2000:])
+        line = [x for x in out.stdout.splitlines() if x.startswith("DIGEST")]
+        assert line, (name, out.stdout[-500:], out.stderr[-500:])
+        digests[name] = line[0]
+    assert len(set(digests.values())) == 1, digests
