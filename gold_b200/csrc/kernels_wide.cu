@@ -2994,6 +2994,9 @@ int wide_step(WideState *w, const WideStep &s, cudaStream_t st, std::string &err
     };
     if (split) {
         WCK(cudaStreamWaitEvent(s1, w->ev_s2, 0));          // dW3 (and, without the pair dX, the db1 column sums)
+        // ... and dX: part 2 rewrites the bf16 shadow of W2, which dX reads as its B operand.  (dW2 normally ends 6 us after
+        // dX, so the wait costs nothing -- without it the result depended on that timing: the variants test caught it.)
+        WCK(cudaStreamWaitEvent(s1, w->ev_dx, 0));
         WCK(launch_update(2, s1, pdl && upd_pdl_mode >= 2 && !dp_launch));
         WCK(cudaEventRecord(w->ev_s1, s1));                  // (re-recorded: the branch now ends with its half of the update)
         if (!w->pair_dx) WCK(cudaStreamWaitEvent(st, w->ev_s2, 0));
